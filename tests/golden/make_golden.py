@@ -1,0 +1,316 @@
+"""Generate the golden fixtures in this directory by running the UNMODIFIED reference.
+
+Run in the build container only (it imports /root/reference, which does not exist on the GPU box):
+
+    python tests/golden/make_golden.py
+
+Each fixture is a flat .npz: seeded inputs, the reference's initial state (after construction /
+``initialize``), and the reference's outputs (per-iteration ELBO, responsibilities or their
+argmax, and the posterior state).  State keys follow ``oracle.vbem_oracle.flatten_state`` naming
+(``dist.mu``, ``dist.invU.invU`` ...), so the same file feeds the oracle tests (CPU) and the CUDA
+parity tests (GPU).  The reference has no golden vectors of its own; these
+files are what pins the oracle.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+REF = os.environ.get("PYVBMP_REFERENCE", "/root/reference")
+sys.path.insert(0, REF)
+import dists  # noqa: E402
+import transforms  # noqa: E402
+import models  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+torch.set_num_threads(8)
+
+
+def T(x):
+    return x.detach().clone().contiguous().numpy() if isinstance(x, torch.Tensor) else np.asarray(x)
+
+
+def wishart_state(w, pre):
+    return {pre + k: T(getattr(w, k)) for k in ("invU_0", "nu_0", "logdet_invU_0", "invU", "U", "nu", "logdet_invU")}
+
+
+def niw_state(d, pre):
+    out = {pre + k: T(getattr(d, k)) for k in ("lambda_mu_0", "lambda_mu", "mu_0", "mu")}
+    out.update(wishart_state(d.invU, pre + "invU."))
+    return out
+
+
+def mnw_state(d, pre):
+    out = {pre + k: T(getattr(d, k)) for k in ("mu_0", "mu", "invV_0", "invV", "V", "logdetinvV", "logdetinvV_0")}
+    out.update(wishart_state(d.invU, pre + "invU."))
+    return out
+
+
+def dir_state(d, pre):
+    return {pre + "alpha_0": T(d.alpha_0), pre + "alpha": T(d.alpha)}
+
+
+def tagged(state, tag):
+    return {tag + "/" + k: v for k, v in state.items()}
+
+
+def save(name, **arrs):
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **arrs)
+    print(f"{name}: {os.path.getsize(path) / 1024:.1f} KiB, {len(arrs)} arrays")
+
+
+def gmm_state(m):
+    s = niw_state(m.dist, "dist.")
+    s.update(dir_state(m.pi, "pi."))
+    return s
+
+
+def two_moons(n_per, seed):
+    """examples/two_moons.py:4-21 data recipe."""
+    g = torch.Generator().manual_seed(seed)
+    x = torch.linspace(-np.pi / 2, np.pi / 2, n_per)
+    a = torch.stack([torch.sin(x), torch.cos(x) - 0.25], -1)
+    b = torch.stack([torch.sin(x) + 1.0, -torch.cos(x) + 0.25], -1)
+    X = torch.cat([a, b], 0)
+    X = X + 0.05 * torch.randn(X.shape, generator=g)
+    return X / X.std()
+
+
+def run_gmm(name, X, nc, iters, lr=1.0, seed=0, keep_p=True):
+    torch.manual_seed(seed)
+    m = models.GaussianMixtureModel(nc, X.shape[-1])
+    m.initialize(X)
+    out = {"X": T(X), "nc": nc, "iters": iters, "lr": lr}
+    out.update(tagged(gmm_state(m), "init"))
+    elbo = []
+    for i in range(iters):
+        m.update(X, 1, lr)
+        elbo.append(float(m.ELBO_last))
+        if i == 0:
+            out.update(tagged(gmm_state(m), "iter1"))
+            out["iter1/logZ"] = T(m.logZ)
+            out["iter1/NA"] = T(m.NA)
+            out["iter1/KL"] = T(m.KLqprior())
+            if keep_p:
+                out["iter1/p"] = T(m.p)
+    out.update(tagged(gmm_state(m), "final"))
+    out["final/logZ"] = T(m.logZ)
+    out["final/NA"] = T(m.NA)
+    out["final/assignment"] = T(m.assignment()).astype(np.int32)
+    if keep_p:
+        out["final/p"] = T(m.p)
+    # one more E-step on the final parameters: logits straight from dist.Elog_like
+    out["final/Elog_like"] = T(m.Elog_like(X)) if keep_p else T(m.Elog_like(X[:256]))
+    out["final/KL"] = T(m.KLqprior())
+    out["ELBO"] = np.asarray(elbo, dtype=np.float64)
+    save(name, **out)
+
+
+def gen_gmm():
+    g = torch.Generator().manual_seed(11)
+    # tests/test_dists.py:202-220 recipe: 6 blobs in 2-d, N=400
+    mu = 4 * torch.randn(6, 2, generator=g)
+    z = torch.randint(6, (400,), generator=g)
+    X = mu[z] + 0.6 * torch.randn(400, 2, generator=g)
+    run_gmm("gmm_d2_k6", X, 6, 8, seed=1)
+    # config 1: two-moons, N=10k, d=2, K=20 (p not stored: 10k x 20)
+    run_gmm("gmm_moons_k20", two_moons(5000, 5), 20, 20, seed=0, keep_p=False)
+    # mid-size full covariance with lr<1
+    A = torch.randn(5, 16, 16, generator=g) / 4 + torch.eye(16)
+    mu = 2.0 * torch.randn(5, 16, generator=g)
+    z = torch.randint(5, (768,), generator=g)
+    X = mu[z] + torch.einsum("nij,nj->ni", A[z], torch.randn(768, 16, generator=g))
+    run_gmm("gmm_d16_k8_lr05", X, 8, 4, lr=0.5, seed=2)
+    # config-2 shaped slice (overlapping clusters variant): d=64, K=32 keeps the file small
+    mu = 0.3 * torch.randn(32, 64, generator=g)
+    z = torch.randint(32, (1024,), generator=g)
+    X = mu[z] + torch.randn(1024, 64, generator=g)
+    run_gmm("gmm_d64_k32_overlap", X, 32, 3, seed=3, keep_p=True)
+
+
+def gen_niw_variants():
+    g = torch.Generator().manual_seed(21)
+    # raw_update with beta forgetting and lr<1, p given  (NormalInverseWishart.py:49-86)
+    torch.manual_seed(4)
+    d = dists.NormalInverseWishart(event_shape=(3,), batch_shape=(4,), scale=0.7)
+    out = tagged(niw_state(d, ""), "init")
+    for i in range(3):
+        X = torch.randn(50, 1, 3, generator=g) + i
+        p = torch.rand(50, 4, generator=g)
+        d.raw_update(X, p, lr=0.6, beta=0.9)
+        out[f"X{i}"], out[f"p{i}"] = T(X), T(p)
+        out.update(tagged(niw_state(d, ""), f"step{i}"))
+        out[f"step{i}/SExx"], out[f"step{i}/SEx"], out[f"step{i}/N"] = T(d.SExx), T(d.SEx), T(d.N)
+    out["final/KL"] = T(d.KLqprior())
+    out["final/Elog_like"] = T(d.Elog_like(X))
+    save("niw_beta_lr", **out)
+
+    # fixed_precision + p=None
+    torch.manual_seed(5)
+    d = dists.NormalInverseWishart(event_shape=(3,), batch_shape=(2,), fixed_precision=True)
+    out = tagged(niw_state(d, ""), "init")
+    X = torch.randn(40, 2, 3, generator=g)
+    d.raw_update(X, None, lr=1.0, beta=None)
+    out["X"] = T(X)
+    out.update(tagged(niw_state(d, ""), "final"))
+    out["final/KL"] = T(d.KLqprior())
+    save("niw_fixed_precision_pnone", **out)
+
+    # Mixture over NIW with a leading replica batch dim: tests/test_dists.py:256-276
+    torch.manual_seed(6)
+    dist = dists.NormalInverseWishart(event_shape=(2,), batch_shape=(3, 6), scale=0.5)
+    m = dists.Mixture(dist, event_shape=(6,))
+    X = torch.randn(200, 3, 2, generator=g) * 2
+    out = {"X": T(X)}
+    out.update(tagged(gmm_state(m), "init"))
+    el = []
+    for i in range(4):
+        m.update(X, 1, 1.0)
+        el.append(T(m.ELBO_last))
+    out.update(tagged(gmm_state(m), "final"))
+    out["final/p"], out["final/NA"], out["final/logZ"] = T(m.p), T(m.NA), T(m.logZ)
+    out["ELBO"] = np.stack(el)
+    save("mixture_batch3_k6", **out)
+
+    # Mixture with event_dim>1 NIW: tests/test_dists.py:278-282
+    torch.manual_seed(7)
+    dist = dists.NormalInverseWishart(event_shape=(3, 2), batch_shape=(5,), scale=0.5)
+    m = dists.Mixture(dist, event_shape=(5,))
+    X = torch.randn(150, 3, 2, generator=g) * 2
+    out = {"X": T(X)}
+    out.update(tagged(gmm_state(m), "init"))
+    el = []
+    for i in range(3):
+        m.update(X, 1, 1.0)
+        el.append(T(m.ELBO_last))
+    out.update(tagged(gmm_state(m), "final"))
+    out["final/p"], out["final/NA"], out["final/logZ"] = T(m.p), T(m.NA), T(m.logZ)
+    out["ELBO"] = np.stack(el)
+    save("mixture_event32_k5", **out)
+
+    # NIW as HMM emission, sample shape (T,S): models/HMM.py:113-117, 138-139
+    torch.manual_seed(8)
+    d = dists.NormalInverseWishart(event_shape=(2,), batch_shape=(4,))
+    Xs = torch.randn(12, 9, 2, generator=g) * 1.5
+    p = torch.softmax(torch.randn(12, 9, 4, generator=g), -1)
+    out = {"X": T(Xs), "p": T(p)}
+    out.update(tagged(niw_state(d, ""), "init"))
+    out["init/Elog_like"] = T(d.Elog_like(Xs.unsqueeze(-2)))
+    d.raw_update(Xs.unsqueeze(-2), p=p, lr=1.0, beta=None)
+    out.update(tagged(niw_state(d, ""), "final"))
+    out["final/Elog_like"] = T(d.Elog_like(Xs.unsqueeze(-2)))
+    out["final/KL"] = T(d.KLqprior())
+    save("niw_hmm_emission_ts", **out)
+
+
+def gen_mnw():
+    g = torch.Generator().manual_seed(31)
+    for pad in (True, False):
+        torch.manual_seed(9)
+        n, p, K, N = 4, 5, 3, 300
+        d = transforms.MatrixNormalWishart(event_shape=(n, p), batch_shape=(K,), scale=0.8, pad_X=pad)
+        out = {"n": n, "p": p, "K": K, "pad_X": int(pad)}
+        out.update(tagged(mnw_state(d, ""), "init"))
+        X = torch.randn(N, 1, p, 1, generator=g)
+        Wt = torch.randn(K, n, p, generator=g)
+        z = torch.randint(K, (N,), generator=g)
+        Y = (Wt[z] @ X.squeeze(1)).unsqueeze(1) + 0.3 * torch.randn(N, 1, n, 1, generator=g) + 0.5
+        r = torch.softmax(torch.randn(N, K, generator=g), -1)
+        out["X"], out["Y"], out["r"] = T(X), T(Y), T(r)
+        out["init/Elog_like"] = T(d.Elog_like(X, Y))
+        out["init/KL"] = T(d.KLqprior())
+        d.raw_update(X, Y, p=r, lr=1.0, beta=None)
+        out.update(tagged(mnw_state(d, ""), "step0"))
+        out["step0/Elog_like"] = T(d.Elog_like(X, Y))
+        out["step0/KL"] = T(d.KLqprior())
+        d.raw_update(X, Y, p=r, lr=0.5, beta=0.8)
+        if not pad:   # the reference's p=None + pad_X branch only accepts X with the full batch shape (:191-202)
+            d.raw_update(X, Y, p=None, lr=0.5, beta=0.8)
+        out.update(tagged(mnw_state(d, ""), "step2"))
+        out["step2/SExx"], out["step2/SEyx"], out["step2/SEyy"], out["step2/N"] = \
+            T(d.SExx), T(d.SEyx), T(d.SEyy), T(d.N)
+        out["step2/Elog_like"] = T(d.Elog_like(X, Y))
+        out["step2/KL"] = T(d.KLqprior())
+        save(f"mnw_n4_p5_k3_pad{int(pad)}", **out)
+
+
+def molt_state(m):
+    s = mnw_state(m.W, "W.")
+    s.update(dir_state(m.pi, "pi."))
+    return s
+
+
+def gen_molt():
+    g = torch.Generator().manual_seed(41)
+    for name, n, p, K, N, iters in (("molt_n3_p4_k5", 3, 4, 5, 600, 5), ("molt_n32_p32_k8", 32, 32, 8, 768, 3)):
+        torch.manual_seed(10)
+        m = transforms.MixtureofLinearTransforms(n, p, K, pad_X=True)
+        X = torch.randn(N, p, generator=g)
+        Wt = torch.randn(K, n, p, generator=g) / np.sqrt(p)
+        b = torch.randn(K, n, generator=g)
+        z = torch.randint(K, (N,), generator=g)
+        Y = torch.einsum("nij,nj->ni", Wt[z], X) + b[z] + 0.1 * torch.randn(N, n, generator=g)
+        out = {"X": T(X), "Y": T(Y), "n": n, "p": p, "K": K, "iters": iters}
+        out.update(tagged(molt_state(m), "init"))
+        el = []
+        for i in range(iters):
+            m.raw_update(X.unsqueeze(-1), Y.unsqueeze(-1), iters=1, lr=1.0)
+            el.append(float(m.ELBO_last))
+            if i == 0:
+                out.update(tagged(molt_state(m), "iter1"))
+                out["iter1/p"], out["iter1/logZ"] = T(m.p), T(m.logZ)
+        out.update(tagged(molt_state(m), "final"))
+        out["final/p"], out["final/logZ"] = T(m.p), T(m.logZ)
+        out["final/assignment"] = T(m.assignment()).astype(np.int32)
+        out["final/KL"] = T(m.KLqprior())
+        out["ELBO"] = np.asarray(el, dtype=np.float64)
+        save(name, **out)
+
+
+def gen_arhmm():
+    g = torch.Generator().manual_seed(51)
+    K, n, p, Tn, S = 4, 2, 3, 40, 25
+    # tests/test_models.py:13-38 style switching AR data
+    Atrue = torch.randn(K, n, p, generator=g) * 0.7
+    btrue = torch.randn(K, n, generator=g)
+    trans = 4 * torch.eye(K) + torch.rand(K, K, generator=g)
+    trans = trans / trans.sum(-1, keepdim=True)
+    z = torch.zeros(Tn, S, dtype=torch.long)
+    z[0] = torch.randint(K, (S,), generator=g)
+    for t in range(1, Tn):
+        z[t] = torch.multinomial(trans[z[t - 1]], 1, generator=g).squeeze(-1)
+    X = torch.randn(Tn, S, p, generator=g)
+    Y = torch.einsum("tsij,tsj->tsi", Atrue[z], X) + btrue[z] + 0.2 * torch.randn(Tn, S, n, generator=g)
+    Xr, Yr = X.unsqueeze(-2).unsqueeze(-1), Y.unsqueeze(-2).unsqueeze(-1)      # (T,S,1,p,1), (T,S,1,n,1)
+    torch.manual_seed(12)
+    m = models.ARHMM(K, n, p)
+    out = {"X": T(Xr), "Y": T(Yr), "K": K, "n": n, "p": p}
+
+    def st():
+        s = mnw_state(m.obs_dist, "obs.")
+        s.update(dir_state(m.transition, "transition."))
+        s.update(dir_state(m.initial, "initial."))
+        return s
+    out.update(tagged(st(), "init"))
+    out["init/obs_logits"] = T(m.obs_logits((Xr, Yr)))
+    el = []
+    for i in range(4):
+        m.update((Xr, Yr), iters=1, lr=1.0)
+        el.append(float(m.ELBO_last))
+        if i == 0:
+            out.update(tagged(st(), "iter1"))
+            out["iter1/p"], out["iter1/logZ"], out["iter1/NA"] = T(m.p), T(m.logZ), T(m.NA)
+    out.update(tagged(st(), "final"))
+    out["final/p"], out["final/logZ"] = T(m.p), T(m.logZ)
+    out["ELBO"] = np.asarray(el, dtype=np.float64)
+    save("arhmm_k4_n2_p3", **out)
+
+
+if __name__ == "__main__":
+    gen_gmm()
+    gen_niw_variants()
+    gen_mnw()
+    gen_molt()
+    gen_arhmm()
