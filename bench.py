@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""bench.py — VB-EM sample·component updates/s (GMM d=64, K=256) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is one full EM iteration of GaussianMixtureModel NIW VB-EM (E-step + softmax + ELBO +
+weighted Gram statistics [+ all-reduce] + NIW update) over the rank's rows.  At N=1 the workload is
+BASELINE.json configs[1] (N=4 194 304, d=64, K=256, fp32); with N>1 ranks every rank owns the same
+number of rows (weak scaling, sample-sharded, one all-reduce of the statistics per iteration).
+Prints ONE JSON line on rank 0.  `--impl reference` times the CPU restatement of the reference's own
+algorithm (oracle/, "port") on the host cores on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "VB-EM sample*component updates/s (GMM d=64 K=256)"
+UNIT = "sample*component updates/s"
+D, K = 64, 256
+ROWS_PER_GPU = 4_194_304
+FLOPS_PER_UPDATE = 4 * D * D          # E 2d^2 + M 2d^2, each real multiply-add counted once
+BYTES_PER_SAMPLE = 8 * D + 8 * K
+
+
+def synth_rows(n, device, seed, k_true=256, d=D, chunk=32768):
+    """cfg2 recipe: mu ~ 3 N(0,I), A_k = I + 0.3 randn/8, x = mu_z + A_z eps."""
+    g = torch.Generator(device=device).manual_seed(4321)          # cluster parameters: same on every rank
+    mu = 3.0 * torch.randn(k_true, d, generator=g, device=device)
+    A = torch.eye(d, device=device) + 0.3 * torch.randn(k_true, d, d, generator=g, device=device) / 8
+    g = torch.Generator(device=device).manual_seed(seed)           # rows: rank-offset stream
+    X = torch.empty(n, d, device=device)
+    for a in range(0, n, chunk):
+        m = min(chunk, n - a)
+        z = torch.randint(k_true, (m,), generator=g, device=device)
+        e = torch.randn(m, d, 1, generator=g, device=device)
+        X[a:a + m] = mu[z] + torch.bmm(A[z], e).squeeze(-1)
+    return X
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for nm, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measure_tf32_peak(device, seconds=1.5):
+    """cuBLAS TF32 8192^3 (same method as MEASURED_PEAKS.json's bf16 figure): burst and sustained TFLOP/s."""
+    n = 8192
+    a = torch.randn(n, n, device=device)
+    b = torch.randn(n, n, device=device)
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        for _ in range(3):
+            a @ b
+        torch.cuda.synchronize(device)
+        best = 1e9
+        for _ in range(10):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record(); a @ b; e.record(); e.synchronize()
+            best = min(best, s.elapsed_time(e))
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = max(10, int(seconds * 1e3 / best))
+        s.record()
+        for _ in range(reps):
+            a @ b
+        e.record(); e.synchronize()
+        sus = s.elapsed_time(e) / reps
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+    fl = 2.0 * n ** 3
+    return fl / best / 1e9, fl / sus / 1e9
+
+
+def cpu_port_iteration_rate(n_rows, iters, threads, seed=0):
+    """The reference's algorithm (broadcast multiply + sum over a materialised (N,K,d,d) temporary,
+    dists/NormalInverseWishart.py:83,93) restated in oracle/, on a bounded sample of the cfg2 workload."""
+    from oracle import vbem_oracle as O
+    torch.set_num_threads(threads)
+    X = synth_rows(n_rows, torch.device("cpu"), 1234 + seed)
+    torch.manual_seed(0)
+    m = O.gmm_new(K, D)
+    m["dist"]["mu"] = X[torch.randint(n_rows, (K,))].clone()
+    O.mixture_update(m, X, 1, exact=True)            # warm-up iteration (allocator, MKL threads)
+    t0 = time.perf_counter()
+    O.mixture_update(m, X, iters, exact=True)
+    dt = time.perf_counter() - t0
+    return iters * n_rows * K / dt, dt / iters
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    n_rows = args.ref_rows
+    torch.set_num_threads(threads)
+    from oracle import vbem_oracle as O
+    X = synth_rows(n_rows, torch.device("cpu"), 1234)
+    torch.manual_seed(0)
+    m = O.gmm_new(K, D)
+    m["dist"]["mu"] = X[torch.randint(n_rows, (K,))].clone()
+    for _ in range(args.warmup):
+        O.mixture_update(m, X, 1, exact=True)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        O.mixture_update(m, X, 1, exact=True)
+    dt = time.perf_counter() - t0
+    val = args.steps * n_rows * K / dt
+    sample = (f"{n_rows} rows of the cfg2 recipe per step (largest chunk whose (N,K,d,d) fp32 temporary fits "
+              f"comfortably: {n_rows * K * D * D * 4 / 2**30:.1f} GiB); full EM iteration per step")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "GaussianMixtureModel NIW VB-EM, d=64, K=256, fp32 (cfg2 recipe), CPU sample",
+                   "rows_per_step": n_rows},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rows-per-gpu", type=int, default=ROWS_PER_GPU)
+    ap.add_argument("--ref-rows", type=int, default=512)
+    ap.add_argument("--cpu-baseline-iters", type=int, default=10)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import torch.distributed as dist
+    import pyvbmp_b200 as V
+    from pyvbmp_b200 import _lib, sharding
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback)")
+    dev = torch.device(f"cuda:{local_rank}")
+    torch.cuda.set_device(dev)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+        sharding.enable()
+
+    n_rows = args.rows_per_gpu
+    X = synth_rows(n_rows, dev, 1234 + rank)
+    # replicated init: same seed on every rank; the initial means are rank 0's rows, broadcast once
+    torch.manual_seed(0)
+    m = V.GaussianMixtureModel(K, D)
+    idx = torch.randint(min(n_rows, 1 << 20), (K,))
+    m.to(dev)
+    mu0 = X[idx.to(dev)].clone()
+    if world > 1:
+        sharding.broadcast_(mu0, 0)
+    m.dist.mu = mu0
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- warm-up, then K timed steps (device-resident inputs) ----------------------------------------
+    for _ in range(args.warmup):
+        m.update(X, 1)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    _lib.PROFILE = {}
+    _lib.LAUNCHES = 0
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        m.update(X, 1)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = _lib.LAUNCHES
+    prof = _lib.PROFILE
+    _lib.PROFILE = None
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t)
+    elbo = float(m.ELBO_last)
+    total_rows = n_rows * world
+    value = args.steps * total_rows * K / (ms / 1e3)
+
+    # per-kernel device times from the CUDA events recorded around each C-ABI call in the timed region
+    kern = {}
+    for name, evs in prof.items():
+        tt = sum(a.elapsed_time(b) for a, b in evs)
+        kern[name] = {"calls": len(evs), "ms_total": tt, "ms_avg": tt / max(len(evs), 1)}
+
+    # ---- end-to-end through the public API with HOST buffers -----------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        Xh = torch.empty(X.shape, dtype=X.dtype, pin_memory=True)
+        Xh.copy_(X)
+        Xd = torch.empty_like(X)
+        res_h = torch.empty(1 + K, dtype=torch.float32, pin_memory=True)
+        for _ in range(2):
+            Xd.copy_(Xh, non_blocking=True); m.update(Xd, 1)
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e2e_steps = args.steps
+        s0.record()
+        for _ in range(e2e_steps):
+            Xd.copy_(Xh, non_blocking=True)                       # H2D of this step's inputs
+            m.update(Xd, 1)
+            res_h.copy_(torch.cat([m.ELBO_last.reshape(1), m.NA.reshape(-1)]), non_blocking=True)   # D2H of the result
+            torch.cuda.current_stream().synchronize()             # the caller reads the ELBO every step
+        s1.record()
+        barrier()
+        tms = torch.tensor([s0.elapsed_time(s1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        e2e = {"value": e2e_steps * total_rows * K / (float(tms) / 1e3), "unit": UNIT,
+               "h2d_bytes_per_step": X.numel() * 4, "d2h_bytes_per_step": res_h.numel() * 4,
+               "ms_per_step": float(tms) / e2e_steps}
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        tf32_burst, tf32_sus = measure_tf32_peak(dev)
+        dom = max(kern, key=lambda k: kern[k]["ms_total"]) if kern else None
+        roof = None
+        if dom is not None:
+            per_launch_flops = 2.0 * n_rows * K * D * D          # E-step GEMM or M-step Gram: 2 d^2 per update
+            ach = per_launch_flops / (kern[dom]["ms_avg"] / 1e3) / 1e12
+            roof = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": tf32_sus, "unit": "TFLOP/s",
+                    "frac": ach / tf32_sus, "traffic": None,
+                    "peak_source": "cuBLAS TF32 8192^3 sustained, measured in this run (MEASURED_PEAKS.json holds "
+                                   "bf16 only: %s burst / %s sustained TFLOP/s)" % (peaks.get("bf16_tflops"),
+                                                                                   peaks.get("bf16_tflops_sustained")),
+                    "peak_tf32_burst": tf32_burst,
+                    "algorithmic_flops_per_launch": per_launch_flops,
+                    "step_tensor_frac": value * FLOPS_PER_UPDATE / world / 1e12 / tf32_sus,
+                    "step_hbm_frac": (value / K / world) * BYTES_PER_SAMPLE / 1e9 / peaks.get("hbm_gbs", 6546.2),
+                    "kernels_ms_avg": {k: round(v["ms_avg"], 4) for k, v in kern.items()}}
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            v, s_per = cpu_port_iteration_rate(args.ref_rows, args.cpu_baseline_iters, threads)
+            cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                   "sample": f"{args.cpu_baseline_iters} EM iterations on {args.ref_rows} rows of the same workload "
+                             f"({s_per:.2f} s/iteration; extrapolates to {s_per * n_rows / args.ref_rows:.0f} s per "
+                             f"full-N iteration); reference op order (N,K,d,d) broadcast-multiply-sum"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"GaussianMixtureModel NIW VB-EM, N={n_rows} rows/GPU x {world} GPU, d={D}, K={K}, "
+                                   "fp32 (BASELINE.json configs[1]; sample-sharded weak scaling for N>1)",
+                       "rows_per_gpu": n_rows, "l2": "inputs_exceed_l2 (X 1 GiB + responsibilities 4 GiB per step)",
+                       "parallelism": f"sample-shard x{world}, 1 all-reduce/iter" if world > 1 else "single GPU"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+            "roofline": roof, "cpu_baseline": cpu, "elbo_last": elbo,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,102 @@
+/* vbmp_b200.h — C ABI of libvbmp_b200.so: the B200 (sm_100a) replacement for pyVBMP's conjugate
+ * VB-EM hot path (NIW / MNW E-step + M-step).  Plain pointers and sizes only; every pointer is a
+ * DEVICE pointer to contiguous row-major fp32 unless noted; the caller owns every buffer and passes
+ * the CUDA stream (cudaStream_t as void*).  All functions return 0 on success and a non-zero
+ * VBMP_ERR_* code otherwise; vbmp_last_error() gives the message (thread-local).
+ *
+ * "C" below is the number of flattened components (all batch dims x extra event dims of the
+ * reference object); "G" x "K" = C splits them into theta groups (replica / extra-event dims) and
+ * the mixture axis.  Each entry cites the reference method it replaces (paths relative to the
+ * pyVBMP tree).
+ */
+#ifndef VBMP_B200_H
+#define VBMP_B200_H
+#include <stddef.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VBMP_ABI_VERSION 1
+
+int vbmp_version(void);
+const char* vbmp_last_error(void);
+
+/* ---- K1: parameter preparation -------------------------------------------------------------------
+ * Reduce the posterior to the whitened form  l[n,c] = cst[c] - 1/2 ||W_c^T z_n - m_c||^2 with W_c
+ * upper triangular, zero padded to Dp x Dp (Dp in {8,16,32,64,128}, Dp >= feature dim).
+ * info[c] != 0 reports a non-SPD matrix (1-based failing column).  logprior may be NULL.
+ *
+ * vbmp_niw_prep: NormalInverseWishart.Elog_like constants — dists/NormalInverseWishart.py:91-97,
+ *   122-123, 131-132; Wishart.EinvSigma / ElogdetinvSigma — dists/Wishart.py:76-77, 82-83.
+ * vbmp_mnw_prep: MatrixNormalWishart.Elog_like constants — transforms/MatrixNormalWishart.py:219-232,
+ *   419-420, 437-438.  Feature order z = [x (p); y (n)];  pp = p + pad_X.                           */
+int vbmp_niw_prep(const float* invU, const float* mu, const float* nu, const float* lambda_mu,
+                  const float* logprior, int C, int d, int Dp,
+                  float* W, float* m, float* cst, int* info, void* stream);
+int vbmp_mnw_prep(const float* invU, const float* nu, const float* mu, const float* invV,
+                  const float* logprior, int C, int n, int pp, int pad_X, int Dp,
+                  float* W, float* m, float* cst, int* info, void* stream);
+
+/* ---- K2: E-step -------------------------------------------------------------------------------------
+ * z = [z0 | z1] per sample (z1 may be NULL with d1 = 0); z_i is (N, GX, d_i) contiguous; xg[G] maps a
+ * theta group to its data column (NULL -> 0).  out is (N, G, K).
+ *   mode 0: out = logits                    NIW/MNW.Elog_like; HMM.obs_logits (models/HMM.py:113-117)
+ *   mode 1: out = exp(l - logZ_n), logZn (N,G), NA (G,K) = sum_n out, logZ (G) = sum_n logZn
+ *           Mixture.update_assignments (dists/Mixture.py:38-45),
+ *           MixtureofLinearTransforms.update_assignments (transforms/MixtureofLinearTransforms.py:34-41)
+ * flags bit 0: force the CUDA-core kernel even where the tcgen05 kernel applies (testing).          */
+size_t vbmp_estep_workspace_bytes(long long N, int G, int K, int Dp, int mode);
+int vbmp_estep(const float* z0, int d0, const float* z1, int d1, long long N, int GX, const int* xg,
+               const float* W, const float* m, const float* cst, int G, int K, int Dp, int mode, int flags,
+               float* out, float* logZn, float* NA, float* logZ,
+               void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- K3: M-step sufficient statistics ----------------------------------------------------------------
+ * gram[g,k] = sum_n p[n,pg[g],k] [z;1][z;1]^T, (D+1)x(D+1) row-major, D = d0 + d1; p is (N, GP, K) or
+ * NULL for unit weights.  Blocks = SExx / SEx / N of NormalInverseWishart.raw_update
+ * (dists/NormalInverseWishart.py:70-86) and SExx / SEyx / SEyy / SEx / SEy / N of
+ * MatrixNormalWishart.raw_update (transforms/MatrixNormalWishart.py:174-204) with z = [x; y].        */
+size_t vbmp_gram_workspace_bytes(long long N, int G, int K, int d0, int d1, int Dp);
+int vbmp_gram(const float* z0, int d0, const float* z1, int d1, long long N, int GX, const int* xg,
+              const float* p, int GP, const int* pg, int G, int K, int Dp, int flags,
+              float* gram, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- K5: natural-parameter updates (replicated; statistics are post-beta) -----------------------------
+ * Wishart.ss_update — dists/Wishart.py:43-56.                                                          */
+int vbmp_wishart_update(const float* SExx, const float* N, const float* invU_0, const float* nu_0,
+                        const float* invU_old, const float* nu_old, int C, int d, float lr,
+                        float* invU, float* nu, float* U, float* logdet_invU, int* info, void* stream);
+/* NormalInverseWishart.ss_update — dists/NormalInverseWishart.py:49-68 (fixed_precision skips the Wishart). */
+int vbmp_niw_update(const float* SExx, const float* SEx, const float* N,
+                    const float* lambda_0, const float* mu_0, const float* invU_0, const float* nu_0,
+                    const float* lambda_old, const float* mu_old, const float* invU_old, const float* nu_old,
+                    int C, int d, float lr, int fixed_precision,
+                    float* lambda_mu, float* mu, float* invU, float* nu, float* U, float* logdet_invU,
+                    int* info, void* stream);
+/* MatrixNormalWishart.ss_update, no-mask branch — transforms/MatrixNormalWishart.py:105-108, 122-135.   */
+int vbmp_mnw_update(const float* SExx, const float* SEyx, const float* SEyy, const float* N,
+                    const float* mu_0, const float* invV_0, const float* invU_0, const float* nu_0,
+                    const float* mu_old, const float* invV_old, const float* invU_old, const float* nu_old,
+                    int C, int n, int pp, float lr, int fixed_precision,
+                    float* mu, float* invV, float* V, float* logdetinvV,
+                    float* invU, float* nu, float* U, float* logdet_invU, int* info, void* stream);
+
+/* ---- expectations / KL (per component, length C) ------------------------------------------------------
+ * Wishart.ElogdetinvSigma — dists/Wishart.py:82-83;  Wishart.KLqprior — :88-94;
+ * NormalInverseWishart.KLqprior — dists/NormalInverseWishart.py:99-105;
+ * MatrixNormalWishart.KLqprior — transforms/MatrixNormalWishart.py:206-216.                             */
+int vbmp_wishart_elogdet(const float* nu, const float* logdet_invU, int C, int d, float* out, void* stream);
+int vbmp_wishart_kl(const float* invU_0, const float* U, const float* nu_0, const float* nu,
+                    const float* logdet_invU, const float* logdet_invU_0, int C, int d, float* out, void* stream);
+int vbmp_niw_kl(const float* lambda_0, const float* lambda_mu, const float* mu_0, const float* mu,
+                const float* invU_0, const float* U, const float* nu_0, const float* nu,
+                const float* logdet_invU, const float* logdet_invU_0, int C, int d, float* out, void* stream);
+int vbmp_mnw_kl(const float* mu_0, const float* mu, const float* invV_0, const float* V,
+                const float* logdetinvV, const float* logdetinvV_0, const float* invU_0, const float* U,
+                const float* nu_0, const float* nu, const float* logdet_invU, const float* logdet_invU_0,
+                int C, int n, int pp, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VBMP_B200_H */

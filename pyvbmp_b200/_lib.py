@@ -1,0 +1,263 @@
+"""ctypes binding of libvbmp_b200.so (the C ABI in include/vbmp_b200.h).
+
+There is no CPU fallback: if the shared library is missing, or a tensor is not a CUDA tensor, the
+call raises.  torch is used only for device memory and the current stream.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_longlong, c_size_t, c_void_p
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvbmp_b200.so")
+_lib = None
+
+FORCE_SIMT = int(os.environ.get("VBMP_FORCE_SIMT", "0"))   # tests flip this to pin the CUDA-core kernels
+
+
+PROFILE = None     # bench.py sets this to {} to collect (start, end) CUDA events per C-ABI call
+LAUNCHES = 0       # kernels launched through the C ABI (bench.py's gpu_launches)
+_NKERNELS = {"vbmp_estep": 2, "vbmp_gram": 2}
+
+
+class VbmpError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load libvbmp_b200.so once; fail loudly when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise VbmpError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "or `make -C pyvbmp_b200/csrc` (there is no CPU fallback)")
+        L = ctypes.CDLL(LIB_PATH)
+        L.vbmp_last_error.restype = c_char_p
+        L.vbmp_version.restype = c_int
+        L.vbmp_estep_workspace_bytes.restype = c_size_t
+        L.vbmp_estep_workspace_bytes.argtypes = [c_longlong, c_int, c_int, c_int, c_int]
+        L.vbmp_gram_workspace_bytes.restype = c_size_t
+        L.vbmp_gram_workspace_bytes.argtypes = [c_longlong, c_int, c_int, c_int, c_int, c_int]
+        _lib = L
+    return _lib
+
+
+EXPORTS = (
+    "vbmp_version", "vbmp_last_error", "vbmp_niw_prep", "vbmp_mnw_prep", "vbmp_estep_workspace_bytes",
+    "vbmp_estep", "vbmp_gram_workspace_bytes", "vbmp_gram", "vbmp_wishart_update", "vbmp_niw_update",
+    "vbmp_mnw_update", "vbmp_wishart_elogdet", "vbmp_wishart_kl", "vbmp_niw_kl", "vbmp_mnw_kl",
+)
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise VbmpError(f"{what} failed (code {rc}): {lib().vbmp_last_error().decode()}")
+
+
+def _call(name, *args):
+    """Invoke one C-ABI entry point on the current stream (optionally bracketed by CUDA events)."""
+    global LAUNCHES
+    fn = getattr(lib(), name)
+    if PROFILE is not None:
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        rc = fn(*args)
+        b.record()
+        PROFILE.setdefault(name, []).append((a, b))
+    else:
+        rc = fn(*args)
+    LAUNCHES += _NKERNELS.get(name, 1)
+    _check(rc, name)
+
+
+def _ptr(t):
+    if t is None:
+        return c_void_p(0)
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise VbmpError("pyvbmp_b200 kernels need CUDA tensors (no CPU fallback); got "
+                        f"{type(t).__name__} on {getattr(t, 'device', '?')}")
+    if not t.is_contiguous():
+        raise VbmpError("internal error: non-contiguous tensor reached the C ABI")
+    return c_void_p(t.data_ptr())
+
+
+def _stream(dev):
+    return c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def f32(t, device=None):
+    """Contiguous fp32 copy/view of ``t`` (on ``device`` when given)."""
+    if device is not None and t.device != device:
+        t = t.to(device)
+    if t.dtype != torch.float32:
+        t = t.to(torch.float32)
+    return t.contiguous()
+
+
+def pad_dim(D):
+    """Padded feature dimension the kernels tile by."""
+    for Dp in (8, 16, 32, 64, 128):
+        if D <= Dp:
+            return Dp
+    raise VbmpError(f"feature dimension {D} > 128 is outside the hot path this library implements")
+
+
+_ws_cache = {}
+
+
+def _workspace(nbytes, dev):
+    """Per-device grow-only scratch buffer (kernels on one stream serialise, so reuse is safe)."""
+    key = (dev.type, dev.index, torch.cuda.current_stream(dev).cuda_stream)
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=dev)
+        _ws_cache[key] = buf
+    return buf
+
+
+# ------------------------------------------------------------------------------------------------
+# thin typed wrappers (all tensors contiguous fp32 CUDA unless noted)
+# ------------------------------------------------------------------------------------------------
+
+def niw_prep(invU, mu, nu, lam, logprior, C, d, Dp):
+    dev = invU.device
+    W = torch.empty((C, Dp, Dp), dtype=torch.float32, device=dev)
+    m = torch.empty((C, Dp), dtype=torch.float32, device=dev)
+    cst = torch.empty((C,), dtype=torch.float32, device=dev)
+    info = torch.empty((C,), dtype=torch.int32, device=dev)
+    _call("vbmp_niw_prep", _ptr(invU), _ptr(mu), _ptr(nu), _ptr(lam), _ptr(logprior), c_int(C), c_int(d),
+                               c_int(Dp), _ptr(W), _ptr(m), _ptr(cst), _ptr(info), _stream(dev))
+    return W, m, cst, info
+
+
+def mnw_prep(invU, nu, mu, invV, logprior, C, n, pp, pad, Dp):
+    dev = invU.device
+    W = torch.empty((C, Dp, Dp), dtype=torch.float32, device=dev)
+    m = torch.empty((C, Dp), dtype=torch.float32, device=dev)
+    cst = torch.empty((C,), dtype=torch.float32, device=dev)
+    info = torch.empty((C,), dtype=torch.int32, device=dev)
+    _call("vbmp_mnw_prep", _ptr(invU), _ptr(nu), _ptr(mu), _ptr(invV), _ptr(logprior), c_int(C), c_int(n),
+                               c_int(pp), c_int(int(pad)), c_int(Dp), _ptr(W), _ptr(m), _ptr(cst), _ptr(info),
+                               _stream(dev))
+    return W, m, cst, info
+
+
+def estep(z0, z1, N, GX, xg, W, m, cst, G, K, Dp, mode, out=None):
+    """z0: (N,GX,d0), z1: (N,GX,d1) or None.  Returns logits (mode 0) or (p, logZn, NA, logZ) (mode 1)."""
+    dev = z0.device
+    d0 = z0.shape[-1]
+    d1 = 0 if z1 is None else z1.shape[-1]
+    if out is None:
+        out = torch.empty((N, G, K), dtype=torch.float32, device=dev)
+    logZn = NA = logZ = None
+    if mode == 1:
+        logZn = torch.empty((N, G), dtype=torch.float32, device=dev)
+        NA = torch.empty((G, K), dtype=torch.float32, device=dev)
+        logZ = torch.empty((G,), dtype=torch.float32, device=dev)
+    nbytes = lib().vbmp_estep_workspace_bytes(c_longlong(N), c_int(G), c_int(K), c_int(Dp), c_int(mode))
+    ws = _workspace(nbytes, dev)
+    _call("vbmp_estep", _ptr(z0), c_int(d0), _ptr(z1), c_int(d1), c_longlong(N), c_int(GX), _ptr(xg),
+                            _ptr(W), _ptr(m), _ptr(cst), c_int(G), c_int(K), c_int(Dp), c_int(mode),
+                            c_int(1 if FORCE_SIMT else 0), _ptr(out), _ptr(logZn), _ptr(NA), _ptr(logZ),
+                            _ptr(ws), c_size_t(ws.numel()), _stream(dev))
+    if mode == 0:
+        return out
+    return out, logZn, NA, logZ
+
+
+def gram(z0, z1, N, GX, xg, p, GP, pg, G, K, Dp):
+    """Returns gram (G,K,D+1,D+1)."""
+    dev = z0.device
+    d0 = z0.shape[-1]
+    d1 = 0 if z1 is None else z1.shape[-1]
+    D1 = d0 + d1 + 1
+    out = torch.empty((G, K, D1, D1), dtype=torch.float32, device=dev)
+    nbytes = lib().vbmp_gram_workspace_bytes(c_longlong(N), c_int(G), c_int(K), c_int(d0), c_int(d1), c_int(Dp))
+    ws = _workspace(nbytes, dev)
+    _call("vbmp_gram", _ptr(z0), c_int(d0), _ptr(z1), c_int(d1), c_longlong(N), c_int(GX), _ptr(xg),
+                           _ptr(p), c_int(GP), _ptr(pg), c_int(G), c_int(K), c_int(Dp),
+                           c_int(1 if FORCE_SIMT else 0), _ptr(out), _ptr(ws), c_size_t(ws.numel()),
+                           _stream(dev))
+    return out
+
+
+def wishart_update(SExx, N, invU0, nu0, invU_old, nu_old, C, d, lr):
+    dev = SExx.device
+    invU = torch.empty((C, d, d), dtype=torch.float32, device=dev)
+    U = torch.empty((C, d, d), dtype=torch.float32, device=dev)
+    nu = torch.empty((C,), dtype=torch.float32, device=dev)
+    logdet = torch.empty((C,), dtype=torch.float32, device=dev)
+    info = torch.empty((C,), dtype=torch.int32, device=dev)
+    _call("vbmp_wishart_update", _ptr(SExx), _ptr(N), _ptr(invU0), _ptr(nu0), _ptr(invU_old), _ptr(nu_old),
+                                     c_int(C), c_int(d), c_float(lr), _ptr(invU), _ptr(nu), _ptr(U), _ptr(logdet),
+                                     _ptr(info), _stream(dev))
+    return invU, nu, U, logdet, info
+
+
+def niw_update(SExx, SEx, N, lam0, mu0, invU0, nu0, lam_old, mu_old, invU_old, nu_old, C, d, lr, fixed_precision):
+    dev = SExx.device
+    lam = torch.empty((C,), dtype=torch.float32, device=dev)
+    mu = torch.empty((C, d), dtype=torch.float32, device=dev)
+    if fixed_precision:
+        invU = nu = U = logdet = None
+    else:
+        invU = torch.empty((C, d, d), dtype=torch.float32, device=dev)
+        U = torch.empty((C, d, d), dtype=torch.float32, device=dev)
+        nu = torch.empty((C,), dtype=torch.float32, device=dev)
+        logdet = torch.empty((C,), dtype=torch.float32, device=dev)
+    info = torch.empty((C,), dtype=torch.int32, device=dev)
+    _call("vbmp_niw_update", _ptr(SExx), _ptr(SEx), _ptr(N), _ptr(lam0), _ptr(mu0), _ptr(invU0), _ptr(nu0),
+                                 _ptr(lam_old), _ptr(mu_old), _ptr(invU_old), _ptr(nu_old), c_int(C), c_int(d),
+                                 c_float(lr), c_int(int(bool(fixed_precision))), _ptr(lam), _ptr(mu), _ptr(invU),
+                                 _ptr(nu), _ptr(U), _ptr(logdet), _ptr(info), _stream(dev))
+    return lam, mu, invU, nu, U, logdet, info
+
+
+def mnw_update(SExx, SEyx, SEyy, N, mu0, invV0, invU0, nu0, mu_old, invV_old, invU_old, nu_old, C, n, pp, lr,
+               fixed_precision):
+    dev = SExx.device
+    e = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)   # noqa: E731
+    mu, invV, V, ldV = e(C, n, pp), e(C, pp, pp), e(C, pp, pp), e(C)
+    if fixed_precision:
+        invU = nu = U = ldU = None
+    else:
+        invU, nu, U, ldU = e(C, n, n), e(C), e(C, n, n), e(C)
+    info = torch.empty((C,), dtype=torch.int32, device=dev)
+    _call("vbmp_mnw_update", _ptr(SExx), _ptr(SEyx), _ptr(SEyy), _ptr(N), _ptr(mu0), _ptr(invV0), _ptr(invU0),
+                                 _ptr(nu0), _ptr(mu_old), _ptr(invV_old), _ptr(invU_old), _ptr(nu_old), c_int(C),
+                                 c_int(n), c_int(pp), c_float(lr), c_int(int(bool(fixed_precision))), _ptr(mu),
+                                 _ptr(invV), _ptr(V), _ptr(ldV), _ptr(invU), _ptr(nu), _ptr(U), _ptr(ldU),
+                                 _ptr(info), _stream(dev))
+    return mu, invV, V, ldV, invU, nu, U, ldU, info
+
+
+def wishart_elogdet(nu, logdet, C, d):
+    out = torch.empty((C,), dtype=torch.float32, device=nu.device)
+    _call("vbmp_wishart_elogdet", _ptr(nu), _ptr(logdet), c_int(C), c_int(d), _ptr(out), _stream(nu.device))
+    return out
+
+
+def wishart_kl(invU0, U, nu0, nu, logdet, logdet0, C, d):
+    out = torch.empty((C,), dtype=torch.float32, device=U.device)
+    _call("vbmp_wishart_kl", _ptr(invU0), _ptr(U), _ptr(nu0), _ptr(nu), _ptr(logdet), _ptr(logdet0), c_int(C),
+                                 c_int(d), _ptr(out), _stream(U.device))
+    return out
+
+
+def niw_kl(lam0, lam, mu0, mu, invU0, U, nu0, nu, logdet, logdet0, C, d):
+    out = torch.empty((C,), dtype=torch.float32, device=U.device)
+    _call("vbmp_niw_kl", _ptr(lam0), _ptr(lam), _ptr(mu0), _ptr(mu), _ptr(invU0), _ptr(U), _ptr(nu0), _ptr(nu),
+                             _ptr(logdet), _ptr(logdet0), c_int(C), c_int(d), _ptr(out), _stream(U.device))
+    return out
+
+
+def mnw_kl(mu0, mu, invV0, V, ldV, ldV0, invU0, U, nu0, nu, ldU, ldU0, C, n, pp):
+    out = torch.empty((C,), dtype=torch.float32, device=U.device)
+    _call("vbmp_mnw_kl", _ptr(mu0), _ptr(mu), _ptr(invV0), _ptr(V), _ptr(ldV), _ptr(ldV0), _ptr(invU0), _ptr(U),
+                             _ptr(nu0), _ptr(nu), _ptr(ldU), _ptr(ldU0), c_int(C), c_int(n), c_int(pp), _ptr(out),
+                             _stream(U.device))
+    return out

@@ -1,0 +1,204 @@
+// extern "C" entry points of libvbmp_b200.so (see include/vbmp_b200.h for the contract).
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include "common.cuh"
+#include "../../include/vbmp_b200.h"
+
+namespace vbmp {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return VBMP_ERR_CUDA;
+  }
+  return VBMP_OK;
+}
+
+// ---- forward declarations of the launchers (prep.cu, update.cu, estep_simt.cu, gram_simt.cu, *_umma.cu)
+int launch_niw_prep(const float*, const float*, const float*, const float*, const float*, int, int, int, float*, float*, float*, int*, cudaStream_t);
+int launch_mnw_prep(const float*, const float*, const float*, const float*, const float*, int, int, int, int, int, float*, float*, float*, int*, cudaStream_t);
+int estep_simt_tile(int Dp);
+int launch_estep_simt(const EstepArgs&, int mode, cudaStream_t);
+int launch_estep_reduce(const float*, const double*, int nb, int G, int K, float* NA, float* logZ, cudaStream_t);
+int gram_simt_plan(long long N, int G, int K, int Dp, long long* S_per, int* splits);
+int launch_gram_simt(const GramArgs&, cudaStream_t);
+int launch_gram_reduce(const float* part, int splits, size_t per, float* gram, cudaStream_t);
+int launch_wishart_update(const float*, const float*, const float*, const float*, const float*, const float*, int, int, float, float*, float*, float*, float*, int*, cudaStream_t);
+int launch_niw_update(const float*, const float*, const float*, const float*, const float*, const float*, const float*, const float*, const float*, const float*, const float*, int, int, float, int, float*, float*, float*, float*, float*, float*, int*, cudaStream_t);
+int launch_mnw_update(const float*, const float*, const float*, const float*, const float*, const float*, const float*, const float*, const float*, const float*, const float*, const float*, int, int, int, float, int, float*, float*, float*, float*, float*, float*, float*, float*, int*, cudaStream_t);
+int launch_wishart_elogdet(const float*, const float*, int, int, float*, cudaStream_t);
+int launch_wishart_kl(const float*, const float*, const float*, const float*, const float*, const float*, int, int, float*, cudaStream_t);
+int launch_niw_kl(const float*, const float*, const float*, const float*, const float*, const float*, const float*, const float*, const float*, const float*, int, int, float*, cudaStream_t);
+int launch_mnw_kl(const float*, const float*, const float*, const float*, const float*, const float*, const float*, const float*, const float*, const float*, const float*, const float*, int, int, int, float*, cudaStream_t);
+// tcgen05 variants (estep_umma.cu / gram_umma.cu)
+bool estep_umma_supported(long long N, int GX, int G, int K, int Dp, int d0, int d1);
+size_t estep_umma_workspace_bytes(long long N, int G, int K, int Dp, int mode);
+int launch_estep_umma(const EstepArgs&, int mode, void* ws, size_t ws_bytes, float* NA, float* logZ, cudaStream_t);
+bool gram_umma_supported(long long N, int GX, int GP, int G, int K, int Dp, int d0, int d1, bool has_p);
+size_t gram_umma_workspace_bytes(long long N, int G, int K, int d0, int d1, int Dp);
+int launch_gram_umma(const GramArgs&, float* gram, void* ws, size_t ws_bytes, cudaStream_t);
+
+static bool valid_dp(int Dp) { return Dp == 8 || Dp == 16 || Dp == 32 || Dp == 64 || Dp == 128; }
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+}  // namespace vbmp
+
+using namespace vbmp;
+
+extern "C" {
+
+int vbmp_version(void) { return VBMP_ABI_VERSION; }
+const char* vbmp_last_error(void) { return g_err; }
+
+int vbmp_niw_prep(const float* invU, const float* mu, const float* nu, const float* lambda_mu, const float* logprior,
+                  int C, int d, int Dp, float* W, float* m, float* cst, int* info, void* stream) {
+  if (!valid_dp(Dp)) { set_error("niw_prep: Dp=%d must be one of 8,16,32,64,128", Dp); return VBMP_ERR_SHAPE; }
+  return launch_niw_prep(invU, mu, nu, lambda_mu, logprior, C, d, Dp, W, m, cst, info, (cudaStream_t)stream);
+}
+
+int vbmp_mnw_prep(const float* invU, const float* nu, const float* mu, const float* invV, const float* logprior,
+                  int C, int n, int pp, int pad_X, int Dp, float* W, float* m, float* cst, int* info, void* stream) {
+  if (!valid_dp(Dp)) { set_error("mnw_prep: Dp=%d must be one of 8,16,32,64,128", Dp); return VBMP_ERR_SHAPE; }
+  return launch_mnw_prep(invU, nu, mu, invV, logprior, C, n, pp, pad_X ? 1 : 0, Dp, W, m, cst, info, (cudaStream_t)stream);
+}
+
+size_t vbmp_estep_workspace_bytes(long long N, int G, int K, int Dp, int mode) {
+  if (!valid_dp(Dp) || N < 0) return 0;
+  size_t simt = 0;
+  if (mode == 1) {
+    const size_t nb = (size_t)cdiv(N, estep_simt_tile(Dp));
+    simt = align_up(nb * G * K * sizeof(float), 256) + align_up(nb * G * sizeof(double), 256);
+  }
+  const size_t umma = estep_umma_workspace_bytes(N, G, K, Dp, mode);
+  return (simt > umma ? simt : umma) + 256;
+}
+
+int vbmp_estep(const float* z0, int d0, const float* z1, int d1, long long N, int GX, const int* xg,
+               const float* W, const float* m, const float* cst, int G, int K, int Dp, int mode, int flags,
+               float* out, float* logZn, float* NA, float* logZ,
+               void* workspace, size_t workspace_bytes, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!valid_dp(Dp) || d0 < 1 || d1 < 0 || d0 + d1 > Dp || G < 1 || K < 1 || GX < 1 || N < 0 || (mode != 0 && mode != 1)) {
+    set_error("estep: bad shape N=%lld GX=%d G=%d K=%d d0=%d d1=%d Dp=%d mode=%d", N, GX, G, K, d0, d1, Dp, mode);
+    return VBMP_ERR_SHAPE;
+  }
+  if (d1 > 0 && !z1) { set_error("estep: z1 is NULL with d1=%d", d1); return VBMP_ERR_SHAPE; }
+  if (mode == 1 && (!logZn || !NA || !logZ)) { set_error("estep: mode 1 needs logZn, NA, logZ"); return VBMP_ERR_SHAPE; }
+  if (N == 0) {
+    if (mode == 1) { cudaMemsetAsync(NA, 0, sizeof(float) * G * K, st); cudaMemsetAsync(logZ, 0, sizeof(float) * G, st); }
+    return VBMP_OK;
+  }
+  if (workspace_bytes < vbmp_estep_workspace_bytes(N, G, K, Dp, mode) && mode == 1) {
+    set_error("estep: workspace too small (%zu < %zu)", workspace_bytes, vbmp_estep_workspace_bytes(N, G, K, Dp, mode));
+    return VBMP_ERR_WORKSPACE;
+  }
+  EstepArgs a{z0, z1, d0, d1, N, GX, xg, W, m, cst, G, K, Dp, out, logZn, nullptr, nullptr};
+  if (!(flags & 1) && estep_umma_supported(N, GX, G, K, Dp, d0, d1))
+    return launch_estep_umma(a, mode, workspace, workspace_bytes, NA, logZ, st);
+  int nb = cdiv(N, estep_simt_tile(Dp));
+  if (mode == 1) {
+    char* ws = (char*)align_up((size_t)workspace, 256);
+    a.NA_part = (float*)ws;
+    a.logZ_part = (double*)(ws + align_up((size_t)nb * G * K * sizeof(float), 256));
+  }
+  int rc = launch_estep_simt(a, mode, st);
+  if (rc) return rc;
+  if (mode == 1) rc = launch_estep_reduce(a.NA_part, a.logZ_part, nb, G, K, NA, logZ, st);
+  return rc;
+}
+
+size_t vbmp_gram_workspace_bytes(long long N, int G, int K, int d0, int d1, int Dp) {
+  if (!valid_dp(Dp) || N < 0) return 0;
+  long long S_per; int splits;
+  gram_simt_plan(N > 0 ? N : 1, G, K, Dp, &S_per, &splits);
+  const size_t D1 = (size_t)d0 + d1 + 1;
+  const size_t simt = (size_t)splits * G * K * D1 * D1 * sizeof(float);
+  const size_t umma = gram_umma_workspace_bytes(N, G, K, d0, d1, Dp);
+  return (simt > umma ? simt : umma) + 256;
+}
+
+int vbmp_gram(const float* z0, int d0, const float* z1, int d1, long long N, int GX, const int* xg,
+              const float* p, int GP, const int* pg, int G, int K, int Dp, int flags,
+              float* gram, void* workspace, size_t workspace_bytes, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!valid_dp(Dp) || d0 < 1 || d1 < 0 || d0 + d1 > Dp || G < 1 || K < 1 || GX < 1 || GP < 1 || N < 0) {
+    set_error("gram: bad shape N=%lld GX=%d GP=%d G=%d K=%d d0=%d d1=%d Dp=%d", N, GX, GP, G, K, d0, d1, Dp);
+    return VBMP_ERR_SHAPE;
+  }
+  if (d1 > 0 && !z1) { set_error("gram: z1 is NULL with d1=%d", d1); return VBMP_ERR_SHAPE; }
+  const size_t D1 = (size_t)d0 + d1 + 1, per = (size_t)G * K * D1 * D1;
+  if (N == 0) { cudaMemsetAsync(gram, 0, per * sizeof(float), st); return VBMP_OK; }
+  if (workspace_bytes < vbmp_gram_workspace_bytes(N, G, K, d0, d1, Dp)) {
+    set_error("gram: workspace too small (%zu < %zu)", workspace_bytes, vbmp_gram_workspace_bytes(N, G, K, d0, d1, Dp));
+    return VBMP_ERR_WORKSPACE;
+  }
+  GramArgs a{z0, z1, d0, d1, N, GX, xg, p, GP, pg, G, K, Dp, 0, 0, nullptr};
+  if (!(flags & 1) && gram_umma_supported(N, GX, GP, G, K, Dp, d0, d1, p != nullptr))
+    return launch_gram_umma(a, gram, workspace, workspace_bytes, st);
+  gram_simt_plan(N, G, K, Dp, &a.S_per, &a.splits);
+  a.part = (float*)align_up((size_t)workspace, 256);
+  int rc = launch_gram_simt(a, st);
+  if (rc) return rc;
+  return launch_gram_reduce(a.part, a.splits, per, gram, st);
+}
+
+int vbmp_wishart_update(const float* SExx, const float* N, const float* invU_0, const float* nu_0,
+                        const float* invU_old, const float* nu_old, int C, int d, float lr,
+                        float* invU, float* nu, float* U, float* logdet_invU, int* info, void* stream) {
+  return launch_wishart_update(SExx, N, invU_0, nu_0, invU_old, nu_old, C, d, lr, invU, nu, U, logdet_invU, info, (cudaStream_t)stream);
+}
+
+int vbmp_niw_update(const float* SExx, const float* SEx, const float* N,
+                    const float* lambda_0, const float* mu_0, const float* invU_0, const float* nu_0,
+                    const float* lambda_old, const float* mu_old, const float* invU_old, const float* nu_old,
+                    int C, int d, float lr, int fixed_precision,
+                    float* lambda_mu, float* mu, float* invU, float* nu, float* U, float* logdet_invU,
+                    int* info, void* stream) {
+  return launch_niw_update(SExx, SEx, N, lambda_0, mu_0, invU_0, nu_0, lambda_old, mu_old, invU_old, nu_old, C, d, lr,
+                           fixed_precision, lambda_mu, mu, invU, nu, U, logdet_invU, info, (cudaStream_t)stream);
+}
+
+int vbmp_mnw_update(const float* SExx, const float* SEyx, const float* SEyy, const float* N,
+                    const float* mu_0, const float* invV_0, const float* invU_0, const float* nu_0,
+                    const float* mu_old, const float* invV_old, const float* invU_old, const float* nu_old,
+                    int C, int n, int pp, float lr, int fixed_precision,
+                    float* mu, float* invV, float* V, float* logdetinvV,
+                    float* invU, float* nu, float* U, float* logdet_invU, int* info, void* stream) {
+  return launch_mnw_update(SExx, SEyx, SEyy, N, mu_0, invV_0, invU_0, nu_0, mu_old, invV_old, invU_old, nu_old, C, n, pp,
+                           lr, fixed_precision, mu, invV, V, logdetinvV, invU, nu, U, logdet_invU, info, (cudaStream_t)stream);
+}
+
+int vbmp_wishart_elogdet(const float* nu, const float* logdet_invU, int C, int d, float* out, void* stream) {
+  return launch_wishart_elogdet(nu, logdet_invU, C, d, out, (cudaStream_t)stream);
+}
+
+int vbmp_wishart_kl(const float* invU_0, const float* U, const float* nu_0, const float* nu,
+                    const float* logdet_invU, const float* logdet_invU_0, int C, int d, float* out, void* stream) {
+  return launch_wishart_kl(invU_0, U, nu_0, nu, logdet_invU, logdet_invU_0, C, d, out, (cudaStream_t)stream);
+}
+
+int vbmp_niw_kl(const float* lambda_0, const float* lambda_mu, const float* mu_0, const float* mu,
+                const float* invU_0, const float* U, const float* nu_0, const float* nu,
+                const float* logdet_invU, const float* logdet_invU_0, int C, int d, float* out, void* stream) {
+  return launch_niw_kl(lambda_0, lambda_mu, mu_0, mu, invU_0, U, nu_0, nu, logdet_invU, logdet_invU_0, C, d, out, (cudaStream_t)stream);
+}
+
+int vbmp_mnw_kl(const float* mu_0, const float* mu, const float* invV_0, const float* V,
+                const float* logdetinvV, const float* logdetinvV_0, const float* invU_0, const float* U,
+                const float* nu_0, const float* nu, const float* logdet_invU, const float* logdet_invU_0,
+                int C, int n, int pp, float* out, void* stream) {
+  return launch_mnw_kl(mu_0, mu, invV_0, V, logdetinvV, logdetinvV_0, invU_0, U, nu_0, nu, logdet_invU, logdet_invU_0, C, n, pp, out, (cudaStream_t)stream);
+}
+
+}  // extern "C"

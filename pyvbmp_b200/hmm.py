@@ -1,0 +1,159 @@
+"""HMM / ARHMM glue with the reference's interface (models/HMM.py:5-178, models/ARHMM.py:13-25).
+
+The emission E-step (obs_logits -> K1 + K2, mode 0) and M-step (raw_update -> weighted Gram +
+update kernel) run in libvbmp_b200.so with the (T, S) sample axes flattened.  The forward-backward
+recursion between them is the "next" row §8f #1: here it is a batched torch recursion on the device.
+"""
+from __future__ import annotations
+
+import torch
+
+from .dirichlet import Dirichlet
+from .mnw import MatrixNormalWishart
+
+
+def _lse(x, dim, keepdim=False):
+    return torch.logsumexp(x, dim=dim, keepdim=keepdim)
+
+
+class HMM():
+    def __init__(self, obs_dist, transition_mask=None, ptemp=1.0):
+        """models/HMM.py:6-31."""
+        self.obs_dist = obs_dist
+        self.event_dim = 1
+        self.dim = obs_dist.batch_shape[-1]
+        self.event_shape = obs_dist.batch_shape[-1:]
+        self.batch_shape = obs_dist.batch_shape[:-1]
+        self.batch_dim = len(self.batch_shape)
+        self.transition_mask = transition_mask
+
+        alpha = torch.eye(self.dim, requires_grad=False) + 0.5
+        if transition_mask is not None:
+            alpha = alpha * transition_mask
+        self.transition = Dirichlet(self.event_shape, self.batch_shape + self.event_shape, prior_parms={'alpha': alpha})
+        self.initial = Dirichlet(self.event_shape, self.batch_shape)
+
+        self.sumlogZ = -torch.inf
+        self.p = None
+        self.ptemp = ptemp
+        self.logZ = torch.tensor(-torch.inf)
+        self.ELBO_last = torch.tensor(-torch.inf)
+
+    def to(self, device):
+        self.obs_dist.to(device)
+        self.transition.to(device)
+        self.initial.to(device)
+        self.logZ = self.logZ.to(device)
+        self.ELBO_last = self.ELBO_last.to(device)
+        return self
+
+    def forward_backward_logits(self, fw_logits):
+        """models/HMM.py:72-105: log-space filter, backward smoother, expected transition counts."""
+        tr = self.transition.loggeomean()
+        init = self.initial.loggeomean()
+        T = fw_logits.shape[0]
+        fw = torch.empty_like(fw_logits)
+        fw[0] = _lse(init.unsqueeze(-1) + tr + fw_logits[0].unsqueeze(-2), -2)
+        for t in range(1, T):
+            fw[t] = _lse(fw[t - 1].unsqueeze(-1) + tr + fw_logits[t].unsqueeze(-2), -2)
+        logZ = _lse(fw[-1], -1, True)
+        fw = fw - logZ
+        logZ = logZ.squeeze(-1)
+        SEzz = torch.zeros(fw.shape[1:] + self.event_shape, dtype=fw.dtype, device=fw.device)
+        for t in range(T - 2, -1, -1):
+            temp = fw[t].unsqueeze(-1) + tr
+            xi = (temp - _lse(temp, -2, True)) + fw[t + 1].unsqueeze(-2)
+            fw[t] = _lse(xi, -1)
+            SEzz = SEzz + (xi - _lse(xi, (-1, -2), True)).exp()
+        temp = init.unsqueeze(-1) + tr
+        xi = (temp - _lse(temp, -2, True)) + fw[0].unsqueeze(-2)
+        SEz0 = _lse(xi, -1)
+        SEz0 = (SEz0 - _lse(SEz0, -1, True)).exp()
+        SEzz = SEzz + (xi - _lse(xi, (-1, -2), True)).exp()
+        p = ((fw - fw.max(-1, keepdim=True)[0]) / self.ptemp).exp()
+        p = p / p.sum(-1, keepdim=True)
+        return p, SEzz, SEz0, logZ
+
+    def assignment_pr(self):
+        return self.p
+
+    def assignment(self):
+        return self.p.argmax(-1)
+
+    def obs_logits(self, X, t=None):
+        """models/HMM.py:113-117."""
+        if t is not None:
+            return self.obs_dist.Elog_like(X[t].unsqueeze(-1 - self.obs_dist.event_dim))
+        return self.obs_dist.Elog_like(X.unsqueeze(-1 - self.obs_dist.event_dim))
+
+    def update_states(self, X, T=None):
+        """models/HMM.py:119-132 (T=None path)."""
+        if T is not None:
+            raise NotImplementedError("the step-wise T path calls an undefined helper in the reference (HMM.py:61)")
+        self.p, SEzz, SEz0, logZ = self.forward_backward_logits(self.obs_logits(X))
+        NA = self.p.sum(0)
+        sample_dims = list(range(NA.ndim - self.batch_dim - self.event_dim))
+        NA = NA.sum(sample_dims)
+        SEzz = SEzz.sum(sample_dims)
+        SEz0 = SEz0.sum(sample_dims)
+        logZ = logZ.sum(sample_dims)
+        return SEzz, SEz0, NA, logZ
+
+    def update_markov_parms(self, SEzz, SEz0, lr=1.0, beta=None):
+        self.transition.ss_update(SEzz, lr=lr, beta=beta)
+        self.initial.ss_update(SEz0, lr=lr, beta=beta)
+
+    def update_obs_parms(self, X, lr=1.0, beta=None):
+        """models/HMM.py:138-139."""
+        self.obs_dist.raw_update(X.unsqueeze(-1 - self.obs_dist.event_dim), p=self.p, lr=lr, beta=beta)
+
+    def update(self, X, iters=1, T=None, lr=1.0, beta=None, verbose=False):
+        """models/HMM.py:141-152 (ELBO is evaluated after the M-step here)."""
+        for i in range(iters):
+            SEzz, SEz0, self.NA, self.logZ = self.update_states(X, T)
+            self.KLqprior_last = self.KLqprior()
+            self.update_markov_parms(SEzz, SEz0, lr=lr, beta=beta)
+            self.update_obs_parms(X, lr=lr, beta=beta)
+            ELBO = self.ELBO()
+            if verbose:
+                print('Percent Change in ELBO = ', ((ELBO - self.ELBO_last) / torch.abs(self.ELBO_last) * 100))
+            self.ELBO_last = ELBO
+
+    def KLqprior(self):
+        return self.obs_dist.KLqprior().sum(-1) + self.transition.KLqprior().sum(-1) + self.initial.KLqprior()
+
+    def ELBO(self):
+        return self.logZ - self.KLqprior()
+
+    def average(self, A, keepdim=False):
+        return (A * self.p).sum(-1, keepdim)
+
+    def event_average(self, A, keepdim=False):
+        out = (A * self.p.view(self.p.shape + (1,) * self.obs_dist.event_dim)).sum(-self.obs_dist.event_dim - 1, keepdim)
+        for i in range(self.event_dim - 1):
+            out = out.sum(-self.obs_dist.event_dim - 1, keepdim)
+        return out
+
+    def event_average_f(self, function_string, keepdim=False):
+        return self.event_average(getattr(self.obs_dist, function_string)(), keepdim)
+
+    def average_f(self, function_string, keepdim=False):
+        return self.average(getattr(self.obs_dist, function_string)(), keepdim)
+
+
+class ARHMM(HMM):
+    def __init__(self, dim, n, p, batch_shape=(), pad_X=True, X_mask=None, mask=None, transition_mask=None):
+        """models/ARHMM.py:14-16."""
+        dist = MatrixNormalWishart(event_shape=(n, p), batch_shape=batch_shape + (dim,), pad_X=pad_X,
+                                   X_mask=X_mask, mask=mask)
+        super().__init__(dist, transition_mask=transition_mask)
+
+    def obs_logits(self, XY, t=None):
+        """models/ARHMM.py:18-22."""
+        if t is not None:
+            return self.obs_dist.Elog_like(XY[0][t], XY[1][t])
+        return self.obs_dist.Elog_like(XY[0], XY[1])
+
+    def update_obs_parms(self, XY, lr, beta):
+        """models/ARHMM.py:24-25."""
+        self.obs_dist.raw_update(XY[0], XY[1], p=self.p, lr=lr, beta=beta)

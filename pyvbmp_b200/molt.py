@@ -1,0 +1,145 @@
+"""MixtureofLinearTransforms with the reference's interface for the raw-data VB-EM loop
+(transforms/MixtureofLinearTransforms.py:10-213, type='Wishart').  update_assignments is the fused
+K1 + K2 (softmax epilogue) sequence; the M-step is one weighted Gram pass + the MNW update kernel."""
+from __future__ import annotations
+
+import torch
+
+from . import _lib, _shapes, sharding
+from .dirichlet import Dirichlet
+from .mnw import MatrixNormalWishart
+
+
+def fused_update_assignments(self, X, Y):
+    """transforms/MixtureofLinearTransforms.py:34-41 on the CUDA path (also the install() method patch)."""
+    W = self.W
+    if not isinstance(W, MatrixNormalWishart) or self.batch_dim != 0 or W.event_dim != 2:
+        return generic_update_assignments(self, X, Y)
+    Xv, Yv = X.unsqueeze(-3), Y.unsqueeze(-3)
+    plan = W._plan(Xv)
+    dev = W.mu.device
+    Wt, m, cst, info, Dp = W._prep(plan, logprior=self.pi.loggeomean())
+    Xc, Yc = W._cols(Xv, Yv, plan)
+    p, logZn, NA, logZ = _lib.estep(Xc, Yc, plan.N, plan.GX, _shapes.idx_tensor(plan.xg, dev), Wt, m, cst,
+                                    plan.G, plan.K, Dp, 1)
+    self.p = p.view(plan.sample_shape + (plan.K,))
+    self.logZ = logZn.view(plan.sample_shape)          # per-sample log normaliser (:41)
+    self.NA = NA.view(plan.K)                          # = p.sum(0) for a single sample dim
+
+
+def generic_update_assignments(self, X, Y):
+    log_p = self.W.Elog_like(X.unsqueeze(-3), Y.unsqueeze(-3)) + self.pi.loggeomean()
+    self.logZ = torch.logsumexp(log_p, -1)
+    self.p = (log_p - self.logZ.unsqueeze(-1)).exp()
+    self.NA = None
+
+
+class MixtureofLinearTransforms():
+
+    def __init__(self, n, p, dim, batch_shape=(), pad_X=True, type='Wishart'):
+        """transforms/MixtureofLinearTransforms.py:12-32."""
+        self.n = n
+        self.p = p
+        self.dim = dim
+        self.event_dim = 1
+        self.event_shape = (dim,)
+        self.batch_dim = len(batch_shape)
+        self.batch_shape = batch_shape
+        if type != 'Wishart':
+            raise NotImplementedError("type='Gamma' (MatrixNormalGamma) is a 'next' row (SURVEY.md §8f #4)")
+        self.W = MatrixNormalWishart(event_shape=(n, p), batch_shape=batch_shape + (dim,),
+                                     scale=1.0 / dim ** (1.0 / n), pad_X=pad_X)
+        self.pi = Dirichlet(event_shape=(dim,), batch_shape=batch_shape)
+        self.KL_last = None
+        self.ELBO_last = -torch.tensor(torch.inf)
+
+    def to(self, device):
+        self.W.to(device)
+        self.pi.to(device)
+        self.ELBO_last = self.ELBO_last.to(device)
+        return self
+
+    update_assignments = fused_update_assignments
+
+    def raw_update(self, X, Y, iters=1, lr=1.0, verbose=False):
+        """transforms/MixtureofLinearTransforms.py:50-61."""
+        for i in range(iters):
+            self.update_assignments(X, Y)
+            NA = self.NA if (getattr(self, "NA", None) is not None and self.p.ndim == 2) else self.p.sum(0)
+            if sharding.enabled():
+                G, plan = self.W._gram(X.unsqueeze(-3), Y.unsqueeze(-3), self.p)
+                G, logZ_sum, NA = sharding.all_reduce_packed([G, self.logZ.sum(0), NA])
+                ELBO = logZ_sum - self.KLqprior()
+                self.pi.ss_update(NA, lr=lr)
+                self.W._update_from_gram(G, plan, True, lr)
+            else:
+                ELBO = self.ELBO()
+                self.pi.ss_update(NA, lr=lr)
+                self.W.raw_update(X.unsqueeze(-3), Y.unsqueeze(-3), p=self.p, lr=lr)
+            if verbose:
+                print('MixLinearTransform: Percent Change in ELBO = ', ((ELBO - self.ELBO_last) / self.ELBO_last.abs()).data * 100)
+            self.ELBO_last = ELBO
+
+    def update(self, pX, pY, iters=1, lr=1, verbose=False):
+        raise NotImplementedError("expectation-input update is a 'next' row (SURVEY.md §8f #2)")
+
+    def predict(self, X):
+        raise NotImplementedError("predict is a 'next' row (SURVEY.md §8f #3)")
+
+    def KLqprior(self):
+        return self.pi.KLqprior() + self.W.KLqprior().sum(-1)
+
+    def ELBO(self):
+        """transforms/MixtureofLinearTransforms.py:126-130."""
+        logZ = self.logZ.sum(0)
+        while logZ.ndim > self.batch_dim:
+            logZ = logZ.sum(0)
+        return logZ - self.KLqprior()
+
+    def assignment_pr(self):
+        return self.p
+
+    def assignment(self):
+        return self.p.argmax(-1)
+
+    def mean(self):
+        return self.p
+
+    def event_average(self, A):
+        p = self.p
+        for i in range(self.W.event_dim):
+            p = p.unsqueeze(-1)
+        out = (A * p)
+        for i in range(self.event_dim):
+            out = out.sum(-self.W.event_dim - 1)
+        return out
+
+    def average(self, A):
+        out = self.p * A
+        for i in range(self.event_dim):
+            out = out.sum(-1)
+        return out
+
+    def EinvUX(self):
+        return self.event_average(self.W.EinvUX())
+
+    def EXTinvU(self):
+        return self.event_average(self.W.EXTinvU())
+
+    def EXTinvUX(self):
+        return self.event_average(self.W.EXTinvUX())
+
+    def EinvSigma(self):
+        return self.event_average(self.W.EinvSigma())
+
+    def ESigma(self):
+        return self.event_average(self.W.ESigma())
+
+    def ElogdetinvSigma(self):
+        return self.average(self.W.ElogdetinvSigma())
+
+    def weights(self):
+        return self.W.weights()
+
+    def bias(self):
+        return self.W.bias()

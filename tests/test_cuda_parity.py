@@ -1,0 +1,335 @@
+"""GPU parity tests: the CUDA path (through the C ABI of libvbmp_b200.so) against
+(a) the committed golden fixtures produced by the UNMODIFIED reference, and
+(b) the CPU oracle on the same seeded inputs,
+at BASELINE.json's tolerance: ELBO and posterior parameters within 1e-4 relative (fp32), argmax
+assignments identical (any mismatch must sit inside the reference's own fp32 top-2 noise).
+Parameter parity is gated step-wise (state copied in before a single E+M step) and ELBO along the
+free-running trajectory, as SURVEY.md Appendix F.3 prescribes.
+"""
+import numpy as np
+import pytest
+import torch
+
+import pyvbmp_b200 as V
+from oracle import vbem_oracle as O
+from _util import load_golden, tag, relerr, assert_close, argmax_mismatch_report
+
+pytestmark = pytest.mark.gpu
+PARITY = 1e-4
+DEV = "cuda:0"
+
+
+def set_state(obj, flat, device=DEV):
+    """Write 'a.b.c' -> tensor entries of a golden state into a pyvbmp_b200 object graph."""
+    for k, v in flat.items():
+        parts = k.split(".")
+        o = obj
+        ok = True
+        for a in parts[:-1]:
+            if not hasattr(o, a):
+                ok = False
+                break
+            o = getattr(o, a)
+        if ok and hasattr(o, parts[-1]) and isinstance(v, torch.Tensor):
+            setattr(o, parts[-1], v.to(device))
+    return obj
+
+
+def get(obj, path):
+    for a in path.split("."):
+        obj = getattr(obj, a)
+    return obj
+
+
+NIW_STATE = ("dist.mu", "dist.lambda_mu", "dist.invU.invU", "dist.invU.U", "dist.invU.nu", "pi.alpha")
+
+
+@pytest.mark.parametrize("name", ["gmm_d2_k6", "gmm_d16_k8_lr05", "gmm_d64_k32_overlap", "gmm_moons_k20"])
+def test_gmm_golden(name):
+    fix = load_golden(name)
+    X = torch.as_tensor(fix["X"]).to(DEV)
+    nc, iters, lr = int(fix["nc"]), int(fix["iters"]), float(fix["lr"])
+    torch.manual_seed(0)
+    m = V.GaussianMixtureModel(nc, X.shape[-1]).to(DEV)
+    set_state(m, tag(fix, "init"))
+    # ---- step-wise gate: one E+M step from the reference's own initial state
+    m.update(X, 1, lr)
+    it1 = tag(fix, "iter1")
+    assert abs(float(m.ELBO_last) - fix["ELBO"][0]) <= PARITY * abs(fix["ELBO"][0])
+    assert_close(m.logZ, it1["logZ"], PARITY, "logZ")
+    assert_close(m.NA, it1["NA"], PARITY, "NA")
+    for k in NIW_STATE:
+        assert_close(get(m, k), it1[k], PARITY, k)
+    assert float((m.dist.invU.logdet_invU.cpu() - it1["dist.invU.logdet_invU"]).abs().max()) < 2e-3
+    assert_close(m.KLqprior(), it1["KL"], PARITY, "KL after step 1")
+    m.dist.invU.check()
+    if "p" in it1:
+        # iteration-1 logits are O(1e3) under the broad prior: the reference's own fp32 noise on p is ~2e-4
+        assert float((m.p.cpu() - it1["p"]).abs().max()) < 1e-3
+        nbad, margins = argmax_mismatch_report(m.p, it1["p"])
+        assert nbad == 0, (nbad, margins)
+    # ---- free-running trajectory: ELBO every iteration, assignments at the end
+    elbo = [float(m.ELBO_last)]
+    for _ in range(iters - 1):
+        m.update(X, 1, lr)
+        elbo.append(float(m.ELBO_last))
+    ref = fix["ELBO"]
+    assert np.max(np.abs(np.array(elbo) - ref) / np.abs(ref)) < PARITY, (elbo, ref)
+    agree = (m.assignment().cpu().numpy() == fix["final/assignment"]).mean()
+    assert agree > 0.999, agree
+    # ---- final-state E-step from the reference's final parameters: logits, p, argmax
+    set_state(m, tag(fix, "final"))
+    n_ll = fix["final/Elog_like"].shape[0]
+    ll = m.Elog_like(X[:n_ll]).cpu()
+    ref_ll = torch.as_tensor(fix["final/Elog_like"])
+    near = ref_ll > ref_ll.max(-1, keepdim=True)[0] - 30.0
+    assert float(((ll - ref_ll).abs() * near).max()) < 5e-3
+    assert_close(m.KLqprior(), fix["final/KL"], PARITY, "KL final")
+    if "final/p" in fix:
+        m.update_assignments(X)
+        assert float((m.p.cpu() - torch.as_tensor(fix["final/p"])).abs().max()) < 2e-4
+        nbad, margins = argmax_mismatch_report(m.p, fix["final/p"], ref_ll)
+        assert nbad == 0 or max(margins) < 1e-3, (nbad, margins)
+        assert_close(m.NA, fix["final/NA"], PARITY, "NA final")
+        assert_close(m.logZ, fix["final/logZ"], PARITY, "logZ final")
+
+
+def test_niw_beta_lr_steps():
+    fix = load_golden("niw_beta_lr")
+    torch.manual_seed(0)
+    s = V.NormalInverseWishart((3,), (4,), scale=0.7).to(DEV)
+    set_state(s, tag(fix, "init"))
+    for i in range(3):
+        s.raw_update(torch.as_tensor(fix[f"X{i}"]).to(DEV), torch.as_tensor(fix[f"p{i}"]).to(DEV), lr=0.6, beta=0.9)
+        ref = tag(fix, f"step{i}")
+        for k in ("mu", "lambda_mu", "invU.invU", "invU.U", "invU.nu", "SExx", "SEx", "N"):
+            assert_close(get(s, k), ref[k], PARITY, f"{k} step{i}")
+        assert float((s.invU.logdet_invU.cpu() - ref["invU.logdet_invU"]).abs().max()) < 1e-4
+    assert_close(s.KLqprior(), fix["final/KL"], PARITY, "KL")
+    assert_close(s.Elog_like(torch.as_tensor(fix["X2"]).to(DEV)), fix["final/Elog_like"], PARITY, "Elog_like")
+
+
+def test_niw_fixed_precision_pnone():
+    fix = load_golden("niw_fixed_precision_pnone")
+    torch.manual_seed(0)
+    s = V.NormalInverseWishart((3,), (2,), fixed_precision=True).to(DEV)
+    set_state(s, tag(fix, "init"))
+    s.raw_update(torch.as_tensor(fix["X"]).to(DEV), None, lr=1.0, beta=None)
+    ref = tag(fix, "final")
+    for k in ("mu", "lambda_mu", "invU.invU", "invU.nu"):
+        assert_close(get(s, k), ref[k], PARITY, k)
+    assert_close(s.KLqprior(), fix["final/KL"], PARITY, "KL")
+
+
+@pytest.mark.parametrize("name,batch,event,nc,iters", [
+    ("mixture_batch3_k6", (3, 6), (2,), 6, 4),
+    ("mixture_event32_k5", (5,), (3, 2), 5, 3),
+])
+def test_mixture_general_shapes(name, batch, event, nc, iters):
+    fix = load_golden(name)
+    X = torch.as_tensor(fix["X"]).to(DEV)
+    torch.manual_seed(0)
+    m = V.Mixture(V.NormalInverseWishart(event, batch, scale=0.5), (nc,)).to(DEV)
+    set_state(m, tag(fix, "init"))
+    el = []
+    for _ in range(iters):
+        m.update(X, 1)
+        el.append(m.ELBO_last.cpu().numpy())
+    el = np.stack(el)
+    assert np.max(np.abs(el - fix["ELBO"]) / np.abs(fix["ELBO"])) < PARITY
+    fin = tag(fix, "final")
+    assert m.p.shape == fin["p"].shape and m.NA.shape == fin["NA"].shape and m.logZ.shape == fin["logZ"].shape
+    assert float((m.p.cpu() - fin["p"]).abs().max()) < 2e-4
+    assert_close(m.NA, fin["NA"], 2e-4, "NA")
+    for k in ("dist.mu", "dist.lambda_mu", "dist.invU.nu", "pi.alpha"):
+        assert get(m, k).shape == fin[k].shape, k
+        assert_close(get(m, k), fin[k], 1e-3, k)     # free-running, SURVEY F.3
+
+
+def test_niw_hmm_emission_sample_shape_ts():
+    fix = load_golden("niw_hmm_emission_ts")
+    torch.manual_seed(0)
+    s = V.NormalInverseWishart((2,), (4,)).to(DEV)
+    set_state(s, tag(fix, "init"))
+    X, p = torch.as_tensor(fix["X"]).unsqueeze(-2).to(DEV), torch.as_tensor(fix["p"]).to(DEV)
+    ll = s.Elog_like(X)
+    assert ll.shape == (12, 9, 4)
+    assert_close(ll, fix["init/Elog_like"], PARITY, "Elog_like init")
+    s.raw_update(X, p)
+    ref = tag(fix, "final")
+    for k in ("mu", "lambda_mu", "invU.invU", "invU.U", "invU.nu"):
+        assert_close(get(s, k), ref[k], PARITY, k)
+    assert_close(s.Elog_like(X), fix["final/Elog_like"], PARITY, "Elog_like final")
+    assert_close(s.KLqprior(), fix["final/KL"], PARITY, "KL")
+
+
+MNW_STATE = ("mu", "invV", "V", "invU.invU", "invU.U", "invU.nu")
+
+
+@pytest.mark.parametrize("pad", [1, 0])
+def test_mnw_steps(pad):
+    fix = load_golden(f"mnw_n4_p5_k3_pad{pad}")
+    n, p, K = int(fix["n"]), int(fix["p"]), int(fix["K"])
+    torch.manual_seed(0)
+    s = V.MatrixNormalWishart((n, p), (K,), scale=0.8, pad_X=bool(pad)).to(DEV)
+    set_state(s, tag(fix, "init"))
+    X, Y, r = (torch.as_tensor(fix[k]).to(DEV) for k in ("X", "Y", "r"))
+    assert_close(s.Elog_like(X, Y), fix["init/Elog_like"], PARITY, "Elog_like init")
+    assert_close(s.KLqprior(), fix["init/KL"], PARITY, "KL init")
+    s.raw_update(X, Y, p=r, lr=1.0, beta=None)
+    ref = tag(fix, "step0")
+    for k in MNW_STATE:
+        assert_close(get(s, k), ref[k], PARITY, k + " step0")
+    assert float((s.logdetinvV.cpu() - ref["logdetinvV"]).abs().max()) < 1e-4
+    assert_close(s.Elog_like(X, Y), fix["step0/Elog_like"], PARITY, "Elog_like step0")
+    assert_close(s.KLqprior(), fix["step0/KL"], PARITY, "KL step0")
+    s.raw_update(X, Y, p=r, lr=0.5, beta=0.8)
+    if not pad:
+        s.raw_update(X, Y, p=None, lr=0.5, beta=0.8)
+    ref = tag(fix, "step2")
+    for k in MNW_STATE + ("SExx", "SEyx", "SEyy", "N"):
+        assert_close(get(s, k), ref[k], PARITY, k + " step2")
+    assert_close(s.KLqprior(), fix["step2/KL"], PARITY, "KL step2")
+
+
+@pytest.mark.parametrize("name", ["molt_n3_p4_k5", "molt_n32_p32_k8"])
+def test_molt_golden(name):
+    fix = load_golden(name)
+    n, p, K, iters = (int(fix[k]) for k in ("n", "p", "K", "iters"))
+    torch.manual_seed(0)
+    m = V.MixtureofLinearTransforms(n, p, K).to(DEV)
+    set_state(m, tag(fix, "init"))
+    X, Y = torch.as_tensor(fix["X"]).unsqueeze(-1).to(DEV), torch.as_tensor(fix["Y"]).unsqueeze(-1).to(DEV)
+    m.raw_update(X, Y, iters=1)
+    it1 = tag(fix, "iter1")
+    assert abs(float(m.ELBO_last) - fix["ELBO"][0]) <= PARITY * abs(fix["ELBO"][0])
+    assert m.p.shape == it1["p"].shape and m.logZ.shape == it1["logZ"].shape
+    assert float((m.p.cpu() - it1["p"]).abs().max()) < 5e-4
+    assert_close(m.logZ, it1["logZ"], PARITY, "logZ_n")
+    for k in ("W.mu", "W.invV", "W.V", "W.invU.invU", "W.invU.U", "W.invU.nu", "pi.alpha"):
+        assert_close(get(m, k), it1[k], PARITY, k)
+    elbo = [float(m.ELBO_last)]
+    for _ in range(iters - 1):
+        m.raw_update(X, Y, iters=1)
+        elbo.append(float(m.ELBO_last))
+    assert np.max(np.abs(np.array(elbo) - fix["ELBO"]) / np.abs(fix["ELBO"])) < PARITY
+    assert (m.assignment().cpu().numpy() == fix["final/assignment"]).mean() > 0.995
+    set_state(m, tag(fix, "final"))
+    assert_close(m.KLqprior(), fix["final/KL"], PARITY, "KL final")
+    m.update_assignments(X, Y)
+    assert float((m.p.cpu() - torch.as_tensor(fix["final/p"])).abs().max()) < 2e-4
+    nbad, margins = argmax_mismatch_report(m.p, fix["final/p"])
+    assert nbad == 0 or max(margins) < 1e-3, (nbad, margins)
+
+
+def test_arhmm_golden():
+    fix = load_golden("arhmm_k4_n2_p3")
+    K, n, p = int(fix["K"]), int(fix["n"]), int(fix["p"])
+    torch.manual_seed(0)
+    h = V.ARHMM(K, n, p).to(DEV)
+    set_state(h, {k.replace("obs.", "obs_dist."): v for k, v in tag(fix, "init").items()})
+    X, Y = torch.as_tensor(fix["X"]).to(DEV), torch.as_tensor(fix["Y"]).to(DEV)
+    ol = h.obs_logits((X, Y))
+    assert ol.shape == fix["init/obs_logits"].shape
+    assert_close(ol, fix["init/obs_logits"], PARITY, "obs_logits")
+    h.update((X, Y), iters=1)
+    it1 = tag(fix, "iter1")
+    assert float((h.p.cpu() - it1["p"]).abs().max()) < 2e-4
+    assert_close(h.logZ, it1["logZ"], PARITY, "logZ")
+    assert_close(h.NA, it1["NA"], PARITY, "NA")
+    for k in ("obs.mu", "obs.invV", "obs.V", "obs.invU.invU", "obs.invU.U", "transition.alpha", "initial.alpha"):
+        assert_close(get(h, k.replace("obs.", "obs_dist.")), it1[k], PARITY, k)
+    elbo = [float(h.ELBO_last)]
+    for _ in range(3):
+        h.update((X, Y), iters=1)
+        elbo.append(float(h.ELBO_last))
+    assert np.max(np.abs(np.array(elbo) - fix["ELBO"]) / np.abs(fix["ELBO"])) < PARITY
+
+
+# -------------------------------------------------------------------------------------------------
+# config-2 shape (d=64, K=256) against the fp64 oracle, overlapping-clusters variant
+# -------------------------------------------------------------------------------------------------
+
+def _cfg2_data(N, K=256, d=64, sep=0.3, seed=1234):
+    g = torch.Generator().manual_seed(seed)
+    mu = sep * torch.randn(K, d, generator=g)
+    A = torch.eye(d) + 0.3 * torch.randn(K, d, d, generator=g) / 8
+    z = torch.randint(K, (N,), generator=g)
+    X = mu[z] + torch.einsum("nij,nj->ni", A[z], torch.randn(N, d, generator=g))
+    return X
+
+
+@pytest.mark.parametrize("sep", [0.3, 3.0])
+def test_gmm_cfg2_shape_vs_fp64_oracle(sep):
+    N, K, d = 8192, 256, 64
+    X = _cfg2_data(N, K, d, sep)
+    torch.manual_seed(7)
+    m = V.GaussianMixtureModel(K, d)
+    m.initialize(X)
+    ref = O.gmm_new(K, d)
+    O.load_state(ref, {"dist.mu": m.dist.mu.clone(), "pi.alpha": m.pi.alpha.clone()})
+    O.to_dtype(ref, torch.float64)
+    m.to(DEV)
+    Xd, X64 = X.to(DEV), X.double()
+    for it in range(3):
+        # step-wise: copy the oracle's state in (fp32), one E+M step on both
+        flat = {k: v.float() for k, v in O.flatten_state(ref).items()}
+        set_state(m, flat)
+        m.update(Xd, 1)
+        tr = O.mixture_update(ref, X64, 1, exact=False, chunk=2048)
+        assert abs(float(m.ELBO_last) - float(tr[0])) <= PARITY * abs(float(tr[0])), it
+        p_ref = ref["p"]
+        assert float((m.p.cpu().double() - p_ref).abs().max()) < 2e-4, it
+        nbad, margins = argmax_mismatch_report(m.p, p_ref, ref["log_p"])
+        assert nbad == 0 or max(margins) < 1e-3, (it, nbad, margins)
+        assert_close(m.NA, ref["NA"], PARITY, "NA")
+        for k in NIW_STATE:
+            assert_close(get(m, k), O.flatten_state(ref)[k], PARITY, f"{k} it{it}")
+        m.dist.invU.check()
+
+
+# -------------------------------------------------------------------------------------------------
+# size-independent properties at large N (no oracle needed)
+# -------------------------------------------------------------------------------------------------
+
+def test_large_n_properties():
+    N, K, d = 1 << 20, 64, 32
+    g = torch.Generator(device=DEV).manual_seed(5)
+    X = torch.randn(N, d, generator=g, device=DEV) * 1.5 + 0.5
+    torch.manual_seed(3)
+    m = V.GaussianMixtureModel(K, d)
+    m.initialize(X.cpu()[:4096])
+    m.to(DEV)
+    m.update(X, 2)
+    m.update_assignments(X)
+    # responsibilities are a distribution; NA and logZ are their reductions
+    rs = m.p.sum(-1)
+    assert float((rs - 1).abs().max()) < 1e-5
+    assert abs(float(m.NA.sum()) - N) < 1e-3 * N / 1000
+    assert_close(m.NA, m.p.double().sum(0), 1e-6, "NA vs p.sum")
+    # E-step of a concatenation = concatenation of E-steps (chunk independence)
+    p_full = m.p.clone()
+    m.update_assignments(X[: N // 2 + 12345])
+    assert torch.equal(m.p, p_full[: N // 2 + 12345])
+    # Gram linearity in the weights and exactness against an fp64 matmul on a slice
+    dist = m.dist
+    Xv = X.view(N, 1, d)
+    r1 = torch.rand(N, K, generator=g, device=DEV)
+    r2 = torch.rand(N, K, generator=g, device=DEV)
+    from pyvbmp_b200 import _lib, _shapes
+    plan = dist._plan(Xv)
+    xg, pg = _shapes.idx_tensor(plan.xg, X.device), _shapes.idx_tensor(plan.pg, X.device)
+
+    def G(r):
+        return _lib.gram(X.view(N, 1, d), None, N, 1, xg, r.view(N, 1, K).contiguous(), 1, pg, 1, K, _lib.pad_dim(d))
+    G1, G2, G12 = G(r1), G(r2), G(r1 + r2)
+    assert relerr(G1 + G2, G12) < 5e-6
+    Z1 = torch.cat([X, torch.ones(N, 1, device=DEV)], -1).double()
+    ref0 = torch.einsum("n,ni,nj->ij", r1[:, 0].double(), Z1, Z1)
+    assert relerr(G1[0, 0], ref0) < 2e-6
+    # centred scatter (the cancellation of NormalInverseWishart.py:63) stays at fp32 noise
+    Nk, Sx, Sxx = ref0[d, d], ref0[:d, d], ref0[:d, :d]
+    S_ref = Sxx - torch.outer(Sx, Sx) / Nk
+    g0 = G1[0, 0].double()
+    S_got = g0[:d, :d] - torch.outer(g0[:d, d], g0[:d, d]) / g0[d, d]
+    assert relerr(S_got, S_ref) < 2e-5
