@@ -45,3 +45,11 @@ def argmax_mismatch_report(p_ours, p_ref, logits_ref=None):
         top = row.topk(2).values
         margins.append(float(top[0] - top[1]))
     return len(bad), margins
+
+
+def assert_maxabs(a, b, tol, what=""):
+    a = torch.as_tensor(a).double().cpu()
+    b = torch.as_tensor(b).double().cpu()
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    e = float((a - b).abs().max()) if a.numel() else 0.0
+    assert e <= tol, f"{what}: max abs err {e:.3e} > {tol:.1e}"
