@@ -1,0 +1,311 @@
+// tools/umma_probe.cu — standalone B200 probe for the tcgen05 building blocks in pyvbmp_b200/csrc/umma.cuh.
+//   (1) correctness of kind::tf32 MMAs with K-major / SWIZZLE_NONE shared-memory operands (SS) and with the
+//       A operand resident in TMEM (TS), for several N and several K-steps (descriptor advance), operands
+//       brought in by cp.async.bulk;
+//   (2) issue-rate microbenchmarks: cycles per MMA for SS / TS and N in {64,...,256} on one SM and on all SMs.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o tools/umma_probe tools/umma_probe.cu
+#include <cstdio>
+#include <cstdlib>
+#include <cmath>
+#include <cstring>
+#include <vector>
+#include "../pyvbmp_b200/csrc/umma.cuh"
+
+using namespace umma;
+
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(2); } } while (0)
+
+// A: [128][K] row-major, B: [N][K] row-major (both already TF32-representable), D: [128][N]
+__global__ void __launch_bounds__(128, 1) probe_kernel(const float* __restrict__ A, const float* __restrict__ Bp,
+                                                        float* __restrict__ D, int N, int K, int ts_mode) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar_b, bar_mma;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  float* As = reinterpret_cast<float*>(smem);                     // K-major core-matrix layout, LBO = 128*16
+  float* Bs = reinterpret_cast<float*>(smem + 128 * K * 4);       // Bp is already packed in that layout: LBO = N*16
+  if (tid == 0) { mbar_init(&bar_b, 1); mbar_init(&bar_mma, 1); fence_barrier_init(); }
+  if (warp == 0) tmem_alloc<512>(&tmem_base_s);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tm = tmem_base_s;
+  // B via bulk copy (packed layout prepared on the host)
+  if (tid == 0) {
+    mbar_arrive_expect_tx(&bar_b, (uint32_t)(N * K * 4));
+    bulk_g2s(Bs, Bp, (uint32_t)(N * K * 4), &bar_b);
+  }
+  // A: row per thread
+  if (!ts_mode) {
+    for (int k = 0; k < K; ++k) As[(k >> 2) * (128 * 4) + tid * 4 + (k & 3)] = A[tid * K + k];
+    fence_proxy_async();
+  } else {
+    for (int k0 = 0; k0 < K; k0 += 8) {
+      uint32_t r[8];
+      for (int j = 0; j < 8; ++j) r[j] = __float_as_uint(A[tid * K + k0 + j]);
+      tmem_st8(tm + ((uint32_t)(warp * 32) << 16) + 256 + k0, r);
+    }
+    tmem_wait_st();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (tid == 0) {
+    mbar_wait(&bar_b, 0);
+    const uint32_t idesc = idesc_tf32(128, N);
+    for (int ks = 0; ks < K / 8; ++ks) {
+      const uint64_t bd = smem_desc(smem_u32(Bs) + ks * 2 * (N * 16), N * 16, 128);
+      if (!ts_mode) {
+        const uint64_t ad = smem_desc(smem_u32(As) + ks * 2 * (128 * 16), 128 * 16, 128);
+        mma_tf32_ss(tm, ad, bd, idesc, ks > 0);
+      } else {
+        mma_tf32_ts(tm, tm + 256 + ks * 8, bd, idesc, ks > 0);
+      }
+    }
+    mma_commit(&bar_mma);
+  }
+  mbar_wait(&bar_mma, 0);
+  tc_fence_after();
+  for (int c0 = 0; c0 < N; c0 += 16) {
+    float v[16];
+    tmem_ld16(tm + ((uint32_t)(warp * 32) << 16) + c0, v);
+    tmem_wait_ld();
+    for (int j = 0; j < 16; ++j) D[(size_t)tid * N + c0 + j] = v[j];
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tm);
+}
+
+// Issue-rate benchmark: every CTA issues iters*8 MMAs (K=64 worth of K-steps, operands fixed in smem / TMEM).
+__global__ void __launch_bounds__(128, 1) rate_kernel(int N, int iters, int ts_mode, int alt_d, long long* cycles) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar_mma;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  float* As = reinterpret_cast<float*>(smem);                  // 128 x 64
+  float* Bs = reinterpret_cast<float*>(smem + 128 * 64 * 4);   // N x 64
+  for (int e = tid; e < 128 * 64 + N * 64; e += 128) As[e] = (float)((e * 37) % 7 - 3);
+  fence_proxy_async();
+  if (tid == 0) { mbar_init(&bar_mma, 1); fence_barrier_init(); }
+  if (warp == 0) tmem_alloc<512>(&tmem_base_s);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tm = tmem_base_s;
+  if (ts_mode) {
+    uint32_t r[16];
+    for (int j = 0; j < 16; ++j) r[j] = __float_as_uint((float)(j - 8));
+    for (int c = 0; c < 64; c += 16) tmem_st16(tm + ((uint32_t)(warp * 32) << 16) + 448 + c, r);
+    tmem_wait_st();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (tid == 0) {
+    const uint32_t idesc = idesc_tf32(128, N);
+    const uint64_t bd0 = smem_desc(smem_u32(Bs), N * 16, 128);
+    const uint64_t ad0 = smem_desc(smem_u32(As), 128 * 16, 128);
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+      const uint32_t d = tm + ((alt_d && (it & 1)) ? (uint32_t)N : 0u);
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) {
+        const uint64_t bd = bd0 + (uint64_t)((ks * 2 * N * 16) >> 4);
+        if (!ts_mode) mma_tf32_ss(d, ad0 + (uint64_t)((ks * 2 * 128 * 16) >> 4), bd, idesc, 1);
+        else mma_tf32_ts(d, tm + 448 + ks * 8, bd, idesc, 1);
+      }
+    }
+    mma_commit(&bar_mma);
+    mbar_wait(&bar_mma, 0);
+    const long long t1 = clock64();
+    cycles[blockIdx.x] = t1 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tm);
+}
+
+
+// nchain independent accumulators, interleaved at MMA granularity (is the ~94-cycle floor a dependent-accumulate latency?)
+template <bool TS, int NCHAIN>
+__global__ void __launch_bounds__(128, 1) chain_kernel(int N, int iters, long long* cycles) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar_mma;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  float* As = reinterpret_cast<float*>(smem);
+  float* Bs = reinterpret_cast<float*>(smem + 128 * 64 * 4);
+  for (int e = tid; e < 128 * 64 + N * 64; e += 128) As[e] = (float)((e * 37) % 7 - 3);
+  fence_proxy_async();
+  if (tid == 0) { mbar_init(&bar_mma, 1); fence_barrier_init(); }
+  if (warp == 0) tmem_alloc<512>(&tmem_base_s);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tm = tmem_base_s;
+  if (warp == 1) {
+    const uint32_t idesc = idesc_tf32(128, N);
+    const uint64_t bd0 = smem_desc(smem_u32(Bs), N * 16, 128);
+    const uint64_t ad0 = smem_desc(smem_u32(As), 128 * 16, 128);
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) {
+        const uint64_t bd = bd0 + (uint64_t)((ks * 2 * N * 16) >> 4);
+#pragma unroll
+        for (int c = 0; c < NCHAIN; ++c) {
+          const uint32_t d = tm + (uint32_t)(c * N);
+          if (elect_one()) {
+            if (!TS) mma_tf32_ss(d, ad0 + (uint64_t)((ks * 2 * 128 * 16) >> 4), bd, idesc, 1);
+            else mma_tf32_ts(d, tm + 448 + ks * 8, bd, idesc, 1);
+          }
+        }
+      }
+    }
+    if (elect_one()) mma_commit(&bar_mma);
+    __syncwarp();
+    mbar_wait(&bar_mma, 0);
+    const long long t1 = clock64();
+    if ((tid & 31) == 0) cycles[blockIdx.x] = t1 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tm);
+}
+
+template <bool TS, int NCHAIN>
+static void run_chain_t(int N, int grid) {
+  const int iters = 1000;
+  long long* dc; CK(cudaMalloc(&dc, grid * sizeof(long long)));
+  const size_t smem = (size_t)(128 + N) * 64 * 4;
+  CK(cudaFuncSetAttribute(chain_kernel<TS, NCHAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  chain_kernel<TS, NCHAIN><<<grid, 128, smem>>>(N, 100, dc);
+  CK(cudaDeviceSynchronize());
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  cudaEventRecord(e0);
+  chain_kernel<TS, NCHAIN><<<grid, 128, smem>>>(N, iters, dc);
+  cudaEventRecord(e1);
+  CK(cudaDeviceSynchronize());
+  float ms; cudaEventElapsedTime(&ms, e0, e1);
+  std::vector<long long> c(grid);
+  CK(cudaMemcpy(c.data(), dc, grid * sizeof(long long), cudaMemcpyDeviceToHost));
+  long long mx = 0; for (auto v : c) if (v > mx) mx = v;
+  const double flops = 2.0 * 128 * N * 8 * iters * 8.0 * NCHAIN * grid;
+  printf("chain %s N=%3d nchain=%d grid=%3d : %.1f cycles/MMA (ideal %.0f)  %.1f TFLOP/s\n", TS ? "TS" : "SS", N, NCHAIN, grid,
+         (double)mx / (iters * 8.0 * NCHAIN), N / 2.0, flops / ms / 1e9);
+  cudaFree(dc);
+}
+static void run_chain(int N, int ts_mode, int nchain, int grid) {
+  if (ts_mode) { if (nchain == 1) run_chain_t<true, 1>(N, grid); else if (nchain == 2) run_chain_t<true, 2>(N, grid); else if (nchain == 3) run_chain_t<true, 3>(N, grid); else run_chain_t<true, 4>(N, grid); }
+  else { if (nchain == 1) run_chain_t<false, 1>(N, grid); else if (nchain == 2) run_chain_t<false, 2>(N, grid); else if (nchain == 3) run_chain_t<false, 3>(N, grid); else run_chain_t<false, 4>(N, grid); }
+}
+static float tf32_exact(int v) { return (float)v; }
+
+static int run_case(int N, int K, int ts_mode) {
+  std::vector<float> A(128 * K), B(N * K), Bp(N * K), D(128 * N), R(128 * N);
+  for (int i = 0; i < 128 * K; ++i) A[i] = tf32_exact((rand() % 17) - 8);
+  for (int i = 0; i < N * K; ++i) B[i] = tf32_exact((rand() % 13) - 6);
+  for (int n = 0; n < N; ++n)
+    for (int k = 0; k < K; ++k) Bp[(k >> 2) * (N * 4) + n * 4 + (k & 3)] = B[n * K + k];
+  for (int m = 0; m < 128; ++m)
+    for (int n = 0; n < N; ++n) {
+      double s = 0;
+      for (int k = 0; k < K; ++k) s += (double)A[m * K + k] * B[n * K + k];
+      R[m * N + n] = (float)s;
+    }
+  float *dA, *dB, *dD;
+  CK(cudaMalloc(&dA, A.size() * 4)); CK(cudaMalloc(&dB, Bp.size() * 4)); CK(cudaMalloc(&dD, D.size() * 4));
+  CK(cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dB, Bp.data(), Bp.size() * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemset(dD, 0xff, D.size() * 4));
+  const size_t smem = (size_t)(128 + N) * K * 4;
+  CK(cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  probe_kernel<<<1, 128, smem>>>(dA, dB, dD, N, K, ts_mode);
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost));
+  int bad = 0; double maxerr = 0;
+  for (int i = 0; i < 128 * N; ++i) { double e = fabs((double)D[i] - R[i]); if (e > maxerr) maxerr = e; if (e > 1e-3) ++bad; }
+  printf("probe %s N=%3d K=%3d : %s (mismatches %d / %d, max err %.3g)  D[0..3]=%g %g %g %g ref %g %g %g %g\n",
+         ts_mode ? "TS" : "SS", N, K, bad ? "FAIL" : "ok", bad, 128 * N, maxerr, D[0], D[1], D[2], D[3], R[0], R[1], R[2], R[3]);
+  cudaFree(dA); cudaFree(dB); cudaFree(dD);
+  return bad != 0;
+}
+
+static void run_rate(int N, int ts_mode, int alt_d, int grid) {
+  const int iters = 2000;
+  long long* dc; CK(cudaMalloc(&dc, grid * sizeof(long long)));
+  const size_t smem = (size_t)(128 + N) * 64 * 4;
+  CK(cudaFuncSetAttribute(rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  rate_kernel<<<grid, 128, smem>>>(N, 200, ts_mode, alt_d, dc);   // warm
+  CK(cudaDeviceSynchronize());
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  cudaEventRecord(e0);
+  rate_kernel<<<grid, 128, smem>>>(N, iters, ts_mode, alt_d, dc);
+  cudaEventRecord(e1);
+  CK(cudaDeviceSynchronize());
+  float ms; cudaEventElapsedTime(&ms, e0, e1);
+  std::vector<long long> c(grid);
+  CK(cudaMemcpy(c.data(), dc, grid * sizeof(long long), cudaMemcpyDeviceToHost));
+  long long mx = 0; for (auto v : c) if (v > mx) mx = v;
+  const double per = (double)mx / (iters * 8.0);
+  const double flops = 2.0 * 128 * N * 8 * iters * 8.0 * grid;
+  printf("rate %s N=%3d alt_d=%d grid=%3d : %.1f cycles/MMA (ideal %.0f), %.3f ms -> %.1f TFLOP/s (tf32 issued)\n",
+         ts_mode ? "TS" : "SS", N, alt_d, grid, per, N / 2.0, ms, flops / ms / 1e9);
+  cudaFree(dc);
+}
+
+
+// Does kind::tf32 truncate or round fp32 operands whose low 13 mantissa bits are set?
+static void run_trunc_test() {
+  const int N = 64, K = 8;
+  std::vector<float> A(128 * K), B(N * K), Bp(N * K), D(128 * N);
+  for (auto& v : A) v = 1.0f + (float)(rand() % 8191) / 8388608.0f * 1.0f + (float)(rand() % 1000) / 1000.0f;   // low bits set
+  for (int i = 0; i < N * K; ++i) B[i] = (i % K == (i / K) % K) ? 1.0f : 0.0f;                                  // picks A[m][n % 8]
+  for (int n = 0; n < N; ++n)
+    for (int k = 0; k < K; ++k) Bp[(k >> 2) * (N * 4) + n * 4 + (k & 3)] = B[n * K + k];
+  float *dA, *dB, *dD;
+  CK(cudaMalloc(&dA, A.size() * 4)); CK(cudaMalloc(&dB, Bp.size() * 4)); CK(cudaMalloc(&dD, D.size() * 4));
+  CK(cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dB, Bp.data(), Bp.size() * 4, cudaMemcpyHostToDevice));
+  const size_t smem = (size_t)(128 + N) * K * 4;
+  for (int ts = 0; ts < 2; ++ts) {
+    probe_kernel<<<1, 128, smem>>>(dA, dB, dD, N, K, ts);
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost));
+    int n_trunc = 0, n_rna = 0, n_exact = 0, n_other = 0;
+    for (int m = 0; m < 128; ++m)
+      for (int n = 0; n < 8; ++n) {
+        const float a = A[m * K + n];
+        uint32_t b; memcpy(&b, &a, 4);
+        uint32_t t = b & 0xffffe000u, r = (b + 0x1000u) & 0xffffe000u;
+        float ft, fr; memcpy(&ft, &t, 4); memcpy(&fr, &r, 4);
+        const float d = D[m * N + n];
+        if (d == a) ++n_exact; else if (d == ft && ft != fr) ++n_trunc; else if (d == fr && ft != fr) ++n_rna; else if (d == ft) ++n_trunc; else ++n_other;
+      }
+    printf("operand low-bit handling (%s): exact %d, truncated %d, rounded %d, other %d\n", ts ? "A in TMEM" : "A in smem", n_exact, n_trunc, n_rna, n_other);
+  }
+  cudaFree(dA); cudaFree(dB); cudaFree(dD);
+}
+
+int main(int argc, char** argv) {
+  srand(1);
+  int fails = 0;
+  if (argc > 1 && atoi(argv[1]) == 3) { run_trunc_test(); return 0; }
+  if (argc > 1 && atoi(argv[1]) == 2) {
+    for (int ts = 0; ts < 2; ++ts)
+      for (int N : {16, 32, 48, 64, 96, 128, 192})
+        for (int nc : {1, 2, 3, 4}) if (nc * N <= 448) run_chain(N, ts, nc, 148);
+    return 0;
+  }
+  for (int ts = 0; ts < 2; ++ts)
+    for (int N : {64, 96, 192, 256})
+      for (int K : {8, 32, 64}) fails += run_case(N, K, ts);
+  for (int ts = 0; ts < 2; ++ts)
+    for (int N : {64, 96, 128, 192, 256}) { run_rate(N, ts, 0, 1); }
+  for (int ts = 0; ts < 2; ++ts)
+    for (int N : {64, 96, 128, 192, 256}) { run_rate(N, ts, 0, 148); run_rate(N, ts, 1, 148); }
+  printf("probe done: %d failing cases\n", fails);
+  return fails ? 1 : 0;
+}
