@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvbmp_b200.so")
 _lib = None
 
-FORCE_SIMT = int(os.environ.get("VBMP_FORCE_SIMT", "0"))   # tests flip this to pin the CUDA-core kernels
+FORCE_SIMT = int(os.environ.get("VBMP_FORCE_SIMT", "0"))   # tests: 1 = CUDA-core kernels for both, 2 = E-step only, 3 = Gram only
 
 
 PROFILE = None     # bench.py sets this to {} to collect (start, end) CUDA events per C-ABI call
@@ -162,7 +162,7 @@ def estep(z0, z1, N, GX, xg, W, m, cst, G, K, Dp, mode, out=None):
     ws = _workspace(nbytes, dev)
     _call("vbmp_estep", _ptr(z0), c_int(d0), _ptr(z1), c_int(d1), c_longlong(N), c_int(GX), _ptr(xg),
                             _ptr(W), _ptr(m), _ptr(cst), c_int(G), c_int(K), c_int(Dp), c_int(mode),
-                            c_int(1 if FORCE_SIMT else 0), _ptr(out), _ptr(logZn), _ptr(NA), _ptr(logZ),
+                            c_int(1 if FORCE_SIMT in (1, 2) else 0), _ptr(out), _ptr(logZn), _ptr(NA), _ptr(logZ),
                             _ptr(ws), c_size_t(ws.numel()), _stream(dev))
     if mode == 0:
         return out
@@ -180,7 +180,7 @@ def gram(z0, z1, N, GX, xg, p, GP, pg, G, K, Dp):
     ws = _workspace(nbytes, dev)
     _call("vbmp_gram", _ptr(z0), c_int(d0), _ptr(z1), c_int(d1), c_longlong(N), c_int(GX), _ptr(xg),
                            _ptr(p), c_int(GP), _ptr(pg), c_int(G), c_int(K), c_int(Dp),
-                           c_int(1 if FORCE_SIMT else 0), _ptr(out), _ptr(ws), c_size_t(ws.numel()),
+                           c_int(1 if FORCE_SIMT in (1, 3) else 0), _ptr(out), _ptr(ws), c_size_t(ws.numel()),
                            _stream(dev))
     return out
 

@@ -7,19 +7,22 @@
 //
 // Design (numbers from tools/umma_probe.cu on a B200, see umma.cuh):
 //   * persistent CTA per SM, 256-sample tiles (two 128-row halves).  The sample tile is the A operand and
-//     lives in TENSOR MEMORY as split-precision TF32 (z = hi + lo): with A in TMEM an M=128 x N=64 x K=8
-//     MMA issues every N/2 cycles, whereas a shared-memory A costs 32 extra cycles of operand fetch.
-//   * the whitening factors are the B operand: one 64-column group (64/DP components) per pipeline stage,
-//     pre-split into hi / lo TF32 and pre-arranged in the K-major core-matrix layout by a pack kernel, so a
-//     stage is ONE cp.async.bulk.  Each stage is used by both halves (6 MMAs per K-step:
-//     hi*hi + lo*hi + hi*lo per half), which halves the L2 -> shared-memory stream per flop.
-//   * W_k is upper triangular, so for DP = 64 K-step ks only feeds output columns >= 16*(ks/2): the MMA is
-//     issued with N = 64 - 16*(ks/2) on the column suffix and only that suffix of B is stored / copied
-//     (62.5 % of the dense work).
-//   * accumulators D[half][buf] (64 fp32 columns each) are double buffered in TMEM; 8 epilogue warps (one
-//     thread per sample row) read them with tcgen05.ld, subtract m_k, square-reduce, keep an online
-//     logsumexp and write the logits.  For mode 1 the tile's rows are then normalised in place (the re-read
-//     hits L2) with coalesced float4 accesses, accumulating NA per CTA in a fixed order (deterministic).
+//     lives in TENSOR MEMORY as split-precision TF32 (z = hi + lo): with A in TMEM an M=128 x N x K=8 MMA
+//     issues every N/2 cycles, whereas a shared-memory A costs 32 extra cycles of operand fetch.
+//   * the whitening factors are the B operand: one 128-column group (CG = 128/DP components) per pipeline
+//     stage, pre-split into hi / lo TF32 and pre-arranged in the K-major core-matrix layout by a pack kernel,
+//     so a stage (plus the group's m and cst) is ONE cp.async.bulk.  Each stage is used by both halves
+//     (hi*hi + lo*hi + hi*lo per half and K-step), which halves the L2 -> shared-memory stream per flop.
+//   * W_k is upper triangular.  The group's columns are interleaved in 8-column blocks,
+//     n = (j/8)*(8 CG) + cl*8 + j%8, so the columns K-step ks can reach (j >= 8 ks) are the contiguous suffix
+//     n >= 8 CG ks: the MMA is issued with N = 128 - 8 CG ks on that suffix and only that suffix of B is
+//     stored / copied (56 % of the dense work at DP = 64).
+//   * one 128-column accumulator per half in TMEM; the halves ping-pong (the epilogue of half 0 runs under the
+//     MMAs of half 1).  8 epilogue warps (one thread per sample row) read D with tcgen05.ld, add -m_k and
+//     square-reduce with packed fp32x2 FADD2 / FFMA2, keep an online logsumexp and write the logits.  For mode 1 the tile's rows are then
+//     normalised in place (the re-read hits L2) with coalesced float4 accesses, accumulating NA per CTA in a
+//     fixed order (deterministic).
+#include <cstdlib>
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -28,16 +31,16 @@ using namespace umma;
 
 constexpr int EU_THREADS = 320;     // warp 0: bulk-copy producer, warp 1: MMA issuer, warps 2..9: workers
 constexpr int EU_TILE = 256;
-constexpr int EU_NSTAGE = 8;
+constexpr int EU_MAXSTAGE = 8;     // the launcher picks the number of stages that fits (5 at DP = 64, K <= 256)
 constexpr int EU_MAXK = 512;
+constexpr int EU_N = 128;           // columns per group
 
 template <int DP>
 struct EuCfg {
-  static constexpr int CG = 64 / DP;          // components per 64-column MMA group
+  static constexpr int CG = EU_N / DP;        // components per 128-column MMA group
   static constexpr int KS = DP / 8;           // K-steps (8 TF32 each)
-  static constexpr bool TRI = (DP == 64);
-  __host__ __device__ static constexpr int n0(int ks) { return TRI ? 16 * (ks / 2) : 0; }
-  __host__ __device__ static constexpr int nn(int ks) { return 64 - n0(ks); }
+  __host__ __device__ static constexpr int n0(int ks) { return ks * CG * 8; }
+  __host__ __device__ static constexpr int nn(int ks) { return EU_N - n0(ks); }
   __host__ __device__ static constexpr int blk_off(int ks) {
     int o = 0;
     for (int i = 0; i < ks; ++i) o += nn(i) * 32;
@@ -45,13 +48,22 @@ struct EuCfg {
   }
   static constexpr int WB = blk_off(KS);      // bytes of one operand image (hi or lo) of a group
   static constexpr int GB = 2 * WB;           // hi image then lo image
-  static constexpr int REC = GB + 64 * 4 + 16; // + m of the group's components (64 floats) + their cst (<= 4 floats)
+  static constexpr int MB = EU_N * 4;         // -m in column order
+  static constexpr int REC = GB + MB + 32;    // + cst of the CG components
   static constexpr int STAGE = (REC + 127) / 128 * 128;
+  // component / feature of column n
+  __host__ __device__ static constexpr int col_cl(int n) { return (n % (CG * 8)) / 8; }
+  __host__ __device__ static constexpr int col_j(int n) { return (n / (CG * 8)) * 8 + n % 8; }
+  // descriptor of K-step block ks (lo = 0/1) relative to a stage at shared address 0 (add stage_addr >> 4)
+  __host__ __device__ static constexpr uint64_t desc0(int ks, int lo) {
+    return (uint64_t)((blk_off(ks) + lo * WB) >> 4) | ((uint64_t)((nn(ks) * 16) >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) |
+           (1ull << 46);
+  }
 };
 
-// ---- pack: W (C, DP, DP) fp32 row-major [i][j] -> per group [hi | lo] images in UMMA K-major core-matrix layout
-// B[n][k] = W_c[i = k][j],  n = cl*DP + j (cl = component within the group); K-step block ks holds rows
-// n >= n0(ks) as [chunk (2)][row][4 floats], i = 8 ks + 4 chunk + e.
+// ---- pack: W (C, DP, DP) fp32 row-major [i][j] -> per group [hi | lo | m | cst] record; B[n][k] = W_c[i = k][j]
+// with (c, j) = column n as above; K-step block ks holds rows n >= n0(ks) as [chunk (2)][row][4 floats],
+// i = 8 ks + 4 chunk + e.
 template <int DP>
 __global__ void estep_pack_kernel(const float* __restrict__ W, const float* __restrict__ m, const float* __restrict__ cst,
                                   int K, uint8_t* __restrict__ Wp) {
@@ -60,9 +72,14 @@ __global__ void estep_pack_kernel(const float* __restrict__ W, const float* __re
   float* hi = reinterpret_cast<float*>(Wp + (size_t)g * C::REC);
   float* lo = reinterpret_cast<float*>(Wp + (size_t)g * C::REC + C::WB);
   float* mo = reinterpret_cast<float*>(Wp + (size_t)g * C::REC + C::GB);
-  for (int o = threadIdx.x; o < 68; o += blockDim.x) {
-    if (o < 64) { const int c = g * C::CG + o / DP; mo[o] = c < K ? m[(size_t)c * DP + o % DP] : 0.f; }
-    else { const int c = g * C::CG + (o - 64); mo[o] = (o - 64 < C::CG && c < K) ? cst[c] : 0.f; }
+  float* co = reinterpret_cast<float*>(Wp + (size_t)g * C::REC + C::GB + C::MB);
+  for (int o = threadIdx.x; o < EU_N; o += blockDim.x) {
+    const int c = g * C::CG + C::col_cl(o);
+    mo[o] = c < K ? -m[(size_t)c * DP + C::col_j(o)] : 0.f;
+  }
+  for (int o = threadIdx.x; o < 8; o += blockDim.x) {
+    const int c = g * C::CG + o;
+    co[o] = (o < C::CG && c < K) ? cst[c] : 0.f;
   }
   for (int o = threadIdx.x; o < C::WB / 4; o += blockDim.x) {
     int ks = 0, rem = o * 4;
@@ -70,7 +87,7 @@ __global__ void estep_pack_kernel(const float* __restrict__ W, const float* __re
     const int nn = C::nn(ks);
     const int ch = rem / (nn * 16);
     const int r = (rem % (nn * 16)) / 16, e = (rem % 16) / 4;
-    const int n = C::n0(ks) + r, cl = n / DP, j = n % DP, i = 8 * ks + 4 * ch + e;
+    const int n = C::n0(ks) + r, cl = C::col_cl(n), j = C::col_j(n), i = 8 * ks + 4 * ch + e;
     const int c = g * C::CG + cl;
     const float v = (c < K) ? W[((size_t)c * DP + i) * DP + j] : 0.f;
     uint32_t h, l;
@@ -81,8 +98,8 @@ __global__ void estep_pack_kernel(const float* __restrict__ W, const float* __re
 }
 
 struct EuSmem {
-  uint64_t full[EU_NSTAGE], empty[EU_NSTAGE];
-  uint64_t tfull[2][2], tempty[2][2];
+  uint64_t full[EU_MAXSTAGE], empty[EU_MAXSTAGE];
+  uint64_t tfull[2], tempty[2];
   uint64_t afull;
   uint32_t tmem_base;
   double red[8];
@@ -94,11 +111,11 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 
 template <int DP, int MODE>
 __global__ void __launch_bounds__(EU_THREADS, 1)
-estep_umma_kernel(EstepArgs a, const uint8_t* __restrict__ Wp, int ntiles, int ngroups) {
+estep_umma_kernel(EstepArgs a, const uint8_t* __restrict__ Wp, int ntiles, int ngroups, int nstage) {
   using C = EuCfg<DP>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* stages = smem_raw;                                             // EU_NSTAGE * STAGE
-  EuSmem* S = reinterpret_cast<EuSmem*>(stages + EU_NSTAGE * C::STAGE);
+  EuSmem* S = reinterpret_cast<EuSmem*>(stages + nstage * C::STAGE);
   float* lz = reinterpret_cast<float*>(S + 1);                            // [256]
   float* colsum = lz + EU_TILE;                                           // [8][K]     (mode 1)
   double* NAacc = reinterpret_cast<double*>(colsum + 8 * a.K);            // [K]        (mode 1)
@@ -106,9 +123,8 @@ estep_umma_kernel(EstepArgs a, const uint8_t* __restrict__ Wp, int ntiles, int n
   const int K = a.K;
 
   if (tid == 0) {
-    for (int s = 0; s < EU_NSTAGE; ++s) { mbar_init(&S->full[s], 1); mbar_init(&S->empty[s], 1 + 256); }
-    for (int h = 0; h < 2; ++h)
-      for (int b = 0; b < 2; ++b) { mbar_init(&S->tfull[h][b], 1); mbar_init(&S->tempty[h][b], 128); }
+    for (int s = 0; s < nstage; ++s) { mbar_init(&S->full[s], 1); mbar_init(&S->empty[s], 1 + 256); }
+    for (int h = 0; h < 2; ++h) { mbar_init(&S->tfull[h], 1); mbar_init(&S->tempty[h], 128); }
     mbar_init(&S->afull, 256);
     fence_barrier_init();
   }
@@ -118,7 +134,7 @@ estep_umma_kernel(EstepArgs a, const uint8_t* __restrict__ Wp, int ntiles, int n
   __syncthreads();
   tc_fence_after();
   const uint32_t tm = S->tmem_base;
-  // TMEM columns: A hi/lo of half h at h*2*DP (+DP for lo); D[h][buf] at 256 + (2h+buf)*64
+  // TMEM columns: A hi/lo of half h at h*2*DP (+DP for lo); D[h] at 256 + 128 h
   const int my_tiles = (ntiles > (int)blockIdx.x) ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
   if (warp == 0) {
@@ -126,8 +142,8 @@ estep_umma_kernel(EstepArgs a, const uint8_t* __restrict__ Wp, int ntiles, int n
     long long it = 0;
     for (int t = 0; t < my_tiles; ++t)
       for (int g = 0; g < ngroups; ++g, ++it) {
-        const int s = (int)(it % EU_NSTAGE);
-        const uint32_t n = (uint32_t)(it / EU_NSTAGE);
+        const int s = (int)(it % nstage);
+        const uint32_t n = (uint32_t)(it / nstage);
         mbar_wait(&S->empty[s], (n & 1) ^ 1);
         if (elect_one()) {
           mbar_arrive_expect_tx(&S->full[s], C::REC);
@@ -142,30 +158,26 @@ estep_umma_kernel(EstepArgs a, const uint8_t* __restrict__ Wp, int ntiles, int n
       mbar_wait(&S->afull, t & 1);
       tc_fence_after();
       for (int g = 0; g < ngroups; ++g, ++it) {
-        const int s = (int)(it % EU_NSTAGE);
-        const uint32_t n = (uint32_t)(it / EU_NSTAGE);
-        const int buf = (int)(it & 1);
-        const uint32_t nb = (uint32_t)(it >> 1);
+        const int s = (int)(it % nstage);
+        const uint32_t n = (uint32_t)(it / nstage);
         mbar_wait(&S->full[s], n & 1);
-        const uint32_t sbase = smem_u32(stages + (size_t)s * C::STAGE);
+        const uint64_t sb = (uint64_t)((smem_u32(stages) + (uint32_t)s * C::STAGE) >> 4);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          mbar_wait(&S->tempty[h][buf], (nb & 1) ^ 1);
+          mbar_wait(&S->tempty[h], (uint32_t)(it & 1) ^ 1);
           tc_fence_after();
-          const uint32_t dcol = tm + 256 + (2 * h + buf) * 64;
+          const uint32_t dcol = tm + 256 + h * EU_N;
           const uint32_t a_hi = tm + h * 2 * DP, a_lo = a_hi + DP;
           if (elect_one()) {
 #pragma unroll
             for (int ks = 0; ks < C::KS; ++ks) {
-              const int nn = C::nn(ks), n0 = C::n0(ks);
-              const uint32_t idesc = idesc_tf32(128, nn);
-              const uint64_t b_hi = smem_desc(sbase + C::blk_off(ks), nn * 16, 128);
-              const uint64_t b_lo = smem_desc(sbase + C::WB + C::blk_off(ks), nn * 16, 128);
-              mma_tf32_ts(dcol + n0, a_lo + ks * 8, b_hi, idesc, ks > 0);   // small terms first
-              mma_tf32_ts(dcol + n0, a_hi + ks * 8, b_lo, idesc, 1);
-              mma_tf32_ts(dcol + n0, a_hi + ks * 8, b_hi, idesc, 1);
+              const uint32_t idesc = idesc_tf32(128, C::nn(ks));
+              const uint64_t b_hi = C::desc0(ks, 0) + sb, b_lo = C::desc0(ks, 1) + sb;
+              mma_tf32_ts(dcol + C::n0(ks), a_lo + ks * 8, b_hi, idesc, ks > 0);   // small terms first
+              mma_tf32_ts(dcol + C::n0(ks), a_hi + ks * 8, b_lo, idesc, 1);
+              mma_tf32_ts(dcol + C::n0(ks), a_hi + ks * 8, b_hi, idesc, 1);
             }
-            mma_commit(&S->tfull[h][buf]);
+            mma_commit(&S->tfull[h]);
             if (h == 1) mma_commit(&S->empty[s]);
           }
           __syncwarp();
@@ -224,36 +236,37 @@ estep_umma_kernel(EstepArgs a, const uint8_t* __restrict__ Wp, int ntiles, int n
       float mx = -INFINITY, sm = 0.f;
       float l4[4];
       for (int g = 0; g < ngroups; ++g, ++it) {
-        const int buf = (int)(it & 1);
-        const uint32_t nb = (uint32_t)(it >> 1);
-        const int s = (int)(it % EU_NSTAGE);
-        const float4* mstage = reinterpret_cast<const float4*>(stages + (size_t)s * C::STAGE + C::GB);
-        mbar_wait(&S->tfull[h][buf], nb & 1);
-        mbar_wait(&S->full[s], (uint32_t)(it / EU_NSTAGE) & 1);   // already complete; acquires the stage's m / cst
+        const int s = (int)(it % nstage);
+        const float2* nm = reinterpret_cast<const float2*>(stages + (size_t)s * C::STAGE + C::GB);   // -m, column order
+        const float* cstage = reinterpret_cast<const float*>(stages + (size_t)s * C::STAGE + C::GB + C::MB);
+        mbar_wait(&S->tfull[h], (uint32_t)(it & 1));
+        mbar_wait(&S->full[s], (uint32_t)(it / nstage) & 1);   // already complete; acquires the stage's m / cst
         tc_fence_after();
-        float y[64];
-        const uint32_t dcol = tm + lane_base + 256 + (2 * h + buf) * 64;
-        tmem_ld32(dcol, y);
-        tmem_ld32(dcol + 32, y + 32);
-        tmem_wait_ld();
-        tc_fence_before();
-        mbar_arrive(&S->tempty[h][buf]);
+        const uint32_t dcol = tm + lane_base + 256 + h * EU_N;
+        float2 q[C::CG];                                     // packed fp32x2 accumulators (FFMA2)
+#pragma unroll
+        for (int cl = 0; cl < C::CG; ++cl) q[cl] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int ps = 0; ps < 2; ++ps) {                     // two passes of 64 columns
+          float y[64];
+          tmem_ld32(dcol + ps * 64, y);
+          tmem_ld32(dcol + ps * 64 + 32, y + 32);
+          tmem_wait_ld();
+          if (ps == 1) { tc_fence_before(); mbar_arrive(&S->tempty[h]); }
+#pragma unroll
+          for (int j = 0; j < 64; j += 2) {
+            const int cl = C::col_cl(ps * 64 + j);            // columns j, j+1 belong to the same component
+            const float2 r = __fadd2_rn(make_float2(y[j], y[j + 1]), nm[(ps * 64 + j) >> 1]);
+            q[cl] = __ffma2_rn(r, r, q[cl]);
+          }
+        }
 #pragma unroll
         for (int cl = 0; cl < C::CG; ++cl) {
           const int c = g * C::CG + cl;
           if (c < K) {
-            const float4* mp = mstage + cl * (DP / 4);
-            float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
-#pragma unroll
-            for (int j = 0; j < DP; j += 4) {
-              const float4 mm = mp[j >> 2];
-              const float r0_ = y[cl * DP + j] - mm.x, r1_ = y[cl * DP + j + 1] - mm.y;
-              const float r2_ = y[cl * DP + j + 2] - mm.z, r3_ = y[cl * DP + j + 3] - mm.w;
-              q0 = fmaf(r0_, r0_, q0); q1 = fmaf(r1_, r1_, q1); q2 = fmaf(r2_, r2_, q2); q3 = fmaf(r3_, r3_, q3);
-            }
-            const float l = reinterpret_cast<const float*>(mstage + 16)[cl] - 0.5f * ((q0 + q1) + (q2 + q3));
-            if (MODE == 1) {          // online logsumexp with one exp per component
-              const float e = expf(-fabsf(l - mx));
+            const float l = cstage[cl] - 0.5f * (q[cl].x + q[cl].y);
+            if (MODE == 1) {          // online logsumexp with one exp per component (ex2.approx: rel. error 2^-22)
+              const float e = exp2f(-1.44269504f * fabsf(l - mx));
               sm = (l > mx) ? fmaf(sm, e, 1.f) : sm + e;
               mx = fmaxf(mx, l);
             }
@@ -262,7 +275,7 @@ estep_umma_kernel(EstepArgs a, const uint8_t* __restrict__ Wp, int ntiles, int n
               *reinterpret_cast<float4*>(a.out + (size_t)row * K + (c - 3)) = make_float4(l4[0], l4[1], l4[2], l4[3]);
           }
         }
-        mbar_arrive(&S->empty[s]);                  // done with the stage's m / cst (the MMA commit is the other arrival)
+        mbar_arrive(&S->empty[s]);                  // done with the stage's cst (the MMA commit is the other arrival)
       }
       if (MODE == 1) {
         const float v = valid ? mx + logf(sm) : 0.f;
@@ -277,10 +290,10 @@ estep_umma_kernel(EstepArgs a, const uint8_t* __restrict__ Wp, int ntiles, int n
         float cs[EU_MAXK / 128][4];
 #pragma unroll
         for (int u = 0; u < EU_MAXK / 128; ++u) { cs[u][0] = cs[u][1] = cs[u][2] = cs[u][3] = 0.f; }
-        for (int r = w8; r < rows; r += 32) {           // four rows in flight per warp (memory-level parallelism)
-          float4 x[4][EU_MAXK / 128];
+        for (int r = w8; r < rows; r += 16) {           // two rows in flight per warp (memory-level parallelism)
+          float4 x[2][EU_MAXK / 128];
 #pragma unroll
-          for (int v = 0; v < 4; ++v) {
+          for (int v = 0; v < 2; ++v) {
             const int rr = r + 8 * v;
             const float4* prow = reinterpret_cast<const float4*>(a.out + (size_t)(row0 + (rr < rows ? rr : r)) * K);
 #pragma unroll
@@ -290,7 +303,7 @@ estep_umma_kernel(EstepArgs a, const uint8_t* __restrict__ Wp, int ntiles, int n
             }
           }
 #pragma unroll
-          for (int v = 0; v < 4; ++v) {
+          for (int v = 0; v < 2; ++v) {
             const int rr = r + 8 * v;
             if (rr < rows) {
               const float lzr = lz[rr];
@@ -354,7 +367,7 @@ static int eu_num_sms() {
 }
 
 static size_t eu_group_bytes(int Dp) { return Dp == 64 ? EuCfg<64>::REC : (Dp == 32 ? EuCfg<32>::REC : EuCfg<16>::REC); }
-static int eu_cg(int Dp) { return 64 / Dp; }
+static int eu_cg(int Dp) { return EU_N / Dp; }
 static size_t eu_align(size_t x) { return (x + 255) / 256 * 256; }
 
 bool estep_umma_supported(long long N, int GX, int G, int K, int Dp, int d0, int d1) {
@@ -382,16 +395,20 @@ static int eu_launch(EstepArgs a, int mode, uint8_t* Wp, float* NA_part, double*
   if (rc) return rc;
   const int ntiles = (int)((a.N + EU_TILE - 1) / EU_TILE);
   const int grid = ntiles < eu_num_sms() ? ntiles : eu_num_sms();
-  const size_t smem = (size_t)EU_NSTAGE * C::STAGE + sizeof(EuSmem) + EU_TILE * sizeof(float) +
-                      (mode == 1 ? (size_t)8 * a.K * sizeof(float) + (size_t)a.K * sizeof(double) : 0) + 64;
+  const size_t fixed = sizeof(EuSmem) + EU_TILE * sizeof(float) +
+                       (mode == 1 ? (size_t)8 * a.K * sizeof(float) + (size_t)a.K * sizeof(double) : 0) + 64;
+  int nstage = (int)((227 * 1024 - fixed) / C::STAGE);
+  if (nstage > EU_MAXSTAGE) nstage = EU_MAXSTAGE;
+  if (nstage < 2) { set_error("estep_umma: shared memory too small for K=%d", a.K); return VBMP_ERR_UNSUPPORTED; }
+  const size_t smem = (size_t)nstage * C::STAGE + fixed;
   a.NA_part = NA_part;
   a.logZ_part = logZ_part;
   if (mode == 0) {
     cudaFuncSetAttribute(estep_umma_kernel<DP, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    estep_umma_kernel<DP, 0><<<grid, EU_THREADS, smem, st>>>(a, Wp, ntiles, ngroups);
+    estep_umma_kernel<DP, 0><<<grid, EU_THREADS, smem, st>>>(a, Wp, ntiles, ngroups, nstage);
   } else {
     cudaFuncSetAttribute(estep_umma_kernel<DP, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    estep_umma_kernel<DP, 1><<<grid, EU_THREADS, smem, st>>>(a, Wp, ntiles, ngroups);
+    estep_umma_kernel<DP, 1><<<grid, EU_THREADS, smem, st>>>(a, Wp, ntiles, ngroups, nstage);
   }
   rc = check_launch("estep_umma");
   if (rc) return rc;

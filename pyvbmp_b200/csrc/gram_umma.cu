@@ -13,8 +13,11 @@
 //   * CTA task = (128-component block) x (NPB <= 224 pair columns) x (sample split).  A operand = R^T
 //     (lanes = components, K = samples) written to TENSOR MEMORY by the workers as split TF32 (hi, lo);
 //     B operand = phi^T generated on the fly in shared memory (K-major core-matrix layout, hi / lo).
-//     D1 (first-level accumulator) and D2 (second level) both live in TMEM: D1 is folded into D2 every
-//     512 samples so no fp32 chain is longer than that, at zero memory traffic.
+//     D1 (first-level accumulator) and D2 (second level) both live in TMEM: D1 is folded into D2 (fp32
+//     round-to-nearest adds on the CUDA cores) every 256 samples, at zero memory traffic.  The tensor core
+//     TRUNCATES on every fp32 accumulate: measured bias -1.0e-7 of the running sum per 16-sample chunk
+//     (tools/gram_bias.py), i.e. -1.6e-6 at 16 chunks per block, -1.3e-5 at 128; hence the short blocks
+//     (SURVEY.md Appendix F.2 anticipated this).
 //   * raw R / Z chunks (16 samples) are brought in by TMA tiled loads (one box per operand, zero-filled past
 //     the last row) into a 4-deep ring (warp 0), the MMAs are
 //     issued by warp 1 (3 split-precision terms x 2 K-steps per chunk), 8 worker warps split / multiply.
@@ -26,11 +29,11 @@
 namespace vbmp {
 using namespace umma;
 
-constexpr int GU_THREADS = 320;
+constexpr int GU_THREADS = 576;      // warp 0 producer, warp 1 MMA issuer, two sets of 8 worker warps (even / odd chunks)
 constexpr int GU_SC = 16;            // samples per chunk (2 K-steps)
 constexpr int GU_NR = 4;             // raw ring depth
 constexpr int GU_NPMAX = 224;        // pair columns per CTA (D1 + D2 = 448 TMEM columns, A buffers = 64)
-constexpr int GU_FL = 32;            // chunks per first-level accumulation block (512 samples)
+constexpr int GU_FL = 16;            // chunks per first-level accumulation block (256 samples)
 constexpr int GU_CB = 128;           // components per CTA
 
 struct GuArgs {
@@ -41,6 +44,7 @@ struct GuArgs {
   int Kp, PP;                        // padded partial dims: Kp = ncb*128, PP = npb*NPB
   int kcb;                           // columns of the R box = min(128, K)
   int FL;                            // chunks per first-level accumulation block
+  int dbg;                           // developer switches (VBMP_GU_DBG): 1 no MMAs, 2 no phi generation, 4 no R split
   float* part;                       // [splits][Kp][PP]
 };
 
@@ -52,26 +56,44 @@ struct GuSmem {
   float consts[2];                   // {1, 0}: the padded "1" feature and the zero used by padding pair columns
 };
 
-#ifndef VBMP_GRAM_ROUND_LO
-#define VBMP_GRAM_ROUND_LO 1
-#endif
-__device__ __forceinline__ void split_fast(float x, uint32_t& hi, uint32_t& lo) {
-  // hi = round-to-nearest (ties away) TF32 of x, lo = round-to-nearest TF32 of the (exact) remainder.
-  hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
-#if VBMP_GRAM_ROUND_LO
-  lo = (__float_as_uint(x - __uint_as_float(hi)) + 0x1000u) & 0xffffe000u;
-#else
-  lo = __float_as_uint(x - __uint_as_float(hi));     // the tensor core ignores the low 13 bits (probe: truncation)
-#endif
+// Pair p of the symmetric (D+1) x (D+1) Gram matrix over zt = [z;1]:  p < D(D+1)/2 walks the upper triangle of the
+// D x D block row by row; the last D+1 pairs are (i, D), i = 0..D (the SEx column and N).  Keeping the pairs that
+// involve the constant feature at the end lets every other warp read both factors with one compile-time stride.
+__host__ __device__ inline void gu_pair(int p, int D, int* i, int* j) {
+  const int T = D * (D + 1) / 2;
+  if (p >= T) { *i = p - T; *j = D; return; }
+  int rem = p, r = 0, len = D;
+  while (rem >= len) { rem -= len; ++r; --len; }
+  *i = r; *j = r + rem;
 }
 
+// Split x = hi + lo for the 3-term TF32 product: hi = TF32(x) rounded to nearest; lo = x - hi is exact in fp32 and
+// needs no rounding of its own because the tensor core ignores the low 13 mantissa bits of a TF32 operand
+// (tools/umma_probe.cu: "operand low-bit handling: truncated").  Feeding x itself as hi (read as trunc(x)) would
+// save two integer ops but adds ~30 % to the bias and triples its spread (tools/gram_bias.py).
+__device__ __forceinline__ void split_fast(float x, uint32_t& hi, uint32_t& lo) {
+  hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
+}
+// two values at a time: the fp32 subtraction runs as one packed FADD2
+__device__ __forceinline__ void split_fast2(float2 x, uint32_t& hi0, uint32_t& hi1, uint32_t& lo0, uint32_t& lo1) {
+  hi0 = (__float_as_uint(x.x) + 0x1000u) & 0xffffe000u;
+  hi1 = (__float_as_uint(x.y) + 0x1000u) & 0xffffe000u;
+  const float2 l = __fadd2_rn(x, make_float2(-__uint_as_float(hi0), -__uint_as_float(hi1)));
+  lo0 = __float_as_uint(l.x); lo1 = __float_as_uint(l.y);
+}
+
+// SF = compile-time row stride (floats) of the raw Z chunk when d0 == SF and (d1 == 0 or d1 == d0), else 0 (generic);
+// R128 = the R box is 128 columns wide (K >= 128).
+template <int SF, bool R128>
 __global__ void __launch_bounds__(GU_THREADS, 1)
 gram_umma_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmZ0,
                  const __grid_constant__ CUtensorMap tmZ1, GuArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const int D = a.d0 + a.d1;
   // carve: raw ring [NR][R 16 x kcb floats | Z0 16 x d0 | Z1 16 x d1], B stages [2][hi NPB*64 B | lo NPB*64 B]
-  const int rawR = GU_SC * a.kcb * 4, rawZ0 = GU_SC * a.d0 * 4, rawZ1 = GU_SC * a.d1 * 4;
+  const int kcb = R128 ? 128 : a.kcb;
+  const int rawR = GU_SC * kcb * 4, rawZ0 = GU_SC * a.d0 * 4, rawZ1 = GU_SC * a.d1 * 4;
   const int rawB = (rawR + rawZ0 + rawZ1 + 127) / 128 * 128;
   const int stageB = 2 * a.NPB * 64;
   uint8_t* raw = smem_raw;
@@ -122,48 +144,54 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant_
   } else if (warp == 1) {
     // ================= MMA issuer =================
     const uint32_t idesc = idesc_tf32(128, NPB);
+    const uint64_t dstep = (uint64_t)((2 * NPB * 16) >> 4);                 // one K-step = two 16-byte chunks
+    const uint64_t d_hi0 = smem_desc(smem_u32(bst), NPB * 16, 128), d_lo0 = d_hi0 + (uint64_t)((NPB * 64) >> 4);
+    int fc = 0, nflush = 0;
     for (int c = 0; c < nchunks; ++c) {
       const int st = c & 1;
       mbar_wait(&S->bfull[st], (c >> 1) & 1);
-      const bool first = (c % FL) == 0;
-      if (first && c > 0) mbar_wait(&S->dempty, ((c / FL) - 1) & 1);
+      const bool first = (fc == 0);
+      if (first && c > 0) mbar_wait(&S->dempty, (nflush - 1) & 1);
       tc_fence_after();
       __syncwarp();
+      const bool flush = (++fc == FL) || (c == nchunks - 1);
       if (elect_one()) {
-        const uint32_t sbase = smem_u32(bst + (size_t)st * stageB);
+        const uint64_t sofs = (uint64_t)((st * stageB) >> 4);
         const uint32_t a_hi = tm + 448 + st * 32, a_lo = a_hi + 16;
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks) {
-          const uint64_t b_hi = smem_desc(sbase + ks * 2 * NPB * 16, NPB * 16, 128);
-          const uint64_t b_lo = smem_desc(sbase + NPB * 64 + ks * 2 * NPB * 16, NPB * 16, 128);
+          if (a.dbg & 1) break;
+          const uint64_t b_hi = d_hi0 + sofs + ks * dstep, b_lo = d_lo0 + sofs + ks * dstep;
           mma_tf32_ts(tm, a_lo + ks * 8, b_hi, idesc, !(first && ks == 0));
           mma_tf32_ts(tm, a_hi + ks * 8, b_lo, idesc, 1);
           mma_tf32_ts(tm, a_hi + ks * 8, b_hi, idesc, 1);
         }
         mma_commit(&S->bempty[st]);
-        if ((c % FL) == FL - 1 || c == nchunks - 1) mma_commit(&S->dfull);
+        if (flush) mma_commit(&S->dfull);
       }
       __syncwarp();
+      if (flush) { fc = 0; ++nflush; }
     }
   } else {
     // ================= workers =================
-    const int w8 = warp - 2, q = warp & 3, sh = w8 >> 2;
-    const int wtid = tid - 64;
+    // two worker sets alternate chunks (set = chunk parity = B stage / A buffer), so the per-chunk latency chain
+    // (barrier wait -> loads -> split -> stores -> fences -> arrive) of one set hides behind the other's
+    const int set = (warp - 2) >> 3;
+    const int w8 = (warp - 2) & 7, q = warp & 3, sh = w8 >> 2;
+    const int wtid = (tid - 64) & 255;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     const int comp = q * 32 + lane;                         // component (TMEM lane) this thread feeds
-    const bool comp_ok = comp < a.kcb && cb * GU_CB + comp < a.K;
-    // pair owned by this thread in the phi generation (row-major upper triangle over D+1 features); the two
-    // factors are read through (base, per-slot stride, per-sample stride) triples so the inner loop is branch free
+    const bool comp_ok = comp < kcb && cb * GU_CB + comp < a.K;
+    // pair owned by this thread in the phi generation; factors are read through (base, per-slot stride, per-sample
+    // stride) triples so the inner loop is branch free.  Warps whose 32 pairs all avoid the constant feature and the
+    // padding use the compile-time stride SF instead.
     const uint8_t* bi; const uint8_t* bj; int sli, slj, sti, stj;
+    bool plain;
     {
       const int pg_ = pb * NPB + wtid;
       const bool pair_ok = (wtid < NPB) && (pg_ < a.P);
       int pi = 0, pj = 0;
-      if (pair_ok) {
-        int rem = pg_, i = 0, len = D + 1;
-        while (rem >= len) { rem -= len; ++i; --len; }
-        pi = i; pj = i + rem;
-      }
+      if (pair_ok) gu_pair(pg_, D, &pi, &pj);
       auto setup = [&](int f, const uint8_t*& b, int& sl, int& stv) {
         if (!pair_ok) { b = reinterpret_cast<const uint8_t*>(&S->consts[1]); sl = 0; stv = 0; }
         else if (f < a.d0) { b = raw + rawR + f * 4; sl = rawB; stv = a.d0 * 4; }
@@ -172,43 +200,73 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant_
       };
       setup(pi, bi, sli, sti);
       setup(pj, bj, slj, stj);
+      plain = SF > 0 && __all_sync(0xffffffffu, pair_ok && pj < D);
     }
-    int nflush = 0;
-    for (int c = 0; c < nchunks; ++c) {
+    const int fls = __ffs(FL) - 1;                       // FL is a power of two
+    for (int c = set; c < nchunks; c += 2) {
       const int s = c % GU_NR, st = c & 1;
+      const int nflush = c >> fls;
       mbar_wait(&S->rfull[s], (c / GU_NR) & 1);
       mbar_wait(&S->bempty[st], ((c >> 1) & 1) ^ 1);
       tc_fence_after();
       // ---- A operand: r[s][comp] for this thread's 8 samples, split, into TMEM
-      {
-        const float* rawr = reinterpret_cast<const float*>(raw + (size_t)s * rawB) + (sh * 8) * a.kcb + comp;
+      if (!(a.dbg & 4)) {
+        const float* rawr = reinterpret_cast<const float*>(raw + (size_t)s * rawB) + (sh * 8) * kcb + comp;
         uint32_t hi[8], lo[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const float r = comp_ok ? rawr[u * a.kcb] : 0.f;
-          split_fast(r, hi[u], lo[u]);
+        for (int u = 0; u < 8; u += 2) {
+          const float2 r = make_float2(comp_ok ? rawr[u * kcb] : 0.f, comp_ok ? rawr[(u + 1) * kcb] : 0.f);
+          split_fast2(r, hi[u], hi[u + 1], lo[u], lo[u + 1]);
         }
         const uint32_t ad = tm + lane_base + 448 + st * 32 + sh * 8;
         tmem_st8(ad, hi);
         tmem_st8(ad + 16, lo);
       }
       // ---- B operand: phi[s][pair] = zt[s][i] * zt[s][j] for 16 samples, split, K-major core-matrix layout
-      if (wtid < NPB) {
+      if (wtid < NPB && !(a.dbg & 2)) {
         uint8_t* bh = bst + (size_t)st * stageB + (size_t)wtid * 16;
         uint8_t* bl = bh + NPB * 64;
         const uint8_t* zi = bi + s * sli;
         const uint8_t* zj = bj + s * slj;
+        if (plain) {
+          // all 32 loads first (the stores below may not be reordered above them), then multiply / split / store
+          float av[16], bv[16];
 #pragma unroll
-        for (int qd = 0; qd < 4; ++qd) {
-          uint32_t hi[4], lo[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int sl = qd * 4 + u;
-            const float v = *reinterpret_cast<const float*>(zi + sl * sti) * *reinterpret_cast<const float*>(zj + sl * stj);
-            split_fast(v, hi[u], lo[u]);
+          for (int sl = 0; sl < 16; ++sl) {
+            av[sl] = *reinterpret_cast<const float*>(zi + sl * (SF * 4));
+            bv[sl] = *reinterpret_cast<const float*>(zj + sl * (SF * 4));
           }
-          *reinterpret_cast<uint4*>(bh + (size_t)qd * NPB * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-          *reinterpret_cast<uint4*>(bl + (size_t)qd * NPB * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+#pragma unroll
+          for (int qd = 0; qd < 4; ++qd) {
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int u = 0; u < 4; u += 2) {
+              const int sl = qd * 4 + u;
+              split_fast2(__fmul2_rn(make_float2(av[sl], av[sl + 1]), make_float2(bv[sl], bv[sl + 1])), hi[u], hi[u + 1],
+                          lo[u], lo[u + 1]);
+            }
+            *reinterpret_cast<uint4*>(bh + (size_t)qd * NPB * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4*>(bl + (size_t)qd * NPB * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          }
+        } else {
+          float av[16], bv[16];
+#pragma unroll
+          for (int sl = 0; sl < 16; ++sl) {
+            av[sl] = *reinterpret_cast<const float*>(zi + sl * sti);
+            bv[sl] = *reinterpret_cast<const float*>(zj + sl * stj);
+          }
+#pragma unroll
+          for (int qd = 0; qd < 4; ++qd) {
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int u = 0; u < 4; u += 2) {
+              const int sl = qd * 4 + u;
+              split_fast2(__fmul2_rn(make_float2(av[sl], av[sl + 1]), make_float2(bv[sl], bv[sl + 1])), hi[u], hi[u + 1],
+                          lo[u], lo[u + 1]);
+            }
+            *reinterpret_cast<uint4*>(bh + (size_t)qd * NPB * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4*>(bl + (size_t)qd * NPB * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          }
         }
       }
       mbar_arrive(&S->rempty[s]);
@@ -218,8 +276,11 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant_
       mbar_arrive(&S->bfull[st]);
 
       const bool last = (c == nchunks - 1);
-      if ((c % FL) == FL - 1 || last) {
+      if (((c + 1) & (FL - 1)) == 0 || last) {
         // ---- fold D1 into D2 (or, at the end, write D1 + D2 to this split's partial)
+        // a parity wait is only unambiguous one phase ahead: when the last block is 1-2 chunks long this set may not
+        // have seen the previous block's completion yet (the other set folded it), so observe that phase first
+        if (nflush > 0) mbar_wait(&S->dfull, (nflush - 1) & 1);
         mbar_wait(&S->dfull, nflush & 1);
         tc_fence_after();
         const bool firstf = (nflush == 0);
@@ -244,10 +305,9 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant_
         tmem_wait_st();
         tc_fence_before();
         mbar_arrive(&S->dempty);
-        ++nflush;
       }
     }
-    if (nchunks == 0) {      // empty split: contribute zeros
+    if (nchunks == 0 && set == 0) {      // empty split: contribute zeros
       float* prow = a.part + ((size_t)split * a.Kp + (size_t)cb * GU_CB + comp) * a.PP + (size_t)pb * NPB;
       for (int c0 = sh * 112; c0 < sh * 112 + 112 && c0 < NPB; ++c0) prow[c0] = 0.f;
     }
@@ -263,12 +323,11 @@ __global__ void gram_pair_reduce_kernel(const float* __restrict__ part, int spli
   const int P = D1 * (D1 + 1) / 2;
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= (long long)K * P) return;
-  const int k = (int)(e / P);
-  int rem = (int)(e % P), i = 0, len = D1;
-  while (rem >= len) { rem -= len; ++i; --len; }
-  const int j = i + rem;
+  const int k = (int)(e / P), p = (int)(e % P);
+  int i, j;
+  gu_pair(p, D1 - 1, &i, &j);
   double acc = 0.0;
-  for (int s = 0; s < splits; ++s) acc += (double)part[((size_t)s * Kp + k) * PP + (e % P)];
+  for (int s = 0; s < splits; ++s) acc += (double)part[((size_t)s * Kp + k) * PP + p];
   const float v = (float)acc;
   gram[((size_t)k * D1 + i) * D1 + j] = v;
   gram[((size_t)k * D1 + j) * D1 + i] = v;
@@ -325,7 +384,7 @@ static int gu_fl() {
   if (fl == 0) {
     const char* e = getenv("VBMP_GRAM_FL");     // tuning knob: chunks (16 samples) per first-level accumulation block
     fl = e ? atoi(e) : GU_FL;
-    if (fl < 1) fl = GU_FL;
+    if (fl < 1 || (fl & (fl - 1))) fl = GU_FL;   // power of two
   }
   return fl;
 }
@@ -337,6 +396,7 @@ int launch_gram_umma(const GramArgs& a, float* gram, void* ws, size_t ws_bytes, 
   gu_plan(a.N, a.K, D, gu_num_sms(), &g);
   g.kcb = a.K < GU_CB ? a.K : GU_CB;
   g.FL = gu_fl();
+  { const char* e = getenv("VBMP_GU_DBG"); g.dbg = e ? atoi(e) : 0; }
   const size_t need = (size_t)g.splits * g.Kp * g.PP * sizeof(float) + 512;
   if (ws_bytes < need) { set_error("gram_umma: workspace too small (%zu < %zu)", ws_bytes, need); return VBMP_ERR_WORKSPACE; }
   g.part = (float*)(((size_t)ws + 255) / 256 * 256);
@@ -348,9 +408,23 @@ int launch_gram_umma(const GramArgs& a, float* gram, void* ws, size_t ws_bytes, 
   if (e) { set_error("gram_umma: cuTensorMapEncodeTiled failed (%d)", e); return VBMP_ERR_CUDA; }
   const int rawB = (GU_SC * g.kcb * 4 + GU_SC * a.d0 * 4 + GU_SC * a.d1 * 4 + 127) / 128 * 128;
   const size_t smem = (size_t)GU_NR * rawB + (size_t)2 * 2 * g.NPB * 64 + sizeof(GuSmem) + 64;
-  cudaFuncSetAttribute(gram_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const int grid = g.splits * g.ncb * g.npb;
-  gram_umma_kernel<<<grid, GU_THREADS, smem, st>>>(tmR, tmZ0, tmZ1, g);
+  const bool same = (a.d1 == 0 || a.d1 == a.d0);
+  const int sf = same && (a.d0 == 64 || a.d0 == 32 || a.d0 == 16) ? a.d0 : 0;
+  const bool r128 = g.kcb == GU_CB;
+#define GU_LAUNCH(SF, R)                                                                                         \
+  do {                                                                                                           \
+    cudaFuncSetAttribute(gram_umma_kernel<SF, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
+    gram_umma_kernel<SF, R><<<grid, GU_THREADS, smem, st>>>(tmR, tmZ0, tmZ1, g);                                 \
+  } while (0)
+  if (sf == 64 && r128) GU_LAUNCH(64, true);
+  else if (sf == 64) GU_LAUNCH(64, false);
+  else if (sf == 32 && r128) GU_LAUNCH(32, true);
+  else if (sf == 32) GU_LAUNCH(32, false);
+  else if (sf == 16) GU_LAUNCH(16, false);
+  else if (r128) GU_LAUNCH(0, true);
+  else GU_LAUNCH(0, false);
+#undef GU_LAUNCH
   int rc = check_launch("gram_umma");
   if (rc) return rc;
   const int D1 = D + 1;

@@ -1,0 +1,108 @@
+"""GPU kernel-level tests through the C ABI: the tcgen05 (UMMA) E-step / Gram kernels and the CUDA-core kernels
+against an fp64 torch restatement of the same op on the same seeded inputs (tolerances: BASELINE.json's 1e-4
+relative on statistics / log-normalisers; logits to fp32 round-off of their magnitude; argmax identical)."""
+import pytest
+import torch
+
+from pyvbmp_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _problem(N, d0, d1, K, seed=0, spread=1.0):
+    dev = torch.device(DEV)
+    g = torch.Generator(device=dev).manual_seed(seed)
+    D = d0 + d1
+    Dp = _lib.pad_dim(D)
+    mu = spread * torch.randn(K, D, generator=g, device=dev)
+    z = mu[torch.randint(K, (N,), generator=g, device=dev)] + torch.randn(N, D, generator=g, device=dev)
+    A = torch.randn(K, D, D, generator=g, device=dev) / D ** 0.5
+    invU = A @ A.transpose(-1, -2) + 0.5 * torch.eye(D, device=dev)
+    nu = D + 2 + 10 * torch.rand(K, generator=g, device=dev)
+    lam = 1 + torch.rand(K, generator=g, device=dev)
+    lp = torch.log_softmax(torch.randn(K, generator=g, device=dev), 0)
+    W, m, cst, info = _lib.niw_prep(invU.contiguous(), mu.contiguous(), nu, lam, lp, K, D, Dp)
+    assert int(info.abs().max()) == 0
+    z0 = z[:, :d0].contiguous()
+    z1 = z[:, d0:].contiguous() if d1 else None
+    y = torch.einsum("ni,kij->nkj", z.double(), W[:, :D, :].double()) - m.double()[None]
+    L = cst.double()[None] - 0.5 * (y * y).sum(-1)
+    return z, z0, z1, W, m, cst, Dp, L
+
+
+CASES = [(5000, 64, 0, 256), (66000, 64, 0, 256), (3001, 32, 32, 64), (4099, 16, 16, 32), (2500, 16, 0, 8),
+         (6000, 48, 0, 20), (300, 64, 0, 16)]
+
+
+@pytest.mark.parametrize("N,d0,d1,K", CASES)
+@pytest.mark.parametrize("simt", [0, 1])
+def test_estep_kernels(N, d0, d1, K, simt):
+    z, z0, z1, W, m, cst, Dp, L = _problem(N, d0, d1, K)
+    xg = torch.zeros(1, dtype=torch.int32, device=DEV)
+    lz = torch.logsumexp(L, -1)
+    P = (L - lz[:, None]).exp()
+    old = _lib.FORCE_SIMT
+    _lib.FORCE_SIMT = simt
+    try:
+        lg = _lib.estep(z0, z1, N, 1, xg, W, m, cst, 1, K, Dp, 0).view(N, K)
+        p, lzn, NA, lZ = _lib.estep(z0, z1, N, 1, xg, W, m, cst, 1, K, Dp, 1)
+    finally:
+        _lib.FORCE_SIMT = old
+    p = p.view(N, K)
+    scale = float(L.abs().max())
+    assert float((lg.double() - L).abs().max()) <= 2e-6 * scale          # fp32 round-off of the logit magnitude
+    assert float((lzn.view(N).double() - lz).abs().max()) <= 2e-6 * scale
+    assert float((p.double() - P).abs().max()) <= 2e-3
+    assert float(((NA.view(K).double() - P.sum(0)).abs() / P.sum(0).clamp_min(1.0)).max()) <= 1e-4
+    assert abs(float(lZ.double().sum() - lz.sum())) <= 1e-5 * abs(float(lz.sum()))
+    # argmax: identical wherever the fp64 top-2 margin exceeds the fp32 logit noise
+    top2 = L.topk(2, -1).values
+    safe = (top2[:, 0] - top2[:, 1]) > 4e-6 * scale
+    assert bool((p.argmax(-1) == P.argmax(-1))[safe].all())
+    assert int((p.argmax(-1) != P.argmax(-1)).sum()) <= max(1, N // 2000)
+
+
+@pytest.mark.parametrize("N,d0,d1,K", CASES)
+@pytest.mark.parametrize("simt", [0, 1])
+def test_gram_kernels(N, d0, d1, K, simt):
+    z, z0, z1, W, m, cst, Dp, L = _problem(N, d0, d1, K, seed=1)
+    D = d0 + d1
+    xg = torch.zeros(1, dtype=torch.int32, device=DEV)
+    P = (L - torch.logsumexp(L, -1)[:, None]).exp()
+    Pf = P.float().contiguous()
+    zt = torch.cat([z.double(), torch.ones(N, 1, device=DEV, dtype=torch.float64)], 1)
+    Gref = torch.zeros(K, D + 1, D + 1, device=DEV, dtype=torch.float64)
+    for a in range(0, N, 4096):
+        Gref += torch.einsum("nk,ni,nj->kij", Pf[a:a + 4096].double(), zt[a:a + 4096], zt[a:a + 4096])
+    old = _lib.FORCE_SIMT
+    _lib.FORCE_SIMT = simt
+    try:
+        G = _lib.gram(z0, z1, N, 1, xg, Pf.view(N, 1, K), 1, xg, 1, K, Dp).view(K, D + 1, D + 1)
+    finally:
+        _lib.FORCE_SIMT = old
+    assert float((G.double() - Gref).abs().max() / Gref.abs().max()) <= 1e-5
+    asym = float((G - G.transpose(-1, -2)).abs().max() / G.abs().max())
+    assert asym == 0.0 if not simt else asym < 1e-6        # the pair-GEMM kernel is symmetric by construction
+
+    def scat(G):   # centred scatter: the cancellation-sensitive quantity the NIW update forms from the blocks
+        G = G.double()
+        return G[:, :D, :D] - G[:, :D, D:] @ G[:, D:, :D] / G[:, D:, D:].clamp_min(1e-30)
+    s_ref = scat(Gref)
+    keep = Gref[:, D, D] > 10.0                                            # components that own some mass
+    err = (scat(G) - s_ref).flatten(1).norm(dim=1) / s_ref.flatten(1).norm(dim=1).clamp_min(1e-30)
+    assert float(err[keep].max()) <= 1e-4
+
+
+def test_gram_is_deterministic_run_to_run():
+    z, z0, z1, W, m, cst, Dp, L = _problem(40000, 64, 0, 64, seed=2)
+    xg = torch.zeros(1, dtype=torch.int32, device=DEV)
+    P = (L - torch.logsumexp(L, -1)[:, None]).exp().float().contiguous()
+    a = _lib.gram(z0, None, 40000, 1, xg, P.view(40000, 1, 64), 1, xg, 1, 64, Dp).clone()
+    b = _lib.gram(z0, None, 40000, 1, xg, P.view(40000, 1, 64), 1, xg, 1, 64, Dp).clone()
+    assert torch.equal(a, b)
+    r1 = _lib.estep(z0, None, 40000, 1, xg, W, m, cst, 1, 64, Dp, 1)
+    r1 = [t.clone() for t in r1]
+    r2 = _lib.estep(z0, None, 40000, 1, xg, W, m, cst, 1, 64, Dp, 1)
+    for u, v in zip(r1, r2):
+        assert torch.equal(u, v)

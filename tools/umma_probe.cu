@@ -289,9 +289,101 @@ static void run_trunc_test() {
   cudaFree(dA); cudaFree(dB); cudaFree(dD);
 }
 
+// Replays the E-step MMA sequence of estep_umma.cu (2 halves x 8 K-steps x 3 split terms per 64-column group)
+// with static operands: TRI = triangular column-suffix skipping, per-group cycles.
+template <bool TRI, int VARIANT>
+__global__ void __launch_bounds__(128, 1) eseq_kernel(int groups, long long* cycles) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar_mma;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  float* Bs = reinterpret_cast<float*>(smem);
+  for (int e = tid; e < 9 * 5120; e += 128) Bs[e] = (float)((e * 37) % 7 - 3);      // 8 stages x 40 KB >= hi+lo images
+  fence_proxy_async();
+  if (tid == 0) { mbar_init(&bar_mma, 1); fence_barrier_init(); }
+  if (warp == 0) tmem_alloc<512>(&tmem_base_s);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tm = tmem_base_s;
+  {
+    uint32_t r[16];
+    for (int j = 0; j < 16; ++j) r[j] = __float_as_uint((float)(j - 8));
+    for (int c = 0; c < 256; c += 16) tmem_st16(tm + ((uint32_t)(warp * 32) << 16) + c, r);
+    tmem_wait_st();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) {
+    const long long t0 = clock64();
+    for (int g = 0; g < groups; ++g) {
+      const uint32_t sbase = smem_u32(smem) + (g & 7) * 20480;
+      const int buf = g & 1;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const uint32_t dcol = tm + 256 + (2 * h + buf) * 64;
+        const uint32_t a_hi = tm + h * 128, a_lo = a_hi + 64;
+        if (elect_one()) {
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {
+            const int n0 = TRI ? 16 * (ks / 2) : 0, nn = 64 - n0;
+            int off = 0;
+            for (int i = 0; i < ks; ++i) off += (64 - (TRI ? 16 * (i / 2) : 0)) * 32;
+            const uint32_t idesc = idesc_tf32(128, nn);
+            const uint64_t b_hi = smem_desc(sbase + off, nn * 16, 128);
+            const uint64_t b_lo = smem_desc(sbase + 10240 + off, nn * 16, 128);
+            if (VARIANT == 0) {
+              mma_tf32_ts(dcol + n0, a_lo + ks * 8, b_hi, idesc, ks > 0);
+              mma_tf32_ts(dcol + n0, a_hi + ks * 8, b_lo, idesc, 1);
+              mma_tf32_ts(dcol + n0, a_hi + ks * 8, b_hi, idesc, 1);
+            } else if (VARIANT == 1) {     // same A for consecutive MMAs where possible
+              mma_tf32_ts(dcol + n0, a_hi + ks * 8, b_lo, idesc, ks > 0);
+              mma_tf32_ts(dcol + n0, a_hi + ks * 8, b_hi, idesc, 1);
+              mma_tf32_ts(dcol + n0, a_lo + ks * 8, b_hi, idesc, 1);
+            } else {                       // D always written at column offset 0 (alignment test; wrong maths)
+              mma_tf32_ts(dcol, a_lo + ks * 8, b_hi, idesc, ks > 0);
+              mma_tf32_ts(dcol, a_hi + ks * 8, b_lo, idesc, 1);
+              mma_tf32_ts(dcol, a_hi + ks * 8, b_hi, idesc, 1);
+            }
+          }
+        }
+        __syncwarp();
+      }
+    }
+    if (elect_one()) mma_commit(&bar_mma);
+    __syncwarp();
+    mbar_wait(&bar_mma, 0);
+    const long long t1 = clock64();
+    if ((tid & 31) == 0) cycles[blockIdx.x] = t1 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tm);
+}
+
+template <bool TRI, int VARIANT>
+static void run_eseq() {
+  const int groups = 4000, grid = 148;
+  long long* dc; CK(cudaMalloc(&dc, grid * sizeof(long long)));
+  const size_t smem = 8 * 40960;
+  CK(cudaFuncSetAttribute(eseq_kernel<TRI, VARIANT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * 20480 + 20480)));
+  eseq_kernel<TRI, VARIANT><<<grid, 128, 8 * 20480 + 20480>>>(100, dc);
+  CK(cudaDeviceSynchronize());
+  eseq_kernel<TRI, VARIANT><<<grid, 128, 8 * 20480 + 20480>>>(groups, dc);
+  CK(cudaDeviceSynchronize());
+  std::vector<long long> c(grid);
+  CK(cudaMemcpy(c.data(), dc, grid * sizeof(long long), cudaMemcpyDeviceToHost));
+  long long mx = 0; for (auto v : c) if (v > mx) mx = v;
+  printf("eseq tri=%d variant=%d : %.1f cycles per group (48 MMAs) -> %.1f per MMA\n", (int)TRI, VARIANT, (double)mx / groups, (double)mx / groups / 48.0);
+  (void)smem;
+  cudaFree(dc);
+}
+
 int main(int argc, char** argv) {
   srand(1);
   int fails = 0;
+  if (argc > 1 && atoi(argv[1]) == 4) { run_eseq<false, 0>(); run_eseq<true, 0>(); run_eseq<true, 1>(); run_eseq<true, 2>(); run_eseq<false, 1>(); return 0; }
   if (argc > 1 && atoi(argv[1]) == 3) { run_trunc_test(); return 0; }
   if (argc > 1 && atoi(argv[1]) == 2) {
     for (int ts = 0; ts < 2; ++ts)
