@@ -29,7 +29,7 @@
 namespace vbmp {
 using namespace umma;
 
-constexpr int EU_THREADS = 320;     // warp 0: bulk-copy producer, warp 1: MMA issuer, warps 2..9: workers
+constexpr int EU_THREADS = 352;     // warp 0: bulk-copy producer, warps 1-2: MMA issuers (one per half), warps 3..10: workers
 constexpr int EU_TILE = 256;
 constexpr int EU_MAXSTAGE = 8;     // the launcher picks the number of stages that fits (5 at DP = 64, K <= 256)
 constexpr int EU_MAXK = 512;
@@ -123,7 +123,7 @@ estep_umma_kernel(EstepArgs a, const uint8_t* __restrict__ Wp, int ntiles, int n
   const int K = a.K;
 
   if (tid == 0) {
-    for (int s = 0; s < nstage; ++s) { mbar_init(&S->full[s], 1); mbar_init(&S->empty[s], 1 + 256); }
+    for (int s = 0; s < nstage; ++s) { mbar_init(&S->full[s], 1); mbar_init(&S->empty[s], 2 + 256); }
     for (int h = 0; h < 2; ++h) { mbar_init(&S->tfull[h], 1); mbar_init(&S->tempty[h], 128); }
     mbar_init(&S->afull, 256);
     fence_barrier_init();
@@ -151,8 +151,12 @@ estep_umma_kernel(EstepArgs a, const uint8_t* __restrict__ Wp, int ntiles, int n
         }
         __syncwarp();
       }
-  } else if (warp == 1) {
-    // ================= MMA issuer =================
+  } else if (warp <= 2) {
+    // ================= MMA issuers: warp 1 drives half 0, warp 2 half 1 =================
+    // (one issuer per half: the barrier waits / descriptor set-up of one half overlap the other half's MMAs)
+    const int h = warp - 1;
+    const uint32_t dcol = tm + 256 + h * EU_N;
+    const uint32_t a_hi = tm + h * 2 * DP, a_lo = a_hi + DP;
     long long it = 0;
     for (int t = 0; t < my_tiles; ++t) {
       mbar_wait(&S->afull, t & 1);
@@ -162,32 +166,27 @@ estep_umma_kernel(EstepArgs a, const uint8_t* __restrict__ Wp, int ntiles, int n
         const uint32_t n = (uint32_t)(it / nstage);
         mbar_wait(&S->full[s], n & 1);
         const uint64_t sb = (uint64_t)((smem_u32(stages) + (uint32_t)s * C::STAGE) >> 4);
+        mbar_wait(&S->tempty[h], (uint32_t)(it & 1) ^ 1);
+        tc_fence_after();
+        if (elect_one()) {
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          mbar_wait(&S->tempty[h], (uint32_t)(it & 1) ^ 1);
-          tc_fence_after();
-          const uint32_t dcol = tm + 256 + h * EU_N;
-          const uint32_t a_hi = tm + h * 2 * DP, a_lo = a_hi + DP;
-          if (elect_one()) {
-#pragma unroll
-            for (int ks = 0; ks < C::KS; ++ks) {
-              const uint32_t idesc = idesc_tf32(128, C::nn(ks));
-              const uint64_t b_hi = C::desc0(ks, 0) + sb, b_lo = C::desc0(ks, 1) + sb;
-              mma_tf32_ts(dcol + C::n0(ks), a_lo + ks * 8, b_hi, idesc, ks > 0);   // small terms first
-              mma_tf32_ts(dcol + C::n0(ks), a_hi + ks * 8, b_lo, idesc, 1);
-              mma_tf32_ts(dcol + C::n0(ks), a_hi + ks * 8, b_hi, idesc, 1);
-            }
-            mma_commit(&S->tfull[h]);
-            if (h == 1) mma_commit(&S->empty[s]);
+          for (int ks = 0; ks < C::KS; ++ks) {
+            const uint32_t idesc = idesc_tf32(128, C::nn(ks));
+            const uint64_t b_hi = C::desc0(ks, 0) + sb, b_lo = C::desc0(ks, 1) + sb;
+            mma_tf32_ts(dcol + C::n0(ks), a_lo + ks * 8, b_hi, idesc, ks > 0);   // small terms first
+            mma_tf32_ts(dcol + C::n0(ks), a_hi + ks * 8, b_lo, idesc, 1);
+            mma_tf32_ts(dcol + C::n0(ks), a_hi + ks * 8, b_hi, idesc, 1);
           }
-          __syncwarp();
+          mma_commit(&S->tfull[h]);
+          mma_commit(&S->empty[s]);
         }
+        __syncwarp();
       }
     }
   } else {
     // ================= workers: A tile -> TMEM, epilogue, normalisation =================
-    const int w8 = warp - 2, h = w8 >> 2, q = warp & 3;
-    const int wtid = tid - 64;                                  // 0..255
+    const int w8 = warp - 3, h = w8 >> 2, q = warp & 3;
+    const int wtid = tid - 96;                                  // 0..255
     const int rloc = h * 128 + q * 32 + lane;                   // row within the tile
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     const int D = a.d0 + a.d1;
@@ -246,19 +245,21 @@ estep_umma_kernel(EstepArgs a, const uint8_t* __restrict__ Wp, int ntiles, int n
         float2 q[C::CG];                                     // packed fp32x2 accumulators (FFMA2)
 #pragma unroll
         for (int cl = 0; cl < C::CG; ++cl) q[cl] = make_float2(0.f, 0.f);
+        // all 128 columns into registers, then hand the accumulator straight back to the MMA warp: the arithmetic
+        // below overlaps the next MMAs on this half
+        float y[EU_N];
+        tmem_ld32(dcol, y);
+        tmem_ld32(dcol + 32, y + 32);
+        tmem_ld32(dcol + 64, y + 64);
+        tmem_ld32(dcol + 96, y + 96);
+        tmem_wait_ld();
+        tc_fence_before();
+        mbar_arrive(&S->tempty[h]);
 #pragma unroll
-        for (int ps = 0; ps < 2; ++ps) {                     // two passes of 64 columns
-          float y[64];
-          tmem_ld32(dcol + ps * 64, y);
-          tmem_ld32(dcol + ps * 64 + 32, y + 32);
-          tmem_wait_ld();
-          if (ps == 1) { tc_fence_before(); mbar_arrive(&S->tempty[h]); }
-#pragma unroll
-          for (int j = 0; j < 64; j += 2) {
-            const int cl = C::col_cl(ps * 64 + j);            // columns j, j+1 belong to the same component
-            const float2 r = __fadd2_rn(make_float2(y[j], y[j + 1]), nm[(ps * 64 + j) >> 1]);
-            q[cl] = __ffma2_rn(r, r, q[cl]);
-          }
+        for (int j = 0; j < EU_N; j += 2) {
+          const int cl = C::col_cl(j);                        // columns j, j+1 belong to the same component
+          const float2 r = __fadd2_rn(make_float2(y[j], y[j + 1]), nm[j >> 1]);
+          q[cl] = __ffma2_rn(r, r, q[cl]);
         }
 #pragma unroll
         for (int cl = 0; cl < C::CG; ++cl) {
@@ -275,7 +276,7 @@ estep_umma_kernel(EstepArgs a, const uint8_t* __restrict__ Wp, int ntiles, int n
               *reinterpret_cast<float4*>(a.out + (size_t)row * K + (c - 3)) = make_float4(l4[0], l4[1], l4[2], l4[3]);
           }
         }
-        mbar_arrive(&S->empty[s]);                  // done with the stage's cst (the MMA commit is the other arrival)
+        mbar_arrive(&S->empty[s]);                  // done with the stage's -m / cst (the two MMA commits are the other arrivals)
       }
       if (MODE == 1) {
         const float v = valid ? mx + logf(sm) : 0.f;
