@@ -146,16 +146,17 @@ def mnw_prep(invU, nu, mu, invV, logprior, C, n, pp, pad, Dp):
     return W, m, cst, info
 
 
-def estep(z0, z1, N, GX, xg, W, m, cst, G, K, Dp, mode, out=None):
+def estep(z0, z1, N, GX, xg, W, m, cst, G, K, Dp, mode, out=None, logZn=None):
     """z0: (N,GX,d0), z1: (N,GX,d1) or None.  Returns logits (mode 0) or (p, logZn, NA, logZ) (mode 1)."""
     dev = z0.device
     d0 = z0.shape[-1]
     d1 = 0 if z1 is None else z1.shape[-1]
     if out is None:
         out = torch.empty((N, G, K), dtype=torch.float32, device=dev)
-    logZn = NA = logZ = None
+    NA = logZ = None
     if mode == 1:
-        logZn = torch.empty((N, G), dtype=torch.float32, device=dev)
+        if logZn is None:
+            logZn = torch.empty((N, G), dtype=torch.float32, device=dev)
         NA = torch.empty((G, K), dtype=torch.float32, device=dev)
         logZ = torch.empty((G,), dtype=torch.float32, device=dev)
     nbytes = lib().vbmp_estep_workspace_bytes(c_longlong(N), c_int(G), c_int(K), c_int(Dp), c_int(mode))

@@ -88,7 +88,17 @@ class Mixture():
         self.update(X, iters=iters, lr=lr, verbose=verbose)
 
     def update(self, X, iters=1, lr=1.0, verbose=False):
-        """dists/Mixture.py:54-62: E-step, ELBO with pre-M-step parameters, M-step."""
+        """dists/Mixture.py:54-62: E-step, ELBO with pre-M-step parameters, M-step.
+
+        X may live in host memory (ideally pinned): each iteration then streams it through the device in row chunks,
+        the H2D copy of chunk i+1 overlapping the E-step + Gram kernels of chunk i (same arithmetic, same results)."""
+        if isinstance(X, torch.Tensor) and not X.is_cuda and self.dist.mu.is_cuda:
+            for i in range(iters):
+                ELBO = self._streamed_iteration(X, lr)
+                if verbose:
+                    print('Percent Change in ELBO:   ', (ELBO - self.ELBO_last) / self.ELBO_last.abs() * 100.0)
+                self.ELBO_last = ELBO
+            return
         for i in range(iters):
             self.update_assignments(X)
             if sharding.enabled():
@@ -99,6 +109,64 @@ class Mixture():
             if verbose:
                 print('Percent Change in ELBO:   ', (ELBO - self.ELBO_last) / self.ELBO_last.abs() * 100.0)
             self.ELBO_last = ELBO
+
+    STREAM_ROWS = 1 << 19      # rows per streamed chunk (128 MiB of X at d = 64)
+
+    def _streamed_iteration(self, Xh, lr):
+        """One EM iteration over host-resident rows: per chunk H2D (copy stream) -> K2 E-step -> K3 Gram on the compute
+        stream; the statistics of the chunks are summed in a fixed order, then ELBO and the (optionally sharded) update."""
+        dist = self.dist
+        dev = dist.mu.device
+        fusable = (isinstance(dist, NormalInverseWishart) and self.event_dim == 1 and dist.event_dim == 1
+                   and dist.batch_dim == 1 and Xh.ndim == 2)
+        if not fusable:
+            Xd = Xh.to(dev, non_blocking=True)
+            self.update_assignments(Xd)
+            ELBO = self.ELBO()
+            self.update_parms(Xd, lr)
+            return ELBO
+        N, d = Xh.shape
+        K = dist.batch_shape[-1]
+        plan = dist._plan(Xh[:1].view(1, 1, d))
+        W, m, cst, info, Dp = dist._prep(plan, logprior=self.pi.loggeomean())
+        xg = _shapes.idx_tensor((0,), dev)
+        rows = min(self.STREAM_ROWS, max(N, 1))
+        st = getattr(self, "_stream_state", None)
+        if st is None or st["key"] != (N, d, K, str(dev)):
+            st = {"key": (N, d, K, str(dev)), "copy": torch.cuda.Stream(dev),
+                  "buf": [torch.empty((rows, d), dtype=torch.float32, device=dev) for _ in range(2)],
+                  "free": [torch.cuda.Event() for _ in range(2)],
+                  "p": torch.empty((N, K), dtype=torch.float32, device=dev),
+                  "lz": torch.empty((N,), dtype=torch.float32, device=dev)}
+            self._stream_state = st
+        cur = torch.cuda.current_stream(dev)
+        for e in st["free"]:
+            e.record(cur)
+        Gs = NA = logZ = None
+        for i, a in enumerate(range(0, N, rows)):
+            b = min(a + rows, N)
+            buf = st["buf"][i & 1][: b - a]
+            ready = torch.cuda.Event()
+            with torch.cuda.stream(st["copy"]):
+                st["copy"].wait_event(st["free"][i & 1])          # the kernels of chunk i-2 are done with this buffer
+                buf.copy_(Xh[a:b], non_blocking=True)
+                ready.record(st["copy"])
+            cur.wait_event(ready)
+            pc, lzc, NAc, lZc = _lib.estep(buf.view(b - a, 1, d), None, b - a, 1, xg, W, m, cst, 1, K, Dp, 1,
+                                           out=st["p"][a:b].view(b - a, 1, K), logZn=st["lz"][a:b].view(b - a, 1))
+            Gc = _lib.gram(buf.view(b - a, 1, d), None, b - a, 1, xg, pc, 1, xg, 1, K, Dp)
+            st["free"][i & 1].record(cur)
+            Gs = Gc if Gs is None else Gs + Gc                   # fixed chunk order: deterministic
+            NA = NAc if NA is None else NA + NAc
+            logZ = lZc if logZ is None else logZ + lZc
+        self.p, self.logZ_n = st["p"], st["lz"]
+        self.NA, self.logZ = NA.view(K), logZ.view(())
+        if sharding.enabled():
+            Gs, self.logZ, self.NA = sharding.all_reduce_packed([Gs, self.logZ, self.NA])
+        ELBO = self.ELBO()
+        self.pi.ss_update(self.NA, lr=lr)
+        dist._update_from_gram(Gs, plan, True, lr)
+        return ELBO
 
     def _sharded_m_step(self, X, lr):
         """Rows are sharded over ranks: local Gram + ONE all-reduce of [Gram | logZ | NA], then the

@@ -354,3 +354,25 @@ def test_large_n_properties():
     g0 = G1[0, 0].double()
     S_got = g0[:d, :d] - torch.outer(g0[:d, d], g0[:d, d]) / g0[d, d]
     assert relerr(S_got, S_ref) < 2e-5
+
+
+def test_streamed_host_rows_match_device_rows():
+    """Mixture.update(X_host) (chunked H2D overlapped with the kernels) = Mixture.update(X_device)."""
+    N, K, d = 1_300_000, 64, 32
+    g = torch.Generator().manual_seed(9)
+    Xh = (torch.randn(N, d, generator=g) * 1.5 + 0.5).pin_memory()
+    ms = []
+    for X in (Xh.to(DEV), Xh):
+        torch.manual_seed(3)
+        m = V.GaussianMixtureModel(K, d)
+        m.initialize(Xh[:4096])
+        m.to(DEV)
+        m.update(X, 2)
+        ms.append(m)
+    a, b = ms
+    assert abs(float(a.ELBO_last) - float(b.ELBO_last)) <= 1e-6 * abs(float(a.ELBO_last))
+    # (the chunked Gram sums in a different order, so the second iteration's parameters differ in the last bits)
+    assert_maxabs(b.p, a.p, 1e-5, 'p')
+    assert bool((a.assignment() == b.assignment()).float().mean() > 0.9999)
+    for k in NIW_STATE:
+        assert_close(get(b, k), get(a, k), 2e-5, k)
