@@ -202,6 +202,7 @@ def main():
     torch.cuda.set_device(dev)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # keep stdout to the ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
         sharding.enable()
 
@@ -297,8 +298,18 @@ def main():
         if dom is not None:
             per_launch_flops = 2.0 * n_rows * K * D * D          # E-step GEMM or M-step Gram: 2 d^2 per update
             ach = per_launch_flops / (kern[dom]["ms_avg"] / 1e3) / 1e12
+            traffic = None
+            try:
+                tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+                if n_rows == ROWS_PER_GPU and dom in tr:
+                    traffic = tr[dom]["bytes"] / 1e9           # GB per launch, from the committed ncu capture
+            except Exception:
+                pass
             roof = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": tf32_sus, "unit": "TFLOP/s",
-                    "frac": ach / tf32_sus, "traffic": None,
+                    "frac": ach / tf32_sus, "traffic": traffic, "traffic_unit": "GB per launch (ncu dram__bytes_read+write, profiles/r01_traffic.json)",
+                    "frac_of_bf16_sustained": ach / peaks.get("bf16_tflops_sustained", 1409.1),
+                    "per_kernel_algorithmic_tflops": {k: round(per_launch_flops / (v["ms_avg"] / 1e3) / 1e12, 1)
+                                                      for k, v in kern.items() if k in ("vbmp_estep", "vbmp_gram")},
                     "peak_source": "cuBLAS TF32 8192^3 sustained, measured in this run (MEASURED_PEAKS.json holds "
                                    "bf16 only: %s burst / %s sustained TFLOP/s)" % (peaks.get("bf16_tflops"),
                                                                                    peaks.get("bf16_tflops_sustained")),

@@ -338,9 +338,11 @@ static int gu_num_sms() {
   static int n = 0;
   if (n == 0) {
     int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+        n <= 0) {
+      cudaGetLastError();
+      n = 148;
+    }
   }
   return n;
 }
@@ -353,7 +355,15 @@ static void gu_plan(long long N, int K, int D, int sms, GuArgs* g) {
   if (g->NPB < 16) g->NPB = 16;
   g->ncb = (K + GU_CB - 1) / GU_CB;
   const int tasks = g->npb * g->ncb;
-  long long sp = sms / tasks;
+  // sample splits: a multiple of the number of task groups that fit the SMs at once, with at most ~128 Ki rows per CTA.
+  // The pair-block CTAs of one (split, component block) stream the same R rows and are launched back to back, so
+  // their re-reads hit L2 as long as they do not drift apart; short tasks bound the drift (ncu: 21 GB of DRAM reads
+  // per cfg2 launch with 600 Ki-row tasks, 5.6 GB with 120 Ki-row tasks).
+  long long per_wave = sms / tasks;
+  if (per_wave < 1) per_wave = 1;
+  long long waves = (N + per_wave * 131072 - 1) / (per_wave * 131072);
+  if (waves < 1) waves = 1;
+  long long sp = per_wave * waves;
   const long long maxsp = (N + 2047) / 2048;
   if (sp > maxsp) sp = maxsp;
   if (sp < 1) sp = 1;
@@ -375,7 +385,7 @@ bool gram_umma_supported(long long N, int GX, int GP, int G, int K, int Dp, int 
 size_t gram_umma_workspace_bytes(long long N, int G, int K, int d0, int d1, int Dp) {
   if (!gram_umma_supported(N, 1, 1, G, K, Dp, d0, d1, true)) return 0;
   GuArgs g{};
-  gu_plan(N, K, d0 + d1, 512, &g);       // upper bound on the SM count -> upper bound on the number of splits
+  gu_plan(N, K, d0 + d1, gu_num_sms(), &g);   // same plan as the launch
   return (size_t)g.splits * g.Kp * g.PP * sizeof(float) + 512;
 }
 
