@@ -380,9 +380,209 @@ static void run_eseq() {
   cudaFree(dc);
 }
 
+// ---- cta_group::2: a CTA pair computes D[256 x N] = A[256 x K] B[N x K]^T; CTA r holds rows r*128.. of A (smem or TMEM),
+//      rows r*N/2.. of B in its shared memory, and receives rows r*128.. of D in its TMEM.
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
+  uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank)); return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mma2_tf32_ss(uint32_t d, uint64_t ad, uint64_t bd, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d), "l"(ad), "l"(bd), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void mma2_tf32_ts(uint32_t d, uint32_t at, uint64_t bd, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d), "r"(at), "l"(bd), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void mma2_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
+pair_kernel(const float* __restrict__ A, const float* __restrict__ Bp, float* __restrict__ D, int N, int K, int ts_mode) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar_ready, bar_mma;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t rank = cluster_ctarank();
+  const int NH = N / 2;
+  float* As = reinterpret_cast<float*>(smem);
+  float* Bs = reinterpret_cast<float*>(smem + 128 * K * 4);
+  if (tid == 0) { mbar_init(&bar_ready, 256); mbar_init(&bar_mma, 1); fence_barrier_init(); }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tm = tmem_base_s;
+  // this CTA's half of B (host-packed per half: [chunk][NH rows][4]) and its 128 rows of A
+  for (int e = tid; e < NH * K; e += 128) Bs[e] = Bp[(size_t)rank * NH * K + e];
+  const float* Ar = A + (size_t)rank * 128 * K;
+  if (!ts_mode) {
+    for (int k = 0; k < K; ++k) As[(k >> 2) * (128 * 4) + tid * 4 + (k & 3)] = Ar[tid * K + k];
+  } else {
+    for (int k0 = 0; k0 < K; k0 += 8) {
+      uint32_t r[8];
+      for (int j = 0; j < 8; ++j) r[j] = __float_as_uint(Ar[tid * K + k0 + j]);
+      tmem_st8(tm + ((uint32_t)(warp * 32) << 16) + 256 + k0, r);
+    }
+    tmem_wait_st();
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  // everyone (both CTAs) arrives on the LEADER's ready barrier
+  mbar_arrive_remote(mapa_u32(smem_u32(&bar_ready), 0));
+  if (rank == 0 && warp == 1) {
+    mbar_wait(&bar_ready, 0);
+    tc_fence_after();
+    if (elect_one()) {
+      const uint32_t idesc = idesc_tf32(256, N);
+      for (int ks = 0; ks < K / 8; ++ks) {
+        const uint64_t bd = smem_desc(smem_u32(Bs) + ks * 2 * (NH * 16), NH * 16, 128);
+        if (!ts_mode) mma2_tf32_ss(tm, smem_desc(smem_u32(As) + ks * 2 * (128 * 16), 128 * 16, 128), bd, idesc, ks > 0);
+        else mma2_tf32_ts(tm, tm + 256 + ks * 8, bd, idesc, ks > 0);
+      }
+      mma2_commit_mc(&bar_mma, 3);
+    }
+    __syncwarp();
+  }
+  mbar_wait(&bar_mma, 0);
+  tc_fence_after();
+  for (int c0 = 0; c0 < N; c0 += 16) {
+    float v[16];
+    tmem_ld16(tm + ((uint32_t)(warp * 32) << 16) + c0, v);
+    tmem_wait_ld();
+    for (int j = 0; j < 16; ++j) D[((size_t)rank * 128 + tid) * N + c0 + j] = v[j];
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tm), "n"(512));
+}
+
+static int run_pair_case(int N, int K, int ts_mode) {
+  const int NH = N / 2;
+  std::vector<float> A(256 * K), B(N * K), Bp(N * K), D(256 * N), R(256 * N);
+  for (auto& v : A) v = (float)((rand() % 17) - 8);
+  for (auto& v : B) v = (float)((rand() % 13) - 6);
+  for (int h = 0; h < 2; ++h)
+    for (int n = 0; n < NH; ++n)
+      for (int k = 0; k < K; ++k) Bp[(size_t)h * NH * K + (k >> 2) * (NH * 4) + n * 4 + (k & 3)] = B[(h * NH + n) * K + k];
+  for (int m = 0; m < 256; ++m)
+    for (int n = 0; n < N; ++n) { double s = 0; for (int k = 0; k < K; ++k) s += (double)A[m * K + k] * B[n * K + k]; R[m * N + n] = (float)s; }
+  float *dA, *dB, *dD;
+  CK(cudaMalloc(&dA, A.size() * 4)); CK(cudaMalloc(&dB, Bp.size() * 4)); CK(cudaMalloc(&dD, D.size() * 4));
+  CK(cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dB, Bp.data(), Bp.size() * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemset(dD, 0xff, D.size() * 4));
+  const size_t smem = (size_t)(128 + NH) * K * 4;
+  CK(cudaFuncSetAttribute(pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  pair_kernel<<<2, 128, smem>>>(dA, dB, dD, N, K, ts_mode);
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost));
+  int bad = 0;
+  for (int i = 0; i < 256 * N; ++i) if (fabs((double)D[i] - R[i]) > 1e-3) ++bad;
+  printf("pair (cta_group::2) %s N=%3d K=%3d : %s (mismatches %d / %d)  D[0]=%g ref %g  D[128*N]=%g ref %g  D[last]=%g ref %g\n", ts_mode ? "TS" : "SS", N, K,
+         bad ? "FAIL" : "ok", bad, 256 * N, D[0], R[0], D[128 * N], R[128 * N], D[256 * N - 1], R[256 * N - 1]);
+  cudaFree(dA); cudaFree(dB); cudaFree(dD);
+  return bad != 0;
+}
+
+// Replays the CURRENT E-step MMA sequence (128-column interleaved groups: N = 128 - 16 ks on the column suffix, 3 split
+// terms, A in TMEM, two halves) with static operands.  MODE 0: tri-skip, 1: dense N = 128, 2: tri-skip rounded up to N % 32 == 0,
+// 3: tri-skip, one term only (8 MMAs per half)
+template <int MODE>
+__global__ void __launch_bounds__(128, 1) eseq2_kernel(int groups, long long* cycles) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar_mma;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  float* Bs = reinterpret_cast<float*>(smem);
+  for (int e = tid; e < 5 * 10240; e += 128) Bs[e] = (float)((e * 37) % 7 - 3);      // 5 stages x 40 KB
+  fence_proxy_async();
+  if (tid == 0) { mbar_init(&bar_mma, 1); fence_barrier_init(); }
+  if (warp == 0) tmem_alloc<512>(&tmem_base_s);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tm = tmem_base_s;
+  {
+    uint32_t r[16];
+    for (int j = 0; j < 16; ++j) r[j] = __float_as_uint((float)(j - 8));
+    for (int c = 0; c < 256; c += 16) tmem_st16(tm + ((uint32_t)(warp * 32) << 16) + c, r);
+    tmem_wait_st();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) {
+    const long long t0 = clock64();
+    for (int g = 0; g < groups; ++g) {
+      const uint32_t sbase = smem_u32(smem) + (g % 5) * 40960;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const uint32_t dcol = tm + 256 + h * 128;
+        const uint32_t a_hi = tm + h * 128, a_lo = a_hi + 64;
+        if (elect_one()) {
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {
+            int n0 = 16 * ks, nn = 128 - n0;
+            if (MODE == 1) { n0 = 0; nn = 128; }
+            if (MODE == 2) { nn = (nn + 31) / 32 * 32; n0 = 128 - nn; }
+            int off = 0;
+            for (int i = 0; i < ks; ++i) off += (128 - 16 * i) * 32;
+            const uint32_t idesc = idesc_tf32(128, nn);
+            const uint64_t b_hi = smem_desc(sbase + off, nn * 16, 128);
+            const uint64_t b_lo = smem_desc(sbase + 18432 + off, nn * 16, 128);
+            mma_tf32_ts(dcol + n0, a_lo + ks * 8, b_hi, idesc, ks > 0);
+            if (MODE != 3) {
+              mma_tf32_ts(dcol + n0, a_hi + ks * 8, b_lo, idesc, 1);
+              mma_tf32_ts(dcol + n0, a_hi + ks * 8, b_hi, idesc, 1);
+            }
+          }
+        }
+        __syncwarp();
+      }
+    }
+    if (elect_one()) mma_commit(&bar_mma);
+    __syncwarp();
+    mbar_wait(&bar_mma, 0);
+    const long long t1 = clock64();
+    if ((tid & 31) == 0) cycles[blockIdx.x] = t1 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tm);
+}
+
+template <int MODE>
+static void run_eseq2() {
+  const int groups = 3000, grid = 148;
+  long long* dc; CK(cudaMalloc(&dc, grid * sizeof(long long)));
+  const int smem = 5 * 40960;
+  CK(cudaFuncSetAttribute(eseq2_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  eseq2_kernel<MODE><<<grid, 128, smem>>>(100, dc);
+  CK(cudaDeviceSynchronize());
+  eseq2_kernel<MODE><<<grid, 128, smem>>>(groups, dc);
+  CK(cudaDeviceSynchronize());
+  std::vector<long long> c(grid);
+  CK(cudaMemcpy(c.data(), dc, grid * sizeof(long long), cudaMemcpyDeviceToHost));
+  long long mx = 0; for (auto v : c) if (v > mx) mx = v;
+  printf("eseq2 mode=%d : %.1f cycles per group (2 components x 256 rows)\n", MODE, (double)mx / groups);
+  cudaFree(dc);
+}
+
 int main(int argc, char** argv) {
   srand(1);
   int fails = 0;
+  if (argc > 1 && atoi(argv[1]) == 6) { run_eseq2<0>(); run_eseq2<1>(); run_eseq2<2>(); run_eseq2<3>(); return 0; }
+  if (argc > 1 && atoi(argv[1]) == 5) { int f = 0; for (int ts = 0; ts < 2; ++ts) for (int N : {64, 128, 224, 256}) for (int K : {8, 32}) f += run_pair_case(N, K, ts); printf("pair probe: %d failing\n", f); return f; }
   if (argc > 1 && atoi(argv[1]) == 4) { run_eseq<false, 0>(); run_eseq<true, 0>(); run_eseq<true, 1>(); run_eseq<true, 2>(); run_eseq<false, 1>(); return 0; }
   if (argc > 1 && atoi(argv[1]) == 3) { run_trunc_test(); return 0; }
   if (argc > 1 && atoi(argv[1]) == 2) {
