@@ -101,6 +101,7 @@ struct EuSmem {
   uint64_t full[EU_MAXSTAGE], empty[EU_MAXSTAGE];
   uint64_t tfull[2], tempty[2];
   uint64_t afull;
+  uint64_t turn[2];           // issue token between the two MMA warps
   uint32_t tmem_base;
   double red[8];
 };
@@ -126,6 +127,7 @@ estep_umma_kernel(EstepArgs a, const uint8_t* __restrict__ Wp, int ntiles, int n
     for (int s = 0; s < nstage; ++s) { mbar_init(&S->full[s], 1); mbar_init(&S->empty[s], 2 + 256); }
     for (int h = 0; h < 2; ++h) { mbar_init(&S->tfull[h], 1); mbar_init(&S->tempty[h], 128); }
     mbar_init(&S->afull, 256);
+    mbar_init(&S->turn[0], 1); mbar_init(&S->turn[1], 1);
     fence_barrier_init();
   }
   if (MODE == 1) for (int k = tid; k < K; k += EU_THREADS) NAacc[k] = 0.0;
@@ -153,7 +155,9 @@ estep_umma_kernel(EstepArgs a, const uint8_t* __restrict__ Wp, int ntiles, int n
       }
   } else if (warp <= 2) {
     // ================= MMA issuers: warp 1 drives half 0, warp 2 half 1 =================
-    // (one issuer per half: the barrier waits / descriptor set-up of one half overlap the other half's MMAs)
+    // (one issuer per half: the barrier waits / descriptor set-up of one half overlap the other half's MMAs).  The two
+    // take strict turns through a token: if their bursts interleaved in the tensor-pipe FIFO both halves would finish
+    // together and both epilogue round trips would be exposed; in turn order half 0's epilogue runs under half 1's MMAs.
     const int h = warp - 1;
     const uint32_t dcol = tm + 256 + h * EU_N;
     const uint32_t a_hi = tm + h * 2 * DP, a_lo = a_hi + DP;
@@ -167,6 +171,7 @@ estep_umma_kernel(EstepArgs a, const uint8_t* __restrict__ Wp, int ntiles, int n
         mbar_wait(&S->full[s], n & 1);
         const uint64_t sb = (uint64_t)((smem_u32(stages) + (uint32_t)s * C::STAGE) >> 4);
         mbar_wait(&S->tempty[h], (uint32_t)(it & 1) ^ 1);
+        mbar_wait(&S->turn[h], h == 0 ? ((uint32_t)(it & 1) ^ 1) : (uint32_t)(it & 1));     // my turn
         tc_fence_after();
         if (elect_one()) {
 #pragma unroll
@@ -179,6 +184,7 @@ estep_umma_kernel(EstepArgs a, const uint8_t* __restrict__ Wp, int ntiles, int n
           }
           mma_commit(&S->tfull[h]);
           mma_commit(&S->empty[s]);
+          mbar_arrive(&S->turn[h ^ 1]);                 // pass the token
         }
         __syncwarp();
       }
