@@ -96,6 +96,16 @@ int vbmp_mnw_kl(const float* mu_0, const float* mu, const float* invV_0, const f
                 const float* nu_0, const float* nu, const float* logdet_invU, const float* logdet_invU_0,
                 int C, int n, int pp, float* out, void* stream);
 
+/* ---- K6: HMM forward-backward -----------------------------------------------------------
+ * HMM.forward_backward_logits — models/HMM.py:72-105 (called by HMM.update_states :119-132 with the output of
+ * obs_logits).  logits (T, S, K): observation log-likelihoods, S sequences (all sample / batch dims but time,
+ * flattened; sequence s uses parameter group s % G); trans (G, K, K) = transition.loggeomean(), init (G, K) =
+ * initial.loggeomean(); K <= 32.  Outputs: p (T, S, K) posterior state probabilities (softmax of the smoothed
+ * log-marginals divided by ptemp), SEzz (S, K, K) expected transition counts incl. the initial step, SEz0 (S, K),
+ * logZ (S).  p may not alias logits.                                                                          */
+int vbmp_hmm_forward_backward(const float* logits, const float* trans, const float* init, int T, long long S, int G, int K,
+                              float ptemp, float* p, float* SEzz, float* SEz0, float* logZ, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -50,6 +50,7 @@ EXPORTS = (
     "vbmp_version", "vbmp_last_error", "vbmp_niw_prep", "vbmp_mnw_prep", "vbmp_estep_workspace_bytes",
     "vbmp_estep", "vbmp_gram_workspace_bytes", "vbmp_gram", "vbmp_wishart_update", "vbmp_niw_update",
     "vbmp_mnw_update", "vbmp_wishart_elogdet", "vbmp_wishart_kl", "vbmp_niw_kl", "vbmp_mnw_kl",
+    "vbmp_hmm_forward_backward",
 )
 
 
@@ -262,3 +263,15 @@ def mnw_kl(mu0, mu, invV0, V, ldV, ldV0, invU0, U, nu0, nu, ldU, ldU0, C, n, pp)
                              _ptr(nu0), _ptr(nu), _ptr(ldU), _ptr(ldU0), c_int(C), c_int(n), c_int(pp), _ptr(out),
                              _stream(U.device))
     return out
+
+
+def hmm_forward_backward(logits, trans, init, T, S, G, K, ptemp):
+    """logits (T,S,K), trans (G,K,K), init (G,K) contiguous fp32 -> p (T,S,K), SEzz (S,K,K), SEz0 (S,K), logZ (S)."""
+    dev = logits.device
+    p = torch.empty((T, S, K), dtype=torch.float32, device=dev)
+    SEzz = torch.empty((S, K, K), dtype=torch.float32, device=dev)
+    SEz0 = torch.empty((S, K), dtype=torch.float32, device=dev)
+    logZ = torch.empty((S,), dtype=torch.float32, device=dev)
+    _call("vbmp_hmm_forward_backward", _ptr(logits), _ptr(trans), _ptr(init), c_int(T), c_longlong(S), c_int(G), c_int(K),
+          c_float(float(ptemp)), _ptr(p), _ptr(SEzz), _ptr(SEz0), _ptr(logZ), _stream(dev))
+    return p, SEzz, SEz0, logZ

@@ -41,6 +41,7 @@ int launch_wishart_elogdet(const float*, const float*, int, int, float*, cudaStr
 int launch_wishart_kl(const float*, const float*, const float*, const float*, const float*, const float*, int, int, float*, cudaStream_t);
 int launch_niw_kl(const float*, const float*, const float*, const float*, const float*, const float*, const float*, const float*, const float*, const float*, int, int, float*, cudaStream_t);
 int launch_mnw_kl(const float*, const float*, const float*, const float*, const float*, const float*, const float*, const float*, const float*, const float*, const float*, const float*, int, int, int, float*, cudaStream_t);
+int launch_hmm_fb(const float*, const float*, const float*, int, long long, int, int, float, float*, float*, float*, float*, cudaStream_t);
 // tcgen05 variants (estep_umma.cu / gram_umma.cu)
 bool estep_umma_supported(long long N, int GX, int G, int K, int Dp, int d0, int d1);
 size_t estep_umma_workspace_bytes(long long N, int G, int K, int Dp, int mode);
@@ -199,6 +200,12 @@ int vbmp_mnw_kl(const float* mu_0, const float* mu, const float* invV_0, const f
                 const float* nu_0, const float* nu, const float* logdet_invU, const float* logdet_invU_0,
                 int C, int n, int pp, float* out, void* stream) {
   return launch_mnw_kl(mu_0, mu, invV_0, V, logdetinvV, logdetinvV_0, invU_0, U, nu_0, nu, logdet_invU, logdet_invU_0, C, n, pp, out, (cudaStream_t)stream);
+}
+
+int vbmp_hmm_forward_backward(const float* logits, const float* trans, const float* init, int T, long long S, int G, int K,
+                              float ptemp, float* p, float* SEzz, float* SEz0, float* logZ, void* stream) {
+  if (p == logits) { set_error("hmm_forward_backward: p must not alias logits"); return VBMP_ERR_SHAPE; }
+  return launch_hmm_fb(logits, trans, init, T, S, G, K, ptemp, p, SEzz, SEz0, logZ, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -2,7 +2,7 @@
 
 The emission E-step (obs_logits -> K1 + K2, mode 0) and M-step (raw_update -> weighted Gram +
 update kernel) run in libvbmp_b200.so with the (T, S) sample axes flattened.  The forward-backward
-recursion between them is the "next" row §8f #1: here it is a batched torch recursion on the device.
+recursion between them is one CUDA kernel for K <= 32 states (csrc/hmm_fb.cu).
 """
 from __future__ import annotations
 
@@ -48,9 +48,32 @@ class HMM():
         return self
 
     def forward_backward_logits(self, fw_logits):
-        """models/HMM.py:72-105: log-space filter, backward smoother, expected transition counts."""
+        """models/HMM.py:72-105: log-space filter, backward smoother, expected transition counts.
+
+        On the device with K <= 32 states this is ONE kernel (vbmp_hmm_forward_backward: a warp per sequence for the
+        whole recursion); otherwise the same recursion as batched torch ops on the tensor's device."""
         tr = self.transition.loggeomean()
         init = self.initial.loggeomean()
+        T = fw_logits.shape[0]
+        K = fw_logits.shape[-1]
+        if fw_logits.is_cuda and K <= 32 and T >= 1 and fw_logits.numel() > 0:
+            from . import _lib
+            dev = fw_logits.device
+            rest = tuple(fw_logits.shape[1:-1])                  # other sample dims + batch dims (batch dims last)
+            G = 1
+            for b in self.batch_shape:
+                G *= int(b)
+            S = 1
+            for r in rest:
+                S *= int(r)
+            lg = _lib.f32(fw_logits, dev).reshape(T, S, K)
+            trf = _lib.f32(tr.expand(tuple(self.batch_shape) + (K, K)), dev).reshape(G, K, K)
+            inf = _lib.f32(init.expand(tuple(self.batch_shape) + (K,)), dev).reshape(G, K)
+            p, SEzz, SEz0, logZ = _lib.hmm_forward_backward(lg, trf, inf, T, S, G, K, float(self.ptemp))
+            return (p.view(fw_logits.shape), SEzz.view(rest + (K, K)), SEz0.view(rest + (K,)), logZ.view(rest))
+        return self._forward_backward_torch(fw_logits, tr, init)
+
+    def _forward_backward_torch(self, fw_logits, tr, init):
         T = fw_logits.shape[0]
         fw = torch.empty_like(fw_logits)
         fw[0] = _lse(init.unsqueeze(-1) + tr + fw_logits[0].unsqueeze(-2), -2)

@@ -106,3 +106,32 @@ def test_gram_is_deterministic_run_to_run():
     r2 = _lib.estep(z0, None, 40000, 1, xg, W, m, cst, 1, 64, Dp, 1)
     for u, v in zip(r1, r2):
         assert torch.equal(u, v)
+
+
+@pytest.mark.parametrize("T,S,G,K,ptemp", [(50, 37, 1, 5, 1.0), (128, 64, 1, 32, 1.0), (17, 12, 3, 24, 2.0), (1, 9, 1, 4, 1.0)])
+def test_hmm_forward_backward_kernel(T, S, G, K, ptemp):
+    """K6 against the torch restatement of models/HMM.py:72-105 in fp64 (same recursion, batched ops)."""
+    import pyvbmp_b200 as V
+    g = torch.Generator(device=DEV).manual_seed(T + K)
+    rest = (S, G) if G > 1 else (S,)
+    logits = 3.0 * torch.randn((T,) + rest + (K,), generator=g, device=DEV) - 5.0
+    tr = torch.log_softmax(torch.randn((G, K, K) if G > 1 else (K, K), generator=g, device=DEV), -1)
+    init = torch.log_softmax(torch.randn((G, K) if G > 1 else (K,), generator=g, device=DEV), -1)
+
+    class _D:        # stand-ins for the Dirichlet nodes: only loggeomean() is used
+        def __init__(self, v): self.v = v
+        def loggeomean(self): return self.v
+    h = V.HMM.__new__(V.HMM)
+    h.batch_shape = (G,) if G > 1 else ()
+    h.event_shape = (K,)
+    h.ptemp = ptemp
+    h.transition, h.initial = _D(tr), _D(init)
+    p, SEzz, SEz0, logZ = h.forward_backward_logits(logits.clone())
+    h.transition, h.initial = _D(tr.double()), _D(init.double())
+    pr, SEzzr, SEz0r, logZr = h._forward_backward_torch(logits.double(), tr.double(), init.double())
+    assert p.shape == pr.shape and SEzz.shape == SEzzr.shape and SEz0.shape == SEz0r.shape and logZ.shape == logZr.shape
+    assert float((p.double() - pr).abs().max()) < 2e-5
+    assert float((SEzz.double() - SEzzr).abs().max()) < 1e-4 * max(1.0, float(SEzzr.abs().max()))
+    assert float((SEz0.double() - SEz0r).abs().max()) < 2e-5
+    assert float(((logZ.double() - logZr).abs() / logZr.abs().clamp_min(1.0)).max()) < 1e-5
+    assert bool((p.argmax(-1) == pr.argmax(-1)).float().mean() > 0.999)
