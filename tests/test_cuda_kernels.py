@@ -32,7 +32,10 @@ def _problem(N, d0, d1, K, seed=0, spread=1.0):
 
 
 CASES = [(5000, 64, 0, 256), (66000, 64, 0, 256), (3001, 32, 32, 64), (4099, 16, 16, 32), (2500, 16, 0, 8),
-         (6000, 48, 0, 20), (300, 64, 0, 16)]
+         (6000, 48, 0, 20), (300, 64, 0, 16),
+         # edges of the tensor-core kernels' shape windows: one row past a tile / chunk, smallest and largest K, ragged
+         # feature counts that need zero padding, K not a multiple of the 128-component block
+         (257, 64, 0, 4), (2048, 8, 8, 4), (2049, 64, 0, 512), (4097, 20, 12, 36), (9000, 64, 0, 132), (2304, 32, 0, 260)]
 
 
 @pytest.mark.parametrize("N,d0,d1,K", CASES)
