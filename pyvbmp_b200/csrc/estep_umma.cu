@@ -18,8 +18,9 @@
 //     n >= 8 CG ks: the MMA is issued with N = 128 - 8 CG ks on that suffix and only that suffix of B is
 //     stored / copied (56 % of the dense work at DP = 64).
 //   * one 128-column accumulator per half in TMEM; the halves ping-pong (the epilogue of half 0 runs under the
-//     MMAs of half 1).  8 epilogue warps (one thread per sample row) read D with tcgen05.ld, add -m_k and
-//     square-reduce with packed fp32x2 FADD2 / FFMA2, keep an online logsumexp and write the logits.  For mode 1 the tile's rows are then
+//     MMAs of half 1).  The accumulator is initialised to -m_k by one extra K-step (a constant block of ones against
+//     [-m_hi; -m_lo], the only shared-memory A operand), so the 8 epilogue warps (one thread per sample row) only read
+//     D with tcgen05.ld, square-reduce with packed fp32x2 FFMA2, keep an online logsumexp and write the logits.  For mode 1 the tile's rows are then
 //     normalised in place (the re-read hits L2) with coalesced float4 accesses, accumulating NA per CTA in a
 //     fixed order (deterministic).
 #include <cstdlib>
@@ -48,12 +49,16 @@ struct EuCfg {
   }
   static constexpr int WB = blk_off(KS);      // bytes of one operand image (hi or lo) of a group
   static constexpr int GB = 2 * WB;           // hi image then lo image
-  static constexpr int MB = EU_N * 4;         // -m in column order
+  static constexpr int MB = EU_N * 32;        // the "-m" operand block: one K-step (k = 0: -m_hi, k = 1: -m_lo, rest 0)
   static constexpr int REC = GB + MB + 32;    // + cst of the CG components
   static constexpr int STAGE = (REC + 127) / 128 * 128;
   // component / feature of column n
   __host__ __device__ static constexpr int col_cl(int n) { return (n % (CG * 8)) / 8; }
   __host__ __device__ static constexpr int col_j(int n) { return (n / (CG * 8)) * 8 + n % 8; }
+  // descriptor of the -m block relative to a stage at shared address 0
+  __host__ __device__ static constexpr uint64_t desc_m() {
+    return (uint64_t)(GB >> 4) | ((uint64_t)((EU_N * 16) >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) | (1ull << 46);
+  }
   // descriptor of K-step block ks (lo = 0/1) relative to a stage at shared address 0 (add stage_addr >> 4)
   __host__ __device__ static constexpr uint64_t desc0(int ks, int lo) {
     return (uint64_t)((blk_off(ks) + lo * WB) >> 4) | ((uint64_t)((nn(ks) * 16) >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) |
@@ -71,11 +76,23 @@ __global__ void estep_pack_kernel(const float* __restrict__ W, const float* __re
   const int g = blockIdx.x;
   float* hi = reinterpret_cast<float*>(Wp + (size_t)g * C::REC);
   float* lo = reinterpret_cast<float*>(Wp + (size_t)g * C::REC + C::WB);
+  // -m as a K-major operand block [chunk (2)][column n (128)][4 floats]: k = 0 holds -m_hi, k = 1 holds -m_lo.  It meets a
+  // constant A block of ones (k = 0, 1) in ONE extra MMA that initialises the accumulator to -m, so y - m comes out of
+  // the tensor core and the epilogue only squares: the epilogue's -m loads were ~900 shared-memory wavefronts per group,
+  // as much as the MMA operand fetch, and the shared-memory pipe is what both compete for.
   float* mo = reinterpret_cast<float*>(Wp + (size_t)g * C::REC + C::GB);
   float* co = reinterpret_cast<float*>(Wp + (size_t)g * C::REC + C::GB + C::MB);
-  for (int o = threadIdx.x; o < EU_N; o += blockDim.x) {
-    const int c = g * C::CG + C::col_cl(o);
-    mo[o] = c < K ? -m[(size_t)c * DP + C::col_j(o)] : 0.f;
+  for (int o = threadIdx.x; o < EU_N * 8; o += blockDim.x) {
+    const int ch = o / (EU_N * 4), n = (o % (EU_N * 4)) / 4, e = o % 4;
+    float v = 0.f;
+    if (ch == 0 && e < 2) {
+      const int c = g * C::CG + C::col_cl(n);
+      const float mv = c < K ? m[(size_t)c * DP + C::col_j(n)] : 0.f;
+      uint32_t h, l;
+      split_tf32(mv, h, l);
+      v = e == 0 ? -__uint_as_float(h) : -__uint_as_float(l);
+    }
+    mo[o] = v;
   }
   for (int o = threadIdx.x; o < 8; o += blockDim.x) {
     const int c = g * C::CG + o;
@@ -116,7 +133,8 @@ estep_umma_kernel(EstepArgs a, const uint8_t* __restrict__ Wp, int ntiles, int n
   using C = EuCfg<DP>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* stages = smem_raw;                                             // EU_NSTAGE * STAGE
-  EuSmem* S = reinterpret_cast<EuSmem*>(stages + nstage * C::STAGE);
+  float* ones = reinterpret_cast<float*>(stages + nstage * C::STAGE);     // A block [chunk (2)][row (128)][4]: 1 at k = 0, 1
+  EuSmem* S = reinterpret_cast<EuSmem*>(stages + nstage * C::STAGE + 4096);
   float* lz = reinterpret_cast<float*>(S + 1);                            // [256]
   float* colsum = lz + EU_TILE;                                           // [8][K]     (mode 1)
   double* NAacc = reinterpret_cast<double*>(colsum + 8 * a.K);            // [K]        (mode 1)
@@ -131,6 +149,8 @@ estep_umma_kernel(EstepArgs a, const uint8_t* __restrict__ Wp, int ntiles, int n
     fence_barrier_init();
   }
   if (MODE == 1) for (int k = tid; k < K; k += EU_THREADS) NAacc[k] = 0.0;
+  for (int o = tid; o < 1024; o += EU_THREADS) ones[o] = (o < 512 && (o & 3) < 2) ? 1.f : 0.f;
+  fence_proxy_async();
   if (warp == 1) tmem_alloc<512>(&S->tmem_base);
   tc_fence_before();
   __syncthreads();
@@ -161,6 +181,7 @@ estep_umma_kernel(EstepArgs a, const uint8_t* __restrict__ Wp, int ntiles, int n
     const int h = warp - 1;
     const uint32_t dcol = tm + 256 + h * EU_N;
     const uint32_t a_hi = tm + h * 2 * DP, a_lo = a_hi + DP;
+    const uint64_t ones_desc = smem_desc(smem_u32(ones), 128 * 16, 128);
     long long it = 0;
     for (int t = 0; t < my_tiles; ++t) {
       mbar_wait(&S->afull, t & 1);
@@ -174,11 +195,12 @@ estep_umma_kernel(EstepArgs a, const uint8_t* __restrict__ Wp, int ntiles, int n
         mbar_wait(&S->turn[h], h == 0 ? ((uint32_t)(it & 1) ^ 1) : (uint32_t)(it & 1));     // my turn
         tc_fence_after();
         if (elect_one()) {
+          mma_tf32_ss(dcol, ones_desc, C::desc_m() + sb, idesc_tf32(128, EU_N), 0);   // D = -m
 #pragma unroll
           for (int ks = 0; ks < C::KS; ++ks) {
             const uint32_t idesc = idesc_tf32(128, C::nn(ks));
             const uint64_t b_hi = C::desc0(ks, 0) + sb, b_lo = C::desc0(ks, 1) + sb;
-            mma_tf32_ts(dcol + C::n0(ks), a_lo + ks * 8, b_hi, idesc, ks > 0);   // small terms first
+            mma_tf32_ts(dcol + C::n0(ks), a_lo + ks * 8, b_hi, idesc, 1);        // small terms first
             mma_tf32_ts(dcol + C::n0(ks), a_hi + ks * 8, b_lo, idesc, 1);
             mma_tf32_ts(dcol + C::n0(ks), a_hi + ks * 8, b_hi, idesc, 1);
           }
@@ -242,7 +264,6 @@ estep_umma_kernel(EstepArgs a, const uint8_t* __restrict__ Wp, int ntiles, int n
       float l4[4];
       for (int g = 0; g < ngroups; ++g, ++it) {
         const int s = (int)(it % nstage);
-        const float2* nm = reinterpret_cast<const float2*>(stages + (size_t)s * C::STAGE + C::GB);   // -m, column order
         const float* cstage = reinterpret_cast<const float*>(stages + (size_t)s * C::STAGE + C::GB + C::MB);
         mbar_wait(&S->tfull[h], (uint32_t)(it & 1));
         mbar_wait(&S->full[s], (uint32_t)(it / nstage) & 1);   // already complete; acquires the stage's m / cst
@@ -262,9 +283,9 @@ estep_umma_kernel(EstepArgs a, const uint8_t* __restrict__ Wp, int ntiles, int n
         tc_fence_before();
         mbar_arrive(&S->tempty[h]);
 #pragma unroll
-        for (int j = 0; j < EU_N; j += 2) {
+        for (int j = 0; j < EU_N; j += 2) {                   // y already holds W^T z - m
           const int cl = C::col_cl(j);                        // columns j, j+1 belong to the same component
-          const float2 r = __fadd2_rn(make_float2(y[j], y[j + 1]), nm[j >> 1]);
+          const float2 r = make_float2(y[j], y[j + 1]);
           q[cl] = __ffma2_rn(r, r, q[cl]);
         }
 #pragma unroll
@@ -402,7 +423,7 @@ static int eu_launch(EstepArgs a, int mode, uint8_t* Wp, float* NA_part, double*
   if (rc) return rc;
   const int ntiles = (int)((a.N + EU_TILE - 1) / EU_TILE);
   const int grid = ntiles < eu_num_sms() ? ntiles : eu_num_sms();
-  const size_t fixed = sizeof(EuSmem) + EU_TILE * sizeof(float) +
+  const size_t fixed = 4096 + sizeof(EuSmem) + EU_TILE * sizeof(float) +
                        (mode == 1 ? (size_t)8 * a.K * sizeof(float) + (size_t)a.K * sizeof(double) : 0) + 64;
   int nstage = (int)((227 * 1024 - fixed) / C::STAGE);
   if (nstage > EU_MAXSTAGE) nstage = EU_MAXSTAGE;

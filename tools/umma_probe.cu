@@ -540,6 +540,10 @@ __global__ void __launch_bounds__(128, 1) eseq2_kernel(int groups, long long* cy
             const uint32_t idesc = idesc_tf32(128, nn);
             const uint64_t b_hi = smem_desc(sbase + off, nn * 16, 128);
             const uint64_t b_lo = smem_desc(sbase + 18432 + off, nn * 16, 128);
+            if (MODE == 4 && ks == 0) {
+              mma_tf32_ss(dcol, smem_desc(sbase + 36864, 128 * 16, 128), smem_desc(sbase + 18432, 128 * 16, 128), idesc_tf32(128, 128), 0);
+              mma_tf32_ts(dcol + n0, a_lo + ks * 8, b_hi, idesc, 1);
+            } else
             mma_tf32_ts(dcol + n0, a_lo + ks * 8, b_hi, idesc, ks > 0);
             if (MODE != 3) {
               mma_tf32_ts(dcol + n0, a_hi + ks * 8, b_lo, idesc, 1);
@@ -581,7 +585,7 @@ static void run_eseq2() {
 int main(int argc, char** argv) {
   srand(1);
   int fails = 0;
-  if (argc > 1 && atoi(argv[1]) == 6) { run_eseq2<0>(); run_eseq2<1>(); run_eseq2<2>(); run_eseq2<3>(); return 0; }
+  if (argc > 1 && atoi(argv[1]) == 6) { run_eseq2<0>(); run_eseq2<1>(); run_eseq2<2>(); run_eseq2<3>(); run_eseq2<4>(); return 0; }
   if (argc > 1 && atoi(argv[1]) == 5) { int f = 0; for (int ts = 0; ts < 2; ++ts) for (int N : {64, 128, 224, 256}) for (int K : {8, 32}) f += run_pair_case(N, K, ts); printf("pair probe: %d failing\n", f); return f; }
   if (argc > 1 && atoi(argv[1]) == 4) { run_eseq<false, 0>(); run_eseq<true, 0>(); run_eseq<true, 1>(); run_eseq<true, 2>(); run_eseq<false, 1>(); return 0; }
   if (argc > 1 && atoi(argv[1]) == 3) { run_trunc_test(); return 0; }
