@@ -135,8 +135,8 @@ estep_umma_kernel(EstepArgs a, const uint8_t* __restrict__ Wp, int ntiles, int n
   uint8_t* stages = smem_raw;                                             // EU_NSTAGE * STAGE
   float* ones = reinterpret_cast<float*>(stages + nstage * C::STAGE);     // A block [chunk (2)][row (128)][4]: 1 at k = 0, 1
   EuSmem* S = reinterpret_cast<EuSmem*>(stages + nstage * C::STAGE + 4096);
-  float* lz = reinterpret_cast<float*>(S + 1);                            // [256]
-  float* colsum = lz + EU_TILE;                                           // [8][K]     (mode 1)
+  float* lz = reinterpret_cast<float*>(S + 1);                            // [2][256] (tile parity)
+  float* colsum = lz + 2 * EU_TILE;                                           // [8][K]     (mode 1)
   double* NAacc = reinterpret_cast<double*>(colsum + 8 * a.K);            // [K]        (mode 1)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int K = a.K;
@@ -220,6 +220,65 @@ estep_umma_kernel(EstepArgs a, const uint8_t* __restrict__ Wp, int ntiles, int n
     const int D = a.d0 + a.d1;
     double lzsum = 0.0;
     long long it = 0;
+    // ---- deferred normalisation (mode 1).  p = exp(l - logZ_n) of tile t is written while the MMAs of tile t+1 run: after
+    //      each of the next tile's first 16 group epilogues every warp normalises two more rows of the previous tile (L2
+    //      hits), accumulating the column sums in its shared-memory row of `colsum`; after slice 15 the 8 rows are added
+    //      in a fixed order into NAacc.  Done synchronously at the tile end this pass cost 7 % of the kernel.
+    const int K4 = K >> 2;
+    int pend_t = -1;                                            // local index of the tile whose rows await normalisation
+    auto norm_slice = [&](int pt, int k) {
+      const long long row0 = ((long long)blockIdx.x + (long long)pt * gridDim.x) * EU_TILE;
+      const long long rem = a.N - row0;
+      const int rows = rem < EU_TILE ? (int)rem : EU_TILE;
+      const float* lzp = lz + (pt & 1) * EU_TILE;
+      const int r = w8 + 16 * k;
+      float4 x[2][EU_MAXK / 128];
+#pragma unroll
+      for (int v = 0; v < 2; ++v) {
+        const int rr = r + 8 * v;
+        const float4* prow = reinterpret_cast<const float4*>(a.out + (size_t)(row0 + (rr < rows ? rr : 0)) * K);
+#pragma unroll
+        for (int u = 0; u < EU_MAXK / 128; ++u) {
+          const int c4 = lane + 32 * u;
+          if (c4 < K4 && rr < rows) x[v][u] = __ldcg(prow + c4);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < EU_MAXK / 128; ++u) {
+        const int c4 = lane + 32 * u;
+        if (c4 < K4) {
+          float4 cs = *reinterpret_cast<float4*>(colsum + (size_t)w8 * K + 4 * c4);
+#pragma unroll
+          for (int v = 0; v < 2; ++v) {
+            const int rr = r + 8 * v;
+            if (rr < rows) {
+              const float lzr = lzp[rr];
+              float4 y = x[v][u];
+              y.x = expf(y.x - lzr); y.y = expf(y.y - lzr); y.z = expf(y.z - lzr); y.w = expf(y.w - lzr);
+              reinterpret_cast<float4*>(a.out + (size_t)(row0 + rr) * K)[c4] = y;
+              cs.x += y.x; cs.y += y.y; cs.z += y.z; cs.w += y.w;
+            }
+          }
+          *reinterpret_cast<float4*>(colsum + (size_t)w8 * K + 4 * c4) = cs;
+        }
+      }
+    };
+    auto norm_finish = [&]() {
+      named_bar_sync(1, 256);
+      for (int k = wtid; k < K; k += 256) {
+        float sacc = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) { sacc += colsum[(size_t)w * K + k]; }      // fixed order
+        NAacc[k] += (double)sacc;
+      }
+      named_bar_sync(1, 256);
+      for (int k = wtid; k < 8 * K; k += 256) colsum[k] = 0.f;
+      named_bar_sync(1, 256);
+    };
+    if (MODE == 1) {
+      for (int k = wtid; k < 8 * K; k += 256) colsum[k] = 0.f;
+      named_bar_sync(1, 256);
+    }
     for (int t = 0; t < my_tiles; ++t) {
       const long long tile = (long long)blockIdx.x + (long long)t * gridDim.x;
       const long long row = tile * EU_TILE + rloc;
@@ -303,66 +362,28 @@ estep_umma_kernel(EstepArgs a, const uint8_t* __restrict__ Wp, int ntiles, int n
               *reinterpret_cast<float4*>(a.out + (size_t)row * K + (c - 3)) = make_float4(l4[0], l4[1], l4[2], l4[3]);
           }
         }
-        mbar_arrive(&S->empty[s]);                  // done with the stage's -m / cst (the two MMA commits are the other arrivals)
+        mbar_arrive(&S->empty[s]);                  // done with the stage's cst (the two MMA commits are the other arrivals)
+        if (MODE == 1 && pend_t >= 0 && g < 16) {
+          norm_slice(pend_t, g);
+          if (g == 15) { norm_finish(); pend_t = -1; }
+        }
+      }
+      if (MODE == 1 && pend_t >= 0) {               // fewer than 16 groups: finish the previous tile now
+        for (int k = ngroups; k < 16; ++k) norm_slice(pend_t, k);
+        norm_finish();
+        pend_t = -1;
       }
       if (MODE == 1) {
         const float v = valid ? mx + logf(sm) : 0.f;
-        lz[rloc] = v;
+        lz[(t & 1) * EU_TILE + rloc] = v;
         if (valid) { a.logZn[row] = v; lzsum += (double)v; }
-        named_bar_sync(1, 256);
-        // ---- normalise the tile's rows in place: p = exp(l - logZ_n); column sums -> NA
-        const long long row0 = tile * EU_TILE;
-        const long long rem = a.N - row0;
-        const int rows = rem < EU_TILE ? (int)rem : EU_TILE;
-        const int K4 = K >> 2;
-        float cs[EU_MAXK / 128][4];
-#pragma unroll
-        for (int u = 0; u < EU_MAXK / 128; ++u) { cs[u][0] = cs[u][1] = cs[u][2] = cs[u][3] = 0.f; }
-        for (int r = w8; r < rows; r += 16) {           // two rows in flight per warp (memory-level parallelism)
-          float4 x[2][EU_MAXK / 128];
-#pragma unroll
-          for (int v = 0; v < 2; ++v) {
-            const int rr = r + 8 * v;
-            const float4* prow = reinterpret_cast<const float4*>(a.out + (size_t)(row0 + (rr < rows ? rr : r)) * K);
-#pragma unroll
-            for (int u = 0; u < EU_MAXK / 128; ++u) {
-              const int c4 = lane + 32 * u;
-              if (c4 < K4) x[v][u] = __ldcg(prow + c4);
-            }
-          }
-#pragma unroll
-          for (int v = 0; v < 2; ++v) {
-            const int rr = r + 8 * v;
-            if (rr < rows) {
-              const float lzr = lz[rr];
-              float4* prow = reinterpret_cast<float4*>(a.out + (size_t)(row0 + rr) * K);
-#pragma unroll
-              for (int u = 0; u < EU_MAXK / 128; ++u) {
-                const int c4 = lane + 32 * u;
-                if (c4 < K4) {
-                  float4 y = x[v][u];
-                  y.x = expf(y.x - lzr); y.y = expf(y.y - lzr); y.z = expf(y.z - lzr); y.w = expf(y.w - lzr);
-                  prow[c4] = y;
-                  cs[u][0] += y.x; cs[u][1] += y.y; cs[u][2] += y.z; cs[u][3] += y.w;
-                }
-              }
-            }
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < EU_MAXK / 128; ++u) {
-          const int c4 = lane + 32 * u;
-          if (c4 < K4) *reinterpret_cast<float4*>(colsum + (size_t)w8 * K + 4 * c4) = make_float4(cs[u][0], cs[u][1], cs[u][2], cs[u][3]);
-        }
-        named_bar_sync(1, 256);
-        for (int k = wtid; k < K; k += 256) {
-          float s = 0.f;
-#pragma unroll
-          for (int w = 0; w < 8; ++w) s += colsum[(size_t)w * K + k];      // fixed order
-          NAacc[k] += (double)s;
-        }
-        // (the next tile's colsum / lz writes happen after its first named barrier)
+        named_bar_sync(1, 256);                     // the tile's logits and logZ_n are visible to all workers
+        pend_t = t;
       }
+    }
+    if (MODE == 1 && pend_t >= 0) {                 // last tile: nothing left to hide behind
+      for (int k = 0; k < 16; ++k) norm_slice(pend_t, k);
+      norm_finish();
     }
     if (MODE == 1) {
       // sum of logZ_n over this CTA's rows (fixed order: warp shuffle tree, then warps in order)
@@ -423,7 +444,7 @@ static int eu_launch(EstepArgs a, int mode, uint8_t* Wp, float* NA_part, double*
   if (rc) return rc;
   const int ntiles = (int)((a.N + EU_TILE - 1) / EU_TILE);
   const int grid = ntiles < eu_num_sms() ? ntiles : eu_num_sms();
-  const size_t fixed = 4096 + sizeof(EuSmem) + EU_TILE * sizeof(float) +
+  const size_t fixed = 4096 + sizeof(EuSmem) + 2 * EU_TILE * sizeof(float) +
                        (mode == 1 ? (size_t)8 * a.K * sizeof(float) + (size_t)a.K * sizeof(double) : 0) + 64;
   int nstage = (int)((227 * 1024 - fixed) / C::STAGE);
   if (nstage > EU_MAXSTAGE) nstage = EU_MAXSTAGE;

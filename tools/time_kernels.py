@@ -21,7 +21,9 @@ def timeit(f, n=5):
 out = torch.empty((N, 1, K), device=dev)
 if "e" in what:
     t = timeit(lambda: _lib.estep(z0, z1, N, 1, xg, W, m, cst, 1, K, Dp, 1, out=out))
-    print(f"estep mode1 N={N} K={K} D={d0+d1}: {t:.3f} ms  ({2.0*N*K*(d0+d1)**2/t/1e9:.1f} algorithmic TFLOP/s)  dbg={os.environ.get('VBMP_EU_DBG','0')}")
+    print(f"estep mode1 N={N} K={K} D={d0+d1}: {t:.3f} ms  ({2.0*N*K*(d0+d1)**2/t/1e9:.1f} algorithmic TFLOP/s)")
+    t = timeit(lambda: _lib.estep(z0, z1, N, 1, xg, W, m, cst, 1, K, Dp, 0, out=out))
+    print(f"estep mode0 N={N} K={K} D={d0+d1}: {t:.3f} ms  (logits only)")
 if "g" in what:
     p, lzn, NA, lZ = _lib.estep(z0, z1, N, 1, xg, W, m, cst, 1, K, Dp, 1)
     t = timeit(lambda: _lib.gram(z0, z1, N, 1, xg, p.view(N, 1, K), 1, xg, 1, K, Dp))
