@@ -359,11 +359,11 @@ static void gu_plan(long long N, int K, int D, int sms, GuArgs* g) {
   // The pair-block CTAs of one (split, component block) stream the same R rows and are launched back to back, so
   // their re-reads hit L2 as long as they do not drift apart; short tasks bound the drift (ncu: 21 GB of DRAM reads
   // per cfg2 launch with 600 Ki-row tasks, 5.6 GB with 120 Ki-row tasks).
-  long long per_wave = sms / tasks;
-  if (per_wave < 1) per_wave = 1;
-  long long waves = (N + per_wave * 131072 - 1) / (per_wave * 131072);
-  if (waves < 1) waves = 1;
-  long long sp = per_wave * waves;
+  // rounds of `sms` co-resident CTAs needed at <= 128 Ki rows per CTA; then as many splits as fill those rounds exactly
+  // (cfg2: 20 tasks, 5 rounds of 148 -> 37 splits = 740 CTAs), so the last round is not a partial one
+  long long rounds = ((long long)N * tasks + (long long)sms * 131072 - 1) / ((long long)sms * 131072);
+  if (rounds < 1) rounds = 1;
+  long long sp = rounds * sms / tasks;
   const long long maxsp = (N + 2047) / 2048;
   if (sp > maxsp) sp = maxsp;
   if (sp < 1) sp = 1;
