@@ -44,7 +44,6 @@ struct GuArgs {
   int Kp, PP;                        // padded partial dims: Kp = ncb*128, PP = npb*NPB
   int kcb;                           // columns of the R box = min(128, K)
   int FL;                            // chunks per first-level accumulation block
-  int dbg;                           // developer switches (VBMP_GU_DBG): 1 no MMAs, 2 no phi generation, 4 no R split
   float* part;                       // [splits][Kp][PP]
 };
 
@@ -160,7 +159,6 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant_
         const uint32_t a_hi = tm + 448 + st * 32, a_lo = a_hi + 16;
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks) {
-          if (a.dbg & 1) break;
           const uint64_t b_hi = d_hi0 + sofs + ks * dstep, b_lo = d_lo0 + sofs + ks * dstep;
           mma_tf32_ts(tm, a_lo + ks * 8, b_hi, idesc, !(first && ks == 0));
           mma_tf32_ts(tm, a_hi + ks * 8, b_lo, idesc, 1);
@@ -210,7 +208,7 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant_
       mbar_wait(&S->bempty[st], ((c >> 1) & 1) ^ 1);
       tc_fence_after();
       // ---- A operand: r[s][comp] for this thread's 8 samples, split, into TMEM
-      if (!(a.dbg & 4)) {
+      {
         const float* rawr = reinterpret_cast<const float*>(raw + (size_t)s * rawB) + (sh * 8) * kcb + comp;
         uint32_t hi[8], lo[8];
 #pragma unroll
@@ -223,7 +221,7 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant_
         tmem_st8(ad + 16, lo);
       }
       // ---- B operand: phi[s][pair] = zt[s][i] * zt[s][j] for 16 samples, split, K-major core-matrix layout
-      if (wtid < NPB && !(a.dbg & 2)) {
+      if (wtid < NPB) {
         uint8_t* bh = bst + (size_t)st * stageB + (size_t)wtid * 16;
         uint8_t* bl = bh + NPB * 64;
         const uint8_t* zi = bi + s * sli;
@@ -406,7 +404,6 @@ int launch_gram_umma(const GramArgs& a, float* gram, void* ws, size_t ws_bytes, 
   gu_plan(a.N, a.K, D, gu_num_sms(), &g);
   g.kcb = a.K < GU_CB ? a.K : GU_CB;
   g.FL = gu_fl();
-  { const char* e = getenv("VBMP_GU_DBG"); g.dbg = e ? atoi(e) : 0; }
   const size_t need = (size_t)g.splits * g.Kp * g.PP * sizeof(float) + 512;
   if (ws_bytes < need) { set_error("gram_umma: workspace too small (%zu < %zu)", ws_bytes, need); return VBMP_ERR_WORKSPACE; }
   g.part = (float*)(((size_t)ws + 255) / 256 * 256);
