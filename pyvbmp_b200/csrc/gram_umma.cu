@@ -10,7 +10,8 @@
 // dimension is the SAMPLE axis.  That is half the flops of forming (r_k o Z)^T Z per component and, unlike
 // it, needs no per-component rescaling of the sample tile: phi is shared by every component.
 //
-//   * CTA task = (128-component block) x (NPB <= 224 pair columns) x (sample split).  A operand = R^T
+//   * CTA task = (128-component block) x (NPB <= 224 pair columns) x (sample split); with an even number of component
+//     blocks two CTAs pair up (cta_group::2, M = 256, NPB <= 192 shared between them).  A operand = R^T
 //     (lanes = components, K = samples) written to TENSOR MEMORY by the workers as split TF32 (hi, lo);
 //     B operand = phi^T generated on the fly in shared memory (K-major core-matrix layout, hi / lo).
 //     D1 (first-level accumulator) and D2 (second level) both live in TMEM: D1 is folded into D2 (fp32
@@ -32,7 +33,12 @@ using namespace umma;
 constexpr int GU_THREADS = 576;      // warp 0 producer, warp 1 MMA issuer, two sets of 8 worker warps (even / odd chunks)
 constexpr int GU_SC = 16;            // samples per chunk (2 K-steps)
 constexpr int GU_NR = 4;             // raw ring depth
-constexpr int GU_NPMAX = 224;        // pair columns per CTA (D1 + D2 = 448 TMEM columns, A buffers = 64)
+// pipeline depth (B stages in shared memory = A buffers in TMEM) and pair columns per MMA.  TMEM budget: D1 + D2 = 2 NPMAX
+// columns + NSTG A buffers of hi + lo = 32 NSTG columns <= 512.  A CTA pair needs 4 stages to hide the cross-CTA barrier
+// round trips (192 columns); a single CTA is best with 2 stages and 224 columns.
+constexpr int GU_MAXSTG = 4;
+__host__ __device__ constexpr int gu_nstg(bool pair) { return pair ? 4 : 2; }
+__host__ __device__ constexpr int gu_npmax(bool pair) { return pair ? 192 : 224; }
 constexpr int GU_FL = 16;            // chunks per first-level accumulation block (256 samples)
 constexpr int GU_CB = 128;           // components per CTA
 
@@ -49,7 +55,7 @@ struct GuArgs {
 
 struct GuSmem {
   uint64_t rfull[GU_NR], rempty[GU_NR];
-  uint64_t bfull[2], bempty[2];
+  uint64_t bfull[GU_MAXSTG], bempty[GU_MAXSTG];
   uint64_t dfull, dempty;
   uint32_t tmem_base;
   float consts[2];                   // {1, 0}: the padded "1" feature and the zero used by padding pair columns
@@ -84,7 +90,10 @@ __device__ __forceinline__ void split_fast2(float2 x, uint32_t& hi0, uint32_t& h
 
 // SF = compile-time row stride (floats) of the raw Z chunk when d0 == SF and (d1 == 0 or d1 == d0), else 0 (generic);
 // R128 = the R box is 128 columns wide (K >= 128).
-template <int SF, bool R128>
+// PAIR: two CTAs (a cluster) take the two component blocks of a 256-component slab and share the phi block through
+// cta_group::2 MMAs (M = 256): each CTA generates and holds HALF of the pair columns, the hardware feeds both tensor
+// cores from both halves, so phi generation and the B-operand reads per SM halve (the shared-memory pipe is the limiter).
+template <int SF, bool R128, bool PAIR>
 __global__ void __launch_bounds__(GU_THREADS, 1)
 gram_umma_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmZ0,
                  const __grid_constant__ CUtensorMap tmZ1, GuArgs a) {
@@ -94,35 +103,42 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant_
   const int kcb = R128 ? 128 : a.kcb;
   const int rawR = GU_SC * kcb * 4, rawZ0 = GU_SC * a.d0 * 4, rawZ1 = GU_SC * a.d1 * 4;
   const int rawB = (rawR + rawZ0 + rawZ1 + 127) / 128 * 128;
-  const int stageB = 2 * a.NPB * 64;
+  constexpr int GU_NSTG = gu_nstg(PAIR), GU_NPMAX = gu_npmax(PAIR);
+  const int NH = PAIR ? a.NPB / 2 : a.NPB;                 // pair columns generated (and held as B rows) by this CTA
+  const int stageB = 2 * NH * 64;
   uint8_t* raw = smem_raw;
   uint8_t* bst = raw + GU_NR * rawB;
-  GuSmem* S = reinterpret_cast<GuSmem*>(bst + 2 * stageB);
+  GuSmem* S = reinterpret_cast<GuSmem*>(bst + GU_NSTG * stageB);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-  // task decode: blockIdx.x = (split * ncb + cb) * npb + pb
-  const int pb = blockIdx.x % a.npb;
-  const int cb = (blockIdx.x / a.npb) % a.ncb;
-  const int split = blockIdx.x / (a.npb * a.ncb);
+  // task decode: cluster (or CTA) index = (split * ncbp + cbp) * npb + pb; a pair covers component blocks 2 cbp, 2 cbp + 1
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const int task = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int ncbp = PAIR ? a.ncb / 2 : a.ncb;
+  const int pb = task % a.npb;
+  const int cb = PAIR ? 2 * ((task / a.npb) % ncbp) + (int)rank : (task / a.npb) % ncbp;
+  const int split = task / (a.npb * ncbp);
   const long long nb = (long long)split * a.S_per;
   long long ne = nb + a.S_per; if (ne > a.N) ne = a.N;
   const int nchunks = ne > nb ? (int)((ne - nb + GU_SC - 1) / GU_SC) : 0;
   const int NPB = a.NPB, FL = a.FL;
 
   if (tid == 0) {
-    for (int s = 0; s < GU_NR; ++s) { mbar_init(&S->rfull[s], 1); mbar_init(&S->rempty[s], 256); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&S->bfull[s], 256); mbar_init(&S->bempty[s], 1); }
-    mbar_init(&S->dfull, 1); mbar_init(&S->dempty, 256);
+    // one arrival per worker warp; in a pair the leader's bfull / dempty collect both CTAs' warps
+    for (int s = 0; s < GU_NR; ++s) { mbar_init(&S->rfull[s], 1); mbar_init(&S->rempty[s], 8); }
+    for (int s = 0; s < GU_NSTG; ++s) { mbar_init(&S->bfull[s], PAIR ? 16 : 8); mbar_init(&S->bempty[s], 1); }
+    mbar_init(&S->dfull, 1); mbar_init(&S->dempty, PAIR ? 16 : 8);
     S->consts[0] = 1.f; S->consts[1] = 0.f;
     fence_barrier_init();
   }
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmR); tma_prefetch_desc(&tmZ0); if (a.d1 > 0) tma_prefetch_desc(&tmZ1); }
-  if (warp == 1) tmem_alloc<512>(&S->tmem_base);
+  if (warp == 1) { if (PAIR) tmem_alloc2<512>(&S->tmem_base); else tmem_alloc<512>(&S->tmem_base); }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tm = S->tmem_base;
-  // TMEM columns: D1 [0,224), D2 [224,448), A buffers at 448 + 32*buf (hi 16 columns, lo 16 columns)
+  // TMEM columns: D1 [0,NPMAX), D2 [NPMAX,2 NPMAX), A buffers at 2 NPMAX + 32*buf (hi 16 columns, lo 16 columns)
+  constexpr int ACOL = 2 * GU_NPMAX;
 
   if (warp == 0) {
     // ================= producer: one TMA box per operand per 16-sample chunk (rows past N are zero filled) ====
@@ -141,34 +157,42 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant_
       __syncwarp();
     }
   } else if (warp == 1) {
-    // ================= MMA issuer =================
-    const uint32_t idesc = idesc_tf32(128, NPB);
-    const uint64_t dstep = (uint64_t)((2 * NPB * 16) >> 4);                 // one K-step = two 16-byte chunks
-    const uint64_t d_hi0 = smem_desc(smem_u32(bst), NPB * 16, 128), d_lo0 = d_hi0 + (uint64_t)((NPB * 64) >> 4);
-    int fc = 0, nflush = 0;
-    for (int c = 0; c < nchunks; ++c) {
-      const int st = c & 1;
-      mbar_wait(&S->bfull[st], (c >> 1) & 1);
-      const bool first = (fc == 0);
-      if (first && c > 0) mbar_wait(&S->dempty, (nflush - 1) & 1);
-      tc_fence_after();
-      __syncwarp();
-      const bool flush = (++fc == FL) || (c == nchunks - 1);
-      if (elect_one()) {
-        const uint64_t sofs = (uint64_t)((st * stageB) >> 4);
-        const uint32_t a_hi = tm + 448 + st * 32, a_lo = a_hi + 16;
+    // ================= MMA issuer (the leader CTA's in a pair) =================
+    if (!PAIR || rank == 0) {
+      const uint32_t idesc = idesc_tf32(PAIR ? 256 : 128, NPB);
+      const uint64_t dstep = (uint64_t)((2 * NH * 16) >> 4);                 // one K-step = two 16-byte chunks
+      const uint64_t d_hi0 = smem_desc(smem_u32(bst), NH * 16, 128), d_lo0 = d_hi0 + (uint64_t)((NH * 64) >> 4);
+      int fc = 0, nflush = 0;
+      for (int c = 0; c < nchunks; ++c) {
+        const int st = c % GU_NSTG;
+        mbar_wait(&S->bfull[st], (c / GU_NSTG) & 1);
+        const bool first = (fc == 0);
+        if (first && c > 0) mbar_wait(&S->dempty, (nflush - 1) & 1);
+        tc_fence_after();
+        __syncwarp();
+        const bool flush = (++fc == FL) || (c == nchunks - 1);
+        if (elect_one()) {
+          const uint64_t sofs = (uint64_t)((st * stageB) >> 4);
+          const uint32_t a_hi = tm + ACOL + st * 32, a_lo = a_hi + 16;
 #pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {
-          const uint64_t b_hi = d_hi0 + sofs + ks * dstep, b_lo = d_lo0 + sofs + ks * dstep;
-          mma_tf32_ts(tm, a_lo + ks * 8, b_hi, idesc, !(first && ks == 0));
-          mma_tf32_ts(tm, a_hi + ks * 8, b_lo, idesc, 1);
-          mma_tf32_ts(tm, a_hi + ks * 8, b_hi, idesc, 1);
+          for (int ks = 0; ks < 2; ++ks) {
+            const uint64_t b_hi = d_hi0 + sofs + ks * dstep, b_lo = d_lo0 + sofs + ks * dstep;
+            if (PAIR) {
+              mma2_tf32_ts(tm, a_lo + ks * 8, b_hi, idesc, !(first && ks == 0));
+              mma2_tf32_ts(tm, a_hi + ks * 8, b_lo, idesc, 1);
+              mma2_tf32_ts(tm, a_hi + ks * 8, b_hi, idesc, 1);
+            } else {
+              mma_tf32_ts(tm, a_lo + ks * 8, b_hi, idesc, !(first && ks == 0));
+              mma_tf32_ts(tm, a_hi + ks * 8, b_lo, idesc, 1);
+              mma_tf32_ts(tm, a_hi + ks * 8, b_hi, idesc, 1);
+            }
+          }
+          if (PAIR) { mma2_commit(&S->bempty[st], 3); if (flush) mma2_commit(&S->dfull, 3); }
+          else { mma_commit(&S->bempty[st]); if (flush) mma_commit(&S->dfull); }
         }
-        mma_commit(&S->bempty[st]);
-        if (flush) mma_commit(&S->dfull);
+        __syncwarp();
+        if (flush) { fc = 0; ++nflush; }
       }
-      __syncwarp();
-      if (flush) { fc = 0; ++nflush; }
     }
   } else {
     // ================= workers =================
@@ -186,8 +210,8 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant_
     const uint8_t* bi; const uint8_t* bj; int sli, slj, sti, stj;
     bool plain;
     {
-      const int pg_ = pb * NPB + wtid;
-      const bool pair_ok = (wtid < NPB) && (pg_ < a.P);
+      const int pg_ = pb * NPB + (int)rank * NH + wtid;
+      const bool pair_ok = (wtid < NH) && (pg_ < a.P);
       int pi = 0, pj = 0;
       if (pair_ok) gu_pair(pg_, D, &pi, &pj);
       auto setup = [&](int f, const uint8_t*& b, int& sl, int& stv) {
@@ -201,11 +225,16 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant_
       plain = SF > 0 && __all_sync(0xffffffffu, pair_ok && pj < D);
     }
     const int fls = __ffs(FL) - 1;                       // FL is a power of two
+    // barriers the workers signal: the leader CTA's (rank 0) in a pair, this CTA's own otherwise
+    uint32_t bfull_addr[GU_NSTG];
+#pragma unroll
+    for (int i = 0; i < GU_NSTG; ++i) bfull_addr[i] = PAIR ? mapa_u32(&S->bfull[i], 0) : smem_u32(&S->bfull[i]);
+    const uint32_t dempty_addr = PAIR ? mapa_u32(&S->dempty, 0) : smem_u32(&S->dempty);
     for (int c = set; c < nchunks; c += 2) {
-      const int s = c % GU_NR, st = c & 1;
+      const int s = c % GU_NR, st = c % GU_NSTG;
       const int nflush = c >> fls;
       mbar_wait(&S->rfull[s], (c / GU_NR) & 1);
-      mbar_wait(&S->bempty[st], ((c >> 1) & 1) ^ 1);
+      mbar_wait(&S->bempty[st], ((c / GU_NSTG) & 1) ^ 1);
       tc_fence_after();
       // ---- A operand: r[s][comp] for this thread's 8 samples, split, into TMEM
       {
@@ -216,14 +245,14 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant_
           const float2 r = make_float2(comp_ok ? rawr[u * kcb] : 0.f, comp_ok ? rawr[(u + 1) * kcb] : 0.f);
           split_fast2(r, hi[u], hi[u + 1], lo[u], lo[u + 1]);
         }
-        const uint32_t ad = tm + lane_base + 448 + st * 32 + sh * 8;
+        const uint32_t ad = tm + lane_base + ACOL + st * 32 + sh * 8;
         tmem_st8(ad, hi);
         tmem_st8(ad + 16, lo);
       }
       // ---- B operand: phi[s][pair] = zt[s][i] * zt[s][j] for 16 samples, split, K-major core-matrix layout
-      if (wtid < NPB) {
+      if (wtid < NH) {
         uint8_t* bh = bst + (size_t)st * stageB + (size_t)wtid * 16;
-        uint8_t* bl = bh + NPB * 64;
+        uint8_t* bl = bh + NH * 64;
         const uint8_t* zi = bi + s * sli;
         const uint8_t* zj = bj + s * slj;
         if (plain) {
@@ -243,8 +272,8 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant_
               split_fast2(__fmul2_rn(make_float2(av[sl], av[sl + 1]), make_float2(bv[sl], bv[sl + 1])), hi[u], hi[u + 1],
                           lo[u], lo[u + 1]);
             }
-            *reinterpret_cast<uint4*>(bh + (size_t)qd * NPB * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-            *reinterpret_cast<uint4*>(bl + (size_t)qd * NPB * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            *reinterpret_cast<uint4*>(bh + (size_t)qd * NH * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4*>(bl + (size_t)qd * NH * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
           }
         } else {
           float av[16], bv[16];
@@ -262,16 +291,23 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant_
               split_fast2(__fmul2_rn(make_float2(av[sl], av[sl + 1]), make_float2(bv[sl], bv[sl + 1])), hi[u], hi[u + 1],
                           lo[u], lo[u + 1]);
             }
-            *reinterpret_cast<uint4*>(bh + (size_t)qd * NPB * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-            *reinterpret_cast<uint4*>(bl + (size_t)qd * NPB * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            *reinterpret_cast<uint4*>(bh + (size_t)qd * NH * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4*>(bl + (size_t)qd * NH * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
           }
         }
       }
-      mbar_arrive(&S->rempty[s]);
+      // one arrival per warp: every lane fences its own writes, the warp converges, lane 0 publishes
       fence_proxy_async();
       tmem_wait_st();
       tc_fence_before();
-      mbar_arrive(&S->bfull[st]);
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&S->rempty[s]);
+        uint32_t ba = bfull_addr[0];
+#pragma unroll
+        for (int i = 1; i < GU_NSTG; ++i) ba = (st == i) ? bfull_addr[i] : ba;
+        mbar_arrive_cluster(ba);
+      }
 
       const bool last = (c == nchunks - 1);
       if (((c + 1) & (FL - 1)) == 0 || last) {
@@ -283,10 +319,10 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant_
         tc_fence_after();
         const bool firstf = (nflush == 0);
         float* prow = a.part + ((size_t)split * a.Kp + (size_t)cb * GU_CB + comp) * a.PP + (size_t)pb * NPB;
-        for (int c0 = sh * 112; c0 < sh * 112 + 112 && c0 < NPB; c0 += 16) {
+        for (int c0 = sh * (GU_NPMAX / 2); c0 < (sh + 1) * (GU_NPMAX / 2) && c0 < NPB; c0 += 16) {
           float v1[16], v2[16];
           tmem_ld16(tm + lane_base + c0, v1);
-          if (!firstf) tmem_ld16(tm + lane_base + 224 + c0, v2);
+          if (!firstf) tmem_ld16(tm + lane_base + GU_NPMAX + c0, v2);
           tmem_wait_ld();
           if (!firstf) {
 #pragma unroll
@@ -297,22 +333,23 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant_
             for (int j = 0; j < 16; j += 4)
               *reinterpret_cast<float4*>(prow + c0 + j) = make_float4(v1[j], v1[j + 1], v1[j + 2], v1[j + 3]);
           } else {
-            tmem_st16(tm + lane_base + 224 + c0, reinterpret_cast<const uint32_t*>(v1));
+            tmem_st16(tm + lane_base + GU_NPMAX + c0, reinterpret_cast<const uint32_t*>(v1));
           }
         }
         tmem_wait_st();
         tc_fence_before();
-        mbar_arrive(&S->dempty);
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(dempty_addr);
       }
     }
     if (nchunks == 0 && set == 0) {      // empty split: contribute zeros
       float* prow = a.part + ((size_t)split * a.Kp + (size_t)cb * GU_CB + comp) * a.PP + (size_t)pb * NPB;
-      for (int c0 = sh * 112; c0 < sh * 112 + 112 && c0 < NPB; ++c0) prow[c0] = 0.f;
+      for (int c0 = sh * (GU_NPMAX / 2); c0 < (sh + 1) * (GU_NPMAX / 2) && c0 < NPB; ++c0) prow[c0] = 0.f;
     }
   }
   tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc<512>(tm);
+  if (PAIR) cluster_sync_all(); else __syncthreads();      // no CTA of a pair may exit while its peer can still signal it
+  if (warp == 1) { if (PAIR) tmem_dealloc2<512>(tm); else tmem_dealloc<512>(tm); }
 }
 
 // gram[k][i][j] = gram[k][j][i] = sum_split part[split][k][pair(i,j)], fp64, fixed order.
@@ -345,7 +382,13 @@ static int gu_num_sms() {
   return n;
 }
 
+static bool gu_pair_mode(int K) {
+  static const int pair_ok = [] { const char* e = getenv("VBMP_GRAM_PAIR"); return e ? atoi(e) : 1; }();
+  return pair_ok && (((K + GU_CB - 1) / GU_CB) % 2 == 0);     // CTA pairs share the phi block (cta_group::2)
+}
+
 static void gu_plan(long long N, int K, int D, int sms, GuArgs* g) {
+  const int GU_NPMAX = gu_npmax(gu_pair_mode(K));
   const int D1 = D + 1;
   g->P = D1 * (D1 + 1) / 2;
   g->npb = (g->P + GU_NPMAX - 1) / GU_NPMAX;
@@ -413,25 +456,46 @@ int launch_gram_umma(const GramArgs& a, float* gram, void* ws, size_t ws_bytes, 
   if (!e && a.d1 > 0) e = make_tmap_2d(&tmZ1, a.z1, (uint64_t)a.d1, (uint64_t)a.N, (uint64_t)a.d1, (uint32_t)a.d1, GU_SC);
   if (a.d1 == 0) tmZ1 = tmZ0;
   if (e) { set_error("gram_umma: cuTensorMapEncodeTiled failed (%d)", e); return VBMP_ERR_CUDA; }
+  const bool pair = gu_pair_mode(a.K);
+  const int NH = pair ? g.NPB / 2 : g.NPB;
   const int rawB = (GU_SC * g.kcb * 4 + GU_SC * a.d0 * 4 + GU_SC * a.d1 * 4 + 127) / 128 * 128;
-  const size_t smem = (size_t)GU_NR * rawB + (size_t)2 * 2 * g.NPB * 64 + sizeof(GuSmem) + 64;
+  const size_t smem = (size_t)GU_NR * rawB + (size_t)gu_nstg(pair) * 2 * NH * 64 + sizeof(GuSmem) + 64;
   const int grid = g.splits * g.ncb * g.npb;
   const bool same = (a.d1 == 0 || a.d1 == a.d0);
   const int sf = same && (a.d0 == 64 || a.d0 == 32 || a.d0 == 16) ? a.d0 : 0;
   const bool r128 = g.kcb == GU_CB;
-#define GU_LAUNCH(SF, R)                                                                                         \
-  do {                                                                                                           \
-    cudaFuncSetAttribute(gram_umma_kernel<SF, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
-    gram_umma_kernel<SF, R><<<grid, GU_THREADS, smem, st>>>(tmR, tmZ0, tmZ1, g);                                 \
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(GU_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = pair ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t le = cudaSuccess;
+#define GU_LAUNCH(SF, R, P)                                                                                       \
+  do {                                                                                                            \
+    cudaFuncSetAttribute(gram_umma_kernel<SF, R, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
+    le = cudaLaunchKernelEx(&cfg, gram_umma_kernel<SF, R, P>, tmR, tmZ0, tmZ1, g);                                \
   } while (0)
-  if (sf == 64 && r128) GU_LAUNCH(64, true);
-  else if (sf == 64) GU_LAUNCH(64, false);
-  else if (sf == 32 && r128) GU_LAUNCH(32, true);
-  else if (sf == 32) GU_LAUNCH(32, false);
-  else if (sf == 16) GU_LAUNCH(16, false);
-  else if (r128) GU_LAUNCH(0, true);
-  else GU_LAUNCH(0, false);
+  if (pair) {                                               // K >= 256: the R box is always 128 wide
+    if (sf == 64) GU_LAUNCH(64, true, true);
+    else if (sf == 32) GU_LAUNCH(32, true, true);
+    else if (sf == 16) GU_LAUNCH(16, true, true);
+    else GU_LAUNCH(0, true, true);
+  } else if (sf == 64 && r128) GU_LAUNCH(64, true, false);
+  else if (sf == 64) GU_LAUNCH(64, false, false);
+  else if (sf == 32 && r128) GU_LAUNCH(32, true, false);
+  else if (sf == 32) GU_LAUNCH(32, false, false);
+  else if (sf == 16) GU_LAUNCH(16, false, false);
+  else if (r128) GU_LAUNCH(0, true, false);
+  else GU_LAUNCH(0, false, false);
 #undef GU_LAUNCH
+  if (le != cudaSuccess) { set_error("gram_umma launch: %s", cudaGetErrorString(le)); return VBMP_ERR_CUDA; }
   int rc = check_launch("gram_umma");
   if (rc) return rc;
   const int D1 = D + 1;
