@@ -96,7 +96,10 @@ def f32(t, device=None):
         t = t.to(device)
     if t.dtype != torch.float32:
         t = t.to(torch.float32)
-    return t.contiguous()
+    t = t.contiguous()
+    if t.is_cuda and t.data_ptr() % 16:
+        t = t.clone()        # the kernels use 16-byte vector / TMA accesses: a view at an odd element offset is re-based
+    return t
 
 
 def pad_dim(D):

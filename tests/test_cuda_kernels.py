@@ -138,3 +138,24 @@ def test_hmm_forward_backward_kernel(T, S, G, K, ptemp):
     assert float((SEz0.double() - SEz0r).abs().max()) < 2e-5
     assert float(((logZ.double() - logZr).abs() / logZr.abs().clamp_min(1.0)).max()) < 1e-5
     assert bool((p.argmax(-1) == pr.argmax(-1)).float().mean() > 0.999)
+
+
+def test_misaligned_views_are_rebased():
+    """A contiguous view that starts at a 4-byte offset must not reach the 16-byte vector / TMA accesses as is."""
+    import pyvbmp_b200 as V
+    N, K, d = 5000, 8, 64
+    g = torch.Generator(device=DEV).manual_seed(4)
+    flat = torch.randn(N * d + 1, generator=g, device=DEV)
+    Xa = flat[1:].view(N, d)                      # data_ptr % 16 == 4
+    Xb = Xa.clone()
+    assert Xa.data_ptr() % 16 != 0 and Xb.data_ptr() % 16 == 0
+    outs = []
+    for X in (Xa, Xb):
+        torch.manual_seed(1)
+        m = V.GaussianMixtureModel(K, d)
+        m.initialize(Xb.cpu()[:512])
+        m.to(DEV)
+        m.update(X, 2)
+        outs.append(m)
+    assert torch.equal(outs[0].p, outs[1].p)
+    assert float(outs[0].ELBO_last) == float(outs[1].ELBO_last)

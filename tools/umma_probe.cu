@@ -382,22 +382,11 @@ static void run_eseq() {
 
 // ---- cta_group::2: a CTA pair computes D[256 x N] = A[256 x K] B[N x K]^T; CTA r holds rows r*128.. of A (smem or TMEM),
 //      rows r*N/2.. of B in its shared memory, and receives rows r*128.. of D in its TMEM.
-__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
-  uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank)); return r;
-}
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void mma2_tf32_ss(uint32_t d, uint64_t ad, uint64_t bd, uint32_t idesc, uint32_t acc) {
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d), "l"(ad), "l"(bd), "r"(idesc), "r"(acc) : "memory");
-}
-__device__ __forceinline__ void mma2_tf32_ts(uint32_t d, uint32_t at, uint64_t bd, uint32_t idesc, uint32_t acc) {
-  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d), "r"(at), "l"(bd), "r"(idesc), "r"(acc) : "memory");
 }
 __device__ __forceinline__ void mma2_commit_mc(uint64_t* bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"(mask) : "memory");
@@ -438,7 +427,7 @@ pair_kernel(const float* __restrict__ A, const float* __restrict__ Bp, float* __
   fence_proxy_async();
   tc_fence_before();
   // everyone (both CTAs) arrives on the LEADER's ready barrier
-  mbar_arrive_remote(mapa_u32(smem_u32(&bar_ready), 0));
+  mbar_arrive_remote(mapa_u32(&bar_ready, 0));
   if (rank == 0 && warp == 1) {
     mbar_wait(&bar_ready, 0);
     tc_fence_after();
@@ -582,9 +571,180 @@ static void run_eseq2() {
   cudaFree(dc);
 }
 
+// ---- kind::f16 (fp16 operands, fp32 accumulate), A in TMEM packed two fp16 per 32-bit column, B K-major in smem:
+//      checks the packing order and the K = 16 step.
+#include <cuda_fp16.h>
+__device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__host__ __device__ constexpr uint32_t idesc_f16(int M, int N) {       // fp16 x fp16 -> f32, both K-major
+  return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// A: [128][K] fp32 values (exactly representable in fp16), Bp: fp16 packed K-major image [K/8 chunks][N rows][8], D: [128][N]
+__global__ void __launch_bounds__(128, 1) f16_kernel(const float* __restrict__ A, const __half* __restrict__ Bp, float* __restrict__ D, int N, int K) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar_mma;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  __half* Bs = reinterpret_cast<__half*>(smem);
+  for (int e = tid; e < N * K; e += 128) Bs[e] = Bp[e];
+  fence_proxy_async();
+  if (tid == 0) { mbar_init(&bar_mma, 1); fence_barrier_init(); }
+  if (warp == 0) tmem_alloc<512>(&tmem_base_s);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tm = tmem_base_s;
+  for (int k0 = 0; k0 < K; k0 += 16) {                        // 16 fp16 = 8 columns; column c = {k = 2c (low), 2c+1 (high)}
+    uint32_t r[8];
+    for (int j = 0; j < 8; ++j) {
+      const __half2 h = __floats2half2_rn(A[tid * K + k0 + 2 * j], A[tid * K + k0 + 2 * j + 1]);
+      r[j] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    tmem_st8(tm + ((uint32_t)(warp * 32) << 16) + 256 + k0 / 2, r);
+  }
+  tmem_wait_st();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) {
+    if (elect_one()) {
+      const uint32_t idesc = idesc_f16(128, N);
+      for (int ks = 0; ks < K / 16; ++ks) {
+        const uint64_t bd = smem_desc(smem_u32(Bs) + ks * 2 * (N * 16), N * 16, 128);
+        mma_f16_ts(tm, tm + 256 + ks * 8, bd, idesc, ks > 0);
+      }
+      mma_commit(&bar_mma);
+    }
+    __syncwarp();
+  }
+  mbar_wait(&bar_mma, 0);
+  tc_fence_after();
+  for (int c0 = 0; c0 < N; c0 += 16) {
+    float v[16];
+    tmem_ld16(tm + ((uint32_t)(warp * 32) << 16) + c0, v);
+    tmem_wait_ld();
+    for (int j = 0; j < 16; ++j) D[(size_t)tid * N + c0 + j] = v[j];
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tm);
+}
+static int run_f16_case(int N, int K) {
+  std::vector<float> A(128 * K), B(N * K), D(128 * N), R(128 * N);
+  std::vector<__half> Bp(N * K);
+  for (auto& v : A) v = (float)((rand() % 17) - 8);
+  for (auto& v : B) v = (float)((rand() % 13) - 6);
+  for (int n = 0; n < N; ++n)
+    for (int k = 0; k < K; ++k) Bp[(k >> 3) * (N * 8) + n * 8 + (k & 7)] = __float2half(B[n * K + k]);
+  for (int m = 0; m < 128; ++m)
+    for (int n = 0; n < N; ++n) { double s = 0; for (int k = 0; k < K; ++k) s += (double)A[m * K + k] * B[n * K + k]; R[m * N + n] = (float)s; }
+  float *dA, *dD; __half* dB;
+  CK(cudaMalloc(&dA, A.size() * 4)); CK(cudaMalloc(&dB, Bp.size() * 2)); CK(cudaMalloc(&dD, D.size() * 4));
+  CK(cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dB, Bp.data(), Bp.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemset(dD, 0xff, D.size() * 4));
+  f16_kernel<<<1, 128, N * K * 2>>>(dA, dB, dD, N, K);
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost));
+  int bad = 0;
+  for (int i = 0; i < 128 * N; ++i) if (fabs((double)D[i] - R[i]) > 1e-3) ++bad;
+  printf("f16 TS N=%3d K=%3d : %s (mismatches %d / %d)  D[0..2]=%g %g %g ref %g %g %g\n", N, K, bad ? "FAIL" : "ok", bad, 128 * N, D[0], D[1], D[2], R[0], R[1], R[2]);
+  cudaFree(dA); cudaFree(dB); cudaFree(dD);
+  return bad != 0;
+}
+
+// Mixed sequence: per half one SS MMA (the -m fold), 8 TF32 TS hi*hi steps (N = 128 - 16 ks) and 2 x 4 fp16 TS correction
+// steps (K = 16, N = 128 - 32 ks16) into the same accumulator.  MODE 0: mixed, 1: the fp16 steps only, 2: TF32 steps only
+template <int MODE>
+__global__ void __launch_bounds__(128, 1) eseq3_kernel(int groups, long long* cycles) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar_mma;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  uint32_t* Bs = reinterpret_cast<uint32_t*>(smem);
+  for (int e = tid; e < 5 * 10240; e += 128) Bs[e] = 0;
+  fence_proxy_async();
+  if (tid == 0) { mbar_init(&bar_mma, 1); fence_barrier_init(); }
+  if (warp == 0) tmem_alloc<512>(&tmem_base_s);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tm = tmem_base_s;
+  {
+    uint32_t r[16];
+    for (int j = 0; j < 16; ++j) r[j] = 0;
+    for (int c = 0; c < 256; c += 16) tmem_st16(tm + ((uint32_t)(warp * 32) << 16) + c, r);
+    tmem_wait_st();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) {
+    const long long t0 = clock64();
+    for (int g = 0; g < groups; ++g) {
+      const uint32_t sbase = smem_u32(smem) + (g % 5) * 40960;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const uint32_t dcol = tm + 256 + h * 128;
+        const uint32_t a_hi = tm + h * 128, a_h16 = a_hi + 64, a_l16 = a_hi + 96;
+        if (elect_one()) {
+          mma_tf32_ss(dcol, smem_desc(sbase + 36864, 128 * 16, 128), smem_desc(sbase + 18432, 128 * 16, 128), idesc_tf32(128, 128), 0);
+          if (MODE != 1) {
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {
+              const int n0 = 16 * ks, nn = 128 - n0;
+              int off = 0;
+              for (int i = 0; i < ks; ++i) off += (128 - 16 * i) * 32;
+              mma_tf32_ts(dcol + n0, a_hi + ks * 8, smem_desc(sbase + off, nn * 16, 128), idesc_tf32(128, nn), 1);
+            }
+          }
+          if (MODE != 2) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              const int n0 = 32 * ks, nn = 128 - n0;
+              int off = 0;
+              for (int i = 0; i < ks; ++i) off += (128 - 32 * i) * 32;
+              mma_f16_ts(dcol + n0, a_l16 + ks * 8, smem_desc(sbase + 18432 + off, nn * 16, 128), idesc_f16(128, nn), 1);
+              mma_f16_ts(dcol + n0, a_h16 + ks * 8, smem_desc(sbase + 18432 + 10240 + off, nn * 16, 128), idesc_f16(128, nn), 1);
+            }
+          }
+        }
+        __syncwarp();
+      }
+    }
+    if (elect_one()) mma_commit(&bar_mma);
+    __syncwarp();
+    mbar_wait(&bar_mma, 0);
+    const long long t1 = clock64();
+    if ((tid & 31) == 0) cycles[blockIdx.x] = t1 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tm);
+}
+template <int MODE>
+static void run_eseq3() {
+  const int groups = 3000, grid = 148;
+  long long* dc; CK(cudaMalloc(&dc, grid * sizeof(long long)));
+  const int smem = 5 * 40960;
+  CK(cudaFuncSetAttribute(eseq3_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  eseq3_kernel<MODE><<<grid, 128, smem>>>(100, dc);
+  CK(cudaDeviceSynchronize());
+  eseq3_kernel<MODE><<<grid, 128, smem>>>(groups, dc);
+  CK(cudaDeviceSynchronize());
+  std::vector<long long> c(grid);
+  CK(cudaMemcpy(c.data(), dc, grid * sizeof(long long), cudaMemcpyDeviceToHost));
+  long long mx = 0; for (auto v : c) if (v > mx) mx = v;
+  printf("eseq3 mode=%d : %.1f cycles per group (2 components x 256 rows)\n", MODE, (double)mx / groups);
+  cudaFree(dc);
+}
+
 int main(int argc, char** argv) {
   srand(1);
   int fails = 0;
+  if (argc > 1 && atoi(argv[1]) == 8) { run_eseq2<4>(); run_eseq3<0>(); run_eseq3<1>(); run_eseq3<2>(); return 0; }
+  if (argc > 1 && atoi(argv[1]) == 7) { int f = 0; for (int N : {32, 96, 128}) for (int K : {16, 64}) f += run_f16_case(N, K); printf("f16 probe: %d failing\n", f); return f; }
   if (argc > 1 && atoi(argv[1]) == 6) { run_eseq2<0>(); run_eseq2<1>(); run_eseq2<2>(); run_eseq2<3>(); run_eseq2<4>(); return 0; }
   if (argc > 1 && atoi(argv[1]) == 5) { int f = 0; for (int ts = 0; ts < 2; ++ts) for (int N : {64, 128, 224, 256}) for (int K : {8, 32}) f += run_pair_case(N, K, ts); printf("pair probe: %d failing\n", f); return f; }
   if (argc > 1 && atoi(argv[1]) == 4) { run_eseq<false, 0>(); run_eseq<true, 0>(); run_eseq<true, 1>(); run_eseq<true, 2>(); run_eseq<false, 1>(); return 0; }
