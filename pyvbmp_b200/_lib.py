@@ -12,7 +12,7 @@ from ctypes import c_char_p, c_float, c_int, c_longlong, c_size_t, c_void_p
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvbmp_b200.so")
+LIB_PATH = os.environ.get("VBMP_LIB") or os.path.join(_HERE, "libvbmp_b200.so")   # VBMP_LIB: developer variant builds
 _lib = None
 
 FORCE_SIMT = int(os.environ.get("VBMP_FORCE_SIMT", "0"))   # tests: 1 = CUDA-core kernels for both, 2 = E-step only, 3 = Gram only

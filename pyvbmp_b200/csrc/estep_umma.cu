@@ -23,24 +23,45 @@
 //     D with tcgen05.ld, square-reduce with packed fp32x2 FFMA2, keep an online logsumexp and write the logits.  For mode 1 the tile's rows are then
 //     normalised in place (the re-read hits L2) with coalesced float4 accesses, accumulating NA per CTA in a
 //     fixed order (deterministic).
+//
+// Operand precision (template parameter F16, the default; VBMP_ESTEP_PREC=tf32 selects the other):
+//   * TF32: z and W are split hi + lo into TF32 (3 MMAs with K = 8 per K-step; the tensor core truncates lo to 10 bits,
+//     product error ~2^-21).
+//   * FP16: each sample row is scaled by 2^sh_n (row maximum -> [2^10, 2^11)) and each component's W by 2^t_k (same
+//     normalisation), both EXACT; then z' = a + b and W' = A + B with a, b, A, B fp16 (a = rn(z'), b = rn(z' - a): 22
+//     significant bits, product error ~2^-22, so it is at least as accurate as the TF32 split) and the same three terms
+//     run as kind::f16 MMAs with K = 16, which issue at twice the TF32 rate and halve the operand bytes (stage 24.6 KB
+//     instead of 41 KB, A 64 instead of 128 TMEM columns per half).  The -m fold stays a TF32 MMA whose A block holds
+//     2^sh_n per row and whose B block holds -m 2^t_k; the epilogue multiplies by 2^-(sh_n + t_k) (exact) before squaring,
+//     so nothing can overflow that would not overflow in the unscaled form.  Zero rows get sh = 0; sh and t are clamped to
+//     +-60.
 #include <cstdlib>
+#include <cuda_fp16.h>
 #include "common.cuh"
 #include "umma.cuh"
 
 namespace vbmp {
 using namespace umma;
 
-constexpr int EU_THREADS = 352;     // warp 0: bulk-copy producer, warps 1-2: MMA issuers (one per half), warps 3..10: workers
+constexpr int EU_THREADS = 384;     // warp 0: bulk-copy producer, warps 1-2: MMA issuers (one per half), warps 3..10: workers,
+                                    // warp 11: normaliser (mode 1)
 constexpr int EU_TILE = 256;
 constexpr int EU_MAXSTAGE = 8;     // the launcher picks the number of stages that fits (5 at DP = 64, K <= 256)
 constexpr int EU_MAXK = 512;
 constexpr int EU_N = 128;           // columns per group
 
-template <int DP>
+template <int DP, bool F16>
 struct EuCfg {
   static constexpr int CG = EU_N / DP;        // components per 128-column MMA group
-  static constexpr int KS = DP / 8;           // K-steps (8 TF32 each)
-  __host__ __device__ static constexpr int n0(int ks) { return ks * CG * 8; }
+  static constexpr int KSTEP = F16 ? 16 : 8;  // reduction length of one MMA
+  static constexpr int KS = DP / KSTEP;       // K-steps
+  static constexpr int ACOLS = F16 ? DP / 2 : DP;   // TMEM columns of one A image (hi or lo) of a half
+  // accumulators: the (group, half) pairs rotate through NBUF 128-column buffers.  With fp16 operands a half's MMAs take
+  // ~630 cycles, less than the commit -> tcgen05.ld -> release round trip of the other half's accumulator, so a third
+  // buffer (the A images only need 128 columns) gives that round trip two bursts to complete.
+  static constexpr int NBUF = F16 ? 3 : 2;
+  static constexpr int DCOL0 = F16 ? 128 : 256;
+  __host__ __device__ static constexpr int n0(int ks) { return ks * CG * KSTEP; }
   __host__ __device__ static constexpr int nn(int ks) { return EU_N - n0(ks); }
   __host__ __device__ static constexpr int blk_off(int ks) {
     int o = 0;
@@ -50,7 +71,7 @@ struct EuCfg {
   static constexpr int WB = blk_off(KS);      // bytes of one operand image (hi or lo) of a group
   static constexpr int GB = 2 * WB;           // hi image then lo image
   static constexpr int MB = EU_N * 32;        // the "-m" operand block: one K-step (k = 0: -m_hi, k = 1: -m_lo, rest 0)
-  static constexpr int REC = GB + MB + 32;    // + cst of the CG components
+  static constexpr int REC = GB + MB + 64;    // + cst of the CG components (floats 0..7) and 2^-t_k (floats 8..15)
   static constexpr int STAGE = (REC + 127) / 128 * 128;
   // component / feature of column n
   __host__ __device__ static constexpr int col_cl(int n) { return (n % (CG * 8)) / 8; }
@@ -66,59 +87,99 @@ struct EuCfg {
   }
 };
 
-// ---- pack: W (C, DP, DP) fp32 row-major [i][j] -> per group [hi | lo | m | cst] record; B[n][k] = W_c[i = k][j]
-// with (c, j) = column n as above; K-step block ks holds rows n >= n0(ks) as [chunk (2)][row][4 floats],
-// i = 8 ks + 4 chunk + e.
-template <int DP>
+// ---- pack: W (C, DP, DP) fp32 row-major [i][j] -> per group [hi | lo | m | cst, 2^-t] record; B[n][k] = W_c[i = k][j]
+// with (c, j) = column n as above; K-step block ks holds rows n >= n0(ks) as [chunk (2)][row][16 bytes]: 4 TF32 or
+// 8 fp16 per chunk, i = KSTEP ks + (KSTEP / 2) chunk + e.
+template <int DP, bool F16>
 __global__ void estep_pack_kernel(const float* __restrict__ W, const float* __restrict__ m, const float* __restrict__ cst,
                                   int K, uint8_t* __restrict__ Wp) {
-  using C = EuCfg<DP>;
+  using C = EuCfg<DP, F16>;
   const int g = blockIdx.x;
-  float* hi = reinterpret_cast<float*>(Wp + (size_t)g * C::REC);
-  float* lo = reinterpret_cast<float*>(Wp + (size_t)g * C::REC + C::WB);
+  __shared__ uint32_t wmax[8];
+  __shared__ float wsc[8];              // 2^t_k of the group's components (1 for TF32)
+  if (threadIdx.x < 8) wmax[threadIdx.x] = 0u;
+  __syncthreads();
+  if (F16) {
+    for (int o = threadIdx.x; o < C::CG * DP * DP; o += blockDim.x) {
+      const int c = g * C::CG + o / (DP * DP);
+      if (c < K) atomicMax(&wmax[o / (DP * DP)], __float_as_uint(fabsf(W[(size_t)c * DP * DP + o % (DP * DP)])) & 0x7f800000u);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x < 8) {
+    int t = 0;
+    if (F16 && wmax[threadIdx.x] != 0u) {
+      t = 10 - ((int)(wmax[threadIdx.x] >> 23) - 127);
+      t = t > 60 ? 60 : (t < -60 ? -60 : t);
+    }
+    wsc[threadIdx.x] = __uint_as_float((uint32_t)(127 + t) << 23);
+  }
+  __syncthreads();
   // -m as a K-major operand block [chunk (2)][column n (128)][4 floats]: k = 0 holds -m_hi, k = 1 holds -m_lo.  It meets a
-  // constant A block of ones (k = 0, 1) in ONE extra MMA that initialises the accumulator to -m, so y - m comes out of
-  // the tensor core and the epilogue only squares: the epilogue's -m loads were ~900 shared-memory wavefronts per group,
-  // as much as the MMA operand fetch, and the shared-memory pipe is what both compete for.
+  // constant A block of ones (k = 0, 1; 2^sh_n for fp16) in ONE extra MMA that initialises the accumulator to -m, so y - m
+  // comes out of the tensor core and the epilogue only squares: the epilogue's -m loads were ~900 shared-memory wavefronts
+  // per group, as much as the MMA operand fetch, and the shared-memory pipe is what both compete for.
   float* mo = reinterpret_cast<float*>(Wp + (size_t)g * C::REC + C::GB);
   float* co = reinterpret_cast<float*>(Wp + (size_t)g * C::REC + C::GB + C::MB);
   for (int o = threadIdx.x; o < EU_N * 8; o += blockDim.x) {
     const int ch = o / (EU_N * 4), n = (o % (EU_N * 4)) / 4, e = o % 4;
     float v = 0.f;
     if (ch == 0 && e < 2) {
-      const int c = g * C::CG + C::col_cl(n);
-      const float mv = c < K ? m[(size_t)c * DP + C::col_j(n)] : 0.f;
+      const int cl = C::col_cl(n), c = g * C::CG + cl;
+      const float mv = c < K ? m[(size_t)c * DP + C::col_j(n)] * wsc[cl] : 0.f;
       uint32_t h, l;
       split_tf32(mv, h, l);
       v = e == 0 ? -__uint_as_float(h) : -__uint_as_float(l);
     }
     mo[o] = v;
   }
-  for (int o = threadIdx.x; o < 8; o += blockDim.x) {
-    const int c = g * C::CG + o;
-    co[o] = (o < C::CG && c < K) ? cst[c] : 0.f;
+  for (int o = threadIdx.x; o < 16; o += blockDim.x) {
+    const int cl = o & 7, c = g * C::CG + cl;
+    const bool ok = cl < C::CG && c < K;
+    co[o] = o < 8 ? (ok ? cst[c] : 0.f) : (ok ? 1.f / wsc[cl] : 1.f);
   }
-  for (int o = threadIdx.x; o < C::WB / 4; o += blockDim.x) {
-    int ks = 0, rem = o * 4;
-    while (ks + 1 < C::KS && rem >= C::nn(ks) * 32) { rem -= C::nn(ks) * 32; ++ks; }
-    const int nn = C::nn(ks);
-    const int ch = rem / (nn * 16);
-    const int r = (rem % (nn * 16)) / 16, e = (rem % 16) / 4;
-    const int n = C::n0(ks) + r, cl = C::col_cl(n), j = C::col_j(n), i = 8 * ks + 4 * ch + e;
-    const int c = g * C::CG + cl;
-    const float v = (c < K) ? W[((size_t)c * DP + i) * DP + j] : 0.f;
-    uint32_t h, l;
-    split_tf32(v, h, l);
-    hi[o] = __uint_as_float(h);
-    lo[o] = __uint_as_float(l);
+  if (F16) {
+    __half* hi = reinterpret_cast<__half*>(Wp + (size_t)g * C::REC);
+    __half* lo = reinterpret_cast<__half*>(Wp + (size_t)g * C::REC + C::WB);
+    for (int o = threadIdx.x; o < C::WB / 2; o += blockDim.x) {
+      int ks = 0, rem = o * 2;
+      while (ks + 1 < C::KS && rem >= C::nn(ks) * 32) { rem -= C::nn(ks) * 32; ++ks; }
+      const int nn = C::nn(ks);
+      const int ch = rem / (nn * 16);
+      const int r = (rem % (nn * 16)) / 16, e = (rem % 16) / 2;
+      const int n = C::n0(ks) + r, cl = C::col_cl(n), j = C::col_j(n), i = 16 * ks + 8 * ch + e;
+      const int c = g * C::CG + cl;
+      const float v = (c < K) ? W[((size_t)c * DP + i) * DP + j] * wsc[cl] : 0.f;
+      const __half a = __float2half_rn(v);
+      hi[o] = a;
+      lo[o] = __float2half_rn(v - __half2float(a));
+    }
+  } else {
+    float* hi = reinterpret_cast<float*>(Wp + (size_t)g * C::REC);
+    float* lo = reinterpret_cast<float*>(Wp + (size_t)g * C::REC + C::WB);
+    for (int o = threadIdx.x; o < C::WB / 4; o += blockDim.x) {
+      int ks = 0, rem = o * 4;
+      while (ks + 1 < C::KS && rem >= C::nn(ks) * 32) { rem -= C::nn(ks) * 32; ++ks; }
+      const int nn = C::nn(ks);
+      const int ch = rem / (nn * 16);
+      const int r = (rem % (nn * 16)) / 16, e = (rem % 16) / 4;
+      const int n = C::n0(ks) + r, cl = C::col_cl(n), j = C::col_j(n), i = 8 * ks + 4 * ch + e;
+      const int c = g * C::CG + cl;
+      const float v = (c < K) ? W[((size_t)c * DP + i) * DP + j] : 0.f;
+      uint32_t h, l;
+      split_tf32(v, h, l);
+      hi[o] = __uint_as_float(h);
+      lo[o] = __uint_as_float(l);
+    }
   }
 }
 
 struct EuSmem {
   uint64_t full[EU_MAXSTAGE], empty[EU_MAXSTAGE];
-  uint64_t tfull[2], tempty[2];
+  uint64_t tfull[3], tempty[3];
   uint64_t afull;
   uint64_t turn[2];           // issue token between the two MMA warps
+  uint64_t ndone[2], nfree[2];  // mode 1: tile's logits + logZ_n complete (workers -> normaliser) / lz buffer free again
   uint32_t tmem_base;
   double red[8];
 };
@@ -127,46 +188,58 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-template <int DP, int MODE>
+// position in a ring of n slots: slot index and the parity of the number of completed laps (no division in the loops)
+struct Ring {
+  int s = 0;
+  uint32_t ph = 0;
+  __device__ __forceinline__ void next(int n) { if (++s == n) { s = 0; ph ^= 1u; } }
+};
+// accumulator-buffer rotation: (group, half) pair number seq = 2 it + h uses buffer seq % NBUF for the (seq / NBUF)-th time
+template <int NBUF>
+struct BufRing {
+  uint32_t buf, ph = 0;
+  __device__ __forceinline__ explicit BufRing(int h) : buf(h % NBUF), ph(h / NBUF) {}
+  __device__ __forceinline__ void next() { buf += 2; if (buf >= NBUF) { buf -= NBUF; ph ^= 1u; } }
+};
+
+template <int DP, int MODE, bool F16>
 __global__ void __launch_bounds__(EU_THREADS, 1)
 estep_umma_kernel(EstepArgs a, const uint8_t* __restrict__ Wp, int ntiles, int ngroups, int nstage) {
-  using C = EuCfg<DP>;
+  using C = EuCfg<DP, F16>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* stages = smem_raw;                                             // EU_NSTAGE * STAGE
-  float* ones = reinterpret_cast<float*>(stages + nstage * C::STAGE);     // A block [chunk (2)][row (128)][4]: 1 at k = 0, 1
-  EuSmem* S = reinterpret_cast<EuSmem*>(stages + nstage * C::STAGE + 4096);
+  float* ones = reinterpret_cast<float*>(stages + nstage * C::STAGE);     // per half: A block [chunk (2)][row (128)][4] with
+                                                                          // 1 (TF32) or 2^sh_row (fp16) at k = 0, 1
+  EuSmem* S = reinterpret_cast<EuSmem*>(stages + nstage * C::STAGE + 8192);
   float* lz = reinterpret_cast<float*>(S + 1);                            // [2][256] (tile parity)
-  float* colsum = lz + 2 * EU_TILE;                                           // [8][K]     (mode 1)
-  double* NAacc = reinterpret_cast<double*>(colsum + 8 * a.K);            // [K]        (mode 1)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int K = a.K;
 
   if (tid == 0) {
     for (int s = 0; s < nstage; ++s) { mbar_init(&S->full[s], 1); mbar_init(&S->empty[s], 2 + 256); }
-    for (int h = 0; h < 2; ++h) { mbar_init(&S->tfull[h], 1); mbar_init(&S->tempty[h], 128); }
+    for (int b = 0; b < 3; ++b) { mbar_init(&S->tfull[b], 1); mbar_init(&S->tempty[b], 128); }
     mbar_init(&S->afull, 256);
     mbar_init(&S->turn[0], 1); mbar_init(&S->turn[1], 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(&S->ndone[b], 256); mbar_init(&S->nfree[b], 1); }
     fence_barrier_init();
   }
-  if (MODE == 1) for (int k = tid; k < K; k += EU_THREADS) NAacc[k] = 0.0;
-  for (int o = tid; o < 1024; o += EU_THREADS) ones[o] = (o < 512 && (o & 3) < 2) ? 1.f : 0.f;
+  for (int o = tid; o < 2048; o += EU_THREADS) ones[o] = ((o & 1023) < 512 && (o & 3) < 2) ? 1.f : 0.f;
   fence_proxy_async();
   if (warp == 1) tmem_alloc<512>(&S->tmem_base);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tm = S->tmem_base;
-  // TMEM columns: A hi/lo of half h at h*2*DP (+DP for lo); D[h] at 256 + 128 h
+  // TMEM columns: A hi/lo of half h at h*2*ACOLS (+ACOLS for lo); accumulator buffer b at DCOL0 + 128 b
   const int my_tiles = (ntiles > (int)blockIdx.x) ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
   if (warp == 0) {
     // ================= producer: one bulk copy per 64-column group =================
-    long long it = 0;
+    Ring rg;
     for (int t = 0; t < my_tiles; ++t)
-      for (int g = 0; g < ngroups; ++g, ++it) {
-        const int s = (int)(it % nstage);
-        const uint32_t n = (uint32_t)(it / nstage);
-        mbar_wait(&S->empty[s], (n & 1) ^ 1);
+      for (int g = 0; g < ngroups; ++g, rg.next(nstage)) {
+        const int s = rg.s;
+        mbar_wait(&S->empty[s], rg.ph ^ 1);
         if (elect_one()) {
           mbar_arrive_expect_tx(&S->full[s], C::REC);
           bulk_g2s(stages + (size_t)s * C::STAGE, Wp + (size_t)g * C::REC, C::REC, &S->full[s]);
@@ -179,120 +252,70 @@ estep_umma_kernel(EstepArgs a, const uint8_t* __restrict__ Wp, int ntiles, int n
     // take strict turns through a token: if their bursts interleaved in the tensor-pipe FIFO both halves would finish
     // together and both epilogue round trips would be exposed; in turn order half 0's epilogue runs under half 1's MMAs.
     const int h = warp - 1;
-    const uint32_t dcol = tm + 256 + h * EU_N;
-    const uint32_t a_hi = tm + h * 2 * DP, a_lo = a_hi + DP;
-    const uint64_t ones_desc = smem_desc(smem_u32(ones), 128 * 16, 128);
-    long long it = 0;
+    const uint32_t a_hi = tm + h * 2 * C::ACOLS, a_lo = a_hi + C::ACOLS;
+    const uint64_t ones_desc = smem_desc(smem_u32(ones + h * 1024), 128 * 16, 128);
+    Ring rg;
+    BufRing<C::NBUF> br(h);
+    uint32_t itp = 0;                      // parity of the group counter
     for (int t = 0; t < my_tiles; ++t) {
       mbar_wait(&S->afull, t & 1);
       tc_fence_after();
-      for (int g = 0; g < ngroups; ++g, ++it) {
-        const int s = (int)(it % nstage);
-        const uint32_t n = (uint32_t)(it / nstage);
-        mbar_wait(&S->full[s], n & 1);
+      for (int g = 0; g < ngroups; ++g, rg.next(nstage), br.next(), itp ^= 1u) {
+        const int s = rg.s;
+        mbar_wait(&S->full[s], rg.ph);
         const uint64_t sb = (uint64_t)((smem_u32(stages) + (uint32_t)s * C::STAGE) >> 4);
-        mbar_wait(&S->tempty[h], (uint32_t)(it & 1) ^ 1);
-        mbar_wait(&S->turn[h], h == 0 ? ((uint32_t)(it & 1) ^ 1) : (uint32_t)(it & 1));     // my turn
+        const uint32_t buf = br.buf;
+        const uint32_t dcol = tm + C::DCOL0 + buf * EU_N;
+        mbar_wait(&S->tempty[buf], br.ph ^ 1);
+        mbar_wait(&S->turn[h], h == 0 ? (itp ^ 1) : itp);     // my turn
         tc_fence_after();
         if (elect_one()) {
           mma_tf32_ss(dcol, ones_desc, C::desc_m() + sb, idesc_tf32(128, EU_N), 0);   // D = -m
 #pragma unroll
           for (int ks = 0; ks < C::KS; ++ks) {
-            const uint32_t idesc = idesc_tf32(128, C::nn(ks));
             const uint64_t b_hi = C::desc0(ks, 0) + sb, b_lo = C::desc0(ks, 1) + sb;
-            mma_tf32_ts(dcol + C::n0(ks), a_lo + ks * 8, b_hi, idesc, 1);        // small terms first
-            mma_tf32_ts(dcol + C::n0(ks), a_hi + ks * 8, b_lo, idesc, 1);
-            mma_tf32_ts(dcol + C::n0(ks), a_hi + ks * 8, b_hi, idesc, 1);
+            if (F16) {
+              const uint32_t idesc = idesc_f16(128, C::nn(ks));
+              mma_f16_ts(dcol + C::n0(ks), a_lo + ks * 8, b_hi, idesc, 1);       // small terms first
+              mma_f16_ts(dcol + C::n0(ks), a_hi + ks * 8, b_lo, idesc, 1);
+              mma_f16_ts(dcol + C::n0(ks), a_hi + ks * 8, b_hi, idesc, 1);
+            } else {
+              const uint32_t idesc = idesc_tf32(128, C::nn(ks));
+              mma_tf32_ts(dcol + C::n0(ks), a_lo + ks * 8, b_hi, idesc, 1);
+              mma_tf32_ts(dcol + C::n0(ks), a_hi + ks * 8, b_lo, idesc, 1);
+              mma_tf32_ts(dcol + C::n0(ks), a_hi + ks * 8, b_hi, idesc, 1);
+            }
           }
-          mma_commit(&S->tfull[h]);
+          mma_commit(&S->tfull[buf]);
           mma_commit(&S->empty[s]);
           mbar_arrive(&S->turn[h ^ 1]);                 // pass the token
         }
         __syncwarp();
       }
     }
-  } else {
-    // ================= workers: A tile -> TMEM, epilogue, normalisation =================
+  } else if (warp <= 10) {
+    // ================= workers: A tile -> TMEM, epilogue =================
     const int w8 = warp - 3, h = w8 >> 2, q = warp & 3;
     const int wtid = tid - 96;                                  // 0..255
     const int rloc = h * 128 + q * 32 + lane;                   // row within the tile
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     const int D = a.d0 + a.d1;
     double lzsum = 0.0;
-    long long it = 0;
-    // ---- deferred normalisation (mode 1).  p = exp(l - logZ_n) of tile t is written while the MMAs of tile t+1 run: after
-    //      each of the next tile's first 16 group epilogues every warp normalises two more rows of the previous tile (L2
-    //      hits), accumulating the column sums in its shared-memory row of `colsum`; after slice 15 the 8 rows are added
-    //      in a fixed order into NAacc.  Done synchronously at the tile end this pass cost 7 % of the kernel.
-    const int K4 = K >> 2;
-    int pend_t = -1;                                            // local index of the tile whose rows await normalisation
-    auto norm_slice = [&](int pt, int k) {
-      const long long row0 = ((long long)blockIdx.x + (long long)pt * gridDim.x) * EU_TILE;
-      const long long rem = a.N - row0;
-      const int rows = rem < EU_TILE ? (int)rem : EU_TILE;
-      const float* lzp = lz + (pt & 1) * EU_TILE;
-      const int r = w8 + 16 * k;
-      float4 x[2][EU_MAXK / 128];
-#pragma unroll
-      for (int v = 0; v < 2; ++v) {
-        const int rr = r + 8 * v;
-        const float4* prow = reinterpret_cast<const float4*>(a.out + (size_t)(row0 + (rr < rows ? rr : 0)) * K);
-#pragma unroll
-        for (int u = 0; u < EU_MAXK / 128; ++u) {
-          const int c4 = lane + 32 * u;
-          if (c4 < K4 && rr < rows) x[v][u] = __ldcg(prow + c4);
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < EU_MAXK / 128; ++u) {
-        const int c4 = lane + 32 * u;
-        if (c4 < K4) {
-          float4 cs = *reinterpret_cast<float4*>(colsum + (size_t)w8 * K + 4 * c4);
-#pragma unroll
-          for (int v = 0; v < 2; ++v) {
-            const int rr = r + 8 * v;
-            if (rr < rows) {
-              const float lzr = lzp[rr];
-              float4 y = x[v][u];
-              y.x = expf(y.x - lzr); y.y = expf(y.y - lzr); y.z = expf(y.z - lzr); y.w = expf(y.w - lzr);
-              reinterpret_cast<float4*>(a.out + (size_t)(row0 + rr) * K)[c4] = y;
-              cs.x += y.x; cs.y += y.y; cs.z += y.z; cs.w += y.w;
-            }
-          }
-          *reinterpret_cast<float4*>(colsum + (size_t)w8 * K + 4 * c4) = cs;
-        }
-      }
-    };
-    auto norm_finish = [&]() {
-      named_bar_sync(1, 256);
-      for (int k = wtid; k < K; k += 256) {
-        float sacc = 0.f;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) { sacc += colsum[(size_t)w * K + k]; }      // fixed order
-        NAacc[k] += (double)sacc;
-      }
-      named_bar_sync(1, 256);
-      for (int k = wtid; k < 8 * K; k += 256) colsum[k] = 0.f;
-      named_bar_sync(1, 256);
-    };
-    if (MODE == 1) {
-      for (int k = wtid; k < 8 * K; k += 256) colsum[k] = 0.f;
-      named_bar_sync(1, 256);
-    }
+    Ring rg;
+    BufRing<C::NBUF> br(h);
     for (int t = 0; t < my_tiles; ++t) {
       const long long tile = (long long)blockIdx.x + (long long)t * gridDim.x;
       const long long row = tile * EU_TILE + rloc;
       const bool valid = row < a.N;
-      // ---- this thread's sample row, split into TF32 hi / lo, into TMEM (previous tile's MMAs on this half
+      // ---- this thread's sample row, split into hi / lo, into TMEM (previous tile's MMAs on this half
       //      are complete: we waited on tfull of its last group)
+      float rs = 1.f;                                            // 2^-sh of this row (fp16 operands)
       {
-        const uint32_t a_hi = tm + lane_base + h * 2 * DP, a_lo = a_hi + DP;
+        const uint32_t a_hi = tm + lane_base + h * 2 * C::ACOLS, a_lo = a_hi + C::ACOLS;
         const float* r0 = a.z0 + (size_t)(valid ? row : 0) * a.d0;
         const float* r1 = a.z1 ? a.z1 + (size_t)(valid ? row : 0) * a.d1 : nullptr;
         const bool vec = valid && (a.d0 % 4 == 0) && (a.d1 % 4 == 0);
-#pragma unroll
-        for (int c0 = 0; c0 < DP; c0 += 16) {
-          float v[16];
+        auto load16 = [&](int c0, float* v) {
           if (vec) {
 #pragma unroll
             for (int j = 0; j < 16; j += 4) {
@@ -309,11 +332,52 @@ estep_umma_kernel(EstepArgs a, const uint8_t* __restrict__ Wp, int ntiles, int n
               v[j] = !valid ? 0.f : (f < a.d0 ? __ldg(r0 + f) : (f < D ? __ldg(r1 + (f - a.d0)) : 0.f));
             }
           }
-          uint32_t hi[16], lo[16];
+        };
+        if (F16) {
+          float v[DP];
+          float mxa = 0.f;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) split_tf32(v[j], hi[j], lo[j]);
-          tmem_st16(a_hi + c0, hi);
-          tmem_st16(a_lo + c0, lo);
+          for (int c0 = 0; c0 < DP; c0 += 16) {
+            load16(c0, v + c0);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) mxa = fmaxf(mxa, fabsf(v[c0 + j]));
+          }
+          int sh = 0;
+          if (mxa > 0.f) {
+            sh = 10 - ((int)(__float_as_uint(mxa) >> 23) - 127);
+            sh = sh > 60 ? 60 : (sh < -60 ? -60 : sh);
+          }
+          const float sc = __uint_as_float((uint32_t)(127 + sh) << 23);
+          rs = __uint_as_float((uint32_t)(127 - sh) << 23);
+#pragma unroll
+          for (int c0 = 0; c0 < DP; c0 += 16) {
+            uint32_t hi[8], lo[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float x0 = v[c0 + 2 * j] * sc, x1 = v[c0 + 2 * j + 1] * sc;
+              const __half2 ah = __floats2half2_rn(x0, x1);
+              const float2 af = __half22float2(ah);
+              const __half2 bh = __floats2half2_rn(x0 - af.x, x1 - af.y);
+              hi[j] = *reinterpret_cast<const uint32_t*>(&ah);
+              lo[j] = *reinterpret_cast<const uint32_t*>(&bh);
+            }
+            tmem_st8(a_hi + c0 / 2, hi);
+            tmem_st8(a_lo + c0 / 2, lo);
+          }
+          // the row's scale into the A block of the -m MMA (k = 0 meets -m_hi, k = 1 meets -m_lo)
+          *reinterpret_cast<float2*>(ones + h * 1024 + (q * 32 + lane) * 4) = make_float2(sc, sc);
+          fence_proxy_async();
+        } else {
+#pragma unroll
+          for (int c0 = 0; c0 < DP; c0 += 16) {
+            float v[16];
+            load16(c0, v);
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) split_tf32(v[j], hi[j], lo[j]);
+            tmem_st16(a_hi + c0, hi);
+            tmem_st16(a_lo + c0, lo);
+          }
         }
         tmem_wait_st();
         tc_fence_before();
@@ -321,37 +385,48 @@ estep_umma_kernel(EstepArgs a, const uint8_t* __restrict__ Wp, int ntiles, int n
       }
       float mx = -INFINITY, sm = 0.f;
       float l4[4];
-      for (int g = 0; g < ngroups; ++g, ++it) {
-        const int s = (int)(it % nstage);
+      for (int g = 0; g < ngroups; ++g, rg.next(nstage), br.next()) {
+        const int s = rg.s;
         const float* cstage = reinterpret_cast<const float*>(stages + (size_t)s * C::STAGE + C::GB + C::MB);
-        mbar_wait(&S->tfull[h], (uint32_t)(it & 1));
-        mbar_wait(&S->full[s], (uint32_t)(it / nstage) & 1);   // already complete; acquires the stage's m / cst
+        mbar_wait(&S->tfull[br.buf], br.ph);      // the MMAs read the stage, so its bulk copy (m, cst too) has landed
         tc_fence_after();
-        const uint32_t dcol = tm + lane_base + 256 + h * EU_N;
-        float2 q[C::CG];                                     // packed fp32x2 accumulators (FFMA2)
-#pragma unroll
-        for (int cl = 0; cl < C::CG; ++cl) q[cl] = make_float2(0.f, 0.f);
+        const uint32_t dcol = tm + lane_base + C::DCOL0 + br.buf * EU_N;
         // all 128 columns into registers, then hand the accumulator straight back to the MMA warp: the arithmetic
-        // below overlaps the next MMAs on this half
+        // below overlaps the next MMAs
         float y[EU_N];
         tmem_ld32(dcol, y);
         tmem_ld32(dcol + 32, y + 32);
         tmem_ld32(dcol + 64, y + 64);
         tmem_ld32(dcol + 96, y + 96);
+        float cs[C::CG], cv[C::CG];
+#pragma unroll
+        for (int cl = 0; cl < C::CG; ++cl) { cv[cl] = cstage[cl]; cs[cl] = cstage[8 + cl]; }
         tmem_wait_ld();
         tc_fence_before();
-        mbar_arrive(&S->tempty[h]);
+        mbar_arrive(&S->tempty[br.buf]);
+        // packed fp32x2 accumulators (FFMA2), NQ independent chains per component
+        constexpr int NQ = C::CG >= 4 ? 1 : 4 / C::CG;
+        float2 qa[C::CG][NQ];
+#pragma unroll
+        for (int cl = 0; cl < C::CG; ++cl)
+#pragma unroll
+          for (int u = 0; u < NQ; ++u) qa[cl][u] = make_float2(0.f, 0.f);
 #pragma unroll
         for (int j = 0; j < EU_N; j += 2) {                   // y already holds W^T z - m
           const int cl = C::col_cl(j);                        // columns j, j+1 belong to the same component
-          const float2 r = make_float2(y[j], y[j + 1]);
-          q[cl] = __ffma2_rn(r, r, q[cl]);
+          const int u = (j / (8 * C::CG)) % NQ;
+          float2 r = make_float2(y[j], y[j + 1]);
+          if (F16) { const float f = rs * cs[cl]; r = __fmul2_rn(r, make_float2(f, f)); }   // 2^-(sh_n + t_k), exact
+          qa[cl][u] = __ffma2_rn(r, r, qa[cl][u]);
         }
 #pragma unroll
         for (int cl = 0; cl < C::CG; ++cl) {
           const int c = g * C::CG + cl;
           if (c < K) {
-            const float l = cstage[cl] - 0.5f * (q[cl].x + q[cl].y);
+            float2 qq = qa[cl][0];
+#pragma unroll
+            for (int u = 1; u < NQ; ++u) qq = __fadd2_rn(qq, qa[cl][u]);
+            const float l = cv[cl] - 0.5f * (qq.x + qq.y);
             if (MODE == 1) {          // online logsumexp with one exp per component (ex2.approx: rel. error 2^-22)
               const float e = exp2f(-1.44269504f * fabsf(l - mx));
               sm = (l > mx) ? fmaf(sm, e, 1.f) : sm + e;
@@ -363,27 +438,14 @@ estep_umma_kernel(EstepArgs a, const uint8_t* __restrict__ Wp, int ntiles, int n
           }
         }
         mbar_arrive(&S->empty[s]);                  // done with the stage's cst (the two MMA commits are the other arrivals)
-        if (MODE == 1 && pend_t >= 0 && g < 16) {
-          norm_slice(pend_t, g);
-          if (g == 15) { norm_finish(); pend_t = -1; }
-        }
-      }
-      if (MODE == 1 && pend_t >= 0) {               // fewer than 16 groups: finish the previous tile now
-        for (int k = ngroups; k < 16; ++k) norm_slice(pend_t, k);
-        norm_finish();
-        pend_t = -1;
       }
       if (MODE == 1) {
         const float v = valid ? mx + logf(sm) : 0.f;
+        if (t >= 2) mbar_wait(&S->nfree[t & 1], ((uint32_t)(t >> 1) & 1) ^ 1);    // tile t-2 has been normalised
         lz[(t & 1) * EU_TILE + rloc] = v;
         if (valid) { a.logZn[row] = v; lzsum += (double)v; }
-        named_bar_sync(1, 256);                     // the tile's logits and logZ_n are visible to all workers
-        pend_t = t;
+        mbar_arrive(&S->ndone[t & 1]);              // release: this thread's logits and logZ_n of the tile
       }
-    }
-    if (MODE == 1 && pend_t >= 0) {                 // last tile: nothing left to hide behind
-      for (int k = 0; k < 16; ++k) norm_slice(pend_t, k);
-      norm_finish();
     }
     if (MODE == 1) {
       // sum of logZ_n over this CTA's rows (fixed order: warp shuffle tree, then warps in order)
@@ -395,7 +457,68 @@ estep_umma_kernel(EstepArgs a, const uint8_t* __restrict__ Wp, int ntiles, int n
         for (int w = 0; w < 8; ++w) s += S->red[w];
         a.logZ_part[blockIdx.x] = s;
       }
-      for (int k = wtid; k < K; k += 256) a.NA_part[(size_t)blockIdx.x * K + k] = (float)NAacc[k];
+    }
+  } else if (MODE == 1) {
+    // ================= normaliser (mode 1): p = exp(l - logZ_n) of tile t, written while the MMAs of tile t+1 run ==========
+    // One warp re-reads the tile's logits (L2 hits), normalises them in place with coalesced float4 accesses, 4 rows in
+    // flight, and keeps the column sums NA of its fixed columns in registers (float per tile, double across tiles: a
+    // fixed order, so NA is deterministic).  Inline in the epilogue warps this pass sat on their critical path.
+    constexpr int NU = EU_MAXK / 128;                      // float4 columns per lane
+    const int K4 = K >> 2;
+    double na[NU][4];
+#pragma unroll
+    for (int u = 0; u < NU; ++u) na[u][0] = na[u][1] = na[u][2] = na[u][3] = 0.0;
+    for (int t = 0; t < my_tiles; ++t) {
+      const long long row0 = ((long long)blockIdx.x + (long long)t * gridDim.x) * EU_TILE;
+      const long long rem = a.N - row0;
+      const int rows = rem < EU_TILE ? (int)rem : EU_TILE;
+      const float* lzp = lz + (t & 1) * EU_TILE;
+      mbar_wait(&S->ndone[t & 1], (uint32_t)(t >> 1) & 1);
+      float4 cs[NU];
+#pragma unroll
+      for (int u = 0; u < NU; ++u) cs[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int r = 0; r < rows; r += 4) {
+        float4 x[4][NU];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          const int rr = r + v < rows ? r + v : rows - 1;
+          const float4* prow = reinterpret_cast<const float4*>(a.out + (size_t)(row0 + rr) * K);
+#pragma unroll
+          for (int u = 0; u < NU; ++u) {
+            const int c4 = lane + 32 * u;
+            if (c4 < K4) x[v][u] = __ldcg(prow + c4);
+          }
+        }
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          if (r + v < rows) {
+            const float lzr = lzp[r + v];
+#pragma unroll
+            for (int u = 0; u < NU; ++u) {
+              const int c4 = lane + 32 * u;
+              if (c4 < K4) {
+                float4 y = x[v][u];
+                y.x = expf(y.x - lzr); y.y = expf(y.y - lzr); y.z = expf(y.z - lzr); y.w = expf(y.w - lzr);
+                reinterpret_cast<float4*>(a.out + (size_t)(row0 + r + v) * K)[c4] = y;
+                cs[u].x += y.x; cs[u].y += y.y; cs[u].z += y.z; cs[u].w += y.w;
+              }
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < NU; ++u) {
+        na[u][0] += (double)cs[u].x; na[u][1] += (double)cs[u].y; na[u][2] += (double)cs[u].z; na[u][3] += (double)cs[u].w;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&S->nfree[t & 1]);
+    }
+#pragma unroll
+    for (int u = 0; u < NU; ++u) {
+      const int c4 = lane + 32 * u;
+      if (c4 < K4)
+        reinterpret_cast<float4*>(a.NA_part + (size_t)blockIdx.x * K)[c4] =
+            make_float4((float)na[u][0], (float)na[u][1], (float)na[u][2], (float)na[u][3]);
     }
   }
   tc_fence_before();
@@ -415,7 +538,16 @@ static int eu_num_sms() {
   return n;
 }
 
-static size_t eu_group_bytes(int Dp) { return Dp == 64 ? EuCfg<64>::REC : (Dp == 32 ? EuCfg<32>::REC : EuCfg<16>::REC); }
+// the TF32 record is the larger one: the workspace is sized for it whichever precision runs
+static size_t eu_group_bytes(int Dp) { return Dp == 64 ? EuCfg<64, false>::REC : (Dp == 32 ? EuCfg<32, false>::REC : EuCfg<16, false>::REC); }
+static bool eu_use_f16() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("VBMP_ESTEP_PREC");
+    v = (e && (e[0] == 't' || e[0] == 'T')) ? 0 : 1;
+  }
+  return v == 1;
+}
 static int eu_cg(int Dp) { return EU_N / Dp; }
 static size_t eu_align(size_t x) { return (x + 255) / 256 * 256; }
 
@@ -434,18 +566,17 @@ size_t estep_umma_workspace_bytes(long long N, int G, int K, int Dp, int mode) {
 
 int launch_estep_reduce(const float*, const double*, int nb, int G, int K, float* NA, float* logZ, cudaStream_t);
 
-template <int DP>
+template <int DP, bool F16>
 static int eu_launch(EstepArgs a, int mode, uint8_t* Wp, float* NA_part, double* logZ_part, float* NA, float* logZ,
                      cudaStream_t st) {
-  using C = EuCfg<DP>;
+  using C = EuCfg<DP, F16>;
   const int ngroups = (a.K + C::CG - 1) / C::CG;
-  estep_pack_kernel<DP><<<ngroups, 256, 0, st>>>(a.W, a.m, a.cst, a.K, Wp);
+  estep_pack_kernel<DP, F16><<<ngroups, 256, 0, st>>>(a.W, a.m, a.cst, a.K, Wp);
   int rc = check_launch("estep_pack");
   if (rc) return rc;
   const int ntiles = (int)((a.N + EU_TILE - 1) / EU_TILE);
   const int grid = ntiles < eu_num_sms() ? ntiles : eu_num_sms();
-  const size_t fixed = 4096 + sizeof(EuSmem) + 2 * EU_TILE * sizeof(float) +
-                       (mode == 1 ? (size_t)8 * a.K * sizeof(float) + (size_t)a.K * sizeof(double) : 0) + 64;
+  const size_t fixed = 8192 + sizeof(EuSmem) + 2 * EU_TILE * sizeof(float) + 64;
   int nstage = (int)((227 * 1024 - fixed) / C::STAGE);
   if (nstage > EU_MAXSTAGE) nstage = EU_MAXSTAGE;
   if (nstage < 2) { set_error("estep_umma: shared memory too small for K=%d", a.K); return VBMP_ERR_UNSUPPORTED; }
@@ -453,11 +584,11 @@ static int eu_launch(EstepArgs a, int mode, uint8_t* Wp, float* NA_part, double*
   a.NA_part = NA_part;
   a.logZ_part = logZ_part;
   if (mode == 0) {
-    cudaFuncSetAttribute(estep_umma_kernel<DP, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    estep_umma_kernel<DP, 0><<<grid, EU_THREADS, smem, st>>>(a, Wp, ntiles, ngroups, nstage);
+    cudaFuncSetAttribute(estep_umma_kernel<DP, 0, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    estep_umma_kernel<DP, 0, F16><<<grid, EU_THREADS, smem, st>>>(a, Wp, ntiles, ngroups, nstage);
   } else {
-    cudaFuncSetAttribute(estep_umma_kernel<DP, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    estep_umma_kernel<DP, 1><<<grid, EU_THREADS, smem, st>>>(a, Wp, ntiles, ngroups, nstage);
+    cudaFuncSetAttribute(estep_umma_kernel<DP, 1, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    estep_umma_kernel<DP, 1, F16><<<grid, EU_THREADS, smem, st>>>(a, Wp, ntiles, ngroups, nstage);
   }
   rc = check_launch("estep_umma");
   if (rc) return rc;
@@ -475,10 +606,18 @@ int launch_estep_umma(const EstepArgs& a, int mode, void* ws, size_t ws_bytes, f
   float* NA_part = (float*)p;
   p += eu_align((size_t)512 * a.K * sizeof(float));
   double* logZ_part = (double*)p;
-  switch (a.Dp) {
-    case 64: return eu_launch<64>(a, mode, Wp, NA_part, logZ_part, NA, logZ, st);
-    case 32: return eu_launch<32>(a, mode, Wp, NA_part, logZ_part, NA, logZ, st);
-    case 16: return eu_launch<16>(a, mode, Wp, NA_part, logZ_part, NA, logZ, st);
+  if (eu_use_f16()) {
+    switch (a.Dp) {
+      case 64: return eu_launch<64, true>(a, mode, Wp, NA_part, logZ_part, NA, logZ, st);
+      case 32: return eu_launch<32, true>(a, mode, Wp, NA_part, logZ_part, NA, logZ, st);
+      case 16: return eu_launch<16, true>(a, mode, Wp, NA_part, logZ_part, NA, logZ, st);
+    }
+  } else {
+    switch (a.Dp) {
+      case 64: return eu_launch<64, false>(a, mode, Wp, NA_part, logZ_part, NA, logZ, st);
+      case 32: return eu_launch<32, false>(a, mode, Wp, NA_part, logZ_part, NA, logZ, st);
+      case 16: return eu_launch<16, false>(a, mode, Wp, NA_part, logZ_part, NA, logZ, st);
+    }
   }
   set_error("estep_umma: Dp=%d not supported", a.Dp);
   return VBMP_ERR_UNSUPPORTED;

@@ -574,12 +574,6 @@ static void run_eseq2() {
 // ---- kind::f16 (fp16 operands, fp32 accumulate), A in TMEM packed two fp16 per 32-bit column, B K-major in smem:
 //      checks the packing order and the K = 16 step.
 #include <cuda_fp16.h>
-__device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__host__ __device__ constexpr uint32_t idesc_f16(int M, int N) {       // fp16 x fp16 -> f32, both K-major
-  return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
 // A: [128][K] fp32 values (exactly representable in fp16), Bp: fp16 packed K-major image [K/8 chunks][N rows][8], D: [128][N]
 __global__ void __launch_bounds__(128, 1) f16_kernel(const float* __restrict__ A, const __half* __restrict__ Bp, float* __restrict__ D, int N, int K) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -740,9 +734,52 @@ static void run_eseq3() {
   cudaFree(dc);
 }
 
+// ---- TMEM read throughput: NW warps each re-read their 32 lanes x 128 columns (4 x tcgen05.ld.32x32b.x32) in a loop.
+__global__ void __launch_bounds__(512, 1) ldtm_kernel(int iters, long long* cycles, float* sink) {
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (warp == 0) tmem_alloc<512>(&tmem_base_s);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tm = tmem_base_s + ((uint32_t)((warp & 3) * 32) << 16) + (warp >> 2) * 128;
+  float acc = 0.f;
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int i = 0; i < iters; ++i) {
+    float y[128];
+    tmem_ld32(tm, y); tmem_ld32(tm + 32, y + 32); tmem_ld32(tm + 64, y + 64); tmem_ld32(tm + 96, y + 96);
+    tmem_wait_ld();
+#pragma unroll
+    for (int j = 0; j < 128; j += 32) acc += y[j];
+  }
+  __syncthreads();
+  const long long t1 = clock64();
+  if (tid == 0) cycles[blockIdx.x] = t1 - t0;
+  sink[blockIdx.x * blockDim.x + tid] = acc;
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tmem_base_s);
+}
+static void run_ldtm(int nwarps) {
+  const int iters = 2000, grid = 148;
+  long long* dc; float* ds;
+  CK(cudaMalloc(&dc, grid * sizeof(long long))); CK(cudaMalloc(&ds, grid * 512 * sizeof(float)));
+  ldtm_kernel<<<grid, nwarps * 32>>>(10, dc, ds);
+  CK(cudaDeviceSynchronize());
+  ldtm_kernel<<<grid, nwarps * 32>>>(iters, dc, ds);
+  CK(cudaDeviceSynchronize());
+  std::vector<long long> c(grid);
+  CK(cudaMemcpy(c.data(), dc, grid * sizeof(long long), cudaMemcpyDeviceToHost));
+  long long mx = 0; for (auto v : c) if (v > mx) mx = v;
+  printf("ldtm %2d warps: %.1f B/cycle/SM (%.0f cycles per 128-col pass)\n", nwarps, (double)nwarps * 32 * 128 * 4 * iters / mx, (double)mx / iters);
+  cudaFree(dc); cudaFree(ds);
+}
+
 int main(int argc, char** argv) {
   srand(1);
   int fails = 0;
+  if (argc > 1 && atoi(argv[1]) == 9) { for (int w : {1, 4, 8, 16}) run_ldtm(w); return 0; }
   if (argc > 1 && atoi(argv[1]) == 8) { run_eseq2<4>(); run_eseq3<0>(); run_eseq3<1>(); run_eseq3<2>(); return 0; }
   if (argc > 1 && atoi(argv[1]) == 7) { int f = 0; for (int N : {32, 96, 128}) for (int K : {16, 64}) f += run_f16_case(N, K); printf("f16 probe: %d failing\n", f); return f; }
   if (argc > 1 && atoi(argv[1]) == 6) { run_eseq2<0>(); run_eseq2<1>(); run_eseq2<2>(); run_eseq2<3>(); run_eseq2<4>(); return 0; }
