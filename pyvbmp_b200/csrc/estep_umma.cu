@@ -36,6 +36,7 @@
 //     so nothing can overflow that would not overflow in the unscaled form.  Zero rows get sh = 0; sh and t are clamped to
 //     +-60.
 #include <cstdlib>
+#include <type_traits>
 #include <cuda_fp16.h>
 #include "common.cuh"
 #include "umma.cuh"
@@ -463,53 +464,69 @@ estep_umma_kernel(EstepArgs a, const uint8_t* __restrict__ Wp, int ntiles, int n
     // One warp re-reads the tile's logits (L2 hits), normalises them in place with coalesced float4 accesses, 4 rows in
     // flight, and keeps the column sums NA of its fixed columns in registers (float per tile, double across tiles: a
     // fixed order, so NA is deterministic).  Inline in the epilogue warps this pass sat on their critical path.
-    constexpr int NU = EU_MAXK / 128;                      // float4 columns per lane
+    constexpr int NU = EU_MAXK / 128;                      // float4 columns per lane (K = 512)
     const int K4 = K >> 2;
-    double na[NU][4];
-#pragma unroll
-    for (int u = 0; u < NU; ++u) na[u][0] = na[u][1] = na[u][2] = na[u][3] = 0.0;
-    for (int t = 0; t < my_tiles; ++t) {
+    double* na = reinterpret_cast<double*>(lz + 2 * EU_TILE);       // [K] running column sums (each lane owns its columns)
+    for (int k = lane; k < K; k += 32) na[k] = 0.0;
+    __syncwarp();
+    // 16 float4 loads in flight per lane: RB rows of NUA float4 columns each (NUA = columns this K needs)
+    auto ex2 = [](float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; };
+    auto norm_tile = [&](auto nua_c, int t) {
+      constexpr int NUA = decltype(nua_c)::value, RB = 16 / NUA;
       const long long row0 = ((long long)blockIdx.x + (long long)t * gridDim.x) * EU_TILE;
       const long long rem = a.N - row0;
       const int rows = rem < EU_TILE ? (int)rem : EU_TILE;
       const float* lzp = lz + (t & 1) * EU_TILE;
-      mbar_wait(&S->ndone[t & 1], (uint32_t)(t >> 1) & 1);
-      float4 cs[NU];
+      float4* base = reinterpret_cast<float4*>(a.out) + (size_t)row0 * K4 + lane;     // 32-bit offsets from here on
+      bool cok[NUA];
 #pragma unroll
-      for (int u = 0; u < NU; ++u) cs[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int r = 0; r < rows; r += 4) {
-        float4 x[4][NU];
+      for (int u = 0; u < NUA; ++u) cok[u] = lane + 32 * u < K4;
+      float4 cs[NUA];
 #pragma unroll
-        for (int v = 0; v < 4; ++v) {
-          const int rr = r + v < rows ? r + v : rows - 1;
-          const float4* prow = reinterpret_cast<const float4*>(a.out + (size_t)(row0 + rr) * K);
+      for (int u = 0; u < NUA; ++u) cs[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int r = 0; r < rows; r += RB) {
+        float4 x[RB][NUA];
 #pragma unroll
-          for (int u = 0; u < NU; ++u) {
-            const int c4 = lane + 32 * u;
-            if (c4 < K4) x[v][u] = __ldcg(prow + c4);
-          }
+        for (int v = 0; v < RB; ++v) {
+          const float4* pr = base + min(r + v, rows - 1) * K4;
+#pragma unroll
+          for (int u = 0; u < NUA; ++u) x[v][u] = cok[u] ? __ldcg(pr + 32 * u) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
-        for (int v = 0; v < 4; ++v) {
-          if (r + v < rows) {
-            const float lzr = lzp[r + v];
+        for (int v = 0; v < RB; ++v) {
+          // exp(l - logZ_n) = 2^((l - logZ_n) log2 e) with ex2.approx (rel. error 2^-22): four instructions per element.
+          // The full-range expf with its operand set-up came to ~50 per element, more than one warp can issue per tile.
+          const bool rok = r + v < rows;
+          const float lzr = lzp[min(r + v, rows - 1)];
+          float4* pw = base + (r + v) * K4;
 #pragma unroll
-            for (int u = 0; u < NU; ++u) {
-              const int c4 = lane + 32 * u;
-              if (c4 < K4) {
-                float4 y = x[v][u];
-                y.x = expf(y.x - lzr); y.y = expf(y.y - lzr); y.z = expf(y.z - lzr); y.w = expf(y.w - lzr);
-                reinterpret_cast<float4*>(a.out + (size_t)(row0 + r + v) * K)[c4] = y;
-                cs[u].x += y.x; cs[u].y += y.y; cs[u].z += y.z; cs[u].w += y.w;
-              }
+          for (int u = 0; u < NUA; ++u) {
+            float4 y = x[v][u];
+            y.x = ex2((y.x - lzr) * 1.44269504f); y.y = ex2((y.y - lzr) * 1.44269504f);
+            y.z = ex2((y.z - lzr) * 1.44269504f); y.w = ex2((y.w - lzr) * 1.44269504f);
+            if (rok && cok[u]) {
+              pw[32 * u] = y;
+              cs[u].x += y.x; cs[u].y += y.y; cs[u].z += y.z; cs[u].w += y.w;
             }
           }
         }
       }
 #pragma unroll
-      for (int u = 0; u < NU; ++u) {
-        na[u][0] += (double)cs[u].x; na[u][1] += (double)cs[u].y; na[u][2] += (double)cs[u].z; na[u][3] += (double)cs[u].w;
+      for (int u = 0; u < NUA; ++u) {
+        const int c4 = lane + 32 * u;
+        if (c4 < K4) {
+          na[4 * c4] += (double)cs[u].x; na[4 * c4 + 1] += (double)cs[u].y;
+          na[4 * c4 + 2] += (double)cs[u].z; na[4 * c4 + 3] += (double)cs[u].w;
+        }
       }
+    };
+    for (int t = 0; t < my_tiles; ++t) {
+      mbar_wait(&S->ndone[t & 1], (uint32_t)(t >> 1) & 1);
+#ifndef EU_DBG_NONORM
+      if (K4 <= 32) norm_tile(std::integral_constant<int, 1>{}, t);
+      else if (K4 <= 64) norm_tile(std::integral_constant<int, 2>{}, t);
+      else norm_tile(std::integral_constant<int, 4>{}, t);
+#endif
       __syncwarp();
       if (lane == 0) mbar_arrive(&S->nfree[t & 1]);
     }
@@ -518,7 +535,7 @@ estep_umma_kernel(EstepArgs a, const uint8_t* __restrict__ Wp, int ntiles, int n
       const int c4 = lane + 32 * u;
       if (c4 < K4)
         reinterpret_cast<float4*>(a.NA_part + (size_t)blockIdx.x * K)[c4] =
-            make_float4((float)na[u][0], (float)na[u][1], (float)na[u][2], (float)na[u][3]);
+            make_float4((float)na[4 * c4], (float)na[4 * c4 + 1], (float)na[4 * c4 + 2], (float)na[4 * c4 + 3]);
     }
   }
   tc_fence_before();
@@ -576,7 +593,7 @@ static int eu_launch(EstepArgs a, int mode, uint8_t* Wp, float* NA_part, double*
   if (rc) return rc;
   const int ntiles = (int)((a.N + EU_TILE - 1) / EU_TILE);
   const int grid = ntiles < eu_num_sms() ? ntiles : eu_num_sms();
-  const size_t fixed = 8192 + sizeof(EuSmem) + 2 * EU_TILE * sizeof(float) + 64;
+  const size_t fixed = 8192 + sizeof(EuSmem) + 2 * EU_TILE * sizeof(float) + (mode == 1 ? (size_t)a.K * sizeof(double) : 0) + 64;
   int nstage = (int)((227 * 1024 - fixed) / C::STAGE);
   if (nstage > EU_MAXSTAGE) nstage = EU_MAXSTAGE;
   if (nstage < 2) { set_error("estep_umma: shared memory too small for K=%d", a.K); return VBMP_ERR_UNSUPPORTED; }
