@@ -23,7 +23,18 @@
 //     the last row) into a 4-deep ring (warp 0), the MMAs are
 //     issued by warp 1 (3 split-precision terms x 2 K-steps per chunk), 8 worker warps split / multiply.
 //   * per-split partials are reduced in a fixed order in fp64 by gram_pair_reduce_kernel (deterministic).
+//
+// Operand precision (template parameter F16; the default, VBMP_GRAM_PREC=tf32 selects the TF32 split only):
+//   * FP16 split: r' = r 2^14 and zt'_i = zt_i 2^u_i (u_i puts the column maximum of |z_i| in [2^6, 2^7), found by a
+//     column-maximum pre-pass over Z) are EXACT rescalings; r' = a + b and phi' = zt'_i zt'_j = A + B with a, b, A, B fp16
+//     (22 significant bits, at least as accurate as the TF32 split) and the three terms run as kind::f16 MMAs with K = 16:
+//     twice the TF32 rate and half the operand bytes through shared memory, which is the kernel's limiter.  Chunks are
+//     32 samples, so a stage has the same footprint as a 16-sample TF32 stage.  The reduce kernel multiplies by
+//     2^-(14 + u_i + u_j) (exact).  Weights outside fp16 range after scaling (|r| > 3.99; responsibilities are <= 1)
+//     raise a device flag; the TF32 kernel, launched right behind, returns at once unless the flag is set, in which case
+//     it recomputes the partials — no host synchronisation, no silent loss of accuracy.
 #include <cstdlib>
+#include <cuda_fp16.h>
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -31,7 +42,10 @@ namespace vbmp {
 using namespace umma;
 
 constexpr int GU_THREADS = 576;      // warp 0 producer, warp 1 MMA issuer, two sets of 8 worker warps (even / odd chunks)
-constexpr int GU_SC = 16;            // samples per chunk (2 K-steps)
+constexpr int GU_SC = 16;            // samples per chunk (2 K-steps): TF32; the fp16 variant takes 32
+__host__ __device__ constexpr int gu_sc(bool f16) { return f16 ? 32 : 16; }
+constexpr int GU_RSH = 14;           // fp16 variant: responsibilities are scaled by 2^14
+constexpr float GU_RMAX = 3.99f;     // ... and must stay below 65504 / 2^14
 constexpr int GU_NR = 4;             // raw ring depth
 // pipeline depth (B stages in shared memory = A buffers in TMEM) and pair columns per MMA.  TMEM budget: D1 + D2 = 2 NPMAX
 // columns + NSTG A buffers of hi + lo = 32 NSTG columns <= 512.  A CTA pair needs 4 stages to hide the cross-CTA barrier
@@ -51,7 +65,25 @@ struct GuArgs {
   int kcb;                           // columns of the R box = min(128, K)
   int FL;                            // chunks per first-level accumulation block
   float* part;                       // [splits][Kp][PP]
+  // fp16 variant: hdr[0..64] = bit patterns of the column maxima of |zt_i| (the constant feature's is 1.0f), hdr[96] = flag
+  // "weights out of fp16 range, recompute with TF32 operands".  The TF32 kernel gets hdr too (nullptr = run always).
+  uint32_t* hdr;
+  // fp16 variant: the weights pre-split by gram_rsplit_kernel: record (component block cb, 16-sample block sb) at
+  // ((cb * nsb + sb) * 8192) bytes = [hi | lo] x [8-sample chunk (2)][component (128)][8 fp16], i.e. the TMEM image of
+  // the A operand of one K-step: lane = component, 16 bytes per chunk
+  const uint8_t* rp;
+  long long nsb;                     // 16-sample blocks per component block (N rounded up to 32, / 16)
 };
+constexpr int GU_HDR_FLAG = 96, GU_HDR_WORDS = 128;
+constexpr int GU_RREC = 8192;
+
+// exponent u_i of the exact feature scale 2^u_i (column maximum -> [2^6, 2^7)); 0 for an all-zero column
+__host__ __device__ inline int gu_feat_exp(uint32_t maxbits) {
+  const int e = (int)((maxbits >> 23) & 0xff);
+  if (e == 0) return 0;
+  int u = 6 - (e - 127);
+  return u > 60 ? 60 : (u < -60 ? -60 : u);
+}
 
 struct GuSmem {
   uint64_t rfull[GU_NR], rempty[GU_NR];
@@ -59,6 +91,7 @@ struct GuSmem {
   uint64_t dfull, dempty;
   uint32_t tmem_base;
   float consts[2];                   // {1, 0}: the padded "1" feature and the zero used by padding pair columns
+  float fscale[65];                  // fp16 variant: 2^u_i per feature of zt
 };
 
 // Pair p of the symmetric (D+1) x (D+1) Gram matrix over zt = [z;1]:  p < D(D+1)/2 walks the upper triangle of the
@@ -93,15 +126,19 @@ __device__ __forceinline__ void split_fast2(float2 x, uint32_t& hi0, uint32_t& h
 // PAIR: two CTAs (a cluster) take the two component blocks of a 256-component slab and share the phi block through
 // cta_group::2 MMAs (M = 256): each CTA generates and holds HALF of the pair columns, the hardware feeds both tensor
 // cores from both halves, so phi generation and the B-operand reads per SM halve (the shared-memory pipe is the limiter).
-template <int SF, bool R128, bool PAIR>
+template <int SF, bool R128, bool PAIR, bool F16>
 __global__ void __launch_bounds__(GU_THREADS, 1)
 gram_umma_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmZ0,
                  const __grid_constant__ CUtensorMap tmZ1, GuArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
+  constexpr int SC = gu_sc(F16);                          // samples per chunk
+  // TF32 variant behind an fp16 launch: only needed when that launch met weights outside fp16 range (uniform exit, before
+  // any barrier or allocation, for both CTAs of a pair)
+  if (!F16 && a.hdr != nullptr && a.hdr[GU_HDR_FLAG] == 0u) return;
   const int D = a.d0 + a.d1;
   // carve: raw ring [NR][R 16 x kcb floats | Z0 16 x d0 | Z1 16 x d1], B stages [2][hi NPB*64 B | lo NPB*64 B]
   const int kcb = R128 ? 128 : a.kcb;
-  const int rawR = GU_SC * kcb * 4, rawZ0 = GU_SC * a.d0 * 4, rawZ1 = GU_SC * a.d1 * 4;
+  const int rawR = F16 ? 2 * GU_RREC : SC * kcb * 4, rawZ0 = SC * a.d0 * 4, rawZ1 = SC * a.d1 * 4;
   const int rawB = (rawR + rawZ0 + rawZ1 + 127) / 128 * 128;
   constexpr int GU_NSTG = gu_nstg(PAIR), GU_NPMAX = gu_npmax(PAIR);
   const int NH = PAIR ? a.NPB / 2 : a.NPB;                 // pair columns generated (and held as B rows) by this CTA
@@ -120,7 +157,7 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant_
   const int split = task / (a.npb * ncbp);
   const long long nb = (long long)split * a.S_per;
   long long ne = nb + a.S_per; if (ne > a.N) ne = a.N;
-  const int nchunks = ne > nb ? (int)((ne - nb + GU_SC - 1) / GU_SC) : 0;
+  const int nchunks = ne > nb ? (int)((ne - nb + SC - 1) / SC) : 0;
   const int NPB = a.NPB, FL = a.FL;
 
   if (tid == 0) {
@@ -131,6 +168,7 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant_
     S->consts[0] = 1.f; S->consts[1] = 0.f;
     fence_barrier_init();
   }
+  if (F16 && tid < 65) S->fscale[tid] = __uint_as_float((uint32_t)(127 + gu_feat_exp(tid == D ? 0x3f800000u : a.hdr[tid])) << 23);
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmR); tma_prefetch_desc(&tmZ0); if (a.d1 > 0) tma_prefetch_desc(&tmZ1); }
   if (warp == 1) { if (PAIR) tmem_alloc2<512>(&S->tmem_base); else tmem_alloc<512>(&S->tmem_base); }
   tc_fence_before();
@@ -147,10 +185,11 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant_
       const int s = c % GU_NR;
       mbar_wait(&S->rempty[s], ((c / GU_NR) & 1) ^ 1);
       if (elect_one()) {
-        const int r0 = (int)(nb + (long long)c * GU_SC);
+        const int r0 = (int)(nb + (long long)c * SC);
         uint8_t* dst = raw + (size_t)s * rawB;
         mbar_arrive_expect_tx(&S->rfull[s], bytes);
-        tma_load_2d(dst, &tmR, cb * GU_CB, r0, &S->rfull[s]);
+        if (F16) bulk_g2s(dst, a.rp + ((size_t)cb * a.nsb + (size_t)(r0 >> 4)) * GU_RREC, 2 * GU_RREC, &S->rfull[s]);
+        else tma_load_2d(dst, &tmR, cb * GU_CB, r0, &S->rfull[s]);
         tma_load_2d(dst + rawR, &tmZ0, 0, r0, &S->rfull[s]);
         if (a.d1 > 0) tma_load_2d(dst + rawR + rawZ0, &tmZ1, 0, r0, &S->rfull[s]);
       }
@@ -159,7 +198,7 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant_
   } else if (warp == 1) {
     // ================= MMA issuer (the leader CTA's in a pair) =================
     if (!PAIR || rank == 0) {
-      const uint32_t idesc = idesc_tf32(PAIR ? 256 : 128, NPB);
+      const uint32_t idesc = F16 ? idesc_f16(PAIR ? 256 : 128, NPB) : idesc_tf32(PAIR ? 256 : 128, NPB);
       const uint64_t dstep = (uint64_t)((2 * NH * 16) >> 4);                 // one K-step = two 16-byte chunks
       const uint64_t d_hi0 = smem_desc(smem_u32(bst), NH * 16, 128), d_lo0 = d_hi0 + (uint64_t)((NH * 64) >> 4);
       int fc = 0, nflush = 0;
@@ -177,7 +216,15 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant_
 #pragma unroll
           for (int ks = 0; ks < 2; ++ks) {
             const uint64_t b_hi = d_hi0 + sofs + ks * dstep, b_lo = d_lo0 + sofs + ks * dstep;
-            if (PAIR) {
+            if (PAIR && F16) {
+              mma2_f16_ts(tm, a_lo + ks * 8, b_hi, idesc, !(first && ks == 0));
+              mma2_f16_ts(tm, a_hi + ks * 8, b_lo, idesc, 1);
+              mma2_f16_ts(tm, a_hi + ks * 8, b_hi, idesc, 1);
+            } else if (F16) {
+              mma_f16_ts(tm, a_lo + ks * 8, b_hi, idesc, !(first && ks == 0));
+              mma_f16_ts(tm, a_hi + ks * 8, b_lo, idesc, 1);
+              mma_f16_ts(tm, a_hi + ks * 8, b_hi, idesc, 1);
+            } else if (PAIR) {
               mma2_tf32_ts(tm, a_lo + ks * 8, b_hi, idesc, !(first && ks == 0));
               mma2_tf32_ts(tm, a_hi + ks * 8, b_lo, idesc, 1);
               mma2_tf32_ts(tm, a_hi + ks * 8, b_hi, idesc, 1);
@@ -209,9 +256,16 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant_
     // padding use the compile-time stride SF instead.
     const uint8_t* bi; const uint8_t* bj; int sli, slj, sti, stj;
     bool plain;
+    // fp16: a chunk has two 16-sample K-steps; when 2 NH <= 256 the threads split them (thread = pair x K-step), else
+    // every pair thread does both
+    const bool split_ks = F16 && 2 * NH <= 256;
+    const int pslot = split_ks ? wtid % NH : wtid;            // pair column (B row) generated by this thread
+    const int ks0 = split_ks ? wtid / NH : 0, ksn = F16 ? (split_ks ? 1 : 2) : 1;
+    const bool gen = split_ks ? wtid < 2 * NH : wtid < NH;
+    float pscale = 1.f;                                       // fp16: 2^(u_i + u_j)
     {
-      const int pg_ = pb * NPB + (int)rank * NH + wtid;
-      const bool pair_ok = (wtid < NH) && (pg_ < a.P);
+      const int pg_ = pb * NPB + (int)rank * NH + pslot;
+      const bool pair_ok = gen && (pg_ < a.P);
       int pi = 0, pj = 0;
       if (pair_ok) gu_pair(pg_, D, &pi, &pj);
       auto setup = [&](int f, const uint8_t*& b, int& sl, int& stv) {
@@ -223,6 +277,10 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant_
       setup(pi, bi, sli, sti);
       setup(pj, bj, slj, stj);
       plain = SF > 0 && __all_sync(0xffffffffu, pair_ok && pj < D);
+      if (F16) {
+        __syncwarp();
+        pscale = pair_ok ? S->fscale[pi] * S->fscale[pj] : 0.f;     // fscale was written before the CTA-wide sync above
+      }
     }
     const int fls = __ffs(FL) - 1;                       // FL is a power of two
     // barriers the workers signal: the leader CTA's (rank 0) in a pair, this CTA's own otherwise
@@ -236,8 +294,18 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant_
       mbar_wait(&S->rfull[s], (c / GU_NR) & 1);
       mbar_wait(&S->bempty[st], ((c / GU_NSTG) & 1) ^ 1);
       tc_fence_after();
-      // ---- A operand: r[s][comp] for this thread's 8 samples, split, into TMEM
-      {
+      // ---- A operand: r[s][comp] for this thread's 8 (fp16: 16) samples, split, into TMEM
+      if (F16) {
+        // pre-split by gram_rsplit_kernel: this thread's 16 samples are two 16-byte chunks of hi and two of lo
+        const uint8_t* rr = raw + (size_t)s * rawB + (size_t)sh * GU_RREC + (size_t)comp * 16;
+        const uint4 h0 = *reinterpret_cast<const uint4*>(rr), h1 = *reinterpret_cast<const uint4*>(rr + 2048);
+        const uint4 l0 = *reinterpret_cast<const uint4*>(rr + 4096), l1 = *reinterpret_cast<const uint4*>(rr + 6144);
+        const uint32_t hi[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+        const uint32_t lo[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+        const uint32_t ad = tm + lane_base + ACOL + st * 32 + sh * 8;
+        tmem_st8(ad, hi);
+        tmem_st8(ad + 16, lo);
+      } else {
         const float* rawr = reinterpret_cast<const float*>(raw + (size_t)s * rawB) + (sh * 8) * kcb + comp;
         uint32_t hi[8], lo[8];
 #pragma unroll
@@ -249,51 +317,81 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant_
         tmem_st8(ad, hi);
         tmem_st8(ad + 16, lo);
       }
-      // ---- B operand: phi[s][pair] = zt[s][i] * zt[s][j] for 16 samples, split, K-major core-matrix layout
-      if (wtid < NH) {
+      // ---- B operand: phi[s][pair] = zt[s][i] * zt[s][j], split, K-major core-matrix layout
+      if (F16) {
+        if (gen) {
+          const uint8_t* zi = bi + s * sli;
+          const uint8_t* zj = bj + s * slj;
+          const float2 ps2 = make_float2(pscale, pscale);
+          for (int kk = 0; kk < ksn; ++kk) {
+            const int ks = ks0 + kk;
+            uint8_t* bh = bst + (size_t)st * stageB + (size_t)ks * (2 * NH * 16) + (size_t)pslot * 16;
+            uint8_t* bl = bh + NH * 64;
+#pragma unroll
+            for (int qd = 0; qd < 2; ++qd) {                  // 8 samples = one 16-byte K-chunk of fp16
+              // the 16 loads first (the stores below may not be reordered above them), then multiply / split / store
+              float av[8], bv[8];
+              if (plain) {
+#pragma unroll
+                for (int sl = 0; sl < 8; ++sl) {
+                  av[sl] = *reinterpret_cast<const float*>(zi + (ks * 16 + qd * 8 + sl) * (SF * 4));
+                  bv[sl] = *reinterpret_cast<const float*>(zj + (ks * 16 + qd * 8 + sl) * (SF * 4));
+                }
+              } else {
+#pragma unroll
+                for (int sl = 0; sl < 8; ++sl) {
+                  av[sl] = *reinterpret_cast<const float*>(zi + (ks * 16 + qd * 8 + sl) * sti);
+                  bv[sl] = *reinterpret_cast<const float*>(zj + (ks * 16 + qd * 8 + sl) * stj);
+                }
+              }
+              uint32_t hi[4], lo[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const int sl = 2 * u;
+                // the fp32 product is rounded exactly as the reference's, then scaled by a power of two
+                const float2 x = __fmul2_rn(__fmul2_rn(make_float2(av[sl], av[sl + 1]), make_float2(bv[sl], bv[sl + 1])), ps2);
+                const __half2 ah = __floats2half2_rn(x.x, x.y);
+                const float2 af = __half22float2(ah);
+                const __half2 bh2 = __floats2half2_rn(x.x - af.x, x.y - af.y);
+                hi[u] = *reinterpret_cast<const uint32_t*>(&ah);
+                lo[u] = *reinterpret_cast<const uint32_t*>(&bh2);
+              }
+              *reinterpret_cast<uint4*>(bh + (size_t)qd * NH * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+              *reinterpret_cast<uint4*>(bl + (size_t)qd * NH * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            }
+          }
+        }
+      } else if (wtid < NH) {
         uint8_t* bh = bst + (size_t)st * stageB + (size_t)wtid * 16;
         uint8_t* bl = bh + NH * 64;
         const uint8_t* zi = bi + s * sli;
         const uint8_t* zj = bj + s * slj;
+        // all 32 loads first (the stores below may not be reordered above them), then multiply / split / store
+        float av[16], bv[16];
         if (plain) {
-          // all 32 loads first (the stores below may not be reordered above them), then multiply / split / store
-          float av[16], bv[16];
 #pragma unroll
           for (int sl = 0; sl < 16; ++sl) {
             av[sl] = *reinterpret_cast<const float*>(zi + sl * (SF * 4));
             bv[sl] = *reinterpret_cast<const float*>(zj + sl * (SF * 4));
           }
-#pragma unroll
-          for (int qd = 0; qd < 4; ++qd) {
-            uint32_t hi[4], lo[4];
-#pragma unroll
-            for (int u = 0; u < 4; u += 2) {
-              const int sl = qd * 4 + u;
-              split_fast2(__fmul2_rn(make_float2(av[sl], av[sl + 1]), make_float2(bv[sl], bv[sl + 1])), hi[u], hi[u + 1],
-                          lo[u], lo[u + 1]);
-            }
-            *reinterpret_cast<uint4*>(bh + (size_t)qd * NH * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-            *reinterpret_cast<uint4*>(bl + (size_t)qd * NH * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-          }
         } else {
-          float av[16], bv[16];
 #pragma unroll
           for (int sl = 0; sl < 16; ++sl) {
             av[sl] = *reinterpret_cast<const float*>(zi + sl * sti);
             bv[sl] = *reinterpret_cast<const float*>(zj + sl * stj);
           }
+        }
 #pragma unroll
-          for (int qd = 0; qd < 4; ++qd) {
-            uint32_t hi[4], lo[4];
+        for (int qd = 0; qd < 4; ++qd) {
+          uint32_t hi[4], lo[4];
 #pragma unroll
-            for (int u = 0; u < 4; u += 2) {
-              const int sl = qd * 4 + u;
-              split_fast2(__fmul2_rn(make_float2(av[sl], av[sl + 1]), make_float2(bv[sl], bv[sl + 1])), hi[u], hi[u + 1],
-                          lo[u], lo[u + 1]);
-            }
-            *reinterpret_cast<uint4*>(bh + (size_t)qd * NH * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-            *reinterpret_cast<uint4*>(bl + (size_t)qd * NH * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          for (int u = 0; u < 4; u += 2) {
+            const int sl = qd * 4 + u;
+            split_fast2(__fmul2_rn(make_float2(av[sl], av[sl + 1]), make_float2(bv[sl], bv[sl + 1])), hi[u], hi[u + 1],
+                        lo[u], lo[u + 1]);
           }
+          *reinterpret_cast<uint4*>(bh + (size_t)qd * NH * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<uint4*>(bl + (size_t)qd * NH * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         }
       }
       // one arrival per warp: every lane fences its own writes, the warp converges, lane 0 publishes
@@ -352,9 +450,10 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant_
   if (warp == 1) { if (PAIR) tmem_dealloc2<512>(tm); else tmem_dealloc<512>(tm); }
 }
 
-// gram[k][i][j] = gram[k][j][i] = sum_split part[split][k][pair(i,j)], fp64, fixed order.
+// gram[k][i][j] = gram[k][j][i] = sum_split part[split][k][pair(i,j)], fp64, fixed order.  hdr != nullptr: the partials
+// came from the fp16 kernel (unless its flag says the TF32 kernel recomputed them) and carry the factor 2^(14 + u_i + u_j).
 __global__ void gram_pair_reduce_kernel(const float* __restrict__ part, int splits, int K, int Kp, int PP, int D1,
-                                        float* __restrict__ gram) {
+                                        const uint32_t* __restrict__ hdr, float* __restrict__ gram) {
   const int P = D1 * (D1 + 1) / 2;
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= (long long)K * P) return;
@@ -363,9 +462,73 @@ __global__ void gram_pair_reduce_kernel(const float* __restrict__ part, int spli
   gu_pair(p, D1 - 1, &i, &j);
   double acc = 0.0;
   for (int s = 0; s < splits; ++s) acc += (double)part[((size_t)s * Kp + k) * PP + p];
+  if (hdr != nullptr && hdr[GU_HDR_FLAG] == 0u) {
+    const int ui = gu_feat_exp(i == D1 - 1 ? 0x3f800000u : hdr[i]), uj = gu_feat_exp(j == D1 - 1 ? 0x3f800000u : hdr[j]);
+    acc = ldexp(acc, -(GU_RSH + ui + uj));
+  }
   const float v = (float)acc;
   gram[((size_t)k * D1 + i) * D1 + j] = v;
   gram[((size_t)k * D1 + j) * D1 + i] = v;
+}
+
+// column maxima of |z| (bit patterns, which order like the values for non-negative floats) into hdr[col0 + c]
+__global__ void __launch_bounds__(256) gram_colmax_kernel(const float* __restrict__ z, int d, long long N, int col0,
+                                                          uint32_t* __restrict__ hdr) {
+  __shared__ uint32_t smax[64];
+  if (threadIdx.x < 64) smax[threadIdx.x] = 0u;
+  __syncthreads();
+  const int d4 = d >> 2;                                         // d % 4 == 0
+  const long long T = ((long long)gridDim.x * blockDim.x) / d4 * d4;   // threads that keep a fixed column group
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < T) {
+    const long long n4 = N * d4;
+    float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f;
+    const float4* z4 = reinterpret_cast<const float4*>(z);
+    for (long long e = g; e < n4; e += T) {
+      const float4 v = __ldg(z4 + e);
+      m0 = fmaxf(m0, fabsf(v.x)); m1 = fmaxf(m1, fabsf(v.y)); m2 = fmaxf(m2, fabsf(v.z)); m3 = fmaxf(m3, fabsf(v.w));
+    }
+    const int c = (int)(g % d4) * 4;
+    atomicMax(&smax[c], __float_as_uint(m0)); atomicMax(&smax[c + 1], __float_as_uint(m1));
+    atomicMax(&smax[c + 2], __float_as_uint(m2)); atomicMax(&smax[c + 3], __float_as_uint(m3));
+  }
+  __syncthreads();
+  if (threadIdx.x < d && smax[threadIdx.x] != 0u) atomicMax(&hdr[col0 + threadIdx.x], smax[threadIdx.x]);
+}
+
+// fp16 variant pre-pass: r' = r 2^14 = a + b (a = rn_fp16(r'), b = rn_fp16(r' - a)) written once as the TMEM images the
+// Gram CTAs copy in (see GuArgs::rp).  Without it every pair-block CTA (12 at d = 64) repeated this split on the same
+// weights, which was 60 % of the worker instructions.  Thread = (8-sample chunk, component): 8 coalesced reads down a
+// column of p, one 16-byte store each to hi and lo.  Weights beyond fp16 range raise the fallback flag.
+__global__ void __launch_bounds__(256) gram_rsplit_kernel(const float* __restrict__ p, long long N, int K, int ncb, long long nsb,
+                                                          uint8_t* __restrict__ rp, uint32_t* __restrict__ hdr) {
+  const long long total = nsb * 2 * (long long)ncb * GU_CB;           // (chunk of 8 samples) x padded component
+  const float rsc = (float)(1 << GU_RSH);
+  float rmax = 0.f;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int kp = (int)(e % (ncb * GU_CB));
+    const long long ch = e / (ncb * GU_CB);                            // global 8-sample chunk
+    const int cb = kp / GU_CB, comp = kp % GU_CB;
+    const long long n0 = ch * 8;
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long n = n0 + 2 * u;
+      const float r0 = (kp < K && n < N) ? __ldg(p + (size_t)n * K + kp) : 0.f;
+      const float r1 = (kp < K && n + 1 < N) ? __ldg(p + (size_t)(n + 1) * K + kp) : 0.f;
+      rmax = fmaxf(rmax, fmaxf(fabsf(r0), fabsf(r1)));                 // (a NaN weight propagates through the MMA by itself)
+      const float x0 = r0 * rsc, x1 = r1 * rsc;
+      const __half2 ah = __floats2half2_rn(x0, x1);
+      const float2 af = __half22float2(ah);
+      const __half2 bh = __floats2half2_rn(x0 - af.x, x1 - af.y);
+      hi[u] = *reinterpret_cast<const uint32_t*>(&ah);
+      lo[u] = *reinterpret_cast<const uint32_t*>(&bh);
+    }
+    uint8_t* rec = rp + ((size_t)cb * nsb + (size_t)(ch >> 1)) * GU_RREC + (size_t)(ch & 1) * 2048 + (size_t)comp * 16;
+    *reinterpret_cast<uint4*>(rec) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(rec + 4096) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+  if (__any_sync(0xffffffffu, rmax > GU_RMAX) && (threadIdx.x & 31) == 0) atomicOr(&hdr[GU_HDR_FLAG], 1u);
 }
 
 // ---- host side -------------------------------------------------------------------------------------------
@@ -409,13 +572,16 @@ static void gu_plan(long long N, int K, int D, int sms, GuArgs* g) {
   if (sp > maxsp) sp = maxsp;
   if (sp < 1) sp = 1;
   long long per = (N + sp - 1) / sp;
-  per = (per + GU_SC - 1) / GU_SC * GU_SC;
+  per = (per + 31) / 32 * 32;                  // whole chunks of either variant (16 / 32 samples)
   g->S_per = per;
   g->splits = (int)((N + per - 1) / per);
   if (g->splits < 1) g->splits = 1;
   g->Kp = g->ncb * GU_CB;
   g->PP = g->npb * g->NPB;
 }
+
+static long long gu_nsb(long long N) { return (N + 31) / 32 * 2; }
+static size_t gu_rp_bytes(long long N, int ncb) { return (size_t)ncb * (size_t)gu_nsb(N) * GU_RREC; }
 
 bool gram_umma_supported(long long N, int GX, int GP, int G, int K, int Dp, int d0, int d1, bool has_p) {
   const int D = d0 + d1;
@@ -427,7 +593,16 @@ size_t gram_umma_workspace_bytes(long long N, int G, int K, int d0, int d1, int 
   if (!gram_umma_supported(N, 1, 1, G, K, Dp, d0, d1, true)) return 0;
   GuArgs g{};
   gu_plan(N, K, d0 + d1, gu_num_sms(), &g);   // same plan as the launch
-  return (size_t)g.splits * g.Kp * g.PP * sizeof(float) + 512;
+  return (size_t)g.splits * g.Kp * g.PP * sizeof(float) + 512 + GU_HDR_WORDS * sizeof(uint32_t) + gu_rp_bytes(N, g.ncb) + 256;
+}
+
+static bool gu_use_f16() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("VBMP_GRAM_PREC");
+    v = (e && (e[0] == 't' || e[0] == 'T')) ? 0 : 1;
+  }
+  return v == 1;
 }
 
 static int gu_fl() {
@@ -440,25 +615,19 @@ static int gu_fl() {
   return fl;
 }
 
-int launch_gram_umma(const GramArgs& a, float* gram, void* ws, size_t ws_bytes, cudaStream_t st) {
-  GuArgs g{};
-  g.d0 = a.d0; g.d1 = a.d1; g.N = a.N; g.K = a.K;
+template <bool F16>
+static int gu_launch_main(const GramArgs& a, GuArgs g, bool pair, cudaStream_t st) {
+  constexpr int SC = gu_sc(F16);
   const int D = a.d0 + a.d1;
-  gu_plan(a.N, a.K, D, gu_num_sms(), &g);
-  g.kcb = a.K < GU_CB ? a.K : GU_CB;
-  g.FL = gu_fl();
-  const size_t need = (size_t)g.splits * g.Kp * g.PP * sizeof(float) + 512;
-  if (ws_bytes < need) { set_error("gram_umma: workspace too small (%zu < %zu)", ws_bytes, need); return VBMP_ERR_WORKSPACE; }
-  g.part = (float*)(((size_t)ws + 255) / 256 * 256);
+  (void)D;
   CUtensorMap tmR, tmZ0, tmZ1;
-  int e = make_tmap_2d(&tmR, a.p, (uint64_t)a.K, (uint64_t)a.N, (uint64_t)a.K, (uint32_t)g.kcb, GU_SC);
-  if (!e) e = make_tmap_2d(&tmZ0, a.z0, (uint64_t)a.d0, (uint64_t)a.N, (uint64_t)a.d0, (uint32_t)a.d0, GU_SC);
-  if (!e && a.d1 > 0) e = make_tmap_2d(&tmZ1, a.z1, (uint64_t)a.d1, (uint64_t)a.N, (uint64_t)a.d1, (uint32_t)a.d1, GU_SC);
+  int e = make_tmap_2d(&tmR, a.p, (uint64_t)a.K, (uint64_t)a.N, (uint64_t)a.K, (uint32_t)g.kcb, SC);
+  if (!e) e = make_tmap_2d(&tmZ0, a.z0, (uint64_t)a.d0, (uint64_t)a.N, (uint64_t)a.d0, (uint32_t)a.d0, SC);
+  if (!e && a.d1 > 0) e = make_tmap_2d(&tmZ1, a.z1, (uint64_t)a.d1, (uint64_t)a.N, (uint64_t)a.d1, (uint32_t)a.d1, SC);
   if (a.d1 == 0) tmZ1 = tmZ0;
   if (e) { set_error("gram_umma: cuTensorMapEncodeTiled failed (%d)", e); return VBMP_ERR_CUDA; }
-  const bool pair = gu_pair_mode(a.K);
   const int NH = pair ? g.NPB / 2 : g.NPB;
-  const int rawB = (GU_SC * g.kcb * 4 + GU_SC * a.d0 * 4 + GU_SC * a.d1 * 4 + 127) / 128 * 128;
+  const int rawB = ((F16 ? 2 * GU_RREC : SC * g.kcb * 4) + SC * a.d0 * 4 + SC * a.d1 * 4 + 127) / 128 * 128;
   const size_t smem = (size_t)GU_NR * rawB + (size_t)gu_nstg(pair) * 2 * NH * 64 + sizeof(GuSmem) + 64;
   const int grid = g.splits * g.ncb * g.npb;
   const bool same = (a.d1 == 0 || a.d1 == a.d0);
@@ -477,10 +646,10 @@ int launch_gram_umma(const GramArgs& a, float* gram, void* ws, size_t ws_bytes, 
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   cudaError_t le = cudaSuccess;
-#define GU_LAUNCH(SF, R, P)                                                                                       \
-  do {                                                                                                            \
-    cudaFuncSetAttribute(gram_umma_kernel<SF, R, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
-    le = cudaLaunchKernelEx(&cfg, gram_umma_kernel<SF, R, P>, tmR, tmZ0, tmZ1, g);                                \
+#define GU_LAUNCH(SF, R, P)                                                                                            \
+  do {                                                                                                                 \
+    cudaFuncSetAttribute(gram_umma_kernel<SF, R, P, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
+    le = cudaLaunchKernelEx(&cfg, gram_umma_kernel<SF, R, P, F16>, tmR, tmZ0, tmZ1, g);                                \
   } while (0)
   if (pair) {                                               // K >= 256: the R box is always 128 wide
     if (sf == 64) GU_LAUNCH(64, true, true);
@@ -496,11 +665,53 @@ int launch_gram_umma(const GramArgs& a, float* gram, void* ws, size_t ws_bytes, 
   else GU_LAUNCH(0, false, false);
 #undef GU_LAUNCH
   if (le != cudaSuccess) { set_error("gram_umma launch: %s", cudaGetErrorString(le)); return VBMP_ERR_CUDA; }
-  int rc = check_launch("gram_umma");
+  return check_launch(F16 ? "gram_umma_f16" : "gram_umma");
+}
+
+int launch_gram_umma(const GramArgs& a, float* gram, void* ws, size_t ws_bytes, cudaStream_t st) {
+  GuArgs g{};
+  g.d0 = a.d0; g.d1 = a.d1; g.N = a.N; g.K = a.K;
+  const int D = a.d0 + a.d1;
+  gu_plan(a.N, a.K, D, gu_num_sms(), &g);
+  g.kcb = a.K < GU_CB ? a.K : GU_CB;
+  g.FL = gu_fl();
+  const size_t part_bytes = ((size_t)g.splits * g.Kp * g.PP * sizeof(float) + 255) / 256 * 256;
+  const size_t need = (size_t)g.splits * g.Kp * g.PP * sizeof(float) + 512 + GU_HDR_WORDS * sizeof(uint32_t) + gu_rp_bytes(a.N, g.ncb) + 256;
+  if (ws_bytes < need) { set_error("gram_umma: workspace too small (%zu < %zu)", ws_bytes, need); return VBMP_ERR_WORKSPACE; }
+  uint32_t* hdr = (uint32_t*)(((size_t)ws + 255) / 256 * 256);
+  g.part = (float*)(hdr + GU_HDR_WORDS);
+  const bool pair = gu_pair_mode(a.K);
+  const bool f16 = gu_use_f16();
+  int rc;
+  if (f16) {
+    // column maxima -> exact power-of-two feature scales; the fp16 kernel; the TF32 kernel as its conditional fallback
+    if (cudaMemsetAsync(hdr, 0, GU_HDR_WORDS * sizeof(uint32_t), st) != cudaSuccess) {
+      set_error("gram_umma: memset failed"); return VBMP_ERR_CUDA;
+    }
+    const int cg = gu_num_sms() * 4;
+    gram_colmax_kernel<<<cg, 256, 0, st>>>(a.z0, a.d0, a.N, 0, hdr);
+    if (a.d1 > 0) gram_colmax_kernel<<<cg, 256, 0, st>>>(a.z1, a.d1, a.N, a.d0, hdr);
+    rc = check_launch("gram_colmax");
+    if (rc) return rc;
+    g.hdr = hdr;
+    g.nsb = gu_nsb(a.N);
+    uint8_t* rp = (uint8_t*)g.part + part_bytes;
+    g.rp = rp;
+    gram_rsplit_kernel<<<gu_num_sms() * 8, 256, 0, st>>>(a.p, a.N, a.K, g.ncb, g.nsb, rp, hdr);
+    rc = check_launch("gram_rsplit");
+    if (rc) return rc;
+    GuArgs g16 = g;
+    g16.FL = g.FL >= 2 ? g.FL / 2 : 1;                       // same number of samples per first-level block
+    rc = gu_launch_main<true>(a, g16, pair, st);
+    if (rc) return rc;
+  } else {
+    g.hdr = nullptr;
+  }
+  rc = gu_launch_main<false>(a, g, pair, st);
   if (rc) return rc;
   const int D1 = D + 1;
   const long long tot = (long long)a.K * g.P;
-  gram_pair_reduce_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(g.part, g.splits, a.K, g.Kp, g.PP, D1, gram);
+  gram_pair_reduce_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(g.part, g.splits, a.K, g.Kp, g.PP, D1, g.hdr, gram);
   return check_launch("gram_pair_reduce");
 }
 
