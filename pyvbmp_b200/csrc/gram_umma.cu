@@ -700,8 +700,10 @@ int launch_gram_umma(const GramArgs& a, float* gram, void* ws, size_t ws_bytes, 
     gram_rsplit_kernel<<<gu_num_sms() * 8, 256, 0, st>>>(a.p, a.N, a.K, g.ncb, g.nsb, rp, hdr);
     rc = check_launch("gram_rsplit");
     if (rc) return rc;
+    // 16 chunks of 32 samples per first-level block: a kind::f16 MMA accumulates 16 samples per step (TF32: 8), so the
+    // truncation bias per block (-1.6e-6, tools/gram_bias.py) matches the TF32 variant's 256-sample blocks while the
+    // fold, during which the tensor pipe idles, comes half as often
     GuArgs g16 = g;
-    g16.FL = g.FL >= 2 ? g.FL / 2 : 1;                       // same number of samples per first-level block
     rc = gu_launch_main<true>(a, g16, pair, st);
     if (rc) return rc;
   } else {
