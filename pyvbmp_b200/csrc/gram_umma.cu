@@ -46,7 +46,10 @@ constexpr int GU_SC = 16;            // samples per chunk (2 K-steps): TF32; the
 __host__ __device__ constexpr int gu_sc(bool f16) { return f16 ? 32 : 16; }
 constexpr int GU_RSH = 14;           // fp16 variant: responsibilities are scaled by 2^14
 constexpr float GU_RMAX = 3.99f;     // ... and must stay below 65504 / 2^14
-constexpr int GU_NR = 4;             // raw ring depth
+#ifndef GU_NR_V
+#define GU_NR_V 6
+#endif
+constexpr int GU_NR = GU_NR_V;       // raw ring depth
 // pipeline depth (B stages in shared memory = A buffers in TMEM) and pair columns per MMA.  TMEM budget: D1 + D2 = 2 NPMAX
 // columns + NSTG A buffers of hi + lo = 32 NSTG columns <= 512.  A CTA pair needs 4 stages to hide the cross-CTA barrier
 // round trips (192 columns); a single CTA is best with 2 stages and 224 columns.
@@ -73,9 +76,16 @@ struct GuArgs {
   // the A operand of one K-step: lane = component, 16 bytes per chunk
   const uint8_t* rp;
   long long nsb;                     // 16-sample blocks per component block (N rounded up to 32, / 16)
+  // fp16 variant: zt = [z;1] scaled by 2^u_i and TRANSPOSED per 32-sample chunk by gram_zprep_kernel: record of zrec bytes
+  // = [feature 0..D-1 | constant 2^6 | zeros][GU_ZS floats], so a pair thread reads its two factors for 16 samples with
+  // eight 16-byte loads (row stride 36 floats: conflict free) instead of 32 scalar ones
+  const uint8_t* zt;
+  int zrec;
 };
 constexpr int GU_HDR_FLAG = 96, GU_HDR_WORDS = 128;
 constexpr int GU_RREC = 8192;
+constexpr int GU_ZS = 36;            // floats per feature row of a transposed 32-sample chunk (32 + 4 padding)
+__host__ __device__ constexpr int gu_zrec(int D) { return (D + 2) * GU_ZS * 4; }
 
 // exponent u_i of the exact feature scale 2^u_i (column maximum -> [2^6, 2^7)); 0 for an all-zero column
 __host__ __device__ inline int gu_feat_exp(uint32_t maxbits) {
@@ -91,7 +101,6 @@ struct GuSmem {
   uint64_t dfull, dempty;
   uint32_t tmem_base;
   float consts[2];                   // {1, 0}: the padded "1" feature and the zero used by padding pair columns
-  float fscale[65];                  // fp16 variant: 2^u_i per feature of zt
 };
 
 // Pair p of the symmetric (D+1) x (D+1) Gram matrix over zt = [z;1]:  p < D(D+1)/2 walks the upper triangle of the
@@ -138,7 +147,7 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant_
   const int D = a.d0 + a.d1;
   // carve: raw ring [NR][R 16 x kcb floats | Z0 16 x d0 | Z1 16 x d1], B stages [2][hi NPB*64 B | lo NPB*64 B]
   const int kcb = R128 ? 128 : a.kcb;
-  const int rawR = F16 ? 2 * GU_RREC : SC * kcb * 4, rawZ0 = SC * a.d0 * 4, rawZ1 = SC * a.d1 * 4;
+  const int rawR = F16 ? 2 * GU_RREC : SC * kcb * 4, rawZ0 = F16 ? a.zrec : SC * a.d0 * 4, rawZ1 = F16 ? 0 : SC * a.d1 * 4;
   const int rawB = (rawR + rawZ0 + rawZ1 + 127) / 128 * 128;
   constexpr int GU_NSTG = gu_nstg(PAIR), GU_NPMAX = gu_npmax(PAIR);
   const int NH = PAIR ? a.NPB / 2 : a.NPB;                 // pair columns generated (and held as B rows) by this CTA
@@ -168,7 +177,6 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant_
     S->consts[0] = 1.f; S->consts[1] = 0.f;
     fence_barrier_init();
   }
-  if (F16 && tid < 65) S->fscale[tid] = __uint_as_float((uint32_t)(127 + gu_feat_exp(tid == D ? 0x3f800000u : a.hdr[tid])) << 23);
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmR); tma_prefetch_desc(&tmZ0); if (a.d1 > 0) tma_prefetch_desc(&tmZ1); }
   if (warp == 1) { if (PAIR) tmem_alloc2<512>(&S->tmem_base); else tmem_alloc<512>(&S->tmem_base); }
   tc_fence_before();
@@ -188,10 +196,14 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant_
         const int r0 = (int)(nb + (long long)c * SC);
         uint8_t* dst = raw + (size_t)s * rawB;
         mbar_arrive_expect_tx(&S->rfull[s], bytes);
-        if (F16) bulk_g2s(dst, a.rp + ((size_t)cb * a.nsb + (size_t)(r0 >> 4)) * GU_RREC, 2 * GU_RREC, &S->rfull[s]);
-        else tma_load_2d(dst, &tmR, cb * GU_CB, r0, &S->rfull[s]);
-        tma_load_2d(dst + rawR, &tmZ0, 0, r0, &S->rfull[s]);
-        if (a.d1 > 0) tma_load_2d(dst + rawR + rawZ0, &tmZ1, 0, r0, &S->rfull[s]);
+        if (F16) {
+          bulk_g2s(dst, a.rp + ((size_t)cb * a.nsb + (size_t)(r0 >> 4)) * GU_RREC, 2 * GU_RREC, &S->rfull[s]);
+          bulk_g2s(dst + rawR, a.zt + (size_t)(r0 >> 5) * a.zrec, (uint32_t)a.zrec, &S->rfull[s]);
+        } else {
+          tma_load_2d(dst, &tmR, cb * GU_CB, r0, &S->rfull[s]);
+          tma_load_2d(dst + rawR, &tmZ0, 0, r0, &S->rfull[s]);
+          if (a.d1 > 0) tma_load_2d(dst + rawR + rawZ0, &tmZ1, 0, r0, &S->rfull[s]);
+        }
       }
       __syncwarp();
     }
@@ -262,7 +274,6 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant_
     const int pslot = split_ks ? wtid % NH : wtid;            // pair column (B row) generated by this thread
     const int ks0 = split_ks ? wtid / NH : 0, ksn = F16 ? (split_ks ? 1 : 2) : 1;
     const bool gen = split_ks ? wtid < 2 * NH : wtid < NH;
-    float pscale = 1.f;                                       // fp16: 2^(u_i + u_j)
     {
       const int pg_ = pb * NPB + (int)rank * NH + pslot;
       const bool pair_ok = gen && (pg_ < a.P);
@@ -277,9 +288,9 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant_
       setup(pi, bi, sli, sti);
       setup(pj, bj, slj, stj);
       plain = SF > 0 && __all_sync(0xffffffffu, pair_ok && pj < D);
-      if (F16) {
-        __syncwarp();
-        pscale = pair_ok ? S->fscale[pi] * S->fscale[pj] : 0.f;     // fscale was written before the CTA-wide sync above
+      if (F16) {       // transposed, pre-scaled chunk: row f of the record; padding pairs read the zero row D + 1
+        bi = raw + rawR + (pair_ok ? pi : D + 1) * (GU_ZS * 4); sli = rawB;
+        bj = raw + rawR + (pair_ok ? pj : D + 1) * (GU_ZS * 4); slj = rawB;
       }
     }
     const int fls = __ffs(FL) - 1;                       // FL is a power of two
@@ -322,34 +333,26 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant_
         if (gen) {
           const uint8_t* zi = bi + s * sli;
           const uint8_t* zj = bj + s * slj;
-          const float2 ps2 = make_float2(pscale, pscale);
           for (int kk = 0; kk < ksn; ++kk) {
             const int ks = ks0 + kk;
             uint8_t* bh = bst + (size_t)st * stageB + (size_t)ks * (2 * NH * 16) + (size_t)pslot * 16;
             uint8_t* bl = bh + NH * 64;
+            // the eight 16-byte loads first (the stores below may not be reordered above them)
+            float4 av[4], bv[4];
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+              av[v] = *reinterpret_cast<const float4*>(zi + ks * 64 + v * 16);
+              bv[v] = *reinterpret_cast<const float4*>(zj + ks * 64 + v * 16);
+            }
 #pragma unroll
             for (int qd = 0; qd < 2; ++qd) {                  // 8 samples = one 16-byte K-chunk of fp16
-              // the 16 loads first (the stores below may not be reordered above them), then multiply / split / store
-              float av[8], bv[8];
-              if (plain) {
-#pragma unroll
-                for (int sl = 0; sl < 8; ++sl) {
-                  av[sl] = *reinterpret_cast<const float*>(zi + (ks * 16 + qd * 8 + sl) * (SF * 4));
-                  bv[sl] = *reinterpret_cast<const float*>(zj + (ks * 16 + qd * 8 + sl) * (SF * 4));
-                }
-              } else {
-#pragma unroll
-                for (int sl = 0; sl < 8; ++sl) {
-                  av[sl] = *reinterpret_cast<const float*>(zi + (ks * 16 + qd * 8 + sl) * sti);
-                  bv[sl] = *reinterpret_cast<const float*>(zj + (ks * 16 + qd * 8 + sl) * stj);
-                }
-              }
               uint32_t hi[4], lo[4];
 #pragma unroll
               for (int u = 0; u < 4; ++u) {
-                const int sl = 2 * u;
-                // the fp32 product is rounded exactly as the reference's, then scaled by a power of two
-                const float2 x = __fmul2_rn(__fmul2_rn(make_float2(av[sl], av[sl + 1]), make_float2(bv[sl], bv[sl + 1])), ps2);
+                const float4 a4 = av[qd * 2 + (u >> 1)], b4 = bv[qd * 2 + (u >> 1)];
+                // factors carry exact power-of-two scales, so this is the reference's fp32 product times 2^(u_i + u_j)
+                const float2 x = (u & 1) ? __fmul2_rn(make_float2(a4.z, a4.w), make_float2(b4.z, b4.w))
+                                         : __fmul2_rn(make_float2(a4.x, a4.y), make_float2(b4.x, b4.y));
                 const __half2 ah = __floats2half2_rn(x.x, x.y);
                 const float2 af = __half22float2(ah);
                 const __half2 bh2 = __floats2half2_rn(x.x - af.x, x.y - af.y);
@@ -531,6 +534,41 @@ __global__ void __launch_bounds__(256) gram_rsplit_kernel(const float* __restric
   if (__any_sync(0xffffffffu, rmax > GU_RMAX) && (threadIdx.x & 31) == 0) atomicOr(&hdr[GU_HDR_FLAG], 1u);
 }
 
+// fp16 variant pre-pass: zt = [z0 | z1 | 1] scaled by the exact feature scales 2^u_i and transposed per 32-sample chunk
+// (see GuArgs::zt).  One block iteration per chunk: coalesced row reads into a shared tile, feature-major 16-byte writes.
+__global__ void __launch_bounds__(256) gram_zprep_kernel(const float* __restrict__ z0, int d0, const float* __restrict__ z1,
+                                                         int d1, long long N, const uint32_t* __restrict__ hdr,
+                                                         uint8_t* __restrict__ zt, int zrec) {
+  __shared__ float tile[32][65];
+  __shared__ float fs[64];
+  const int D = d0 + d1;
+  if (threadIdx.x < D) fs[threadIdx.x] = __uint_as_float((uint32_t)(127 + gu_feat_exp(hdr[threadIdx.x])) << 23);
+  __syncthreads();
+  const long long nch = (N + 31) / 32;
+  for (long long ch = blockIdx.x; ch < nch; ch += gridDim.x) {
+    for (int e = threadIdx.x; e < 32 * D; e += 256) {
+      const int sidx = e / D, f = e % D;
+      const long long n = ch * 32 + sidx;
+      float v = 0.f;
+      if (n < N) v = f < d0 ? __ldg(z0 + (size_t)n * d0 + f) : __ldg(z1 + (size_t)n * d1 + (f - d0));
+      tile[sidx][f] = v * fs[f];
+    }
+    __syncthreads();
+    float* rec = reinterpret_cast<float*>(zt + (size_t)ch * zrec);
+    for (int e = threadIdx.x; e < (D + 2) * 8; e += 256) {              // (feature row, group of 4 samples)
+      const int f = e >> 3, s4 = (e & 7) * 4;
+      float4 o;
+      if (f < D) o = make_float4(tile[s4][f], tile[s4 + 1][f], tile[s4 + 2][f], tile[s4 + 3][f]);
+      else if (f == D) {           // the constant feature: 1 * 2^6 on real rows, 0 on the zero-filled tail
+        const long long n = ch * 32 + s4;
+        o = make_float4(n < N ? 64.f : 0.f, n + 1 < N ? 64.f : 0.f, n + 2 < N ? 64.f : 0.f, n + 3 < N ? 64.f : 0.f);
+      } else o = make_float4(0.f, 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4*>(rec + f * GU_ZS + s4) = o;
+    }
+    __syncthreads();
+  }
+}
+
 // ---- host side -------------------------------------------------------------------------------------------
 static int gu_num_sms() {
   static int n = 0;
@@ -582,6 +620,7 @@ static void gu_plan(long long N, int K, int D, int sms, GuArgs* g) {
 
 static long long gu_nsb(long long N) { return (N + 31) / 32 * 2; }
 static size_t gu_rp_bytes(long long N, int ncb) { return (size_t)ncb * (size_t)gu_nsb(N) * GU_RREC; }
+static size_t gu_zt_bytes(long long N, int D) { return (size_t)((N + 31) / 32) * gu_zrec(D) + 256; }
 
 bool gram_umma_supported(long long N, int GX, int GP, int G, int K, int Dp, int d0, int d1, bool has_p) {
   const int D = d0 + d1;
@@ -593,7 +632,7 @@ size_t gram_umma_workspace_bytes(long long N, int G, int K, int d0, int d1, int 
   if (!gram_umma_supported(N, 1, 1, G, K, Dp, d0, d1, true)) return 0;
   GuArgs g{};
   gu_plan(N, K, d0 + d1, gu_num_sms(), &g);   // same plan as the launch
-  return (size_t)g.splits * g.Kp * g.PP * sizeof(float) + 512 + GU_HDR_WORDS * sizeof(uint32_t) + gu_rp_bytes(N, g.ncb) + 256;
+  return (size_t)g.splits * g.Kp * g.PP * sizeof(float) + 512 + GU_HDR_WORDS * sizeof(uint32_t) + gu_rp_bytes(N, g.ncb) + 256 + gu_zt_bytes(N, d0 + d1);
 }
 
 static bool gu_use_f16() {
@@ -627,7 +666,7 @@ static int gu_launch_main(const GramArgs& a, GuArgs g, bool pair, cudaStream_t s
   if (a.d1 == 0) tmZ1 = tmZ0;
   if (e) { set_error("gram_umma: cuTensorMapEncodeTiled failed (%d)", e); return VBMP_ERR_CUDA; }
   const int NH = pair ? g.NPB / 2 : g.NPB;
-  const int rawB = ((F16 ? 2 * GU_RREC : SC * g.kcb * 4) + SC * a.d0 * 4 + SC * a.d1 * 4 + 127) / 128 * 128;
+  const int rawB = (F16 ? 2 * GU_RREC + g.zrec : SC * g.kcb * 4 + SC * a.d0 * 4 + SC * a.d1 * 4) / 128 * 128 + 128;
   const size_t smem = (size_t)GU_NR * rawB + (size_t)gu_nstg(pair) * 2 * NH * 64 + sizeof(GuSmem) + 64;
   const int grid = g.splits * g.ncb * g.npb;
   const bool same = (a.d1 == 0 || a.d1 == a.d0);
@@ -676,7 +715,7 @@ int launch_gram_umma(const GramArgs& a, float* gram, void* ws, size_t ws_bytes, 
   g.kcb = a.K < GU_CB ? a.K : GU_CB;
   g.FL = gu_fl();
   const size_t part_bytes = ((size_t)g.splits * g.Kp * g.PP * sizeof(float) + 255) / 256 * 256;
-  const size_t need = (size_t)g.splits * g.Kp * g.PP * sizeof(float) + 512 + GU_HDR_WORDS * sizeof(uint32_t) + gu_rp_bytes(a.N, g.ncb) + 256;
+  const size_t need = (size_t)g.splits * g.Kp * g.PP * sizeof(float) + 512 + GU_HDR_WORDS * sizeof(uint32_t) + gu_rp_bytes(a.N, g.ncb) + 256 + gu_zt_bytes(a.N, D);
   if (ws_bytes < need) { set_error("gram_umma: workspace too small (%zu < %zu)", ws_bytes, need); return VBMP_ERR_WORKSPACE; }
   uint32_t* hdr = (uint32_t*)(((size_t)ws + 255) / 256 * 256);
   g.part = (float*)(hdr + GU_HDR_WORDS);
@@ -699,6 +738,12 @@ int launch_gram_umma(const GramArgs& a, float* gram, void* ws, size_t ws_bytes, 
     g.rp = rp;
     gram_rsplit_kernel<<<gu_num_sms() * 8, 256, 0, st>>>(a.p, a.N, a.K, g.ncb, g.nsb, rp, hdr);
     rc = check_launch("gram_rsplit");
+    if (rc) return rc;
+    uint8_t* zt = rp + (gu_rp_bytes(a.N, g.ncb) + 255) / 256 * 256;
+    g.zt = zt;
+    g.zrec = gu_zrec(D);
+    gram_zprep_kernel<<<gu_num_sms() * 8, 256, 0, st>>>(a.z0, a.d0, a.z1, a.d1, a.N, hdr, zt, g.zrec);
+    rc = check_launch("gram_zprep");
     if (rc) return rc;
     // 16 chunks of 32 samples per first-level block: a kind::f16 MMA accumulates 16 samples per step (TF32: 8), so the
     // truncation bias per block (-1.6e-6, tools/gram_bias.py) matches the TF32 variant's 256-sample blocks while the
