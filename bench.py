@@ -307,11 +307,12 @@ def main():
                 pass
             # The kernels issue 16-bit-operand MMAs (kind::f16, the bf16 rate), three split terms per algorithmic product:
             # the roofline denominator is the measured dense bf16 figure; `issued` counts the MMAs actually executed
-            # (Gram: 3 terms; E-step: 3 terms on the triangular 62.5 % of the columns + the TF32 "-m" step = 2.12x).
+            # per algorithmic flop (2 d^2 per sample*component): E-step 3 terms on the triangular 62.5 % of the columns +
+            # the TF32 "-m" step = 2.12x; Gram 3 terms on the 2304 padded symmetric pair columns of 4096 = 1.69x.
             bf16_sus = peaks.get("bf16_tflops_sustained")
             peak, peak_src = (bf16_sus, "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)") \
                 if bf16_sus else (1409.1, "fallback: B200_PROFILING.md sustained bf16 figure (MEASURED_PEAKS.json absent)")
-            issued = {"vbmp_estep": 2.12, "vbmp_gram": 3.0}
+            issued = {"vbmp_estep": 2.12, "vbmp_gram": 3.0 * (12 * 192) / (D * D) if D == 64 else 3.0 * ((D + 1) * (D + 2) / 2) / (D * D)}
             roof = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": peak, "unit": "TFLOP/s",
                     "frac": ach / peak, "traffic": traffic, "traffic_unit": "GB per launch (ncu dram__bytes_read+write, profiles/r01_traffic.json)",
                     "issued_per_algorithmic_flop": issued,

@@ -20,7 +20,7 @@ FORCE_SIMT = int(os.environ.get("VBMP_FORCE_SIMT", "0"))   # tests: 1 = CUDA-cor
 
 PROFILE = None     # bench.py sets this to {} to collect (start, end) CUDA events per C-ABI call
 LAUNCHES = 0       # kernels launched through the C ABI (bench.py's gpu_launches)
-_NKERNELS = {"vbmp_estep": 3, "vbmp_gram": 6}      # pack + E-step + reduce; column maxima + weight split + sample transpose + Gram (fp16) + Gram (TF32, returns at once unless flagged) + reduce
+_NKERNELS = {"vbmp_estep": 4, "vbmp_gram": 6}      # row scales + pack + E-step + reduce; column maxima + weight split + sample transpose + Gram (fp16) + Gram (TF32, returns at once unless flagged) + reduce
 
 
 class VbmpError(RuntimeError):

@@ -34,7 +34,10 @@
 //     instead of 41 KB, A 64 instead of 128 TMEM columns per half).  The -m fold stays a TF32 MMA whose A block holds
 //     2^sh_n per row and whose B block holds -m 2^t_k; the epilogue multiplies by 2^-(sh_n + t_k) (exact) before squaring,
 //     so nothing can overflow that would not overflow in the unscaled form.  Zero rows get sh = 0; sh and t are clamped to
-//     +-60.
+//     +-60.  Before that, feature i of z is multiplied by 2^e_i and row i of every W_k by 2^-e_i (e_i = exponent of the
+//     largest |W_k[i][.]| over all components, estep_rowscale_kernel): the product is unchanged, and features measured in
+//     very different units (tests: 10 decades apart) all land inside the fp16 window — W's rows carry 1/sigma_i, so this
+//     is a whitening by the narrowest component.
 #include <cstdlib>
 #include <type_traits>
 #include <cuda_fp16.h>
@@ -91,9 +94,29 @@ struct EuCfg {
 // ---- pack: W (C, DP, DP) fp32 row-major [i][j] -> per group [hi | lo | m | cst, 2^-t] record; B[n][k] = W_c[i = k][j]
 // with (c, j) = column n as above; K-step block ks holds rows n >= n0(ks) as [chunk (2)][row][16 bytes]: 4 TF32 or
 // 8 fp16 per chunk, i = KSTEP ks + (KSTEP / 2) chunk + e.
+// fp16 operands: fs[i] = 2^e_i (applied to feature i of the samples), fs[64 + i] = 2^-e_i (applied to row i of every W_k)
+template <int DP>
+__global__ void estep_rowscale_kernel(const float* __restrict__ W, int K, float* __restrict__ fs) {
+  __shared__ uint32_t mx;
+  const int i = blockIdx.x;
+  if (threadIdx.x == 0) mx = 0u;
+  __syncthreads();
+  uint32_t v = 0u;
+  for (int o = threadIdx.x; o < K * DP; o += blockDim.x)
+    v = max(v, __float_as_uint(fabsf(W[((size_t)(o / DP) * DP + i) * DP + o % DP])) & 0x7f800000u);
+  atomicMax(&mx, v);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int e = 0;
+    if (mx != 0u) { e = (int)(mx >> 23) - 127; e = e > 60 ? 60 : (e < -60 ? -60 : e); }
+    fs[i] = __uint_as_float((uint32_t)(127 + e) << 23);
+    fs[64 + i] = __uint_as_float((uint32_t)(127 - e) << 23);
+  }
+}
+
 template <int DP, bool F16>
 __global__ void estep_pack_kernel(const float* __restrict__ W, const float* __restrict__ m, const float* __restrict__ cst,
-                                  int K, uint8_t* __restrict__ Wp) {
+                                  int K, const float* __restrict__ fs, uint8_t* __restrict__ Wp) {
   using C = EuCfg<DP, F16>;
   const int g = blockIdx.x;
   __shared__ uint32_t wmax[8];
@@ -103,7 +126,9 @@ __global__ void estep_pack_kernel(const float* __restrict__ W, const float* __re
   if (F16) {
     for (int o = threadIdx.x; o < C::CG * DP * DP; o += blockDim.x) {
       const int c = g * C::CG + o / (DP * DP);
-      if (c < K) atomicMax(&wmax[o / (DP * DP)], __float_as_uint(fabsf(W[(size_t)c * DP * DP + o % (DP * DP)])) & 0x7f800000u);
+      if (c < K)
+        atomicMax(&wmax[o / (DP * DP)],
+                  __float_as_uint(fabsf(W[(size_t)c * DP * DP + o % (DP * DP)] * fs[64 + (o % (DP * DP)) / DP])) & 0x7f800000u);
     }
     __syncthreads();
   }
@@ -150,7 +175,7 @@ __global__ void estep_pack_kernel(const float* __restrict__ W, const float* __re
       const int r = (rem % (nn * 16)) / 16, e = (rem % 16) / 2;
       const int n = C::n0(ks) + r, cl = C::col_cl(n), j = C::col_j(n), i = 16 * ks + 8 * ch + e;
       const int c = g * C::CG + cl;
-      const float v = (c < K) ? W[((size_t)c * DP + i) * DP + j] * wsc[cl] : 0.f;
+      const float v = (c < K) ? W[((size_t)c * DP + i) * DP + j] * fs[64 + i] * wsc[cl] : 0.f;     // both factors: powers of 2
       const __half a = __float2half_rn(v);
       hi[o] = a;
       lo[o] = __float2half_rn(v - __half2float(a));
@@ -182,6 +207,7 @@ struct EuSmem {
   uint64_t turn[2];           // issue token between the two MMA warps
   uint64_t ndone[2], nfree[2];  // mode 1: tile's logits + logZ_n complete (workers -> normaliser) / lz buffer free again
   uint32_t tmem_base;
+  alignas(16) float fsc[64];  // fp16 operands: 2^e_i per feature
   double red[8];
 };
 
@@ -205,7 +231,8 @@ struct BufRing {
 
 template <int DP, int MODE, bool F16>
 __global__ void __launch_bounds__(EU_THREADS, 1)
-estep_umma_kernel(EstepArgs a, const uint8_t* __restrict__ Wp, int ntiles, int ngroups, int nstage) {
+estep_umma_kernel(EstepArgs a, const uint8_t* __restrict__ Wp, const float* __restrict__ fs, int ntiles, int ngroups,
+                  int nstage) {
   using C = EuCfg<DP, F16>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* stages = smem_raw;                                             // EU_NSTAGE * STAGE
@@ -225,6 +252,7 @@ estep_umma_kernel(EstepArgs a, const uint8_t* __restrict__ Wp, int ntiles, int n
     fence_barrier_init();
   }
   for (int o = tid; o < 2048; o += EU_THREADS) ones[o] = ((o & 1023) < 512 && (o & 3) < 2) ? 1.f : 0.f;
+  if (F16 && tid < 64) S->fsc[tid] = tid < DP ? fs[tid] : 1.f;
   fence_proxy_async();
   if (warp == 1) tmem_alloc<512>(&S->tmem_base);
   tc_fence_before();
@@ -340,6 +368,11 @@ estep_umma_kernel(EstepArgs a, const uint8_t* __restrict__ Wp, int ntiles, int n
 #pragma unroll
           for (int c0 = 0; c0 < DP; c0 += 16) {
             load16(c0, v + c0);
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              const float4 f4 = *reinterpret_cast<const float4*>(&S->fsc[c0 + j]);
+              v[c0 + j] *= f4.x; v[c0 + j + 1] *= f4.y; v[c0 + j + 2] *= f4.z; v[c0 + j + 3] *= f4.w;
+            }
 #pragma unroll
             for (int j = 0; j < 16; ++j) mxa = fmaxf(mxa, fabsf(v[c0 + j]));
           }
@@ -578,17 +611,22 @@ size_t estep_umma_workspace_bytes(long long N, int G, int K, int Dp, int mode) {
   if (!estep_umma_supported(N, 1, G, K, Dp, 1, 0)) return 0;
   const int ngroups = (K + eu_cg(Dp) - 1) / eu_cg(Dp);
   const size_t ctas = 512;   // upper bound on the persistent grid
-  return eu_align((size_t)ngroups * eu_group_bytes(Dp)) + eu_align(ctas * K * sizeof(float)) + eu_align(ctas * sizeof(double)) + 256;
+  return eu_align((size_t)ngroups * eu_group_bytes(Dp)) + 512 + eu_align(ctas * K * sizeof(float)) + eu_align(ctas * sizeof(double)) + 256;
 }
 
 int launch_estep_reduce(const float*, const double*, int nb, int G, int K, float* NA, float* logZ, cudaStream_t);
 
 template <int DP, bool F16>
-static int eu_launch(EstepArgs a, int mode, uint8_t* Wp, float* NA_part, double* logZ_part, float* NA, float* logZ,
+static int eu_launch(EstepArgs a, int mode, uint8_t* Wp, float* fs, float* NA_part, double* logZ_part, float* NA, float* logZ,
                      cudaStream_t st) {
   using C = EuCfg<DP, F16>;
   const int ngroups = (a.K + C::CG - 1) / C::CG;
-  estep_pack_kernel<DP, F16><<<ngroups, 256, 0, st>>>(a.W, a.m, a.cst, a.K, Wp);
+  if (F16) {
+    estep_rowscale_kernel<DP><<<DP, 256, 0, st>>>(a.W, a.K, fs);
+    int rc0 = check_launch("estep_rowscale");
+    if (rc0) return rc0;
+  }
+  estep_pack_kernel<DP, F16><<<ngroups, 256, 0, st>>>(a.W, a.m, a.cst, a.K, fs, Wp);
   int rc = check_launch("estep_pack");
   if (rc) return rc;
   const int ntiles = (int)((a.N + EU_TILE - 1) / EU_TILE);
@@ -602,10 +640,10 @@ static int eu_launch(EstepArgs a, int mode, uint8_t* Wp, float* NA_part, double*
   a.logZ_part = logZ_part;
   if (mode == 0) {
     cudaFuncSetAttribute(estep_umma_kernel<DP, 0, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    estep_umma_kernel<DP, 0, F16><<<grid, EU_THREADS, smem, st>>>(a, Wp, ntiles, ngroups, nstage);
+    estep_umma_kernel<DP, 0, F16><<<grid, EU_THREADS, smem, st>>>(a, Wp, fs, ntiles, ngroups, nstage);
   } else {
     cudaFuncSetAttribute(estep_umma_kernel<DP, 1, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    estep_umma_kernel<DP, 1, F16><<<grid, EU_THREADS, smem, st>>>(a, Wp, ntiles, ngroups, nstage);
+    estep_umma_kernel<DP, 1, F16><<<grid, EU_THREADS, smem, st>>>(a, Wp, fs, ntiles, ngroups, nstage);
   }
   rc = check_launch("estep_umma");
   if (rc) return rc;
@@ -620,20 +658,22 @@ int launch_estep_umma(const EstepArgs& a, int mode, void* ws, size_t ws_bytes, f
   char* p = (char*)eu_align((size_t)ws);
   uint8_t* Wp = (uint8_t*)p;
   p += eu_align((size_t)ngroups * eu_group_bytes(a.Dp));
+  float* fs = (float*)p;                                    // feature scales of the fp16 operands: [2^e_i | 2^-e_i]
+  p += 512;
   float* NA_part = (float*)p;
   p += eu_align((size_t)512 * a.K * sizeof(float));
   double* logZ_part = (double*)p;
   if (eu_use_f16()) {
     switch (a.Dp) {
-      case 64: return eu_launch<64, true>(a, mode, Wp, NA_part, logZ_part, NA, logZ, st);
-      case 32: return eu_launch<32, true>(a, mode, Wp, NA_part, logZ_part, NA, logZ, st);
-      case 16: return eu_launch<16, true>(a, mode, Wp, NA_part, logZ_part, NA, logZ, st);
+      case 64: return eu_launch<64, true>(a, mode, Wp, fs, NA_part, logZ_part, NA, logZ, st);
+      case 32: return eu_launch<32, true>(a, mode, Wp, fs, NA_part, logZ_part, NA, logZ, st);
+      case 16: return eu_launch<16, true>(a, mode, Wp, fs, NA_part, logZ_part, NA, logZ, st);
     }
   } else {
     switch (a.Dp) {
-      case 64: return eu_launch<64, false>(a, mode, Wp, NA_part, logZ_part, NA, logZ, st);
-      case 32: return eu_launch<32, false>(a, mode, Wp, NA_part, logZ_part, NA, logZ, st);
-      case 16: return eu_launch<16, false>(a, mode, Wp, NA_part, logZ_part, NA, logZ, st);
+      case 64: return eu_launch<64, false>(a, mode, Wp, fs, NA_part, logZ_part, NA, logZ, st);
+      case 32: return eu_launch<32, false>(a, mode, Wp, fs, NA_part, logZ_part, NA, logZ, st);
+      case 16: return eu_launch<16, false>(a, mode, Wp, fs, NA_part, logZ_part, NA, logZ, st);
     }
   }
   set_error("estep_umma: Dp=%d not supported", a.Dp);

@@ -539,29 +539,42 @@ __global__ void __launch_bounds__(256) gram_rsplit_kernel(const float* __restric
 __global__ void __launch_bounds__(256) gram_zprep_kernel(const float* __restrict__ z0, int d0, const float* __restrict__ z1,
                                                          int d1, long long N, const uint32_t* __restrict__ hdr,
                                                          uint8_t* __restrict__ zt, int zrec) {
-  __shared__ float tile[32][65];
+  __shared__ float tile[64][33];                 // [feature][sample], stride 33: both phases are bank-conflict free
   __shared__ float fs[64];
   const int D = d0 + d1;
   if (threadIdx.x < D) fs[threadIdx.x] = __uint_as_float((uint32_t)(127 + gu_feat_exp(hdr[threadIdx.x])) << 23);
   __syncthreads();
   const long long nch = (N + 31) / 32;
+  const int sidx = threadIdx.x >> 3, c0 = threadIdx.x & 7;       // 8 threads per sample row, float4 columns c0 and c0 + 8
+  const int q0 = d0 >> 2, q1 = d1 >> 2;
   for (long long ch = blockIdx.x; ch < nch; ch += gridDim.x) {
-    for (int e = threadIdx.x; e < 32 * D; e += 256) {
-      const int sidx = e / D, f = e % D;
-      const long long n = ch * 32 + sidx;
-      float v = 0.f;
-      if (n < N) v = f < d0 ? __ldg(z0 + (size_t)n * d0 + f) : __ldg(z1 + (size_t)n * d1 + (f - d0));
-      tile[sidx][f] = v * fs[f];
+    const long long n = ch * 32 + sidx;
+    const bool ok = n < N;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int c4 = c0 + 8 * h;
+      if (c4 < q0) {
+        const float4 v = ok ? __ldg(reinterpret_cast<const float4*>(z0 + (size_t)n * d0) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const int f = 4 * c4;
+        tile[f][sidx] = v.x * fs[f]; tile[f + 1][sidx] = v.y * fs[f + 1];
+        tile[f + 2][sidx] = v.z * fs[f + 2]; tile[f + 3][sidx] = v.w * fs[f + 3];
+      }
+      if (c4 < q1) {
+        const float4 v = ok ? __ldg(reinterpret_cast<const float4*>(z1 + (size_t)n * d1) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const int f = d0 + 4 * c4;
+        tile[f][sidx] = v.x * fs[f]; tile[f + 1][sidx] = v.y * fs[f + 1];
+        tile[f + 2][sidx] = v.z * fs[f + 2]; tile[f + 3][sidx] = v.w * fs[f + 3];
+      }
     }
     __syncthreads();
     float* rec = reinterpret_cast<float*>(zt + (size_t)ch * zrec);
     for (int e = threadIdx.x; e < (D + 2) * 8; e += 256) {              // (feature row, group of 4 samples)
       const int f = e >> 3, s4 = (e & 7) * 4;
       float4 o;
-      if (f < D) o = make_float4(tile[s4][f], tile[s4 + 1][f], tile[s4 + 2][f], tile[s4 + 3][f]);
+      if (f < D) o = make_float4(tile[f][s4], tile[f][s4 + 1], tile[f][s4 + 2], tile[f][s4 + 3]);
       else if (f == D) {           // the constant feature: 1 * 2^6 on real rows, 0 on the zero-filled tail
-        const long long n = ch * 32 + s4;
-        o = make_float4(n < N ? 64.f : 0.f, n + 1 < N ? 64.f : 0.f, n + 2 < N ? 64.f : 0.f, n + 3 < N ? 64.f : 0.f);
+        const long long m = ch * 32 + s4;
+        o = make_float4(m < N ? 64.f : 0.f, m + 1 < N ? 64.f : 0.f, m + 2 < N ? 64.f : 0.f, m + 3 < N ? 64.f : 0.f);
       } else o = make_float4(0.f, 0.f, 0.f, 0.f);
       *reinterpret_cast<float4*>(rec + f * GU_ZS + s4) = o;
     }

@@ -10,7 +10,8 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
-def _problem(N, d0, d1, K, seed=0, spread=1.0):
+def _problem(N, d0, d1, K, seed=0, spread=1.0, fscale=None):
+    """fscale: per-feature units (D,) applied to the data and, consistently, to the component parameters."""
     dev = torch.device(DEV)
     g = torch.Generator(device=dev).manual_seed(seed)
     D = d0 + d1
@@ -19,6 +20,11 @@ def _problem(N, d0, d1, K, seed=0, spread=1.0):
     z = mu[torch.randint(K, (N,), generator=g, device=dev)] + torch.randn(N, D, generator=g, device=dev)
     A = torch.randn(K, D, D, generator=g, device=dev) / D ** 0.5
     invU = A @ A.transpose(-1, -2) + 0.5 * torch.eye(D, device=dev)
+    if fscale is not None:
+        fscale = fscale.to(dev)
+        mu = mu * fscale
+        z = z * fscale
+        invU = invU * fscale[:, None] * fscale[None, :]
     nu = D + 2 + 10 * torch.rand(K, generator=g, device=dev)
     lam = 1 + torch.rand(K, generator=g, device=dev)
     lp = torch.log_softmax(torch.randn(K, generator=g, device=dev), 0)
@@ -95,6 +101,57 @@ def test_gram_kernels(N, d0, d1, K, simt):
     keep = Gref[:, D, D] > 10.0                                            # components that own some mass
     err = (scat(G) - s_ref).flatten(1).norm(dim=1) / s_ref.flatten(1).norm(dim=1).clamp_min(1e-30)
     assert float(err[keep].max()) <= 1e-4
+
+
+def _units(D, decades, seed=7):
+    g = torch.Generator().manual_seed(seed)
+    return 10.0 ** ((torch.rand(D, generator=g) * 2 - 1) * decades)
+
+
+@pytest.mark.parametrize("decades", [1.0, 3.0, 5.0])
+def test_estep_features_in_different_units(decades):
+    """Features whose units differ by up to 10^(2 decades): the split-precision operands are rescaled per feature (from the
+    whitening factors), per sample row and per component, so the logits keep fp32 accuracy."""
+    N, d0, K = 6000, 64, 64
+    z, z0, z1, W, m, cst, Dp, L = _problem(N, d0, 0, K, seed=3, fscale=_units(d0, decades))
+    xg = torch.zeros(1, dtype=torch.int32, device=DEV)
+    lz = torch.logsumexp(L, -1)
+    P = (L - lz[:, None]).exp()
+    lg = _lib.estep(z0, z1, N, 1, xg, W, m, cst, 1, K, Dp, 0).view(N, K)
+    p, lzn, NA, lZ = _lib.estep(z0, z1, N, 1, xg, W, m, cst, 1, K, Dp, 1)
+    scale = float(L.abs().max())
+    assert float((lg.double() - L).abs().max()) <= 2e-6 * scale
+    assert float((lzn.view(N).double() - lz).abs().max()) <= 2e-6 * scale
+    assert float((p.view(N, K).double() - P).abs().max()) <= 2e-3
+
+
+@pytest.mark.parametrize("decades", [1.0, 3.0, 5.0])
+def test_gram_features_in_different_units(decades):
+    N, d0, K = 6000, 64, 64
+    u = _units(d0, decades)
+    z, z0, z1, W, m, cst, Dp, L = _problem(N, d0, 0, K, seed=4, fscale=u)
+    xg = torch.zeros(1, dtype=torch.int32, device=DEV)
+    Pf = (L - torch.logsumexp(L, -1)[:, None]).exp().float().contiguous()
+    zt = torch.cat([z.double(), torch.ones(N, 1, device=DEV, dtype=torch.float64)], 1)
+    Gref = torch.einsum("nk,ni,nj->kij", Pf.double(), zt, zt)
+    G = _lib.gram(z0, z1, N, 1, xg, Pf.view(N, 1, K), 1, xg, 1, K, Dp).view(K, d0 + 1, d0 + 1)
+    s = torch.cat([u.double(), torch.ones(1, dtype=torch.float64)]).to(DEV)
+    En = (G.double() - Gref) / (s[:, None] * s[None, :])              # every entry in its own units
+    Rn = Gref / (s[:, None] * s[None, :])
+    assert float(En.abs().max() / Rn.abs().max()) <= 1e-5
+
+
+def test_gram_weights_beyond_fp16_range_use_the_tf32_path():
+    """Weights above the fp16 window (responsibilities never are) must not lose accuracy: the device-side flag routes the
+    call to the TF32 kernel."""
+    N, d0, K = 5000, 64, 64
+    z, z0, z1, W, m, cst, Dp, L = _problem(N, d0, 0, K, seed=5)
+    xg = torch.zeros(1, dtype=torch.int32, device=DEV)
+    Pf = (37.5 * (L - torch.logsumexp(L, -1)[:, None]).exp()).float().contiguous()
+    zt = torch.cat([z.double(), torch.ones(N, 1, device=DEV, dtype=torch.float64)], 1)
+    Gref = torch.einsum("nk,ni,nj->kij", Pf.double(), zt, zt)
+    G = _lib.gram(z0, z1, N, 1, xg, Pf.view(N, 1, K), 1, xg, 1, K, Dp).view(K, d0 + 1, d0 + 1)
+    assert float((G.double() - Gref).abs().max() / Gref.abs().max()) <= 1e-5
 
 
 def test_gram_is_deterministic_run_to_run():
