@@ -610,13 +610,16 @@ static void gu_plan(long long N, int K, int D, int sms, GuArgs* g) {
   if (g->NPB < 16) g->NPB = 16;
   g->ncb = (K + GU_CB - 1) / GU_CB;
   const int tasks = g->npb * g->ncb;
-  // sample splits: a multiple of the number of task groups that fit the SMs at once, with at most ~128 Ki rows per CTA.
-  // The pair-block CTAs of one (split, component block) stream the same R rows and are launched back to back, so
-  // their re-reads hit L2 as long as they do not drift apart; short tasks bound the drift (ncu: 21 GB of DRAM reads
-  // per cfg2 launch with 600 Ki-row tasks, 5.6 GB with 120 Ki-row tasks).
-  // rounds of `sms` co-resident CTAs needed at <= 128 Ki rows per CTA; then as many splits as fill those rounds exactly
-  // (cfg2: 20 tasks, 5 rounds of 148 -> 37 splits = 740 CTAs), so the last round is not a partial one
-  long long rounds = ((long long)N * tasks + (long long)sms * 131072 - 1) / ((long long)sms * 131072);
+  // sample splits: a multiple of the number of task groups that fit the SMs at once, with at most `cap` rows per CTA.
+  // The pair-block CTAs of one (split, component block) stream the same weight rows and are launched back to back, so
+  // their re-reads hit L2 as long as they do not drift apart; short tasks bound the drift.  ncu, cfg2, fp16 variant:
+  // 13.4 GB of DRAM reads per launch with 128 Ki-row tasks, 8.0 GB at 64 Ki, 6.6 GB at 32 Ki (5.5 GB is one pass over
+  // the packed weights and samples), 5.8 GB at 16 Ki where the per-task prologue starts to cost time; 32 Ki is also
+  // the fastest.  rounds of `sms` co-resident CTAs needed at <= cap rows per CTA; then as many splits as fill those
+  // rounds exactly (cfg2: 24 tasks, 21 rounds of 148 -> 129 splits), so the last round is not a partial one.
+  // VBMP_GRAM_ROWS overrides the cap (tuning).
+  static const long long cap = [] { const char* e = getenv("VBMP_GRAM_ROWS"); long long v = e ? atoll(e) : 0; return v >= 2048 ? v : 131072; }();
+  long long rounds = ((long long)N * tasks + (long long)sms * cap - 1) / ((long long)sms * cap);
   if (rounds < 1) rounds = 1;
   long long sp = rounds * sms / tasks;
   const long long maxsp = (N + 2047) / 2048;
