@@ -61,6 +61,22 @@ int vbmp_gram(const float* z0, int d0, const float* z1, int d1, long long N, int
               const float* p, int GP, const int* pg, int G, int K, int Dp, int flags,
               float* gram, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- K2 -> K3 hand-over (optional) ---------------------------------------------------------------------
+ * Mixture.update runs update_assignments (K2 mode 1) and then raw_update (K3) on the SAME responsibilities
+ * (dists/Mixture.py:38-45 -> :47-53).  vbmp_estep_rpack is vbmp_estep that, where the tcgen05 fp16 kernels apply
+ * (mode 1, K <= 256), ALSO writes the responsibilities pre-split into the fp16 operand images K3 consumes
+ * (vbmp_rpack_bytes(N, K) bytes, caller-owned), saving K3's own pass over p; *packed reports whether it did.
+ * vbmp_gram_rpack is vbmp_gram given that buffer (it must hold the images of exactly the p passed; NULL = vbmp_gram). */
+size_t vbmp_rpack_bytes(long long N, int K);
+int vbmp_estep_rpack(const float* z0, int d0, const float* z1, int d1, long long N, int GX, const int* xg,
+                     const float* W, const float* m, const float* cst, int G, int K, int Dp, int mode, int flags,
+                     float* out, float* logZn, float* NA, float* logZ,
+                     void* workspace, size_t workspace_bytes, void* stream,
+                     void* rpack, size_t rpack_bytes, int* packed);
+int vbmp_gram_rpack(const float* z0, int d0, const float* z1, int d1, long long N, int GX, const int* xg,
+                    const float* p, int GP, const int* pg, int G, int K, int Dp, int flags,
+                    float* gram, void* workspace, size_t workspace_bytes, void* stream, const void* rpack);
+
 /* ---- K5: natural-parameter updates (replicated; statistics are post-beta) -----------------------------
  * Wishart.ss_update — dists/Wishart.py:43-56.                                                          */
 int vbmp_wishart_update(const float* SExx, const float* N, const float* invU_0, const float* nu_0,

@@ -20,7 +20,7 @@ FORCE_SIMT = int(os.environ.get("VBMP_FORCE_SIMT", "0"))   # tests: 1 = CUDA-cor
 
 PROFILE = None     # bench.py sets this to {} to collect (start, end) CUDA events per C-ABI call
 LAUNCHES = 0       # kernels launched through the C ABI (bench.py's gpu_launches)
-_NKERNELS = {"vbmp_estep": 4, "vbmp_gram": 6}      # row scales + pack + E-step + reduce; column maxima + weight split + sample transpose + Gram (fp16) + Gram (TF32, returns at once unless flagged) + reduce
+_NKERNELS = {"vbmp_estep": 4, "vbmp_estep_rpack": 4, "vbmp_gram": 6, "vbmp_gram_rpack": 5}      # row scales + pack + E-step + reduce; column maxima + weight split + sample transpose + Gram (fp16) + Gram (TF32, returns at once unless flagged) + reduce
 
 
 class VbmpError(RuntimeError):
@@ -40,6 +40,8 @@ def lib():
         L.vbmp_version.restype = c_int
         L.vbmp_estep_workspace_bytes.restype = c_size_t
         L.vbmp_estep_workspace_bytes.argtypes = [c_longlong, c_int, c_int, c_int, c_int]
+        L.vbmp_rpack_bytes.restype = c_size_t
+        L.vbmp_rpack_bytes.argtypes = [c_longlong, c_int]
         L.vbmp_gram_workspace_bytes.restype = c_size_t
         L.vbmp_gram_workspace_bytes.argtypes = [c_longlong, c_int, c_int, c_int, c_int, c_int]
         _lib = L
@@ -50,7 +52,7 @@ EXPORTS = (
     "vbmp_version", "vbmp_last_error", "vbmp_niw_prep", "vbmp_mnw_prep", "vbmp_estep_workspace_bytes",
     "vbmp_estep", "vbmp_gram_workspace_bytes", "vbmp_gram", "vbmp_wishart_update", "vbmp_niw_update",
     "vbmp_mnw_update", "vbmp_wishart_elogdet", "vbmp_wishart_kl", "vbmp_niw_kl", "vbmp_mnw_kl",
-    "vbmp_hmm_forward_backward",
+    "vbmp_hmm_forward_backward", "vbmp_rpack_bytes", "vbmp_estep_rpack", "vbmp_gram_rpack",
 )
 
 
@@ -68,7 +70,7 @@ def _call(name, *args):
         a.record()
         rc = fn(*args)
         b.record()
-        PROFILE.setdefault(name, []).append((a, b))
+        PROFILE.setdefault(name.replace("_rpack", ""), []).append((a, b))     # the hand-over variants time as K2 / K3
     else:
         rc = fn(*args)
     LAUNCHES += _NKERNELS.get(name, 1)
@@ -150,6 +152,22 @@ def mnw_prep(invU, nu, mu, invV, logprior, C, n, pp, pad, Dp):
     return W, m, cst, info
 
 
+# K2 -> K3 hand-over: the most recent mode-1 E-step on a stream may have left the responsibilities pre-split for the Gram
+# kernel (vbmp_estep_rpack).  The record ties that buffer to the exact responsibilities tensor: same storage, offset, size and
+# torch version counter (any in-place edit bumps it), so gram() only uses the images for the untouched p they were made of.
+RPACK = int(os.environ.get("VBMP_RPACK", "1"))
+_rpack_cache = {}     # stream key -> buffer
+_rpack_rec = {}       # stream key -> (storage ptr, storage offset, numel, version, N, K)
+
+
+def _rpack_key(dev):
+    return (dev.type, dev.index, torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _rpack_sig(t):
+    return (t.untyped_storage().data_ptr(), t.storage_offset(), t.numel(), t._version)
+
+
 def estep(z0, z1, N, GX, xg, W, m, cst, G, K, Dp, mode, out=None, logZn=None):
     """z0: (N,GX,d0), z1: (N,GX,d1) or None.  Returns logits (mode 0) or (p, logZn, NA, logZ) (mode 1)."""
     dev = z0.device
@@ -165,6 +183,22 @@ def estep(z0, z1, N, GX, xg, W, m, cst, G, K, Dp, mode, out=None, logZn=None):
         logZ = torch.empty((G,), dtype=torch.float32, device=dev)
     nbytes = lib().vbmp_estep_workspace_bytes(c_longlong(N), c_int(G), c_int(K), c_int(Dp), c_int(mode))
     ws = _workspace(nbytes, dev)
+    key = _rpack_key(dev)
+    _rpack_rec.pop(key, None)                    # whatever was packed before is about to be overwritten
+    if mode == 1 and RPACK and G == 1 and GX == 1 and K <= 256 and not FORCE_SIMT:
+        rb = int(lib().vbmp_rpack_bytes(c_longlong(N), c_int(K)))
+        buf = _rpack_cache.get(key)
+        if buf is None or buf.numel() < rb:
+            buf = torch.empty(max(rb, 1), dtype=torch.uint8, device=dev)
+            _rpack_cache[key] = buf
+        packed = c_int(0)
+        _call("vbmp_estep_rpack", _ptr(z0), c_int(d0), _ptr(z1), c_int(d1), c_longlong(N), c_int(GX), _ptr(xg),
+              _ptr(W), _ptr(m), _ptr(cst), c_int(G), c_int(K), c_int(Dp), c_int(mode), c_int(0), _ptr(out), _ptr(logZn),
+              _ptr(NA), _ptr(logZ), _ptr(ws), c_size_t(ws.numel()), _stream(dev), _ptr(buf), c_size_t(buf.numel()),
+              ctypes.byref(packed))
+        if packed.value:
+            _rpack_rec[key] = _rpack_sig(out) + (N, K)
+        return out, logZn, NA, logZ
     _call("vbmp_estep", _ptr(z0), c_int(d0), _ptr(z1), c_int(d1), c_longlong(N), c_int(GX), _ptr(xg),
                             _ptr(W), _ptr(m), _ptr(cst), c_int(G), c_int(K), c_int(Dp), c_int(mode),
                             c_int(1 if FORCE_SIMT in (1, 2) else 0), _ptr(out), _ptr(logZn), _ptr(NA), _ptr(logZ),
@@ -183,6 +217,13 @@ def gram(z0, z1, N, GX, xg, p, GP, pg, G, K, Dp):
     out = torch.empty((G, K, D1, D1), dtype=torch.float32, device=dev)
     nbytes = lib().vbmp_gram_workspace_bytes(c_longlong(N), c_int(G), c_int(K), c_int(d0), c_int(d1), c_int(Dp))
     ws = _workspace(nbytes, dev)
+    key = _rpack_key(dev)
+    rec = _rpack_rec.get(key)
+    if rec is not None and p is not None and not FORCE_SIMT and GP == 1 and rec == _rpack_sig(p) + (N, K):
+        _call("vbmp_gram_rpack", _ptr(z0), c_int(d0), _ptr(z1), c_int(d1), c_longlong(N), c_int(GX), _ptr(xg),
+              _ptr(p), c_int(GP), _ptr(pg), c_int(G), c_int(K), c_int(Dp), c_int(0), _ptr(out), _ptr(ws),
+              c_size_t(ws.numel()), _stream(dev), _ptr(_rpack_cache[key]))
+        return out
     _call("vbmp_gram", _ptr(z0), c_int(d0), _ptr(z1), c_int(d1), c_longlong(N), c_int(GX), _ptr(xg),
                            _ptr(p), c_int(GP), _ptr(pg), c_int(G), c_int(K), c_int(Dp),
                            c_int(1 if FORCE_SIMT in (1, 3) else 0), _ptr(out), _ptr(ws), c_size_t(ws.numel()),

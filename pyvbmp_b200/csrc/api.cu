@@ -49,6 +49,8 @@ int launch_estep_umma(const EstepArgs&, int mode, void* ws, size_t ws_bytes, flo
 bool gram_umma_supported(long long N, int GX, int GP, int G, int K, int Dp, int d0, int d1, bool has_p);
 size_t gram_umma_workspace_bytes(long long N, int G, int K, int d0, int d1, int Dp);
 int launch_gram_umma(const GramArgs&, float* gram, void* ws, size_t ws_bytes, cudaStream_t);
+bool estep_umma_can_pack(long long N, int GX, int G, int K, int Dp, int d0, int d1, int mode);
+size_t gram_rpack_bytes(long long N, int K);
 
 static bool valid_dp(int Dp) { return Dp == 8 || Dp == 16 || Dp == 32 || Dp == 64 || Dp == 128; }
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -85,11 +87,12 @@ size_t vbmp_estep_workspace_bytes(long long N, int G, int K, int Dp, int mode) {
   return (simt > umma ? simt : umma) + 256;
 }
 
-int vbmp_estep(const float* z0, int d0, const float* z1, int d1, long long N, int GX, const int* xg,
-               const float* W, const float* m, const float* cst, int G, int K, int Dp, int mode, int flags,
-               float* out, float* logZn, float* NA, float* logZ,
-               void* workspace, size_t workspace_bytes, void* stream) {
+static int estep_impl(const float* z0, int d0, const float* z1, int d1, long long N, int GX, const int* xg,
+                      const float* W, const float* m, const float* cst, int G, int K, int Dp, int mode, int flags,
+                      float* out, float* logZn, float* NA, float* logZ,
+                      void* workspace, size_t workspace_bytes, void* stream, void* rpack, size_t rpack_bytes, int* packed) {
   cudaStream_t st = (cudaStream_t)stream;
+  if (packed) *packed = 0;
   if (!valid_dp(Dp) || d0 < 1 || d1 < 0 || d0 + d1 > Dp || G < 1 || K < 1 || GX < 1 || N < 0 || (mode != 0 && mode != 1)) {
     set_error("estep: bad shape N=%lld GX=%d G=%d K=%d d0=%d d1=%d Dp=%d mode=%d", N, GX, G, K, d0, d1, Dp, mode);
     return VBMP_ERR_SHAPE;
@@ -105,8 +108,17 @@ int vbmp_estep(const float* z0, int d0, const float* z1, int d1, long long N, in
     return VBMP_ERR_WORKSPACE;
   }
   EstepArgs a{z0, z1, d0, d1, N, GX, xg, W, m, cst, G, K, Dp, out, logZn, nullptr, nullptr};
-  if (!(flags & 1) && estep_umma_supported(N, GX, G, K, Dp, d0, d1))
+  if (!(flags & 1) && estep_umma_supported(N, GX, G, K, Dp, d0, d1)) {
+    if (rpack && packed && estep_umma_can_pack(N, GX, G, K, Dp, d0, d1, mode)) {
+      if (rpack_bytes < gram_rpack_bytes(N, K)) {
+        set_error("estep_rpack: buffer too small (%zu < %zu)", rpack_bytes, gram_rpack_bytes(N, K));
+        return VBMP_ERR_WORKSPACE;
+      }
+      a.rpack = (unsigned char*)rpack;
+      *packed = 1;
+    }
     return launch_estep_umma(a, mode, workspace, workspace_bytes, NA, logZ, st);
+  }
   int nb = cdiv(N, estep_simt_tile(Dp));
   if (mode == 1) {
     char* ws = (char*)align_up((size_t)workspace, 256);
@@ -119,6 +131,25 @@ int vbmp_estep(const float* z0, int d0, const float* z1, int d1, long long N, in
   return rc;
 }
 
+int vbmp_estep(const float* z0, int d0, const float* z1, int d1, long long N, int GX, const int* xg,
+               const float* W, const float* m, const float* cst, int G, int K, int Dp, int mode, int flags,
+               float* out, float* logZn, float* NA, float* logZ,
+               void* workspace, size_t workspace_bytes, void* stream) {
+  return estep_impl(z0, d0, z1, d1, N, GX, xg, W, m, cst, G, K, Dp, mode, flags, out, logZn, NA, logZ, workspace,
+                    workspace_bytes, stream, nullptr, 0, nullptr);
+}
+
+size_t vbmp_rpack_bytes(long long N, int K) { return (N < 0 || K < 1) ? 0 : gram_rpack_bytes(N, K); }
+
+int vbmp_estep_rpack(const float* z0, int d0, const float* z1, int d1, long long N, int GX, const int* xg,
+                     const float* W, const float* m, const float* cst, int G, int K, int Dp, int mode, int flags,
+                     float* out, float* logZn, float* NA, float* logZ,
+                     void* workspace, size_t workspace_bytes, void* stream, void* rpack, size_t rpack_bytes, int* packed) {
+  if (!packed) { set_error("estep_rpack: packed is NULL"); return VBMP_ERR_SHAPE; }
+  return estep_impl(z0, d0, z1, d1, N, GX, xg, W, m, cst, G, K, Dp, mode, flags, out, logZn, NA, logZ, workspace,
+                    workspace_bytes, stream, rpack, rpack_bytes, packed);
+}
+
 size_t vbmp_gram_workspace_bytes(long long N, int G, int K, int d0, int d1, int Dp) {
   if (!valid_dp(Dp) || N < 0) return 0;
   long long S_per; int splits;
@@ -129,9 +160,9 @@ size_t vbmp_gram_workspace_bytes(long long N, int G, int K, int d0, int d1, int 
   return (simt > umma ? simt : umma) + 256;
 }
 
-int vbmp_gram(const float* z0, int d0, const float* z1, int d1, long long N, int GX, const int* xg,
-              const float* p, int GP, const int* pg, int G, int K, int Dp, int flags,
-              float* gram, void* workspace, size_t workspace_bytes, void* stream) {
+static int gram_impl(const float* z0, int d0, const float* z1, int d1, long long N, int GX, const int* xg,
+                     const float* p, int GP, const int* pg, int G, int K, int Dp, int flags,
+                     float* gram, void* workspace, size_t workspace_bytes, void* stream, const void* rpack) {
   cudaStream_t st = (cudaStream_t)stream;
   if (!valid_dp(Dp) || d0 < 1 || d1 < 0 || d0 + d1 > Dp || G < 1 || K < 1 || GX < 1 || GP < 1 || N < 0) {
     set_error("gram: bad shape N=%lld GX=%d GP=%d G=%d K=%d d0=%d d1=%d Dp=%d", N, GX, GP, G, K, d0, d1, Dp);
@@ -145,6 +176,7 @@ int vbmp_gram(const float* z0, int d0, const float* z1, int d1, long long N, int
     return VBMP_ERR_WORKSPACE;
   }
   GramArgs a{z0, z1, d0, d1, N, GX, xg, p, GP, pg, G, K, Dp, 0, 0, nullptr};
+  a.rpack = (const unsigned char*)rpack;
   if (!(flags & 1) && gram_umma_supported(N, GX, GP, G, K, Dp, d0, d1, p != nullptr))
     return launch_gram_umma(a, gram, workspace, workspace_bytes, st);
   gram_simt_plan(N, G, K, Dp, &a.S_per, &a.splits);
@@ -152,6 +184,18 @@ int vbmp_gram(const float* z0, int d0, const float* z1, int d1, long long N, int
   int rc = launch_gram_simt(a, st);
   if (rc) return rc;
   return launch_gram_reduce(a.part, a.splits, per, gram, st);
+}
+
+int vbmp_gram(const float* z0, int d0, const float* z1, int d1, long long N, int GX, const int* xg,
+              const float* p, int GP, const int* pg, int G, int K, int Dp, int flags,
+              float* gram, void* workspace, size_t workspace_bytes, void* stream) {
+  return gram_impl(z0, d0, z1, d1, N, GX, xg, p, GP, pg, G, K, Dp, flags, gram, workspace, workspace_bytes, stream, nullptr);
+}
+
+int vbmp_gram_rpack(const float* z0, int d0, const float* z1, int d1, long long N, int GX, const int* xg,
+                    const float* p, int GP, const int* pg, int G, int K, int Dp, int flags,
+                    float* gram, void* workspace, size_t workspace_bytes, void* stream, const void* rpack) {
+  return gram_impl(z0, d0, z1, d1, N, GX, xg, p, GP, pg, G, K, Dp, flags, gram, workspace, workspace_bytes, stream, rpack);
 }
 
 int vbmp_wishart_update(const float* SExx, const float* N, const float* invU_0, const float* nu_0,

@@ -20,6 +20,7 @@ struct EstepArgs {
   const float* W; const float* m; const float* cst;  // (G,K,Dp,Dp), (G,K,Dp), (G,K)
   int G, K, Dp;
   float* out; float* logZn; float* NA_part; double* logZ_part;
+  unsigned char* rpack = nullptr;                    // mode 1, tcgen05 fp16 path: also emit K3's pre-split weight images
 };
 struct GramArgs {
   const float* z0; const float* z1; int d0, d1;
@@ -28,6 +29,7 @@ struct GramArgs {
   int G, K, Dp;
   long long S_per; int splits;
   float* part;                                        // [splits][G][K][(D+1)^2]
+  const unsigned char* rpack = nullptr;               // pre-split weight images written by K2 (vbmp_estep_rpack)
 };
 
 void set_error(const char* fmt, ...);

@@ -232,7 +232,7 @@ struct BufRing {
 template <int DP, int MODE, bool F16>
 __global__ void __launch_bounds__(EU_THREADS, 1)
 estep_umma_kernel(EstepArgs a, const uint8_t* __restrict__ Wp, const float* __restrict__ fs, int ntiles, int ngroups,
-                  int nstage) {
+                  int nstage, long long nsb) {
   using C = EuCfg<DP, F16>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* stages = smem_raw;                                             // EU_NSTAGE * STAGE
@@ -504,11 +504,16 @@ estep_umma_kernel(EstepArgs a, const uint8_t* __restrict__ Wp, const float* __re
     __syncwarp();
     // 16 float4 loads in flight per lane: RB rows of NUA float4 columns each (NUA = columns this K needs)
     auto ex2 = [](float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; };
+    // a.rpack != nullptr (host: K <= 256): also emit the responsibilities as the Gram kernel's fp16 A-operand images,
+    // r 2^14 = a + b per 8-sample chunk and component (gram_umma.cu, GuArgs::rp) — every value is in a register here, and
+    // a lane's four components are 64 contiguous bytes of the image, a warp's 2 KB.
     auto norm_tile = [&](auto nua_c, int t) {
       constexpr int NUA = decltype(nua_c)::value, RB = 16 / NUA;
       const long long row0 = ((long long)blockIdx.x + (long long)t * gridDim.x) * EU_TILE;
       const long long rem = a.N - row0;
       const int rows = rem < EU_TILE ? (int)rem : EU_TILE;
+      const bool pack = NUA <= 2 && a.rpack != nullptr;
+      const int rows_p = pack ? min(EU_TILE, (rows + 31) & ~31) : rows;      // the images cover whole 32-sample chunks
       const float* lzp = lz + (t & 1) * EU_TILE;
       float4* base = reinterpret_cast<float4*>(a.out) + (size_t)row0 * K4 + lane;     // 32-bit offsets from here on
       bool cok[NUA];
@@ -517,7 +522,7 @@ estep_umma_kernel(EstepArgs a, const uint8_t* __restrict__ Wp, const float* __re
       float4 cs[NUA];
 #pragma unroll
       for (int u = 0; u < NUA; ++u) cs[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int r = 0; r < rows; r += RB) {
+      for (int r = 0; r < rows_p; r += RB) {
         float4 x[RB][NUA];
 #pragma unroll
         for (int v = 0; v < RB; ++v) {
@@ -540,6 +545,39 @@ estep_umma_kernel(EstepArgs a, const uint8_t* __restrict__ Wp, const float* __re
             if (rok && cok[u]) {
               pw[32 * u] = y;
               cs[u].x += y.x; cs[u].y += y.y; cs[u].z += y.z; cs[u].w += y.w;
+            }
+            x[v][u] = rok ? y : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+        if (pack) {
+          constexpr float RS = 16384.f;                                   // GU_RSH = 14
+#pragma unroll
+          for (int c = 0; c < RB / 8; ++c) {
+            const long long ch = ((row0 + r) >> 3) + c;                   // global 8-sample chunk
+#pragma unroll
+            for (int u = 0; u < NUA; ++u) {
+              if (cok[u]) {
+                const int comp0 = 4 * (lane + 32 * u);
+                uint8_t* rec = a.rpack + ((size_t)(comp0 >> 7) * nsb + (size_t)(ch >> 1)) * 8192 + (size_t)(ch & 1) * 2048 +
+                               (size_t)(comp0 & 127) * 16;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  uint32_t hi[4], lo[4];
+#pragma unroll
+                  for (int w = 0; w < 4; ++w) {
+                    const float4 f0 = x[8 * c + 2 * w][u], f1 = x[8 * c + 2 * w + 1][u];
+                    const float x0 = (j == 0 ? f0.x : j == 1 ? f0.y : j == 2 ? f0.z : f0.w) * RS;
+                    const float x1 = (j == 0 ? f1.x : j == 1 ? f1.y : j == 2 ? f1.z : f1.w) * RS;
+                    const __half2 ah = __floats2half2_rn(x0, x1);
+                    const float2 af = __half22float2(ah);
+                    const __half2 bh = __floats2half2_rn(x0 - af.x, x1 - af.y);
+                    hi[w] = *reinterpret_cast<const uint32_t*>(&ah);
+                    lo[w] = *reinterpret_cast<const uint32_t*>(&bh);
+                  }
+                  *reinterpret_cast<uint4*>(rec + j * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                  *reinterpret_cast<uint4*>(rec + 4096 + j * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                }
+              }
             }
           }
         }
@@ -606,6 +644,13 @@ bool estep_umma_supported(long long N, int GX, int G, int K, int Dp, int d0, int
   return G == 1 && GX == 1 && (Dp == 16 || Dp == 32 || Dp == 64) && (K % 4 == 0) && K <= EU_MAXK && N >= 256;
 }
 
+bool gram_rpack_usable();
+// K2 can hand K3 the pre-split weights when both run their fp16 tensor-core variants and one normaliser batch covers
+// whole 8-sample chunks of every component (K <= 256)
+bool estep_umma_can_pack(long long N, int GX, int G, int K, int Dp, int d0, int d1, int mode) {
+  return mode == 1 && K <= 256 && eu_use_f16() && gram_rpack_usable() && estep_umma_supported(N, GX, G, K, Dp, d0, d1);
+}
+
 size_t estep_umma_workspace_bytes(long long N, int G, int K, int Dp, int mode) {
   (void)mode;
   if (!estep_umma_supported(N, 1, G, K, Dp, 1, 0)) return 0;
@@ -631,6 +676,8 @@ static int eu_launch(EstepArgs a, int mode, uint8_t* Wp, float* fs, float* NA_pa
   if (rc) return rc;
   const int ntiles = (int)((a.N + EU_TILE - 1) / EU_TILE);
   const int grid = ntiles < eu_num_sms() ? ntiles : eu_num_sms();
+  const long long nsb = (a.N + 31) / 32 * 2;               // 16-sample blocks per component block of the weight images
+  if (!F16) a.rpack = nullptr;
   const size_t fixed = 8192 + sizeof(EuSmem) + 2 * EU_TILE * sizeof(float) + (mode == 1 ? (size_t)a.K * sizeof(double) : 0) + 64;
   int nstage = (int)((227 * 1024 - fixed) / C::STAGE);
   if (nstage > EU_MAXSTAGE) nstage = EU_MAXSTAGE;
@@ -640,10 +687,10 @@ static int eu_launch(EstepArgs a, int mode, uint8_t* Wp, float* fs, float* NA_pa
   a.logZ_part = logZ_part;
   if (mode == 0) {
     cudaFuncSetAttribute(estep_umma_kernel<DP, 0, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    estep_umma_kernel<DP, 0, F16><<<grid, EU_THREADS, smem, st>>>(a, Wp, fs, ntiles, ngroups, nstage);
+    estep_umma_kernel<DP, 0, F16><<<grid, EU_THREADS, smem, st>>>(a, Wp, fs, ntiles, ngroups, nstage, nsb);
   } else {
     cudaFuncSetAttribute(estep_umma_kernel<DP, 1, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    estep_umma_kernel<DP, 1, F16><<<grid, EU_THREADS, smem, st>>>(a, Wp, fs, ntiles, ngroups, nstage);
+    estep_umma_kernel<DP, 1, F16><<<grid, EU_THREADS, smem, st>>>(a, Wp, fs, ntiles, ngroups, nstage, nsb);
   }
   rc = check_launch("estep_umma");
   if (rc) return rc;

@@ -638,6 +638,11 @@ static long long gu_nsb(long long N) { return (N + 31) / 32 * 2; }
 static size_t gu_rp_bytes(long long N, int ncb) { return (size_t)ncb * (size_t)gu_nsb(N) * GU_RREC; }
 static size_t gu_zt_bytes(long long N, int D) { return (size_t)((N + 31) / 32) * gu_zrec(D) + 256; }
 
+static bool gu_use_f16();
+// bytes of the pre-split weight images of (N, K): what gram_rsplit_kernel writes and vbmp_estep_rpack may write instead
+size_t gram_rpack_bytes(long long N, int K) { return gu_rp_bytes(N, (K + GU_CB - 1) / GU_CB); }
+bool gram_rpack_usable() { return gu_use_f16(); }
+
 bool gram_umma_supported(long long N, int GX, int GP, int G, int K, int Dp, int d0, int d1, bool has_p) {
   const int D = d0 + d1;
   return has_p && G == 1 && GX == 1 && GP == 1 && Dp >= 16 && Dp <= 64 && D <= 64 && (K % 4 == 0) && (d0 % 4 == 0) &&
@@ -751,10 +756,14 @@ int launch_gram_umma(const GramArgs& a, float* gram, void* ws, size_t ws_bytes, 
     g.hdr = hdr;
     g.nsb = gu_nsb(a.N);
     uint8_t* rp = (uint8_t*)g.part + part_bytes;
-    g.rp = rp;
-    gram_rsplit_kernel<<<gu_num_sms() * 8, 256, 0, st>>>(a.p, a.N, a.K, g.ncb, g.nsb, rp, hdr);
-    rc = check_launch("gram_rsplit");
-    if (rc) return rc;
+    if (a.rpack) {
+      g.rp = a.rpack;                                        // already written by the E-step's normaliser
+    } else {
+      g.rp = rp;
+      gram_rsplit_kernel<<<gu_num_sms() * 8, 256, 0, st>>>(a.p, a.N, a.K, g.ncb, g.nsb, rp, hdr);
+      rc = check_launch("gram_rsplit");
+      if (rc) return rc;
+    }
     uint8_t* zt = rp + (gu_rp_bytes(a.N, g.ncb) + 255) / 256 * 256;
     g.zt = zt;
     g.zrec = gu_zrec(D);

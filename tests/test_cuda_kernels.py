@@ -154,6 +154,23 @@ def test_gram_weights_beyond_fp16_range_use_the_tf32_path():
     assert float((G.double() - Gref).abs().max() / Gref.abs().max()) <= 1e-5
 
 
+@pytest.mark.parametrize("N,d0,d1,K", [(5000, 64, 0, 256), (3001, 32, 32, 64), (2049, 16, 0, 132), (4099, 16, 16, 32)])
+def test_estep_hands_presplit_weights_to_gram(N, d0, d1, K):
+    """K2 (mode 1) leaves the responsibilities pre-split for K3; the Gram from those images must equal (bit for bit) the
+    Gram K3 computes when it splits the same p itself, and an edited p must not use stale images."""
+    z, z0, z1, W, m, cst, Dp, L = _problem(N, d0, d1, K, seed=6)
+    xg = torch.zeros(1, dtype=torch.int32, device=DEV)
+    p, lzn, NA, lZ = _lib.estep(z0, z1, N, 1, xg, W, m, cst, 1, K, Dp, 1)
+    key = _lib._rpack_key(p.device)
+    assert key in _lib._rpack_rec                                       # the hand-over happened
+    G1 = _lib.gram(z0, z1, N, 1, xg, p, 1, xg, 1, K, Dp).clone()
+    G2 = _lib.gram(z0, z1, N, 1, xg, p.clone(), 1, xg, 1, K, Dp).clone()       # a copy: K3 splits it itself
+    assert torch.equal(G1, G2)
+    p.mul_(0.5)                                                         # in-place edit: version counter moves on
+    G3 = _lib.gram(z0, z1, N, 1, xg, p, 1, xg, 1, K, Dp)
+    assert float((G3.double() - 0.5 * G2.double()).abs().max() / G2.abs().max()) <= 1e-5
+
+
 def test_gram_is_deterministic_run_to_run():
     z, z0, z1, W, m, cst, Dp, L = _problem(40000, 64, 0, 64, seed=2)
     xg = torch.zeros(1, dtype=torch.int32, device=DEV)
