@@ -618,7 +618,7 @@ static void gu_plan(long long N, int K, int D, int sms, GuArgs* g) {
   // the fastest.  rounds of `sms` co-resident CTAs needed at <= cap rows per CTA; then as many splits as fill those
   // rounds exactly (cfg2: 24 tasks, 21 rounds of 148 -> 129 splits), so the last round is not a partial one.
   // VBMP_GRAM_ROWS overrides the cap (tuning).
-  static const long long cap = [] { const char* e = getenv("VBMP_GRAM_ROWS"); long long v = e ? atoll(e) : 0; return v >= 2048 ? v : 131072; }();
+  static const long long cap = [] { const char* e = getenv("VBMP_GRAM_ROWS"); long long v = e ? atoll(e) : 0; return v >= 2048 ? v : 32768; }();
   long long rounds = ((long long)N * tasks + (long long)sms * cap - 1) / ((long long)sms * cap);
   if (rounds < 1) rounds = 1;
   long long sp = rounds * sms / tasks;
