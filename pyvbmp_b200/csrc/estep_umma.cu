@@ -543,7 +543,8 @@ estep_umma_kernel(EstepArgs a, const uint8_t* __restrict__ Wp, const float* __re
             y.x = ex2((y.x - lzr) * 1.44269504f); y.y = ex2((y.y - lzr) * 1.44269504f);
             y.z = ex2((y.z - lzr) * 1.44269504f); y.w = ex2((y.w - lzr) * 1.44269504f);
             if (rok && cok[u]) {
-              pw[32 * u] = y;
+              __stcs(pw + 32 * u, y);          // streaming (evict-first): p is not re-read by this kernel, the logits of
+                                               // the tiles still in flight should stay in L2 until they are overwritten
               cs[u].x += y.x; cs[u].y += y.y; cs[u].z += y.z; cs[u].w += y.w;
             }
             x[v][u] = rok ? y : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -574,8 +575,8 @@ estep_umma_kernel(EstepArgs a, const uint8_t* __restrict__ Wp, const float* __re
                     hi[w] = *reinterpret_cast<const uint32_t*>(&ah);
                     lo[w] = *reinterpret_cast<const uint32_t*>(&bh);
                   }
-                  *reinterpret_cast<uint4*>(rec + j * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                  *reinterpret_cast<uint4*>(rec + 4096 + j * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                  __stcs(reinterpret_cast<uint4*>(rec + j * 16), make_uint4(hi[0], hi[1], hi[2], hi[3]));
+                  __stcs(reinterpret_cast<uint4*>(rec + 4096 + j * 16), make_uint4(lo[0], lo[1], lo[2], lo[3]));
                 }
               }
             }
