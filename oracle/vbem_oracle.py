@@ -553,6 +553,40 @@ def molt_raw_update(m, X, Y, iters=1, lr=1.0, exact=True, chunk=None):
     return trace
 
 
+def mnw_predict(s, X):
+    """transforms/MatrixNormalWishart.py:381-390 (pad_X branch :383-384): natural parameters of p(y | x) per component and
+    the per-component log evidence Res - pY.Res() (dists/MultivariateNormal_vector_format.py:118-119).  X: (..., p, 1)."""
+    EinvUX, EXTinvUX = mnw_EinvUX(s), mnw_EXTinvUX(s)
+    n = s["n"]
+    log2pi = torch.log(2 * torch.tensor(torch.pi, dtype=X.dtype))
+    if s["pad_X"]:
+        invSigmamu_y = EinvUX[..., :, :-1] @ X + EinvUX[..., :, -1:]
+        Res = -0.5 * X.transpose(-1, -2) @ EXTinvUX[..., :-1, :-1] @ X - EXTinvUX[..., -1:, :-1] @ X - 0.5 * EXTinvUX[..., -1:, -1:]
+    else:
+        invSigmamu_y = EinvUX @ X
+        Res = -0.5 * X.transpose(-1, -2) @ EXTinvUX @ X
+    Res = Res.squeeze(-1).squeeze(-1) + 0.5 * wishart_ElogdetinvSigma(s["invU"]) - 0.5 * n * log2pi
+    invSigma = wishart_EinvSigma(s["invU"])
+    mean = invSigma.inverse() @ invSigmamu_y
+    pY_Res = -0.5 * (mean * invSigmamu_y).sum(-1).sum(-1) + 0.5 * invSigma.logdet() - 0.5 * n * log2pi
+    return invSigma, invSigmamu_y, mean, Res - pY_Res
+
+
+def molt_predict(m, X):
+    """transforms/MixtureofLinearTransforms.py:91-108: mixture-of-experts predictive mean / covariance and the gate
+    probabilities for inputs X (N, p, 1).  Returns (mu (N,n,1), Sigma (N,n,n), p (N,K))."""
+    invSigma, _, mean, Res = mnw_predict(m["W"], X.unsqueeze(-3))
+    log_p = Res + dirichlet_loggeomean(m["pi"])
+    log_p = log_p - log_p.max(-1, True)[0]
+    p = log_p.exp()
+    p = p / p.sum(-1, True)
+    pe = p.unsqueeze(-1).unsqueeze(-1)
+    Sigma = ((invSigma.inverse() + mean @ mean.transpose(-2, -1)) * pe).sum(-3)
+    mu = (mean * pe).sum(-3)
+    Sigma = Sigma - mu @ mu.transpose(-2, -1)
+    return mu, Sigma, p
+
+
 # --------------------------------------------------------------------------------------
 # HMM / ARHMM                          reference: models/HMM.py, models/ARHMM.py
 # --------------------------------------------------------------------------------------

@@ -10,6 +10,7 @@ from .mnw import MatrixNormalWishart
 from .dirichlet import Dirichlet
 from .mixture import Mixture, GaussianMixtureModel
 from .molt import MixtureofLinearTransforms
+from .mvn import MultivariateNormal_vector_format
 from .hmm import HMM, ARHMM
 from .install import install, uninstall
 from . import sharding

@@ -251,6 +251,44 @@ class MatrixNormalWishart():
     def var(self):
         return self.ESigma().diagonal(dim1=-1, dim2=-2).unsqueeze(-1) * self.V.diagonal(dim1=-1, dim2=-2).unsqueeze(-2)
 
+    def predict(self, X):
+        """transforms/MatrixNormalWishart.py:381-390: natural parameters of p(y | x) per component and the per-component
+        log evidence.  Same op order as the reference (small per-component matrices, one batched product with X)."""
+        from .mvn import MultivariateNormal_vector_format
+        if self.pad_X:
+            invSigmamu_y = (self.EinvUX()[..., :, :-1] @ X + self.EinvUX()[..., :, -1:])
+            Res = (-0.5 * X.transpose(-1, -2) @ self.EXTinvUX()[..., :-1, :-1] @ X - self.EXTinvUX()[..., -1:, :-1] @ X
+                   - 0.5 * self.EXTinvUX()[..., -1:, -1:])
+        else:
+            invSigmamu_y = (self.EinvUX() @ X)
+            Res = -0.5 * X.transpose(-1, -2) @ self.EXTinvUX() @ X
+        Res = Res.squeeze(-1).squeeze(-1) + 0.5 * self.ElogdetinvSigma() - 0.5 * self.n * self.log2pi
+        pY = MultivariateNormal_vector_format(invSigma=self.EinvSigma(), invSigmamu=invSigmamu_y)
+        return pY, Res - pY.Res()
+
+    def _predict_factors(self, logprior=None):
+        """Whitened form of `predict`'s per-component log evidence for the E-step kernel (K2):
+        Res - pY.Res() = -1/2 n xt^T V xt + 1/2 (E logdet invSigma - logdet E invSigma),  xt = [x;1]  (the mu-dependent
+        quadratic terms of :384 and of MultivariateNormal_vector_format.Res cancel), so with n V = U U^T, U upper
+        triangular, it is cst - 1/2 ||W^T x - m||^2 with W = U[:p], m = -U[p] (the row of the constant feature).
+        K small matrices, fp64 on the device; returns (W (K,Dp,Dp), m (K,Dp), cst (K), Dp)."""
+        assert self.batch_dim == 1 and self.event_dim == 2
+        dev = self.mu.device
+        pp, K = self.p, self.batch_shape[0]
+        p_in = pp - int(self.pad_X)
+        A = (self.n * self.V).double().expand(K, pp, pp)
+        U = torch.linalg.cholesky(A.flip(-1, -2)).flip(-1, -2)            # A = U U^T, U upper triangular
+        Dp = _lib.pad_dim(pp)
+        W = torch.zeros(K, Dp, Dp, dtype=torch.float64, device=dev)
+        m = torch.zeros(K, Dp, dtype=torch.float64, device=dev)
+        W[:, :p_in, :pp] = U[:, :p_in, :]
+        if self.pad_X:
+            m[:, :pp] = -U[:, p_in, :]
+        cst = 0.5 * (self.ElogdetinvSigma().double() - self.EinvSigma().double().logdet()).expand(K)
+        if logprior is not None:
+            cst = cst + logprior.double()
+        return W.float().contiguous(), m.float().contiguous(), cst.float().contiguous(), Dp
+
     def EinvUX(self):
         return self.invU.EinvSigma() @ self.mu
 

@@ -83,8 +83,56 @@ class MixtureofLinearTransforms():
     def update(self, pX, pY, iters=1, lr=1, verbose=False):
         raise NotImplementedError("expectation-input update is a 'next' row (SURVEY.md §8f #2)")
 
+    PREDICT_ROWS = 1 << 16       # rows per block of the (rows, K, n) temporaries of the moment sums
+
     def predict(self, X):
-        raise NotImplementedError("predict is a 'next' row (SURVEY.md §8f #3)")
+        """transforms/MixtureofLinearTransforms.py:91-108: mixture-of-experts predictive distribution of Y and the gate
+        probabilities for inputs X (..., p, 1).  On the CUDA path the gate probabilities come from the fused E-step kernel
+        (K2, softmax epilogue) on the whitened form of the per-component evidence (MatrixNormalWishart._predict_factors);
+        the moment sums over components are three GEMM-shaped torch steps per block of rows."""
+        from .mvn import MultivariateNormal_vector_format
+        W = self.W
+        if not (isinstance(W, MatrixNormalWishart) and self.batch_dim == 0 and W.event_dim == 2 and X.is_cuda and X.ndim == 3):
+            pY, Res = W.predict(X.unsqueeze(-3))
+            log_p = Res + self.pi.loggeomean()
+            log_p = log_p - log_p.max(-1, True)[0]
+            p = log_p.exp()
+            p = p / p.sum(-1, True)
+            pe = p.unsqueeze(-1).unsqueeze(-1)
+            Sigma = ((pY.ESigma() + pY.mean() @ pY.mean().transpose(-2, -1)) * pe).sum(-3)
+            mu = (pY.mean() * pe).sum(-3)
+            Sigma = Sigma - mu @ mu.transpose(-2, -1)
+            return MultivariateNormal_vector_format(mu=mu, Sigma=Sigma), p
+        dev = W.mu.device
+        N, K, n = X.shape[0], self.dim, self.n
+        p_in = W.p - int(W.pad_X)
+        Wt, m, cst, Dp = W._predict_factors(self.pi.loggeomean())
+        Xc = _lib.f32(X, dev).reshape(N, 1, p_in)
+        xg = _shapes.idx_tensor((0,), dev)
+        p = _lib.estep(Xc, None, N, 1, xg, Wt, m, cst, 1, K, Dp, 1)[0].view(N, K)
+        M = W.mu                                                           # (K, n, p'): mean_k(x) = M_k [x;1]
+        ES = W.EinvSigma().inverse().expand(K, n, n)                       # = pY.ESigma(): (E invSigma)^-1 = invU / nu (:389)
+        Mw = M[..., :p_in].reshape(K * n, p_in).t().contiguous()           # (p, K n)
+        Mb = M[..., -1].reshape(1, K * n) if W.pad_X else None
+        ESf = ES.reshape(K, n * n).contiguous()
+        mu = torch.empty(N, n, 1, device=dev)
+        Sigma = torch.empty(N, n, n, device=dev)
+        X2 = Xc.view(N, p_in)
+        # per block of rows (fp32): all component means at once, the p-weighted second moment as a batched A^T A with
+        # A = sqrt(p) * mean, and the p-weighted component covariances
+        for a in range(0, N, self.PREDICT_ROWS):
+            b = min(N, a + self.PREDICT_ROWS)
+            mean = X2[a:b] @ Mw
+            if Mb is not None:
+                mean = mean + Mb
+            mean = mean.view(b - a, K, n)
+            pe = p[a:b]
+            mu_b = torch.bmm(pe.unsqueeze(1), mean).squeeze(1)                                  # (rows, n)
+            A = mean * pe.sqrt().unsqueeze(-1)
+            S = torch.baddbmm((pe @ ESf).view(b - a, n, n), A.transpose(1, 2), A)
+            mu[a:b, :, 0] = mu_b
+            Sigma[a:b] = S - mu_b.unsqueeze(-1) * mu_b.unsqueeze(-2)
+        return MultivariateNormal_vector_format(mu=mu, Sigma=Sigma), p
 
     def KLqprior(self):
         return self.pi.KLqprior() + self.W.KLqprior().sum(-1)

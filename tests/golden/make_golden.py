@@ -269,6 +269,26 @@ def gen_molt():
         save(name, **out)
 
 
+def gen_molt_predict():
+    """MixtureofLinearTransforms.predict on held-out inputs after a few EM iterations (SURVEY.md §8f #3)."""
+    g = torch.Generator().manual_seed(43)
+    for name, n, p, K, N, iters in (("molt_predict_n3_p4_k5", 3, 4, 5, 600, 4), ("molt_predict_n16_p32_k8", 16, 32, 8, 768, 3)):
+        torch.manual_seed(12)
+        m = transforms.MixtureofLinearTransforms(n, p, K, pad_X=True)
+        X = torch.randn(N, p, generator=g)
+        Wt = torch.randn(K, n, p, generator=g) / np.sqrt(p)
+        b = torch.randn(K, n, generator=g)
+        z = torch.randint(K, (N,), generator=g)
+        Y = torch.einsum("nij,nj->ni", Wt[z], X) + b[z] + 0.1 * torch.randn(N, n, generator=g)
+        m.raw_update(X.unsqueeze(-1), Y.unsqueeze(-1), iters=iters, lr=1.0)
+        Xt = 1.5 * torch.randn(200, p, generator=g)
+        pY, pr = m.predict(Xt.unsqueeze(-1))
+        out = {"Xt": T(Xt), "n": n, "p": p, "K": K}
+        out.update(tagged(molt_state(m), "state"))
+        out["predict/mu"], out["predict/Sigma"], out["predict/p"] = T(pY.mean()), T(pY.ESigma()), T(pr)
+        save(name, **out)
+
+
 def gen_arhmm():
     g = torch.Generator().manual_seed(51)
     K, n, p, Tn, S = 4, 2, 3, 40, 25
@@ -313,4 +333,5 @@ if __name__ == "__main__":
     gen_niw_variants()
     gen_mnw()
     gen_molt()
+    gen_molt_predict()
     gen_arhmm()

@@ -230,6 +230,50 @@ def test_molt_golden(name):
     assert nbad == 0 or max(margins) < 1e-3, (nbad, margins)
 
 
+@pytest.mark.parametrize("name", ["molt_predict_n3_p4_k5", "molt_predict_n16_p32_k8"])
+def test_molt_predict_golden(name):
+    """MixtureofLinearTransforms.predict: gate probabilities from the fused E-step kernel on the whitened
+    evidence, predictive moments in the reference's op order — against the reference's own outputs (golden) and, at a
+    size that takes the tensor-core kernel, against the fp64 oracle."""
+    fix = load_golden(name)
+    n, p, K = (int(fix[k]) for k in ("n", "p", "K"))
+    torch.manual_seed(0)
+    m = V.MixtureofLinearTransforms(n, p, K).to(DEV)
+    set_state(m, tag(fix, "state"))
+    Xt = torch.as_tensor(fix["Xt"]).unsqueeze(-1).to(DEV)
+    pY, pr = m.predict(Xt)
+    pf = tag(fix, "predict")
+    assert pr.shape == pf["p"].shape and pY.mean().shape == pf["mu"].shape and pY.ESigma().shape == pf["Sigma"].shape
+    # The evidence of far-out inputs cancels heavily: on the small fixture the reference's own fp32 outputs sit 3.5e-5 (p),
+    # 5.2e-5 (mean) from an fp64 evaluation of the same state, ours 3.8e-5 / 6.9e-5 — so the golden gate is 2.5x PARITY and
+    # the strict 1e-4 gate is against the fp64 oracle.
+    assert_maxabs(pr.cpu(), pf["p"], 1e-4, "gate probabilities")
+    assert_close(pY.mean(), pf["mu"], 2.5 * PARITY, "predictive mean")
+    assert_close(pY.ESigma(), pf["Sigma"], 5 * PARITY, "predictive covariance")
+    ref0 = O.molt_new(n, p, K)
+    O.load_state(ref0, tag(fix, "state"))
+    O.to_dtype(ref0, torch.float64)
+    mu0, Sig0, p0 = O.molt_predict(ref0, Xt.cpu().double())
+    assert_maxabs(pr.cpu().double(), p0, 1e-4, "gate probabilities (fp64 oracle, fixture inputs)")
+    assert_close(pY.mean().cpu().double(), mu0, PARITY, "predictive mean (fp64 oracle, fixture inputs)")
+    assert_close(pY.ESigma().cpu().double(), Sig0, PARITY, "predictive covariance (fp64 oracle, fixture inputs)")
+    # the generic (reference op order) branch of the mirror must agree with the fused one
+    pY2, Res = m.W.predict(Xt.unsqueeze(-3))
+    lp = Res + m.pi.loggeomean()
+    assert_maxabs(torch.softmax(lp, -1).cpu(), pr.cpu(), 1e-4, "generic vs fused gates")
+    # larger batch (tensor-core E-step kernel when p, K allow) against the fp64 oracle
+    g = torch.Generator().manual_seed(5)
+    Xb = 1.5 * torch.randn(4096, p, 1, generator=g)
+    ref = O.molt_new(n, p, K)
+    O.load_state(ref, tag(fix, "state"))
+    O.to_dtype(ref, torch.float64)
+    mu_r, Sig_r, p_r = O.molt_predict(ref, Xb.double())
+    pYb, prb = m.predict(Xb.to(DEV))
+    assert_maxabs(prb.cpu().double(), p_r, 1e-4, "gate probabilities (oracle)")
+    assert_close(pYb.mean().cpu().double(), mu_r, PARITY, "predictive mean (oracle)")
+    assert_close(pYb.ESigma().cpu().double(), Sig_r, 5 * PARITY, "predictive covariance (oracle)")
+
+
 def test_arhmm_golden():
     fix = load_golden("arhmm_k4_n2_p3")
     K, n, p = int(fix["K"]), int(fix["n"]), int(fix["p"])

@@ -189,6 +189,25 @@ def test_molt_trajectory(name, exact):
     assert (m["p"].argmax(-1).numpy() == fix["final/assignment"]).mean() > 0.995
 
 
+@pytest.mark.parametrize("name", ["molt_predict_n3_p4_k5", "molt_predict_n16_p32_k8"])
+@pytest.mark.parametrize("f64", [False, True])
+def test_molt_predict(name, f64):
+    """MixtureofLinearTransforms.predict (transforms/MixtureofLinearTransforms.py:91-108) on held-out inputs."""
+    fix = load_golden(name)
+    n, p, K = (int(fix[k]) for k in ("n", "p", "K"))
+    m = O.molt_new(n, p, K)
+    O.load_state(m, tag(fix, "state"))
+    Xt = torch.as_tensor(fix["Xt"]).unsqueeze(-1)
+    if f64:
+        O.to_dtype(m, torch.float64)
+        Xt = Xt.double()
+    mu, Sigma, pr = O.molt_predict(m, Xt)
+    pf = tag(fix, "predict")
+    assert float((pr - pf["p"]).abs().max()) < 5e-5
+    assert_close(mu, pf["mu"], PARITY, "predict mean")
+    assert_close(Sigma, pf["Sigma"], 5 * PARITY, "predict covariance")       # formed as a difference of second moments
+
+
 @pytest.mark.parametrize("exact", [True, False])
 def test_arhmm_trajectory(exact):
     fix = load_golden("arhmm_k4_n2_p3")

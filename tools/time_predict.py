@@ -1,0 +1,30 @@
+"""Time MixtureofLinearTransforms.predict on held-out inputs (dev tool)."""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import pyvbmp_b200 as V
+from pyvbmp_b200 import _lib
+dev = torch.device("cuda:0")
+n, p, K = 32, 32, 64
+N = int(os.environ.get("TP_N", 1 << 20))
+g = torch.Generator(device=dev).manual_seed(0)
+torch.manual_seed(0)
+m = V.MixtureofLinearTransforms(n, p, K).to(dev)
+X = torch.randn(N, p, 1, generator=g, device=dev)
+Wt = torch.randn(K, n, p, generator=g, device=dev) / p ** 0.5
+z = torch.randint(K, (N,), generator=g, device=dev)
+Y = (torch.einsum("nij,nj->ni", Wt[z], X[..., 0]) + 0.1 * torch.randn(N, n, generator=g, device=dev)).unsqueeze(-1)
+m.raw_update(X, Y, iters=2)
+def run():
+    return m.predict(X)
+for _ in range(2): run()
+torch.cuda.synchronize()
+_lib.PROFILE = {}
+a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+a.record()
+for _ in range(3): pY, pr = run()
+b.record(); b.synchronize()
+t = a.elapsed_time(b) / 3
+ke = sum(x.elapsed_time(y) for x, y in _lib.PROFILE.get("vbmp_estep", [])) / 3
+print(f"MoLT.predict N={N} p={p} n={n} K={K}: {t:.2f} ms per call ({N * K / t / 1e6:.2f}e9 sample*component evaluations/s); "
+      f"gate probabilities (K2 kernel) {ke:.2f} ms, moment sums (torch batched GEMMs, {N * n * n * 4 / 1e9:.2f} GB of covariances out) {t - ke:.2f} ms")
