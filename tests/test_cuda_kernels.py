@@ -171,6 +171,35 @@ def test_estep_hands_presplit_weights_to_gram(N, d0, d1, K):
     assert float((G3.double() - 0.5 * G2.double()).abs().max() / G2.abs().max()) <= 1e-5
 
 
+def test_tf32_operand_variants_still_agree():
+    """The TF32-split kernels stay in the library (VBMP_ESTEP_PREC / VBMP_GRAM_PREC = tf32, read once per process, and the
+    Gram's on-device fallback): run them in a fresh interpreter against the same fp64 restatement."""
+    import os, subprocess, sys, textwrap
+    code = textwrap.dedent("""
+        import sys, torch
+        sys.path.insert(0, %r); sys.path.insert(0, %r)
+        import test_cuda_kernels as T
+        from pyvbmp_b200 import _lib
+        N, d0, K = 5000, 64, 64
+        z, z0, z1, W, m, cst, Dp, L = T._problem(N, d0, 0, K, seed=8)
+        xg = torch.zeros(1, dtype=torch.int32, device=T.DEV)
+        lg = _lib.estep(z0, z1, N, 1, xg, W, m, cst, 1, K, Dp, 0).view(N, K)
+        p, lzn, NA, lZ = _lib.estep(z0, z1, N, 1, xg, W, m, cst, 1, K, Dp, 1)
+        scale = float(L.abs().max())
+        assert float((lg.double() - L).abs().max()) <= 2e-6 * scale
+        P = (L - torch.logsumexp(L, -1)[:, None]).exp()
+        assert float((p.view(N, K).double() - P).abs().max()) <= 2e-3
+        zt = torch.cat([z.double(), torch.ones(N, 1, device=T.DEV, dtype=torch.float64)], 1)
+        Gref = torch.einsum("nk,ni,nj->kij", p.view(N, K).double(), zt, zt)
+        G = _lib.gram(z0, z1, N, 1, xg, p, 1, xg, 1, K, Dp).view(K, d0 + 1, d0 + 1)
+        assert float((G.double() - Gref).abs().max() / Gref.abs().max()) <= 1e-5
+        print("tf32 variants ok")
+    """) % (os.path.dirname(os.path.abspath(__file__)), os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    env = dict(os.environ, VBMP_ESTEP_PREC="tf32", VBMP_GRAM_PREC="tf32")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "tf32 variants ok" in out.stdout, out.stderr[-2000:]
+
+
 def test_gram_is_deterministic_run_to_run():
     z, z0, z1, W, m, cst, Dp, L = _problem(40000, 64, 0, 64, seed=2)
     xg = torch.zeros(1, dtype=torch.int32, device=DEV)
