@@ -1,73 +1,72 @@
-"""MultivariateNormal_vector_format with the reference's interface (dists/MultivariateNormal_vector_format.py:3-119):
-the value type `predict` returns.  A plain container of moments / natural parameters with lazy conversions; nothing here
-is on the VB-EM hot path (batches of n x n inverses of an (N, n, n) result are torch plumbing)."""
+"""Value type returned by `predict`: a (batch of) Gaussian over column vectors held either by moments (mu, Sigma) or by
+natural parameters (invSigma, invSigmamu), with the accessor names of the reference's
+dists/MultivariateNormal_vector_format.py (mean / ESigma / EinvSigma / EinvSigmamu / ElogdetinvSigma / EX / EXXT / EXTX /
+Res).  Whichever representation is missing is derived on first use and cached.  Nothing here is on the VB-EM hot path;
+the conversions are batched n x n inverses on the device."""
 from __future__ import annotations
+
+import math
 
 import torch
 
 
 class MultivariateNormal_vector_format():
+    event_dim = 2            # vectors are (dim, 1) matrices
 
     def __init__(self, mu=None, Sigma=None, invSigmamu=None, invSigma=None, logdetinvSigma=None):
-        """dists/MultivariateNormal_vector_format.py:4-27: vectors are (dim, 1) matrices."""
-        self.mu = mu
-        self.Sigma = Sigma
-        self.invSigmamu = invSigmamu
-        self.invSigma = invSigma
+        self.mu, self.Sigma = mu, Sigma
+        self.invSigmamu, self.invSigma = invSigmamu, invSigma
         self.logdetinvSigma = logdetinvSigma
-        self.event_dim = 2
-        if self.mu is not None:
-            self.dim = mu.shape[-2]
-            self.event_shape = mu.shape[-2:]
-            self.batch_shape = mu.shape[:-2]
-        elif self.invSigmamu is not None:
-            self.dim = invSigmamu.shape[-2]
-            self.event_shape = invSigmamu.shape[-2:]
-            self.batch_shape = invSigmamu.shape[:-2]
-        else:
-            print('mu and invSigmamu are both None: cannont initialize MultivariateNormal')
-            return None
+        vec = mu if mu is not None else invSigmamu
+        if vec is None:
+            raise ValueError("MultivariateNormal_vector_format needs mu or invSigmamu")
+        self.dim = vec.shape[-2]
+        self.event_shape = tuple(vec.shape[-2:])
+        self.batch_shape = tuple(vec.shape[:-2])
         self.batch_dim = len(self.batch_shape)
-        self.event_dim = len(self.event_shape)
 
     @property
     def shape(self):
         return self.batch_shape + self.event_shape
 
-    def mean(self):                                                     # :79-82
-        if self.mu is None:
-            self.mu = self.invSigma.inverse() @ self.invSigmamu
-        return self.mu
-
-    def ESigma(self):                                                   # :84-87
+    # ---- the two representations, each filled in from the other on demand ---------------------------------
+    def ESigma(self):
         if self.Sigma is None:
-            self.Sigma = self.invSigma.inverse()
+            self.Sigma = torch.linalg.inv(self.invSigma)
         return self.Sigma
 
-    def EinvSigma(self):                                                # :89-92
+    def EinvSigma(self):
         if self.invSigma is None:
-            self.invSigma = self.Sigma.inverse()
+            self.invSigma = torch.linalg.inv(self.Sigma)
         return self.invSigma
 
-    def EinvSigmamu(self):                                              # :94-97
+    def mean(self):
+        if self.mu is None:
+            self.mu = self.ESigma() @ self.invSigmamu
+        return self.mu
+
+    def EinvSigmamu(self):
         if self.invSigmamu is None:
             self.invSigmamu = self.EinvSigma() @ self.mean()
         return self.invSigmamu
 
-    def ElogdetinvSigma(self):                                          # :104-107
+    def ElogdetinvSigma(self):
         if self.logdetinvSigma is None:
-            self.logdetinvSigma = self.EinvSigma().logdet()
+            self.logdetinvSigma = torch.logdet(self.EinvSigma())
         return self.logdetinvSigma
 
-    def EX(self):
-        return self.mean()
+    # ---- expectations -----------------------------------------------------------------------------------
+    EX = mean
 
-    def EXXT(self):                                                     # :112-113
-        return self.ESigma() + self.mean() @ self.mean().transpose(-2, -1)
+    def EXXT(self):
+        m = self.mean()
+        return self.ESigma() + m @ m.transpose(-2, -1)
 
-    def EXTX(self):                                                     # :115-116
-        return self.ESigma().sum(-1).sum(-1) + (self.mean().transpose(-2, -1) @ self.mean()).squeeze(-1).squeeze(-1)
+    def EXTX(self):
+        m = self.mean()
+        return self.ESigma().sum((-2, -1)) + (m * m).sum((-2, -1))
 
-    def Res(self):                                                      # :118-119
-        return (- 0.5 * (self.mean() * self.EinvSigmamu()).sum(-1).sum(-1) + 0.5 * self.ElogdetinvSigma()
-                - 0.5 * self.dim * torch.log(2 * torch.tensor(torch.pi, requires_grad=False)))
+    def Res(self):
+        """Log normaliser of the natural form: -mu^T invSigma mu / 2 + logdet(invSigma) / 2 - dim log(2 pi) / 2."""
+        quad = (self.mean() * self.EinvSigmamu()).sum((-2, -1))
+        return 0.5 * (self.ElogdetinvSigma() - quad - self.dim * math.log(2.0 * math.pi))
