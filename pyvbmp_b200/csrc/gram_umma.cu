@@ -150,8 +150,7 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant_
   const int rawR = F16 ? 2 * GU_RREC : SC * kcb * 4, rawZ0 = F16 ? a.zrec : SC * a.d0 * 4, rawZ1 = F16 ? 0 : SC * a.d1 * 4;
   const int rawB = (rawR + rawZ0 + rawZ1 + 127) / 128 * 128;
   constexpr int GU_NSTG = gu_nstg(PAIR), GU_NPMAX = gu_npmax(PAIR);
-  const int NH = PAIR ? a.NPB / 2 : a.NPB;                 // pair columns generated (and held as B rows) by this CTA
-  const int stageB = 2 * NH * 64;
+  const int stageB = 2 * (PAIR ? a.NPB / 2 : a.NPB) * 64;    // sized for a full-width pair block
   uint8_t* raw = smem_raw;
   uint8_t* bst = raw + GU_NR * rawB;
   GuSmem* S = reinterpret_cast<GuSmem*>(bst + GU_NSTG * stageB);
@@ -167,7 +166,10 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant_
   const long long nb = (long long)split * a.S_per;
   long long ne = nb + a.S_per; if (ne > a.N) ne = a.N;
   const int nchunks = ne > nb ? (int)((ne - nb + SC - 1) / SC) : 0;
-  const int NPB = a.NPB, FL = a.FL;
+  // the last pair block is narrower (cfg2: 11 blocks of 192 columns and one of 48 instead of 12 x 192): its MMAs, phi
+  // columns and folds shrink with it; the partial buffer keeps the full-width stride a.NPB
+  const int NPB = min(a.NPB, (a.P - pb * a.NPB + 15) / 16 * 16), FL = a.FL;
+  const int NH = PAIR ? NPB / 2 : NPB;                     // pair columns generated (and held as B rows) by this CTA
 
   if (tid == 0) {
     // one arrival per worker warp; in a pair the leader's bfull / dempty collect both CTAs' warps
@@ -275,7 +277,7 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant_
     const int ks0 = split_ks ? wtid / NH : 0, ksn = F16 ? (split_ks ? 1 : 2) : 1;
     const bool gen = split_ks ? wtid < 2 * NH : wtid < NH;
     {
-      const int pg_ = pb * NPB + (int)rank * NH + pslot;
+      const int pg_ = pb * a.NPB + (int)rank * NH + pslot;
       const bool pair_ok = gen && (pg_ < a.P);
       int pi = 0, pj = 0;
       if (pair_ok) gu_pair(pg_, D, &pi, &pj);
@@ -419,7 +421,7 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant_
         mbar_wait(&S->dfull, nflush & 1);
         tc_fence_after();
         const bool firstf = (nflush == 0);
-        float* prow = a.part + ((size_t)split * a.Kp + (size_t)cb * GU_CB + comp) * a.PP + (size_t)pb * NPB;
+        float* prow = a.part + ((size_t)split * a.Kp + (size_t)cb * GU_CB + comp) * a.PP + (size_t)pb * a.NPB;
         for (int c0 = sh * (GU_NPMAX / 2); c0 < (sh + 1) * (GU_NPMAX / 2) && c0 < NPB; c0 += 16) {
           float v1[16], v2[16];
           tmem_ld16(tm + lane_base + c0, v1);
@@ -444,7 +446,7 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant_
       }
     }
     if (nchunks == 0 && set == 0) {      // empty split: contribute zeros
-      float* prow = a.part + ((size_t)split * a.Kp + (size_t)cb * GU_CB + comp) * a.PP + (size_t)pb * NPB;
+      float* prow = a.part + ((size_t)split * a.Kp + (size_t)cb * GU_CB + comp) * a.PP + (size_t)pb * a.NPB;
       for (int c0 = sh * (GU_NPMAX / 2); c0 < (sh + 1) * (GU_NPMAX / 2) && c0 < NPB; ++c0) prow[c0] = 0.f;
     }
   }
