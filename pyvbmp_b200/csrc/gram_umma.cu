@@ -607,7 +607,9 @@ static void gu_plan(long long N, int K, int D, int sms, GuArgs* g) {
   const int GU_NPMAX = gu_npmax(gu_pair_mode(K));
   const int D1 = D + 1;
   g->P = D1 * (D1 + 1) / 2;
-  g->npb = (g->P + GU_NPMAX - 1) / GU_NPMAX;
+  static const int npb_cap = [] { const char* e = getenv("VBMP_GRAM_NPB"); return e ? atoi(e) : 0; }();   // tuning: pair columns per block
+  const int npmax = (npb_cap >= 16 && npb_cap <= GU_NPMAX) ? npb_cap : GU_NPMAX;
+  g->npb = (g->P + npmax - 1) / npmax;
   g->NPB = ((g->P + g->npb - 1) / g->npb + 15) / 16 * 16;
   if (g->NPB < 16) g->NPB = 16;
   g->ncb = (K + GU_CB - 1) / GU_CB;
