@@ -553,6 +553,63 @@ def molt_raw_update(m, X, Y, iters=1, lr=1.0, exact=True, chunk=None):
     return trace
 
 
+def mnw_elog_like_given(s, mux, EXXTx, muy, EXXTy):
+    """transforms/MatrixNormalWishart.py:234-249 (Elog_like_given_pX_pY): expected log likelihood under Gaussian beliefs
+    about input and output, given their means (..., p, 1) / (..., n, 1) and second moments E[xx^T], E[yy^T]."""
+    ES, EinvUX, EXTinvUX = wishart_EinvSigma(s["invU"]), mnw_EinvUX(s), mnw_EXTinvUX(s)
+    ELL = -0.5 * (EXXTy * ES).sum(-1).sum(-1)
+    if s["pad_X"]:
+        ELL = ELL + (muy.transpose(-2, -1) @ (EinvUX[..., :, :-1] @ mux + EinvUX[..., :, -1:])).squeeze(-1).squeeze(-1)
+        ELL = ELL - 0.5 * (EXXTx * EXTinvUX[..., :-1, :-1]).sum(-1).sum(-1)
+        ELL = ELL - (EXTinvUX[..., -1:, :-1] @ mux).squeeze(-1).squeeze(-1)
+        ELL = ELL - 0.5 * (EXTinvUX[..., -1, -1])
+    else:
+        ELL = ELL + (muy.transpose(-2, -1) @ EinvUX @ mux).squeeze(-1).squeeze(-1)
+        ELL = ELL - 0.5 * (EXXTx * EXTinvUX).sum(-1).sum(-1)
+    return ELL + 0.5 * wishart_ElogdetinvSigma(s["invU"]) - 0.5 * s["n"] * torch.log(2 * torch.tensor(torch.pi, dtype=mux.dtype))
+
+
+def mnw_stats_given(s, mux, EXXTx, muy, EXXTy, p):
+    """transforms/MatrixNormalWishart.py:143-170: the statistics of update(pX, pY, p) (no cross-covariance between the two
+    beliefs: SEyx uses the means only)."""
+    sample_shape = mux.shape[:-s["event_dim"] - s["batch_dim"]]
+    sd = tuple(range(len(sample_shape)))
+    if p is None:
+        N = torch.tensor(float(math.prod(sample_shape)), dtype=mux.dtype).expand(s["batch_shape"] + s["event_shape"][:-2])
+        w = lambda t: t.sum(sd)                                                  # noqa: E731
+    else:
+        N = p.sum(sd)
+        pv = p.view(p.shape + s["event_dim"] * (1,))
+        w = lambda t: (t * pv).sum(sd)                                           # noqa: E731
+    SExx, SEyy, SEyx = w(EXXTx), w(EXXTy), w(muy @ mux.transpose(-2, -1))
+    if s["pad_X"]:
+        SEx, SEy = w(mux), w(muy)
+        SExx = torch.cat((SExx, SEx), dim=-1)
+        SEx1 = torch.cat((SEx, N.view(N.shape + (1, 1))), dim=-2)
+        SExx = torch.cat((SExx, SEx1.transpose(-2, -1)), dim=-2)
+        SEyx = torch.cat((SEyx, SEy.expand(SEyx.shape[:-1] + (1,))), dim=-1)
+    return SExx, SEyx, SEyy, N
+
+
+def molt_update_given(m, mux, Sx, muy, Sy, lr=1.0):
+    """transforms/MixtureofLinearTransforms.py:62-69, 77-90: one E + M iteration of update(pX, pY) for beliefs with means
+    mux (N,p,1), muy (N,n,1) and covariances Sx, Sy.  Returns the ELBO (computed between E and M)."""
+    mx, my = mux.unsqueeze(-3), muy.unsqueeze(-3)
+    Exx = (Sx + mux @ mux.transpose(-2, -1)).unsqueeze(-3)
+    Eyy = (Sy + muy @ muy.transpose(-2, -1)).unsqueeze(-3)
+    log_p = mnw_elog_like_given(m["W"], mx, Exx, my, Eyy) + dirichlet_loggeomean(m["pi"])
+    shift = log_p.max(-1, True)[0]
+    pu = (log_p - shift).exp()
+    Z = pu.sum(-1, True)
+    m["p"] = pu / Z
+    m["logZ"] = (Z.log() + shift).squeeze(-1)
+    elbo = molt_elbo(m)
+    dirichlet_ss_update(m["pi"], m["p"].sum(0), lr=lr)
+    mnw_ss_update(m["W"], *mnw_stats_given(m["W"], mx, Exx, my, Eyy, m["p"]), lr=lr, beta=None)
+    m["ELBO_last"] = elbo
+    return elbo
+
+
 def mnw_predict(s, X):
     """transforms/MatrixNormalWishart.py:381-390 (pad_X branch :383-384): natural parameters of p(y | x) per component and
     the per-component log evidence Res - pY.Res() (dists/MultivariateNormal_vector_format.py:118-119).  X: (..., p, 1)."""

@@ -206,8 +206,80 @@ class MatrixNormalWishart():
         G, plan = self._gram(X, Y, p)
         self._update_from_gram(G, plan, p is not None, lr, beta)
 
+    def _beliefs_plan(self, pX, pY):
+        """Beliefs whose means look like raw data to the kernels: (sample..., 1, p, 1) / (sample..., 1, n, 1) on the device,
+        one component axis.  Returns (N, means, flattened covariances) or None."""
+        mx, my = pX.EX(), pY.EX()
+        p_in = self.p - int(self.pad_X)
+        if not (self.batch_dim == 1 and self.event_dim == 2 and mx.is_cuda and mx.ndim >= 4 and mx.shape[-3] == 1
+                and my.shape[-3] == 1 and mx.shape[:-3] == my.shape[:-3]):
+            return None
+        sample = tuple(mx.shape[:-3])
+        N = 1
+        for v in sample:
+            N *= v
+        Sx = pX.ESigma().expand(sample + (1, p_in, p_in)).reshape(N, p_in * p_in)
+        Sy = pY.ESigma().expand(sample + (1, self.n, self.n)).reshape(N, self.n * self.n)
+        return N, sample, mx, my, Sx, Sy
+
     def update(self, pX, pY, p=None, lr=1.0, beta=None):
-        raise NotImplementedError("expectation-input update is a 'next' row (SURVEY.md §8f #2)")
+        """transforms/MatrixNormalWishart.py:143-172: M-step from Gaussian beliefs about inputs and outputs.
+        E[xx^T] = Sigma_x + mu_x mu_x^T (same for y; the cross term uses the means only), so the statistics are the weighted
+        Gram pass (K3) over the MEANS plus the responsibility-weighted sums of the covariances — one skinny
+        (K x N) (N x p^2) product per belief, added into the x-x and y-y blocks before the update kernel."""
+        bp = self._beliefs_plan(pX, pY) if p is not None else None
+        if bp is not None:
+            N, sample, mx, my, Sx, Sy = bp
+            G, plan = self._gram(mx, my, p)
+            if plan.G == 1 and plan.GX == 1:
+                K, n = plan.K, self.n
+                p_in = self.p - int(self.pad_X)
+                D = p_in + n
+                P2 = _lib.f32(p, self.mu.device).reshape(N, K)
+                Cx, Cy = P2.t() @ Sx, P2.t() @ Sy
+                Gk = G.view(K, D + 1, D + 1)
+                Gk[:, :p_in, :p_in] += Cx.view(K, p_in, p_in)
+                Gk[:, p_in:D, p_in:D] += Cy.view(K, n, n)
+                self._update_from_gram(G, plan, p is not None, lr, beta)
+                return
+        # any other layout: the reference's op order on torch
+        sample_shape = pX.shape[:-self.event_dim - self.batch_dim]
+        sd = tuple(range(len(sample_shape)))
+        if p is None:
+            w = lambda t: t.sum(sd)                                              # noqa: E731
+            N = torch.tensor(float(torch.Size(sample_shape).numel()), device=self.mu.device)
+            N = N.expand(self.batch_shape + self.event_shape[:-2])
+        else:
+            N = p.sum(sd)
+            pv = p.view(p.shape + self.event_dim * (1,))
+            w = lambda t: (t * pv).sum(sd)                                       # noqa: E731
+        SExx, SEyy, SEyx = w(pX.EXXT()), w(pY.EXXT()), w(pY.EX() @ pX.EX().transpose(-2, -1))
+        if self.pad_X:
+            SEx, SEy = w(pX.EX()), w(pY.EX())
+            SExx = torch.cat((SExx, SEx), dim=-1)
+            SEx = torch.cat((SEx, N.view(N.shape + (1, 1))), dim=-2)
+            SExx = torch.cat((SExx, SEx.transpose(-2, -1)), dim=-2)
+            SEyx = torch.cat((SEyx, SEy.expand(SEyx.shape[:-1] + (1,))), dim=-1)
+        self.ss_update(SExx, SEyx, SEyy, N, lr=lr, beta=beta)
+
+    def Elog_like_given_pX_pY(self, pX, pY):
+        """transforms/MatrixNormalWishart.py:234-249.  The expected log likelihood is linear in E[xx^T], E[yy^T], so it is
+        the ordinary Elog_like at the means (K1 + K2) minus 1/2 tr(Sigma_y E[invSigma_k]) + 1/2 tr(Sigma_x E[X^T invU X]_k)
+        (the x-x block), two skinny products over the flattened covariances."""
+        base = self.Elog_like(pX.mean(), pY.mean())
+        p_in = self.p - int(self.pad_X)
+        Exx = self.EXTinvUX()[..., :p_in, :p_in]
+        bp = self._beliefs_plan(pX, pY)
+        if bp is not None and self.event_dim == 2:
+            N, sample, mx, my, Sx, Sy = bp
+            K = self.batch_shape[0]
+            corr = Sy @ self.EinvSigma().expand(K, self.n, self.n).reshape(K, -1).t() \
+                + Sx @ Exx.expand(K, p_in, p_in).reshape(K, -1).t()
+            return base - 0.5 * corr.view(sample + (K,))
+        corr = (pY.ESigma() * self.EinvSigma()).sum(-1).sum(-1) + (pX.ESigma() * Exx).sum(-1).sum(-1)
+        for i in range(self.event_dim - 2):
+            corr = corr.sum(-1)
+        return base - 0.5 * corr
 
     def KLqprior(self):
         """transforms/MatrixNormalWishart.py:206-216 -> vbmp_mnw_kl."""
@@ -233,10 +305,10 @@ class MatrixNormalWishart():
 
     def _out_of_scope(self, *a, **k):
         raise NotImplementedError("message-passing methods of MatrixNormalWishart are outside the VB-EM hot path "
-                                  "(SURVEY.md §2.1 #5, §8f #2-#3)")
+                                  "(SURVEY.md §2.1 #5)")
 
-    Elog_like_given_pX_pY = Elog_like_X = Elog_like_X_given_pY = Eforward = forward = backward = _out_of_scope
-    predict = postdict = predict_given_pX = Ebackward = forward_old = _out_of_scope
+    Elog_like_X = Elog_like_X_given_pY = Eforward = forward = backward = _out_of_scope
+    postdict = predict_given_pX = Ebackward = forward_old = _out_of_scope
 
     # ---- K-sized expectations (transforms/MatrixNormalWishart.py:400-471) ------------------------------
     def mean(self):

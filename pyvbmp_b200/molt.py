@@ -80,8 +80,33 @@ class MixtureofLinearTransforms():
                 print('MixLinearTransform: Percent Change in ELBO = ', ((ELBO - self.ELBO_last) / self.ELBO_last.abs()).data * 100)
             self.ELBO_last = ELBO
 
+    def update_assignments_given_pX_pY(self, pX, pY):
+        """transforms/MixtureofLinearTransforms.py:62-69: max-shifted softmax of the expected log likelihoods."""
+        log_p = self.W.Elog_like_given_pX_pY(pX.unsqueeze(-3), pY.unsqueeze(-3)) + self.pi.loggeomean()
+        self.logZ = torch.logsumexp(log_p, -1)
+        self.p = (log_p - self.logZ.unsqueeze(-1)).exp()
+        self.NA = None
+
+    def Elog_like_given_pX_pY(self, pX, pY):
+        """transforms/MixtureofLinearTransforms.py:71-75."""
+        ELL = (self.W.Elog_like(pX.unsqueeze(-3), pY.unsqueeze(-3)) * self.p).sum(-1)
+        for i in range(self.event_dim - 1):
+            ELL = ELL.sum(-1)
+        return ELL
+
     def update(self, pX, pY, iters=1, lr=1, verbose=False):
-        raise NotImplementedError("expectation-input update is a 'next' row (SURVEY.md §8f #2)")
+        """transforms/MixtureofLinearTransforms.py:77-90: VB-EM on Gaussian beliefs about inputs and outputs
+        (SURVEY.md §8f #2)."""
+        if sharding.enabled():
+            raise NotImplementedError("update(pX, pY) is not sample-sharded; use raw_update for sharded runs")
+        for i in range(iters):
+            self.update_assignments_given_pX_pY(pX, pY)
+            ELBO = self.ELBO()
+            self.pi.ss_update(self.p.sum(0), lr=lr)
+            self.W.update(pX.unsqueeze(-3), pY.unsqueeze(-3), p=self.p, lr=lr)
+            if verbose:
+                print('MixLinearTransform: Percent Change in ELBO = ', ((ELBO - self.ELBO_last) / self.ELBO_last.abs()).data * 100)
+            self.ELBO_last = ELBO
 
     PREDICT_ROWS = 1 << 16       # rows per block of the (rows, K, n) temporaries of the moment sums
 

@@ -29,6 +29,12 @@ class MultivariateNormal_vector_format():
     def shape(self):
         return self.batch_shape + self.event_shape
 
+    def unsqueeze(self, dim):
+        """A new belief with a singleton batch axis at `dim` (counted from the end, in front of the (dim, 1) event)."""
+        assert dim + self.event_dim < 0
+        un = lambda t: None if t is None else t.unsqueeze(dim)      # noqa: E731
+        return MultivariateNormal_vector_format(un(self.mu), un(self.Sigma), un(self.invSigmamu), un(self.invSigma))
+
     # ---- the two representations, each filled in from the other on demand ---------------------------------
     def ESigma(self):
         if self.Sigma is None:

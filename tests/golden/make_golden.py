@@ -289,6 +289,34 @@ def gen_molt_predict():
         save(name, **out)
 
 
+def gen_molt_given():
+    """Expectation-input E and M steps: MatrixNormalWishart.Elog_like_given_pX_pY / update(pX, pY, p) and
+    MixtureofLinearTransforms.update(pX, pY) with Gaussian beliefs about the inputs and outputs."""
+    from dists.MultivariateNormal_vector_format import MultivariateNormal_vector_format as MVN
+    g = torch.Generator().manual_seed(47)
+    for name, n, p, K, N, lr in (("molt_given_n3_p4_k5", 3, 4, 5, 500, 1.0), ("molt_given_n8_p16_k6", 8, 16, 6, 640, 0.5)):
+        torch.manual_seed(14)
+        m = transforms.MixtureofLinearTransforms(n, p, K, pad_X=True)
+        X = torch.randn(N, p, generator=g)
+        Wt = torch.randn(K, n, p, generator=g) / np.sqrt(p)
+        b = torch.randn(K, n, generator=g)
+        z = torch.randint(K, (N,), generator=g)
+        Y = torch.einsum("nij,nj->ni", Wt[z], X) + b[z] + 0.1 * torch.randn(N, n, generator=g)
+        m.raw_update(X.unsqueeze(-1), Y.unsqueeze(-1), iters=3, lr=1.0)
+        Ax = 0.2 * torch.randn(N, p, p, generator=g)
+        Ay = 0.1 * torch.randn(N, n, n, generator=g)
+        Sx = Ax @ Ax.transpose(-1, -2) + 0.01 * torch.eye(p)
+        Sy = Ay @ Ay.transpose(-1, -2) + 0.01 * torch.eye(n)
+        out = {"mux": T(X), "Sx": T(Sx), "muy": T(Y), "Sy": T(Sy), "n": n, "p": p, "K": K, "lr": lr}
+        out.update(tagged(molt_state(m), "state"))
+        pX, pY = MVN(mu=X.unsqueeze(-1), Sigma=Sx), MVN(mu=Y.unsqueeze(-1), Sigma=Sy)
+        out["given/ELL"] = T(m.W.Elog_like_given_pX_pY(pX.unsqueeze(-3), pY.unsqueeze(-3)))
+        m.update(pX, pY, iters=1, lr=lr)
+        out.update(tagged(molt_state(m), "after"))
+        out["after/p"], out["after/logZ"], out["after/ELBO"] = T(m.p), T(m.logZ), np.float64(float(m.ELBO_last))
+        save(name, **out)
+
+
 def gen_arhmm():
     g = torch.Generator().manual_seed(51)
     K, n, p, Tn, S = 4, 2, 3, 40, 25
@@ -334,4 +362,5 @@ if __name__ == "__main__":
     gen_mnw()
     gen_molt()
     gen_molt_predict()
+    gen_molt_given()
     gen_arhmm()

@@ -274,6 +274,31 @@ def test_molt_predict_golden(name):
     assert_close(pYb.ESigma().cpu().double(), Sig_r, 5 * PARITY, "predictive covariance (oracle)")
 
 
+@pytest.mark.parametrize("name", ["molt_given_n3_p4_k5", "molt_given_n8_p16_k6"])
+def test_molt_given_beliefs_golden(name):
+    """Expectation-input E and M steps: Elog_like_given_pX_pY and update(pX, pY) against the reference's
+    own outputs; the means go through the E-step / Gram kernels, the covariances through two skinny products."""
+    fix = load_golden(name)
+    n, p, K, lr = int(fix["n"]), int(fix["p"]), int(fix["K"]), float(fix["lr"])
+    torch.manual_seed(0)
+    m = V.MixtureofLinearTransforms(n, p, K).to(DEV)
+    set_state(m, tag(fix, "state"))
+    t = lambda k: torch.as_tensor(fix[k]).to(DEV)                                   # noqa: E731
+    pX = V.MultivariateNormal_vector_format(mu=t("mux").unsqueeze(-1), Sigma=t("Sx"))
+    pY = V.MultivariateNormal_vector_format(mu=t("muy").unsqueeze(-1), Sigma=t("Sy"))
+    ELL = m.W.Elog_like_given_pX_pY(pX.unsqueeze(-3), pY.unsqueeze(-3))
+    ref_ELL = tag(fix, "given")["ELL"]
+    assert ELL.shape == ref_ELL.shape
+    assert_close(ELL, ref_ELL, PARITY, "Elog_like_given_pX_pY")
+    m.update(pX, pY, iters=1, lr=lr)
+    aft = tag(fix, "after")
+    assert abs(float(m.ELBO_last) - float(fix["after/ELBO"])) <= PARITY * abs(float(fix["after/ELBO"]))
+    assert_maxabs(m.p.cpu(), aft["p"], 2e-4, "responsibilities")
+    assert_close(m.logZ, aft["logZ"], PARITY, "logZ_n")
+    for k in ("W.mu", "W.invV", "W.V", "W.invU.invU", "W.invU.U", "W.invU.nu", "pi.alpha"):
+        assert_close(get(m, k), aft[k], PARITY, k)
+
+
 def test_arhmm_golden():
     fix = load_golden("arhmm_k4_n2_p3")
     K, n, p = int(fix["K"]), int(fix["n"]), int(fix["p"])

@@ -208,6 +208,29 @@ def test_molt_predict(name, f64):
     assert_close(Sigma, pf["Sigma"], 5 * PARITY, "predict covariance")       # formed as a difference of second moments
 
 
+@pytest.mark.parametrize("name", ["molt_given_n3_p4_k5", "molt_given_n8_p16_k6"])
+def test_molt_given_beliefs(name):
+    """Expectation-input E and M steps (transforms/MatrixNormalWishart.py:143-172, 234-249;
+    transforms/MixtureofLinearTransforms.py:62-90)."""
+    fix = load_golden(name)
+    n, p, K, lr = int(fix["n"]), int(fix["p"]), int(fix["K"]), float(fix["lr"])
+    m = O.molt_new(n, p, K)
+    O.load_state(m, tag(fix, "state"))
+    mux, muy = torch.as_tensor(fix["mux"]).unsqueeze(-1), torch.as_tensor(fix["muy"]).unsqueeze(-1)
+    Sx, Sy = torch.as_tensor(fix["Sx"]), torch.as_tensor(fix["Sy"])
+    Exx = (Sx + mux @ mux.transpose(-2, -1)).unsqueeze(-3)
+    Eyy = (Sy + muy @ muy.transpose(-2, -1)).unsqueeze(-3)
+    ELL = O.mnw_elog_like_given(m["W"], mux.unsqueeze(-3), Exx, muy.unsqueeze(-3), Eyy)
+    assert_close(ELL, tag(fix, "given")["ELL"], 2e-5, "Elog_like_given_pX_pY")
+    elbo = O.molt_update_given(m, mux, Sx, muy, Sy, lr=lr)
+    aft = tag(fix, "after")
+    assert abs(float(elbo) - float(fix["after/ELBO"])) <= PARITY * abs(float(fix["after/ELBO"]))
+    assert float((m["p"] - aft["p"]).abs().max()) < 5e-5
+    assert_close(m["logZ"], aft["logZ"], 2e-5, "logZ_n")
+    for k in ("W.mu", "W.invV", "W.V", "W.invU.invU", "W.invU.U", "W.invU.nu", "pi.alpha"):
+        assert_close(O.flatten_state(m)[k], aft[k], PARITY, k)
+
+
 @pytest.mark.parametrize("exact", [True, False])
 def test_arhmm_trajectory(exact):
     fix = load_golden("arhmm_k4_n2_p3")
