@@ -741,6 +741,28 @@ def arhmm_update(h, X, Y, iters=1, lr=1.0, beta=None, exact=True):
     return trace
 
 
+def arhmm_prxy_update(h, mux, Sx, muy, Sy, iters=1, lr=1.0, beta=None):
+    """models/HMM.py:141-152 with models/ARHMM.py:35-46 (ARHMM_prXY): observation logits from Elog_like_given_pX_pY, the
+    observation update from update(pX, pY, p).  Beliefs: means (T,S,1,p,1) / (T,S,1,n,1), covariances (T,S,1,p,p) / (T,S,1,n,n)."""
+    W = h["obs"]
+    Exx = Sx + mux @ mux.transpose(-2, -1)
+    Eyy = Sy + muy @ muy.transpose(-2, -1)
+    trace = []
+    for _ in range(iters):
+        p, SEzz, SEz0, logZ = hmm_forward_backward_logits(h, mnw_elog_like_given(W, mux, Exx, muy, Eyy))
+        h["p"] = p
+        NA = p.sum(0)
+        sd = list(range(NA.ndim - 1))
+        h["NA"], SEzz, SEz0, h["logZ"] = NA.sum(sd), SEzz.sum(sd), SEz0.sum(sd), logZ.sum(sd)
+        dirichlet_ss_update(h["transition"], SEzz, lr=lr, beta=beta)
+        dirichlet_ss_update(h["initial"], SEz0, lr=lr, beta=beta)
+        mnw_ss_update(W, *mnw_stats_given(W, mux, Exx, muy, Eyy, p), lr=lr, beta=beta)
+        elbo = h["logZ"] - hmm_kl(h, mnw_kl(W))
+        h["ELBO_last"] = elbo
+        trace.append(elbo)
+    return trace
+
+
 # --------------------------------------------------------------------------------------
 # state (de)serialisation helpers used by the golden fixtures and the GPU parity tests
 # --------------------------------------------------------------------------------------

@@ -11,7 +11,7 @@ from .dirichlet import Dirichlet
 from .mixture import Mixture, GaussianMixtureModel
 from .molt import MixtureofLinearTransforms
 from .mvn import MultivariateNormal_vector_format
-from .hmm import HMM, ARHMM
+from .hmm import HMM, ARHMM, ARHMM_prXY
 from .install import install, uninstall
 from . import sharding
 from ._lib import VbmpError, LIB_PATH

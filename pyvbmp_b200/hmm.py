@@ -180,3 +180,26 @@ class ARHMM(HMM):
     def update_obs_parms(self, XY, lr, beta):
         """models/ARHMM.py:24-25."""
         self.obs_dist.raw_update(XY[0], XY[1], p=self.p, lr=lr, beta=beta)
+
+
+class ARHMM_prXY(HMM):
+    """models/ARHMM.py:35-46: the ARHMM driven by Gaussian beliefs (pX, pY) about regressors and outputs instead of raw data
+    (SURVEY.md §8f #2).  Observation logits are the expected log likelihoods, the observation update uses expected
+    sufficient statistics; both run on the E-step / Gram kernels over the means plus covariance corrections."""
+
+    def __init__(self, dim, n, p, batch_shape=(), X_mask=None, mask=None, pad_X=True, transition_mask=None):
+        dist = MatrixNormalWishart(event_shape=(n, p), batch_shape=batch_shape + (dim,), pad_X=pad_X,
+                                   X_mask=X_mask, mask=mask)
+        super().__init__(dist, transition_mask=transition_mask)
+
+    def obs_logits(self, XY, t=None):
+        if t is not None:
+            raise NotImplementedError("time-sliced beliefs (HMM.update with T) are not supported for ARHMM_prXY")
+        return self.obs_dist.Elog_like_given_pX_pY(XY[0], XY[1])
+
+    def update_obs_parms(self, XY, lr, beta=None):
+        self.obs_dist.update(XY[0], XY[1], self.p, lr=lr, beta=beta)
+
+    def Elog_like_X_given_pY(self, pY):
+        raise NotImplementedError("message passing to X is outside the VB-EM hot path (SURVEY.md §2.1 #5)")
+

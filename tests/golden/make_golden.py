@@ -356,6 +356,48 @@ def gen_arhmm():
     save("arhmm_k4_n2_p3", **out)
 
 
+def gen_arhmm_prxy():
+    """models.ARHMM.ARHMM_prXY (models/ARHMM.py:35-46): the ARHMM driven by Gaussian beliefs about regressors and outputs."""
+    from dists.MultivariateNormal_vector_format import MultivariateNormal_vector_format as MVN
+    from models.ARHMM import ARHMM_prXY
+    g = torch.Generator().manual_seed(53)
+    K, n, p, Tn, S = 4, 2, 3, 40, 12
+    Atrue = torch.randn(K, n, p, generator=g)
+    btrue = torch.randn(K, n, generator=g)
+    trans = torch.full((K, K), 0.1 / (K - 1)) + torch.eye(K) * (0.9 - 0.1 / (K - 1))
+    z = torch.zeros(Tn, S, dtype=torch.long)
+    z[0] = torch.randint(K, (S,), generator=g)
+    for t in range(1, Tn):
+        z[t] = torch.multinomial(trans[z[t - 1]], 1, generator=g).squeeze(-1)
+    X = torch.randn(Tn, S, p, generator=g)
+    Y = torch.einsum("tsij,tsj->tsi", Atrue[z], X) + btrue[z] + 0.2 * torch.randn(Tn, S, n, generator=g)
+    Ax, Ay = 0.2 * torch.randn(Tn, S, 1, p, p, generator=g), 0.1 * torch.randn(Tn, S, 1, n, n, generator=g)
+    Sx = Ax @ Ax.transpose(-1, -2) + 0.01 * torch.eye(p)
+    Sy = Ay @ Ay.transpose(-1, -2) + 0.01 * torch.eye(n)
+    mux, muy = X.unsqueeze(-2).unsqueeze(-1), Y.unsqueeze(-2).unsqueeze(-1)        # (T,S,1,p,1), (T,S,1,n,1)
+    torch.manual_seed(16)
+    m = ARHMM_prXY(K, n, p)
+    out = {"mux": T(mux), "Sx": T(Sx), "muy": T(muy), "Sy": T(Sy), "K": K, "n": n, "p": p}
+
+    def st():
+        s = mnw_state(m.obs_dist, "obs.")
+        s.update(dir_state(m.transition, "transition."))
+        s.update(dir_state(m.initial, "initial."))
+        return s
+    out.update(tagged(st(), "init"))
+    pX, pY = MVN(mu=mux, Sigma=Sx), MVN(mu=muy, Sigma=Sy)
+    out["init/obs_logits"] = T(m.obs_logits((pX, pY)))
+    el = []
+    for i in range(3):
+        m.update((pX, pY), iters=1, lr=1.0)
+        el.append(float(m.ELBO_last))
+        if i == 0:
+            out.update(tagged(st(), "iter1"))
+            out["iter1/p"], out["iter1/logZ"], out["iter1/NA"] = T(m.p), T(m.logZ), T(m.NA)
+    out["ELBO"] = np.asarray(el, dtype=np.float64)
+    save("arhmm_prxy_k4_n2_p3", **out)
+
+
 if __name__ == "__main__":
     gen_gmm()
     gen_niw_variants()
@@ -364,3 +406,4 @@ if __name__ == "__main__":
     gen_molt_predict()
     gen_molt_given()
     gen_arhmm()
+    gen_arhmm_prxy()

@@ -323,6 +323,33 @@ def test_arhmm_golden():
     assert np.max(np.abs(np.array(elbo) - fix["ELBO"]) / np.abs(fix["ELBO"])) < PARITY
 
 
+def test_arhmm_prxy_golden():
+    """ARHMM_prXY (models/ARHMM.py:35-46) against the reference's own outputs."""
+    fix = load_golden("arhmm_prxy_k4_n2_p3")
+    K, n, p = int(fix["K"]), int(fix["n"]), int(fix["p"])
+    torch.manual_seed(0)
+    h = V.ARHMM_prXY(K, n, p).to(DEV)
+    set_state(h, {k.replace("obs.", "obs_dist."): v for k, v in tag(fix, "init").items()})
+    t = lambda k: torch.as_tensor(fix[k]).to(DEV)                                   # noqa: E731
+    pX = V.MultivariateNormal_vector_format(mu=t("mux"), Sigma=t("Sx"))
+    pY = V.MultivariateNormal_vector_format(mu=t("muy"), Sigma=t("Sy"))
+    ol = h.obs_logits((pX, pY))
+    assert ol.shape == fix["init/obs_logits"].shape
+    assert_close(ol, fix["init/obs_logits"], PARITY, "obs_logits")
+    h.update((pX, pY), iters=1)
+    it1 = tag(fix, "iter1")
+    assert_maxabs(h.p.cpu(), it1["p"], 2e-4, "h.p.cpu()")
+    assert_close(h.logZ, it1["logZ"], PARITY, "logZ")
+    assert_close(h.NA, it1["NA"], PARITY, "NA")
+    for k in ("obs.mu", "obs.invV", "obs.V", "obs.invU.invU", "obs.invU.U", "transition.alpha", "initial.alpha"):
+        assert_close(get(h, k.replace("obs.", "obs_dist.")), it1[k], PARITY, k)
+    elbo = [float(h.ELBO_last)]
+    for _ in range(2):
+        h.update((pX, pY), iters=1)
+        elbo.append(float(h.ELBO_last))
+    assert np.max(np.abs(np.array(elbo) - fix["ELBO"]) / np.abs(fix["ELBO"])) < PARITY
+
+
 # -------------------------------------------------------------------------------------------------
 # config-2 shape (d=64, K=256) against the fp64 oracle, overlapping-clusters variant (SURVEY App. F)
 # -------------------------------------------------------------------------------------------------

@@ -208,6 +208,28 @@ def test_molt_predict(name, f64):
     assert_close(Sigma, pf["Sigma"], 5 * PARITY, "predict covariance")       # formed as a difference of second moments
 
 
+def test_arhmm_prxy_trajectory():
+    """ARHMM_prXY (models/ARHMM.py:35-46): HMM forward-backward on expectation-input observation logits."""
+    fix = load_golden("arhmm_prxy_k4_n2_p3")
+    K, n, p = int(fix["K"]), int(fix["n"]), int(fix["p"])
+    h = O.arhmm_new(K, n, p)
+    O.load_state(h, tag(fix, "init"))
+    t = lambda k: torch.as_tensor(fix[k])                                           # noqa: E731
+    mux, Sx, muy, Sy = t("mux"), t("Sx"), t("muy"), t("Sy")
+    ol = O.mnw_elog_like_given(h["obs"], mux, Sx + mux @ mux.transpose(-2, -1), muy, Sy + muy @ muy.transpose(-2, -1))
+    assert_close(ol, fix["init/obs_logits"], 2e-5, "obs_logits")
+    trace = O.arhmm_prxy_update(h, mux, Sx, muy, Sy, iters=1)
+    it1 = tag(fix, "iter1")
+    assert float((h["p"] - it1["p"]).abs().max()) < 5e-5
+    assert_close(h["logZ"], it1["logZ"], PARITY, "logZ")
+    assert_close(h["NA"], it1["NA"], PARITY, "NA")
+    for k in ("obs.mu", "obs.invV", "obs.invU.invU", "transition.alpha", "initial.alpha"):
+        assert_close(O.flatten_state(h)[k], it1[k], PARITY, k)
+    trace += O.arhmm_prxy_update(h, mux, Sx, muy, Sy, iters=2)
+    got = np.array([float(e) for e in trace])
+    assert np.max(np.abs(got - fix["ELBO"]) / np.abs(fix["ELBO"])) < PARITY
+
+
 @pytest.mark.parametrize("name", ["molt_given_n3_p4_k5", "molt_given_n8_p16_k6"])
 def test_molt_given_beliefs(name):
     """Expectation-input E and M steps (transforms/MatrixNormalWishart.py:143-172, 234-249;
