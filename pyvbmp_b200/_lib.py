@@ -125,6 +125,14 @@ def _workspace(nbytes, dev):
     return buf
 
 
+def release_workspaces():
+    """Drop the cached scratch buffers (kernel workspaces and the K2 -> K3 hand-over images; ~10 GB at cfg2).  They are
+    grow-only and per (device, stream); call this between workloads of very different size."""
+    _ws_cache.clear()
+    _rpack_cache.clear()
+    _rpack_rec.clear()
+
+
 # ------------------------------------------------------------------------------------------------
 # thin typed wrappers (all tensors contiguous fp32 CUDA unless noted)
 # ------------------------------------------------------------------------------------------------
