@@ -6,23 +6,26 @@
 //                                                           MixtureofLinearTransforms.update_assignments :34-41)
 //
 // Design (numbers from tools/umma_probe.cu on a B200, see umma.cuh):
-//   * persistent CTA per SM, 256-sample tiles (two 128-row halves).  The sample tile is the A operand and
-//     lives in TENSOR MEMORY as split-precision TF32 (z = hi + lo): with A in TMEM an M=128 x N x K=8 MMA
-//     issues every N/2 cycles, whereas a shared-memory A costs 32 extra cycles of operand fetch.
-//   * the whitening factors are the B operand: one 128-column group (CG = 128/DP components) per pipeline
-//     stage, pre-split into hi / lo TF32 and pre-arranged in the K-major core-matrix layout by a pack kernel,
-//     so a stage (plus the group's m and cst) is ONE cp.async.bulk.  Each stage is used by both halves
-//     (hi*hi + lo*hi + hi*lo per half and K-step), which halves the L2 -> shared-memory stream per flop.
-//   * W_k is upper triangular.  The group's columns are interleaved in 8-column blocks,
-//     n = (j/8)*(8 CG) + cl*8 + j%8, so the columns K-step ks can reach (j >= 8 ks) are the contiguous suffix
-//     n >= 8 CG ks: the MMA is issued with N = 128 - 8 CG ks on that suffix and only that suffix of B is
-//     stored / copied (56 % of the dense work at DP = 64).
-//   * one 128-column accumulator per half in TMEM; the halves ping-pong (the epilogue of half 0 runs under the
-//     MMAs of half 1).  The accumulator is initialised to -m_k by one extra K-step (a constant block of ones against
-//     [-m_hi; -m_lo], the only shared-memory A operand), so the 8 epilogue warps (one thread per sample row) only read
-//     D with tcgen05.ld, square-reduce with packed fp32x2 FFMA2, keep an online logsumexp and write the logits.  For mode 1 the tile's rows are then
-//     normalised in place (the re-read hits L2) with coalesced float4 accesses, accumulating NA per CTA in a
-//     fixed order (deterministic).
+//   * persistent CTA per SM, 256-sample tiles (two 128-row halves).  The sample tile is the A operand and lives in TENSOR
+//     MEMORY as two split-precision images (z = hi + lo): with A in TMEM the MMA issue rate is set by N alone, whereas a
+//     shared-memory A costs 32 extra cycles of operand fetch per MMA.
+//   * the whitening factors are the B operand: one 128-column group (CG = 128/DP components) per pipeline stage,
+//     pre-split into two images and pre-arranged in the K-major core-matrix layout by a pack kernel, so a stage (plus the
+//     group's -m block, cst and scales) is ONE cp.async.bulk.  Each stage is used by both halves (hi*hi + lo*hi + hi*lo
+//     per half and K-step), which halves the L2 -> shared-memory stream per flop.
+//   * W_k is upper triangular.  The group's columns are interleaved in 8-column blocks, n = (j/8)*(8 CG) + cl*8 + j%8,
+//     so the columns K-step ks can reach (j >= KSTEP ks) are the contiguous suffix n >= KSTEP CG ks: the MMA is issued
+//     with N = 128 - KSTEP CG ks on that suffix and only that suffix of B is stored / copied (DP = 64: 62.5 % of the
+//     dense work with KSTEP = 16, 56 % with KSTEP = 8).
+//   * 128-column fp32 accumulators in TMEM, rotating over the (group, half) sequence (two with TF32 operands, three
+//     with fp16 ones); the two MMA-issuing warps (one per half) take strict turns, so the epilogue of one half runs
+//     under the MMAs of the other.  Each burst starts with one TF32 MMA of a small shared-memory A block (1, or the
+//     row's scale) against [-m_hi; -m_lo], which initialises the accumulator to -m: the 8 epilogue warps (one thread per
+//     sample row) only read D with tcgen05.ld, square-reduce with packed fp32x2 FFMA2, keep an online logsumexp and write
+//     the logits.
+//   * mode 1: a 12th warp normalises tile t (p = exp(l - logZ_n), in place, L2 hits, coalesced float4, ex2.approx) while
+//     the MMAs of tile t + 1 run, keeps NA of its fixed columns in a fixed order (deterministic) and, on request, also
+//     writes the responsibilities pre-split into the Gram kernel's fp16 operand images (EstepArgs::rpack).
 //
 // Operand precision (template parameter F16, the default; VBMP_ESTEP_PREC=tf32 selects the other):
 //   * TF32: z and W are split hi + lo into TF32 (3 MMAs with K = 8 per K-step; the tensor core truncates lo to 10 bits,
@@ -594,11 +597,9 @@ estep_umma_kernel(EstepArgs a, const uint8_t* __restrict__ Wp, const float* __re
     };
     for (int t = 0; t < my_tiles; ++t) {
       mbar_wait(&S->ndone[t & 1], (uint32_t)(t >> 1) & 1);
-#ifndef EU_DBG_NONORM
       if (K4 <= 32) norm_tile(std::integral_constant<int, 1>{}, t);
       else if (K4 <= 64) norm_tile(std::integral_constant<int, 2>{}, t);
       else norm_tile(std::integral_constant<int, 4>{}, t);
-#endif
       __syncwarp();
       if (lane == 0) mbar_arrive(&S->nfree[t & 1]);
     }

@@ -11,17 +11,18 @@
 // it, needs no per-component rescaling of the sample tile: phi is shared by every component.
 //
 //   * CTA task = (128-component block) x (NPB <= 224 pair columns) x (sample split); with an even number of component
-//     blocks two CTAs pair up (cta_group::2, M = 256, NPB <= 192 shared between them).  A operand = R^T
-//     (lanes = components, K = samples) written to TENSOR MEMORY by the workers as split TF32 (hi, lo);
-//     B operand = phi^T generated on the fly in shared memory (K-major core-matrix layout, hi / lo).
-//     D1 (first-level accumulator) and D2 (second level) both live in TMEM: D1 is folded into D2 (fp32
-//     round-to-nearest adds on the CUDA cores) every 256 samples, at zero memory traffic.  The tensor core
-//     TRUNCATES on every fp32 accumulate: measured bias -1.0e-7 of the running sum per 16-sample chunk
+//     blocks two CTAs pair up (cta_group::2, M = 256, NPB <= 192 shared between them; the last pair block is only as
+//     wide as the pairs it holds).  A operand = R^T (lanes = components, K = samples) in TENSOR MEMORY as two
+//     split-precision images; B operand = phi^T generated on the fly in shared memory (K-major core-matrix layout,
+//     two images).  D1 (first-level accumulator) and D2 (second level) both live in TMEM: D1 is folded into D2 (fp32
+//     round-to-nearest adds on the CUDA cores) every 16 chunks, at zero memory traffic.  The tensor core TRUNCATES
+//     on every fp32 accumulate: measured bias -1.0e-7 of the running sum per 16-sample TF32 chunk
 //     (tools/gram_bias.py), i.e. -1.6e-6 at 16 chunks per block, -1.3e-5 at 128; hence the short blocks
 //     (SURVEY.md Appendix F.2 anticipated this).
-//   * raw R / Z chunks (16 samples) are brought in by TMA tiled loads (one box per operand, zero-filled past
-//     the last row) into a 4-deep ring (warp 0), the MMAs are
-//     issued by warp 1 (3 split-precision terms x 2 K-steps per chunk), 8 worker warps split / multiply.
+//   * warp 0 brings the chunk operands into a 6-deep ring (TF32: TMA tiled loads of the raw R / Z rows, zero-filled past
+//     the last row; fp16: two bulk copies of the pre-split weight images and the transposed, pre-scaled samples),
+//     warp 1 issues the MMAs (3 split-precision terms x 2 K-steps per chunk), two sets of 8 worker warps alternate
+//     chunks: copy / split the A images into TMEM, multiply and split phi into the B stage.
 //   * per-split partials are reduced in a fixed order in fp64 by gram_pair_reduce_kernel (deterministic).
 //
 // Operand precision (template parameter F16; the default, VBMP_GRAM_PREC=tf32 selects the TF32 split only):
