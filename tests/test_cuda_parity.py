@@ -452,6 +452,56 @@ def test_large_n_properties():
     assert relerr(S_got, S_ref) < 2e-5
 
 
+def test_cfg2_full_size_properties():
+    """BASELINE.json configs[1] at full size (N = 4 194 304, d = 64, K = 256): properties that need no oracle."""
+    N, K, d = 1 << 22, 256, 64
+    g = torch.Generator(device=DEV).manual_seed(7)
+    mu = 3.0 * torch.randn(K, d, generator=g, device=DEV)
+    X = torch.empty(N, d, device=DEV)
+    for a in range(0, N, 1 << 20):
+        X[a:a + (1 << 20)] = mu[torch.randint(K, (1 << 20,), generator=g, device=DEV)] + \
+            torch.randn(1 << 20, d, generator=g, device=DEV)
+    torch.manual_seed(3)
+    m = V.GaussianMixtureModel(K, d)
+    m.initialize(X[:65536].cpu())
+    m.to(DEV)
+    elbo = []
+    for _ in range(3):
+        m.update(X, 1)
+        elbo.append(float(m.ELBO_last))
+    assert all(np.isfinite(elbo))
+    assert elbo[1] >= elbo[0] - 1e-6 * abs(elbo[0]) and elbo[2] >= elbo[1] - 1e-6 * abs(elbo[1])     # VB-EM is monotone
+    m.update_assignments(X)
+    p, NA = m.p, m.NA
+    rs = p.sum(-1)
+    assert_maxabs(rs, torch.ones_like(rs), 2e-5, "rows of p sum to 1")
+    assert abs(float(NA.double().sum()) - N) < 1e-6 * N
+    assert_close(NA, p.double().sum(0), 1e-5, "NA vs p.sum")
+    assert abs(float(m.logZ) - float(m.logZ_n.double().sum() if hasattr(m, "logZ_n") else m.logZ)) <= 1e-5 * abs(float(m.logZ))
+    # chunk independence of the E-step (bitwise)
+    p_full = p.clone()
+    m.update_assignments(X[: N // 2 + 12345])
+    assert torch.equal(m.p, p_full[: N // 2 + 12345])
+    m.update_assignments(X)
+    # the Gram from the images the E-step handed over equals the Gram that splits the same p itself, bit for bit;
+    # it is exactly symmetric, its corner is NA, and it matches an fp64 evaluation on one component
+    from pyvbmp_b200 import _lib, _shapes
+    xg = _shapes.idx_tensor((0,), X.device)
+    G1 = _lib.gram(X.view(N, 1, d), None, N, 1, xg, m.p.view(N, 1, K), 1, xg, 1, K, _lib.pad_dim(d)).clone()
+    G2 = _lib.gram(X.view(N, 1, d), None, N, 1, xg, m.p.clone().view(N, 1, K), 1, xg, 1, K, _lib.pad_dim(d))
+    assert torch.equal(G1, G2)
+    G = G1[0]
+    assert torch.equal(G, G.transpose(-1, -2))
+    assert_close(G[:, d, d], m.NA, 1e-5, "Gram corner vs NA")
+    k0 = int(m.NA.argmax())
+    Z1 = torch.cat([X, torch.ones(N, 1, device=DEV)], -1)
+    ref = torch.zeros(d + 1, d + 1, dtype=torch.float64, device=DEV)
+    for a in range(0, N, 1 << 19):
+        z = Z1[a:a + (1 << 19)].double()
+        ref += (z * m.p[a:a + (1 << 19), k0].double().unsqueeze(-1)).t() @ z
+    assert relerr(G[k0], ref) < 8e-6
+
+
 def test_streamed_host_rows_match_device_rows():
     """Mixture.update(X_host) (chunked H2D overlapped with the kernels) = Mixture.update(X_device)."""
     N, K, d = 1_300_000, 64, 32
