@@ -54,9 +54,15 @@ constexpr int GU_NR = GU_NR_V;       // raw ring depth
 // pipeline depth (B stages in shared memory = A buffers in TMEM) and pair columns per MMA.  TMEM budget: D1 + D2 = 2 NPMAX
 // columns + NSTG A buffers of hi + lo = 32 NSTG columns <= 512.  A CTA pair needs 4 stages to hide the cross-CTA barrier
 // round trips (192 columns); a single CTA is best with 2 stages and 224 columns.
-constexpr int GU_MAXSTG = 4;
-__host__ __device__ constexpr int gu_nstg(bool pair) { return pair ? 4 : 2; }
-__host__ __device__ constexpr int gu_npmax(bool pair) { return pair ? 192 : 224; }
+// (measured at cfg2, whole call: 4 stages x 192 columns 10.5 ms, 5 x 176 10.8 ms, 6 x 160 11.2 ms)
+#ifndef GU_PAIR_NSTG
+#define GU_PAIR_NSTG 4
+#define GU_PAIR_NPMAX 192
+#endif
+constexpr int GU_MAXSTG = 6;
+__host__ __device__ constexpr int gu_nstg(bool pair) { return pair ? GU_PAIR_NSTG : 2; }
+__host__ __device__ constexpr int gu_npmax(bool pair) { return pair ? GU_PAIR_NPMAX : 224; }
+static_assert(2 * GU_PAIR_NPMAX + 32 * GU_PAIR_NSTG <= 512, "TMEM budget of a CTA pair");
 constexpr int GU_FL = 16;            // chunks per first-level accumulation block (256 samples)
 constexpr int GU_CB = 128;           // components per CTA
 
