@@ -16,7 +16,7 @@
 extern "C" {
 #endif
 
-#define VBMP_ABI_VERSION 1
+#define VBMP_ABI_VERSION 2
 
 int vbmp_version(void);
 const char* vbmp_last_error(void);
@@ -76,6 +76,24 @@ int vbmp_estep_rpack(const float* z0, int d0, const float* z1, int d1, long long
 int vbmp_gram_rpack(const float* z0, int d0, const float* z1, int d1, long long N, int GX, const int* xg,
                     const float* p, int GP, const int* pg, int G, int K, int Dp, int flags,
                     float* gram, void* workspace, size_t workspace_bytes, void* stream, const void* rpack);
+
+/* ---- K3 sample image (optional) ---------------------------------------------------------------------------
+ * The rows of an EM run are the same every iteration (Mixture.update passes the same X to every update_assignments /
+ * update_parms, dists/Mixture.py:54-62; MixtureofLinearTransforms.raw_update likewise, :50-61), so the layout K3's
+ * tcgen05 fp16 kernel reads them in — column maxima -> exact power-of-two feature scales, then [z0 | z1 | 1] scaled and
+ * transposed per 32-sample chunk — can be made once per data set instead of once per call.  vbmp_gram_zpack writes that
+ * image (vbmp_zpack_bytes(N, d0, d1) bytes, caller-owned; *packed = 0 when the kernels that take this shape do not use
+ * one); vbmp_gram_ex is vbmp_gram given the weight images (rpack, see above) and / or the sample image (zpack), either
+ * may be NULL; its workspace (vbmp_gram_ex_workspace_bytes) omits the images that are handed in.  The caller must pass
+ * images made from exactly the p / z0 / z1 of the call.                                                              */
+size_t vbmp_zpack_bytes(long long N, int d0, int d1);
+int vbmp_gram_zpack(const float* z0, int d0, const float* z1, int d1, long long N, int K, int Dp,
+                    void* zpack, size_t zpack_bytes, int* packed, void* stream);
+size_t vbmp_gram_ex_workspace_bytes(long long N, int G, int K, int d0, int d1, int Dp, int has_rpack, int has_zpack);
+int vbmp_gram_ex(const float* z0, int d0, const float* z1, int d1, long long N, int GX, const int* xg,
+                 const float* p, int GP, const int* pg, int G, int K, int Dp, int flags,
+                 float* gram, void* workspace, size_t workspace_bytes, void* stream,
+                 const void* rpack, const void* zpack);
 
 /* ---- K5: natural-parameter updates (replicated; statistics are post-beta) -----------------------------
  * Wishart.ss_update — dists/Wishart.py:43-56.                                                          */

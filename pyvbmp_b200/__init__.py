@@ -12,7 +12,7 @@ from .mixture import Mixture, GaussianMixtureModel
 from .molt import MixtureofLinearTransforms
 from .mvn import MultivariateNormal_vector_format
 from .hmm import HMM, ARHMM, ARHMM_prXY
-from .install import install, uninstall
+from .install import install, uninstall, installed_classes
 from . import sharding
 from ._lib import VbmpError, LIB_PATH
 

@@ -20,7 +20,13 @@ FORCE_SIMT = int(os.environ.get("VBMP_FORCE_SIMT", "0"))   # tests: 1 = CUDA-cor
 
 PROFILE = None     # bench.py sets this to {} to collect (start, end) CUDA events per C-ABI call
 LAUNCHES = 0       # kernels launched through the C ABI (bench.py's gpu_launches)
-_NKERNELS = {"vbmp_estep": 4, "vbmp_estep_rpack": 4, "vbmp_gram": 6, "vbmp_gram_rpack": 5}      # row scales + pack + E-step + reduce; column maxima + weight split + sample transpose + Gram (fp16) + Gram (TF32, returns at once unless flagged) + reduce
+# kernels per C-ABI call on the tcgen05 path (bench.py's gpu_launches; counted from the launchers in csrc/):
+#   E-step: row scales + pack + E-step + reduce.  Gram: [column maxima + sample transpose] + [weight split] + Gram (fp16) +
+#   reduce + Gram (TF32; returns at once unless flagged) + its reduce (likewise)
+_NKERNELS = {"vbmp_estep": 4, "vbmp_estep_rpack": 4, "vbmp_gram": 7, "vbmp_gram_rpack": 6, "vbmp_gram_zpack": 2,
+             "vbmp_gram_ex": 4}
+_PROFILE_AS = {"vbmp_estep_rpack": "vbmp_estep", "vbmp_gram_rpack": "vbmp_gram", "vbmp_gram_ex": "vbmp_gram",
+               "vbmp_gram_zpack": "vbmp_gram"}
 
 
 class VbmpError(RuntimeError):
@@ -44,6 +50,10 @@ def lib():
         L.vbmp_rpack_bytes.argtypes = [c_longlong, c_int]
         L.vbmp_gram_workspace_bytes.restype = c_size_t
         L.vbmp_gram_workspace_bytes.argtypes = [c_longlong, c_int, c_int, c_int, c_int, c_int]
+        L.vbmp_gram_ex_workspace_bytes.restype = c_size_t
+        L.vbmp_gram_ex_workspace_bytes.argtypes = [c_longlong, c_int, c_int, c_int, c_int, c_int, c_int, c_int]
+        L.vbmp_zpack_bytes.restype = c_size_t
+        L.vbmp_zpack_bytes.argtypes = [c_longlong, c_int, c_int]
         _lib = L
     return _lib
 
@@ -53,6 +63,7 @@ EXPORTS = (
     "vbmp_estep", "vbmp_gram_workspace_bytes", "vbmp_gram", "vbmp_wishart_update", "vbmp_niw_update",
     "vbmp_mnw_update", "vbmp_wishart_elogdet", "vbmp_wishart_kl", "vbmp_niw_kl", "vbmp_mnw_kl",
     "vbmp_hmm_forward_backward", "vbmp_rpack_bytes", "vbmp_estep_rpack", "vbmp_gram_rpack",
+    "vbmp_zpack_bytes", "vbmp_gram_zpack", "vbmp_gram_ex_workspace_bytes", "vbmp_gram_ex",
 )
 
 
@@ -61,18 +72,21 @@ def _check(rc, what):
         raise VbmpError(f"{what} failed (code {rc}): {lib().vbmp_last_error().decode()}")
 
 
-def _call(name, *args):
-    """Invoke one C-ABI entry point on the current stream (optionally bracketed by CUDA events)."""
+def _call(name, dev, *args):
+    """Invoke one C-ABI entry point on ``dev``'s current stream (optionally bracketed by CUDA events).  The call runs under
+    a device guard: kernel launches, attribute queries and the library's per-device caches all follow the CUDA *current*
+    device, which need not be the tensors' device in a single-process multi-GPU program."""
     global LAUNCHES
     fn = getattr(lib(), name)
-    if PROFILE is not None:
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        rc = fn(*args)
-        b.record()
-        PROFILE.setdefault(name.replace("_rpack", ""), []).append((a, b))     # the hand-over variants time as K2 / K3
-    else:
-        rc = fn(*args)
+    with torch.cuda.device(dev):
+        if PROFILE is not None:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            rc = fn(*args)
+            b.record()
+            PROFILE.setdefault(_PROFILE_AS.get(name, name), []).append((a, b))     # the hand-over variants time as K2 / K3
+        else:
+            rc = fn(*args)
     LAUNCHES += _NKERNELS.get(name, 1)
     _check(rc, name)
 
@@ -131,6 +145,7 @@ def release_workspaces():
     _ws_cache.clear()
     _rpack_cache.clear()
     _rpack_rec.clear()
+    _zpack_cache.clear()
 
 
 # ------------------------------------------------------------------------------------------------
@@ -143,7 +158,7 @@ def niw_prep(invU, mu, nu, lam, logprior, C, d, Dp):
     m = torch.empty((C, Dp), dtype=torch.float32, device=dev)
     cst = torch.empty((C,), dtype=torch.float32, device=dev)
     info = torch.empty((C,), dtype=torch.int32, device=dev)
-    _call("vbmp_niw_prep", _ptr(invU), _ptr(mu), _ptr(nu), _ptr(lam), _ptr(logprior), c_int(C), c_int(d),
+    _call("vbmp_niw_prep", dev, _ptr(invU), _ptr(mu), _ptr(nu), _ptr(lam), _ptr(logprior), c_int(C), c_int(d),
                                c_int(Dp), _ptr(W), _ptr(m), _ptr(cst), _ptr(info), _stream(dev))
     return W, m, cst, info
 
@@ -154,26 +169,44 @@ def mnw_prep(invU, nu, mu, invV, logprior, C, n, pp, pad, Dp):
     m = torch.empty((C, Dp), dtype=torch.float32, device=dev)
     cst = torch.empty((C,), dtype=torch.float32, device=dev)
     info = torch.empty((C,), dtype=torch.int32, device=dev)
-    _call("vbmp_mnw_prep", _ptr(invU), _ptr(nu), _ptr(mu), _ptr(invV), _ptr(logprior), c_int(C), c_int(n),
+    _call("vbmp_mnw_prep", dev, _ptr(invU), _ptr(nu), _ptr(mu), _ptr(invV), _ptr(logprior), c_int(C), c_int(n),
                                c_int(pp), c_int(int(pad)), c_int(Dp), _ptr(W), _ptr(m), _ptr(cst), _ptr(info),
                                _stream(dev))
     return W, m, cst, info
 
 
 # K2 -> K3 hand-over: the most recent mode-1 E-step on a stream may have left the responsibilities pre-split for the Gram
-# kernel (vbmp_estep_rpack).  The record ties that buffer to the exact responsibilities tensor: same storage, offset, size and
-# torch version counter (any in-place edit bumps it), so gram() only uses the images for the untouched p they were made of.
+# kernel (vbmp_estep_rpack).  The record ties that buffer to the exact responsibilities it was made of: it HOLDS the
+# storage object of that tensor (so the allocator cannot hand its address to another tensor while the record lives) and
+# compares storage identity, offset, size and torch's version counter (any in-place ATen edit bumps it).  Writes that
+# bypass ATen (another library's kernel through a raw pointer, DLPack consumers) are invisible to the counter: code that
+# edits p that way must call invalidate_handover() (or set VBMP_RPACK=0).
 RPACK = int(os.environ.get("VBMP_RPACK", "1"))
+ZCACHE = int(os.environ.get("VBMP_ZCACHE", "1"))
 _rpack_cache = {}     # stream key -> buffer
-_rpack_rec = {}       # stream key -> (storage ptr, storage offset, numel, version, N, K)
+_rpack_rec = {}       # stream key -> (storage, storage offset, numel, version, N, K)
+_zpack_cache = {}     # stream key -> (signature, storages, buffer): K3's sample image of the rows it was last given
 
 
 def _rpack_key(dev):
     return (dev.type, dev.index, torch.cuda.current_stream(dev).cuda_stream)
 
 
-def _rpack_sig(t):
-    return (t.untyped_storage().data_ptr(), t.storage_offset(), t.numel(), t._version)
+def _same_tensor(rec, t):
+    """rec = (storage, offset, numel, version) taken from a tensor earlier: is ``t`` that tensor, unedited?"""
+    st = t.untyped_storage()
+    return (st.data_ptr() == rec[0].data_ptr() and st.nbytes() == rec[0].nbytes() and t.storage_offset() == rec[1]
+            and t.numel() == rec[2] and t._version == rec[3])
+
+
+def _tensor_rec(t):
+    return (t.untyped_storage(), t.storage_offset(), t.numel(), t._version)
+
+
+def invalidate_handover():
+    """Forget the K2 -> K3 weight images and the cached sample images (call after editing p / X behind torch's back)."""
+    _rpack_rec.clear()
+    _zpack_cache.clear()
 
 
 def estep(z0, z1, N, GX, xg, W, m, cst, G, K, Dp, mode, out=None, logZn=None):
@@ -181,6 +214,8 @@ def estep(z0, z1, N, GX, xg, W, m, cst, G, K, Dp, mode, out=None, logZn=None):
     dev = z0.device
     d0 = z0.shape[-1]
     d1 = 0 if z1 is None else z1.shape[-1]
+    key = _rpack_key(dev)
+    _rpack_rec.pop(key, None)                    # whatever was packed before is about to be overwritten
     if out is None:
         out = torch.empty((N, G, K), dtype=torch.float32, device=dev)
     NA = logZ = None
@@ -191,8 +226,7 @@ def estep(z0, z1, N, GX, xg, W, m, cst, G, K, Dp, mode, out=None, logZn=None):
         logZ = torch.empty((G,), dtype=torch.float32, device=dev)
     nbytes = lib().vbmp_estep_workspace_bytes(c_longlong(N), c_int(G), c_int(K), c_int(Dp), c_int(mode))
     ws = _workspace(nbytes, dev)
-    key = _rpack_key(dev)
-    _rpack_rec.pop(key, None)                    # whatever was packed before is about to be overwritten
+    _note_path("estep", N, GX, G, K, Dp, d0, d1, True)
     if mode == 1 and RPACK and G == 1 and GX == 1 and K <= 256 and not FORCE_SIMT:
         rb = int(lib().vbmp_rpack_bytes(c_longlong(N), c_int(K)))
         buf = _rpack_cache.get(key)
@@ -200,20 +234,45 @@ def estep(z0, z1, N, GX, xg, W, m, cst, G, K, Dp, mode, out=None, logZn=None):
             buf = torch.empty(max(rb, 1), dtype=torch.uint8, device=dev)
             _rpack_cache[key] = buf
         packed = c_int(0)
-        _call("vbmp_estep_rpack", _ptr(z0), c_int(d0), _ptr(z1), c_int(d1), c_longlong(N), c_int(GX), _ptr(xg),
+        _call("vbmp_estep_rpack", dev, _ptr(z0), c_int(d0), _ptr(z1), c_int(d1), c_longlong(N), c_int(GX), _ptr(xg),
               _ptr(W), _ptr(m), _ptr(cst), c_int(G), c_int(K), c_int(Dp), c_int(mode), c_int(0), _ptr(out), _ptr(logZn),
               _ptr(NA), _ptr(logZ), _ptr(ws), c_size_t(ws.numel()), _stream(dev), _ptr(buf), c_size_t(buf.numel()),
               ctypes.byref(packed))
         if packed.value:
-            _rpack_rec[key] = _rpack_sig(out) + (N, K)
+            _rpack_rec[key] = _tensor_rec(out) + (N, K)
         return out, logZn, NA, logZ
-    _call("vbmp_estep", _ptr(z0), c_int(d0), _ptr(z1), c_int(d1), c_longlong(N), c_int(GX), _ptr(xg),
-                            _ptr(W), _ptr(m), _ptr(cst), c_int(G), c_int(K), c_int(Dp), c_int(mode),
-                            c_int(1 if FORCE_SIMT in (1, 2) else 0), _ptr(out), _ptr(logZn), _ptr(NA), _ptr(logZ),
-                            _ptr(ws), c_size_t(ws.numel()), _stream(dev))
+    _call("vbmp_estep", dev, _ptr(z0), c_int(d0), _ptr(z1), c_int(d1), c_longlong(N), c_int(GX), _ptr(xg),
+          _ptr(W), _ptr(m), _ptr(cst), c_int(G), c_int(K), c_int(Dp), c_int(mode),
+          c_int(1 if FORCE_SIMT in (1, 2) else 0), _ptr(out), _ptr(logZn), _ptr(NA), _ptr(logZ),
+          _ptr(ws), c_size_t(ws.numel()), _stream(dev))
     if mode == 0:
         return out
     return out, logZn, NA, logZ
+
+
+def _zpack(z0, z1, N, K, Dp, key, dev):
+    """K3's sample image of (z0, z1), made once per data set: reused while the rows are the same, unedited tensors."""
+    if not ZCACHE:
+        return None
+    d0 = z0.shape[-1]
+    d1 = 0 if z1 is None else z1.shape[-1]
+    ent = _zpack_cache.get(key)
+    if ent is not None:
+        sig, recs, buf = ent
+        if sig == (N, K, Dp, d0, d1) and _same_tensor(recs[0], z0) and (z1 is None or _same_tensor(recs[1], z1)):
+            return buf
+    zb = int(lib().vbmp_zpack_bytes(c_longlong(N), c_int(d0), c_int(d1)))
+    buf = ent[2] if (ent is not None and ent[2].numel() >= zb) else None
+    _zpack_cache.pop(key, None)
+    if buf is None:
+        buf = torch.empty(max(zb, 1), dtype=torch.uint8, device=dev)
+    packed = c_int(0)
+    _call("vbmp_gram_zpack", dev, _ptr(z0), c_int(d0), _ptr(z1), c_int(d1), c_longlong(N), c_int(K), c_int(Dp), _ptr(buf),
+          c_size_t(buf.numel()), ctypes.byref(packed), _stream(dev))
+    if not packed.value:
+        return None
+    _zpack_cache[key] = ((N, K, Dp, d0, d1), (_tensor_rec(z0), None if z1 is None else _tensor_rec(z1)), buf)
+    return buf
 
 
 def gram(z0, z1, N, GX, xg, p, GP, pg, G, K, Dp):
@@ -223,20 +282,67 @@ def gram(z0, z1, N, GX, xg, p, GP, pg, G, K, Dp):
     d1 = 0 if z1 is None else z1.shape[-1]
     D1 = d0 + d1 + 1
     out = torch.empty((G, K, D1, D1), dtype=torch.float32, device=dev)
+    key = _rpack_key(dev)
+    _note_path("gram", N, GX, G, K, Dp, d0, d1, p is not None and GP == 1)
+    if p is not None and not FORCE_SIMT and GP == 1 and GX == 1 and G == 1:
+        rec = _rpack_rec.get(key)
+        rbuf = None
+        if rec is not None and rec[4:] == (N, K) and _same_tensor(rec, p):
+            rbuf = _rpack_cache[key]
+        zbuf = _zpack(z0, z1, N, K, Dp, key, dev)
+        if rbuf is not None or zbuf is not None:
+            nbytes = lib().vbmp_gram_ex_workspace_bytes(c_longlong(N), c_int(G), c_int(K), c_int(d0), c_int(d1), c_int(Dp),
+                                                        c_int(rbuf is not None), c_int(zbuf is not None))
+            ws = _workspace(nbytes, dev)
+            _call("vbmp_gram_ex", dev, _ptr(z0), c_int(d0), _ptr(z1), c_int(d1), c_longlong(N), c_int(GX), _ptr(xg),
+                  _ptr(p), c_int(GP), _ptr(pg), c_int(G), c_int(K), c_int(Dp), c_int(0), _ptr(out), _ptr(ws),
+                  c_size_t(ws.numel()), _stream(dev), _ptr(rbuf), _ptr(zbuf))
+            global LAUNCHES
+            LAUNCHES += (rbuf is None) + 2 * (zbuf is None)          # images the call had to make itself
+            return out
     nbytes = lib().vbmp_gram_workspace_bytes(c_longlong(N), c_int(G), c_int(K), c_int(d0), c_int(d1), c_int(Dp))
     ws = _workspace(nbytes, dev)
-    key = _rpack_key(dev)
-    rec = _rpack_rec.get(key)
-    if rec is not None and p is not None and not FORCE_SIMT and GP == 1 and rec == _rpack_sig(p) + (N, K):
-        _call("vbmp_gram_rpack", _ptr(z0), c_int(d0), _ptr(z1), c_int(d1), c_longlong(N), c_int(GX), _ptr(xg),
-              _ptr(p), c_int(GP), _ptr(pg), c_int(G), c_int(K), c_int(Dp), c_int(0), _ptr(out), _ptr(ws),
-              c_size_t(ws.numel()), _stream(dev), _ptr(_rpack_cache[key]))
-        return out
-    _call("vbmp_gram", _ptr(z0), c_int(d0), _ptr(z1), c_int(d1), c_longlong(N), c_int(GX), _ptr(xg),
-                           _ptr(p), c_int(GP), _ptr(pg), c_int(G), c_int(K), c_int(Dp),
-                           c_int(1 if FORCE_SIMT in (1, 3) else 0), _ptr(out), _ptr(ws), c_size_t(ws.numel()),
-                           _stream(dev))
+    _call("vbmp_gram", dev, _ptr(z0), c_int(d0), _ptr(z1), c_int(d1), c_longlong(N), c_int(GX), _ptr(xg),
+          _ptr(p), c_int(GP), _ptr(pg), c_int(G), c_int(K), c_int(Dp),
+          c_int(1 if FORCE_SIMT in (1, 3) else 0), _ptr(out), _ptr(ws), c_size_t(ws.numel()),
+          _stream(dev))
     return out
+
+
+_warned = set()
+
+
+def _note_path(what, N, GX, G, K, Dp, d0, d1, weighted):
+    """One warning per (kernel, reason) when a LARGE call leaves the tensor-core window and runs on the CUDA-core kernels
+    (same results, ~20x slower at cfg2's shape: 559 vs 26 ms per iteration) — no silent performance cliff."""
+    if FORCE_SIMT or N * K < (1 << 22):
+        return
+    why = []
+    if G != 1 or GX != 1:
+        why.append(f"replica / extra-event groups (G={G}, GX={GX})")
+    if Dp not in _TC_DP:
+        why.append(f"padded feature dimension {Dp}")
+    if K % 4:
+        why.append(f"K={K} is not a multiple of 4")
+    if what == "estep" and K > 512:
+        why.append(f"K={K} > 512")
+    if what == "gram":
+        if not weighted:
+            why.append("unit or per-group weights")
+        if d0 % 4 or d1 % 4:
+            why.append(f"feature blocks ({d0}, {d1}) not multiples of 4")
+    if not why:
+        return
+    tag = (what, tuple(why))
+    if tag in _warned:
+        return
+    _warned.add(tag)
+    import warnings
+    warnings.warn(f"pyvbmp_b200: {what} with N={N}, K={K} runs on the CUDA-core kernel, not tcgen05 ({'; '.join(why)}); "
+                  "results are identical, throughput is ~20x lower", RuntimeWarning, stacklevel=3)
+
+
+_TC_DP = (16, 32, 64)
 
 
 def wishart_update(SExx, N, invU0, nu0, invU_old, nu_old, C, d, lr):
@@ -246,7 +352,7 @@ def wishart_update(SExx, N, invU0, nu0, invU_old, nu_old, C, d, lr):
     nu = torch.empty((C,), dtype=torch.float32, device=dev)
     logdet = torch.empty((C,), dtype=torch.float32, device=dev)
     info = torch.empty((C,), dtype=torch.int32, device=dev)
-    _call("vbmp_wishart_update", _ptr(SExx), _ptr(N), _ptr(invU0), _ptr(nu0), _ptr(invU_old), _ptr(nu_old),
+    _call("vbmp_wishart_update", dev, _ptr(SExx), _ptr(N), _ptr(invU0), _ptr(nu0), _ptr(invU_old), _ptr(nu_old),
                                      c_int(C), c_int(d), c_float(lr), _ptr(invU), _ptr(nu), _ptr(U), _ptr(logdet),
                                      _ptr(info), _stream(dev))
     return invU, nu, U, logdet, info
@@ -264,7 +370,7 @@ def niw_update(SExx, SEx, N, lam0, mu0, invU0, nu0, lam_old, mu_old, invU_old, n
         nu = torch.empty((C,), dtype=torch.float32, device=dev)
         logdet = torch.empty((C,), dtype=torch.float32, device=dev)
     info = torch.empty((C,), dtype=torch.int32, device=dev)
-    _call("vbmp_niw_update", _ptr(SExx), _ptr(SEx), _ptr(N), _ptr(lam0), _ptr(mu0), _ptr(invU0), _ptr(nu0),
+    _call("vbmp_niw_update", dev, _ptr(SExx), _ptr(SEx), _ptr(N), _ptr(lam0), _ptr(mu0), _ptr(invU0), _ptr(nu0),
                                  _ptr(lam_old), _ptr(mu_old), _ptr(invU_old), _ptr(nu_old), c_int(C), c_int(d),
                                  c_float(lr), c_int(int(bool(fixed_precision))), _ptr(lam), _ptr(mu), _ptr(invU),
                                  _ptr(nu), _ptr(U), _ptr(logdet), _ptr(info), _stream(dev))
@@ -281,7 +387,7 @@ def mnw_update(SExx, SEyx, SEyy, N, mu0, invV0, invU0, nu0, mu_old, invV_old, in
     else:
         invU, nu, U, ldU = e(C, n, n), e(C), e(C, n, n), e(C)
     info = torch.empty((C,), dtype=torch.int32, device=dev)
-    _call("vbmp_mnw_update", _ptr(SExx), _ptr(SEyx), _ptr(SEyy), _ptr(N), _ptr(mu0), _ptr(invV0), _ptr(invU0),
+    _call("vbmp_mnw_update", dev, _ptr(SExx), _ptr(SEyx), _ptr(SEyy), _ptr(N), _ptr(mu0), _ptr(invV0), _ptr(invU0),
                                  _ptr(nu0), _ptr(mu_old), _ptr(invV_old), _ptr(invU_old), _ptr(nu_old), c_int(C),
                                  c_int(n), c_int(pp), c_float(lr), c_int(int(bool(fixed_precision))), _ptr(mu),
                                  _ptr(invV), _ptr(V), _ptr(ldV), _ptr(invU), _ptr(nu), _ptr(U), _ptr(ldU),
@@ -291,27 +397,27 @@ def mnw_update(SExx, SEyx, SEyy, N, mu0, invV0, invU0, nu0, mu_old, invV_old, in
 
 def wishart_elogdet(nu, logdet, C, d):
     out = torch.empty((C,), dtype=torch.float32, device=nu.device)
-    _call("vbmp_wishart_elogdet", _ptr(nu), _ptr(logdet), c_int(C), c_int(d), _ptr(out), _stream(nu.device))
+    _call("vbmp_wishart_elogdet", nu.device, _ptr(nu), _ptr(logdet), c_int(C), c_int(d), _ptr(out), _stream(nu.device))
     return out
 
 
 def wishart_kl(invU0, U, nu0, nu, logdet, logdet0, C, d):
     out = torch.empty((C,), dtype=torch.float32, device=U.device)
-    _call("vbmp_wishart_kl", _ptr(invU0), _ptr(U), _ptr(nu0), _ptr(nu), _ptr(logdet), _ptr(logdet0), c_int(C),
+    _call("vbmp_wishart_kl", U.device, _ptr(invU0), _ptr(U), _ptr(nu0), _ptr(nu), _ptr(logdet), _ptr(logdet0), c_int(C),
                                  c_int(d), _ptr(out), _stream(U.device))
     return out
 
 
 def niw_kl(lam0, lam, mu0, mu, invU0, U, nu0, nu, logdet, logdet0, C, d):
     out = torch.empty((C,), dtype=torch.float32, device=U.device)
-    _call("vbmp_niw_kl", _ptr(lam0), _ptr(lam), _ptr(mu0), _ptr(mu), _ptr(invU0), _ptr(U), _ptr(nu0), _ptr(nu),
+    _call("vbmp_niw_kl", U.device, _ptr(lam0), _ptr(lam), _ptr(mu0), _ptr(mu), _ptr(invU0), _ptr(U), _ptr(nu0), _ptr(nu),
                              _ptr(logdet), _ptr(logdet0), c_int(C), c_int(d), _ptr(out), _stream(U.device))
     return out
 
 
 def mnw_kl(mu0, mu, invV0, V, ldV, ldV0, invU0, U, nu0, nu, ldU, ldU0, C, n, pp):
     out = torch.empty((C,), dtype=torch.float32, device=U.device)
-    _call("vbmp_mnw_kl", _ptr(mu0), _ptr(mu), _ptr(invV0), _ptr(V), _ptr(ldV), _ptr(ldV0), _ptr(invU0), _ptr(U),
+    _call("vbmp_mnw_kl", U.device, _ptr(mu0), _ptr(mu), _ptr(invV0), _ptr(V), _ptr(ldV), _ptr(ldV0), _ptr(invU0), _ptr(U),
                              _ptr(nu0), _ptr(nu), _ptr(ldU), _ptr(ldU0), c_int(C), c_int(n), c_int(pp), _ptr(out),
                              _stream(U.device))
     return out
@@ -324,6 +430,6 @@ def hmm_forward_backward(logits, trans, init, T, S, G, K, ptemp):
     SEzz = torch.empty((S, K, K), dtype=torch.float32, device=dev)
     SEz0 = torch.empty((S, K), dtype=torch.float32, device=dev)
     logZ = torch.empty((S,), dtype=torch.float32, device=dev)
-    _call("vbmp_hmm_forward_backward", _ptr(logits), _ptr(trans), _ptr(init), c_int(T), c_longlong(S), c_int(G), c_int(K),
+    _call("vbmp_hmm_forward_backward", dev, _ptr(logits), _ptr(trans), _ptr(init), c_int(T), c_longlong(S), c_int(G), c_int(K),
           c_float(float(ptemp)), _ptr(p), _ptr(SEzz), _ptr(SEz0), _ptr(logZ), _stream(dev))
     return p, SEzz, SEz0, logZ

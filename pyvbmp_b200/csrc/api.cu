@@ -47,7 +47,10 @@ bool estep_umma_supported(long long N, int GX, int G, int K, int Dp, int d0, int
 size_t estep_umma_workspace_bytes(long long N, int G, int K, int Dp, int mode);
 int launch_estep_umma(const EstepArgs&, int mode, void* ws, size_t ws_bytes, float* NA, float* logZ, cudaStream_t);
 bool gram_umma_supported(long long N, int GX, int GP, int G, int K, int Dp, int d0, int d1, bool has_p);
-size_t gram_umma_workspace_bytes(long long N, int G, int K, int d0, int d1, int Dp);
+size_t gram_umma_workspace_bytes(long long N, int G, int K, int d0, int d1, int Dp, bool has_rpack, bool has_zpack);
+size_t gram_zpack_bytes(long long N, int D);
+bool gram_zpack_usable(long long N, int K, int Dp, int d0, int d1);
+int launch_gram_zpack(const float* z0, int d0, const float* z1, int d1, long long N, void* zpack, cudaStream_t st);
 int launch_gram_umma(const GramArgs&, float* gram, void* ws, size_t ws_bytes, cudaStream_t);
 bool estep_umma_can_pack(long long N, int GX, int G, int K, int Dp, int d0, int d1, int mode);
 size_t gram_rpack_bytes(long long N, int K);
@@ -150,19 +153,50 @@ int vbmp_estep_rpack(const float* z0, int d0, const float* z1, int d1, long long
                     workspace_bytes, stream, rpack, rpack_bytes, packed);
 }
 
-size_t vbmp_gram_workspace_bytes(long long N, int G, int K, int d0, int d1, int Dp) {
+static size_t gram_ws_bytes(long long N, int G, int K, int d0, int d1, int Dp, bool has_rpack, bool has_zpack) {
   if (!valid_dp(Dp) || N < 0) return 0;
   long long S_per; int splits;
   gram_simt_plan(N > 0 ? N : 1, G, K, Dp, &S_per, &splits);
   const size_t D1 = (size_t)d0 + d1 + 1;
   const size_t simt = (size_t)splits * G * K * D1 * D1 * sizeof(float);
-  const size_t umma = gram_umma_workspace_bytes(N, G, K, d0, d1, Dp);
+  const size_t umma = gram_umma_workspace_bytes(N, G, K, d0, d1, Dp, has_rpack, has_zpack);
   return (simt > umma ? simt : umma) + 256;
+}
+
+size_t vbmp_gram_workspace_bytes(long long N, int G, int K, int d0, int d1, int Dp) {
+  return gram_ws_bytes(N, G, K, d0, d1, Dp, false, false);
+}
+
+size_t vbmp_gram_ex_workspace_bytes(long long N, int G, int K, int d0, int d1, int Dp, int has_rpack, int has_zpack) {
+  return gram_ws_bytes(N, G, K, d0, d1, Dp, has_rpack != 0, has_zpack != 0);
+}
+
+size_t vbmp_zpack_bytes(long long N, int d0, int d1) {
+  return (N < 0 || d0 < 1 || d1 < 0) ? 0 : gram_zpack_bytes(N, d0 + d1);
+}
+
+int vbmp_gram_zpack(const float* z0, int d0, const float* z1, int d1, long long N, int K, int Dp,
+                    void* zpack, size_t zpack_bytes, int* packed, void* stream) {
+  if (!packed) { set_error("gram_zpack: packed is NULL"); return VBMP_ERR_SHAPE; }
+  *packed = 0;
+  if (!valid_dp(Dp) || d0 < 1 || d1 < 0 || d0 + d1 > Dp || N < 0 || K < 1 || (d1 > 0 && !z1)) {
+    set_error("gram_zpack: bad shape N=%lld K=%d d0=%d d1=%d Dp=%d", N, K, d0, d1, Dp);
+    return VBMP_ERR_SHAPE;
+  }
+  if (!gram_zpack_usable(N, K, Dp, d0, d1)) return VBMP_OK;       // the kernels that take this shape do not use an image
+  if (zpack_bytes < gram_zpack_bytes(N, d0 + d1)) {
+    set_error("gram_zpack: buffer too small (%zu < %zu)", zpack_bytes, gram_zpack_bytes(N, d0 + d1));
+    return VBMP_ERR_WORKSPACE;
+  }
+  int rc = launch_gram_zpack(z0, d0, z1, d1, N, zpack, (cudaStream_t)stream);
+  if (rc == VBMP_OK) *packed = 1;
+  return rc;
 }
 
 static int gram_impl(const float* z0, int d0, const float* z1, int d1, long long N, int GX, const int* xg,
                      const float* p, int GP, const int* pg, int G, int K, int Dp, int flags,
-                     float* gram, void* workspace, size_t workspace_bytes, void* stream, const void* rpack) {
+                     float* gram, void* workspace, size_t workspace_bytes, void* stream, const void* rpack,
+                     const void* zpack = nullptr) {
   cudaStream_t st = (cudaStream_t)stream;
   if (!valid_dp(Dp) || d0 < 1 || d1 < 0 || d0 + d1 > Dp || G < 1 || K < 1 || GX < 1 || GP < 1 || N < 0) {
     set_error("gram: bad shape N=%lld GX=%d GP=%d G=%d K=%d d0=%d d1=%d Dp=%d", N, GX, GP, G, K, d0, d1, Dp);
@@ -171,12 +205,14 @@ static int gram_impl(const float* z0, int d0, const float* z1, int d1, long long
   if (d1 > 0 && !z1) { set_error("gram: z1 is NULL with d1=%d", d1); return VBMP_ERR_SHAPE; }
   const size_t D1 = (size_t)d0 + d1 + 1, per = (size_t)G * K * D1 * D1;
   if (N == 0) { cudaMemsetAsync(gram, 0, per * sizeof(float), st); return VBMP_OK; }
-  if (workspace_bytes < vbmp_gram_workspace_bytes(N, G, K, d0, d1, Dp)) {
-    set_error("gram: workspace too small (%zu < %zu)", workspace_bytes, vbmp_gram_workspace_bytes(N, G, K, d0, d1, Dp));
+  const size_t need = gram_ws_bytes(N, G, K, d0, d1, Dp, rpack != nullptr, zpack != nullptr);
+  if (workspace_bytes < need) {
+    set_error("gram: workspace too small (%zu < %zu)", workspace_bytes, need);
     return VBMP_ERR_WORKSPACE;
   }
   GramArgs a{z0, z1, d0, d1, N, GX, xg, p, GP, pg, G, K, Dp, 0, 0, nullptr};
   a.rpack = (const unsigned char*)rpack;
+  a.zpack = (const unsigned char*)zpack;
   if (!(flags & 1) && gram_umma_supported(N, GX, GP, G, K, Dp, d0, d1, p != nullptr))
     return launch_gram_umma(a, gram, workspace, workspace_bytes, st);
   gram_simt_plan(N, G, K, Dp, &a.S_per, &a.splits);
@@ -196,6 +232,12 @@ int vbmp_gram_rpack(const float* z0, int d0, const float* z1, int d1, long long 
                     const float* p, int GP, const int* pg, int G, int K, int Dp, int flags,
                     float* gram, void* workspace, size_t workspace_bytes, void* stream, const void* rpack) {
   return gram_impl(z0, d0, z1, d1, N, GX, xg, p, GP, pg, G, K, Dp, flags, gram, workspace, workspace_bytes, stream, rpack);
+}
+
+int vbmp_gram_ex(const float* z0, int d0, const float* z1, int d1, long long N, int GX, const int* xg,
+                 const float* p, int GP, const int* pg, int G, int K, int Dp, int flags,
+                 float* gram, void* workspace, size_t workspace_bytes, void* stream, const void* rpack, const void* zpack) {
+  return gram_impl(z0, d0, z1, d1, N, GX, xg, p, GP, pg, G, K, Dp, flags, gram, workspace, workspace_bytes, stream, rpack, zpack);
 }
 
 int vbmp_wishart_update(const float* SExx, const float* N, const float* invU_0, const float* nu_0,

@@ -30,10 +30,23 @@ struct GramArgs {
   long long S_per; int splits;
   float* part;                                        // [splits][G][K][(D+1)^2]
   const unsigned char* rpack = nullptr;               // pre-split weight images written by K2 (vbmp_estep_rpack)
+  const unsigned char* zpack = nullptr;               // sample image written by vbmp_gram_zpack (column maxima + transposed chunks)
 };
 
 void set_error(const char* fmt, ...);
 int check_launch(const char* what);
+
+// SM count of the CURRENT device, cached per device (a process may drive several GPUs)
+inline int num_sms() {
+  static int cache[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return 148; }
+  if (dev >= 0 && dev < 64 && cache[dev] > 0) return cache[dev];
+  int n = 0;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) { cudaGetLastError(); n = 148; }
+  if (dev >= 0 && dev < 64) cache[dev] = n;
+  return n;
+}
 
 __host__ __device__ inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 __host__ __device__ inline int tri(int i, int j) { return i * (i + 1) / 2 + j; }   // packed lower index, j <= i

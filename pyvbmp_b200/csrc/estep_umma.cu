@@ -617,16 +617,7 @@ estep_umma_kernel(EstepArgs a, const uint8_t* __restrict__ Wp, const float* __re
 }
 
 // ---- host side -------------------------------------------------------------------------------------------
-static int eu_num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
-}
+static int eu_num_sms() { return num_sms(); }
 
 // the TF32 record is the larger one: the workspace is sized for it whichever precision runs
 static size_t eu_group_bytes(int Dp) { return Dp == 64 ? EuCfg<64, false>::REC : (Dp == 32 ? EuCfg<32, false>::REC : EuCfg<16, false>::REC); }

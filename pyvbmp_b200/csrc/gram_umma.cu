@@ -69,15 +69,19 @@ constexpr int GU_CB = 128;           // components per CTA
 struct GuArgs {
   int d0, d1;
   long long N; int K;
-  int npb, NPB, P, ncb, splits;      // pair blocks, pairs per block, total pairs, component blocks, sample splits
+  int npb, NPB, P, ncb, splits;      // pair blocks, pair columns of the widest block, total pairs, component blocks, sample splits
+  int wbase, wextra;                 // block pb holds 16 (wbase + (pb < wextra)) pair columns starting at 16 (pb wbase + min(pb, wextra))
   long long S_per;                   // samples per split (multiple of GU_SC)
-  int Kp, PP;                        // padded partial dims: Kp = ncb*128, PP = npb*NPB
+  int Kp, PP;                        // padded partial dims: Kp = ncb*128, PP = P rounded up to 16
   int kcb;                           // columns of the R box = min(128, K)
   int FL;                            // chunks per first-level accumulation block
   float* part;                       // [splits][Kp][PP]
-  // fp16 variant: hdr[0..64] = bit patterns of the column maxima of |zt_i| (the constant feature's is 1.0f), hdr[96] = flag
-  // "weights out of fp16 range, recompute with TF32 operands".  The TF32 kernel gets hdr too (nullptr = run always).
-  uint32_t* hdr;
+  // fp16 variant: cmax[0..D) = bit patterns of the column maxima of |z_i| (head of the sample image, see vbmp_gram_zpack);
+  // flag[0] != 0 = "operands outside the fp16 window, recompute with TF32 operands" (weights beyond range: set by
+  // gram_rsplit_kernel; a component whose samples sit below the resolution of a feature's scale: set by the first reduce).
+  // The TF32 kernel gets flag too (nullptr = run always).
+  const uint32_t* cmax;
+  uint32_t* flag;
   // fp16 variant: the weights pre-split by gram_rsplit_kernel: record (component block cb, 16-sample block sb) at
   // ((cb * nsb + sb) * 8192) bytes = [hi | lo] x [8-sample chunk (2)][component (128)][8 fp16], i.e. the TMEM image of
   // the A operand of one K-step: lane = component, 16 bytes per chunk
@@ -89,7 +93,7 @@ struct GuArgs {
   const uint8_t* zt;
   int zrec;
 };
-constexpr int GU_HDR_FLAG = 96, GU_HDR_WORDS = 128;
+constexpr int GU_HDR_WORDS = 256;    // words of the sample image's header (column maxima) and of the per-call flag block
 constexpr int GU_RREC = 8192;
 constexpr int GU_ZS = 36;            // floats per feature row of a transposed 32-sample chunk (32 + 4 padding)
 __host__ __device__ constexpr int gu_zrec(int D) { return (D + 2) * GU_ZS * 4; }
@@ -150,7 +154,7 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant_
   constexpr int SC = gu_sc(F16);                          // samples per chunk
   // TF32 variant behind an fp16 launch: only needed when that launch met weights outside fp16 range (uniform exit, before
   // any barrier or allocation, for both CTAs of a pair)
-  if (!F16 && a.hdr != nullptr && a.hdr[GU_HDR_FLAG] == 0u) return;
+  if (!F16 && a.flag != nullptr && a.flag[0] == 0u) return;
   const int D = a.d0 + a.d1;
   // carve: raw ring [NR][R 16 x kcb floats | Z0 16 x d0 | Z1 16 x d1], B stages [2][hi NPB*64 B | lo NPB*64 B]
   const int kcb = R128 ? 128 : a.kcb;
@@ -173,9 +177,12 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant_
   const long long nb = (long long)split * a.S_per;
   long long ne = nb + a.S_per; if (ne > a.N) ne = a.N;
   const int nchunks = ne > nb ? (int)((ne - nb + SC - 1) / SC) : 0;
-  // the last pair block is narrower (cfg2: 11 blocks of 192 columns and one of 48 instead of 12 x 192): its MMAs, phi
-  // columns and folds shrink with it; the partial buffer keeps the full-width stride a.NPB
-  const int NPB = min(a.NPB, (a.P - pb * a.NPB + 15) / 16 * 16), FL = a.FL;
+  // the pair columns (P rounded up to 16) are dealt out in 16-column units as evenly as they go (cfg2: 3 blocks of 192
+  // and 9 of 176 = 2160 columns for 2145 pairs): the blocks of one sample range then run at nearly the same rate and
+  // stay within L2 reach of each other — one narrow last block (11 x 192 + 48) finished its rows four times faster
+  // and its re-reads of the weight images all missed (+4 GB of DRAM reads per launch at cfg2)
+  const int NPB = 16 * (a.wbase + (pb < a.wextra ? 1 : 0)), FL = a.FL;
+  const int poff = 16 * (pb * a.wbase + min(pb, a.wextra));
   const int NH = PAIR ? NPB / 2 : NPB;                     // pair columns generated (and held as B rows) by this CTA
 
   if (tid == 0) {
@@ -284,7 +291,7 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant_
     const int ks0 = split_ks ? wtid / NH : 0, ksn = F16 ? (split_ks ? 1 : 2) : 1;
     const bool gen = split_ks ? wtid < 2 * NH : wtid < NH;
     {
-      const int pg_ = pb * a.NPB + (int)rank * NH + pslot;
+      const int pg_ = poff + (int)rank * NH + pslot;
       const bool pair_ok = gen && (pg_ < a.P);
       int pi = 0, pj = 0;
       if (pair_ok) gu_pair(pg_, D, &pi, &pj);
@@ -428,7 +435,7 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant_
         mbar_wait(&S->dfull, nflush & 1);
         tc_fence_after();
         const bool firstf = (nflush == 0);
-        float* prow = a.part + ((size_t)split * a.Kp + (size_t)cb * GU_CB + comp) * a.PP + (size_t)pb * a.NPB;
+        float* prow = a.part + ((size_t)split * a.Kp + (size_t)cb * GU_CB + comp) * a.PP + (size_t)poff;
         for (int c0 = sh * (GU_NPMAX / 2); c0 < (sh + 1) * (GU_NPMAX / 2) && c0 < NPB; c0 += 16) {
           float v1[16], v2[16];
           tmem_ld16(tm + lane_base + c0, v1);
@@ -453,7 +460,7 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant_
       }
     }
     if (nchunks == 0 && set == 0) {      // empty split: contribute zeros
-      float* prow = a.part + ((size_t)split * a.Kp + (size_t)cb * GU_CB + comp) * a.PP + (size_t)pb * a.NPB;
+      float* prow = a.part + ((size_t)split * a.Kp + (size_t)cb * GU_CB + comp) * a.PP + (size_t)poff;
       for (int c0 = sh * (GU_NPMAX / 2); c0 < (sh + 1) * (GU_NPMAX / 2) && c0 < NPB; ++c0) prow[c0] = 0.f;
     }
   }
@@ -462,10 +469,20 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant_
   if (warp == 1) { if (PAIR) tmem_dealloc2<512>(tm); else tmem_dealloc<512>(tm); }
 }
 
-// gram[k][i][j] = gram[k][j][i] = sum_split part[split][k][pair(i,j)], fp64, fixed order.  hdr != nullptr: the partials
-// came from the fp16 kernel (unless its flag says the TF32 kernel recomputed them) and carry the factor 2^(14 + u_i + u_j).
+// gram[k][i][j] = gram[k][j][i] = sum_split part[split][k][pair(i,j)], fp64, fixed order.
+//   MODE 0: partials of the TF32 kernel (raw units), unconditional.
+//   MODE 1: partials of the fp16 kernel: they carry the factor 2^(14 + u_i + u_j).  The threads of the diagonal pairs
+//           also check that the fp16 window resolved every component: mean_k(z'_i^2) (z' = z 2^u_i, column maximum in
+//           [2^6, 2^7)) below 2^-6 means component k's samples sit more than ~9 binades under feature i's scale, where
+//           the low piece of phi' = z'_i z'_j falls into fp16's subnormals (absolute floor 2^-25) and the statistic
+//           would lose bits the fp32 reference keeps (one huge outlier in a column, a tight cluster inside a wide data
+//           range).  Such a component raises flag[0]; the TF32 kernel behind this one then recomputes the partials.
+//   MODE 2: runs after the conditional TF32 kernel; returns at once unless flag[0] is set, else as MODE 0.
+template <int MODE>
 __global__ void gram_pair_reduce_kernel(const float* __restrict__ part, int splits, int K, int Kp, int PP, int D1,
-                                        const uint32_t* __restrict__ hdr, float* __restrict__ gram) {
+                                        const uint32_t* __restrict__ cmax, uint32_t* __restrict__ flag,
+                                        float* __restrict__ gram) {
+  if (MODE == 2 && flag[0] == 0u) return;
   const int P = D1 * (D1 + 1) / 2;
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= (long long)K * P) return;
@@ -474,8 +491,14 @@ __global__ void gram_pair_reduce_kernel(const float* __restrict__ part, int spli
   gu_pair(p, D1 - 1, &i, &j);
   double acc = 0.0;
   for (int s = 0; s < splits; ++s) acc += (double)part[((size_t)s * Kp + k) * PP + p];
-  if (hdr != nullptr && hdr[GU_HDR_FLAG] == 0u) {
-    const int ui = gu_feat_exp(i == D1 - 1 ? 0x3f800000u : hdr[i]), uj = gu_feat_exp(j == D1 - 1 ? 0x3f800000u : hdr[j]);
+  if (MODE == 1) {
+    const int ui = gu_feat_exp(i == D1 - 1 ? 0x3f800000u : cmax[i]), uj = gu_feat_exp(j == D1 - 1 ? 0x3f800000u : cmax[j]);
+    if (i == j && i < D1 - 1 && cmax[i] != 0u) {
+      double accn = 0.0;                                   // the (1, 1) pair: 2^(14 + 12) sum_n r[n,k]
+      for (int s = 0; s < splits; ++s) accn += (double)part[((size_t)s * Kp + k) * PP + (P - 1)];
+      const double nk = ldexp(accn, -(GU_RSH + 12));
+      if (nk >= 4.0 && acc * 4096.0 < accn * 0.015625) atomicOr(flag, 2u);     // mean z'^2 < 2^-6 over >= 4 samples' weight
+    }
     acc = ldexp(acc, -(GU_RSH + ui + uj));
   }
   const float v = (float)acc;
@@ -513,7 +536,7 @@ __global__ void __launch_bounds__(256) gram_colmax_kernel(const float* __restric
 // weights, which was 60 % of the worker instructions.  Thread = (8-sample chunk, component): 8 coalesced reads down a
 // column of p, one 16-byte store each to hi and lo.  Weights beyond fp16 range raise the fallback flag.
 __global__ void __launch_bounds__(256) gram_rsplit_kernel(const float* __restrict__ p, long long N, int K, int ncb, long long nsb,
-                                                          uint8_t* __restrict__ rp, uint32_t* __restrict__ hdr) {
+                                                          uint8_t* __restrict__ rp, uint32_t* __restrict__ flag) {
   const long long total = nsb * 2 * (long long)ncb * GU_CB;           // (chunk of 8 samples) x padded component
   const float rsc = (float)(1 << GU_RSH);
   float rmax = 0.f;
@@ -540,7 +563,7 @@ __global__ void __launch_bounds__(256) gram_rsplit_kernel(const float* __restric
     *reinterpret_cast<uint4*>(rec) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
     *reinterpret_cast<uint4*>(rec + 4096) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
   }
-  if (__any_sync(0xffffffffu, rmax > GU_RMAX) && (threadIdx.x & 31) == 0) atomicOr(&hdr[GU_HDR_FLAG], 1u);
+  if (__any_sync(0xffffffffu, rmax > GU_RMAX) && (threadIdx.x & 31) == 0) atomicOr(flag, 1u);
 }
 
 // fp16 variant pre-pass: zt = [z0 | z1 | 1] scaled by the exact feature scales 2^u_i and transposed per 32-sample chunk
@@ -592,18 +615,7 @@ __global__ void __launch_bounds__(256) gram_zprep_kernel(const float* __restrict
 }
 
 // ---- host side -------------------------------------------------------------------------------------------
-static int gu_num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
-        n <= 0) {
-      cudaGetLastError();
-      n = 148;
-    }
-  }
-  return n;
-}
+static int gu_num_sms() { return num_sms(); }
 
 static bool gu_pair_mode(int K) {
   static const int pair_ok = [] { const char* e = getenv("VBMP_GRAM_PAIR"); return e ? atoi(e) : 1; }();
@@ -615,10 +627,13 @@ static void gu_plan(long long N, int K, int D, int sms, GuArgs* g) {
   const int D1 = D + 1;
   g->P = D1 * (D1 + 1) / 2;
   static const int npb_cap = [] { const char* e = getenv("VBMP_GRAM_NPB"); return e ? atoi(e) : 0; }();   // tuning: pair columns per block
-  const int npmax = (npb_cap >= 16 && npb_cap <= GU_NPMAX) ? npb_cap : GU_NPMAX;
-  g->npb = (g->P + npmax - 1) / npmax;
-  g->NPB = ((g->P + g->npb - 1) / g->npb + 15) / 16 * 16;
-  if (g->NPB < 16) g->NPB = 16;
+  const int npmax = (npb_cap >= 16 && npb_cap <= GU_NPMAX) ? npb_cap / 16 * 16 : GU_NPMAX;
+  // 16-column units dealt out evenly: the first wextra blocks are one unit wider than the rest
+  const int units = (g->P + 15) / 16;
+  g->npb = (units * 16 + npmax - 1) / npmax;
+  g->wbase = units / g->npb;
+  g->wextra = units % g->npb;
+  g->NPB = 16 * (g->wbase + (g->wextra ? 1 : 0));
   g->ncb = (K + GU_CB - 1) / GU_CB;
   const int tasks = g->npb * g->ncb;
   // sample splits: a multiple of the number of task groups that fit the SMs at once, with at most `cap` rows per CTA.
@@ -642,9 +657,10 @@ static void gu_plan(long long N, int K, int D, int sms, GuArgs* g) {
   g->splits = (int)((N + per - 1) / per);
   if (g->splits < 1) g->splits = 1;
   g->Kp = g->ncb * GU_CB;
-  g->PP = g->npb * g->NPB;
+  g->PP = units * 16;
 }
 
+static size_t gu_al(size_t x) { return (x + 255) / 256 * 256; }
 static long long gu_nsb(long long N) { return (N + 31) / 32 * 2; }
 static size_t gu_rp_bytes(long long N, int ncb) { return (size_t)ncb * (size_t)gu_nsb(N) * GU_RREC; }
 static size_t gu_zt_bytes(long long N, int D) { return (size_t)((N + 31) / 32) * gu_zrec(D) + 256; }
@@ -653,6 +669,8 @@ static bool gu_use_f16();
 // bytes of the pre-split weight images of (N, K): what gram_rsplit_kernel writes and vbmp_estep_rpack may write instead
 size_t gram_rpack_bytes(long long N, int K) { return gu_rp_bytes(N, (K + GU_CB - 1) / GU_CB); }
 bool gram_rpack_usable() { return gu_use_f16(); }
+// bytes of the sample image of (N, D): [column maxima, GU_HDR_WORDS words | transposed, pre-scaled 32-sample chunks]
+size_t gram_zpack_bytes(long long N, int D) { return GU_HDR_WORDS * sizeof(uint32_t) + gu_al(gu_zt_bytes(N, D)); }
 
 bool gram_umma_supported(long long N, int GX, int GP, int G, int K, int Dp, int d0, int d1, bool has_p) {
   const int D = d0 + d1;
@@ -660,11 +678,13 @@ bool gram_umma_supported(long long N, int GX, int GP, int G, int K, int Dp, int 
          (d1 % 4 == 0) && N >= 2048;
 }
 
-size_t gram_umma_workspace_bytes(long long N, int G, int K, int d0, int d1, int Dp) {
+// [flag block | per-split partials | weight images unless handed in | sample image unless handed in]
+size_t gram_umma_workspace_bytes(long long N, int G, int K, int d0, int d1, int Dp, bool has_rpack, bool has_zpack) {
   if (!gram_umma_supported(N, 1, 1, G, K, Dp, d0, d1, true)) return 0;
   GuArgs g{};
   gu_plan(N, K, d0 + d1, gu_num_sms(), &g);   // same plan as the launch
-  return (size_t)g.splits * g.Kp * g.PP * sizeof(float) + 512 + GU_HDR_WORDS * sizeof(uint32_t) + gu_rp_bytes(N, g.ncb) + 256 + gu_zt_bytes(N, d0 + d1);
+  return 512 + GU_HDR_WORDS * sizeof(uint32_t) + gu_al((size_t)g.splits * g.Kp * g.PP * sizeof(float)) +
+         (has_rpack ? 0 : gu_al(gu_rp_bytes(N, g.ncb))) + (has_zpack ? 0 : gram_zpack_bytes(N, d0 + d1));
 }
 
 static bool gu_use_f16() {
@@ -739,6 +759,27 @@ static int gu_launch_main(const GramArgs& a, GuArgs g, bool pair, cudaStream_t s
   return check_launch(F16 ? "gram_umma_f16" : "gram_umma");
 }
 
+// column maxima -> exact power-of-two feature scales; then the transposed, pre-scaled sample chunks (fp16 variant).
+// zpack = [GU_HDR_WORDS words | image]: what vbmp_gram_zpack hands back to the caller, who may keep it for as long as the
+// samples do not change (the rows of an EM run are the same every iteration, dists/Mixture.py:54-62).
+int launch_gram_zpack(const float* z0, int d0, const float* z1, int d1, long long N, void* zpack, cudaStream_t st) {
+  const int D = d0 + d1;
+  uint32_t* cmax = (uint32_t*)zpack;
+  if (cudaMemsetAsync(cmax, 0, GU_HDR_WORDS * sizeof(uint32_t), st) != cudaSuccess) {
+    set_error("gram_zpack: memset failed"); return VBMP_ERR_CUDA;
+  }
+  const int cg = gu_num_sms() * 4;
+  gram_colmax_kernel<<<cg, 256, 0, st>>>(z0, d0, N, 0, cmax);
+  if (d1 > 0) gram_colmax_kernel<<<cg, 256, 0, st>>>(z1, d1, N, d0, cmax);
+  int rc = check_launch("gram_colmax");
+  if (rc) return rc;
+  gram_zprep_kernel<<<gu_num_sms() * 8, 256, 0, st>>>(z0, d0, z1, d1, N, cmax, (uint8_t*)(cmax + GU_HDR_WORDS), gu_zrec(D));
+  return check_launch("gram_zprep");
+}
+bool gram_zpack_usable(long long N, int K, int Dp, int d0, int d1) {
+  return gu_use_f16() && gram_umma_supported(N, 1, 1, 1, K, Dp, d0, d1, true);
+}
+
 int launch_gram_umma(const GramArgs& a, float* gram, void* ws, size_t ws_bytes, cudaStream_t st) {
   GuArgs g{};
   g.d0 = a.d0; g.d1 = a.d1; g.N = a.N; g.K = a.K;
@@ -746,56 +787,61 @@ int launch_gram_umma(const GramArgs& a, float* gram, void* ws, size_t ws_bytes, 
   gu_plan(a.N, a.K, D, gu_num_sms(), &g);
   g.kcb = a.K < GU_CB ? a.K : GU_CB;
   g.FL = gu_fl();
-  const size_t part_bytes = ((size_t)g.splits * g.Kp * g.PP * sizeof(float) + 255) / 256 * 256;
-  const size_t need = (size_t)g.splits * g.Kp * g.PP * sizeof(float) + 512 + GU_HDR_WORDS * sizeof(uint32_t) + gu_rp_bytes(a.N, g.ncb) + 256 + gu_zt_bytes(a.N, D);
-  if (ws_bytes < need) { set_error("gram_umma: workspace too small (%zu < %zu)", ws_bytes, need); return VBMP_ERR_WORKSPACE; }
-  uint32_t* hdr = (uint32_t*)(((size_t)ws + 255) / 256 * 256);
-  g.part = (float*)(hdr + GU_HDR_WORDS);
-  const bool pair = gu_pair_mode(a.K);
   const bool f16 = gu_use_f16();
-  int rc;
-  if (f16) {
-    // column maxima -> exact power-of-two feature scales; the fp16 kernel; the TF32 kernel as its conditional fallback
-    if (cudaMemsetAsync(hdr, 0, GU_HDR_WORDS * sizeof(uint32_t), st) != cudaSuccess) {
-      set_error("gram_umma: memset failed"); return VBMP_ERR_CUDA;
-    }
-    const int cg = gu_num_sms() * 4;
-    gram_colmax_kernel<<<cg, 256, 0, st>>>(a.z0, a.d0, a.N, 0, hdr);
-    if (a.d1 > 0) gram_colmax_kernel<<<cg, 256, 0, st>>>(a.z1, a.d1, a.N, a.d0, hdr);
-    rc = check_launch("gram_colmax");
-    if (rc) return rc;
-    g.hdr = hdr;
-    g.nsb = gu_nsb(a.N);
-    uint8_t* rp = (uint8_t*)g.part + part_bytes;
-    if (a.rpack) {
-      g.rp = a.rpack;                                        // already written by the E-step's normaliser
-    } else {
-      g.rp = rp;
-      gram_rsplit_kernel<<<gu_num_sms() * 8, 256, 0, st>>>(a.p, a.N, a.K, g.ncb, g.nsb, rp, hdr);
-      rc = check_launch("gram_rsplit");
-      if (rc) return rc;
-    }
-    uint8_t* zt = rp + (gu_rp_bytes(a.N, g.ncb) + 255) / 256 * 256;
-    g.zt = zt;
-    g.zrec = gu_zrec(D);
-    gram_zprep_kernel<<<gu_num_sms() * 8, 256, 0, st>>>(a.z0, a.d0, a.z1, a.d1, a.N, hdr, zt, g.zrec);
-    rc = check_launch("gram_zprep");
-    if (rc) return rc;
-    // 16 chunks of 32 samples per first-level block: a kind::f16 MMA accumulates 16 samples per step (TF32: 8), so the
-    // truncation bias per block (-1.6e-6, tools/gram_bias.py) matches the TF32 variant's 256-sample blocks while the
-    // fold, during which the tensor pipe idles, comes half as often
-    GuArgs g16 = g;
-    rc = gu_launch_main<true>(a, g16, pair, st);
-    if (rc) return rc;
-  } else {
-    g.hdr = nullptr;
-  }
-  rc = gu_launch_main<false>(a, g, pair, st);
-  if (rc) return rc;
+  const size_t part_bytes = gu_al((size_t)g.splits * g.Kp * g.PP * sizeof(float));
+  const size_t need = gram_umma_workspace_bytes(a.N, a.G, a.K, a.d0, a.d1, a.Dp, a.rpack != nullptr, a.zpack != nullptr);
+  if (ws_bytes < need) { set_error("gram_umma: workspace too small (%zu < %zu)", ws_bytes, need); return VBMP_ERR_WORKSPACE; }
+  uint32_t* flag = (uint32_t*)gu_al((size_t)ws);
+  g.part = (float*)(flag + GU_HDR_WORDS);
+  const bool pair = gu_pair_mode(a.K);
   const int D1 = D + 1;
   const long long tot = (long long)a.K * g.P;
-  gram_pair_reduce_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(g.part, g.splits, a.K, g.Kp, g.PP, D1, g.hdr, gram);
-  return check_launch("gram_pair_reduce");
+  const unsigned rgrid = (unsigned)((tot + 255) / 256);
+  int rc;
+  if (!f16) {
+    g.flag = nullptr; g.cmax = nullptr;
+    rc = gu_launch_main<false>(a, g, pair, st);
+    if (rc) return rc;
+    gram_pair_reduce_kernel<0><<<rgrid, 256, 0, st>>>(g.part, g.splits, a.K, g.Kp, g.PP, D1, nullptr, nullptr, gram);
+    return check_launch("gram_pair_reduce");
+  }
+  if (cudaMemsetAsync(flag, 0, GU_HDR_WORDS * sizeof(uint32_t), st) != cudaSuccess) {
+    set_error("gram_umma: memset failed"); return VBMP_ERR_CUDA;
+  }
+  g.flag = flag;
+  g.nsb = gu_nsb(a.N);
+  uint8_t* next = (uint8_t*)g.part + part_bytes;
+  if (a.rpack) {
+    g.rp = a.rpack;                                        // already written by the E-step's normaliser
+  } else {
+    g.rp = next;
+    gram_rsplit_kernel<<<gu_num_sms() * 8, 256, 0, st>>>(a.p, a.N, a.K, g.ncb, g.nsb, next, flag);
+    rc = check_launch("gram_rsplit");
+    if (rc) return rc;
+    next += gu_al(gu_rp_bytes(a.N, g.ncb));
+  }
+  const uint8_t* zp = a.zpack;
+  if (!zp) {                                               // no image handed in: make it in the workspace
+    rc = launch_gram_zpack(a.z0, a.d0, a.z1, a.d1, a.N, next, st);
+    if (rc) return rc;
+    zp = next;
+  }
+  g.cmax = (const uint32_t*)zp;
+  g.zt = zp + GU_HDR_WORDS * sizeof(uint32_t);
+  g.zrec = gu_zrec(D);
+  // 16 chunks of 32 samples per first-level block: a kind::f16 MMA accumulates 16 samples per step (TF32: 8), so the
+  // truncation bias per block (-1.6e-6, tools/gram_bias.py) matches the TF32 variant's 256-sample blocks while the
+  // fold, during which the tensor pipe idles, comes half as often
+  rc = gu_launch_main<true>(a, g, pair, st);
+  if (rc) return rc;
+  // reduce + resolution check; then the TF32 kernel and its reduce, both of which return at once unless the flag is up
+  gram_pair_reduce_kernel<1><<<rgrid, 256, 0, st>>>(g.part, g.splits, a.K, g.Kp, g.PP, D1, g.cmax, flag, gram);
+  rc = check_launch("gram_pair_reduce");
+  if (rc) return rc;
+  rc = gu_launch_main<false>(a, g, pair, st);
+  if (rc) return rc;
+  gram_pair_reduce_kernel<2><<<rgrid, 256, 0, st>>>(g.part, g.splits, a.K, g.Kp, g.PP, D1, nullptr, flag, gram);
+  return check_launch("gram_pair_reduce2");
 }
 
 }  // namespace vbmp

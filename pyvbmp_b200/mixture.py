@@ -12,17 +12,19 @@ from .dirichlet import Dirichlet
 from .niw import NormalInverseWishart
 
 
-def fused_update_assignments(self, X):
+def fused_update_assignments(self, X, fallback=None):
     """dists/Mixture.py:38-45 on the CUDA path.  Also used as the method patch install() puts on the
-    reference's Mixture class."""
+    reference's Mixture class (``fallback`` = the reference's own method, taken for anything this does not fuse)."""
     dist = self.dist
-    fusable = (isinstance(dist, NormalInverseWishart) and self.event_dim == 1 and dist.event_dim == 1)
+    other = fallback if fallback is not None else generic_update_assignments
+    fusable = (isinstance(dist, NormalInverseWishart) and self.event_dim == 1 and dist.event_dim == 1
+               and (fallback is None or dist.mu.is_cuda))
     if not fusable:
-        return generic_update_assignments(self, X)
+        return other(self, X)
     Xv = X.view(X.shape[:-dist.event_dim] + self.event_dim * (1,) + dist.event_shape)
     plan = dist._plan(Xv)
     if not plan.k_is_batch:
-        return generic_update_assignments(self, X)
+        return other(self, X)
     dev = dist.mu.device
     W, m, cst, info, Dp = dist._prep(plan, logprior=self.pi.loggeomean())
     Xc = _lib.f32(Xv, dev).reshape(plan.N, plan.GX, dist.dim)

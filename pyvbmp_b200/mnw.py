@@ -1,8 +1,8 @@
 """MatrixNormalWishart node with the reference's interface for the VB-EM hot path
-(transforms/MatrixNormalWishart.py:8-471): Elog_like / raw_update / ss_update / KLqprior and the
-K-sized expectation getters.  The mask / X_mask branches and the message-passing methods
-(forward / backward / predict / update(pX, pY)) are outside the scope table
-and raise NotImplementedError instead of silently running something else.
+(transforms/MatrixNormalWishart.py:8-471): Elog_like / raw_update / ss_update / KLqprior, the expectation-input
+update(pX, pY, p) / Elog_like_given_pX_pY, predict and the K-sized expectation getters.  The mask / X_mask branches
+and the message-passing methods (forward / backward / Elog_like_X ...) are outside the scope table:
+the class pyvbmp_b200.install() binds into a pyVBMP tree inherits them from the reference; stand-alone they are absent.
 """
 from __future__ import annotations
 
@@ -303,12 +303,17 @@ class MatrixNormalWishart():
             out = out.sum(-1)
         return out
 
-    def _out_of_scope(self, *a, **k):
-        raise NotImplementedError("message-passing methods of MatrixNormalWishart are outside the VB-EM hot path "
-                                  "(SURVEY.md §2.1 #5)")
+    # The message-passing methods (transforms/MatrixNormalWishart.py:251-398: Elog_like_X, forward, backward, ...) are not
+    # defined here on purpose: the class install() binds into a pyVBMP tree inherits them from the reference class
+    # (pyvbmp_b200/install.py), and this stand-alone class says where they live instead of running something else.
+    _REFERENCE_ONLY = ("Elog_like_X", "Elog_like_X_given_pY", "Elog_like_X_given_Y", "Eforward", "forward", "backward",
+                       "postdict", "predict_given_pX", "Ebackward", "forward_old")
 
-    Elog_like_X = Elog_like_X_given_pY = Eforward = forward = backward = _out_of_scope
-    postdict = predict_given_pX = Ebackward = forward_old = _out_of_scope
+    def __getattr__(self, name):
+        if name in MatrixNormalWishart._REFERENCE_ONLY:
+            raise AttributeError(f"MatrixNormalWishart.{name} is a message-passing method outside the VB-EM hot path "
+                                 "(SURVEY.md §2.1 #5); pyvbmp_b200.install() keeps the reference's implementation of it")
+        raise AttributeError(f"{type(self).__name__!r} object has no attribute {name!r}")
 
     # ---- K-sized expectations (transforms/MatrixNormalWishart.py:400-471) ------------------------------
     def mean(self):

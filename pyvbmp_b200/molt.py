@@ -10,11 +10,14 @@ from .dirichlet import Dirichlet
 from .mnw import MatrixNormalWishart
 
 
-def fused_update_assignments(self, X, Y):
-    """transforms/MixtureofLinearTransforms.py:34-41 on the CUDA path (also the install() method patch)."""
+def fused_update_assignments(self, X, Y, fallback=None):
+    """transforms/MixtureofLinearTransforms.py:34-41 on the CUDA path (also the install() method patch; ``fallback`` = the
+    reference's own method, taken for anything this does not fuse)."""
     W = self.W
-    if not isinstance(W, MatrixNormalWishart) or self.batch_dim != 0 or W.event_dim != 2:
-        return generic_update_assignments(self, X, Y)
+    other = fallback if fallback is not None else generic_update_assignments
+    if (not isinstance(W, MatrixNormalWishart) or self.batch_dim != 0 or W.event_dim != 2
+            or (fallback is not None and not W.mu.is_cuda)):
+        return other(self, X, Y)
     Xv, Yv = X.unsqueeze(-3), Y.unsqueeze(-3)
     plan = W._plan(Xv)
     dev = W.mu.device

@@ -27,9 +27,16 @@ class Wishart():
 
         self.invU_0 = (scale ** 2 * torch.eye(self.dim, requires_grad=False)).expand(batch_shape + event_shape)
         self.nu_0 = torch.tensor(self.dim + 2.0).expand(batch_shape + event_shape[:-2])
-        # constructor-time constants of a scaled identity (one-off, closed form)
-        s2 = float(scale) ** 2
-        self.logdet_invU_0 = torch.full(tuple(batch_shape + event_shape[:-2]), self.dim * math.log(s2))
+        # constructor-time constants of a scaled identity (one-off, closed form: logdet = dim log scale^2, U = I / scale^2);
+        # scale may be any tensor that broadcasts against batch_shape + event_shape, as in the reference
+        s2 = torch.as_tensor(scale, dtype=torch.float32) ** 2
+        if s2.ndim >= 2:
+            assert s2.shape[-1] == 1 and s2.shape[-2] == 1, "scale must broadcast as a scalar per matrix"
+            ld = self.dim * s2[..., 0, 0].log()
+        else:
+            assert s2.numel() == 1, "scale must broadcast as a scalar per matrix"
+            ld = self.dim * s2.reshape(()).log()
+        self.logdet_invU_0 = ld.expand(tuple(batch_shape + event_shape[:-2])).clone()
         self.invU = self.invU_0
         self.U = (torch.eye(self.dim, requires_grad=False) / s2).expand(batch_shape + event_shape)
         self.nu = self.nu_0

@@ -1,0 +1,152 @@
+"""Model-level GPU parity at the BASELINE.json shapes (SURVEY.md Appendix D rows that the small golden fixtures do
+not reach): MixtureofLinearTransforms n = p = 32, K = 64, N = 65 536 (cfg3 shape) and ARHMM K = 32, n = p = 16,
+T = 64, S = 64 (cfg4 shape), step-wise against the fp64 oracle.  These are the cases where mnw_prep, the tcgen05
+E-step, the tcgen05 Gram (D = 64 / 32 with a two-part z = [x; y]) and mnw_update meet the oracle TOGETHER; plus the
+standalone Wishart entry points.
+"""
+import pytest
+import torch
+
+import pyvbmp_b200 as V
+from oracle import vbem_oracle as O
+from _util import assert_close, argmax_mismatch_report, assert_maxabs
+from test_cuda_parity import set_state, get
+
+pytestmark = pytest.mark.gpu
+PARITY = 1e-4
+DEV = "cuda:0"
+
+MOLT_STATE = ("W.mu", "W.invV", "W.V", "W.invU.invU", "W.invU.U", "W.invU.nu", "pi.alpha")
+
+
+def _cfg3_data(N, n=32, p=32, K=64, seed=11):
+    """SURVEY.md §8d cfg3 recipe: X ~ N(0, I), W_k = randn / sqrt(p), b_k = randn, Y = W_z x + b_z + 0.1 randn."""
+    g = torch.Generator().manual_seed(seed)
+    X = torch.randn(N, p, generator=g)
+    W = torch.randn(K, n, p, generator=g) / p ** 0.5
+    b = torch.randn(K, n, generator=g)
+    z = torch.randint(K, (N,), generator=g)
+    Y = torch.einsum("nij,nj->ni", W[z], X) + b[z] + 0.1 * torch.randn(N, n, generator=g)
+    return X.unsqueeze(-1), Y.unsqueeze(-1)
+
+
+def _p_gate(p_gpu, ref, what):
+    """Responsibilities against the fp64 oracle: 2e-5 where the logits are O(1e2) or smaller (converged states; the
+    reference's own fp32 noise there is 1.6e-5), otherwise the fp32 floor eps32 * |logit|."""
+    L = float(ref["log_p"].max(-1)[0].abs().max())
+    err = float((p_gpu.cpu().double() - ref["p"]).abs().max())
+    print(f"[p-gate] {what}: max |dp| = {err:.2e} at |logit| <= {L:.2e}")
+    assert_maxabs(p_gpu.cpu().double(), ref["p"], max(2e-5, 2e-7 * L), f"{what} (|logit| {L:.2e})")
+    nbad, margins = argmax_mismatch_report(p_gpu, ref["p"], ref["log_p"])
+    assert nbad == 0 or max(margins) < 1e-3, (what, nbad, margins)
+    return L
+
+
+def test_molt_cfg3_shape_vs_fp64_oracle():
+    """MoLT n = p = 32, K = 64, N = 65 536: three step-wise E+M iterations (state copied from the oracle before each)."""
+    N, n, p, K = 65536, 32, 32, 64
+    X, Y = _cfg3_data(N, n, p, K)
+    torch.manual_seed(5)
+    m = V.MixtureofLinearTransforms(n, p, K)
+    ref = O.molt_new(n, p, K)
+    O.load_state(ref, {"W.mu": m.W.mu.clone(), "pi.alpha": m.pi.alpha.clone()})
+    O.to_dtype(ref, torch.float64)
+    m.to(DEV)
+    Xd, Yd, X64, Y64 = X.to(DEV), Y.to(DEV), X.double(), Y.double()
+    from pyvbmp_b200 import _lib
+    for it in range(3):
+        set_state(m, {k: v.float() for k, v in O.flatten_state(ref).items()})
+        n0 = _lib.LAUNCHES
+        m.raw_update(Xd, Yd, iters=1)
+        assert _lib.LAUNCHES > n0
+        tr = O.molt_raw_update(ref, X64, Y64, 1, exact=False, chunk=8192)
+        assert abs(float(m.ELBO_last) - float(tr[0])) <= PARITY * abs(float(tr[0])), it
+        _p_gate(m.p, ref, f"p it{it}")
+        assert_close(m.logZ, ref["logZ"], PARITY, f"logZ_n it{it}")
+        flat = O.flatten_state(ref)
+        for k in MOLT_STATE:
+            # iteration 0 starts from O(1e3) logits under the broad prior: the reference's own fp32 run is ~1.5e-4 from its
+            # fp64 run there; from iteration 1 on the 1e-4 gate applies against the fp64 truth
+            assert_close(get(m, k), flat[k], 3e-4 if it == 0 else PARITY, f"{k} it{it}")
+        assert_maxabs(m.W.logdetinvV.cpu().double(), flat["W.logdetinvV"], 2e-3, "logdetinvV")
+        assert int((m.W.info != 0).sum()) == 0
+    # converged-state E-step: a few free-running iterations of the oracle, then one E-step on its state
+    O.molt_raw_update(ref, X64, Y64, 3, exact=False, chunk=8192)
+    set_state(m, {k: v.float() for k, v in O.flatten_state(ref).items()})
+    O.molt_update_assignments(ref, X64, Y64, exact=False, chunk=8192)
+    m.update_assignments(Xd, Yd)
+    L = _p_gate(m.p, ref, "p converged")
+    assert L < 2e2, L                                     # i.e. the 2e-5 gate was the one applied
+    assert_close(m.logZ, ref["logZ"], PARITY, "logZ_n converged")
+    assert (m.assignment().cpu() == ref["p"].argmax(-1)).float().mean() > 0.9999
+
+
+def test_arhmm_cfg4_shape_vs_fp64_oracle():
+    """ARHMM K = 32, n = p = 16, T = 64, S = 64 (tcgen05 E-step and Gram on z = [x; y], D = 32; forward-backward kernel)."""
+    K, n, T, S = 32, 16, 64, 64
+    g = torch.Generator().manual_seed(3)
+    # a switching AR(1): A_k = 0.95 Q_k (random orthogonal), sticky transitions (tests/test_models.py:20-28)
+    Q = torch.linalg.qr(torch.randn(K, n, n, generator=g))[0] * 0.95
+    trans = 4.0 * torch.eye(K) + torch.rand(K, K, generator=g)
+    trans = trans / trans.sum(-1, True)
+    y = torch.zeros(T + 1, S, n)
+    y[0] = torch.randn(S, n, generator=g)
+    z = torch.randint(K, (S,), generator=g)
+    for t in range(T):
+        z = torch.multinomial(trans[z], 1, generator=g).squeeze(-1)
+        y[t + 1] = torch.einsum("sij,sj->si", Q[z], y[t]) + 0.3 * torch.randn(S, n, generator=g)
+    X = y[:-1].reshape(T, S, 1, n, 1).contiguous()
+    Y = y[1:].reshape(T, S, 1, n, 1).contiguous()
+    torch.manual_seed(9)
+    h = V.ARHMM(K, n, n)
+    ref = O.arhmm_new(K, n, n)
+    O.load_state(ref, {"obs.mu": h.obs_dist.mu.clone(), "transition.alpha": h.transition.alpha.clone(),
+                       "initial.alpha": h.initial.alpha.clone()})
+    O.to_dtype(ref, torch.float64)
+    h.to(DEV)
+    Xd, Yd, X64, Y64 = X.to(DEV), Y.to(DEV), X.double(), Y.double()
+    keys = ("obs.mu", "obs.invV", "obs.V", "obs.invU.invU", "obs.invU.U", "obs.invU.nu", "transition.alpha", "initial.alpha")
+    for it in range(3):
+        set_state(h, {k.replace("obs.", "obs_dist."): v.float() for k, v in O.flatten_state(ref).items()})
+        ol = h.obs_logits((Xd, Yd))
+        ol_ref = O.arhmm_obs_logits(ref, X64, Y64, exact=False)
+        assert ol.shape == ol_ref.shape
+        # logits relative to their own magnitude (fp32 floor), and absolutely near each row's maximum
+        assert_close(ol, ol_ref, 2e-6, f"obs_logits it{it}")
+        h.update((Xd, Yd), iters=1)
+        tr = O.arhmm_update(ref, X64, Y64, 1, exact=False)
+        L = float(ol_ref.abs().max())
+        assert_maxabs(h.p.cpu().double(), ref["p"], max(5e-5, 1e-6 * L), f"p after forward-backward it{it} (|logit| {L:.1e})")
+        assert_close(h.logZ, ref["logZ"], PARITY, f"logZ it{it}")
+        assert_close(h.NA, ref["NA"], PARITY, f"NA it{it}")
+        assert abs(float(h.ELBO_last) - float(tr[0])) <= PARITY * abs(float(tr[0])), it
+        flat = O.flatten_state(ref)
+        for k in keys:
+            assert_close(get(h, k.replace("obs.", "obs_dist.")), flat[k], 3e-4 if it == 0 else PARITY, f"{k} it{it}")
+
+
+def test_wishart_standalone_update_and_kl():
+    """Wishart.ss_update / KLqprior / ElogdetinvSigma called directly (dists/Wishart.py:43-56, 82-94): SURVEY.md §8 a9."""
+    d, K = 24, 7
+    g = torch.Generator().manual_seed(2)
+    torch.manual_seed(0)
+    w = V.Wishart((d, d), (K,), scale=torch.tensor(0.6)).to(DEV)
+    ref = O.wishart_new(d, (K,), scale=0.6, dtype=torch.float64)
+    for step, (lr, beta) in enumerate([(1.0, None), (0.5, None), (0.7, 0.9)]):
+        A = torch.randn(K, 40, d, generator=g)
+        SExx = A.transpose(-1, -2) @ A
+        Nk = torch.full((K,), 40.0) + torch.rand(K, generator=g)
+        w.ss_update(SExx.to(DEV), Nk.to(DEV), lr=lr, beta=beta)
+        O.wishart_ss_update(ref, SExx.double(), Nk.double(), lr=lr, beta=beta)
+        for k in ("invU", "U", "nu"):
+            assert_close(getattr(w, k), ref[k], PARITY, f"{k} step{step}")
+        assert_maxabs(w.logdet_invU.cpu().double(), ref["logdet_invU"], 1e-4 * d, f"logdet step{step}")
+        assert_close(w.KLqprior(), O.wishart_kl(ref), PARITY, f"KL step{step}")
+        assert_close(w.ElogdetinvSigma(), O.wishart_ElogdetinvSigma(ref), PARITY, f"ElogdetinvSigma step{step}")
+        w.check()
+    # a tensor-valued (per-component) scale, as the reference's constructor accepts (dists/Wishart.py:9-26)
+    sc = (0.5 + torch.rand(K, 1, 1, generator=g))
+    w2 = V.Wishart((d, d), (K,), scale=sc)
+    assert_close(w2.invU_0, sc ** 2 * torch.eye(d), 1e-7, "invU_0 per-component scale")
+    assert_close(w2.logdet_invU_0, (sc ** 2 * torch.eye(d)).logdet(), 1e-5, "logdet_invU_0 per-component scale")
+    assert_close(w2.U, (sc ** 2 * torch.eye(d)).inverse(), 1e-6, "U per-component scale")

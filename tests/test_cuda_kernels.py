@@ -154,6 +154,85 @@ def test_gram_weights_beyond_fp16_range_use_the_tf32_path():
     assert float((G.double() - Gref).abs().max() / Gref.abs().max()) <= 1e-5
 
 
+def _per_component_relerr(G, Gref, min_mass=4.0):
+    """max over components that own some mass of ||G_k - Gref_k||_F / ||Gref_k||_F, and the same for each component's
+    diagonal entry by entry (every feature in that component's own scale)."""
+    D = Gref.shape[-1] - 1
+    keep = Gref[:, D, D] > min_mass
+    E = (G.double() - Gref)
+    fro = E.flatten(1).norm(dim=1) / Gref.flatten(1).norm(dim=1).clamp_min(1e-300)
+    dg = E.diagonal(dim1=-1, dim2=-2).abs() / Gref.diagonal(dim1=-1, dim2=-2).abs().clamp_min(1e-300)
+    return float(fro[keep].max()), float(dg[keep].max())
+
+
+@pytest.mark.parametrize("case", ["outlier", "tight_cluster", "plain"])
+def test_gram_data_outside_the_fp16_window(case):
+    """One feature scale per COLUMN cannot cover every data set in fp16's window: a single huge outlier in a column pushes
+    every ordinary sample ~20 binades under that column's scale, and a tight cluster inside a wide data range sits far below
+    every column's scale.  The fp16 kernel's products for those samples fall into fp16 subnormals (or flush to zero: the
+    covariance of the components that own them would collapse); the first reduce detects a component whose mean square in
+    a feature is below the resolvable floor and the TF32 kernel recomputes.  Gate: PER-COMPONENT relative error, each
+    diagonal entry in its own scale — a global-maximum norm cannot see the damage."""
+    N, d0, K = 6000, 64, 16
+    dev = torch.device(DEV)
+    g = torch.Generator(device=dev).manual_seed(11)
+    lab = torch.randint(K, (N,), generator=g, device=dev)
+    mu = torch.randn(K, d0, generator=g, device=dev)
+    z = mu[lab] + 0.5 * torch.randn(N, d0, generator=g, device=dev)
+    if case == "outlier":
+        z[17, 5] = 1.0e6                                       # one wild value in column 5
+    elif case == "tight_cluster":
+        own = lab == 3
+        z[own] = 1e-5 * (1.0 + 0.1 * torch.randn(int(own.sum()), d0, generator=g, device=dev))    # values ~1e-5 of the range
+    P = torch.full((N, K), 1e-4, device=dev)
+    P[torch.arange(N, device=dev), lab] = 1.0 - 1e-4 * (K - 1)
+    P = P.contiguous()
+    xg = torch.zeros(1, dtype=torch.int32, device=DEV)
+    zt = torch.cat([z.double(), torch.ones(N, 1, device=DEV, dtype=torch.float64)], 1)
+    Gref = torch.einsum("nk,ni,nj->kij", P.double(), zt, zt)
+    G = _lib.gram(z.contiguous(), None, N, 1, xg, P.view(N, 1, K), 1, xg, 1, K, _lib.pad_dim(d0)).view(K, d0 + 1, d0 + 1)
+    fro, dg = _per_component_relerr(G, Gref)
+    assert fro <= 1e-5, (case, fro)
+    assert dg <= 2e-5, (case, dg)
+
+
+def test_gram_sample_image_is_cached_per_data_set_and_invalidated_by_edits():
+    """K3's sample image (column maxima + transposed, pre-scaled chunks) is made once per data set: a second call on the
+    same rows reuses it (bit-identical Gram), an in-place edit of the rows (torch's version counter) or other rows at the
+    same size do not."""
+    N, d0, d1, K = 5000, 32, 32, 64
+    z, z0, z1, W, m, cst, Dp, L = _problem(N, d0, d1, K, seed=12)
+    xg = torch.zeros(1, dtype=torch.int32, device=DEV)
+    P = (L - torch.logsumexp(L, -1)[:, None]).exp().float().contiguous().view(N, 1, K)
+    key = _lib._rpack_key(P.device)
+    _lib._zpack_cache.clear()
+    n0 = _lib.LAUNCHES
+    G1 = _lib.gram(z0, z1, N, 1, xg, P, 1, xg, 1, K, Dp).clone()
+    n1 = _lib.LAUNCHES
+    assert key in _lib._zpack_cache
+    G2 = _lib.gram(z0, z1, N, 1, xg, P, 1, xg, 1, K, Dp).clone()
+    n2 = _lib.LAUNCHES
+    assert torch.equal(G1, G2)
+    assert (n1 - n0) - (n2 - n1) == 2                                    # the second call skipped the two image kernels
+    old = _lib.ZCACHE
+    _lib.ZCACHE = 0
+    try:
+        G0 = _lib.gram(z0, z1, N, 1, xg, P, 1, xg, 1, K, Dp).clone()     # image made inside the call's workspace
+    finally:
+        _lib.ZCACHE = old
+    assert torch.equal(G0, G1)
+    z0.mul_(3.0)                                                         # in-place edit: the cached image is stale
+    G3 = _lib.gram(z0, z1, N, 1, xg, P, 1, xg, 1, K, Dp)
+    zt = torch.cat([z0.double(), z1.double(), torch.ones(N, 1, device=DEV, dtype=torch.float64)], 1)
+    Gref = torch.einsum("nk,ni,nj->kij", P.view(N, K).double(), zt, zt)
+    assert float((G3.double() - Gref).abs().max() / Gref.abs().max()) <= 1e-5
+    z0b = (z0 * 0.5).contiguous()                                        # other rows, same shape
+    G4 = _lib.gram(z0b, z1, N, 1, xg, P, 1, xg, 1, K, Dp)
+    zt = torch.cat([z0b.double(), z1.double(), torch.ones(N, 1, device=DEV, dtype=torch.float64)], 1)
+    Gref = torch.einsum("nk,ni,nj->kij", P.view(N, K).double(), zt, zt)
+    assert float((G4.double() - Gref).abs().max() / Gref.abs().max()) <= 1e-5
+
+
 @pytest.mark.parametrize("N,d0,d1,K", [(5000, 64, 0, 256), (3001, 32, 32, 64), (2049, 16, 0, 132), (4099, 16, 16, 32)])
 def test_estep_hands_presplit_weights_to_gram(N, d0, d1, K):
     """K2 (mode 1) leaves the responsibilities pre-split for K3; the Gram from those images must equal (bit for bit) the

@@ -1,0 +1,248 @@
+"""install() must not take anything away from a pyVBMP tree (SURVEY.md §8b, Appendix D "untouched models still run
+through the boundary").  These tests need the reference itself: they run where it is importable
+(``PYVBMP_REFERENCE`` or /root/reference, i.e. the build container) and skip elsewhere.
+
+CPU part (no GPU needed): after install() the reference's out-of-scope models — LinearDynamicalSystems,
+DynamicMarkovBlanketDiscovery, dMixtureofLinearTransforms, masked MatrixNormalWishart, the message-passing methods —
+construct and update, and give the SAME numbers as before install() from the same seed (CPU-resident nodes keep the
+reference's own code; nothing in this library computes on the CPU).
+
+GPU part (``-m gpu``): the reference's OWN GaussianMixtureModel / MixtureofLinearTransforms / ARHMM classes, constructed
+under ``torch.set_default_device('cuda')`` after install(), run on libvbmp_b200.so and reproduce the golden fixtures
+made by the unmodified reference on the CPU.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import pyvbmp_b200 as V
+from _util import load_golden, tag, assert_close, assert_maxabs
+
+REF = os.environ.get("PYVBMP_REFERENCE", "/root/reference")
+HAVE_REF = os.path.isdir(os.path.join(REF, "dists")) and os.path.isdir(os.path.join(REF, "models"))
+needs_ref = pytest.mark.skipif(not HAVE_REF, reason="the pyVBMP reference tree is not available here")
+
+
+@pytest.fixture
+def ref_tree():
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    import dists, transforms, models          # noqa: F401,E401
+    yield sys.modules["dists"], sys.modules["transforms"], sys.modules["models"]
+    V.uninstall()
+
+
+def _lds_run(models):
+    torch.manual_seed(3)
+    T, B, obs, hid, cd, rd = 12, 5, 4, 2, 2, 2
+    y, u, r = torch.randn(T, B, obs), torch.randn(T, B, cd), torch.randn(T, B, rd)
+    lds = models.LinearDynamicalSystems((obs,), hid, cd, rd, latent_noise='shared')
+    lds.update(y, u, r, iters=2, lr=1.0, verbose=False)
+    return lds.px.mean().clone(), lds.ELBO().clone() if hasattr(lds, "ELBO") else torch.zeros(())
+
+
+def _dmolt_run(transforms):
+    torch.manual_seed(4)
+    n, p, nc, N = 3, 4, 3, 200
+    X, Y = torch.randn(N, p), torch.randn(N, n)
+    m = transforms.dMixtureofLinearTransforms(n, p, nc, batch_shape=(), pad_X=True)
+    m.raw_update(X, Y, iters=2, lr=1.0, verbose=False)
+    pY, pr = m.predict(X)
+    return pY.mean().clone(), pr.clone()
+
+
+def _dmbd_run(models):
+    torch.manual_seed(5)
+    T, B, nobj, od = 8, 3, 4, 2
+    data = torch.randn(T, B, nobj, od)
+    m = models.DynamicMarkovBlanketDiscovery(obs_shape=(nobj, od), role_dims=(2, 2, 2), hidden_dims=(2, 2, 2),
+                                             batch_shape=(), number_of_objects=1)
+    m.update(data, None, None, iters=1, latent_iters=1, lr=0.5, verbose=False)
+    return m.px.mean().clone(), m.obs_model.p.clone()
+
+
+def _masked_mnw_run(transforms):
+    torch.manual_seed(6)
+    n, p, K, N = 3, 4, 2, 50
+    mask = torch.ones(n, p, dtype=torch.bool)
+    mask[0, 1] = False
+    w = transforms.MatrixNormalWishart(event_shape=(n, p), batch_shape=(K,), mask=mask)
+    X, Y = torch.randn(N, 1, p, 1), torch.randn(N, 1, n, 1)
+    w.raw_update(X, Y, p=torch.rand(N, K))
+    return w.mu.clone(), w.Elog_like(X, Y).clone()
+
+
+def _message_passing_run(transforms, dists):
+    torch.manual_seed(7)
+    n, p, K, N = 3, 4, 2, 20
+    w = transforms.MatrixNormalWishart(event_shape=(n, p), batch_shape=(K,), pad_X=True)
+    X, Y = torch.randn(N, 1, p, 1), torch.randn(N, 1, n, 1)
+    w.raw_update(X, Y, p=torch.rand(N, K))
+    invS, invSmu, Res = w.Elog_like_X(Y)
+    pX = dists.MultivariateNormal_vector_format(mu=X, Sigma=torch.eye(p).expand(N, 1, p, p) * 0.1)
+    out = w.forward(pX)
+    pY = out[0] if isinstance(out, tuple) else out
+    return invS.clone(), invSmu.clone(), Res.clone(), pY.mean().clone()
+
+
+@needs_ref
+@pytest.mark.parametrize("which", ["lds", "dmolt", "dmbd", "masked_mnw", "message_passing"])
+def test_install_keeps_out_of_scope_models_working_on_cpu(ref_tree, which):
+    dists, transforms, models = ref_tree
+    run = {"lds": lambda: _lds_run(models), "dmolt": lambda: _dmolt_run(transforms), "dmbd": lambda: _dmbd_run(models),
+           "masked_mnw": lambda: _masked_mnw_run(transforms),
+           "message_passing": lambda: _message_passing_run(transforms, dists)}[which]
+    V.uninstall()
+    before = run()
+    n = V.install(REF)
+    assert n > 0
+    cls = V.installed_classes()
+    assert transforms.MatrixNormalWishart is cls["MatrixNormalWishart"]
+    assert issubclass(cls["MatrixNormalWishart"], V.MatrixNormalWishart)
+    after = run()
+    for a, b in zip(before, after):
+        assert a.shape == b.shape
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-6), (which, float((a - b).abs().max()))
+    V.uninstall()
+    assert transforms.MatrixNormalWishart is not cls["MatrixNormalWishart"]
+
+
+@needs_ref
+def test_installed_classes_are_subclasses_of_both(ref_tree):
+    dists, transforms, models = ref_tree
+    V.uninstall()
+    ref_niw, ref_w, ref_mnw = dists.NormalInverseWishart, dists.Wishart, transforms.MatrixNormalWishart
+    V.install(REF)
+    cls = V.installed_classes()
+    for key, ref, ours in (("NormalInverseWishart", ref_niw, V.NormalInverseWishart), ("Wishart", ref_w, V.Wishart),
+                           ("MatrixNormalWishart", ref_mnw, V.MatrixNormalWishart)):
+        assert issubclass(cls[key], ref) and issubclass(cls[key], ours)
+    # the reference's model modules now construct installed nodes
+    torch.manual_seed(0)
+    g = models.GaussianMixtureModel(4, 3)
+    assert isinstance(g.dist, cls["NormalInverseWishart"]) and isinstance(g.dist.invU, cls["Wishart"])
+    h = models.ARHMM(3, 2, 2)
+    assert isinstance(h.obs_dist, cls["MatrixNormalWishart"]) and isinstance(h.obs_dist.invU, cls["Wishart"])
+    # masked nodes are plain reference objects, message-passing methods are the reference's
+    w = transforms.MatrixNormalWishart(event_shape=(2, 2), batch_shape=(), mask=torch.ones(2, 2, dtype=torch.bool))
+    assert type(w) is ref_mnw
+    assert cls["MatrixNormalWishart"].forward is ref_mnw.forward
+    assert not hasattr(V.MatrixNormalWishart((2, 2), (3,)), "forward")
+    # identical RNG consumption: same seed -> same initial state as the reference class
+    V.uninstall()
+    torch.manual_seed(11)
+    a = models.GaussianMixtureModel(5, 3)
+    V.install(REF)
+    torch.manual_seed(11)
+    b = models.GaussianMixtureModel(5, 3)
+    assert torch.equal(a.dist.mu, b.dist.mu) and torch.equal(a.pi.alpha, b.pi.alpha)
+    assert torch.allclose(a.dist.invU.U, b.dist.invU.U) and torch.allclose(a.dist.invU.logdet_invU, b.dist.invU.logdet_invU)
+
+
+# -------------------------------------------------------------------------------------------------------------------
+# GPU: the reference's own model classes on the CUDA path, against the fixtures the unmodified reference produced
+# -------------------------------------------------------------------------------------------------------------------
+
+def _set_state(obj, flat, device):
+    for k, v in flat.items():
+        parts = k.split(".")
+        o = obj
+        ok = True
+        for a in parts[:-1]:
+            if not hasattr(o, a):
+                ok = False
+                break
+            o = getattr(o, a)
+        if ok and isinstance(getattr(o, parts[-1], None), (torch.Tensor, float)) and isinstance(v, torch.Tensor):
+            setattr(o, parts[-1], v.to(device))
+
+
+def _get(obj, path):
+    for a in path.split("."):
+        obj = getattr(obj, a)
+    return obj
+
+
+@pytest.fixture
+def cuda_default(ref_tree):
+    old = torch.empty(0).device
+    torch.set_default_device("cuda:0")
+    V.install(REF)
+    yield ref_tree
+    torch.set_default_device(old)
+    V.uninstall()
+
+
+@needs_ref
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["gmm_d2_k6", "gmm_d64_k32_overlap"])
+def test_reference_gmm_runs_on_the_cuda_path(cuda_default, name):
+    dists, transforms, models = cuda_default
+    from pyvbmp_b200 import _lib
+    fix = load_golden(name)
+    X = torch.as_tensor(fix["X"]).to("cuda:0")
+    nc, iters, lr = int(fix["nc"]), int(fix["iters"]), float(fix["lr"])
+    torch.manual_seed(0)
+    m = models.GaussianMixtureModel(nc, X.shape[-1])
+    assert type(m).__module__.startswith("models.") and m.dist.mu.is_cuda
+    _set_state(m, tag(fix, "init"), "cuda:0")
+    n0 = _lib.LAUNCHES
+    elbo = []
+    for i in range(iters):
+        m.update(X, 1, lr)                                    # the reference's Mixture.update loop (dists/Mixture.py:54-62)
+        elbo.append(float(m.ELBO_last))
+        if i == 0:
+            it1 = tag(fix, "iter1")
+            for k in ("dist.mu", "dist.lambda_mu", "dist.invU.invU", "dist.invU.U", "dist.invU.nu", "pi.alpha"):
+                assert_close(_get(m, k), it1[k], 1e-4, k)
+            assert_close(m.NA, it1["NA"], 1e-4, "NA")
+    assert _lib.LAUNCHES - n0 >= 5 * iters                    # K1, K2, KL, K3, K5 every iteration: the kernels ran
+    ref = fix["ELBO"]
+    assert np.max(np.abs(np.array(elbo) - ref) / np.abs(ref)) < 1e-4, (elbo, ref)
+    assert (m.assignment().cpu().numpy() == fix["final/assignment"]).mean() > 0.999
+
+
+@needs_ref
+@pytest.mark.gpu
+def test_reference_molt_and_arhmm_run_on_the_cuda_path(cuda_default):
+    dists, transforms, models = cuda_default
+    from pyvbmp_b200 import _lib
+    fix = load_golden("molt_n32_p32_k8")
+    n, p, K, iters = (int(fix[k]) for k in ("n", "p", "K", "iters"))
+    torch.manual_seed(0)
+    m = transforms.MixtureofLinearTransforms(n, p, K)
+    _set_state(m, tag(fix, "init"), "cuda:0")
+    X, Y = torch.as_tensor(fix["X"]).unsqueeze(-1).to("cuda:0"), torch.as_tensor(fix["Y"]).unsqueeze(-1).to("cuda:0")
+    n0 = _lib.LAUNCHES
+    elbo = []
+    for _ in range(iters):
+        m.raw_update(X, Y, iters=1)
+        elbo.append(float(m.ELBO_last))
+    assert _lib.LAUNCHES - n0 >= 5 * iters
+    assert np.max(np.abs(np.array(elbo) - fix["ELBO"]) / np.abs(fix["ELBO"])) < 1e-4
+    assert (m.assignment().cpu().numpy() == fix["final/assignment"]).mean() > 0.995
+    # the message-passing side of the same (CUDA-resident, updated) node is still the reference's code
+    pY, pr = m.predict(X)
+    assert pr.shape == (X.shape[0], K) and torch.isfinite(pY.mean()).all()
+
+    fix = load_golden("arhmm_k4_n2_p3")
+    K, n, p = int(fix["K"]), int(fix["n"]), int(fix["p"])
+    torch.manual_seed(0)
+    h = models.ARHMM(K, n, p)
+    _set_state(h, {k.replace("obs.", "obs_dist."): v for k, v in tag(fix, "init").items()}, "cuda:0")
+    X, Y = torch.as_tensor(fix["X"]).to("cuda:0"), torch.as_tensor(fix["Y"]).to("cuda:0")
+    elbo = []
+    n0 = _lib.LAUNCHES
+    for i in range(4):
+        h.update((X, Y), iters=1)
+        elbo.append(float(h.ELBO_last))
+        if i == 0:
+            it1 = tag(fix, "iter1")
+            assert_maxabs(h.p.cpu(), it1["p"], 2e-4, "p")
+            for k in ("obs.mu", "obs.invV", "obs.invU.invU", "transition.alpha", "initial.alpha"):
+                assert_close(_get(h, k.replace("obs.", "obs_dist.")), it1[k], 1e-4, k)
+    assert _lib.LAUNCHES - n0 >= 4 * 5
+    assert np.max(np.abs(np.array(elbo) - fix["ELBO"]) / np.abs(fix["ELBO"])) < 1e-4
