@@ -7,8 +7,15 @@ A "step" is one full EM iteration of GaussianMixtureModel NIW VB-EM (E-step + so
 weighted Gram statistics [+ all-reduce] + NIW update) over the rank's rows.  At N=1 the workload is
 BASELINE.json configs[1] (N=4 194 304, d=64, K=256, fp32); with N>1 ranks every rank owns the same
 number of rows (weak scaling, sample-sharded, one all-reduce of the statistics per iteration).
-Prints ONE JSON line on rank 0.  `--impl reference` times the CPU restatement of the reference's own
-algorithm (oracle/, "port") on the host cores on a bounded sample of the same workload.
+Prints ONE JSON line on rank 0.  Besides the contract's keys the line carries
+  * `secondary` (N=1): BASELINE.json configs[2] (MixtureofLinearTransforms N=8 388 608, n=p=32, K=64) and configs[3]
+    (ARHMM 4096 sequences x T=1024, d=16, K=32), each timed the same way (ms/step, per-kernel ms, roofline fraction);
+  * `cfg5` (N=8): BASELINE.json configs[4] at its stated size, 8 388 608 rows per GPU = 67 108 864 rows in total;
+  * `e2e_iters20`: one public call update(X_pinned_host, iters=20) — the rows cross the host link once per call;
+  * `replicas_bitwise_equal` (N>1): the posterior is bit-identical on every rank after the timed steps.
+`--impl reference` times the reference's own CPU path on the host cores on a bounded sample of the same workload:
+the UNMODIFIED reference when it is importable (baseline/_ref, `kind: "reference"`), else its restatement in
+oracle/ (`kind: "port"`).
 """
 import argparse
 import json
@@ -121,20 +128,42 @@ def measure_tf32_peak(device, seconds=1.5):
     return fl / best / 1e9, fl / sus / 1e9
 
 
-def cpu_port_iteration_rate(n_rows, iters, threads, seed=0):
-    """The reference's algorithm (broadcast multiply + sum over a materialised (N,K,d,d) temporary,
-    dists/NormalInverseWishart.py:83,93) restated in oracle/, on a bounded sample of the cfg2 workload."""
-    from oracle import vbem_oracle as O
+def _reference_tree():
+    """Path of an importable, unmodified pyVBMP tree (PYVBMP_REFERENCE, or the install under baseline/_ref), else None."""
+    for p in (os.environ.get("PYVBMP_REFERENCE"), os.path.join(ROOT, "baseline", "_ref")):
+        if p and os.path.isdir(os.path.join(p, "dists")) and os.path.isdir(os.path.join(p, "models")):
+            return p
+    return None
+
+
+def cpu_iteration_rate(n_rows, iters, warmup, threads, seed=0):
+    """Full EM iterations of the reference's CPU path on a bounded sample of the cfg2 workload.  The reference's algorithm is a
+    broadcast multiply + sum over a materialised (N,K,d,d) temporary (dists/NormalInverseWishart.py:83,93), so 512 rows is
+    the largest sample whose temporary fits comfortably (2 GiB).  Returns (updates/s, s/iteration, kind)."""
     torch.set_num_threads(threads)
     X = synth_rows(n_rows, torch.device("cpu"), 1234 + seed)
-    torch.manual_seed(0)
-    m = O.gmm_new(K, D)
-    m["dist"]["mu"] = X[torch.randint(n_rows, (K,))].clone()
-    O.mixture_update(m, X, 1, exact=True)            # warm-up iteration (allocator, MKL threads)
+    ref = _reference_tree()
+    if ref is not None:
+        if ref not in sys.path:
+            sys.path.insert(0, ref)
+        import models as ref_models                      # the unmodified reference (no install(): its own torch code)
+        torch.manual_seed(0)
+        m = ref_models.GaussianMixtureModel(K, D)
+        m.dist.mu = X[torch.randint(n_rows, (K,))].clone()
+        step = lambda n: m.update(X, iters=n, lr=1.0, verbose=False)      # noqa: E731
+        kind = "reference"
+    else:
+        from oracle import vbem_oracle as O
+        torch.manual_seed(0)
+        m = O.gmm_new(K, D)
+        m["dist"]["mu"] = X[torch.randint(n_rows, (K,))].clone()
+        step = lambda n: O.mixture_update(m, X, n, exact=True)             # noqa: E731
+        kind = "port"
+    step(max(warmup, 1))                                 # warm-up iterations (allocator, MKL threads)
     t0 = time.perf_counter()
-    O.mixture_update(m, X, iters, exact=True)
+    step(iters)
     dt = time.perf_counter() - t0
-    return iters * n_rows * K / dt, dt / iters
+    return iters * n_rows * K / dt, dt / iters, kind
 
 
 def run_reference(args, rank, world):
@@ -142,32 +171,119 @@ def run_reference(args, rank, world):
         return
     threads = os.cpu_count() or 1
     n_rows = args.ref_rows
-    torch.set_num_threads(threads)
-    from oracle import vbem_oracle as O
-    X = synth_rows(n_rows, torch.device("cpu"), 1234)
-    torch.manual_seed(0)
-    m = O.gmm_new(K, D)
-    m["dist"]["mu"] = X[torch.randint(n_rows, (K,))].clone()
-    for _ in range(args.warmup):
-        O.mixture_update(m, X, 1, exact=True)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        O.mixture_update(m, X, 1, exact=True)
-    dt = time.perf_counter() - t0
-    val = args.steps * n_rows * K / dt
+    val, s_per, kind = cpu_iteration_rate(n_rows, args.steps, args.warmup, threads)
+    what = ("the unmodified reference (models.GaussianMixtureModel.update on CPU torch)" if kind == "reference"
+            else "oracle/ restatement of the reference's op order")
     sample = (f"{n_rows} rows of the cfg2 recipe per step (largest chunk whose (N,K,d,d) fp32 temporary fits "
-              f"comfortably: {n_rows * K * D * D * 4 / 2**30:.1f} GiB); full EM iteration per step")
+              f"comfortably: {n_rows * K * D * D * 4 / 2**30:.1f} GiB); full EM iteration per step; {what}")
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": s_per * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "GaussianMixtureModel NIW VB-EM, d=64, K=256, fp32 (cfg2 recipe), CPU sample",
                    "rows_per_step": n_rows},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def numa_pin(dev_index):
+    """Bind this process to the CPUs next to its GPU BEFORE any pinned host memory is allocated (first touch then places the
+    staging buffers on the GPU's NUMA node).  Returns a short description for the JSON line."""
+    try:
+        pr = torch.cuda.get_device_properties(dev_index)
+        bus = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        base = f"/sys/bus/pci/devices/{bus}"
+        node = open(base + "/numa_node").read().strip()
+        cpus = open(base + "/local_cpulist").read().strip()
+        ids = set()
+        for part in cpus.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                ids.update(range(int(a), int(b) + 1))
+            elif part:
+                ids.add(int(part))
+        allowed = os.sched_getaffinity(0)
+        ids &= allowed
+        if ids and ids != allowed:
+            os.sched_setaffinity(0, ids)
+        return {"numa_node": node, "cpus": cpus, "pinned": bool(ids and ids != allowed), "host_cpus": len(allowed)}
+    except Exception as e:                       # containers without sysfs access: report and carry on
+        return {"error": str(e)[:80]}
+
+
+def time_steps(fn, steps, warmup, dev, barrier):
+    """W warm-up + K timed steps, CUDA events on the current stream, per-C-ABI-call events collected on the side."""
+    from pyvbmp_b200 import _lib
+    for _ in range(warmup):
+        fn()
+    barrier()
+    _lib.PROFILE = {}
+    n0 = _lib.lib().vbmp_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(steps):
+        fn()
+    ev1.record()
+    barrier()
+    prof, _lib.PROFILE = _lib.PROFILE, None
+    kern = {}
+    for name, evs in prof.items():
+        tt = sum(a.elapsed_time(b) for a, b in evs)
+        kern[name] = {"calls": len(evs), "ms_total": tt, "ms_avg": tt / max(len(evs), 1), "ms_per_step": tt / steps}
+    return ev0.elapsed_time(ev1), kern, int(_lib.lib().vbmp_launch_count() - n0)
+
+
+def secondary_cfg3(dev, peak, steps=5, warmup=3, N=8_388_608, p=32, n=32, Kc=64):
+    """BASELINE.json configs[2]: MixtureofLinearTransforms (MatrixNormalWishart regression), SURVEY.md §8d recipe."""
+    import pyvbmp_b200 as V
+    g = torch.Generator(device=dev).manual_seed(1)
+    X = torch.randn(N, p, generator=g, device=dev)
+    W = torch.randn(Kc, n, p, generator=g, device=dev) / p ** 0.5
+    b = torch.randn(Kc, n, generator=g, device=dev)
+    z = torch.randint(Kc, (N,), generator=g, device=dev)
+    Y = torch.empty(N, n, device=dev)
+    for a in range(0, N, 1 << 20):
+        e = min(a + (1 << 20), N)
+        Y[a:e] = torch.einsum("nij,nj->ni", W[z[a:e]], X[a:e]) + b[z[a:e]] + 0.1 * torch.randn(e - a, n, generator=g, device=dev)
+    torch.manual_seed(0)
+    m = V.MixtureofLinearTransforms(n, p, Kc, pad_X=True).to(dev)
+    Xc, Yc = X.unsqueeze(-1), Y.unsqueeze(-1)
+    ms, kern, launches = time_steps(lambda: m.raw_update(Xc, Yc, iters=1, lr=1), steps, warmup, dev, lambda: torch.cuda.synchronize(dev))
+    fl = 2 * (n * (p + 1) + n * n + (p + 1) ** 2) + 2 * (n + p + 1) ** 2       # SURVEY.md §8d: 14 788 at n = p = 32
+    val = steps * N * Kc / (ms / 1e3)
+    return {"workload": f"MixtureofLinearTransforms raw_update, N={N}, p={p} (+1 pad), n={n}, K={Kc} (BASELINE.json configs[2])",
+            "ms_per_step": ms / steps, "value": val, "unit": UNIT, "steps": steps, "warmup": warmup,
+            "flops_per_update": fl, "roofline_frac": val * fl / 1e12 / peak, "gpu_launches": launches,
+            "kernels_ms_per_step": {k: round(v["ms_per_step"], 4) for k, v in kern.items()}, "elbo_last": float(m.ELBO_last)}
+
+
+def secondary_cfg4(dev, peak, steps=5, warmup=3, S=4096, T=1024, d=16, Kc=32):
+    """BASELINE.json configs[3]: ARHMM with MatrixNormalWishart emissions, 4096 sequences x T = 1024 (SURVEY.md §8d recipe)."""
+    import pyvbmp_b200 as V
+    g = torch.Generator(device=dev).manual_seed(2)
+    A = 0.95 * torch.linalg.qr(torch.randn(Kc, d, d, generator=g, device=dev))[0]
+    P = 4 * torch.eye(Kc, device=dev) + torch.rand(Kc, Kc, generator=g, device=dev)
+    P = P / P.sum(-1, keepdim=True)
+    y = torch.zeros(T + 1, S, d, device=dev)
+    zt = torch.randint(Kc, (S,), generator=g, device=dev)
+    y[0] = torch.randn(S, d, generator=g, device=dev)
+    for t in range(T):
+        y[t + 1] = torch.einsum("sij,sj->si", A[zt], y[t]) + 0.3 * torch.randn(S, d, generator=g, device=dev)
+        zt = torch.multinomial(P[zt], 1, generator=g).squeeze(-1)
+    X = y[:-1].reshape(T, S, 1, d, 1).contiguous()
+    Y = y[1:].reshape(T, S, 1, d, 1).contiguous()
+    torch.manual_seed(0)
+    m = V.ARHMM(Kc, d, d).to(dev)
+    ms, kern, launches = time_steps(lambda: m.update((X, Y), iters=1, lr=1), steps, warmup, dev, lambda: torch.cuda.synchronize(dev))
+    fl = 2 * (d * (d + 1) + d * d + (d + 1) ** 2) + 2 * (2 * d + 1) ** 2       # SURVEY.md §8d: 3 812 at d = 16
+    val = steps * S * T * Kc / (ms / 1e3)
+    return {"workload": f"ARHMM update, {S} sequences x T={T}, d={d}, K={Kc} (BASELINE.json configs[3])",
+            "ms_per_step": ms / steps, "value": val, "unit": UNIT, "steps": steps, "warmup": warmup,
+            "flops_per_update": fl, "roofline_frac": val * fl / 1e12 / peak, "gpu_launches": launches,
+            "kernels_ms_per_step": {k: round(v["ms_per_step"], 4) for k, v in kern.items()}, "elbo_last": float(m.ELBO_last)}
 
 
 def main():
@@ -181,6 +297,9 @@ def main():
     ap.add_argument("--cpu-baseline-iters", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true")
+    ap.add_argument("--cfg5", choices=["auto", "on", "off"], default="auto",
+                    help="also time BASELINE.json configs[4] at 8 388 608 rows per GPU (auto: when 8 ranks run)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -193,73 +312,71 @@ def main():
         args.warmup = 3
 
     import torch.distributed as dist
-    import pyvbmp_b200 as V
-    from pyvbmp_b200 import _lib, sharding
-
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback)")
     dev = torch.device(f"cuda:{local_rank}")
     torch.cuda.set_device(dev)
+    numa = numa_pin(local_rank)                              # before the first pinned allocation
+    import pyvbmp_b200 as V
+    from pyvbmp_b200 import _lib, sharding
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # keep stdout to the ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
         sharding.enable()
 
-    n_rows = args.rows_per_gpu
-    X = synth_rows(n_rows, dev, 1234 + rank)
-    # replicated init: same seed on every rank; the initial means are rank 0's rows, broadcast once
-    torch.manual_seed(0)
-    m = V.GaussianMixtureModel(K, D)
-    idx = torch.randint(min(n_rows, 1 << 20), (K,))
-    m.to(dev)
-    mu0 = X[idx.to(dev)].clone()
-    if world > 1:
-        sharding.broadcast_(mu0, 0)
-    m.dist.mu = mu0
-
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    def max_over_ranks(ms):
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+
+    def new_model(X, n_rows):
+        # replicated init: same seed on every rank; the initial means are rank 0's rows, broadcast once
+        torch.manual_seed(0)
+        m = V.GaussianMixtureModel(K, D)
+        idx = torch.randint(min(n_rows, 1 << 20), (K,))
+        m.to(dev)
+        mu0 = X[idx.to(dev)].clone()
+        if world > 1:
+            sharding.broadcast_(mu0, 0)
+        m.dist.mu = mu0
+        return m
+
+    n_rows = args.rows_per_gpu
+    X = synth_rows(n_rows, dev, 1234 + rank)
+    m = new_model(X, n_rows)
+
     # ---- warm-up, then K timed steps (device-resident inputs) ----------------------------------------
+    sampler = ClockSampler(local_rank)
     for _ in range(args.warmup):
         m.update(X, 1)
     barrier()
-    sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    _lib.PROFILE = {}
-    _lib.LAUNCHES = 0
-    barrier()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for _ in range(args.steps):
-        m.update(X, 1)
-    ev1.record()
-    barrier()
-    ms = ev0.elapsed_time(ev1)
-    launches = _lib.LAUNCHES
-    prof = _lib.PROFILE
-    _lib.PROFILE = None
+    ms, kern, launches = time_steps(lambda: m.update(X, 1), args.steps, 0, dev, barrier)
     clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t)
+    ms = max_over_ranks(ms)
     elbo = float(m.ELBO_last)
     total_rows = n_rows * world
     value = args.steps * total_rows * K / (ms / 1e3)
 
-    # per-kernel device times from the CUDA events recorded around each C-ABI call in the timed region
-    kern = {}
-    for name, evs in prof.items():
-        tt = sum(a.elapsed_time(b) for a, b in evs)
-        kern[name] = {"calls": len(evs), "ms_total": tt, "ms_avg": tt / max(len(evs), 1)}
+    replicas_equal = None
+    if world > 1:
+        # the posterior must be the same bits on every rank (one all-reduce, then the identical replicated update)
+        sig = torch.cat([m.ELBO_last.reshape(1).double(), m.dist.mu.double().sum().reshape(1),
+                         m.dist.invU.invU.double().sum().reshape(1), m.pi.alpha.double().sum().reshape(1)])
+        buf = [torch.empty_like(sig) for _ in range(world)]
+        dist.all_gather(buf, sig)
+        replicas_equal = all(torch.equal(buf[0], b) for b in buf[1:])
 
     # ---- end-to-end through the public API with HOST buffers -----------------------------------------
-    e2e = None
+    e2e = e2e20 = None
     if not args.no_e2e:
         # the public call with HOST rows: Mixture.update(X_host) streams them through the device in row chunks
         # (H2D of chunk i+1 under the kernels of chunk i) and the caller reads ELBO / NA back every step
@@ -278,13 +395,56 @@ def main():
             torch.cuda.current_stream().synchronize()             # the caller reads the ELBO every step
         s1.record()
         barrier()
-        tms = torch.tensor([s0.elapsed_time(s1)], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-        e2e = {"value": e2e_steps * total_rows * K / (float(tms) / 1e3), "unit": UNIT,
+        tms = max_over_ranks(s0.elapsed_time(s1))
+        e2e = {"value": e2e_steps * total_rows * K / (tms / 1e3), "unit": UNIT,
                "h2d_bytes_per_step": X.numel() * 4, "d2h_bytes_per_step": res_h.numel() * 4,
-               "ms_per_step": float(tms) / e2e_steps,
-               "api": "GaussianMixtureModel.update(X_pinned_host, 1): chunked H2D overlapped with E-step + Gram"}
+               "ms_per_step": tms / e2e_steps,
+               "api": "GaussianMixtureModel.update(X_pinned_host, 1): chunked H2D overlapped with E-step + Gram, every step"}
+        # ONE call of 20 iterations on host rows (the reference's own usage, dists/Mixture.py:54-62: same X every iteration):
+        # the rows cross the host link once, iterations 2..20 run on the resident copy
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        m.update(Xh, 20)
+        res_h.copy_(torch.cat([m.ELBO_last.reshape(1), m.NA.reshape(-1)]), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        s1.record()
+        barrier()
+        tms = max_over_ranks(s0.elapsed_time(s1))
+        e2e20 = {"value": 20 * total_rows * K / (tms / 1e3), "unit": UNIT, "iters_per_call": 20,
+                 "h2d_bytes_per_call": X.numel() * 4, "d2h_bytes_per_call": res_h.numel() * 4, "ms_per_iteration": tms / 20,
+                 "api": "GaussianMixtureModel.update(X_pinned_host, 20): rows streamed once, then device-resident"}
+        del Xh
+
+    # ---- BASELINE.json configs[4] at its stated size: 8 388 608 rows per GPU -------------------------------------
+    cfg5 = None
+    if args.cfg5 == "on" or (args.cfg5 == "auto" and world == 8):
+        del m, X
+        _lib.release_workspaces()
+        torch.cuda.empty_cache()
+        torch.cuda.reset_peak_memory_stats(dev)
+        n5 = 8_388_608
+        X5 = synth_rows(n5, dev, 4321 + rank)
+        m5 = new_model(X5, n5)
+        steps5 = max(5, args.steps // 2)
+        for _ in range(3):
+            m5.update(X5, 1)
+        barrier()
+        ms5, kern5, _l5 = time_steps(lambda: m5.update(X5, 1), steps5, 0, dev, barrier)
+        ms5 = max_over_ranks(ms5)
+        hw = torch.tensor([float(torch.cuda.max_memory_allocated(dev))], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(hw, op=dist.ReduceOp.MAX)
+        v5 = steps5 * n5 * world * K / (ms5 / 1e3)
+        cfg5 = {"workload": f"GaussianMixtureModel NIW VB-EM, N={n5 * world} ({n5} rows/GPU x {world} GPU), d={D}, K={K} "
+                            "(BASELINE.json configs[4]; sample-sharded, one all-reduce of the statistics per iteration)",
+                "rows_per_gpu": n5, "n_total": n5 * world, "steps": steps5, "warmup": 3, "ms_per_step": ms5 / steps5,
+                "value": v5, "unit": UNIT, "elbo_last": float(m5.ELBO_last),
+                "per_gpu_vs_4Mi_rows_rate": (v5 / world) / (value / world),
+                "kernels_ms_per_step": {k: round(v["ms_per_step"], 4) for k, v in kern5.items()},
+                "step_tensor_frac": None, "mem_high_water_gib": float(hw) / 2 ** 30}
+        del m5, X5
+        m = X = None
 
     if rank == 0:
         peaks = {}
@@ -293,31 +453,37 @@ def main():
         except Exception:
             pass
         tf32_burst, tf32_sus = measure_tf32_peak(dev)
+        bf16_sus = peaks.get("bf16_tflops_sustained")
+        peak, peak_src = (bf16_sus, "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)") \
+            if bf16_sus else (1409.1, "fallback: B200_PROFILING.md sustained bf16 figure (MEASURED_PEAKS.json absent)")
+        if cfg5 is not None:
+            cfg5["step_tensor_frac"] = cfg5["value"] * FLOPS_PER_UPDATE / world / 1e12 / peak
         dom = max(kern, key=lambda k: kern[k]["ms_total"]) if kern else None
         roof = None
         if dom is not None:
             per_launch_flops = 2.0 * n_rows * K * D * D          # E-step GEMM or M-step Gram: 2 d^2 per update
-            ach = per_launch_flops / (kern[dom]["ms_avg"] / 1e3) / 1e12
-            traffic = None
-            try:
-                tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-                if n_rows == ROWS_PER_GPU and dom in tr:
-                    traffic = tr[dom]["bytes"] / 1e9           # GB per launch, from the committed ncu capture
-            except Exception:
-                pass
+            ach = per_launch_flops / (kern[dom]["ms_per_step"] / 1e3) / 1e12
+            traffic, traffic_src = None, None
+            for fn in ("r02_traffic.json", "r01_traffic.json"):
+                try:
+                    tr = json.load(open(os.path.join(ROOT, "profiles", fn)))
+                    if n_rows == ROWS_PER_GPU and dom in tr:
+                        traffic = tr[dom]["bytes"] / 1e9           # GB per launch, from the committed ncu capture
+                        traffic_src = f"static:profiles/{fn} (ncu --set full capture of this workload; not measured in this run)"
+                        break
+                except Exception:
+                    pass
             # The kernels issue 16-bit-operand MMAs (kind::f16, the bf16 rate), three split terms per algorithmic product:
             # the roofline denominator is the measured dense bf16 figure; `issued` counts the MMAs actually executed
             # per algorithmic flop (2 d^2 per sample*component): E-step 3 terms on the triangular 62.5 % of the columns +
-            # the TF32 "-m" step = 2.12x; Gram 3 terms on the 2304 padded symmetric pair columns of 4096 = 1.69x.
-            bf16_sus = peaks.get("bf16_tflops_sustained")
-            peak, peak_src = (bf16_sus, "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)") \
-                if bf16_sus else (1409.1, "fallback: B200_PROFILING.md sustained bf16 figure (MEASURED_PEAKS.json absent)")
-            issued = {"vbmp_estep": 2.12, "vbmp_gram": 3.0 * (12 * 192) / (D * D) if D == 64 else 3.0 * ((D + 1) * (D + 2) / 2) / (D * D)}
+            # the TF32 "-m" step = 2.12x; Gram 3 terms on the 2160 symmetric pair columns (2145 pairs padded to 16) of 4096.
+            issued = {"vbmp_estep": 2.12, "vbmp_gram": 3.0 * (((D + 1) * (D + 2) // 2 + 15) // 16 * 16) / (D * D)}
             roof = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                    "frac": ach / peak, "traffic": traffic, "traffic_unit": "GB per launch (ncu dram__bytes_read+write, profiles/r01_traffic.json)",
+                    "frac": ach / peak, "traffic": traffic, "traffic_unit": "GB per launch (ncu dram__bytes_read+write)",
+                    "traffic_source": traffic_src,
                     "issued_per_algorithmic_flop": issued,
                     "issued_frac": ach * issued.get(dom, 1.0) / peak,
-                    "per_kernel_algorithmic_tflops": {k: round(per_launch_flops / (v["ms_avg"] / 1e3) / 1e12, 1)
+                    "per_kernel_algorithmic_tflops": {k: round(per_launch_flops / (v["ms_per_step"] / 1e3) / 1e12, 1)
                                                       for k, v in kern.items() if k in ("vbmp_estep", "vbmp_gram")},
                     "peak_source": peak_src,
                     "peak_bf16_burst": peaks.get("bf16_tflops"),
@@ -325,15 +491,30 @@ def main():
                     "algorithmic_flops_per_launch": per_launch_flops,
                     "step_tensor_frac": value * FLOPS_PER_UPDATE / world / 1e12 / peak,
                     "step_hbm_frac": (value / K / world) * BYTES_PER_SAMPLE / 1e9 / peaks.get("hbm_gbs", 6546.2),
-                    "kernels_ms_avg": {k: round(v["ms_avg"], 4) for k, v in kern.items()}}
+                    "kernels_ms_per_step": {k: round(v["ms_per_step"], 4) for k, v in kern.items()}}
+        secondary = None
+        if world == 1 and not args.no_secondary:
+            del m, X
+            _lib.release_workspaces()
+            torch.cuda.empty_cache()
+            secondary = {}
+            for name, fn in (("cfg3", secondary_cfg3), ("cfg4", secondary_cfg4)):
+                try:
+                    secondary[name] = fn(dev, peak)
+                except Exception as e:                    # a secondary configuration must not take the headline down
+                    secondary[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
+                _lib.release_workspaces()
+                torch.cuda.empty_cache()
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            v, s_per = cpu_port_iteration_rate(args.ref_rows, args.cpu_baseline_iters, threads)
-            cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+            v, s_per, kind = cpu_iteration_rate(args.ref_rows, args.cpu_baseline_iters, 1, threads)
+            what = ("the unmodified reference (baseline/_ref: models.GaussianMixtureModel.update, CPU torch)" if kind == "reference"
+                    else "oracle/ restatement in the reference's op order")
+            cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": kind,
                    "sample": f"{args.cpu_baseline_iters} EM iterations on {args.ref_rows} rows of the same workload "
                              f"({s_per:.2f} s/iteration; extrapolates to {s_per * n_rows / args.ref_rows:.0f} s per "
-                             f"full-N iteration); reference op order (N,K,d,d) broadcast-multiply-sum"}
+                             f"full-N iteration); {what}: (N,K,d,d) broadcast-multiply-sum"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -343,10 +524,20 @@ def main():
                        "rows_per_gpu": n_rows, "l2": "inputs_exceed_l2 (X 1 GiB + responsibilities 4 GiB per step)",
                        "arithmetic": "fp32 inputs, outputs and accumulators; products as 3-term fp16 split (22 significant "
                                      "bits after exact power-of-two scaling) on tcgen05 kind::f16",
-                       "parallelism": f"sample-shard x{world}, 1 all-reduce/iter" if world > 1 else "single GPU"},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+                       "data_layout": "K3 reads the rows through a transposed, pre-scaled image made once per data set "
+                                      "(vbmp_gram_zpack, reused while X is the same unedited tensor); every step still reads "
+                                      "X (E-step) and that image (Gram) from HBM",
+                       "parallelism": f"sample-shard x{world}, 1 all-reduce/iter" if world > 1 else "single GPU",
+                       "host_affinity": numa},
+            "clocks": clocks, "e2e": e2e, "e2e_iters20": e2e20, "gpu_launches": launches,
             "roofline": roof, "cpu_baseline": cpu, "elbo_last": elbo,
         }
+        if replicas_equal is not None:
+            line["replicas_bitwise_equal"] = replicas_equal
+        if secondary is not None:
+            line["secondary"] = secondary
+        if cfg5 is not None:
+            line["cfg5"] = cfg5
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

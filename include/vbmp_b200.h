@@ -20,6 +20,8 @@ extern "C" {
 
 int vbmp_version(void);
 const char* vbmp_last_error(void);
+/* kernels this library has launched in this process so far (every launch site counts itself; bench.py's gpu_launches) */
+unsigned long long vbmp_launch_count(void);
 
 /* ---- K1: parameter preparation -------------------------------------------------------------------
  * Reduce the posterior to the whitened form  l[n,c] = cst[c] - 1/2 ||W_c^T z_n - m_c||^2 with W_c

@@ -19,12 +19,7 @@ FORCE_SIMT = int(os.environ.get("VBMP_FORCE_SIMT", "0"))   # tests: 1 = CUDA-cor
 
 
 PROFILE = None     # bench.py sets this to {} to collect (start, end) CUDA events per C-ABI call
-LAUNCHES = 0       # kernels launched through the C ABI (bench.py's gpu_launches)
-# kernels per C-ABI call on the tcgen05 path (bench.py's gpu_launches; counted from the launchers in csrc/):
-#   E-step: row scales + pack + E-step + reduce.  Gram: [column maxima + sample transpose] + [weight split] + Gram (fp16) +
-#   reduce + Gram (TF32; returns at once unless flagged) + its reduce (likewise)
-_NKERNELS = {"vbmp_estep": 4, "vbmp_estep_rpack": 4, "vbmp_gram": 7, "vbmp_gram_rpack": 6, "vbmp_gram_zpack": 2,
-             "vbmp_gram_ex": 4}
+LAUNCHES = 0       # kernels launched by the library so far (vbmp_launch_count(): every launch site counts itself)
 _PROFILE_AS = {"vbmp_estep_rpack": "vbmp_estep", "vbmp_gram_rpack": "vbmp_gram", "vbmp_gram_ex": "vbmp_gram",
                "vbmp_gram_zpack": "vbmp_gram"}
 
@@ -44,6 +39,7 @@ def lib():
         L = ctypes.CDLL(LIB_PATH)
         L.vbmp_last_error.restype = c_char_p
         L.vbmp_version.restype = c_int
+        L.vbmp_launch_count.restype = ctypes.c_ulonglong
         L.vbmp_estep_workspace_bytes.restype = c_size_t
         L.vbmp_estep_workspace_bytes.argtypes = [c_longlong, c_int, c_int, c_int, c_int]
         L.vbmp_rpack_bytes.restype = c_size_t
@@ -59,7 +55,7 @@ def lib():
 
 
 EXPORTS = (
-    "vbmp_version", "vbmp_last_error", "vbmp_niw_prep", "vbmp_mnw_prep", "vbmp_estep_workspace_bytes",
+    "vbmp_version", "vbmp_last_error", "vbmp_launch_count", "vbmp_niw_prep", "vbmp_mnw_prep", "vbmp_estep_workspace_bytes",
     "vbmp_estep", "vbmp_gram_workspace_bytes", "vbmp_gram", "vbmp_wishart_update", "vbmp_niw_update",
     "vbmp_mnw_update", "vbmp_wishart_elogdet", "vbmp_wishart_kl", "vbmp_niw_kl", "vbmp_mnw_kl",
     "vbmp_hmm_forward_backward", "vbmp_rpack_bytes", "vbmp_estep_rpack", "vbmp_gram_rpack",
@@ -87,7 +83,7 @@ def _call(name, dev, *args):
             PROFILE.setdefault(_PROFILE_AS.get(name, name), []).append((a, b))     # the hand-over variants time as K2 / K3
         else:
             rc = fn(*args)
-    LAUNCHES += _NKERNELS.get(name, 1)
+    LAUNCHES = int(lib().vbmp_launch_count())
     _check(rc, name)
 
 
@@ -297,8 +293,6 @@ def gram(z0, z1, N, GX, xg, p, GP, pg, G, K, Dp):
             _call("vbmp_gram_ex", dev, _ptr(z0), c_int(d0), _ptr(z1), c_int(d1), c_longlong(N), c_int(GX), _ptr(xg),
                   _ptr(p), c_int(GP), _ptr(pg), c_int(G), c_int(K), c_int(Dp), c_int(0), _ptr(out), _ptr(ws),
                   c_size_t(ws.numel()), _stream(dev), _ptr(rbuf), _ptr(zbuf))
-            global LAUNCHES
-            LAUNCHES += (rbuf is None) + 2 * (zbuf is None)          # images the call had to make itself
             return out
     nbytes = lib().vbmp_gram_workspace_bytes(c_longlong(N), c_int(G), c_int(K), c_int(d0), c_int(d1), c_int(Dp))
     ws = _workspace(nbytes, dev)

@@ -1,4 +1,5 @@
 // extern "C" entry points of libvbmp_b200.so (see include/vbmp_b200.h for the contract).
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -16,7 +17,12 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static std::atomic<unsigned long long> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+
+// called once behind every kernel launch: counts it (vbmp_launch_count) and turns a launch error into a return code
 int check_launch(const char* what) {
+  count_launch(1);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("%s: %s", what, cudaGetErrorString(e));
@@ -66,6 +72,7 @@ extern "C" {
 
 int vbmp_version(void) { return VBMP_ABI_VERSION; }
 const char* vbmp_last_error(void) { return g_err; }
+unsigned long long vbmp_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 int vbmp_niw_prep(const float* invU, const float* mu, const float* nu, const float* lambda_mu, const float* logprior,
                   int C, int d, int Dp, float* W, float* m, float* cst, int* info, void* stream) {

@@ -35,6 +35,7 @@ struct GramArgs {
 
 void set_error(const char* fmt, ...);
 int check_launch(const char* what);
+void count_launch(int n);
 
 // SM count of the CURRENT device, cached per device (a process may drive several GPUs)
 inline int num_sms() {

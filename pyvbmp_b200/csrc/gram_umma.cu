@@ -770,7 +770,7 @@ int launch_gram_zpack(const float* z0, int d0, const float* z1, int d1, long lon
   }
   const int cg = gu_num_sms() * 4;
   gram_colmax_kernel<<<cg, 256, 0, st>>>(z0, d0, N, 0, cmax);
-  if (d1 > 0) gram_colmax_kernel<<<cg, 256, 0, st>>>(z1, d1, N, d0, cmax);
+  if (d1 > 0) { gram_colmax_kernel<<<cg, 256, 0, st>>>(z1, d1, N, d0, cmax); count_launch(1); }
   int rc = check_launch("gram_colmax");
   if (rc) return rc;
   gram_zprep_kernel<<<gu_num_sms() * 8, 256, 0, st>>>(z0, d0, z1, d1, N, cmax, (uint8_t*)(cmax + GU_HDR_WORDS), gu_zrec(D));

@@ -92,15 +92,29 @@ class Mixture():
     def update(self, X, iters=1, lr=1.0, verbose=False):
         """dists/Mixture.py:54-62: E-step, ELBO with pre-M-step parameters, M-step.
 
-        X may live in host memory (ideally pinned): each iteration then streams it through the device in row chunks,
-        the H2D copy of chunk i+1 overlapping the E-step + Gram kernels of chunk i (same arithmetic, same results)."""
+        X may live in host memory (ideally pinned): the first iteration streams it through the device in row chunks,
+        the H2D copy of chunk i+1 overlapping the E-step + Gram kernels of chunk i (same arithmetic, same results).  The
+        reference's loop passes the same X to every iteration, so with iters > 1 the chunks land in ONE device tensor (when it
+        fits beside the responsibilities) and iterations 2.. run on the resident rows: the host link is crossed once per
+        call, not once per iteration."""
         if isinstance(X, torch.Tensor) and not X.is_cuda and self.dist.mu.is_cuda:
-            for i in range(iters):
-                ELBO = self._streamed_iteration(X, lr)
-                if verbose:
-                    print('Percent Change in ELBO:   ', (ELBO - self.ELBO_last) / self.ELBO_last.abs() * 100.0)
-                self.ELBO_last = ELBO
-            return
+            keep = iters > 1 and self._rows_fit(X)
+            ELBO = self._streamed_iteration(X, lr, keep=keep)
+            if verbose:
+                print('Percent Change in ELBO:   ', (ELBO - self.ELBO_last) / self.ELBO_last.abs() * 100.0)
+            self.ELBO_last = ELBO
+            if iters == 1:
+                return
+            if keep:
+                X = self._stream_state.pop("resident")
+                iters -= 1                                     # ... and fall through to the device loop below
+            else:
+                for i in range(iters - 1):
+                    ELBO = self._streamed_iteration(X, lr)
+                    if verbose:
+                        print('Percent Change in ELBO:   ', (ELBO - self.ELBO_last) / self.ELBO_last.abs() * 100.0)
+                    self.ELBO_last = ELBO
+                return
         for i in range(iters):
             self.update_assignments(X)
             if sharding.enabled():
@@ -115,9 +129,17 @@ class Mixture():
     STREAM_ROWS = 1 << 19      # rows per streamed chunk (128 MiB of X at d = 64)
     STREAM_FIRST = 1 << 15     # rows of the first chunk
 
-    def _streamed_iteration(self, Xh, lr):
+    def _rows_fit(self, Xh):
+        """Room for a device copy of the rows beside the responsibilities, their operand images and the workspaces?"""
+        dev = self.dist.mu.device
+        K = self.dist.batch_shape[-1] if self.dist.batch_dim else 1
+        need = Xh.numel() * 4 + 3 * Xh.shape[0] * K * 4 + (2 << 30)
+        return torch.cuda.mem_get_info(dev)[0] > need
+
+    def _streamed_iteration(self, Xh, lr, keep=False):
         """One EM iteration over host-resident rows: per chunk H2D (copy stream) -> K2 E-step -> K3 Gram on the compute
-        stream; the statistics of the chunks are summed in a fixed order, then ELBO and the (optionally sharded) update."""
+        stream; the statistics of the chunks are summed in a fixed order, then ELBO and the (optionally sharded) update.
+        keep: the chunks land in one device tensor (left in self._stream_state["resident"]) instead of two staging buffers."""
         dist = self.dist
         dev = dist.mu.device
         fusable = (isinstance(dist, NormalInverseWishart) and self.event_dim == 1 and dist.event_dim == 1
@@ -125,8 +147,15 @@ class Mixture():
         if not fusable:
             Xd = Xh.to(dev, non_blocking=True)
             self.update_assignments(Xd)
-            ELBO = self.ELBO()
-            self.update_parms(Xd, lr)
+            if sharding.enabled():
+                ELBO = self._sharded_m_step(Xd, lr)
+            else:
+                ELBO = self.ELBO()
+                self.update_parms(Xd, lr)
+            if keep:
+                if getattr(self, "_stream_state", None) is None:
+                    self._stream_state = {"key": None}
+                self._stream_state["resident"] = Xd
             return ELBO
         N, d = Xh.shape
         K = dist.batch_shape[-1]
@@ -145,6 +174,7 @@ class Mixture():
         cur = torch.cuda.current_stream(dev)
         for e in st["free"]:
             e.record(cur)
+        full = torch.empty((N, d), dtype=torch.float32, device=dev) if keep else None
         Gs = NA = logZ = None
         # chunk sizes ramp up from STREAM_FIRST rows by doubling: only the first, small copy is exposed (the copy of a
         # full 128 MiB chunk is 2.4 ms at PCIe 5 x16 rates), every later one hides behind the kernels of its predecessor
@@ -154,7 +184,7 @@ class Mixture():
             a += size
             size = min(2 * size, rows)
         for i, (a, b) in enumerate(bounds):
-            buf = st["buf"][i & 1][: b - a]
+            buf = full[a:b] if keep else st["buf"][i & 1][: b - a]
             ready = torch.cuda.Event()
             with torch.cuda.stream(st["copy"]):
                 st["copy"].wait_event(st["free"][i & 1])          # the kernels of chunk i-2 are done with this buffer
@@ -168,6 +198,9 @@ class Mixture():
             Gs = Gc if Gs is None else Gs + Gc                   # fixed chunk order: deterministic
             NA = NAc if NA is None else NA + NAc
             logZ = lZc if logZ is None else logZ + lZc
+        if keep:
+            full.record_stream(st["copy"])
+            st["resident"] = full
         self.p, self.logZ_n = st["p"], st["lz"]
         self.NA, self.logZ = NA.view(K), logZ.view(())
         if sharding.enabled():

@@ -213,7 +213,8 @@ def test_gram_sample_image_is_cached_per_data_set_and_invalidated_by_edits():
     G2 = _lib.gram(z0, z1, N, 1, xg, P, 1, xg, 1, K, Dp).clone()
     n2 = _lib.LAUNCHES
     assert torch.equal(G1, G2)
-    assert (n1 - n0) - (n2 - n1) == 2                                    # the second call skipped the two image kernels
+    assert (n1 - n0) - (n2 - n1) == 3                                    # the second call skipped the image kernels
+                                                                         # (column maxima of z0 and of z1, transpose)
     old = _lib.ZCACHE
     _lib.ZCACHE = 0
     try:

@@ -508,17 +508,22 @@ def test_streamed_host_rows_match_device_rows():
     g = torch.Generator().manual_seed(9)
     Xh = (torch.randn(N, d, generator=g) * 1.5 + 0.5).pin_memory()
     ms = []
-    for X in (Xh.to(DEV), Xh):
+    # device rows; host rows in ONE call (chunks land in a resident device tensor, iteration 2 runs on it); host rows in two
+    # calls (every call streams the rows again)
+    for X, calls in ((Xh.to(DEV), (2,)), (Xh, (2,)), (Xh, (1, 1))):
         torch.manual_seed(3)
         m = V.GaussianMixtureModel(K, d)
         m.initialize(Xh[:4096])
         m.to(DEV)
-        m.update(X, 2)
+        for it in calls:
+            m.update(X, it)
         ms.append(m)
-    a, b = ms
-    assert abs(float(a.ELBO_last) - float(b.ELBO_last)) <= 1e-6 * abs(float(a.ELBO_last))
-    # (the chunked Gram sums in a different order, so the second iteration's parameters differ in the last bits)
-    assert_maxabs(b.p, a.p, 1e-4, 'p')
-    assert bool((a.assignment() == b.assignment()).float().mean() > 0.9999)
-    for k in NIW_STATE:
-        assert_close(get(b, k), get(a, k), 2e-5, k)
+    a, b, c = ms
+    for o in (b, c):
+        assert abs(float(a.ELBO_last) - float(o.ELBO_last)) <= 1e-6 * abs(float(a.ELBO_last))
+        # (the chunked Gram sums in a different order, so the second iteration's parameters differ in the last bits)
+        assert_maxabs(o.p, a.p, 1e-4, 'p')
+        assert bool((a.assignment() == o.assignment()).float().mean() > 0.9999)
+        for k in NIW_STATE:
+            assert_close(get(o, k), get(a, k), 2e-5, k)
+    assert getattr(b, "_stream_state", {}).get("resident") is None          # the resident copy is dropped after the call

@@ -1,6 +1,7 @@
 """install() must not take anything away from a pyVBMP tree (SURVEY.md §8b, Appendix D "untouched models still run
 through the boundary").  These tests need the reference itself: they run where it is importable
-(``PYVBMP_REFERENCE`` or /root/reference, i.e. the build container) and skip elsewhere.
+(``PYVBMP_REFERENCE``, /root/reference in the build container, or the offline install under baseline/_ref) and skip
+elsewhere.
 
 CPU part (no GPU needed): after install() the reference's out-of-scope models — LinearDynamicalSystems,
 DynamicMarkovBlanketDiscovery, dMixtureofLinearTransforms, masked MatrixNormalWishart, the message-passing methods —
@@ -21,8 +22,13 @@ import torch
 import pyvbmp_b200 as V
 from _util import load_golden, tag, assert_close, assert_maxabs
 
-REF = os.environ.get("PYVBMP_REFERENCE", "/root/reference")
-HAVE_REF = os.path.isdir(os.path.join(REF, "dists")) and os.path.isdir(os.path.join(REF, "models"))
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# an importable, unmodified pyVBMP tree: $PYVBMP_REFERENCE, the build container's /root/reference, or the offline install
+# under baseline/_ref (git-ignored; `pip install --no-deps --target baseline/_ref <reference>`) which travels
+# to the GPU box
+REF = next((p for p in (os.environ.get("PYVBMP_REFERENCE"), "/root/reference", os.path.join(_ROOT, "baseline", "_ref"))
+            if p and os.path.isdir(os.path.join(p, "dists")) and os.path.isdir(os.path.join(p, "models"))), "")
+HAVE_REF = bool(REF)
 needs_ref = pytest.mark.skipif(not HAVE_REF, reason="the pyVBMP reference tree is not available here")
 
 
