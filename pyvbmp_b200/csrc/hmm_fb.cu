@@ -153,25 +153,35 @@ __global__ void __launch_bounds__(128, 4) hmm_fb_log_kernel(const float* __restr
 
 // ---- scaled linear-domain variant (ptemp == 1) ---------------------------------------------------------------------
 // The log-space recursion above spends ~K exponentials per lane per step on each of its three K-term logsumexps (MUFU
-// bound: 8.2 ms at 4096 sequences x T = 1024, K = 32).  The same quantities in the probability domain with per-step
-// renormalisation need K FMAs per matrix-vector product and ONE exponential per lane per step (the emission term):
-//   forward   u_j = (sum_i ah_i A_ij) 2^((l_t[j] - max_j l_t) log2 e),  c_t = sum_j u_j,  ah <- u / c_t,
-//             logZ = log sum_i pi_i + sum_t (log c_t + max_j l_t)                       (ah = normalised filtered marginal)
-//   backward  n_j = sum_i f_i A_ij,  c_j = g_j / n_j,  x_ij = A_ij c_j,  g'_i = f_i sum_j x_ij,  tot = sum_i g'_i,
-//             SEzz_ij += x_ij f_i / tot,  g <- g' / tot = p_t                           (g = smoothed marginal)
+// bound: 8.2 ms at 4096 sequences x T = 1024, K = 32).  The same quantities in the probability domain need K FMAs per
+// matrix-vector product and ONE exponential per lane per step (the emission term):
+//   forward   a_t[j] = (sum_i a_{t-1}[i] A_ij) e_t[j] / d_t,   e_t[j] = 2^((l_t[j] - max_j l_t) log2 e),  d_t = sum_j a_{t-1}[j]
+//             logZ = sum_t (log d_t + max_j l_t) + log sum_j a_{T-1}[j]
+//             (a_t is the filtered marginal up to a warp-uniform scale: the divisor is the PREVIOUS step's sum, so the
+//             reduction runs beside the matrix-vector product instead of behind it; sum_j a_t[j] is the one-step
+//             likelihood ratio, in (0, 1])
+//   backward  n_j = sum_i f_i A_ij,  c_j = g_j / n_j,  g'_i = f_i sum_j A_ij c_j,  tot = sum_i g'_i,
+//             SEzz_ij += A_ij c_j f_i / tot,  p_t = g' / tot,  g <- g'            (g = smoothed marginal of step t+1)
 // which is models/HMM.py:72-105 term by term: xi_ij = f_i A_ij / n_j g_j, fw[t] = lse_j xi, SEzz += exp(xi - lse_ij xi),
-// p = softmax(fw).  Vectors cross lanes through a 128-byte shared-memory line per warp (one store + KP/4 broadcast
-// 16-byte loads instead of KP shuffles).  States whose probability underflows fp32 here are below e^-87 in the
-// reference's p as well.  logZ is accumulated in fp64 (T terms of size |l|).  ptemp != 1 raises the smoothed marginals
-// to 1/ptemp, where an underflowed state could matter: those calls keep the log-space kernel.
+// p = softmax(fw); like the reference the carried g' is not renormalised (its sum is 1 up to rounding), so only
+// c_j -> matrix-vector product -> f_i * . sits on the recursion's dependency chain; n_j (a function of the stored
+// filtered values only), tot, p_t and the SEzz update are off it.  A_ij is factored out of the SEzz sum over time.
+// Vectors cross lanes through a 128-byte shared-memory line per warp (one store + KP/4 broadcast 16-byte loads instead
+// of KP shuffles); products run as packed fp32x2 FMAs.  States whose probability underflows fp32 here are below e^-87 in
+// the reference's p as well.  logZ is accumulated in fp64 (T terms of size |l|).  ptemp != 1 raises the smoothed
+// marginals to 1/ptemp, where an underflowed state could matter: those calls keep the log-space kernel.
 // (K = 32: three register arrays of 32 — column and row of A, the lane's row of SEzz — do not fit 128 registers; three
 // resident blocks of 4 warps instead of four avoid the spills)
 template <int KP>
-__global__ void __launch_bounds__(128, KP == 32 ? 3 : 4) hmm_fb_lin_kernel(const float* __restrict__ logits, const float* __restrict__ trans,
-                                                         const float* __restrict__ init, int T, long long S, int G, int K,
-                                                         float* __restrict__ p, float* __restrict__ SEzz,
-                                                         float* __restrict__ SEz0, float* __restrict__ logZ) {
-  __shared__ __align__(16) float sh[4][2][32];
+__global__ void __launch_bounds__(128, KP == 32 ? 3 : 4) hmm_fb_lin_kernel(const float* __restrict__ logits,
+                                                                        const float* __restrict__ trans,
+                                                                        const float* __restrict__ init, int T, long long S,
+                                                                        int G, int K, float* __restrict__ p,
+                                                                        float* __restrict__ SEzz, float* __restrict__ SEz0,
+                                                                        float* __restrict__ logZ) {
+  constexpr int PF = KP == 32 ? 6 : 8;                       // prefetch distance (steps) of the per-step global loads
+  constexpr int H = KP / 2;
+  __shared__ __align__(16) float sh[4][3][32];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const long long s = (long long)blockIdx.x * (blockDim.x >> 5) + wib;
   if (s >= S) return;
@@ -179,100 +189,120 @@ __global__ void __launch_bounds__(128, KP == 32 ? 3 : 4) hmm_fb_lin_kernel(const
   const bool live = lane < K;
   const float* Atr = trans + (size_t)g * K * K;
   constexpr float L2E = 1.4426950408889634f;
-  float ac[KP];
+  float2 ac[H];                                              // column `lane` of A = exp(log transition), packed pairs
 #pragma unroll
-  for (int i = 0; i < KP; ++i) ac[i] = (live && i < K) ? exp2f(Atr[i * K + lane] * L2E) : 0.f;   // column `lane` of A = exp(log transition)
+  for (int i = 0; i < H; ++i)
+    ac[i] = make_float2((live && 2 * i < K) ? exp2f(Atr[(2 * i) * K + lane] * L2E) : 0.f,
+                        (live && 2 * i + 1 < K) ? exp2f(Atr[(2 * i + 1) * K + lane] * L2E) : 0.f);
   const float pi0 = live ? exp2f(init[(size_t)g * K + lane] * L2E) : 0.f;
-  float* va = sh[wib][0];                                    // vector being broadcast (filtered marginal / f)
-  float* vc = sh[wib][1];                                    // second vector (c)
+  float* va = sh[wib][0];
+  float* vb = sh[wib][1];
+  float* vc = sh[wib][2];
   const size_t stride = (size_t)S * K;
   const float* lg = logits + (size_t)s * K + lane;
   float* pb = p + (size_t)s * K + lane;
   const float NEG = -INFINITY;
 
-  // matrix-vector product against the vector in `v` (shared): sum_i v[i] m[i], four partial sums
-  auto dot = [&](const float* v, const float (&m)[KP]) {
-    float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+  // sum_i v[i] m[i] against a vector in shared memory: KP/4 broadcast 16-byte loads, packed FMAs, two chains
+  auto dot = [&](const float* v, const float2 (&m)[H]) {
+    float2 q0 = make_float2(0.f, 0.f), q1 = make_float2(0.f, 0.f);
 #pragma unroll
     for (int i = 0; i < KP; i += 4) {
       const float4 x = *reinterpret_cast<const float4*>(v + i);
-      q0 = fmaf(x.x, m[i], q0); q1 = fmaf(x.y, m[i + 1], q1); q2 = fmaf(x.z, m[i + 2], q2); q3 = fmaf(x.w, m[i + 3], q3);
+      q0 = __ffma2_rn(make_float2(x.x, x.y), m[i / 2], q0);
+      q1 = __ffma2_rn(make_float2(x.z, x.w), m[i / 2 + 1], q1);
     }
-    return (q0 + q1) + (q2 + q3);
+    return (q0.x + q0.y) + (q1.x + q1.y);
   };
 
   // ---- forward filter
-  const float s0 = warp_sum(pi0);
-  float ah = pi0 / s0;
-  double lzacc = (double)logf(s0);
-  float lbuf[4];
+  float at = pi0;
+  float d = warp_sum(pi0);                                   // divisor of the coming step = sum of the current vector
+  double lzacc = 0.0;
+  float lbuf[PF];
 #pragma unroll
-  for (int u = 0; u < 4; ++u) lbuf[u] = (live && u < T) ? lg[(size_t)u * stride] : NEG;
+  for (int u = 0; u < PF; ++u) lbuf[u] = (live && u < T) ? lg[(size_t)u * stride] : NEG;
   // emission factor of the NEXT step, computed one step ahead so its max-reduction is off the recursion's chain
   float mx = warp_max(lbuf[0]);
   float em = live ? exp2f((lbuf[0] - mx) * L2E) : 0.f;
-  for (int t0 = 0; t0 < T; t0 += 4) {
+  for (int t0 = 0; t0 < T; t0 += PF) {
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < PF; ++u) {
       const int t = t0 + u;
       if (t >= T) break;
       const float e_t = em, mx_t = mx;
-      lbuf[u] = (live && t + 4 < T) ? lg[(size_t)(t + 4) * stride] : NEG;
+      lbuf[u] = (live && t + PF < T) ? lg[(size_t)(t + PF) * stride] : NEG;
       if (t + 1 < T) {
-        const float ln = lbuf[(u + 1) & 3];
+        const float ln = lbuf[(u + 1) % PF];
         mx = warp_max(ln);
         em = live ? exp2f((ln - mx) * L2E) : 0.f;
       }
-      va[lane] = ah;
+      float* v = (u & 1) ? vb : va;                          // alternate lines: one __syncwarp per step
+      v[lane] = at;
       __syncwarp();
-      const float uj = dot(va, ac) * e_t;
-      __syncwarp();
-      const float c = warp_sum(uj);
-      ah = uj / c;
-      lzacc += (double)(logf(c) + mx_t);
-      if (live) pb[(size_t)t * stride] = ah;
+      const float n = dot(v, ac);
+      lzacc += (double)(__logf(d) + mx_t);
+      at = n * (e_t * __frcp_rn(d));
+      d = warp_sum(at);                                      // used by the NEXT step, beside its matrix-vector product
+      if (live) pb[(size_t)t * stride] = at;
     }
   }
-  if (lane == 0) logZ[s] = (float)lzacc;
+  if (lane == 0) logZ[s] = (float)(lzacc + (double)logf(d));
   __syncwarp();
 
   // ---- backward smoother (row `lane` of A and this lane's row of SEzz only live from here on: register budget)
-  float ar[KP], zz[KP];
+  float2 ar[H], zz[H];
 #pragma unroll
-  for (int i = 0; i < KP; ++i) {
-    ar[i] = (live && i < K) ? exp2f(Atr[lane * K + i] * L2E) : 0.f;
-    zz[i] = 0.f;
+  for (int i = 0; i < H; ++i) {
+    ar[i] = make_float2((live && 2 * i < K) ? exp2f(Atr[lane * K + 2 * i] * L2E) : 0.f,
+                        (live && 2 * i + 1 < K) ? exp2f(Atr[lane * K + 2 * i + 1] * L2E) : 0.f);
+    zz[i] = make_float2(0.f, 0.f);
   }
-  float gm = ah;                                             // smoothed marginal of step t+1 (= filtered at T-1)
-  float fbuf[4];
+  float gm = at / d;                                         // smoothed marginal of step t+1 (= filtered, normalised, at T-1)
+  if (live) pb[(size_t)(T - 1) * stride] = gm;
+  float fbuf[PF];
 #pragma unroll
-  for (int u = 0; u < 4; ++u) fbuf[u] = (live && T - 2 - u >= 0) ? pb[(size_t)(T - 2 - u) * stride] : 0.f;
-  for (int t0 = T - 2; t0 >= -1; t0 -= 4) {
+  for (int u = 0; u < PF; ++u) fbuf[u] = (live && T - 2 - u >= 0) ? pb[(size_t)(T - 2 - u) * stride] : 0.f;
+  // n_j of the coming step, one step ahead (it depends on the stored filtered values only)
+  float fcur = (T >= 2) ? fbuf[0] : pi0;
+  va[lane] = fcur;
+  __syncwarp();
+  float ncur = dot(va, ac);
+  for (int t0 = T - 2; t0 >= -1; t0 -= PF) {
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < PF; ++u) {
       const int t = t0 - u;
       if (t < -1) break;
-      const float f = (t >= 0) ? fbuf[u] : pi0;              // t = -1: the initial-state step (HMM.py:94-98)
-      fbuf[u] = (live && t - 4 >= 0) ? pb[(size_t)(t - 4) * stride] : 0.f;
-      va[lane] = f;
-      __syncwarp();
-      const float nj = dot(va, ac);                          // lane j: sum_i f_i A_ij
+      const float f = fcur, nj = ncur;                       // t = -1: the initial-state step (f = pi_0, HMM.py:94-98)
+      fbuf[u] = (live && t - PF >= 0) ? pb[(size_t)(t - PF) * stride] : 0.f;
+      // ---- the recursion's chain: c -> row -> g'
       const float cj = nj > 0.f ? gm / nj : 0.f;
       vc[lane] = cj;
-      __syncwarp();
-      const float gn = f * dot(vc, ar);                      // lane i: f_i sum_j A_ij c_j
-      const float inv = 1.f / warp_sum(gn);
-      const float w = f * inv;
-#pragma unroll
-      for (int j = 0; j < KP; j += 4) {                      // SEzz_ij += A_ij c_j f_i / tot (c re-read: 32 fewer live registers)
-        const float4 c4 = *reinterpret_cast<const float4*>(vc + j);
-        zz[j] = fmaf(ar[j] * w, c4.x, zz[j]); zz[j + 1] = fmaf(ar[j + 1] * w, c4.y, zz[j + 1]);
-        zz[j + 2] = fmaf(ar[j + 2] * w, c4.z, zz[j + 2]); zz[j + 3] = fmaf(ar[j + 3] * w, c4.w, zz[j + 3]);
+      // (off the chain) next step's f and n_j; lines va / vb alternate so one barrier covers both stores
+      float fnext = 0.f;
+      float* v = (u & 1) ? va : vb;
+      if (t >= 0) {
+        fnext = (t >= 1) ? fbuf[(u + 1) % PF] : pi0;
+        v[lane] = fnext;
       }
       __syncwarp();
+      const float gn = f * dot(vc, ar);                      // lane i: f_i sum_j A_ij c_j
+      if (t >= 0) ncur = dot(v, ac);
+      // ---- off the chain: normaliser, outputs, expected transition counts
+      const float inv = __frcp_rn(warp_sum(gn));
+      const float w = f * inv;
+      const float2 w2 = make_float2(w, w);
+#pragma unroll
+      for (int j = 0; j < KP; j += 4) {                      // zz_ij += c_j f_i / tot (A_ij is applied once, at the end)
+        const float4 c4 = *reinterpret_cast<const float4*>(vc + j);
+        zz[j / 2] = __ffma2_rn(w2, make_float2(c4.x, c4.y), zz[j / 2]);
+        zz[j / 2 + 1] = __ffma2_rn(w2, make_float2(c4.z, c4.w), zz[j / 2 + 1]);
+      }
+      __syncwarp();                                          // vc is rewritten by the next step
       if (t >= 0) {
-        gm = gn * inv;
-        if (live) pb[(size_t)t * stride] = gm;
+        if (live) pb[(size_t)t * stride] = gn * inv;
+        gm = gn;
+        fcur = fnext;
       } else if (live) {
         SEz0[(size_t)s * K + lane] = gn * inv;
       }
@@ -282,7 +312,7 @@ __global__ void __launch_bounds__(128, KP == 32 ? 3 : 4) hmm_fb_lin_kernel(const
     float* out = SEzz + ((size_t)s * K + lane) * K;
 #pragma unroll
     for (int j = 0; j < KP; ++j)
-      if (j < K) out[j] = zz[j];
+      if (j < K) out[j] = ((j & 1) ? zz[j / 2].y * ar[j / 2].y : zz[j / 2].x * ar[j / 2].x);
   }
 }
 

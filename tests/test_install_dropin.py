@@ -172,14 +172,29 @@ def _get(obj, path):
     return obj
 
 
+def _purge_reference_modules():
+    for name in [n for n in sys.modules if n in ("dists", "transforms", "models", "utils")
+                 or n.startswith(("dists.", "transforms.", "models.", "utils."))]:
+        del sys.modules[name]
+
+
 @pytest.fixture
-def cuda_default(ref_tree):
+def cuda_default():
+    """The reference creates constants — and the tensors in its mutable default arguments (dists/Dirichlet.py:4,
+    dists/NormalInverseWishart.py:7-10) — on the DEFAULT device at import time, so a GPU run must import it under
+    torch.set_default_device('cuda'): purge, set the device, import, install."""
+    V.uninstall()
+    _purge_reference_modules()
     old = torch.empty(0).device
     torch.set_default_device("cuda:0")
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    import dists, transforms, models          # noqa: F401,E401
     V.install(REF)
-    yield ref_tree
+    yield sys.modules["dists"], sys.modules["transforms"], sys.modules["models"]
     torch.set_default_device(old)
     V.uninstall()
+    _purge_reference_modules()
 
 
 @needs_ref
