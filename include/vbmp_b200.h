@@ -39,6 +39,13 @@ int vbmp_mnw_prep(const float* invU, const float* nu, const float* mu, const flo
                   const float* logprior, int C, int n, int pp, int pad_X, int Dp,
                   float* W, float* m, float* cst, int* info, void* stream);
 
+/* vbmp_mnw_prep_ex: vbmp_mnw_prep that also serves MatrixNormalGamma.Elog_like (transforms/MatrixNormalGamma.py:219-232),
+ *   whose E[invSigma] is the diagonal of a Gamma node (dists/DiagonalWishart.py:44-48): pass tau (C, n) = alpha / beta and
+ *   elogdet (C) = sum_i log alpha_i - log beta_i with invU = nu = NULL; with tau = elogdet = NULL it is vbmp_mnw_prep.   */
+int vbmp_mnw_prep_ex(const float* invU, const float* nu, const float* mu, const float* invV, const float* logprior,
+                     const float* tau, const float* elogdet, int C, int n, int pp, int pad_X, int Dp,
+                     float* W, float* m, float* cst, int* info, void* stream);
+
 /* ---- K2: E-step -------------------------------------------------------------------------------------
  * z = [z0 | z1] per sample (z1 may be NULL with d1 = 0); z_i is (N, GX, d_i) contiguous; xg[G] maps a
  * theta group to its data column (NULL -> 0).  out is (N, G, K).
@@ -96,6 +103,22 @@ int vbmp_gram_ex(const float* z0, int d0, const float* z1, int d1, long long N, 
                  const float* p, int GP, const int* pg, int G, int K, int Dp, int flags,
                  float* gram, void* workspace, size_t workspace_bytes, void* stream,
                  const void* rpack, const void* zpack);
+
+/* ---- diagonal-precision nodes ------------------------------------------------------------------
+ * vbmp_diag_estep: l[n,g,k] = cst[g,k] - 1/2 sum_i tau[g,k,i] (x[n,xg[g],i] - mu[g,k,i])^2 — NormalGamma.Elog_like
+ *   (dists/NormalGamma.py:76-86) with tau = gamma.mean() = alpha / beta (dists/Gamma.py:93-94) and cst = 1/2 sum_i
+ *   gamma.loggeomean()_i (:102-103) [+ the mixture's log prior]; mode 1 adds the responsibility softmax of
+ *   Mixture.update_assignments (dists/Mixture.py:38-45) exactly as vbmp_estep does — GaussianMixtureModel(isotropic=True),
+ *   models/GaussianMixtureModel.py:8-11.  x (N, GX, d), mu / tau (G, K, d), cst (G, K), d <= 128; out (N, G, K).
+ * The weighted statistics of NormalGamma.raw_update (:58-73: sum r x, sum r x^2, sum r) are vbmp_gram / vbmp_gram_ex with
+ *   flags bit 1 set ("diagonal statistics only"): the result is the usual (G, K, D+1, D+1) array with the diagonal, the
+ *   last row / column and the corner filled and — from the tensor-core kernel — zeros elsewhere.
+ * MatrixNormalGamma (transforms/MatrixNormalGamma.py:87-245) runs on vbmp_mnw_prep_ex + vbmp_estep + vbmp_gram +
+ *   vbmp_mnw_update (its invV / mu part) — see vbmp_mnw_prep_ex below.                                              */
+size_t vbmp_diag_estep_workspace_bytes(long long N, int G, int K, int d, int mode);
+int vbmp_diag_estep(const float* x, int d, long long N, int GX, const int* xg, const float* mu, const float* tau,
+                    const float* cst, int G, int K, int mode, float* out, float* logZn, float* NA, float* logZ,
+                    void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- K5: natural-parameter updates (replicated; statistics are post-beta) -----------------------------
  * Wishart.ss_update — dists/Wishart.py:43-56.                                                          */

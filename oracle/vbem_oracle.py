@@ -258,6 +258,117 @@ def niw_kl(s):
 
 
 # --------------------------------------------------------------------------------------
+# Gamma / NormalGamma (diagonal precision)   reference: dists/Gamma.py, dists/NormalGamma.py
+# --------------------------------------------------------------------------------------
+
+def gamma_new(event_shape, batch_shape=(), alpha0=1.0, beta0=1.0, dtype=torch.float32):
+    """dists/Gamma.py:7-23: alpha = alpha_0 + rand, beta = beta_0 + rand (RNG, in this order)."""
+    shape = tuple(batch_shape) + tuple(event_shape)
+    a0 = torch.as_tensor(alpha0, dtype=dtype).expand(shape)
+    b0 = torch.as_tensor(beta0, dtype=dtype).expand(shape)
+    return {"event_dim": len(event_shape), "batch_dim": len(batch_shape), "alpha_0": a0, "beta_0": b0,
+            "alpha": a0 + torch.rand(shape, dtype=dtype), "beta": b0 + torch.rand(shape, dtype=dtype),
+            "SEx": 0.0, "SElogx": 0.0}
+
+
+def gamma_ss_update(g, SElogx, SEx, lr=1.0, beta=None):
+    """dists/Gamma.py:34-47."""
+    if beta is not None:
+        g["SEx"] = beta * g["SEx"] + SEx
+        g["SElogx"] = beta * g["SElogx"] + SElogx
+        SEx, SElogx = g["SEx"], g["SElogx"]
+    g["alpha"] = (g["alpha_0"] + SElogx) * lr + g["alpha"] * (1 - lr)
+    g["beta"] = (g["beta_0"] + SEx) * lr + g["beta"] * (1 - lr)
+
+
+def gamma_mean(g):
+    """dists/Gamma.py:93-94."""
+    return g["alpha"] / g["beta"]
+
+
+def gamma_meaninv(g):
+    """dists/Gamma.py:99-100."""
+    return g["beta"] / (g["alpha"] - 1)
+
+
+def gamma_loggeomean(g):
+    """dists/Gamma.py:105-106 (log alpha - log beta)."""
+    return g["alpha"].log() - g["beta"].log()
+
+
+def gamma_kl(g):
+    """dists/Gamma.py:117-119."""
+    a, b, a0, b0 = g["alpha"], g["beta"], g["alpha_0"], g["beta_0"]
+    KL = (a - a0) * a.digamma() - a.lgamma() + a0.lgamma() + a0 * (b.log() - b0.log()) + a * (b0 / b - 1)
+    return KL.sum(list(range(-g["event_dim"], 0)))
+
+
+def ng_new(event_shape, batch_shape=(), scale=1.0, dtype=torch.float32):
+    """dists/NormalGamma.py:6-28: lambda = lambda_0 + rand, Gamma(alpha_0 = 2, beta_0 = 2 scale^2), mu = mu_0 + randn /
+    sqrt(gamma.mean()); event_dim is 1 whatever the event shape (:13)."""
+    event_shape, batch_shape = tuple(event_shape), tuple(batch_shape)
+    lam0 = torch.tensor(1.0, dtype=dtype).expand(batch_shape + event_shape[:-1])
+    lam = lam0 + torch.rand_like(lam0)
+    mu0 = torch.tensor(0.0, dtype=dtype).expand(batch_shape + event_shape)
+    g = gamma_new(event_shape, batch_shape, 2.0, 2.0 * scale ** 2, dtype=dtype)
+    mu = mu0 + torch.randn_like(mu0) / gamma_mean(g).sqrt()
+    return {"kind": "ng", "dim": event_shape[-1], "event_shape": event_shape, "batch_shape": batch_shape,
+            "event_dim": 1, "batch_dim": len(batch_shape), "lambda_mu_0": lam0, "lambda_mu": lam, "mu_0": mu0, "mu": mu,
+            "gamma": g, "SExx": 0.0, "SEx": 0.0, "N": 0.0}
+
+
+def ng_elog_like(s, X):
+    """dists/NormalGamma.py:76-86: the expression that survives is :83,
+    -1/2 ((X - mu)^2 gamma.mean()).sum(-1) + 1/2 gamma.loggeomean().sum(-1)."""
+    out = -0.5 * ((X - s["mu"]) ** 2 * gamma_mean(s["gamma"])).sum(-1) + 0.5 * gamma_loggeomean(s["gamma"]).sum(-1)
+    for _ in range(s["event_dim"] - 1):
+        out = out.sum(-1)
+    return out
+
+
+def ng_raw_stats(s, X, p):
+    """dists/NormalGamma.py:58-73."""
+    sample_shape = X.shape[:-s["event_dim"] - s["batch_dim"]]
+    sd = list(range(len(sample_shape)))
+    if p is None:
+        SEx = X.sum(sd)
+        SExx = (X ** 2).sum(sd)
+        N = torch.tensor(float(math.prod(sample_shape)), dtype=X.dtype).expand(s["batch_shape"] + s["event_shape"][:-1])
+    else:
+        N = p.sum(sd)
+        pv = p.view(p.shape + s["event_dim"] * (1,))
+        SEx = (X * pv).sum(sd)
+        SExx = (X ** 2 * pv).sum(sd)
+    return SExx, SEx, N
+
+
+def ng_ss_update(s, SExx, SEx, N, lr=1.0, beta=None):
+    """dists/NormalGamma.py:41-56."""
+    if beta is not None:
+        s["SExx"] = SExx + beta * s["SExx"]
+        s["SEx"] = SEx + beta * s["SEx"]
+        s["N"] = N + beta * s["N"]
+        SExx, SEx, N = s["SExx"], s["SEx"], s["N"]
+    lam0, mu0 = s["lambda_mu_0"], s["mu_0"]
+    lam = lam0 + N
+    mu = (lam0.unsqueeze(-1) * mu0 + SEx) / lam.unsqueeze(-1)
+    SExx = SExx + lam0.unsqueeze(-1) * mu0 ** 2 - lam.unsqueeze(-1) * mu ** 2
+    s["lambda_mu"] = lr * lam + (1 - lr) * s["lambda_mu"]
+    s["mu"] = lr * mu + (1 - lr) * s["mu"]
+    gamma_ss_update(s["gamma"], 0.5 * N.unsqueeze(-1), 0.5 * SExx, lr, beta)
+
+
+def ng_kl(s):
+    """dists/NormalGamma.py:88-94."""
+    lam0, lam = s["lambda_mu_0"], s["lambda_mu"]
+    out = lam0 / 2.0 * ((s["mu"] - s["mu_0"]) ** 2 * gamma_mean(s["gamma"])).sum(-1)
+    out = out + s["dim"] / 2.0 * (lam0 / lam - (lam0 / lam).log() - 1)
+    for _ in range(s["event_dim"] - 1):
+        out = out.sum(-1)
+    return out + gamma_kl(s["gamma"]).sum(-1)
+
+
+# --------------------------------------------------------------------------------------
 # Mixture / GaussianMixtureModel    reference: dists/Mixture.py, models/GaussianMixtureModel.py
 # --------------------------------------------------------------------------------------
 
@@ -282,9 +393,11 @@ def mixture_new(dist, event_shape, dtype=torch.float32):
             "logZ": torch.tensor(-torch.inf), "ELBO_last": torch.tensor(-torch.inf)}
 
 
-def gmm_new(nc, dim, dtype=torch.float32):
-    """models/GaussianMixtureModel.py:7-12 (full-covariance branch), scale = nc^(-1/dim)."""
-    return mixture_new(niw_new((dim,), (nc,), scale=1.0 / nc ** (1.0 / dim), dtype=dtype), (nc,), dtype=dtype)
+def gmm_new(nc, dim, dtype=torch.float32, isotropic=False):
+    """models/GaussianMixtureModel.py:7-12, scale = nc^(-1/dim): NormalInverseWishart components, or NormalGamma ones
+    (isotropic=True).  As in the reference the component node is constructed before the Dirichlet (RNG order)."""
+    make = ng_new if isotropic else niw_new
+    return mixture_new(make((dim,), (nc,), scale=1.0 / nc ** (1.0 / dim), dtype=dtype), (nc,), dtype=dtype)
 
 
 def _mixture_view(m, X):
@@ -295,6 +408,8 @@ def _mixture_view(m, X):
 def mixture_elog_like(m, X, exact=True):
     """dists/Mixture.py:68-70."""
     d = m["dist"]
+    if d.get("kind") == "ng":
+        return ng_elog_like(d, _mixture_view(m, X)) + dirichlet_loggeomean(m["pi"])
     if exact:
         return niw_elog_like_exact(d, _mixture_view(m, X)) + dirichlet_loggeomean(m["pi"])
     return niw_elog_like_fast(d, X) + dirichlet_loggeomean(m["pi"])
@@ -318,7 +433,8 @@ def mixture_update_assignments(m, X, exact=True, chunk=None):
 
 def mixture_kl(m):
     """dists/Mixture.py:72-73."""
-    return niw_kl(m["dist"]).sum(list(range(-m["event_dim"], 0))) + dirichlet_kl(m["pi"])
+    kl = ng_kl(m["dist"]) if m["dist"].get("kind") == "ng" else niw_kl(m["dist"])
+    return kl.sum(list(range(-m["event_dim"], 0))) + dirichlet_kl(m["pi"])
 
 
 def mixture_elbo(m):
@@ -330,7 +446,9 @@ def mixture_update_parms(m, X, lr=1.0, exact=True):
     """dists/Mixture.py:47-49, 65-66."""
     dirichlet_ss_update(m["pi"], m["NA"], lr=lr)
     d = m["dist"]
-    if exact:
+    if d.get("kind") == "ng":
+        ng_ss_update(d, *ng_raw_stats(d, _mixture_view(m, X), m["p"]), lr=lr, beta=None)
+    elif exact:
         niw_raw_update_exact(d, _mixture_view(m, X), m["p"], lr)
     else:
         G = weighted_gram_fast(X, m["p"]).to(X.dtype)
@@ -495,12 +613,113 @@ def mnw_kl(s):
 
 
 # --------------------------------------------------------------------------------------
+# MatrixNormalGamma (diagonal output precision)   reference: transforms/MatrixNormalGamma.py, dists/DiagonalWishart.py
+# --------------------------------------------------------------------------------------
+
+def mng_new(event_shape, batch_shape=(), scale=1.0, pad_X=False, fixed_precision=False, dtype=torch.float32):
+    """transforms/MatrixNormalGamma.py:22-86 (no masks): mu = randn / sqrt(p') (no mu_0 term), invV_0 = I,
+    DiagonalWishart -> Gamma(alpha_0 = 2, beta_0 = scale^2 / 0.5) over the n outputs (dists/DiagonalWishart.py:9-20)."""
+    event_shape, batch_shape = tuple(event_shape), tuple(batch_shape)
+    n, p = event_shape[-2], event_shape[-1]
+    if pad_X:
+        p = p + 1
+        event_shape = event_shape[:-1] + (p,)
+    mu0 = torch.tensor(0.0, dtype=dtype).expand(batch_shape + event_shape)
+    mu = torch.randn_like(mu0) / torch.sqrt(torch.tensor(float(p), dtype=dtype))
+    invV0 = torch.eye(p, dtype=dtype).expand(batch_shape + event_shape[:-2] + (p, p))
+    return {
+        "kind": "mng", "n": n, "p": p, "pad_X": pad_X, "fixed_precision": fixed_precision,
+        "event_shape": event_shape, "event_dim": len(event_shape), "batch_shape": batch_shape, "batch_dim": len(batch_shape),
+        "mu_0": mu0, "mu": mu, "invV_0": invV0, "invV": invV0, "V": invV0.inverse(),
+        "logdetinvV": invV0.logdet(), "logdetinvV_0": invV0.logdet(),
+        "invU": {"gamma": gamma_new(event_shape[:-1], batch_shape, 2.0, scale ** 2 / 0.5, dtype=dtype)},
+        "SEyy": 0.0, "SExx": 0.0, "SEyx": 0.0, "N": 0.0, "log2pi": math.log(2 * math.pi),
+    }
+
+
+def _diag_embed(v):
+    return v.unsqueeze(-1) * torch.eye(v.shape[-1], dtype=v.dtype)
+
+
+def mng_EinvSigma(s):
+    """transforms/MatrixNormalGamma.py:466-467 -> dists/DiagonalWishart.py:56-57."""
+    return _diag_embed(gamma_mean(s["invU"]["gamma"]))
+
+
+def mng_EinvUX(s):
+    """transforms/MatrixNormalGamma.py:421-422."""
+    return gamma_mean(s["invU"]["gamma"]).unsqueeze(-1) * s["mu"]
+
+
+def mng_EXTinvUX(s):
+    """transforms/MatrixNormalGamma.py:439-440."""
+    return s["n"] * s["V"] + s["mu"].transpose(-1, -2) @ (gamma_mean(s["invU"]["gamma"]).unsqueeze(-1) * s["mu"])
+
+
+def mng_elog_like(s, X, Y):
+    """transforms/MatrixNormalGamma.py:227-243 (X: (...,p,1), Y: (...,n,1))."""
+    ELL = -0.5 * (Y.transpose(-2, -1) @ mng_EinvSigma(s) @ Y).squeeze(-1).squeeze(-1)
+    A, B = mng_EinvUX(s), mng_EXTinvUX(s)
+    if s["pad_X"]:
+        ELL = ELL + (Y.transpose(-2, -1) @ (A[..., :, :-1] @ X + A[..., :, -1:])).squeeze(-1).squeeze(-1)
+        ELL = ELL - 0.5 * (X.transpose(-2, -1) @ B[..., :-1, :-1] @ X + 2 * B[..., -1:, :-1] @ X
+                           + B[..., -1:, -1:]).squeeze(-1).squeeze(-1)
+    else:
+        ELL = ELL + (Y.transpose(-2, -1) @ A @ X).squeeze(-1).squeeze(-1)
+        ELL = ELL - 0.5 * (X.transpose(-2, -1) @ B @ X).squeeze(-1).squeeze(-1)
+    ELL = ELL + 0.5 * gamma_loggeomean(s["invU"]["gamma"]).sum(-1) - 0.5 * s["n"] * s["log2pi"]
+    for _ in range(s["event_dim"] - 2):
+        ELL = ELL.sum(-1)
+    return ELL
+
+
+def mng_ss_update(s, SExx, SEyx, SEyy, N, lr=1.0, beta=None):
+    """transforms/MatrixNormalGamma.py:87-141, no-mask branch (:112-116, :129-141)."""
+    if beta is not None:
+        s["SExx"] = beta * s["SExx"] + SExx
+        s["SEyx"] = beta * s["SEyx"] + SEyx
+        s["SEyy"] = beta * s["SEyy"] + SEyy
+        s["N"] = beta * s["N"] + N
+        SExx, SEyx, SEyy, N = s["SExx"], s["SEyx"], s["SEyy"], s["N"]
+    invV = s["invV_0"] + SExx
+    muinvV = s["mu_0"] @ s["invV_0"] + SEyx
+    mu = torch.linalg.solve(invV, muinvV.transpose(-2, -1)).transpose(-2, -1)
+    if s["fixed_precision"] is False:
+        SEyy = SEyy - mu @ invV @ mu.transpose(-2, -1) + s["mu_0"] @ s["invV_0"] @ s["mu_0"].transpose(-2, -1)
+        # dists/DiagonalWishart.py:32-37: gamma.ss_update(N / 2, diag / 2, lr, beta=None)
+        gamma_ss_update(s["invU"]["gamma"], N.unsqueeze(-1) / 2.0, SEyy.diagonal(dim1=-2, dim2=-1) / 2.0, lr, None)
+    s["invV"] = lr * invV + (1.0 - lr) * s["invV"]
+    s["invV"] = 0.5 * (s["invV"] + s["invV"].transpose(-2, -1))
+    s["mu"] = lr * mu + (1.0 - lr) * s["mu"]
+    s["V"] = s["invV"].inverse()
+    s["logdetinvV"] = s["invV"].logdet()
+
+
+def mng_kl(s):
+    """transforms/MatrixNormalGamma.py:206-225 (X_mask None, uniform_precision False)."""
+    n, p = s["n"], s["p"]
+    KL = n / 2.0 * s["logdetinvV"] - n / 2.0 * s["logdetinvV_0"] - n * p / 2.0
+    KL = KL + 0.5 * n * (s["invV_0"] * s["V"]).sum(-1).sum(-1)
+    dm = s["mu"] - s["mu_0"]
+    temp = dm.transpose(-2, -1) @ (gamma_mean(s["invU"]["gamma"]).unsqueeze(-1) * dm)
+    KL = KL + 0.5 * (s["invV_0"] * temp).sum(-1).sum(-1)
+    for _ in range(s["event_dim"] - 2):
+        KL = KL.sum(-1)
+    KL = KL + gamma_kl(s["invU"]["gamma"])
+    for _ in range(s["event_dim"] - 2):
+        KL = KL.sum(-1)
+    return KL
+
+
+# --------------------------------------------------------------------------------------
 # MixtureofLinearTransforms           reference: transforms/MixtureofLinearTransforms.py
 # --------------------------------------------------------------------------------------
 
-def molt_new(n, p, dim, pad_X=True, dtype=torch.float32):
-    """transforms/MixtureofLinearTransforms.py:12-32 (type='Wishart', batch_shape=())."""
-    W = mnw_new((n, p), (dim,), scale=1.0 / dim ** (1.0 / n), pad_X=pad_X, dtype=dtype)
+def molt_new(n, p, dim, pad_X=True, dtype=torch.float32, type='Wishart'):
+    """transforms/MixtureofLinearTransforms.py:12-32 (batch_shape=()): MatrixNormalWishart experts, or MatrixNormalGamma
+    ones (type='Gamma')."""
+    make = mng_new if type == 'Gamma' else mnw_new
+    W = make((n, p), (dim,), scale=1.0 / dim ** (1.0 / n), pad_X=pad_X, dtype=dtype)
     return {"n": n, "p": p, "dim": dim, "W": W, "pi": dirichlet_new((dim,), dtype=dtype),
             "ELBO_last": -torch.tensor(torch.inf)}
 
@@ -508,6 +727,8 @@ def molt_new(n, p, dim, pad_X=True, dtype=torch.float32):
 def molt_update_assignments(m, X, Y, exact=True, chunk=None):
     """transforms/MixtureofLinearTransforms.py:34-41: max-shift softmax, per-sample logZ."""
     def ell(Xc, Yc):
+        if m["W"].get("kind") == "mng":
+            return mng_elog_like(m["W"], Xc.unsqueeze(-3), Yc.unsqueeze(-3))
         if exact:
             return mnw_elog_like_exact(m["W"], Xc.unsqueeze(-3), Yc.unsqueeze(-3))
         return mnw_elog_like_fast(m["W"], Xc.squeeze(-1), Yc.squeeze(-1))
@@ -526,7 +747,7 @@ def molt_update_assignments(m, X, Y, exact=True, chunk=None):
 
 def molt_kl(m):
     """transforms/MixtureofLinearTransforms.py:123-124."""
-    return dirichlet_kl(m["pi"]) + mnw_kl(m["W"]).sum(-1)
+    return dirichlet_kl(m["pi"]) + (mng_kl(m["W"]) if m["W"].get("kind") == "mng" else mnw_kl(m["W"])).sum(-1)
 
 
 def molt_elbo(m):
@@ -542,7 +763,9 @@ def molt_raw_update(m, X, Y, iters=1, lr=1.0, exact=True, chunk=None):
         elbo = molt_elbo(m)
         dirichlet_ss_update(m["pi"], m["p"].sum(0), lr=lr)
         W = m["W"]
-        if exact:
+        if W.get("kind") == "mng":     # transforms/MatrixNormalGamma.py:174-204 forms the same statistics as the Wishart node
+            mng_ss_update(W, *mnw_raw_stats_exact(W, X.unsqueeze(-3), Y.unsqueeze(-3), m["p"]), lr=lr, beta=None)
+        elif exact:
             mnw_ss_update(W, *mnw_raw_stats_exact(W, X.unsqueeze(-3), Y.unsqueeze(-3), m["p"]), lr=lr, beta=None)
         else:
             Z = torch.cat([Y.squeeze(-1), X.squeeze(-1)], -1)

@@ -7,6 +7,9 @@ the arithmetic runs in hand-written CUDA kernels behind the C ABI of ``libvbmp_b
 from .wishart import Wishart
 from .niw import NormalInverseWishart
 from .mnw import MatrixNormalWishart
+from .gamma import Gamma, DiagonalWishart
+from .normal_gamma import NormalGamma
+from .mng import MatrixNormalGamma
 from .dirichlet import Dirichlet
 from .mixture import Mixture, GaussianMixtureModel
 from .molt import MixtureofLinearTransforms
@@ -16,6 +19,7 @@ from .install import install, uninstall, installed_classes
 from . import sharding
 from ._lib import VbmpError, LIB_PATH
 
-__all__ = ["Wishart", "NormalInverseWishart", "MatrixNormalWishart", "Dirichlet", "Mixture",
+__all__ = ["Wishart", "NormalInverseWishart", "MatrixNormalWishart", "Gamma", "DiagonalWishart", "NormalGamma",
+           "MatrixNormalGamma", "Dirichlet", "Mixture",
            "GaussianMixtureModel", "MixtureofLinearTransforms", "HMM", "ARHMM", "install", "uninstall",
            "VbmpError", "LIB_PATH"]

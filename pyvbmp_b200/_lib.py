@@ -48,6 +48,8 @@ def lib():
         L.vbmp_gram_workspace_bytes.argtypes = [c_longlong, c_int, c_int, c_int, c_int, c_int]
         L.vbmp_gram_ex_workspace_bytes.restype = c_size_t
         L.vbmp_gram_ex_workspace_bytes.argtypes = [c_longlong, c_int, c_int, c_int, c_int, c_int, c_int, c_int]
+        L.vbmp_diag_estep_workspace_bytes.restype = c_size_t
+        L.vbmp_diag_estep_workspace_bytes.argtypes = [c_longlong, c_int, c_int, c_int, c_int]
         L.vbmp_zpack_bytes.restype = c_size_t
         L.vbmp_zpack_bytes.argtypes = [c_longlong, c_int, c_int]
         _lib = L
@@ -60,6 +62,7 @@ EXPORTS = (
     "vbmp_mnw_update", "vbmp_wishart_elogdet", "vbmp_wishart_kl", "vbmp_niw_kl", "vbmp_mnw_kl",
     "vbmp_hmm_forward_backward", "vbmp_rpack_bytes", "vbmp_estep_rpack", "vbmp_gram_rpack",
     "vbmp_zpack_bytes", "vbmp_gram_zpack", "vbmp_gram_ex_workspace_bytes", "vbmp_gram_ex",
+    "vbmp_diag_estep_workspace_bytes", "vbmp_diag_estep", "vbmp_mnw_prep_ex",
 )
 
 
@@ -159,16 +162,42 @@ def niw_prep(invU, mu, nu, lam, logprior, C, d, Dp):
     return W, m, cst, info
 
 
-def mnw_prep(invU, nu, mu, invV, logprior, C, n, pp, pad, Dp):
-    dev = invU.device
+def mnw_prep(invU, nu, mu, invV, logprior, C, n, pp, pad, Dp, tau=None, elogdet=None):
+    """tau (C, n) / elogdet (C): the diagonal-precision form (MatrixNormalGamma) in place of (invU, nu)."""
+    dev = mu.device
     W = torch.empty((C, Dp, Dp), dtype=torch.float32, device=dev)
     m = torch.empty((C, Dp), dtype=torch.float32, device=dev)
     cst = torch.empty((C,), dtype=torch.float32, device=dev)
     info = torch.empty((C,), dtype=torch.int32, device=dev)
+    if tau is not None:
+        _call("vbmp_mnw_prep_ex", dev, _ptr(None), _ptr(None), _ptr(mu), _ptr(invV), _ptr(logprior), _ptr(tau), _ptr(elogdet),
+              c_int(C), c_int(n), c_int(pp), c_int(int(pad)), c_int(Dp), _ptr(W), _ptr(m), _ptr(cst), _ptr(info), _stream(dev))
+        return W, m, cst, info
     _call("vbmp_mnw_prep", dev, _ptr(invU), _ptr(nu), _ptr(mu), _ptr(invV), _ptr(logprior), c_int(C), c_int(n),
                                c_int(pp), c_int(int(pad)), c_int(Dp), _ptr(W), _ptr(m), _ptr(cst), _ptr(info),
                                _stream(dev))
     return W, m, cst, info
+
+
+def diag_estep(x, N, GX, xg, mu, tau, cst, G, K, d, mode):
+    """Diagonal-precision E-step (vbmp_diag_estep): x (N,GX,d), mu / tau (G*K,d), cst (G*K).  Returns logits (mode 0) or
+    (p, logZn, NA, logZ) (mode 1)."""
+    dev = x.device
+    _rpack_rec.pop(_rpack_key(dev), None)
+    out = torch.empty((N, G, K), dtype=torch.float32, device=dev)
+    logZn = NA = logZ = None
+    if mode == 1:
+        logZn = torch.empty((N, G), dtype=torch.float32, device=dev)
+        NA = torch.empty((G, K), dtype=torch.float32, device=dev)
+        logZ = torch.empty((G,), dtype=torch.float32, device=dev)
+    nbytes = lib().vbmp_diag_estep_workspace_bytes(c_longlong(N), c_int(G), c_int(K), c_int(d), c_int(mode))
+    ws = _workspace(nbytes, dev)
+    _call("vbmp_diag_estep", dev, _ptr(x), c_int(d), c_longlong(N), c_int(GX), _ptr(xg), _ptr(mu), _ptr(tau), _ptr(cst),
+          c_int(G), c_int(K), c_int(mode), _ptr(out), _ptr(logZn), _ptr(NA), _ptr(logZ), _ptr(ws), c_size_t(ws.numel()),
+          _stream(dev))
+    if mode == 0:
+        return out
+    return out, logZn, NA, logZ
 
 
 # K2 -> K3 hand-over: the most recent mode-1 E-step on a stream may have left the responsibilities pre-split for the Gram
@@ -271,8 +300,9 @@ def _zpack(z0, z1, N, K, Dp, key, dev):
     return buf
 
 
-def gram(z0, z1, N, GX, xg, p, GP, pg, G, K, Dp):
-    """Returns gram (G,K,D+1,D+1)."""
+def gram(z0, z1, N, GX, xg, p, GP, pg, G, K, Dp, diag=False):
+    """Returns gram (G,K,D+1,D+1).  diag: only the diagonal, the last row / column and the corner are needed (the
+    statistics of the diagonal-precision nodes); the tensor-core kernel then leaves zeros elsewhere."""
     dev = z0.device
     d0 = z0.shape[-1]
     d1 = 0 if z1 is None else z1.shape[-1]
@@ -291,14 +321,14 @@ def gram(z0, z1, N, GX, xg, p, GP, pg, G, K, Dp):
                                                         c_int(rbuf is not None), c_int(zbuf is not None))
             ws = _workspace(nbytes, dev)
             _call("vbmp_gram_ex", dev, _ptr(z0), c_int(d0), _ptr(z1), c_int(d1), c_longlong(N), c_int(GX), _ptr(xg),
-                  _ptr(p), c_int(GP), _ptr(pg), c_int(G), c_int(K), c_int(Dp), c_int(0), _ptr(out), _ptr(ws),
+                  _ptr(p), c_int(GP), _ptr(pg), c_int(G), c_int(K), c_int(Dp), c_int(2 if diag else 0), _ptr(out), _ptr(ws),
                   c_size_t(ws.numel()), _stream(dev), _ptr(rbuf), _ptr(zbuf))
             return out
     nbytes = lib().vbmp_gram_workspace_bytes(c_longlong(N), c_int(G), c_int(K), c_int(d0), c_int(d1), c_int(Dp))
     ws = _workspace(nbytes, dev)
     _call("vbmp_gram", dev, _ptr(z0), c_int(d0), _ptr(z1), c_int(d1), c_longlong(N), c_int(GX), _ptr(xg),
           _ptr(p), c_int(GP), _ptr(pg), c_int(G), c_int(K), c_int(Dp),
-          c_int(1 if FORCE_SIMT in (1, 3) else 0), _ptr(out), _ptr(ws), c_size_t(ws.numel()),
+          c_int((1 if FORCE_SIMT in (1, 3) else 0) | (2 if diag else 0)), _ptr(out), _ptr(ws), c_size_t(ws.numel()),
           _stream(dev))
     return out
 

@@ -33,7 +33,7 @@ int check_launch(const char* what) {
 
 // ---- forward declarations of the launchers (prep.cu, update.cu, estep_simt.cu, gram_simt.cu, *_umma.cu)
 int launch_niw_prep(const float*, const float*, const float*, const float*, const float*, int, int, int, float*, float*, float*, int*, cudaStream_t);
-int launch_mnw_prep(const float*, const float*, const float*, const float*, const float*, int, int, int, int, int, float*, float*, float*, int*, cudaStream_t);
+int launch_mnw_prep(const float*, const float*, const float*, const float*, const float*, int, int, int, int, int, float*, float*, float*, int*, cudaStream_t, const float* tau = nullptr, const float* elogdet = nullptr);
 int estep_simt_tile(int Dp);
 int launch_estep_simt(const EstepArgs&, int mode, cudaStream_t);
 int launch_estep_reduce(const float*, const double*, int nb, int G, int K, float* NA, float* logZ, cudaStream_t);
@@ -58,6 +58,10 @@ size_t gram_zpack_bytes(long long N, int D);
 bool gram_zpack_usable(long long N, int K, int Dp, int d0, int d1);
 int launch_gram_zpack(const float* z0, int d0, const float* z1, int d1, long long N, void* zpack, cudaStream_t st);
 int launch_gram_umma(const GramArgs&, float* gram, void* ws, size_t ws_bytes, cudaStream_t);
+size_t diag_estep_workspace_bytes(long long N, int G, int K, int d, int mode);
+int launch_diag_estep(const float* x, int d, long long N, int GX, const int* xg, const float* mu, const float* tau,
+                      const float* cst, int G, int K, int mode, float* out, float* logZn, float* NA, float* logZ,
+                      void* ws, size_t ws_bytes, cudaStream_t st);
 bool estep_umma_can_pack(long long N, int GX, int G, int K, int Dp, int d0, int d1, int mode);
 size_t gram_rpack_bytes(long long N, int K);
 
@@ -84,6 +88,14 @@ int vbmp_mnw_prep(const float* invU, const float* nu, const float* mu, const flo
                   int C, int n, int pp, int pad_X, int Dp, float* W, float* m, float* cst, int* info, void* stream) {
   if (!valid_dp(Dp)) { set_error("mnw_prep: Dp=%d must be one of 8,16,32,64,128", Dp); return VBMP_ERR_SHAPE; }
   return launch_mnw_prep(invU, nu, mu, invV, logprior, C, n, pp, pad_X ? 1 : 0, Dp, W, m, cst, info, (cudaStream_t)stream);
+}
+
+int vbmp_mnw_prep_ex(const float* invU, const float* nu, const float* mu, const float* invV, const float* logprior,
+                     const float* tau, const float* elogdet, int C, int n, int pp, int pad_X, int Dp,
+                     float* W, float* m, float* cst, int* info, void* stream) {
+  if (!valid_dp(Dp)) { set_error("mnw_prep_ex: Dp=%d must be one of 8,16,32,64,128", Dp); return VBMP_ERR_SHAPE; }
+  return launch_mnw_prep(invU, nu, mu, invV, logprior, C, n, pp, pad_X ? 1 : 0, Dp, W, m, cst, info, (cudaStream_t)stream,
+                         tau, elogdet);
 }
 
 size_t vbmp_estep_workspace_bytes(long long N, int G, int K, int Dp, int mode) {
@@ -147,6 +159,17 @@ int vbmp_estep(const float* z0, int d0, const float* z1, int d1, long long N, in
                void* workspace, size_t workspace_bytes, void* stream) {
   return estep_impl(z0, d0, z1, d1, N, GX, xg, W, m, cst, G, K, Dp, mode, flags, out, logZn, NA, logZ, workspace,
                     workspace_bytes, stream, nullptr, 0, nullptr);
+}
+
+size_t vbmp_diag_estep_workspace_bytes(long long N, int G, int K, int d, int mode) {
+  return (N < 0 || G < 1 || K < 1 || d < 1) ? 0 : diag_estep_workspace_bytes(N, G, K, d, mode);
+}
+
+int vbmp_diag_estep(const float* x, int d, long long N, int GX, const int* xg, const float* mu, const float* tau,
+                    const float* cst, int G, int K, int mode, float* out, float* logZn, float* NA, float* logZ,
+                    void* workspace, size_t workspace_bytes, void* stream) {
+  return launch_diag_estep(x, d, N, GX, xg, mu, tau, cst, G, K, mode, out, logZn, NA, logZ, workspace, workspace_bytes,
+                           (cudaStream_t)stream);
 }
 
 size_t vbmp_rpack_bytes(long long N, int K) { return (N < 0 || K < 1) ? 0 : gram_rpack_bytes(N, K); }
@@ -220,6 +243,7 @@ static int gram_impl(const float* z0, int d0, const float* z1, int d1, long long
   GramArgs a{z0, z1, d0, d1, N, GX, xg, p, GP, pg, G, K, Dp, 0, 0, nullptr};
   a.rpack = (const unsigned char*)rpack;
   a.zpack = (const unsigned char*)zpack;
+  a.diag = (flags & 2) ? 1 : 0;            // the tcgen05 kernel then forms only the pairs (i, i), (i, D); the CUDA-core one ignores it
   if (!(flags & 1) && gram_umma_supported(N, GX, GP, G, K, Dp, d0, d1, p != nullptr))
     return launch_gram_umma(a, gram, workspace, workspace_bytes, st);
   gram_simt_plan(N, G, K, Dp, &a.S_per, &a.splits);

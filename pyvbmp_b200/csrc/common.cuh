@@ -31,6 +31,7 @@ struct GramArgs {
   float* part;                                        // [splits][G][K][(D+1)^2]
   const unsigned char* rpack = nullptr;               // pre-split weight images written by K2 (vbmp_estep_rpack)
   const unsigned char* zpack = nullptr;               // sample image written by vbmp_gram_zpack (column maxima + transposed chunks)
+  int diag = 0;                                       // flags bit 1: only diag(SExx), SEx, N are needed (diagonal-precision nodes)
 };
 
 void set_error(const char* fmt, ...);

@@ -70,6 +70,7 @@ struct GuArgs {
   int d0, d1;
   long long N; int K;
   int npb, NPB, P, ncb, splits;      // pair blocks, pair columns of the widest block, total pairs, component blocks, sample splits
+  int diag;                          // 1: only the pairs (i, i) and (i, D) — the statistics of the diagonal-precision nodes
   int wbase, wextra;                 // block pb holds 16 (wbase + (pb < wextra)) pair columns starting at 16 (pb wbase + min(pb, wextra))
   long long S_per;                   // samples per split (multiple of GU_SC)
   int Kp, PP;                        // padded partial dims: Kp = ncb*128, PP = P rounded up to 16
@@ -124,6 +125,14 @@ __host__ __device__ inline void gu_pair(int p, int D, int* i, int* j) {
   while (rem >= len) { rem -= len; ++r; --len; }
   *i = r; *j = r + rem;
 }
+
+// diag = 1 (NormalGamma.raw_update, dists/NormalGamma.py:58-73: SExx_i = sum r x_i^2, SEx_i = sum r x_i, N = sum r): the
+// 2 D + 1 pairs (i, i), i < D, then (i, D), i <= D — the same kernel on 3 % of the pair columns, HBM-bound.
+__host__ __device__ inline void gu_pair_any(int p, int D, int diag, int* i, int* j) {
+  if (!diag) { gu_pair(p, D, i, j); return; }
+  if (p < D) { *i = p; *j = p; } else { *i = p - D; *j = D; }
+}
+__host__ __device__ inline int gu_npairs(int D, int diag) { return diag ? 2 * D + 1 : (D + 1) * (D + 2) / 2; }
 
 // Split x = hi + lo for the 3-term TF32 product: hi = TF32(x) rounded to nearest; lo = x - hi is exact in fp32 and
 // needs no rounding of its own because the tensor core ignores the low 13 mantissa bits of a TF32 operand
@@ -294,7 +303,7 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant_
       const int pg_ = poff + (int)rank * NH + pslot;
       const bool pair_ok = gen && (pg_ < a.P);
       int pi = 0, pj = 0;
-      if (pair_ok) gu_pair(pg_, D, &pi, &pj);
+      if (pair_ok) gu_pair_any(pg_, D, a.diag, &pi, &pj);
       auto setup = [&](int f, const uint8_t*& b, int& sl, int& stv) {
         if (!pair_ok) { b = reinterpret_cast<const uint8_t*>(&S->consts[1]); sl = 0; stv = 0; }
         else if (f < a.d0) { b = raw + rawR + f * 4; sl = rawB; stv = a.d0 * 4; }
@@ -481,14 +490,14 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant_
 template <int MODE>
 __global__ void gram_pair_reduce_kernel(const float* __restrict__ part, int splits, int K, int Kp, int PP, int D1,
                                         const uint32_t* __restrict__ cmax, uint32_t* __restrict__ flag,
-                                        float* __restrict__ gram) {
+                                        float* __restrict__ gram, int diag) {
   if (MODE == 2 && flag[0] == 0u) return;
-  const int P = D1 * (D1 + 1) / 2;
+  const int P = gu_npairs(D1 - 1, diag);
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= (long long)K * P) return;
   const int k = (int)(e / P), p = (int)(e % P);
   int i, j;
-  gu_pair(p, D1 - 1, &i, &j);
+  gu_pair_any(p, D1 - 1, diag, &i, &j);
   double acc = 0.0;
   for (int s = 0; s < splits; ++s) acc += (double)part[((size_t)s * Kp + k) * PP + p];
   if (MODE == 1) {
@@ -622,10 +631,10 @@ static bool gu_pair_mode(int K) {
   return pair_ok && (((K + GU_CB - 1) / GU_CB) % 2 == 0);     // CTA pairs share the phi block (cta_group::2)
 }
 
-static void gu_plan(long long N, int K, int D, int sms, GuArgs* g) {
+static void gu_plan(long long N, int K, int D, int sms, GuArgs* g, int diag = 0) {
   const int GU_NPMAX = gu_npmax(gu_pair_mode(K));
-  const int D1 = D + 1;
-  g->P = D1 * (D1 + 1) / 2;
+  g->diag = diag;
+  g->P = gu_npairs(D, diag);
   static const int npb_cap = [] { const char* e = getenv("VBMP_GRAM_NPB"); return e ? atoi(e) : 0; }();   // tuning: pair columns per block
   const int npmax = (npb_cap >= 16 && npb_cap <= GU_NPMAX) ? npb_cap / 16 * 16 : GU_NPMAX;
   // 16-column units dealt out evenly: the first wextra blocks are one unit wider than the rest
@@ -784,7 +793,7 @@ int launch_gram_umma(const GramArgs& a, float* gram, void* ws, size_t ws_bytes, 
   GuArgs g{};
   g.d0 = a.d0; g.d1 = a.d1; g.N = a.N; g.K = a.K;
   const int D = a.d0 + a.d1;
-  gu_plan(a.N, a.K, D, gu_num_sms(), &g);
+  gu_plan(a.N, a.K, D, gu_num_sms(), &g, a.diag ? 1 : 0);
   g.kcb = a.K < GU_CB ? a.K : GU_CB;
   g.FL = gu_fl();
   const bool f16 = gu_use_f16();
@@ -795,6 +804,9 @@ int launch_gram_umma(const GramArgs& a, float* gram, void* ws, size_t ws_bytes, 
   g.part = (float*)(flag + GU_HDR_WORDS);
   const bool pair = gu_pair_mode(a.K);
   const int D1 = D + 1;
+  if (g.diag && cudaMemsetAsync(gram, 0, (size_t)a.K * D1 * D1 * sizeof(float), st) != cudaSuccess) {
+    set_error("gram_umma: memset failed"); return VBMP_ERR_CUDA;       // only the diagonal and the last row / column are written
+  }
   const long long tot = (long long)a.K * g.P;
   const unsigned rgrid = (unsigned)((tot + 255) / 256);
   int rc;
@@ -802,7 +814,7 @@ int launch_gram_umma(const GramArgs& a, float* gram, void* ws, size_t ws_bytes, 
     g.flag = nullptr; g.cmax = nullptr;
     rc = gu_launch_main<false>(a, g, pair, st);
     if (rc) return rc;
-    gram_pair_reduce_kernel<0><<<rgrid, 256, 0, st>>>(g.part, g.splits, a.K, g.Kp, g.PP, D1, nullptr, nullptr, gram);
+    gram_pair_reduce_kernel<0><<<rgrid, 256, 0, st>>>(g.part, g.splits, a.K, g.Kp, g.PP, D1, nullptr, nullptr, gram, g.diag);
     return check_launch("gram_pair_reduce");
   }
   if (cudaMemsetAsync(flag, 0, GU_HDR_WORDS * sizeof(uint32_t), st) != cudaSuccess) {
@@ -835,12 +847,12 @@ int launch_gram_umma(const GramArgs& a, float* gram, void* ws, size_t ws_bytes, 
   rc = gu_launch_main<true>(a, g, pair, st);
   if (rc) return rc;
   // reduce + resolution check; then the TF32 kernel and its reduce, both of which return at once unless the flag is up
-  gram_pair_reduce_kernel<1><<<rgrid, 256, 0, st>>>(g.part, g.splits, a.K, g.Kp, g.PP, D1, g.cmax, flag, gram);
+  gram_pair_reduce_kernel<1><<<rgrid, 256, 0, st>>>(g.part, g.splits, a.K, g.Kp, g.PP, D1, g.cmax, flag, gram, g.diag);
   rc = check_launch("gram_pair_reduce");
   if (rc) return rc;
   rc = gu_launch_main<false>(a, g, pair, st);
   if (rc) return rc;
-  gram_pair_reduce_kernel<2><<<rgrid, 256, 0, st>>>(g.part, g.splits, a.K, g.Kp, g.PP, D1, nullptr, flag, gram);
+  gram_pair_reduce_kernel<2><<<rgrid, 256, 0, st>>>(g.part, g.splits, a.K, g.Kp, g.PP, D1, nullptr, flag, gram, g.diag);
   return check_launch("gram_pair_reduce2");
 }
 

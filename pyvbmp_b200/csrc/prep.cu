@@ -63,11 +63,15 @@ __global__ void niw_prep_kernel(const float* __restrict__ invU, const float* __r
 //   W (upper triangular):  x-out j<p : W[i][j] = sqrt(n) Fi[j'][i'] (i <= j);
 //                          y-out j>=p: W[i<p][j] = -(A M)[j-p][i],  W[i>=p][j] = A[j-p][i-p] (i <= j)
 //   m: x-out -sqrt(n) Fi[j'][0] (pad) ; y-out (A b) (pad) ; cst per transforms/MatrixNormalWishart.py:229.
+// MatrixNormalGamma (transforms/MatrixNormalGamma.py:219-232: the same expression with a DIAGONAL E[invSigma] =
+// diag(alpha / beta), dists/DiagonalWishart.py:44-48): tau != nullptr replaces sqrt(nu) C^{-1} by diag(sqrt(tau)) and
+// elogdet[c] replaces d log 2 - logdet invU + psi_d(nu / 2) (the Gamma node's sum_i log alpha_i - log beta_i).
 __global__ void mnw_prep_kernel(const float* __restrict__ invU, const float* __restrict__ nu,
                                 const float* __restrict__ mu, const float* __restrict__ invV,
                                 const float* __restrict__ logprior, int n, int pp, int pad, int Dp,
                                 float* __restrict__ W, float* __restrict__ m, float* __restrict__ cst,
-                                int* __restrict__ info) {
+                                int* __restrict__ info, const float* __restrict__ tau,
+                                const float* __restrict__ elogdet) {
   extern __shared__ double sm[];
   const int c = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
   const int p = pp - pad, D = p + n;
@@ -79,10 +83,12 @@ __global__ void mnw_prep_kernel(const float* __restrict__ invU, const float* __r
   double* red = LiV + npV;     // 32
   __shared__ int s_info;
   if (tid == 0) s_info = 0;
-  const float* Ac = invU + (size_t)c * n * n;
-  for (int e = tid; e < n * n; e += nt) {
-    const int i = e / n, j = e % n;
-    if (j <= i) LU[tri(i, j)] = 0.5 * ((double)Ac[i * n + j] + (double)Ac[j * n + i]);
+  if (tau == nullptr) {
+    const float* Ac = invU + (size_t)c * n * n;
+    for (int e = tid; e < n * n; e += nt) {
+      const int i = e / n, j = e % n;
+      if (j <= i) LU[tri(i, j)] = 0.5 * ((double)Ac[i * n + j] + (double)Ac[j * n + i]);
+    }
   }
   const float* Vc = invV + (size_t)c * pp * pp;
   // permuted index: position 0 <- the pad coordinate (pp-1), position t>0 <- coordinate t-1
@@ -94,13 +100,25 @@ __global__ void mnw_prep_kernel(const float* __restrict__ invU, const float* __r
       LV[tri(i, j)] = 0.5 * ((double)Vc[oi * pp + oj] + (double)Vc[oj * pp + oi]);
     }
   }
-  const double logdetU = chol_packed(LU, n, &s_info, red);
-  tri_inverse_packed(LU, LiU, n);
+  double logdetU = 0.0;
+  if (tau == nullptr) {
+    logdetU = chol_packed(LU, n, &s_info, red);
+    tri_inverse_packed(LU, LiU, n);
+  } else {
+    for (int e = tid; e < npU; e += nt) LiU[e] = 0.0;
+    __syncthreads();
+    for (int j = tid; j < n; j += nt) {
+      const double t = (double)tau[(size_t)c * n + j];
+      if (!(t > 0.0) && s_info == 0) s_info = j + 1;
+      LiU[tri(j, j)] = sqrt(t);
+    }
+    __syncthreads();
+  }
   __shared__ int s_info2;
   if (tid == 0) s_info2 = 0;
   (void)chol_packed(LV, pp, &s_info2, red);
   tri_inverse_packed(LV, LiV, pp);
-  const double nuc = (double)nu[c];
+  const double nuc = tau ? 1.0 : (double)nu[c];
   const double sq = sqrt(nuc), sn = sqrt((double)n);
   const float* muc = mu + (size_t)c * n * pp;     // (n, pp) row-major, bias in the last column when pad
   float* Wc = W + (size_t)c * Dp * Dp;
@@ -134,9 +152,9 @@ __global__ void mnw_prep_kernel(const float* __restrict__ invU, const float* __r
     }
     m[(size_t)c * Dp + j] = (float)v;
   }
-  const double psi = mv_digamma_block(0.5 * nuc, n, red);
+  const double psi = tau ? 0.0 : mv_digamma_block(0.5 * nuc, n, red);
   if (tid == 0) {
-    double v = 0.5 * (n * M_LN2 - logdetU + psi) - 0.5 * n * log(2.0 * M_PI);
+    double v = 0.5 * (tau ? (double)elogdet[c] : n * M_LN2 - logdetU + psi) - 0.5 * n * log(2.0 * M_PI);
     if (pad) { const double k0 = LiV[0]; v -= 0.5 * n * k0 * k0; }
     if (logprior) v += (double)logprior[c];
     cst[c] = (float)v;
@@ -155,13 +173,17 @@ int launch_niw_prep(const float* invU, const float* mu, const float* nu, const f
 }
 
 int launch_mnw_prep(const float* invU, const float* nu, const float* mu, const float* invV, const float* logprior,
-                    int C, int n, int pp, int pad, int Dp, float* W, float* m, float* cst, int* info, cudaStream_t st) {
+                    int C, int n, int pp, int pad, int Dp, float* W, float* m, float* cst, int* info, cudaStream_t st,
+                    const float* tau, const float* elogdet) {
   if (C <= 0) return VBMP_OK;
   const int D = n + pp - pad;
   if (n < 1 || pp - pad < 1 || D > VBMP_MAX_D || Dp < D || Dp > VBMP_MAX_D) { set_error("mnw_prep: n=%d p'=%d Dp=%d out of range", n, pp, Dp); return VBMP_ERR_SHAPE; }
   const size_t smem = (size_t)(n * (n + 1) + pp * (pp + 1) + 32) * sizeof(double);
   cudaFuncSetAttribute(mnw_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  mnw_prep_kernel<<<C, 256, smem, st>>>(invU, nu, mu, invV, logprior, n, pp, pad, Dp, W, m, cst, info);
+  if ((tau == nullptr) != (elogdet == nullptr) || (tau == nullptr && (!invU || !nu))) {
+    set_error("mnw_prep: give (invU, nu) or (tau, elogdet)"); return VBMP_ERR_SHAPE;
+  }
+  mnw_prep_kernel<<<C, 256, smem, st>>>(invU, nu, mu, invV, logprior, n, pp, pad, Dp, W, m, cst, info, tau, elogdet);
   return check_launch("mnw_prep");
 }
 

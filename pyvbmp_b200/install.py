@@ -4,7 +4,8 @@ The reference binds its node classes into module globals at import time
 (``import dists.NormalInverseWishart as NormalInverseWishart`` — models/GaussianMixtureModel.py:2-4,
 transforms/MixtureofLinearTransforms.py:5-8, models/ARHMM.py:7-11), so install() walks the loaded
 ``dists.* / transforms.* / models.*`` modules and rebinds every global that *is* the reference
-``NormalInverseWishart`` / ``Wishart`` / ``MatrixNormalWishart`` class to an INSTALLED class built here:
+``NormalInverseWishart`` / ``Wishart`` / ``MatrixNormalWishart`` / ``NormalGamma`` / ``MatrixNormalGamma`` class to an
+INSTALLED class built here:
 
     class NormalInverseWishart(pyvbmp_b200.NormalInverseWishart, <reference NormalInverseWishart>)
 
@@ -55,6 +56,8 @@ def _build_classes(refs):
     from .niw import NormalInverseWishart
     from .wishart import Wishart
     from .mnw import MatrixNormalWishart
+    from .normal_gamma import NormalGamma
+    from .mng import MatrixNormalGamma
 
     hot = {
         "Wishart": (Wishart, lambda s: s.invU, ("ss_update", "ElogdetinvSigma", "KLqprior")),
@@ -62,6 +65,10 @@ def _build_classes(refs):
         "MatrixNormalWishart": (MatrixNormalWishart, lambda s: s.mu,
                                 ("ss_update", "raw_update", "update", "Elog_like", "Elog_like_given_pX_pY", "KLqprior",
                                  "predict")),
+        "NormalGamma": (NormalGamma, lambda s: s.mu, ("raw_update", "Elog_like")),
+        "MatrixNormalGamma": (MatrixNormalGamma, lambda s: s.mu,
+                              ("ss_update", "raw_update", "update", "Elog_like", "Elog_like_given_pX_pY", "KLqprior",
+                               "predict")),
     }
     out = {}
     for key, (ours, probe, names) in hot.items():
@@ -69,15 +76,18 @@ def _build_classes(refs):
         ns = {n: _dispatch(ours, ref, n, probe) for n in names if hasattr(ref, n)}
         ns["__doc__"] = f"pyvbmp_b200.{key} installed over the reference class (see pyvbmp_b200/install.py)."
         ns["__module__"] = ours.__module__
-        if key == "MatrixNormalWishart":
-            def __new__(cls, *a, **k):
-                # transforms/MatrixNormalWishart.py:20: (event_shape, batch_shape, prior_parms, scale, mask, X_mask, ...)
-                mask = k.get("mask", a[4] if len(a) > 4 else None)
-                X_mask = k.get("X_mask", a[5] if len(a) > 5 else None)
-                if mask is not None or X_mask is not None:
-                    return ref(*a, **k)             # masked nodes are outside the accelerated path: a reference object
-                return object.__new__(cls)
-            ns["__new__"] = __new__
+        if key in ("MatrixNormalWishart", "MatrixNormalGamma"):
+            # transforms/MatrixNormalWishart.py:20: (event_shape, batch_shape, prior_parms, scale, mask, X_mask, ...);
+            # transforms/MatrixNormalGamma.py:22-24: (..., scale, uniform_precision, mask, X_mask, ...)
+            def _make_new(ref, at):
+                def __new__(cls, *a, **k):
+                    mask = k.get("mask", a[at] if len(a) > at else None)
+                    X_mask = k.get("X_mask", a[at + 1] if len(a) > at + 1 else None)
+                    if mask is not None or X_mask is not None:
+                        return ref(*a, **k)         # masked nodes are outside the accelerated path: a reference object
+                    return object.__new__(cls)
+                return __new__
+            ns["__new__"] = _make_new(ref, 4 if key == "MatrixNormalWishart" else 5)
         out[key] = type(key, (ours, ref), ns)
     return out
 
@@ -98,6 +108,8 @@ def install(reference_root=None, fuse_assignments=True, fuse_hmm=True, verbose=F
         "NormalInverseWishart": _ref_class("dists.NormalInverseWishart", "NormalInverseWishart", dists),
         "Wishart": _ref_class("dists.Wishart", "Wishart", dists),
         "MatrixNormalWishart": _ref_class("transforms.MatrixNormalWishart", "MatrixNormalWishart", transforms),
+        "NormalGamma": _ref_class("dists.NormalGamma", "NormalGamma", dists),
+        "MatrixNormalGamma": _ref_class("transforms.MatrixNormalGamma", "MatrixNormalGamma", transforms),
     }
     new = _build_classes(refs)
     _installed.clear()

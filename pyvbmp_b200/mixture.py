@@ -10,6 +10,7 @@ import torch
 from . import _lib, _shapes, sharding
 from .dirichlet import Dirichlet
 from .niw import NormalInverseWishart
+from .normal_gamma import NormalGamma
 
 
 def fused_update_assignments(self, X, fallback=None):
@@ -17,7 +18,7 @@ def fused_update_assignments(self, X, fallback=None):
     reference's Mixture class (``fallback`` = the reference's own method, taken for anything this does not fuse)."""
     dist = self.dist
     other = fallback if fallback is not None else generic_update_assignments
-    fusable = (isinstance(dist, NormalInverseWishart) and self.event_dim == 1 and dist.event_dim == 1
+    fusable = (isinstance(dist, (NormalInverseWishart, NormalGamma)) and self.event_dim == 1 and dist.event_dim == 1
                and (fallback is None or dist.mu.is_cuda))
     if not fusable:
         return other(self, X)
@@ -26,10 +27,15 @@ def fused_update_assignments(self, X, fallback=None):
     if not plan.k_is_batch:
         return other(self, X)
     dev = dist.mu.device
-    W, m, cst, info, Dp = dist._prep(plan, logprior=self.pi.loggeomean())
     Xc = _lib.f32(Xv, dev).reshape(plan.N, plan.GX, dist.dim)
-    p, logZn, NA, logZ = _lib.estep(Xc, None, plan.N, plan.GX, _shapes.idx_tensor(plan.xg, dev), W, m, cst,
-                                    plan.G, plan.K, Dp, 1)
+    if isinstance(dist, NormalGamma):          # diagonal precision: the streaming E-step with the same softmax epilogue
+        mu, tau, cst = dist._prep(plan, logprior=self.pi.loggeomean())
+        p, logZn, NA, logZ = _lib.diag_estep(Xc, plan.N, plan.GX, _shapes.idx_tensor(plan.xg, dev), mu, tau, cst,
+                                             plan.G, plan.K, dist.dim, 1)
+    else:
+        W, m, cst, info, Dp = dist._prep(plan, logprior=self.pi.loggeomean())
+        p, logZn, NA, logZ = _lib.estep(Xc, None, plan.N, plan.GX, _shapes.idx_tensor(plan.xg, dev), W, m, cst,
+                                        plan.G, plan.K, Dp, 1)
     self.p = p.view(plan.sample_shape + plan.lead + (plan.K,))
     self.logZ_n = logZn.view(plan.sample_shape + plan.lead)
     self.NA = NA.view(plan.lead + (plan.K,))
@@ -214,6 +220,15 @@ class Mixture():
         """Rows are sharded over ranks: local Gram + ONE all-reduce of [Gram | logZ | NA], then the
         replicated update (identical on every rank).  ELBO still uses the pre-update parameters."""
         Xv = X.view(X.shape[:-self.dist.event_dim] + self.event_dim * (1,) + self.dist.event_shape)
+        if isinstance(self.dist, NormalGamma):
+            SExx, SEx, N = self.dist._stats(Xv, self.p)
+            SExx, SEx, N, logZ, NA = sharding.all_reduce_packed([SExx.contiguous(), SEx.contiguous(), N.contiguous(),
+                                                                 self.logZ, self.NA])
+            self.logZ, self.NA = logZ, NA
+            ELBO = self.ELBO()
+            self.pi.ss_update(self.NA, lr=lr)
+            self.dist.ss_update(SExx, SEx, N, lr)
+            return ELBO
         G, plan = self.dist._gram(Xv, self.p)
         G, logZ, NA = sharding.all_reduce_packed([G, self.logZ, self.NA])
         self.logZ, self.NA = logZ, NA
@@ -267,10 +282,11 @@ class Mixture():
 
 class GaussianMixtureModel(Mixture):
     def __init__(self, nc, dim, isotropic=False):
-        """models/GaussianMixtureModel.py:7-12 (full-covariance branch; NormalGamma is SURVEY §8f #4)."""
-        if isotropic is not False:
-            raise NotImplementedError("isotropic=True (NormalGamma) is outside the NIW hot path (SURVEY.md §8f)")
-        dist = NormalInverseWishart(event_shape=(dim,), batch_shape=(nc,), scale=1.0 / nc ** (1.0 / dim))
+        """models/GaussianMixtureModel.py:7-12."""
+        if isotropic is False:
+            dist = NormalInverseWishart(event_shape=(dim,), batch_shape=(nc,), scale=1.0 / nc ** (1.0 / dim))
+        else:
+            dist = NormalGamma(event_shape=(dim,), batch_shape=(nc,), scale=1.0 / nc ** (1.0 / dim))
         super().__init__(dist, event_shape=(nc,))
 
     def initialize(self, data):

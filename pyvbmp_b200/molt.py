@@ -8,6 +8,7 @@ import torch
 from . import _lib, _shapes, sharding
 from .dirichlet import Dirichlet
 from .mnw import MatrixNormalWishart
+from .mng import MatrixNormalGamma
 
 
 def fused_update_assignments(self, X, Y, fallback=None):
@@ -48,10 +49,14 @@ class MixtureofLinearTransforms():
         self.event_shape = (dim,)
         self.batch_dim = len(batch_shape)
         self.batch_shape = batch_shape
-        if type != 'Wishart':
-            raise NotImplementedError("type='Gamma' (MatrixNormalGamma) is a 'next' row (SURVEY.md §8f #4)")
-        self.W = MatrixNormalWishart(event_shape=(n, p), batch_shape=batch_shape + (dim,),
-                                     scale=1.0 / dim ** (1.0 / n), pad_X=pad_X)
+        if type == 'Wishart':
+            self.W = MatrixNormalWishart(event_shape=(n, p), batch_shape=batch_shape + (dim,),
+                                         scale=1.0 / dim ** (1.0 / n), pad_X=pad_X)
+        elif type == 'Gamma':
+            self.W = MatrixNormalGamma(event_shape=(n, p), batch_shape=batch_shape + (dim,),
+                                       scale=1.0 / dim ** (1.0 / n), pad_X=pad_X)
+        else:
+            raise ValueError('type must be either Wishart (default) or Gamma')
         self.pi = Dirichlet(event_shape=(dim,), batch_shape=batch_shape)
         self.KL_last = None
         self.ELBO_last = -torch.tensor(torch.inf)
@@ -120,7 +125,8 @@ class MixtureofLinearTransforms():
         the moment sums over components are three GEMM-shaped torch steps per block of rows."""
         from .mvn import MultivariateNormal_vector_format
         W = self.W
-        if not (isinstance(W, MatrixNormalWishart) and self.batch_dim == 0 and W.event_dim == 2 and X.is_cuda and X.ndim == 3):
+        if not (isinstance(W, MatrixNormalWishart) and not isinstance(W, MatrixNormalGamma) and self.batch_dim == 0
+                and W.event_dim == 2 and X.is_cuda and X.ndim == 3):
             pY, Res = W.predict(X.unsqueeze(-3))
             log_p = Res + self.pi.loggeomean()
             log_p = log_p - log_p.max(-1, True)[0]

@@ -397,8 +397,136 @@ def gen_arhmm_prxy():
     out["ELBO"] = np.asarray(el, dtype=np.float64)
     save("arhmm_prxy_k4_n2_p3", **out)
 
+# ---- diagonal-precision nodes: NormalGamma / GaussianMixtureModel(isotropic=True), MatrixNormalGamma /
+# ---- MixtureofLinearTransforms(type='Gamma')
+
+def gamma_state(g, pre):
+    return {pre + k: T(getattr(g, k)) for k in ("alpha_0", "beta_0", "alpha", "beta")}
+
+
+def ng_state(d, pre):
+    out = {pre + k: T(getattr(d, k)) for k in ("lambda_mu_0", "lambda_mu", "mu_0", "mu")}
+    out.update(gamma_state(d.gamma, pre + "gamma."))
+    return out
+
+
+def mng_state(d, pre):
+    out = {pre + k: T(getattr(d, k)) for k in ("mu_0", "mu", "invV_0", "invV", "V", "logdetinvV", "logdetinvV_0")}
+    out.update(gamma_state(d.invU.gamma, pre + "invU.gamma."))
+    return out
+
+
+def gen_diag():
+    g = torch.Generator().manual_seed(51)
+    # GaussianMixtureModel(isotropic=True): NormalGamma components (models/GaussianMixtureModel.py:8-11)
+    for name, d, K, N, iters, seed in (("gmm_iso_d8_k6", 8, 6, 600, 8, 4), ("gmm_iso_d64_k32", 64, 32, 1024, 4, 5)):
+        mu = (2.0 if d == 8 else 0.5) * torch.randn(K, d, generator=g)
+        sd = 0.5 + torch.rand(K, d, generator=g)
+        z = torch.randint(K, (N,), generator=g)
+        X = mu[z] + sd[z] * torch.randn(N, d, generator=g)
+        torch.manual_seed(seed)
+        m = models.GaussianMixtureModel(K, d, isotropic=True)
+        m.initialize(X)
+
+        def st():
+            s = ng_state(m.dist, "dist.")
+            s.update(dir_state(m.pi, "pi."))
+            return s
+        out = {"X": T(X), "nc": K, "iters": iters, "lr": 1.0}
+        out.update(tagged(st(), "init"))
+        out["init/Elog_like"] = T(m.dist.Elog_like(X.unsqueeze(-2)))
+        out["init/KL"] = T(m.KLqprior())
+        el = []
+        for i in range(iters):
+            m.update(X, 1, 1.0)
+            el.append(float(m.ELBO_last))
+            if i == 0:
+                out.update(tagged(st(), "iter1"))
+                out["iter1/logZ"], out["iter1/NA"], out["iter1/KL"], out["iter1/p"] = T(m.logZ), T(m.NA), T(m.KLqprior()), T(m.p)
+        out.update(tagged(st(), "final"))
+        out["final/assignment"] = T(m.assignment()).astype(np.int32)
+        out["final/Elog_like"] = T(m.Elog_like(X))
+        out["final/KL"] = T(m.KLqprior())
+        out["ELBO"] = np.asarray(el, dtype=np.float64)
+        save(name, **out)
+    # NormalGamma.raw_update with beta forgetting and lr < 1, then the unit-weight branch (dists/NormalGamma.py:41-73)
+    torch.manual_seed(6)
+    d = dists.NormalGamma((3,), (4,), scale=0.7)
+    out = tagged(ng_state(d, ""), "init")
+    for i in range(3):
+        X = torch.randn(50, 1, 3, generator=g) * 1.3 + 0.4
+        pw = torch.softmax(torch.randn(50, 4, generator=g), -1)
+        d.raw_update(X, pw, lr=0.6, beta=0.9)
+        out[f"X{i}"], out[f"p{i}"] = T(X), T(pw)
+        out.update(tagged(ng_state(d, ""), f"step{i}"))
+        out[f"step{i}/SExx"], out[f"step{i}/SEx"], out[f"step{i}/N"] = T(d.SExx), T(d.SEx), T(d.N)
+    Xb = torch.randn(40, 4, 3, generator=g)
+    d.raw_update(Xb, None, lr=1.0, beta=None)
+    out["Xb"] = T(Xb)
+    out.update(tagged(ng_state(d, ""), "pnone"))
+    out["final/KL"] = T(d.KLqprior())
+    out["final/Elog_like"] = T(d.Elog_like(torch.as_tensor(out["X2"])))
+    save("ng_beta_lr", **out)
+    # MatrixNormalGamma steps (transforms/MatrixNormalGamma.py:87-243)
+    for pad in (True, False):
+        torch.manual_seed(9)
+        n, p, K, N = 4, 5, 3, 300
+        d = transforms.MatrixNormalGamma(event_shape=(n, p), batch_shape=(K,), scale=0.8, pad_X=pad)
+        out = {"n": n, "p": p, "K": K, "pad_X": int(pad)}
+        out.update(tagged(mng_state(d, ""), "init"))
+        X = torch.randn(N, 1, p, 1, generator=g)
+        Wt = torch.randn(K, n, p, generator=g)
+        z = torch.randint(K, (N,), generator=g)
+        Y = (Wt[z] @ X.squeeze(1)).unsqueeze(1) + 0.3 * torch.randn(N, 1, n, 1, generator=g) + 0.5
+        r = torch.softmax(torch.randn(N, K, generator=g), -1)
+        out["X"], out["Y"], out["r"] = T(X), T(Y), T(r)
+        out["init/Elog_like"] = T(d.Elog_like(X, Y))
+        out["init/KL"] = T(d.KLqprior())
+        d.raw_update(X, Y, p=r, lr=1.0, beta=None)
+        out.update(tagged(mng_state(d, ""), "step0"))
+        out["step0/Elog_like"] = T(d.Elog_like(X, Y))
+        out["step0/KL"] = T(d.KLqprior())
+        d.raw_update(X, Y, p=r, lr=0.5, beta=0.8)
+        out.update(tagged(mng_state(d, ""), "step1"))
+        out["step1/SExx"], out["step1/SEyx"], out["step1/SEyy"], out["step1/N"] = T(d.SExx), T(d.SEyx), T(d.SEyy), T(d.N)
+        out["step1/Elog_like"] = T(d.Elog_like(X, Y))
+        out["step1/KL"] = T(d.KLqprior())
+        save(f"mng_n4_p5_k3_pad{int(pad)}", **out)
+    # MixtureofLinearTransforms(type='Gamma') trajectories
+    for name, n, p, K, N, iters in (("molt_gamma_n3_p4_k5", 3, 4, 5, 600, 5), ("molt_gamma_n32_p32_k8", 32, 32, 8, 768, 3)):
+        torch.manual_seed(10)
+        m = transforms.MixtureofLinearTransforms(n, p, K, pad_X=True, type='Gamma')
+        X = torch.randn(N, p, generator=g)
+        Wt = torch.randn(K, n, p, generator=g) / np.sqrt(p)
+        b = torch.randn(K, n, generator=g)
+        z = torch.randint(K, (N,), generator=g)
+        Y = torch.einsum("nij,nj->ni", Wt[z], X) + b[z] + 0.1 * torch.randn(N, n, generator=g)
+
+        def st():
+            s = mng_state(m.W, "W.")
+            s.update(dir_state(m.pi, "pi."))
+            return s
+        out = {"X": T(X), "Y": T(Y), "n": n, "p": p, "K": K, "iters": iters}
+        out.update(tagged(st(), "init"))
+        el = []
+        for i in range(iters):
+            m.raw_update(X.unsqueeze(-1), Y.unsqueeze(-1), iters=1, lr=1.0)
+            el.append(float(m.ELBO_last))
+            if i == 0:
+                out.update(tagged(st(), "iter1"))
+                out["iter1/p"], out["iter1/logZ"] = T(m.p), T(m.logZ)
+        out.update(tagged(st(), "final"))
+        out["final/p"], out["final/logZ"] = T(m.p), T(m.logZ)
+        out["final/assignment"] = T(m.assignment()).astype(np.int32)
+        out["final/KL"] = T(m.KLqprior())
+        out["ELBO"] = np.asarray(el, dtype=np.float64)
+        save(name, **out)
+
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "diag":      # only the fixtures added in round 2
+        gen_diag()
+        sys.exit(0)
     gen_gmm()
     gen_niw_variants()
     gen_mnw()
@@ -407,3 +535,4 @@ if __name__ == "__main__":
     gen_molt_given()
     gen_arhmm()
     gen_arhmm_prxy()
+    gen_diag()
