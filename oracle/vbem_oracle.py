@@ -986,6 +986,42 @@ def arhmm_prxy_update(h, mux, Sx, muy, Sy, iters=1, lr=1.0, beta=None):
     return trace
 
 
+def arhmm_prxry_new(K, n, p1, p2, pad_X=False, dtype=torch.float32):
+    """models/ARHMM.py:56-60: MNW(event=(n, p1 + p2), batch=(K,), pad_X=False by default) emissions under an HMM."""
+    return hmm_new(mnw_new((n, p1 + p2), (K,), pad_X=pad_X, dtype=dtype), K, dtype=dtype)
+
+
+def arhmm_prxry_beliefs(mux, Sx, R, Y):
+    """models/ARHMM.py:65-71: the stacked regressor belief — mean [E x; r], covariance diag(Sigma_x, 0) — and the observed
+    outputs as a point mass.  Returns (mu, E[xx^T], y, yy^T) as mnw_elog_like_given / mnw_stats_given take them."""
+    p1, p2 = mux.shape[-2], R.shape[-2]
+    Sigma = torch.zeros(Sx.shape[:-2] + (p1 + p2, p1 + p2), dtype=Sx.dtype)
+    Sigma[..., :p1, :p1] = Sx
+    mu = torch.cat((mux, R), dim=-2)
+    return mu, Sigma + mu @ mu.transpose(-2, -1), Y, Y @ Y.transpose(-2, -1)
+
+
+def arhmm_prxry_update(h, mux, Sx, R, Y, iters=1, lr=1.0, beta=None):
+    """models/HMM.py:141-152 with models/ARHMM.py:62-77 (ARHMM_prXRY).  Beliefs / data: mux (T,S,1,p1,1), Sx (T,S,1,p1,p1),
+    R (T,S,1,p2,1), Y (T,S,1,n,1)."""
+    W = h["obs"]
+    mu, Exx, y, Eyy = arhmm_prxry_beliefs(mux, Sx, R, Y)
+    trace = []
+    for _ in range(iters):
+        p, SEzz, SEz0, logZ = hmm_forward_backward_logits(h, mnw_elog_like_given(W, mu, Exx, y, Eyy))
+        h["p"] = p
+        NA = p.sum(0)
+        sd = list(range(NA.ndim - 1))
+        h["NA"], SEzz, SEz0, h["logZ"] = NA.sum(sd), SEzz.sum(sd), SEz0.sum(sd), logZ.sum(sd)
+        dirichlet_ss_update(h["transition"], SEzz, lr=lr, beta=beta)
+        dirichlet_ss_update(h["initial"], SEz0, lr=lr, beta=beta)
+        mnw_ss_update(W, *mnw_stats_given(W, mu, Exx, y, Eyy, p), lr=lr, beta=beta)
+        elbo = h["logZ"] - hmm_kl(h, mnw_kl(W))
+        h["ELBO_last"] = elbo
+        trace.append(elbo)
+    return trace
+
+
 # --------------------------------------------------------------------------------------
 # state (de)serialisation helpers used by the golden fixtures and the GPU parity tests
 # --------------------------------------------------------------------------------------

@@ -13,8 +13,8 @@ from .mng import MatrixNormalGamma
 from .dirichlet import Dirichlet
 from .mixture import Mixture, GaussianMixtureModel
 from .molt import MixtureofLinearTransforms
-from .mvn import MultivariateNormal_vector_format
-from .hmm import HMM, ARHMM, ARHMM_prXY
+from .mvn import MultivariateNormal_vector_format, Delta
+from .hmm import HMM, ARHMM, ARHMM_prXY, ARHMM_prXRY
 from .install import install, uninstall, installed_classes
 from . import sharding
 from ._lib import VbmpError, LIB_PATH

@@ -203,3 +203,38 @@ class ARHMM_prXY(HMM):
     def Elog_like_X_given_pY(self, pY):
         raise NotImplementedError("message passing to X is outside the VB-EM hot path (SURVEY.md §2.1 #5)")
 
+
+class ARHMM_prXRY(HMM):
+    """models/ARHMM.py:55-91: the ARHMM whose regressors are a belief about latent X (a MultivariateNormal_vector_format)
+    stacked on OBSERVED regressors R, with observed outputs Y — DynamicMarkovBlanketDiscovery's observation model.  The
+    stacked regressor belief has mean [E x; r] and the block-diagonal covariance diag(Sigma_x, 0), so the observation
+    logits and the observation update are MatrixNormalWishart.Elog_like_given_pX_pY / update on the kernels."""
+
+    def __init__(self, dim, n, p1, p2, batch_shape=(), mask=None, X_mask=None, transition_mask=None, pad_X=False):
+        self.p1 = p1
+        self.p2 = p2
+        dist = MatrixNormalWishart(event_shape=(n, p1 + p2), batch_shape=batch_shape + (dim,), pad_X=pad_X,
+                                   X_mask=X_mask, mask=mask)
+        super().__init__(dist, transition_mask=transition_mask)
+
+    def _stack(self, XRY):
+        from .mvn import MultivariateNormal_vector_format
+        Sx = XRY[0].ESigma()
+        lead, p1, p2 = Sx.shape[:-2], self.p1, self.p2
+        Sigma = torch.zeros(lead + (p1 + p2, p1 + p2), dtype=Sx.dtype, device=Sx.device)
+        Sigma[..., :p1, :p1] = Sx                                           # utils/matrix_utils.py:4-9 with a zero R block
+        mu = torch.cat((XRY[0].mean(), XRY[1]), dim=-2)
+        return MultivariateNormal_vector_format(mu=mu, Sigma=Sigma)
+
+    def Elog_like(self, XRY):
+        return (self.obs_logits(XRY) * self.p).sum(-1)
+
+    def obs_logits(self, XRY, t=None):
+        from .mvn import Delta
+        if t is not None:
+            raise NotImplementedError("time-sliced beliefs (HMM.update with T) are not supported for ARHMM_prXRY")
+        return self.obs_dist.Elog_like_given_pX_pY(self._stack(XRY), Delta(XRY[2]))
+
+    def update_obs_parms(self, XRY, lr, beta=None):
+        from .mvn import Delta
+        self.obs_dist.update(self._stack(XRY), Delta(XRY[2]), p=self.p, lr=lr, beta=beta)

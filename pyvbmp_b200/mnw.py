@@ -218,8 +218,9 @@ class MatrixNormalWishart():
         N = 1
         for v in sample:
             N *= v
-        Sx = pX.ESigma().expand(sample + (1, p_in, p_in)).reshape(N, p_in * p_in)
-        Sy = pY.ESigma().expand(sample + (1, self.n, self.n)).reshape(N, self.n * self.n)
+        # a point mass (dists/Delta.py: no ESigma) contributes no covariance term
+        Sx = pX.ESigma().expand(sample + (1, p_in, p_in)).reshape(N, p_in * p_in) if hasattr(pX, "ESigma") else None
+        Sy = pY.ESigma().expand(sample + (1, self.n, self.n)).reshape(N, self.n * self.n) if hasattr(pY, "ESigma") else None
         return N, sample, mx, my, Sx, Sy
 
     def update(self, pX, pY, p=None, lr=1.0, beta=None):
@@ -236,10 +237,11 @@ class MatrixNormalWishart():
                 p_in = self.p - int(self.pad_X)
                 D = p_in + n
                 P2 = _lib.f32(p, self.mu.device).reshape(N, K)
-                Cx, Cy = P2.t() @ Sx, P2.t() @ Sy
                 Gk = G.view(K, D + 1, D + 1)
-                Gk[:, :p_in, :p_in] += Cx.view(K, p_in, p_in)
-                Gk[:, p_in:D, p_in:D] += Cy.view(K, n, n)
+                if Sx is not None:
+                    Gk[:, :p_in, :p_in] += (P2.t() @ Sx).view(K, p_in, p_in)
+                if Sy is not None:
+                    Gk[:, p_in:D, p_in:D] += (P2.t() @ Sy).view(K, n, n)
                 self._update_from_gram(G, plan, p is not None, lr, beta)
                 return
         # any other layout: the reference's op order on torch
@@ -273,10 +275,21 @@ class MatrixNormalWishart():
         if bp is not None and self.event_dim == 2:
             N, sample, mx, my, Sx, Sy = bp
             K = self.batch_shape[0]
-            corr = Sy @ self.EinvSigma().expand(K, self.n, self.n).reshape(K, -1).t() \
-                + Sx @ Exx.expand(K, p_in, p_in).reshape(K, -1).t()
+            corr = 0.0
+            if Sy is not None:
+                corr = corr + Sy @ self.EinvSigma().expand(K, self.n, self.n).reshape(K, -1).t()
+            if Sx is not None:
+                corr = corr + Sx @ Exx.expand(K, p_in, p_in).reshape(K, -1).t()
+            if isinstance(corr, float):
+                return base
             return base - 0.5 * corr.view(sample + (K,))
-        corr = (pY.ESigma() * self.EinvSigma()).sum(-1).sum(-1) + (pX.ESigma() * Exx).sum(-1).sum(-1)
+        corr = 0.0
+        if hasattr(pY, "ESigma"):
+            corr = corr + (pY.ESigma() * self.EinvSigma()).sum(-1).sum(-1)
+        if hasattr(pX, "ESigma"):
+            corr = corr + (pX.ESigma() * Exx).sum(-1).sum(-1)
+        if isinstance(corr, float):
+            return base
         for i in range(self.event_dim - 2):
             corr = corr.sum(-1)
         return base - 0.5 * corr

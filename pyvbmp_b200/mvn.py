@@ -76,3 +76,51 @@ class MultivariateNormal_vector_format():
         """Log normaliser of the natural form: -mu^T invSigma mu / 2 + logdet(invSigma) / 2 - dim log(2 pi) / 2."""
         quad = (self.mean() * self.EinvSigmamu()).sum((-2, -1))
         return 0.5 * (self.ElogdetinvSigma() - quad - self.dim * math.log(2.0 * math.pi))
+
+
+class Delta():
+    """dists/Delta.py:6-52: an observation dressed as a distribution (a point mass at X), so that callers can ask it for the
+    expectations a belief provides.  ESigma (not in the reference class) is the zero covariance, as a scalar that broadcasts."""
+
+    def __init__(self, X):
+        self.X = X
+
+    def unsqueeze(self, dim):
+        return Delta(self.X.unsqueeze(dim))
+
+    def squeeze(self, dim):
+        return Delta(self.X.squeeze(dim))
+
+    def sum(self, dim, keepdim=False):
+        return self.X.sum(dim, keepdim=keepdim)
+
+    def cumsum(self, dim):
+        return self.X.cumsum(dim)
+
+    @property
+    def shape(self):
+        return self.X.shape
+
+    def mean(self):
+        return self.X
+
+    def EX(self):
+        return self.X
+
+    def EXXT(self):
+        return self.X @ self.X.transpose(-1, -2)
+
+    def EXTX(self):
+        return self.X.transpose(-1, -2) @ self.X
+
+    def EXTAX(self, A):
+        return self.X.transpose(-1, -2) @ A @ self.X
+
+    def EXX(self):
+        return self.X ** 2
+
+    def ElogX(self):
+        return torch.log(self.X)
+
+    def E(self, f):
+        return f(self.X)

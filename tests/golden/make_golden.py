@@ -397,6 +397,49 @@ def gen_arhmm_prxy():
     out["ELBO"] = np.asarray(el, dtype=np.float64)
     save("arhmm_prxy_k4_n2_p3", **out)
 
+def gen_arhmm_prxry():
+    """models.ARHMM.ARHMM_prXRY (models/ARHMM.py:55-77): belief about latent regressors X stacked on observed regressors R,
+    observed outputs Y (DynamicMarkovBlanketDiscovery's observation model)."""
+    from dists.MultivariateNormal_vector_format import MultivariateNormal_vector_format as MVN
+    from models.ARHMM import ARHMM_prXRY
+    g = torch.Generator().manual_seed(57)
+    K, n, p1, p2, Tn, S = 4, 2, 2, 1, 40, 12
+    Atrue = torch.randn(K, n, p1 + p2, generator=g)
+    trans = torch.full((K, K), 0.1 / (K - 1)) + torch.eye(K) * (0.9 - 0.1 / (K - 1))
+    z = torch.zeros(Tn, S, dtype=torch.long)
+    z[0] = torch.randint(K, (S,), generator=g)
+    for t in range(1, Tn):
+        z[t] = torch.multinomial(trans[z[t - 1]], 1, generator=g).squeeze(-1)
+    XR = torch.randn(Tn, S, p1 + p2, generator=g)
+    Y = torch.einsum("tsij,tsj->tsi", Atrue[z], XR) + 0.2 * torch.randn(Tn, S, n, generator=g)
+    Ax = 0.2 * torch.randn(Tn, S, 1, p1, p1, generator=g)
+    Sx = Ax @ Ax.transpose(-1, -2) + 0.01 * torch.eye(p1)
+    mux = XR[..., :p1].unsqueeze(-2).unsqueeze(-1)                                  # (T,S,1,p1,1)
+    R = XR[..., p1:].unsqueeze(-2).unsqueeze(-1)                                    # (T,S,1,p2,1)
+    Yv = Y.unsqueeze(-2).unsqueeze(-1)                                              # (T,S,1,n,1)
+    torch.manual_seed(17)
+    m = ARHMM_prXRY(K, n, p1, p2)
+    out = {"mux": T(mux), "Sx": T(Sx), "R": T(R), "Y": T(Yv), "K": K, "n": n, "p1": p1, "p2": p2}
+
+    def st():
+        s = mnw_state(m.obs_dist, "obs.")
+        s.update(dir_state(m.transition, "transition."))
+        s.update(dir_state(m.initial, "initial."))
+        return s
+    out.update(tagged(st(), "init"))
+    XRY = (MVN(mu=mux, Sigma=Sx), R, Yv)
+    out["init/obs_logits"] = T(m.obs_logits(XRY))
+    el = []
+    for i in range(3):
+        m.update(XRY, iters=1, lr=1.0)
+        el.append(float(m.ELBO_last))
+        if i == 0:
+            out.update(tagged(st(), "iter1"))
+            out["iter1/p"], out["iter1/logZ"], out["iter1/NA"] = T(m.p), T(m.logZ), T(m.NA)
+    out["ELBO"] = np.asarray(el, dtype=np.float64)
+    save("arhmm_prxry_k4_n2_p21", **out)
+
+
 # ---- diagonal-precision nodes (SURVEY.md §8f #4): NormalGamma / GaussianMixtureModel(isotropic=True), MatrixNormalGamma /
 # ---- MixtureofLinearTransforms(type='Gamma')
 
@@ -524,7 +567,8 @@ def gen_diag():
 
 
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "diag":      # only the fixtures added in round 2
+    if len(sys.argv) > 1 and sys.argv[1] == "round2":    # only the fixtures added in round 2
+        gen_arhmm_prxry()
         gen_diag()
         sys.exit(0)
     gen_gmm()
@@ -536,3 +580,4 @@ if __name__ == "__main__":
     gen_arhmm()
     gen_arhmm_prxy()
     gen_diag()
+    gen_arhmm_prxry()

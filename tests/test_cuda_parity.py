@@ -350,6 +350,33 @@ def test_arhmm_prxy_golden():
     assert np.max(np.abs(np.array(elbo) - fix["ELBO"]) / np.abs(fix["ELBO"])) < PARITY
 
 
+def test_arhmm_prxry_golden():
+    """ARHMM_prXRY (models/ARHMM.py:55-77; DynamicMarkovBlanketDiscovery's observation model) against the reference's own
+    outputs: belief about latent regressors stacked on observed ones, outputs as a point mass."""
+    fix = load_golden("arhmm_prxry_k4_n2_p21")
+    K, n, p1, p2 = (int(fix[k]) for k in ("K", "n", "p1", "p2"))
+    torch.manual_seed(0)
+    h = V.ARHMM_prXRY(K, n, p1, p2).to(DEV)
+    set_state(h, {k.replace("obs.", "obs_dist."): v for k, v in tag(fix, "init").items()})
+    t = lambda k: torch.as_tensor(fix[k]).to(DEV)                                   # noqa: E731
+    XRY = (V.MultivariateNormal_vector_format(mu=t("mux"), Sigma=t("Sx")), t("R"), t("Y"))
+    ol = h.obs_logits(XRY)
+    assert ol.shape == fix["init/obs_logits"].shape
+    assert_close(ol, fix["init/obs_logits"], PARITY, "obs_logits")
+    h.update(XRY, iters=1)
+    it1 = tag(fix, "iter1")
+    assert_maxabs(h.p.cpu(), it1["p"], 2e-4, "h.p.cpu()")
+    assert_close(h.logZ, it1["logZ"], PARITY, "logZ")
+    assert_close(h.NA, it1["NA"], PARITY, "NA")
+    for k in ("obs.mu", "obs.invV", "obs.V", "obs.invU.invU", "obs.invU.U", "transition.alpha", "initial.alpha"):
+        assert_close(get(h, k.replace("obs.", "obs_dist.")), it1[k], PARITY, k)
+    elbo = [float(h.ELBO_last)]
+    for _ in range(2):
+        h.update(XRY, iters=1)
+        elbo.append(float(h.ELBO_last))
+    assert np.max(np.abs(np.array(elbo) - fix["ELBO"]) / np.abs(fix["ELBO"])) < PARITY
+
+
 # -------------------------------------------------------------------------------------------------
 # config-2 shape (d=64, K=256) against the fp64 oracle, overlapping-clusters variant (SURVEY App. F)
 # -------------------------------------------------------------------------------------------------

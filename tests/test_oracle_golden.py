@@ -230,6 +230,28 @@ def test_arhmm_prxy_trajectory():
     assert np.max(np.abs(got - fix["ELBO"]) / np.abs(fix["ELBO"])) < PARITY
 
 
+def test_arhmm_prxry_trajectory():
+    """ARHMM_prXRY (models/ARHMM.py:55-77): latent-regressor belief stacked on observed regressors, observed outputs."""
+    fix = load_golden("arhmm_prxry_k4_n2_p21")
+    K, n, p1, p2 = (int(fix[k]) for k in ("K", "n", "p1", "p2"))
+    h = O.arhmm_prxry_new(K, n, p1, p2)
+    O.load_state(h, tag(fix, "init"))
+    t = lambda k: torch.as_tensor(fix[k])                                           # noqa: E731
+    mux, Sx, R, Y = t("mux"), t("Sx"), t("R"), t("Y")
+    ol = O.mnw_elog_like_given(h["obs"], *O.arhmm_prxry_beliefs(mux, Sx, R, Y))
+    assert_close(ol, fix["init/obs_logits"], 2e-5, "obs_logits")
+    trace = O.arhmm_prxry_update(h, mux, Sx, R, Y, iters=1)
+    it1 = tag(fix, "iter1")
+    assert float((h["p"] - it1["p"]).abs().max()) < 5e-5
+    assert_close(h["logZ"], it1["logZ"], PARITY, "logZ")
+    assert_close(h["NA"], it1["NA"], PARITY, "NA")
+    for k in ("obs.mu", "obs.invV", "obs.invU.invU", "transition.alpha", "initial.alpha"):
+        assert_close(O.flatten_state(h)[k], it1[k], PARITY, k)
+    trace += O.arhmm_prxry_update(h, mux, Sx, R, Y, iters=2)
+    got = np.array([float(e) for e in trace])
+    assert np.max(np.abs(got - fix["ELBO"]) / np.abs(fix["ELBO"])) < PARITY
+
+
 @pytest.mark.parametrize("name", ["molt_given_n3_p4_k5", "molt_given_n8_p16_k6"])
 def test_molt_given_beliefs(name):
     """Expectation-input E and M steps (transforms/MatrixNormalWishart.py:143-172, 234-249;
