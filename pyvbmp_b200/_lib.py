@@ -366,7 +366,7 @@ def _note_path(what, N, GX, G, K, Dp, d0, d1, weighted):
                   "results are identical, throughput is ~20x lower", RuntimeWarning, stacklevel=3)
 
 
-_TC_DP = (16, 32, 64)
+_TC_DP = (16, 32, 64, 128)
 
 
 def wishart_update(SExx, N, invU0, nu0, invU_old, nu_old, C, d, lr):

@@ -56,6 +56,7 @@ constexpr int EU_TILE = 256;
 constexpr int EU_MAXSTAGE = 8;     // the launcher picks the number of stages that fits (5 at DP = 64, K <= 256)
 constexpr int EU_MAXK = 512;
 constexpr int EU_N = 128;           // columns per group
+constexpr int EU_FS = 128;          // feature-scale table: fs[i] = 2^e_i, fs[EU_FS + i] = 2^-e_i
 
 template <int DP, bool F16>
 struct EuCfg {
@@ -65,9 +66,11 @@ struct EuCfg {
   static constexpr int ACOLS = F16 ? DP / 2 : DP;   // TMEM columns of one A image (hi or lo) of a half
   // accumulators: the (group, half) pairs rotate through NBUF 128-column buffers.  With fp16 operands a half's MMAs take
   // ~630 cycles, less than the commit -> tcgen05.ld -> release round trip of the other half's accumulator, so a third
-  // buffer (the A images only need 128 columns) gives that round trip two bursts to complete.
-  static constexpr int NBUF = F16 ? 3 : 2;
-  static constexpr int DCOL0 = F16 ? 128 : 256;
+  // buffer (the A images only need 128 columns up to DP = 64) gives that round trip two bursts to complete.  DP = 128
+  // (fp16 operands only): the A images of the two halves take 4 x 64 = 256 columns, which leaves two accumulators.
+  static constexpr int DCOL0 = 4 * ACOLS > 128 ? 4 * ACOLS : 128;
+  static constexpr int NBUF = (512 - DCOL0) / EU_N >= 3 ? 3 : 2;
+  static_assert(DCOL0 + NBUF * EU_N <= 512, "TMEM budget");
   __host__ __device__ static constexpr int n0(int ks) { return ks * CG * KSTEP; }
   __host__ __device__ static constexpr int nn(int ks) { return EU_N - n0(ks); }
   __host__ __device__ static constexpr int blk_off(int ks) {
@@ -97,7 +100,7 @@ struct EuCfg {
 // ---- pack: W (C, DP, DP) fp32 row-major [i][j] -> per group [hi | lo | m | cst, 2^-t] record; B[n][k] = W_c[i = k][j]
 // with (c, j) = column n as above; K-step block ks holds rows n >= n0(ks) as [chunk (2)][row][16 bytes]: 4 TF32 or
 // 8 fp16 per chunk, i = KSTEP ks + (KSTEP / 2) chunk + e.
-// fp16 operands: fs[i] = 2^e_i (applied to feature i of the samples), fs[64 + i] = 2^-e_i (applied to row i of every W_k)
+// fp16 operands: fs[i] = 2^e_i (applied to feature i of the samples), fs[EU_FS + i] = 2^-e_i (applied to row i of every W_k)
 template <int DP>
 __global__ void estep_rowscale_kernel(const float* __restrict__ W, int K, float* __restrict__ fs) {
   __shared__ uint32_t mx;
@@ -113,7 +116,7 @@ __global__ void estep_rowscale_kernel(const float* __restrict__ W, int K, float*
     int e = 0;
     if (mx != 0u) { e = (int)(mx >> 23) - 127; e = e > 60 ? 60 : (e < -60 ? -60 : e); }
     fs[i] = __uint_as_float((uint32_t)(127 + e) << 23);
-    fs[64 + i] = __uint_as_float((uint32_t)(127 - e) << 23);
+    fs[EU_FS + i] = __uint_as_float((uint32_t)(127 - e) << 23);
   }
 }
 
@@ -131,7 +134,7 @@ __global__ void estep_pack_kernel(const float* __restrict__ W, const float* __re
       const int c = g * C::CG + o / (DP * DP);
       if (c < K)
         atomicMax(&wmax[o / (DP * DP)],
-                  __float_as_uint(fabsf(W[(size_t)c * DP * DP + o % (DP * DP)] * fs[64 + (o % (DP * DP)) / DP])) & 0x7f800000u);
+                  __float_as_uint(fabsf(W[(size_t)c * DP * DP + o % (DP * DP)] * fs[EU_FS + (o % (DP * DP)) / DP])) & 0x7f800000u);
     }
     __syncthreads();
   }
@@ -178,7 +181,7 @@ __global__ void estep_pack_kernel(const float* __restrict__ W, const float* __re
       const int r = (rem % (nn * 16)) / 16, e = (rem % 16) / 2;
       const int n = C::n0(ks) + r, cl = C::col_cl(n), j = C::col_j(n), i = 16 * ks + 8 * ch + e;
       const int c = g * C::CG + cl;
-      const float v = (c < K) ? W[((size_t)c * DP + i) * DP + j] * fs[64 + i] * wsc[cl] : 0.f;     // both factors: powers of 2
+      const float v = (c < K) ? W[((size_t)c * DP + i) * DP + j] * fs[EU_FS + i] * wsc[cl] : 0.f;     // both factors: powers of 2
       const __half a = __float2half_rn(v);
       hi[o] = a;
       lo[o] = __float2half_rn(v - __half2float(a));
@@ -210,7 +213,7 @@ struct EuSmem {
   uint64_t turn[2];           // issue token between the two MMA warps
   uint64_t ndone[2], nfree[2];  // mode 1: tile's logits + logZ_n complete (workers -> normaliser) / lz buffer free again
   uint32_t tmem_base;
-  alignas(16) float fsc[64];  // fp16 operands: 2^e_i per feature
+  alignas(16) float fsc[EU_FS];  // fp16 operands: 2^e_i per feature
   double red[8];
 };
 
@@ -255,7 +258,7 @@ estep_umma_kernel(EstepArgs a, const uint8_t* __restrict__ Wp, const float* __re
     fence_barrier_init();
   }
   for (int o = tid; o < 2048; o += EU_THREADS) ones[o] = ((o & 1023) < 512 && (o & 3) < 2) ? 1.f : 0.f;
-  if (F16 && tid < 64) S->fsc[tid] = tid < DP ? fs[tid] : 1.f;
+  if (F16 && tid < EU_FS) S->fsc[tid] = tid < DP ? fs[tid] : 1.f;
   fence_proxy_async();
   if (warp == 1) tmem_alloc<512>(&S->tmem_base);
   tc_fence_before();
@@ -620,7 +623,9 @@ estep_umma_kernel(EstepArgs a, const uint8_t* __restrict__ Wp, const float* __re
 static int eu_num_sms() { return num_sms(); }
 
 // the TF32 record is the larger one: the workspace is sized for it whichever precision runs
-static size_t eu_group_bytes(int Dp) { return Dp == 64 ? EuCfg<64, false>::REC : (Dp == 32 ? EuCfg<32, false>::REC : EuCfg<16, false>::REC); }
+static size_t eu_group_bytes(int Dp) {
+  return Dp == 128 ? EuCfg<128, true>::REC : Dp == 64 ? EuCfg<64, false>::REC : (Dp == 32 ? EuCfg<32, false>::REC : EuCfg<16, false>::REC);
+}
 static bool eu_use_f16() {
   static int v = -1;
   if (v < 0) {
@@ -632,9 +637,12 @@ static bool eu_use_f16() {
 static int eu_cg(int Dp) { return EU_N / Dp; }
 static size_t eu_align(size_t x) { return (x + 255) / 256 * 256; }
 
+static bool eu_use_f16();
 bool estep_umma_supported(long long N, int GX, int G, int K, int Dp, int d0, int d1) {
   (void)d0; (void)d1;
-  return G == 1 && GX == 1 && (Dp == 16 || Dp == 32 || Dp == 64) && (K % 4 == 0) && K <= EU_MAXK && N >= 256;
+  // Dp = 128 exists with fp16 operands only (the TF32 images of two 128-row halves alone would fill tensor memory)
+  return G == 1 && GX == 1 && (Dp == 16 || Dp == 32 || Dp == 64 || (Dp == 128 && eu_use_f16())) && (K % 4 == 0) &&
+         K <= EU_MAXK && N >= 256;
 }
 
 bool gram_rpack_usable();
@@ -649,7 +657,7 @@ size_t estep_umma_workspace_bytes(long long N, int G, int K, int Dp, int mode) {
   if (!estep_umma_supported(N, 1, G, K, Dp, 1, 0)) return 0;
   const int ngroups = (K + eu_cg(Dp) - 1) / eu_cg(Dp);
   const size_t ctas = 512;   // upper bound on the persistent grid
-  return eu_align((size_t)ngroups * eu_group_bytes(Dp)) + 512 + eu_align(ctas * K * sizeof(float)) + eu_align(ctas * sizeof(double)) + 256;
+  return eu_align((size_t)ngroups * eu_group_bytes(Dp)) + 2 * EU_FS * sizeof(float) + eu_align(ctas * K * sizeof(float)) + eu_align(ctas * sizeof(double)) + 256;
 }
 
 int launch_estep_reduce(const float*, const double*, int nb, int G, int K, float* NA, float* logZ, cudaStream_t);
@@ -699,12 +707,13 @@ int launch_estep_umma(const EstepArgs& a, int mode, void* ws, size_t ws_bytes, f
   uint8_t* Wp = (uint8_t*)p;
   p += eu_align((size_t)ngroups * eu_group_bytes(a.Dp));
   float* fs = (float*)p;                                    // feature scales of the fp16 operands: [2^e_i | 2^-e_i]
-  p += 512;
+  p += 2 * EU_FS * sizeof(float);
   float* NA_part = (float*)p;
   p += eu_align((size_t)512 * a.K * sizeof(float));
   double* logZ_part = (double*)p;
   if (eu_use_f16()) {
     switch (a.Dp) {
+      case 128: return eu_launch<128, true>(a, mode, Wp, fs, NA_part, logZ_part, NA, logZ, st);
       case 64: return eu_launch<64, true>(a, mode, Wp, fs, NA_part, logZ_part, NA, logZ, st);
       case 32: return eu_launch<32, true>(a, mode, Wp, fs, NA_part, logZ_part, NA, logZ, st);
       case 16: return eu_launch<16, true>(a, mode, Wp, fs, NA_part, logZ_part, NA, logZ, st);

@@ -50,7 +50,8 @@ constexpr float GU_RMAX = 3.99f;     // ... and must stay below 65504 / 2^14
 #ifndef GU_NR_V
 #define GU_NR_V 6
 #endif
-constexpr int GU_NR = GU_NR_V;       // raw ring depth
+constexpr int GU_NR = GU_NR_V;       // raw ring depth (the launcher takes fewer slots when the chunk records of a wide
+                                     // feature vector, D > 64, would not fit shared memory: GuArgs::nr)
 // pipeline depth (B stages in shared memory = A buffers in TMEM) and pair columns per MMA.  TMEM budget: D1 + D2 = 2 NPMAX
 // columns + NSTG A buffers of hi + lo = 32 NSTG columns <= 512.  A CTA pair needs 4 stages to hide the cross-CTA barrier
 // round trips (192 columns); a single CTA is best with 2 stages and 224 columns.
@@ -70,6 +71,7 @@ struct GuArgs {
   int d0, d1;
   long long N; int K;
   int npb, NPB, P, ncb, splits;      // pair blocks, pair columns of the widest block, total pairs, component blocks, sample splits
+  int nr;                            // raw ring slots in use, 2 <= nr <= GU_NR
   int diag;                          // 1: only the pairs (i, i) and (i, D) — the statistics of the diagonal-precision nodes
   int wbase, wextra;                 // block pb holds 16 (wbase + (pb < wextra)) pair columns starting at 16 (pb wbase + min(pb, wextra))
   long long S_per;                   // samples per split (multiple of GU_SC)
@@ -172,7 +174,8 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant_
   constexpr int GU_NSTG = gu_nstg(PAIR), GU_NPMAX = gu_npmax(PAIR);
   const int stageB = 2 * (PAIR ? a.NPB / 2 : a.NPB) * 64;    // sized for a full-width pair block
   uint8_t* raw = smem_raw;
-  uint8_t* bst = raw + GU_NR * rawB;
+  const int nr = a.nr;
+  uint8_t* bst = raw + nr * rawB;
   GuSmem* S = reinterpret_cast<GuSmem*>(bst + GU_NSTG * stageB);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -214,9 +217,10 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant_
   if (warp == 0) {
     // ================= producer: one TMA box per operand per 16-sample chunk (rows past N are zero filled) ====
     const uint32_t bytes = (uint32_t)(rawR + rawZ0 + rawZ1);
-    for (int c = 0; c < nchunks; ++c) {
-      const int s = c % GU_NR;
-      mbar_wait(&S->rempty[s], ((c / GU_NR) & 1) ^ 1);
+    int s = 0;
+    uint32_t rph = 0;                                     // slot and lap parity of the raw ring (no division in the loop)
+    for (int c = 0; c < nchunks; ++c, s = (s + 1 == nr ? 0 : s + 1), rph ^= (s == 0 ? 1u : 0u)) {
+      mbar_wait(&S->rempty[s], rph ^ 1);
       if (elect_one()) {
         const int r0 = (int)(nb + (long long)c * SC);
         uint8_t* dst = raw + (size_t)s * rawB;
@@ -324,10 +328,13 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant_
 #pragma unroll
     for (int i = 0; i < GU_NSTG; ++i) bfull_addr[i] = PAIR ? mapa_u32(&S->bfull[i], 0) : smem_u32(&S->bfull[i]);
     const uint32_t dempty_addr = PAIR ? mapa_u32(&S->dempty, 0) : smem_u32(&S->dempty);
-    for (int c = set; c < nchunks; c += 2) {
-      const int s = c % GU_NR, st = c % GU_NSTG;
+    int s = set;                                           // raw ring position of chunk c (nr >= 2): slot, lap parity
+    uint32_t rph = 0;
+    for (int c = set; c < nchunks; c += 2, s += 2) {
+      if (s >= nr) { s -= nr; rph ^= 1u; }
+      const int st = c % GU_NSTG;
       const int nflush = c >> fls;
-      mbar_wait(&S->rfull[s], (c / GU_NR) & 1);
+      mbar_wait(&S->rfull[s], rph);
       mbar_wait(&S->bempty[st], ((c / GU_NSTG) & 1) ^ 1);
       tc_fence_after();
       // ---- A operand: r[s][comp] for this thread's 8 (fp16: 16) samples, split, into TMEM
@@ -518,8 +525,8 @@ __global__ void gram_pair_reduce_kernel(const float* __restrict__ part, int spli
 // column maxima of |z| (bit patterns, which order like the values for non-negative floats) into hdr[col0 + c]
 __global__ void __launch_bounds__(256) gram_colmax_kernel(const float* __restrict__ z, int d, long long N, int col0,
                                                           uint32_t* __restrict__ hdr) {
-  __shared__ uint32_t smax[64];
-  if (threadIdx.x < 64) smax[threadIdx.x] = 0u;
+  __shared__ uint32_t smax[VBMP_MAX_D];
+  if (threadIdx.x < VBMP_MAX_D) smax[threadIdx.x] = 0u;
   __syncthreads();
   const int d4 = d >> 2;                                         // d % 4 == 0
   const long long T = ((long long)gridDim.x * blockDim.x) / d4 * d4;   // threads that keep a fixed column group
@@ -580,19 +587,19 @@ __global__ void __launch_bounds__(256) gram_rsplit_kernel(const float* __restric
 __global__ void __launch_bounds__(256) gram_zprep_kernel(const float* __restrict__ z0, int d0, const float* __restrict__ z1,
                                                          int d1, long long N, const uint32_t* __restrict__ hdr,
                                                          uint8_t* __restrict__ zt, int zrec) {
-  __shared__ float tile[64][33];                 // [feature][sample], stride 33: both phases are bank-conflict free
-  __shared__ float fs[64];
+  __shared__ float tile[VBMP_MAX_D][33];         // [feature][sample], stride 33: both phases are bank-conflict free
+  __shared__ float fs[VBMP_MAX_D];
   const int D = d0 + d1;
   if (threadIdx.x < D) fs[threadIdx.x] = __uint_as_float((uint32_t)(127 + gu_feat_exp(hdr[threadIdx.x])) << 23);
   __syncthreads();
   const long long nch = (N + 31) / 32;
-  const int sidx = threadIdx.x >> 3, c0 = threadIdx.x & 7;       // 8 threads per sample row, float4 columns c0 and c0 + 8
+  const int sidx = threadIdx.x >> 3, c0 = threadIdx.x & 7;       // 8 threads per sample row, float4 columns c0 + 8 h
   const int q0 = d0 >> 2, q1 = d1 >> 2;
   for (long long ch = blockIdx.x; ch < nch; ch += gridDim.x) {
     const long long n = ch * 32 + sidx;
     const bool ok = n < N;
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
+    for (int h = 0; h < VBMP_MAX_D / 32; ++h) {
       const int c4 = c0 + 8 * h;
       if (c4 < q0) {
         const float4 v = ok ? __ldg(reinterpret_cast<const float4*>(z0 + (size_t)n * d0) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -683,8 +690,9 @@ size_t gram_zpack_bytes(long long N, int D) { return GU_HDR_WORDS * sizeof(uint3
 
 bool gram_umma_supported(long long N, int GX, int GP, int G, int K, int Dp, int d0, int d1, bool has_p) {
   const int D = d0 + d1;
-  return has_p && G == 1 && GX == 1 && GP == 1 && Dp >= 16 && Dp <= 64 && D <= 64 && (K % 4 == 0) && (d0 % 4 == 0) &&
-         (d1 % 4 == 0) && N >= 2048;
+  // D > 64 (Dp = 128) exists with fp16 operands only: the TF32 kernel stays its on-device fallback
+  return has_p && G == 1 && GX == 1 && GP == 1 && Dp >= 16 && Dp <= 128 && D <= 128 && (D <= 64 || gu_use_f16()) &&
+         (K % 4 == 0) && (d0 % 4 == 0) && (d1 % 4 == 0) && N >= 2048;
 }
 
 // [flag block | per-split partials | weight images unless handed in | sample image unless handed in]
@@ -728,7 +736,12 @@ static int gu_launch_main(const GramArgs& a, GuArgs g, bool pair, cudaStream_t s
   if (e) { set_error("gram_umma: cuTensorMapEncodeTiled failed (%d)", e); return VBMP_ERR_CUDA; }
   const int NH = pair ? g.NPB / 2 : g.NPB;
   const int rawB = (F16 ? 2 * GU_RREC + g.zrec : SC * g.kcb * 4 + SC * a.d0 * 4 + SC * a.d1 * 4) / 128 * 128 + 128;
-  const size_t smem = (size_t)GU_NR * rawB + (size_t)gu_nstg(pair) * 2 * NH * 64 + sizeof(GuSmem) + 64;
+  const size_t stages = (size_t)gu_nstg(pair) * 2 * NH * 64 + sizeof(GuSmem) + 64;
+  int nr = (int)((227 * 1024 - stages) / rawB);
+  if (nr > GU_NR) nr = GU_NR;
+  if (nr < 2) { set_error("gram_umma: D=%d does not fit shared memory", D); return VBMP_ERR_UNSUPPORTED; }
+  g.nr = nr;
+  const size_t smem = (size_t)nr * rawB + stages;
   const int grid = g.splits * g.ncb * g.npb;
   const bool same = (a.d1 == 0 || a.d1 == a.d0);
   const int sf = same && (a.d0 == 64 || a.d0 == 32 || a.d0 == 16) ? a.d0 : 0;

@@ -125,6 +125,44 @@ def test_arhmm_cfg4_shape_vs_fp64_oracle():
             assert_close(get(h, k.replace("obs.", "obs_dist.")), flat[k], 3e-4 if it == 0 else PARITY, f"{k} it{it}")
 
 
+def test_gmm_d128_vs_fp64_oracle():
+    """GaussianMixtureModel d = 128 (the north star's upper feature dimension), K = 64, N = 16 384: the tcgen05 kernels at
+    Dp = 128 — E-step with two accumulator buffers, Gram over 8385 pair columns — step-wise against the fp64 oracle."""
+    from pyvbmp_b200 import _lib
+    N, K, d = 16384, 64, 128
+    g = torch.Generator().manual_seed(13)
+    mu = 0.4 * torch.randn(K, d, generator=g)
+    A = torch.eye(d) + 0.3 * torch.randn(K, d, d, generator=g) / 11
+    z = torch.randint(K, (N,), generator=g)
+    X = mu[z] + torch.einsum("nij,nj->ni", A[z], torch.randn(N, d, generator=g))
+    torch.manual_seed(7)
+    m = V.GaussianMixtureModel(K, d)
+    m.initialize(X)
+    ref = O.gmm_new(K, d)
+    O.load_state(ref, {"dist.mu": m.dist.mu.clone(), "pi.alpha": m.pi.alpha.clone()})
+    O.to_dtype(ref, torch.float64)
+    m.to(DEV)
+    Xd, X64 = X.to(DEV), X.double()
+    keys = ("dist.mu", "dist.lambda_mu", "dist.invU.invU", "dist.invU.U", "dist.invU.nu", "pi.alpha")
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")                   # leaving the tensor-core window would warn: it must not
+        for it in range(3):
+            set_state(m, {k: v.float() for k, v in O.flatten_state(ref).items()})
+            m.update(Xd, 1)
+            tr = O.mixture_update(ref, X64, 1, exact=False, chunk=2048)
+            assert abs(float(m.ELBO_last) - float(tr[0])) <= PARITY * abs(float(tr[0])), it
+            L = float(ref["log_p"].max(-1)[0].abs().max())
+            assert_maxabs(m.p.cpu().double(), ref["p"], max(2e-4, 4e-7 * L), f"p it{it} (|logit| {L:.2e})")
+            nbad, margins = argmax_mismatch_report(m.p, ref["p"], ref["log_p"])
+            assert nbad == 0 or max(margins) < 1e-3, (it, nbad, margins)
+            assert_close(m.NA, ref["NA"], PARITY, "NA")
+            flat = O.flatten_state(ref)
+            for k in keys:
+                assert_close(get(m, k), flat[k], 3e-4 if (it == 0 or k == "dist.invU.U") else PARITY, f"{k} it{it}")
+            m.dist.invU.check()
+
+
 def test_wishart_standalone_update_and_kl():
     """Wishart.ss_update / KLqprior / ElogdetinvSigma called directly (dists/Wishart.py:43-56, 82-94): SURVEY.md §8 a9."""
     d, K = 24, 7
