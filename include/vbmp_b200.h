@@ -119,6 +119,11 @@ size_t vbmp_diag_estep_workspace_bytes(long long N, int G, int K, int d, int mod
 int vbmp_diag_estep(const float* x, int d, long long N, int GX, const int* xg, const float* mu, const float* tau,
                     const float* cst, int G, int K, int mode, float* out, float* logZn, float* NA, float* logZ,
                     void* workspace, size_t workspace_bytes, void* stream);
+/* ... and with the K2 -> K3 hand-over of vbmp_estep_rpack (mode 1, G = 1, K <= 256): the weight images for vbmp_gram_ex */
+int vbmp_diag_estep_rpack(const float* x, int d, long long N, int GX, const int* xg, const float* mu, const float* tau,
+                          const float* cst, int G, int K, int mode, float* out, float* logZn, float* NA, float* logZ,
+                          void* workspace, size_t workspace_bytes, void* stream,
+                          void* rpack, size_t rpack_bytes, int* packed);
 
 /* ---- K5: natural-parameter updates (replicated; statistics are post-beta) -----------------------------
  * Wishart.ss_update — dists/Wishart.py:43-56.                                                          */

@@ -20,7 +20,7 @@ FORCE_SIMT = int(os.environ.get("VBMP_FORCE_SIMT", "0"))   # tests: 1 = CUDA-cor
 
 PROFILE = None     # bench.py sets this to {} to collect (start, end) CUDA events per C-ABI call
 LAUNCHES = 0       # kernels launched by the library so far (vbmp_launch_count(): every launch site counts itself)
-_PROFILE_AS = {"vbmp_estep_rpack": "vbmp_estep", "vbmp_gram_rpack": "vbmp_gram", "vbmp_gram_ex": "vbmp_gram",
+_PROFILE_AS = {"vbmp_estep_rpack": "vbmp_estep", "vbmp_diag_estep_rpack": "vbmp_diag_estep", "vbmp_gram_rpack": "vbmp_gram", "vbmp_gram_ex": "vbmp_gram",
                "vbmp_gram_zpack": "vbmp_gram"}
 
 
@@ -62,7 +62,7 @@ EXPORTS = (
     "vbmp_mnw_update", "vbmp_wishart_elogdet", "vbmp_wishart_kl", "vbmp_niw_kl", "vbmp_mnw_kl",
     "vbmp_hmm_forward_backward", "vbmp_rpack_bytes", "vbmp_estep_rpack", "vbmp_gram_rpack",
     "vbmp_zpack_bytes", "vbmp_gram_zpack", "vbmp_gram_ex_workspace_bytes", "vbmp_gram_ex",
-    "vbmp_diag_estep_workspace_bytes", "vbmp_diag_estep", "vbmp_mnw_prep_ex",
+    "vbmp_diag_estep_workspace_bytes", "vbmp_diag_estep", "vbmp_diag_estep_rpack", "vbmp_mnw_prep_ex",
 )
 
 
@@ -183,7 +183,8 @@ def diag_estep(x, N, GX, xg, mu, tau, cst, G, K, d, mode):
     """Diagonal-precision E-step (vbmp_diag_estep): x (N,GX,d), mu / tau (G*K,d), cst (G*K).  Returns logits (mode 0) or
     (p, logZn, NA, logZ) (mode 1)."""
     dev = x.device
-    _rpack_rec.pop(_rpack_key(dev), None)
+    key = _rpack_key(dev)
+    _rpack_rec.pop(key, None)
     out = torch.empty((N, G, K), dtype=torch.float32, device=dev)
     logZn = NA = logZ = None
     if mode == 1:
@@ -192,6 +193,19 @@ def diag_estep(x, N, GX, xg, mu, tau, cst, G, K, d, mode):
         logZ = torch.empty((G,), dtype=torch.float32, device=dev)
     nbytes = lib().vbmp_diag_estep_workspace_bytes(c_longlong(N), c_int(G), c_int(K), c_int(d), c_int(mode))
     ws = _workspace(nbytes, dev)
+    if mode == 1 and RPACK and G == 1 and GX == 1 and K <= 256 and not FORCE_SIMT:
+        rb = int(lib().vbmp_rpack_bytes(c_longlong(N), c_int(K)))
+        buf = _rpack_cache.get(key)
+        if buf is None or buf.numel() < rb:
+            buf = torch.empty(max(rb, 1), dtype=torch.uint8, device=dev)
+            _rpack_cache[key] = buf
+        packed = c_int(0)
+        _call("vbmp_diag_estep_rpack", dev, _ptr(x), c_int(d), c_longlong(N), c_int(GX), _ptr(xg), _ptr(mu), _ptr(tau),
+              _ptr(cst), c_int(G), c_int(K), c_int(mode), _ptr(out), _ptr(logZn), _ptr(NA), _ptr(logZ), _ptr(ws),
+              c_size_t(ws.numel()), _stream(dev), _ptr(buf), c_size_t(buf.numel()), ctypes.byref(packed))
+        if packed.value:
+            _rpack_rec[key] = _tensor_rec(out) + (N, K)
+        return out, logZn, NA, logZ
     _call("vbmp_diag_estep", dev, _ptr(x), c_int(d), c_longlong(N), c_int(GX), _ptr(xg), _ptr(mu), _ptr(tau), _ptr(cst),
           c_int(G), c_int(K), c_int(mode), _ptr(out), _ptr(logZn), _ptr(NA), _ptr(logZ), _ptr(ws), c_size_t(ws.numel()),
           _stream(dev))

@@ -61,7 +61,8 @@ int launch_gram_umma(const GramArgs&, float* gram, void* ws, size_t ws_bytes, cu
 size_t diag_estep_workspace_bytes(long long N, int G, int K, int d, int mode);
 int launch_diag_estep(const float* x, int d, long long N, int GX, const int* xg, const float* mu, const float* tau,
                       const float* cst, int G, int K, int mode, float* out, float* logZn, float* NA, float* logZ,
-                      void* ws, size_t ws_bytes, cudaStream_t st);
+                      void* ws, size_t ws_bytes, cudaStream_t st, unsigned char* rpack = nullptr);
+bool gram_rpack_usable();
 bool estep_umma_can_pack(long long N, int GX, int G, int K, int Dp, int d0, int d1, int mode);
 size_t gram_rpack_bytes(long long N, int K);
 
@@ -170,6 +171,27 @@ int vbmp_diag_estep(const float* x, int d, long long N, int GX, const int* xg, c
                     void* workspace, size_t workspace_bytes, void* stream) {
   return launch_diag_estep(x, d, N, GX, xg, mu, tau, cst, G, K, mode, out, logZn, NA, logZ, workspace, workspace_bytes,
                            (cudaStream_t)stream);
+}
+
+int vbmp_diag_estep_rpack(const float* x, int d, long long N, int GX, const int* xg, const float* mu, const float* tau,
+                          const float* cst, int G, int K, int mode, float* out, float* logZn, float* NA, float* logZ,
+                          void* workspace, size_t workspace_bytes, void* stream, void* rpack, size_t rpack_bytes, int* packed) {
+  if (!packed) { set_error("diag_estep_rpack: packed is NULL"); return VBMP_ERR_SHAPE; }
+  *packed = 0;
+  unsigned char* rp = nullptr;
+  // the images are what the tcgen05 fp16 Gram kernel consumes: same window as the dense E-step's hand-over
+  if (rpack && mode == 1 && G == 1 && GX == 1 && K <= 256 && (K % 4) == 0 && N >= 2048 && d >= 9 && (d % 4) == 0 &&
+      gram_rpack_usable()) {
+    if (rpack_bytes < gram_rpack_bytes(N, K)) {
+      set_error("diag_estep_rpack: buffer too small (%zu < %zu)", rpack_bytes, gram_rpack_bytes(N, K));
+      return VBMP_ERR_WORKSPACE;
+    }
+    rp = (unsigned char*)rpack;
+  }
+  int rc = launch_diag_estep(x, d, N, GX, xg, mu, tau, cst, G, K, mode, out, logZn, NA, logZ, workspace, workspace_bytes,
+                             (cudaStream_t)stream, rp);
+  if (rc == VBMP_OK && rp) *packed = 1;
+  return rc;
 }
 
 size_t vbmp_rpack_bytes(long long N, int K) { return (N < 0 || K < 1) ? 0 : gram_rpack_bytes(N, K); }

@@ -10,10 +10,15 @@
 // before the square, as in the reference (the expanded form x^2 tau - 2 x tau mu + tau mu^2 would cancel for |mu| >> sigma).
 //
 // A CTA owns 128 samples of one theta group; components stream through shared memory in tiles of 128 (mu and tau,
-// feature-major, cp.async double buffered); each of the 256 threads owns an 8-sample x 8-component register tile and
-// walks the features with packed fp32x2 arithmetic: 6 shared 16-byte loads per 64 (sample, component) pairs.
+// feature-major, cp.async); each of the 256 threads owns an 8-sample x 8-component register tile — components
+// 4 tk .. 4 tk + 3 and 64 + 4 tk .. 64 + 4 tk + 3, so that the 16 lanes of a half-warp read consecutive 16-byte words
+// (conflict free; 8 consecutive components per lane put lanes l and l + 4 on the same banks: measured 15.6 ms per 4 Mi
+// rows at d = 64, K = 256, shared-memory bound) — and walks the features with packed fp32x2 arithmetic: 6 shared 16-byte
+// loads per 64 (sample, component) pairs.  Up to d = 64 one parameter tile is resident per CTA and two CTAs share an SM
+// (the loads of one hide behind the arithmetic of the other).
 // Mode 1 reuses the CUDA-core E-step's epilogue: online logsumexp per sample, logits normalised in place from L2,
 // per-CTA partial NA / sum logZ_n reduced in a fixed order (estep_reduce_kernel).
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 namespace vbmp {
@@ -34,6 +39,10 @@ struct DiagArgs {
   const float* cst;                                       // (G, K)
   int G, K, Kp, d, nbuf;                                  // nbuf: parameter tiles in flight (2 while they fit, d <= 64)
   float* out; float* logZn; float* NA_part; double* logZ_part;
+  // mode 1, optional: also emit the responsibilities as K3's pre-split fp16 weight images (gram_umma.cu, GuArgs::rp: record
+  // (component block, 16-sample block) = [hi | lo][8-sample chunk][component][8 fp16] of r 2^14), as the tcgen05 E-step's
+  // normaliser does — the M-step of a NormalGamma mixture then skips its own pass over p (G = 1, K <= 256)
+  unsigned char* rpack; long long nsb;
 };
 
 // (G, K, d) -> (G, d, Kp), zero padded (tau = 0 makes a padding component's quadratic form vanish)
@@ -49,7 +58,7 @@ __global__ void diag_transpose_kernel(const float* __restrict__ mu, const float*
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(256) diag_estep_kernel(DiagArgs a) {
+__global__ void __launch_bounds__(256, 2) diag_estep_kernel(DiagArgs a) {
   extern __shared__ __align__(16) float smf[];
   const int tid = threadIdx.x;
   const int d = a.d;
@@ -92,7 +101,7 @@ __global__ void __launch_bounds__(256) diag_estep_kernel(DiagArgs a) {
     else if (kt + 1 < nkt) { prefetch(kt + 1, (kt + 1) & 1); dg_cp_async_wait<1>(); }
     else { dg_cp_async_wait<0>(); }
     __syncthreads();
-    const float* Mk = Pb + (size_t)(dbl ? (kt & 1) : 0) * 2 * d * DG_KT + tk * 8;
+    const float* Mk = Pb + (size_t)(dbl ? (kt & 1) : 0) * 2 * d * DG_KT + tk * 4;
     const float* Tk = Mk + (size_t)d * DG_KT;
     const float* Xr = Xs + ts * 8;
     float2 acc[8][4];                                 // [sample][component pair]
@@ -105,9 +114,9 @@ __global__ void __launch_bounds__(256) diag_estep_kernel(DiagArgs a) {
       const float4 xa = *reinterpret_cast<const float4*>(Xr + i * XS);
       const float4 xb = *reinterpret_cast<const float4*>(Xr + i * XS + 4);
       const float4 ma = *reinterpret_cast<const float4*>(Mk + i * DG_KT);
-      const float4 mb = *reinterpret_cast<const float4*>(Mk + i * DG_KT + 4);
+      const float4 mb = *reinterpret_cast<const float4*>(Mk + i * DG_KT + 64);
       const float4 ta = *reinterpret_cast<const float4*>(Tk + i * DG_KT);
-      const float4 tb = *reinterpret_cast<const float4*>(Tk + i * DG_KT + 4);
+      const float4 tb = *reinterpret_cast<const float4*>(Tk + i * DG_KT + 64);
       const float xv[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
       const float2 nm[4] = {make_float2(-ma.x, -ma.y), make_float2(-ma.z, -ma.w), make_float2(-mb.x, -mb.y), make_float2(-mb.z, -mb.w)};
       const float2 tt[4] = {make_float2(ta.x, ta.y), make_float2(ta.z, ta.w), make_float2(tb.x, tb.y), make_float2(tb.z, tb.w)};
@@ -125,22 +134,26 @@ __global__ void __launch_bounds__(256) diag_estep_kernel(DiagArgs a) {
 #pragma unroll
     for (int s = 0; s < 8; ++s) {
       const long long n = n0 + ts * 8 + s;
-      const int k0 = kt * DG_KT + tk * 8;
+      const int k0 = kt * DG_KT + tk * 4;                 // this thread's components: k0 .. k0 + 3 and k0 + 64 .. k0 + 67
       float l[8];
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        l[2 * c] = (k0 + 2 * c < a.K) ? a.cst[(size_t)g * a.K + k0 + 2 * c] - 0.5f * acc[s][c].x : -INFINITY;
-        l[2 * c + 1] = (k0 + 2 * c + 1 < a.K) ? a.cst[(size_t)g * a.K + k0 + 2 * c + 1] - 0.5f * acc[s][c].y : -INFINITY;
+        const int ka = k0 + (c >> 1) * 64 + (c & 1) * 2;
+        l[2 * c] = (ka < a.K) ? a.cst[(size_t)g * a.K + ka] - 0.5f * acc[s][c].x : -INFINITY;
+        l[2 * c + 1] = (ka + 1 < a.K) ? a.cst[(size_t)g * a.K + ka + 1] - 0.5f * acc[s][c].y : -INFINITY;
       }
       if (n < a.N) {
-        float* o = a.out + ((size_t)n * a.G + g) * a.K + k0;
-        if ((a.K & 3) == 0 && k0 + 8 <= a.K) {
-          *reinterpret_cast<float4*>(o) = make_float4(l[0], l[1], l[2], l[3]);
-          *reinterpret_cast<float4*>(o + 4) = make_float4(l[4], l[5], l[6], l[7]);
-        } else {
 #pragma unroll
-          for (int c = 0; c < 8; ++c)
-            if (k0 + c < a.K) o[c] = l[c];
+        for (int h = 0; h < 2; ++h) {
+          const int kb = k0 + 64 * h;
+          float* o = a.out + ((size_t)n * a.G + g) * a.K + kb;
+          if ((a.K & 3) == 0 && kb + 4 <= a.K) {
+            *reinterpret_cast<float4*>(o) = make_float4(l[4 * h], l[4 * h + 1], l[4 * h + 2], l[4 * h + 3]);
+          } else {
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              if (kb + c < a.K) o[c] = l[4 * h + c];
+          }
         }
       }
       if (MODE == 1) {
@@ -185,10 +198,42 @@ __global__ void __launch_bounds__(256) diag_estep_kernel(DiagArgs a) {
     const int rows = rem < DG_TN ? (int)rem : DG_TN;
     int KT = 1; while (KT < a.K && KT < 256) KT <<= 1;
     const int RT = 256 / KT, tx = tid % KT, ty = tid / KT;
+    const long long npad = (a.N + 31) / 32 * 32;           // the weight images cover whole 32-sample chunks
     for (int kb = 0; kb < a.K; kb += KT) {
       const int kk = kb + tx;
       float cs = 0.f;
-      if (kk < a.K) {
+      if (kk < a.K && a.rpack != nullptr) {
+        // thread = (component, group of 8 consecutive rows): p as before, plus one 16-byte store each to the hi and lo image
+        for (int rg = ty; rg < DG_TN / 8 && n0 + rg * 8 < npad; rg += RT) {
+          uint32_t hi[4], lo[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            float pv[2];
+#pragma unroll
+            for (int v = 0; v < 2; ++v) {
+              const int r = rg * 8 + 2 * u + v;
+              pv[v] = 0.f;
+              if (r < rows) {
+                const size_t ad = ((size_t)(n0 + r) * a.G + g) * a.K + kk;
+                pv[v] = expf(a.out[ad] - lz[r]);
+                a.out[ad] = pv[v];
+                cs += pv[v];
+              }
+            }
+            const float x0 = pv[0] * 16384.f, x1 = pv[1] * 16384.f;
+            const __half2 ah = __floats2half2_rn(x0, x1);
+            const float2 af = __half22float2(ah);
+            const __half2 bh = __floats2half2_rn(x0 - af.x, x1 - af.y);
+            hi[u] = *reinterpret_cast<const uint32_t*>(&ah);
+            lo[u] = *reinterpret_cast<const uint32_t*>(&bh);
+          }
+          const long long ch = (n0 + rg * 8) >> 3;
+          unsigned char* rec = a.rpack + ((size_t)(kk >> 7) * a.nsb + (size_t)(ch >> 1)) * 8192 + (size_t)(ch & 1) * 2048 +
+                               (size_t)(kk & 127) * 16;
+          *reinterpret_cast<uint4*>(rec) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<uint4*>(rec + 4096) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+      } else if (kk < a.K) {
         for (int r = ty; r < rows; r += RT) {
           const size_t ad = ((size_t)(n0 + r) * a.G + g) * a.K + kk;
           const float p = expf(a.out[ad] - lz[r]);
@@ -227,7 +272,7 @@ size_t diag_estep_workspace_bytes(long long N, int G, int K, int d, int mode) {
 
 int launch_diag_estep(const float* x, int d, long long N, int GX, const int* xg, const float* mu, const float* tau,
                       const float* cst, int G, int K, int mode, float* out, float* logZn, float* NA, float* logZ,
-                      void* ws, size_t ws_bytes, cudaStream_t st) {
+                      void* ws, size_t ws_bytes, cudaStream_t st, unsigned char* rpack) {
   if (d < 1 || d > VBMP_MAX_D || G < 1 || K < 1 || GX < 1 || N < 0 || (mode != 0 && mode != 1)) {
     set_error("diag_estep: bad shape N=%lld GX=%d G=%d K=%d d=%d mode=%d (d <= %d)", N, GX, G, K, d, mode, VBMP_MAX_D);
     return VBMP_ERR_SHAPE;
@@ -250,8 +295,9 @@ int launch_diag_estep(const float* x, int d, long long N, int GX, const int* xg,
   diag_transpose_kernel<<<(unsigned)((tot + 255) / 256 < 4096 ? (tot + 255) / 256 : 4096), 256, 0, st>>>(mu, tau, G, K, Kp, d, mut, taut);
   int rc = check_launch("diag_transpose");
   if (rc) return rc;
-  const int nbuf = d <= 64 ? 2 : 1;
-  DiagArgs a{x, N, GX, xg, mut, taut, cst, G, K, Kp, d, nbuf, out, logZn, mode == 1 ? NA_part : nullptr, mode == 1 ? logZ_part : nullptr};
+  const int nbuf = 1;                      // one resident parameter tile: two CTAs per SM up to d = 64 (see the header)
+  DiagArgs a{x, N, GX, xg, mut, taut, cst, G, K, Kp, d, nbuf, out, logZn, mode == 1 ? NA_part : nullptr,
+             mode == 1 ? logZ_part : nullptr, (mode == 1 && G == 1) ? rpack : nullptr, (N + 31) / 32 * 2};
   const size_t smem = ((size_t)d * (DG_TN + 4) + (size_t)2 * nbuf * d * DG_KT + DG_TN + 256) * sizeof(float);
   if (smem > 227 * 1024) { set_error("diag_estep: d=%d needs %zu bytes of shared memory", d, smem); return VBMP_ERR_UNSUPPORTED; }
   dim3 grid((unsigned)nb, (unsigned)G);

@@ -309,3 +309,11 @@ def test_isotropic_gmm_cfg2_shape_vs_fp64_oracle():
     assert_close(b, SEx, 1e-5, "SEx")
     assert float(((a.double() - SExx).abs() / SExx.abs().clamp_min(1e-30)).max()) < 2e-5
     assert_close(c, pw.sum(0), 1e-5, "N")
+    # the diagonal E-step handed the responsibilities over pre-split (K2 -> K3): same statistics, bit for bit, as from a copy
+    # of p, which the Gram call has to split itself
+    m.update_assignments(Xd)
+    assert _lib._rpack_key(Xd.device) in _lib._rpack_rec
+    s1 = [t.clone() for t in m.dist._stats(Xd.view(N, 1, d), m.p)]
+    s2 = m.dist._stats(Xd.view(N, 1, d), m.p.clone())
+    for u, v in zip(s1, s2):
+        assert torch.equal(u, v)
