@@ -485,6 +485,223 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant_
   if (warp == 1) { if (PAIR) tmem_dealloc2<512>(tm); else tmem_dealloc<512>(tm); }
 }
 
+
+// ---- K <= 64 components: operand roles swapped ----------------------------------------------------------------------
+// With K <= 64 the kernel above fills at most half of the 128 accumulator lanes (lanes = components): cfg3 (K = 64) spent
+// 13.3 of its 22.4 ms there, cfg4 (K = 32) a quarter of the lanes.  Here the PAIRS are the MMA's M dimension and the
+// components its N:   D[pair][k] += phi[pair][n] r[n][k]   with
+//   * A = phi^T in TENSOR MEMORY (lane = pair, two fp16 per column: one K-step of 16 samples = 8 columns), written by the
+//     worker thread that owns the pair — tcgen05.st straight from the registers it multiplied in, no shared-memory stage;
+//   * B = the pre-split weight images AS THEY ARE in the raw ring: [hi | lo][8-sample chunk][component][8 fp16] is
+//     the K-major core-matrix layout already (SBO = 128 B between 8-component groups, LBO = Kp x 16 B between the two
+//     8-sample chunks of a K-step); only the first Kp = K rounded up to 16 components of each piece are copied in;
+//   * a CTA owns GS_J = 2 blocks of 128 pairs (D1 and D2 of both: 4 Kp <= 256 columns; A stages: 4 x 2 x 32 = 256), so
+//     a weight stage is used by 12 MMAs with N = Kp.  MMA time per 32-sample chunk ~ 12 x 0.57 Kp cycles for 256 pairs
+//     against 6 x 0.57 x 224 for 224 pairs: 2.1x less at K = 64, 4.3x at K = 32.
+// Everything else — the sample image, the balanced sample splits, the two-level fp32 accumulation with round-to-nearest
+// folds every GU_FL chunks, the fixed-order fp64 reduce with the resolution check and the TF32 fallback — is shared.
+constexpr int GS_J = 2;              // pair blocks of 128 per CTA
+constexpr int GS_NSTG = 4;           // A (phi) stages in tensor memory
+constexpr int GS_KMAX = 64;
+
+struct GsSmem {
+  uint64_t rfull[GU_NR], rempty[GU_NR];
+  uint64_t bfull[GS_NSTG], bempty[GS_NSTG];
+  uint64_t dfull, dempty;
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(GU_THREADS, 1) gram_swap_kernel(GuArgs a, int Kp, int nblk) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  constexpr int SC = 32;
+  const int D = a.d0 + a.d1;
+  const int rawR = 8 * Kp * 16;                        // 2 K-steps x [hi c0 | hi c1 | lo c0 | lo c1] x Kp components x 16 B
+  const int rawB = (rawR + a.zrec + 127) / 128 * 128;
+  const int nr = a.nr;
+  uint8_t* raw = smem_raw;
+  GsSmem* S = reinterpret_cast<GsSmem*>(raw + (size_t)nr * rawB);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ntask = (nblk + GS_J - 1) / GS_J;          // pair-block groups
+  const int task = (int)blockIdx.x % ntask, split = (int)blockIdx.x / ntask;
+  const long long nb = (long long)split * a.S_per;
+  long long ne = nb + a.S_per; if (ne > a.N) ne = a.N;
+  const int nchunks = ne > nb ? (int)((ne - nb + SC - 1) / SC) : 0;
+  const int FL = a.FL;
+  const int jn = min(GS_J, nblk - task * GS_J);        // pair blocks this CTA really has
+
+  if (tid == 0) {
+    for (int s = 0; s < GU_NR; ++s) { mbar_init(&S->rfull[s], 1); mbar_init(&S->rempty[s], 9); }   // 8 worker warps + the MMAs
+    for (int s = 0; s < GS_NSTG; ++s) { mbar_init(&S->bfull[s], 8); mbar_init(&S->bempty[s], 1); }
+    mbar_init(&S->dfull, 1); mbar_init(&S->dempty, 8);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<512>(&S->tmem_base);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tm = S->tmem_base;
+  // TMEM columns: D1 of block j at 64 j, D2 at 128 + 64 j, A stage (st, j) at 256 + 32 (2 st + j): hi 16 columns, lo 16
+  constexpr int D2COL = 128, ACOL = 256;
+
+  if (warp == 0) {
+    // ================= producer: per chunk 8 slices of the weight images + the transposed sample chunk =================
+    const uint32_t bytes = (uint32_t)(rawR + a.zrec);
+    const uint32_t piece = (uint32_t)Kp * 16;
+    int s = 0;
+    uint32_t rph = 0;
+    for (int c = 0; c < nchunks; ++c, s = (s + 1 == nr ? 0 : s + 1), rph ^= (s == 0 ? 1u : 0u)) {
+      mbar_wait(&S->rempty[s], rph ^ 1);
+      if (elect_one()) {
+        const long long r0 = nb + (long long)c * SC;
+        uint8_t* dst = raw + (size_t)s * rawB;
+        mbar_arrive_expect_tx(&S->rfull[s], bytes);
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+          const uint8_t* rec = a.rp + (size_t)((r0 >> 4) + ks) * GU_RREC;          // component block 0: K <= 64
+#pragma unroll
+          for (int pc = 0; pc < 4; ++pc)
+            bulk_g2s(dst + (size_t)(ks * 4 + pc) * piece, rec + (size_t)pc * 2048, piece, &S->rfull[s]);
+        }
+        bulk_g2s(dst + rawR, a.zt + (size_t)(r0 >> 5) * a.zrec, (uint32_t)a.zrec, &S->rfull[s]);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    const uint32_t idesc = idesc_f16(128, Kp);
+    const uint32_t piece = (uint32_t)Kp * 16;
+    int s = 0, fc = 0, nflush = 0;
+    uint32_t rph = 0;
+    for (int c = 0; c < nchunks; ++c, s = (s + 1 == nr ? 0 : s + 1), rph ^= (s == 0 ? 1u : 0u)) {
+      const int st = c % GS_NSTG;
+      mbar_wait(&S->rfull[s], rph);                          // the weight slices are read by the tensor core itself
+      mbar_wait(&S->bfull[st], (c / GS_NSTG) & 1);
+      const bool first = (fc == 0);
+      if (first && c > 0) mbar_wait(&S->dempty, (nflush - 1) & 1);
+      tc_fence_after();
+      __syncwarp();
+      const bool flush = (++fc == FL) || (c == nchunks - 1);
+      if (elect_one()) {
+        const uint32_t sbase = smem_u32(raw + (size_t)s * rawB);
+        for (int j = 0; j < jn; ++j) {
+          const uint32_t dcol = tm + j * 64;
+          const uint32_t a_hi = tm + ACOL + (st * GS_J + j) * 32, a_lo = a_hi + 16;
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks) {
+            const uint64_t b_hi = smem_desc(sbase + (uint32_t)(ks * 4) * piece, piece, 128);
+            const uint64_t b_lo = smem_desc(sbase + (uint32_t)(ks * 4 + 2) * piece, piece, 128);
+            mma_f16_ts(dcol, a_lo + ks * 8, b_hi, idesc, !(first && ks == 0));
+            mma_f16_ts(dcol, a_hi + ks * 8, b_lo, idesc, 1);
+            mma_f16_ts(dcol, a_hi + ks * 8, b_hi, idesc, 1);
+          }
+        }
+        mma_commit(&S->bempty[st]);
+        mma_commit(&S->rempty[s]);
+        if (flush) mma_commit(&S->dfull);
+      }
+      __syncwarp();
+      if (flush) { fc = 0; ++nflush; }
+    }
+  } else {
+    // ================= workers: thread = pair (tensor-memory lane), two sets of 8 warps alternate chunks =================
+    const int set = (warp - 2) >> 3, w8 = (warp - 2) & 7;
+    const int j = w8 >> 2, q = warp & 3;                      // pair block, lane quarter (a warp reaches lanes 32 (warp % 4) ..)
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    const int prow = q * 32 + lane;
+    const int pg_ = (task * GS_J + j) * 128 + prow;           // pair column of the symmetric statistics
+    const bool jok = j < jn;
+    const bool pair_ok = jok && pg_ < a.P;
+    int pi = 0, pj = 0;
+    if (pair_ok) gu_pair_any(pg_, D, a.diag, &pi, &pj);
+    const uint8_t* bi = raw + rawR + (size_t)(pair_ok ? pi : D + 1) * (GU_ZS * 4);      // row D + 1 of the record: zeros
+    const uint8_t* bj = raw + rawR + (size_t)(pair_ok ? pj : D + 1) * (GU_ZS * 4);
+    const int fls = __ffs(FL) - 1;
+    int s = set;
+    uint32_t rph = 0;
+    for (int c = set; c < nchunks; c += 2, s += 2) {
+      if (s >= nr) { s -= nr; rph ^= 1u; }
+      const int st = c % GS_NSTG;
+      const int nflush = c >> fls;
+      mbar_wait(&S->rfull[s], rph);
+      mbar_wait(&S->bempty[st], ((c / GS_NSTG) & 1) ^ 1);
+      tc_fence_after();
+      if (jok) {
+        const uint8_t* zi = bi + (size_t)s * rawB;
+        const uint8_t* zj = bj + (size_t)s * rawB;
+        const uint32_t ad = tm + lane_base + ACOL + (st * GS_J + j) * 32;
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+          float4 av[4], bv[4];
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            av[v] = *reinterpret_cast<const float4*>(zi + ks * 64 + v * 16);
+            bv[v] = *reinterpret_cast<const float4*>(zj + ks * 64 + v * 16);
+          }
+          uint32_t hi[8], lo[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const float4 a4 = av[u >> 1], b4 = bv[u >> 1];
+            // factors carry exact power-of-two scales, so this is the reference's fp32 product times 2^(u_i + u_j)
+            const float2 x = (u & 1) ? __fmul2_rn(make_float2(a4.z, a4.w), make_float2(b4.z, b4.w))
+                                     : __fmul2_rn(make_float2(a4.x, a4.y), make_float2(b4.x, b4.y));
+            const __half2 ah = __floats2half2_rn(x.x, x.y);
+            const float2 af = __half22float2(ah);
+            const __half2 bh2 = __floats2half2_rn(x.x - af.x, x.y - af.y);
+            hi[u] = *reinterpret_cast<const uint32_t*>(&ah);
+            lo[u] = *reinterpret_cast<const uint32_t*>(&bh2);
+          }
+          tmem_st8(ad + ks * 8, hi);
+          tmem_st8(ad + 16 + ks * 8, lo);
+        }
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(&S->rempty[s]); mbar_arrive(&S->bfull[st]); }
+
+      const bool last = (c == nchunks - 1);
+      if (((c + 1) & (FL - 1)) == 0 || last) {
+        // ---- fold D1 into D2 (or, at the end, write D1 + D2 to this split's partial): thread = pair row, Kp columns
+        if (nflush > 0) mbar_wait(&S->dfull, (nflush - 1) & 1);
+        mbar_wait(&S->dfull, nflush & 1);
+        tc_fence_after();
+        const bool firstf = (nflush == 0);
+        if (jok) {
+          float* prw = a.part + ((size_t)split * a.PP + (size_t)(task * GS_J + j) * 128 + prow) * Kp;
+          for (int c0 = 0; c0 < Kp; c0 += 16) {
+            float v1[16], v2[16];
+            tmem_ld16(tm + lane_base + j * 64 + c0, v1);
+            if (!firstf) tmem_ld16(tm + lane_base + D2COL + j * 64 + c0, v2);
+            tmem_wait_ld();
+            if (!firstf) {
+#pragma unroll
+              for (int u = 0; u < 16; ++u) v1[u] += v2[u];
+            }
+            if (last) {
+#pragma unroll
+              for (int u = 0; u < 16; u += 4)
+                *reinterpret_cast<float4*>(prw + c0 + u) = make_float4(v1[u], v1[u + 1], v1[u + 2], v1[u + 3]);
+            } else {
+              tmem_st16(tm + lane_base + D2COL + j * 64 + c0, reinterpret_cast<const uint32_t*>(v1));
+            }
+          }
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&S->dempty);
+      }
+    }
+    if (nchunks == 0 && set == 0 && jok) {      // empty split: contribute zeros
+      float* prw = a.part + ((size_t)split * a.PP + (size_t)(task * GS_J + j) * 128 + prow) * Kp;
+      for (int c0 = 0; c0 < Kp; ++c0) prw[c0] = 0.f;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tm);
+}
+
 // gram[k][i][j] = gram[k][j][i] = sum_split part[split][k][pair(i,j)], fp64, fixed order.
 //   MODE 0: partials of the TF32 kernel (raw units), unconditional.
 //   MODE 1: partials of the fp16 kernel: they carry the factor 2^(14 + u_i + u_j).  The threads of the diagonal pairs
@@ -497,7 +714,8 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant_
 template <int MODE>
 __global__ void gram_pair_reduce_kernel(const float* __restrict__ part, int splits, int K, int Kp, int PP, int D1,
                                         const uint32_t* __restrict__ cmax, uint32_t* __restrict__ flag,
-                                        float* __restrict__ gram, int diag) {
+                                        float* __restrict__ gram, int diag, int swapKp = 0) {
+  // swapKp > 0: partials of gram_swap_kernel, part[split][pair (PP)][component (swapKp)]
   if (MODE == 2 && flag[0] == 0u) return;
   const int P = gu_npairs(D1 - 1, diag);
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -506,12 +724,14 @@ __global__ void gram_pair_reduce_kernel(const float* __restrict__ part, int spli
   int i, j;
   gu_pair_any(p, D1 - 1, diag, &i, &j);
   double acc = 0.0;
-  for (int s = 0; s < splits; ++s) acc += (double)part[((size_t)s * Kp + k) * PP + p];
+  if (swapKp > 0) { for (int s = 0; s < splits; ++s) acc += (double)part[((size_t)s * PP + p) * swapKp + k]; }
+  else { for (int s = 0; s < splits; ++s) acc += (double)part[((size_t)s * Kp + k) * PP + p]; }
   if (MODE == 1) {
     const int ui = gu_feat_exp(i == D1 - 1 ? 0x3f800000u : cmax[i]), uj = gu_feat_exp(j == D1 - 1 ? 0x3f800000u : cmax[j]);
     if (i == j && i < D1 - 1 && cmax[i] != 0u) {
       double accn = 0.0;                                   // the (1, 1) pair: 2^(14 + 12) sum_n r[n,k]
-      for (int s = 0; s < splits; ++s) accn += (double)part[((size_t)s * Kp + k) * PP + (P - 1)];
+      if (swapKp > 0) { for (int s = 0; s < splits; ++s) accn += (double)part[((size_t)s * PP + (P - 1)) * swapKp + k]; }
+      else { for (int s = 0; s < splits; ++s) accn += (double)part[((size_t)s * Kp + k) * PP + (P - 1)]; }
       const double nk = ldexp(accn, -(GU_RSH + 12));
       if (nk >= 4.0 && acc * 4096.0 < accn * 0.015625) atomicOr(flag, 2u);     // mean z'^2 < 2^-6 over >= 4 samples' weight
     }
