@@ -34,6 +34,7 @@
 //     2^-(14 + u_i + u_j) (exact).  Weights outside fp16 range after scaling (|r| > 3.99; responsibilities are <= 1)
 //     raise a device flag; the TF32 kernel, launched right behind, returns at once unless the flag is set, in which case
 //     it recomputes the partials — no host synchronisation, no silent loss of accuracy.
+#include <algorithm>
 #include <cstdlib>
 #include <cuda_fp16.h>
 #include "common.cuh"
@@ -897,6 +898,34 @@ static void gu_plan(long long N, int K, int D, int sms, GuArgs* g, int diag = 0)
 }
 
 static size_t gu_al(size_t x) { return (x + 255) / 256 * 256; }
+
+// ---- plan of the swapped-role kernel (K <= GS_KMAX): blocks of 128 pairs, GS_J per CTA, same split rule as gu_plan
+struct GsPlan { int Kp, nblk, ntask, splits, PP; long long S_per; };
+static bool gs_enabled() {
+  static const int on = [] { const char* e = getenv("VBMP_GRAM_SWAP"); return e ? atoi(e) : 1; }();
+  return on != 0;
+}
+static GsPlan gs_plan(long long N, int K, int D, int diag, int sms) {
+  GsPlan q{};
+  q.Kp = (K + 15) / 16 * 16;
+  const int P = gu_npairs(D, diag);
+  q.nblk = (P + 127) / 128;
+  q.ntask = (q.nblk + GS_J - 1) / GS_J;
+  q.PP = q.nblk * 128;
+  const long long cap = 32768;
+  long long rounds = ((long long)N * q.ntask + (long long)sms * cap - 1) / ((long long)sms * cap);
+  if (rounds < 1) rounds = 1;
+  long long sp = rounds * sms / q.ntask;
+  const long long maxsp = (N + 2047) / 2048;
+  if (sp > maxsp) sp = maxsp;
+  if (sp < 1) sp = 1;
+  long long per = (N + sp - 1) / sp;
+  per = (per + 31) / 32 * 32;
+  q.S_per = per;
+  q.splits = (int)((N + per - 1) / per);
+  if (q.splits < 1) q.splits = 1;
+  return q;
+}
 static long long gu_nsb(long long N) { return (N + 31) / 32 * 2; }
 static size_t gu_rp_bytes(long long N, int ncb) { return (size_t)ncb * (size_t)gu_nsb(N) * GU_RREC; }
 static size_t gu_zt_bytes(long long N, int D) { return (size_t)((N + 31) / 32) * gu_zrec(D) + 256; }
@@ -920,7 +949,13 @@ size_t gram_umma_workspace_bytes(long long N, int G, int K, int d0, int d1, int 
   if (!gram_umma_supported(N, 1, 1, G, K, Dp, d0, d1, true)) return 0;
   GuArgs g{};
   gu_plan(N, K, d0 + d1, gu_num_sms(), &g);   // same plan as the launch
-  return 512 + GU_HDR_WORDS * sizeof(uint32_t) + gu_al((size_t)g.splits * g.Kp * g.PP * sizeof(float)) +
+  size_t part = (size_t)g.splits * g.Kp * g.PP * sizeof(float);
+  if (K <= GS_KMAX) {                         // the swapped-role kernel's partials share the region
+    const GsPlan q = gs_plan(N, K, d0 + d1, 0, gu_num_sms());
+    const size_t ps = (size_t)q.splits * q.PP * q.Kp * sizeof(float);
+    if (ps > part) part = ps;
+  }
+  return 512 + GU_HDR_WORDS * sizeof(uint32_t) + gu_al(part) +
          (has_rpack ? 0 : gu_al(gu_rp_bytes(N, g.ncb))) + (has_zpack ? 0 : gram_zpack_bytes(N, d0 + d1));
 }
 
@@ -1030,7 +1065,14 @@ int launch_gram_umma(const GramArgs& a, float* gram, void* ws, size_t ws_bytes, 
   g.kcb = a.K < GU_CB ? a.K : GU_CB;
   g.FL = gu_fl();
   const bool f16 = gu_use_f16();
-  const size_t part_bytes = gu_al((size_t)g.splits * g.Kp * g.PP * sizeof(float));
+  const bool swap = f16 && a.K <= GS_KMAX && gs_enabled();
+  const GsPlan q = gs_plan(a.N, a.K, D, a.diag ? 1 : 0, gu_num_sms());
+  size_t part_raw = (size_t)g.splits * g.Kp * g.PP * sizeof(float);
+  if (a.K <= GS_KMAX) {
+    const GsPlan q0 = gs_plan(a.N, a.K, D, 0, gu_num_sms());        // as the workspace query sized it (diag or not)
+    part_raw = std::max(part_raw, (size_t)q0.splits * q0.PP * q0.Kp * sizeof(float));
+  }
+  const size_t part_bytes = gu_al(part_raw);
   const size_t need = gram_umma_workspace_bytes(a.N, a.G, a.K, a.d0, a.d1, a.Dp, a.rpack != nullptr, a.zpack != nullptr);
   if (ws_bytes < need) { set_error("gram_umma: workspace too small (%zu < %zu)", ws_bytes, need); return VBMP_ERR_WORKSPACE; }
   uint32_t* flag = (uint32_t*)gu_al((size_t)ws);
@@ -1077,12 +1119,30 @@ int launch_gram_umma(const GramArgs& a, float* gram, void* ws, size_t ws_bytes, 
   // 16 chunks of 32 samples per first-level block: a kind::f16 MMA accumulates 16 samples per step (TF32: 8), so the
   // truncation bias per block (-1.6e-6, tools/gram_bias.py) matches the TF32 variant's 256-sample blocks while the
   // fold, during which the tensor pipe idles, comes half as often
-  rc = gu_launch_main<true>(a, g, pair, st);
-  if (rc) return rc;
-  // reduce + resolution check; then the TF32 kernel and its reduce, both of which return at once unless the flag is up
-  gram_pair_reduce_kernel<1><<<rgrid, 256, 0, st>>>(g.part, g.splits, a.K, g.Kp, g.PP, D1, g.cmax, flag, gram, g.diag);
-  rc = check_launch("gram_pair_reduce");
-  if (rc) return rc;
+  if (swap) {
+    // K <= 64: pairs on the MMA's M dimension, components on N (gram_swap_kernel)
+    GuArgs gs = g;
+    gs.S_per = q.S_per; gs.splits = q.splits; gs.PP = q.PP;
+    const int rawB = (8 * q.Kp * 16 + g.zrec + 127) / 128 * 128;
+    int nr = (int)((227 * 1024 - sizeof(GsSmem) - 64) / rawB);
+    if (nr > GU_NR) nr = GU_NR;
+    gs.nr = nr;
+    const size_t smem = (size_t)nr * rawB + sizeof(GsSmem) + 64;
+    cudaFuncSetAttribute(gram_swap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    gram_swap_kernel<<<(unsigned)(q.ntask * q.splits), GU_THREADS, smem, st>>>(gs, q.Kp, q.nblk);
+    rc = check_launch("gram_swap");
+    if (rc) return rc;
+    gram_pair_reduce_kernel<1><<<rgrid, 256, 0, st>>>(g.part, q.splits, a.K, g.Kp, q.PP, D1, g.cmax, flag, gram, g.diag, q.Kp);
+    rc = check_launch("gram_pair_reduce");
+    if (rc) return rc;
+  } else {
+    rc = gu_launch_main<true>(a, g, pair, st);
+    if (rc) return rc;
+    // reduce + resolution check; then the TF32 kernel and its reduce, both of which return at once unless the flag is up
+    gram_pair_reduce_kernel<1><<<rgrid, 256, 0, st>>>(g.part, g.splits, a.K, g.Kp, g.PP, D1, g.cmax, flag, gram, g.diag);
+    rc = check_launch("gram_pair_reduce");
+    if (rc) return rc;
+  }
   rc = gu_launch_main<false>(a, g, pair, st);
   if (rc) return rc;
   gram_pair_reduce_kernel<2><<<rgrid, 256, 0, st>>>(g.part, g.splits, a.K, g.Kp, g.PP, D1, nullptr, flag, gram, g.diag);

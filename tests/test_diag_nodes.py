@@ -317,3 +317,22 @@ def test_isotropic_gmm_cfg2_shape_vs_fp64_oracle():
     s2 = m.dist._stats(Xd.view(N, 1, d), m.p.clone())
     for u, v in zip(s1, s2):
         assert torch.equal(u, v)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N,d,K", [(5000, 64, 32), (4100, 32, 64), (3000, 96, 16), (6000, 64, 132)])
+def test_diagonal_statistics_kernel(N, d, K):
+    """The Gram kernels' diagonal mode (vbmp_gram flags bit 1) on both tensor-core variants — components on the MMA's N
+    dimension for K <= 64, on M above — against an fp64 evaluation, per component."""
+    from pyvbmp_b200 import _lib
+    g = torch.Generator(device=DEV).manual_seed(N + K)
+    X = (torch.randn(N, d, generator=g, device=DEV) * 1.7 + 0.3).contiguous()
+    P = torch.softmax(2.0 * torch.randn(N, K, generator=g, device=DEV), -1).contiguous()
+    xg = torch.zeros(1, dtype=torch.int32, device=DEV)
+    G = _lib.gram(X.view(N, 1, d), None, N, 1, xg, P.view(N, 1, K), 1, xg, 1, K, _lib.pad_dim(d), diag=True).view(K, d + 1, d + 1)
+    Pd, Xd = P.double(), X.double()
+    SExx, SEx, Nk = Pd.t() @ Xd ** 2, Pd.t() @ Xd, Pd.sum(0)
+    assert float(((G[:, :d, :d].diagonal(dim1=-2, dim2=-1).double() - SExx).abs() / SExx).max()) < 1e-5
+    assert float((G[:, :d, d].double() - SEx).abs().max() / SEx.abs().max()) < 1e-5
+    assert float(((G[:, d, d].double() - Nk).abs() / Nk).max()) < 1e-5
+    assert torch.equal(G[:, :d, d], G[:, d, :d])
