@@ -130,12 +130,11 @@ class Wishart():
         return self.invU / (self.nu.view(self.nu.shape + (1, 1)))
 
     def ElogdetinvSigma(self):
-        """dists/Wishart.py:82-83 -> vbmp_wishart_elogdet (CUDA) — plain torch while the node is on the CPU."""
-        if self.nu.is_cuda:
-            C, d, g, ms = self._flat()
-            out = _lib.wishart_elogdet(g(self.nu, ms[:-2]), g(self.logdet_invU, ms[:-2]), C, d)
-            return out.view(ms[:-2])
-        return self.dim * math.log(2.0) - self.logdet_invU + self.log_mvdigamma(self.nu / 2.0)
+        """dists/Wishart.py:82-83 -> vbmp_wishart_elogdet (CUDA only, like every other kernel-backed method: a node on the
+        CPU raises VbmpError; the class install() binds keeps the reference's own code for CPU-resident nodes)."""
+        C, d, g, ms = self._flat()
+        out = _lib.wishart_elogdet(g(self.nu, ms[:-2]), g(self.logdet_invU, ms[:-2]), C, d)
+        return out.view(ms[:-2])
 
     def logdetEinvSigma(self):
         return -self.logdet_invU + self.nu.log()
