@@ -729,7 +729,10 @@ __global__ void gram_pair_reduce_kernel(const float* __restrict__ part, int spli
   else { for (int s = 0; s < splits; ++s) acc += (double)part[((size_t)s * Kp + k) * PP + p]; }
   if (MODE == 1) {
     const int ui = gu_feat_exp(i == D1 - 1 ? 0x3f800000u : cmax[i]), uj = gu_feat_exp(j == D1 - 1 ? 0x3f800000u : cmax[j]);
-    if (i == j && i < D1 - 1 && cmax[i] != 0u) {
+    // column i needs the check only if it holds a nonzero value below 2^-3 after scaling (column maximum in [2^6, 2^7))
+    const bool small_values = cmax[i < D1 - 1 ? i : 0] != 0u && cmax[VBMP_MAX_D + (i < D1 - 1 ? i : 0)] != 0u &&
+        ldexpf(__uint_as_float(0x7f800000u - cmax[VBMP_MAX_D + (i < D1 - 1 ? i : 0)]), ui) < 0.125f;
+    if (i == j && i < D1 - 1 && small_values) {
       double accn = 0.0;                                   // the (1, 1) pair: 2^(14 + 12) sum_n r[n,k]
       if (swapKp > 0) { for (int s = 0; s < splits; ++s) accn += (double)part[((size_t)s * PP + (P - 1)) * swapKp + k]; }
       else { for (int s = 0; s < splits; ++s) accn += (double)part[((size_t)s * Kp + k) * PP + (P - 1)]; }
@@ -746,8 +749,11 @@ __global__ void gram_pair_reduce_kernel(const float* __restrict__ part, int spli
 // column maxima of |z| (bit patterns, which order like the values for non-negative floats) into hdr[col0 + c]
 __global__ void __launch_bounds__(256) gram_colmax_kernel(const float* __restrict__ z, int d, long long N, int col0,
                                                           uint32_t* __restrict__ hdr) {
-  __shared__ uint32_t smax[VBMP_MAX_D];
-  if (threadIdx.x < VBMP_MAX_D) smax[threadIdx.x] = 0u;
+  // hdr[c] = bits of max |z_c|; hdr[VBMP_MAX_D + c] = 0x7f800000 - bits of the smallest NONZERO |z_c| (0 = none seen):
+  // the resolution check of the first reduce only applies to columns that hold nonzero values far below their maximum —
+  // exact zeros (one-hot / sparse / integer-coded features) are exact in any format and must not trigger the fallback
+  __shared__ uint32_t smax[VBMP_MAX_D], smin[VBMP_MAX_D];
+  if (threadIdx.x < VBMP_MAX_D) { smax[threadIdx.x] = 0u; smin[threadIdx.x] = 0u; }
   __syncthreads();
   const int d4 = d >> 2;                                         // d % 4 == 0
   const long long T = ((long long)gridDim.x * blockDim.x) / d4 * d4;   // threads that keep a fixed column group
@@ -755,17 +761,27 @@ __global__ void __launch_bounds__(256) gram_colmax_kernel(const float* __restric
   if (g < T) {
     const long long n4 = N * d4;
     float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f;
+    const float BIG = __uint_as_float(0x7f800000u);
+    float n0 = BIG, n1 = BIG, n2 = BIG, n3 = BIG;
     const float4* z4 = reinterpret_cast<const float4*>(z);
     for (long long e = g; e < n4; e += T) {
       const float4 v = __ldg(z4 + e);
-      m0 = fmaxf(m0, fabsf(v.x)); m1 = fmaxf(m1, fabsf(v.y)); m2 = fmaxf(m2, fabsf(v.z)); m3 = fmaxf(m3, fabsf(v.w));
+      const float a0 = fabsf(v.x), a1 = fabsf(v.y), a2 = fabsf(v.z), a3 = fabsf(v.w);
+      m0 = fmaxf(m0, a0); m1 = fmaxf(m1, a1); m2 = fmaxf(m2, a2); m3 = fmaxf(m3, a3);
+      n0 = a0 > 0.f ? fminf(n0, a0) : n0; n1 = a1 > 0.f ? fminf(n1, a1) : n1;
+      n2 = a2 > 0.f ? fminf(n2, a2) : n2; n3 = a3 > 0.f ? fminf(n3, a3) : n3;
     }
     const int c = (int)(g % d4) * 4;
     atomicMax(&smax[c], __float_as_uint(m0)); atomicMax(&smax[c + 1], __float_as_uint(m1));
     atomicMax(&smax[c + 2], __float_as_uint(m2)); atomicMax(&smax[c + 3], __float_as_uint(m3));
+    atomicMax(&smin[c], 0x7f800000u - __float_as_uint(n0)); atomicMax(&smin[c + 1], 0x7f800000u - __float_as_uint(n1));
+    atomicMax(&smin[c + 2], 0x7f800000u - __float_as_uint(n2)); atomicMax(&smin[c + 3], 0x7f800000u - __float_as_uint(n3));
   }
   __syncthreads();
-  if (threadIdx.x < d && smax[threadIdx.x] != 0u) atomicMax(&hdr[col0 + threadIdx.x], smax[threadIdx.x]);
+  if (threadIdx.x < d && smax[threadIdx.x] != 0u) {
+    atomicMax(&hdr[col0 + threadIdx.x], smax[threadIdx.x]);
+    atomicMax(&hdr[VBMP_MAX_D + col0 + threadIdx.x], smin[threadIdx.x]);
+  }
 }
 
 // fp16 variant pre-pass: r' = r 2^14 = a + b (a = rn_fp16(r'), b = rn_fp16(r' - a)) written once as the TMEM images the

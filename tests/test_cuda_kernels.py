@@ -168,7 +168,7 @@ def _per_component_relerr(G, Gref, min_mass=4.0):
     return float(fro[keep].max()), float(dg[keep].max())
 
 
-@pytest.mark.parametrize("case", ["outlier", "tight_cluster", "plain"])
+@pytest.mark.parametrize("case", ["outlier", "tight_cluster", "one_hot", "plain"])
 def test_gram_data_outside_the_fp16_window(case):
     """One feature scale per COLUMN cannot cover every data set in fp16's window: a single huge outlier in a column pushes
     every ordinary sample ~20 binades under that column's scale, and a tight cluster inside a wide data range sits far below
@@ -187,6 +187,10 @@ def test_gram_data_outside_the_fp16_window(case):
     elif case == "tight_cluster":
         own = lab == 3
         z[own] = 1e-5 * (1.0 + 0.1 * torch.randn(int(own.sum()), d0, generator=g, device=dev))    # values ~1e-5 of the range
+    elif case == "one_hot":
+        # exact zeros are exact in any format: columns without small NONZERO values are exempt from the check (a component
+        # that never sees feature f has mean z_f^2 = 0, which must not be mistaken for "below the resolvable floor")
+        z[:, :K] = torch.nn.functional.one_hot(lab, K).float()
     P = torch.full((N, K), 1e-4, device=dev)
     P[torch.arange(N, device=dev), lab] = 1.0 - 1e-4 * (K - 1)
     P = P.contiguous()

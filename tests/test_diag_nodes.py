@@ -336,3 +336,55 @@ def test_diagonal_statistics_kernel(N, d, K):
     assert float((G[:, :d, d].double() - SEx).abs().max() / SEx.abs().max()) < 1e-5
     assert float(((G[:, d, d].double() - Nk).abs() / Nk).max()) < 1e-5
     assert torch.equal(G[:, :d, d], G[:, d, :d])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N,d,K,G", [(777, 5, 6, 1), (1300, 19, 3, 4), (4099, 64, 260, 1), (130, 128, 17, 1)])
+def test_diag_estep_kernel_general_shapes(N, d, K, G):
+    """vbmp_diag_estep on ragged shapes (N not a multiple of the 128-row tile, K not a multiple of 4 / 128, replica groups
+    with their own data columns, d = 128 with a single resident parameter tile) against an fp64 evaluation."""
+    from pyvbmp_b200 import _lib
+    g = torch.Generator(device=DEV).manual_seed(N + d)
+    X = (1.5 * torch.randn(N, G, d, generator=g, device=DEV) + 0.2).contiguous()
+    mu = torch.randn(G * K, d, generator=g, device=DEV)
+    tau = (0.2 + torch.rand(G * K, d, generator=g, device=DEV)).contiguous()
+    cst = torch.randn(G * K, generator=g, device=DEV)
+    xg = torch.arange(G, dtype=torch.int32, device=DEV)
+    L = cst.double().view(1, G, K) - 0.5 * ((X.double().unsqueeze(2) - mu.double().view(1, G, K, d)) ** 2
+                                            * tau.double().view(1, G, K, d)).sum(-1)
+    lg = _lib.diag_estep(X, N, G, xg, mu, tau, cst, G, K, d, 0)
+    scale = float(L.abs().max())
+    assert float((lg.double() - L).abs().max()) <= 2e-6 * scale
+    p, lzn, NA, lZ = _lib.diag_estep(X, N, G, xg, mu, tau, cst, G, K, d, 1)
+    lz = torch.logsumexp(L, -1)
+    P = (L - lz.unsqueeze(-1)).exp()
+    assert float((lzn.double() - lz).abs().max()) <= 2e-6 * scale
+    assert float((p.double() - P).abs().max()) <= 1e-4
+    assert float(((NA.double() - P.sum(0)).abs() / P.sum(0).clamp_min(1.0)).max()) <= 1e-4
+    assert float(((lZ.double() - lz.sum(0)).abs() / lz.sum(0).abs().clamp_min(1.0)).max()) <= 1e-5
+
+
+@pytest.mark.gpu
+def test_normal_gamma_mixture_with_replica_batch_dim_vs_oracle():
+    """Mixture over NormalGamma(event=(d,), batch=(G, K)) with one data column per replica (the layout of
+    tests/test_dists.py:261-276 with diagonal components): E-step, statistics and update against the fp64 oracle."""
+    N, G, K, d = 900, 3, 5, 4
+    g = torch.Generator().manual_seed(8)
+    X = torch.randn(N, G, d, generator=g) * 1.2 + torch.randn(G, d, generator=g)
+    torch.manual_seed(4)
+    m = V.Mixture(V.NormalGamma((d,), (G, K), scale=0.6), (K,))
+    torch.manual_seed(4)
+    ref = O.mixture_new(O.ng_new((d,), (G, K), scale=0.6), (K,))
+    assert torch.equal(m.dist.mu, ref["dist"]["mu"]) and torch.equal(m.pi.alpha, ref["pi"]["alpha"])
+    O.to_dtype(ref, torch.float64)
+    m.to(DEV)
+    Xd = X.to(DEV)
+    for it in range(3):
+        m.update(Xd, 1)
+        tr = O.mixture_update(ref, X.double(), 1)
+        assert m.p.shape == ref["p"].shape and m.NA.shape == ref["NA"].shape and m.logZ.shape == ref["logZ"].shape
+        assert_close(m.ELBO_last, tr[0], PARITY, f"ELBO it{it}")
+        assert_maxabs(m.p.cpu().double(), ref["p"], 2e-4, f"p it{it}")
+        flat = O.flatten_state(ref)
+        for k in NG_STATE:
+            assert_close(_get(m, k), flat[k], 3e-4 if it == 0 else PARITY, f"{k} it{it}")
