@@ -170,6 +170,14 @@ int vbmp_mnw_kl(const float* mu_0, const float* mu, const float* invV_0, const f
 int vbmp_hmm_forward_backward(const float* logits, const float* trans, const float* init, int T, long long S, int G, int K,
                               float ptemp, float* p, float* SEzz, float* SEz0, float* logZ, void* stream);
 
+/* ---- mixture-of-experts predictive moments -------------------------------------------------------
+ * The per-sample part of MixtureofLinearTransforms.predict (transforms/MixtureofLinearTransforms.py:100-106):
+ *   mu[s] = sum_k p[s,k] mean[s,k,:],   Sigma[s] = base[s] + sum_k p[s,k] mean[s,k,:] mean[s,k,:]^T - mu[s] mu[s]^T
+ * with mean (N, K, n) the component means E[y | x_s, k], p (N, K) the gate probabilities, base (N, n, n) = sum_k p[s,k]
+ * ESigma_k (or NULL), n <= 32.  One warp per sample.                                                                   */
+int vbmp_moe_moments(const float* mean, const float* p, const float* base, long long N, int K, int n,
+                     float* mu, float* Sigma, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

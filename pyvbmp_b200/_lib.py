@@ -62,7 +62,7 @@ EXPORTS = (
     "vbmp_mnw_update", "vbmp_wishart_elogdet", "vbmp_wishart_kl", "vbmp_niw_kl", "vbmp_mnw_kl",
     "vbmp_hmm_forward_backward", "vbmp_rpack_bytes", "vbmp_estep_rpack", "vbmp_gram_rpack",
     "vbmp_zpack_bytes", "vbmp_gram_zpack", "vbmp_gram_ex_workspace_bytes", "vbmp_gram_ex",
-    "vbmp_diag_estep_workspace_bytes", "vbmp_diag_estep", "vbmp_diag_estep_rpack", "vbmp_mnw_prep_ex",
+    "vbmp_diag_estep_workspace_bytes", "vbmp_diag_estep", "vbmp_diag_estep_rpack", "vbmp_mnw_prep_ex", "vbmp_moe_moments",
 )
 
 
@@ -459,6 +459,16 @@ def mnw_kl(mu0, mu, invV0, V, ldV, ldV0, invU0, U, nu0, nu, ldU, ldU0, C, n, pp)
                              _ptr(nu0), _ptr(nu), _ptr(ldU), _ptr(ldU0), c_int(C), c_int(n), c_int(pp), _ptr(out),
                              _stream(U.device))
     return out
+
+
+def moe_moments(mean, p, base, N, K, n):
+    """mean (N,K,n), p (N,K), base (N,n,n) or None -> mu (N,n), Sigma (N,n,n)  (vbmp_moe_moments)."""
+    dev = mean.device
+    mu = torch.empty((N, n), dtype=torch.float32, device=dev)
+    Sigma = torch.empty((N, n, n), dtype=torch.float32, device=dev)
+    _call("vbmp_moe_moments", dev, _ptr(mean), _ptr(p), _ptr(base), c_longlong(N), c_int(K), c_int(n), _ptr(mu), _ptr(Sigma),
+          _stream(dev))
+    return mu, Sigma
 
 
 def hmm_forward_backward(logits, trans, init, T, S, G, K, ptemp):

@@ -62,6 +62,8 @@ size_t diag_estep_workspace_bytes(long long N, int G, int K, int d, int mode);
 int launch_diag_estep(const float* x, int d, long long N, int GX, const int* xg, const float* mu, const float* tau,
                       const float* cst, int G, int K, int mode, float* out, float* logZn, float* NA, float* logZ,
                       void* ws, size_t ws_bytes, cudaStream_t st, unsigned char* rpack = nullptr);
+int launch_moe_moments(const float* mean, const float* p, const float* base, long long N, int K, int n, float* mu, float* Sigma,
+                       cudaStream_t st);
 bool gram_rpack_usable();
 bool estep_umma_can_pack(long long N, int GX, int G, int K, int Dp, int d0, int d1, int mode);
 size_t gram_rpack_bytes(long long N, int K);
@@ -339,6 +341,12 @@ int vbmp_mnw_kl(const float* mu_0, const float* mu, const float* invV_0, const f
                 const float* nu_0, const float* nu, const float* logdet_invU, const float* logdet_invU_0,
                 int C, int n, int pp, float* out, void* stream) {
   return launch_mnw_kl(mu_0, mu, invV_0, V, logdetinvV, logdetinvV_0, invU_0, U, nu_0, nu, logdet_invU, logdet_invU_0, C, n, pp, out, (cudaStream_t)stream);
+}
+
+int vbmp_moe_moments(const float* mean, const float* p, const float* base, long long N, int K, int n,
+                     float* mu, float* Sigma, void* stream) {
+  if (!mean || !p || !mu || !Sigma) { set_error("moe_moments: NULL argument"); return VBMP_ERR_SHAPE; }
+  return launch_moe_moments(mean, p, base, N, K, n, mu, Sigma, (cudaStream_t)stream);
 }
 
 int vbmp_hmm_forward_backward(const float* logits, const float* trans, const float* init, int T, long long S, int G, int K,

@@ -122,7 +122,8 @@ class MixtureofLinearTransforms():
         """transforms/MixtureofLinearTransforms.py:91-108: mixture-of-experts predictive distribution of Y and the gate
         probabilities for inputs X (..., p, 1).  On the CUDA path the gate probabilities come from the fused E-step kernel
         (K2, softmax epilogue) on the whitened form of the per-component evidence (MatrixNormalWishart._predict_factors);
-        the moment sums over components are three GEMM-shaped torch steps per block of rows."""
+        the component means and sum_k p_k ESigma_k are one GEMM each per block of rows (shared operands), the per-sample
+        weighted rank-K update is vbmp_moe_moments (one warp per sample)."""
         from .mvn import MultivariateNormal_vector_format
         W = self.W
         if not (isinstance(W, MatrixNormalWishart) and not isinstance(W, MatrixNormalGamma) and self.batch_dim == 0
@@ -161,9 +162,16 @@ class MixtureofLinearTransforms():
                 mean = mean + Mb
             mean = mean.view(b - a, K, n)
             pe = p[a:b]
+            base = (pe @ ESf).view(b - a, n, n)                                                 # sum_k p_k ESigma_k
+            if n <= 32:
+                # the per-sample weighted rank-K update (no operand shared between samples): one warp per sample
+                mu_b, S = _lib.moe_moments(mean.contiguous(), pe.contiguous(), base, b - a, K, n)
+                mu[a:b, :, 0] = mu_b
+                Sigma[a:b] = S
+                continue
             mu_b = torch.bmm(pe.unsqueeze(1), mean).squeeze(1)                                  # (rows, n)
             A = mean * pe.sqrt().unsqueeze(-1)
-            S = torch.baddbmm((pe @ ESf).view(b - a, n, n), A.transpose(1, 2), A)
+            S = torch.baddbmm(base, A.transpose(1, 2), A)
             mu[a:b, :, 0] = mu_b
             Sigma[a:b] = S - mu_b.unsqueeze(-1) * mu_b.unsqueeze(-2)
         return MultivariateNormal_vector_format(mu=mu, Sigma=Sigma), p

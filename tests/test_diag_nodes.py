@@ -364,27 +364,6 @@ def test_diag_estep_kernel_general_shapes(N, d, K, G):
     assert float(((lZ.double() - lz.sum(0)).abs() / lz.sum(0).abs().clamp_min(1.0)).max()) <= 1e-5
 
 
-@pytest.mark.gpu
-def test_normal_gamma_mixture_with_replica_batch_dim_vs_oracle():
-    """Mixture over NormalGamma(event=(d,), batch=(G, K)) with one data column per replica (the layout of
-    tests/test_dists.py:261-276 with diagonal components): E-step, statistics and update against the fp64 oracle."""
-    N, G, K, d = 900, 3, 5, 4
-    g = torch.Generator().manual_seed(8)
-    X = torch.randn(N, G, d, generator=g) * 1.2 + torch.randn(G, d, generator=g)
-    torch.manual_seed(4)
-    m = V.Mixture(V.NormalGamma((d,), (G, K), scale=0.6), (K,))
-    torch.manual_seed(4)
-    ref = O.mixture_new(O.ng_new((d,), (G, K), scale=0.6), (K,))
-    assert torch.equal(m.dist.mu, ref["dist"]["mu"]) and torch.equal(m.pi.alpha, ref["pi"]["alpha"])
-    O.to_dtype(ref, torch.float64)
-    m.to(DEV)
-    Xd = X.to(DEV)
-    for it in range(3):
-        m.update(Xd, 1)
-        tr = O.mixture_update(ref, X.double(), 1)
-        assert m.p.shape == ref["p"].shape and m.NA.shape == ref["NA"].shape and m.logZ.shape == ref["logZ"].shape
-        assert_close(m.ELBO_last, tr[0], PARITY, f"ELBO it{it}")
-        assert_maxabs(m.p.cpu().double(), ref["p"], 2e-4, f"p it{it}")
-        flat = O.flatten_state(ref)
-        for k in NG_STATE:
-            assert_close(_get(m, k), flat[k], 3e-4 if it == 0 else PARITY, f"{k} it{it}")
+# (No replica-batch Mixture test for NormalGamma: dists/NormalGamma.py:88-94 adds `self.gamma.KLqprior().sum(-1)` — the Gamma
+# KL summed over the LAST BATCH dim as well — to a per-component vector, which broadcasts only for batch_shape = (K,); with
+# batch (G, K) the reference itself raises.  The mirror and the oracle reproduce that expression, quirk included.)
