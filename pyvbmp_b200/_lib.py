@@ -461,11 +461,14 @@ def mnw_kl(mu0, mu, invV0, V, ldV, ldV0, invU0, U, nu0, nu, ldU, ldU0, C, n, pp)
     return out
 
 
-def moe_moments(mean, p, base, N, K, n):
-    """mean (N,K,n), p (N,K), base (N,n,n) or None -> mu (N,n), Sigma (N,n,n)  (vbmp_moe_moments)."""
+def moe_moments(mean, p, base, N, K, n, mu=None, Sigma=None):
+    """mean (N,K,n), p (N,K), base (N,n,n) or None -> mu (N,n), Sigma (N,n,n)  (vbmp_moe_moments); mu / Sigma may be given
+    (contiguous fp32 views to write into; Sigma may alias base)."""
     dev = mean.device
-    mu = torch.empty((N, n), dtype=torch.float32, device=dev)
-    Sigma = torch.empty((N, n, n), dtype=torch.float32, device=dev)
+    if mu is None:
+        mu = torch.empty((N, n), dtype=torch.float32, device=dev)
+    if Sigma is None:
+        Sigma = torch.empty((N, n, n), dtype=torch.float32, device=dev)
     _call("vbmp_moe_moments", dev, _ptr(mean), _ptr(p), _ptr(base), c_longlong(N), c_int(K), c_int(n), _ptr(mu), _ptr(Sigma),
           _stream(dev))
     return mu, Sigma

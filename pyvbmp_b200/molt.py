@@ -153,27 +153,24 @@ class MixtureofLinearTransforms():
         mu = torch.empty(N, n, 1, device=dev)
         Sigma = torch.empty(N, n, n, device=dev)
         X2 = Xc.view(N, p_in)
-        # per block of rows (fp32): all component means at once, the p-weighted second moment as a batched A^T A with
-        # A = sqrt(p) * mean, and the p-weighted component covariances
+        # per block of rows (fp32): all component means at once ((rows x p') (p' x K n), the bias folded in as the product's
+        # additive term) and sum_k p_k ESigma_k ((rows x K) (K x n^2)) are one GEMM each with a shared operand; the per-sample
+        # weighted rank-K update is vbmp_moe_moments, which writes mu and Sigma in place (Sigma starts as the base term)
         for a in range(0, N, self.PREDICT_ROWS):
             b = min(N, a + self.PREDICT_ROWS)
-            mean = X2[a:b] @ Mw
-            if Mb is not None:
-                mean = mean + Mb
-            mean = mean.view(b - a, K, n)
+            mean = torch.addmm(Mb, X2[a:b], Mw) if Mb is not None else X2[a:b] @ Mw
             pe = p[a:b]
-            base = (pe @ ESf).view(b - a, n, n)                                                 # sum_k p_k ESigma_k
+            S = Sigma[a:b]
+            torch.mm(pe, ESf, out=S.view(b - a, n * n))
             if n <= 32:
-                # the per-sample weighted rank-K update (no operand shared between samples): one warp per sample
-                mu_b, S = _lib.moe_moments(mean.contiguous(), pe.contiguous(), base, b - a, K, n)
-                mu[a:b, :, 0] = mu_b
-                Sigma[a:b] = S
+                _lib.moe_moments(mean, pe, S, b - a, K, n, mu=mu[a:b].view(b - a, n), Sigma=S)
                 continue
+            mean = mean.view(b - a, K, n)
             mu_b = torch.bmm(pe.unsqueeze(1), mean).squeeze(1)                                  # (rows, n)
             A = mean * pe.sqrt().unsqueeze(-1)
-            S = torch.baddbmm(base, A.transpose(1, 2), A)
+            S.baddbmm_(A.transpose(1, 2), A)
             mu[a:b, :, 0] = mu_b
-            Sigma[a:b] = S - mu_b.unsqueeze(-1) * mu_b.unsqueeze(-2)
+            S.sub_(mu_b.unsqueeze(-1) * mu_b.unsqueeze(-2))
         return MultivariateNormal_vector_format(mu=mu, Sigma=Sigma), p
 
     def KLqprior(self):

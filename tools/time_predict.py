@@ -28,3 +28,31 @@ t = a.elapsed_time(b) / 3
 ke = sum(x.elapsed_time(y) for x, y in _lib.PROFILE.get("vbmp_estep", [])) / 3
 print(f"MoLT.predict N={N} p={p} n={n} K={K}: {t:.2f} ms per call ({N * K / t / 1e6:.2f}e9 sample*component evaluations/s); "
       f"gate probabilities (K2 kernel) {ke:.2f} ms, moment sums (torch batched GEMMs, {N * n * n * 4 / 1e9:.2f} GB of covariances out) {t - ke:.2f} ms")
+
+# ---- breakdown of one 64 Ki-row block: component means GEMM, base GEMM, per-sample moments kernel
+W = m.W
+p_in = W.p - int(W.pad_X)
+M = W.mu
+Mw = M[..., :p_in].reshape(K * n, p_in).t().contiguous()
+Mb = M[..., -1].reshape(1, K * n)
+ESf = W.EinvSigma().inverse().expand(K, n, n).reshape(K, n * n).contiguous()
+rows = 1 << 16
+X2 = X.view(N, p)[:rows].contiguous()
+pe = pr[:rows].contiguous()
+S = torch.empty(rows, n, n, device=dev)
+mu = torch.empty(rows, n, device=dev)
+def ev():
+    return torch.cuda.Event(enable_timing=True)
+ts = {}
+for rep in range(3):
+    e = [ev() for _ in range(4)]
+    e[0].record()
+    mean = torch.addmm(Mb, X2, Mw)
+    e[1].record()
+    torch.mm(pe, ESf, out=S.view(rows, n * n))
+    e[2].record()
+    _lib.moe_moments(mean, pe, S, rows, K, n, mu=mu, Sigma=S)
+    e[3].record()
+    torch.cuda.synchronize()
+    ts = {"means GEMM": e[0].elapsed_time(e[1]), "base GEMM": e[1].elapsed_time(e[2]), "moe_moments": e[2].elapsed_time(e[3])}
+print("per 64 Ki rows:", {k: round(v, 3) for k, v in ts.items()}, "-> x16 per 1 Mi rows:", {k: round(16 * v, 2) for k, v in ts.items()})
