@@ -7,10 +7,12 @@
 // The component means of a block of samples are ONE GEMM with a shared operand ((rows x p') (p' x K n)) and so is base
 // ((rows x K) (K x n^2)); what is left is a weighted rank-K update PER SAMPLE — (n x K) (K x n) with no operand shared
 // between samples — which as a batch of tiny GEMMs was 60 % of predict's time (35 ms per 1 Mi inputs at n = p = 32, K = 64).
-// Here one warp owns one sample: lane a keeps row a of Sigma_s in registers (n <= 32), walks the components, and reads the
-// component mean once as its own element (coalesced) and once as a row broadcast through L1 (eight 16-byte loads that
-// every lane issues to the same address): 2 K n^2 flops against 4 K n bytes per sample, HBM-bound on the means
-// (8.6 GB per 1 Mi samples at K n = 2048) and on the n^2 outputs.
+// Here one warp owns one sample and its 32 lanes tile Sigma_s in 4 x 8 register blocks (lane = (row group of 4, column
+// group of 8), n <= 32, n % 4 == 0): per component a lane loads the 4 + 8 mean entries of its block's rows and columns —
+// 48 bytes, 1.5 KB per warp — and does 32 FMAs.  What bounds such a kernel is the load path's delivery rate into registers
+// (128 B per cycle per SM), not the flops: the first version kept a full ROW of Sigma_s per lane and therefore every lane
+// read the whole mean vector of every component (132 bytes per lane, 4.2 KB per warp and component — 19.9 ms per 1 Mi
+// samples at n = 32, K = 64, measured).  Other n take that simpler row-per-lane kernel.
 #include "common.cuh"
 
 namespace vbmp {
@@ -64,6 +66,64 @@ __global__ void __launch_bounds__(256) moe_moments_kernel(const float* __restric
   }
 }
 
+// lane = (rg, cg): rows 4 rg .. 4 rg + 3 (rg = lane / 4), columns 8 cg .. 8 cg + 7 (cg = lane % 4) of the 32 x 32 frame
+__global__ void __launch_bounds__(256) moe_moments_tile_kernel(const float* __restrict__ mean, const float* __restrict__ p,
+                                                               const float* __restrict__ base, long long N, int K, int n,
+                                                               float* __restrict__ mu, float* __restrict__ Sigma) {
+  const int lane = threadIdx.x & 31;
+  const long long w0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int r0 = (lane >> 2) * 4, c0 = (lane & 3) * 8;
+  const bool rok = r0 < n, cok0 = c0 < n, cok1 = c0 + 4 < n;         // n % 4 == 0: a float4 is all inside or all outside
+  for (long long s = w0; s < N; s += nw) {
+    const float* ms = mean + (size_t)s * K * n;
+    const float* ps = p + (size_t)s * K;
+    float acc[4][8];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[a][j] = 0.f;
+    float4 mur = make_float4(0.f, 0.f, 0.f, 0.f), muc0 = mur, muc1 = mur;
+#pragma unroll 2
+    for (int k = 0; k < K; ++k) {
+      const float pk = __ldg(ps + k);
+      const float* mk = ms + (size_t)k * n;
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 mr = rok ? __ldg(reinterpret_cast<const float4*>(mk + r0)) : z;
+      const float4 ma = cok0 ? __ldg(reinterpret_cast<const float4*>(mk + c0)) : z;
+      const float4 mb = cok1 ? __ldg(reinterpret_cast<const float4*>(mk + c0 + 4)) : z;
+      const float w[4] = {pk * mr.x, pk * mr.y, pk * mr.z, pk * mr.w};
+      const float c[8] = {ma.x, ma.y, ma.z, ma.w, mb.x, mb.y, mb.z, mb.w};
+      mur.x += w[0]; mur.y += w[1]; mur.z += w[2]; mur.w += w[3];
+      muc0.x = fmaf(pk, ma.x, muc0.x); muc0.y = fmaf(pk, ma.y, muc0.y); muc0.z = fmaf(pk, ma.z, muc0.z); muc0.w = fmaf(pk, ma.w, muc0.w);
+      muc1.x = fmaf(pk, mb.x, muc1.x); muc1.y = fmaf(pk, mb.y, muc1.y); muc1.z = fmaf(pk, mb.z, muc1.z); muc1.w = fmaf(pk, mb.w, muc1.w);
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[a][j] = fmaf(w[a], c[j], acc[a][j]);
+    }
+    if (rok && (lane & 3) == 0) *reinterpret_cast<float4*>(mu + (size_t)s * n + r0) = mur;
+    const float mrow[4] = {mur.x, mur.y, mur.z, mur.w};
+    const float mcol[8] = {muc0.x, muc0.y, muc0.z, muc0.w, muc1.x, muc1.y, muc1.z, muc1.w};
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      if (!rok) break;
+      float* So = Sigma + ((size_t)s * n + r0 + a) * n + c0;
+      const float* Bo = base ? base + ((size_t)s * n + r0 + a) * n + c0 : nullptr;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (!(h ? cok1 : cok0)) continue;
+        float4 b4 = Bo ? *reinterpret_cast<const float4*>(Bo + 4 * h) : make_float4(0.f, 0.f, 0.f, 0.f);
+        b4.x += acc[a][4 * h] - mrow[a] * mcol[4 * h];
+        b4.y += acc[a][4 * h + 1] - mrow[a] * mcol[4 * h + 1];
+        b4.z += acc[a][4 * h + 2] - mrow[a] * mcol[4 * h + 2];
+        b4.w += acc[a][4 * h + 3] - mrow[a] * mcol[4 * h + 3];
+        *reinterpret_cast<float4*>(So + 4 * h) = b4;
+      }
+    }
+  }
+}
+
 int launch_moe_moments(const float* mean, const float* p, const float* base, long long N, int K, int n, float* mu, float* Sigma,
                        cudaStream_t st) {
   if (N < 0 || K < 1 || n < 1 || n > 32) { set_error("moe_moments: bad shape N=%lld K=%d n=%d (n <= 32)", N, K, n); return VBMP_ERR_SHAPE; }
@@ -72,6 +132,11 @@ int launch_moe_moments(const float* mean, const float* p, const float* base, lon
   long long blocks = (N + 7) / 8;
   const long long cap = (long long)num_sms() * 16;
   if (blocks > cap) blocks = cap;
+  const bool aligned = ((size_t)mean % 16 == 0) && ((size_t)Sigma % 16 == 0) && ((size_t)mu % 16 == 0) && (!base || (size_t)base % 16 == 0);
+  if ((n & 3) == 0 && aligned) {
+    moe_moments_tile_kernel<<<(unsigned)blocks, 256, 0, st>>>(mean, p, base, N, K, n, mu, Sigma);
+    return check_launch("moe_moments_tile");
+  }
   switch (np) {
 #define MM_CASE(V) case V: moe_moments_kernel<V><<<(unsigned)blocks, 256, 0, st>>>(mean, p, base, N, K, n, mu, Sigma); break;
     MM_CASE(4) MM_CASE(8) MM_CASE(12) MM_CASE(16) MM_CASE(20) MM_CASE(24) MM_CASE(28) MM_CASE(32)

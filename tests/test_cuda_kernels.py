@@ -349,3 +349,29 @@ def test_misaligned_views_are_rebased():
         outs.append(m)
     assert torch.equal(outs[0].p, outs[1].p)
     assert float(outs[0].ELBO_last) == float(outs[1].ELBO_last)
+
+
+@pytest.mark.parametrize("N,K,n,with_base", [(5000, 64, 32, True), (3001, 8, 16, True), (777, 5, 12, False), (1025, 20, 7, True),
+                                              (300, 3, 1, False)])
+def test_moe_moments_kernel(N, K, n, with_base):
+    """vbmp_moe_moments (the per-sample part of MixtureofLinearTransforms.predict, transforms/MixtureofLinearTransforms.py:
+    100-106) against an fp64 evaluation: both the 4 x 8 register-tiled kernel (n % 4 == 0) and the row-per-lane one."""
+    g = torch.Generator(device=DEV).manual_seed(N + n)
+    mean = (torch.randn(N, K, n, generator=g, device=DEV) * 1.3 + 0.4).contiguous()
+    p = torch.softmax(1.5 * torch.randn(N, K, generator=g, device=DEV), -1).contiguous()
+    base = None
+    if with_base:
+        A = torch.randn(N, n, n, generator=g, device=DEV) * 0.2
+        base = (A @ A.transpose(-1, -2)).contiguous()
+    mu, Sig = _lib.moe_moments(mean, p, base, N, K, n)
+    md, pd = mean.double(), p.double()
+    mu_ref = torch.einsum("nk,nki->ni", pd, md)
+    S_ref = torch.einsum("nk,nki,nkj->nij", pd, md, md) - mu_ref.unsqueeze(-1) * mu_ref.unsqueeze(-2)
+    if with_base:
+        S_ref = S_ref + base.double()
+    assert float((mu.double() - mu_ref).abs().max()) <= 1e-5 * float(mu_ref.abs().max())
+    assert float((Sig.double() - S_ref).abs().max()) <= 2e-5 * float(S_ref.abs().max())
+    if with_base:      # in place: Sigma may alias base
+        b2 = base.clone()
+        mu2, Sig2 = _lib.moe_moments(mean, p, b2, N, K, n, Sigma=b2)
+        assert torch.equal(Sig2, Sig) and torch.equal(mu2, mu)
