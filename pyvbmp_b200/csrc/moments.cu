@@ -66,32 +66,67 @@ __global__ void __launch_bounds__(256) moe_moments_kernel(const float* __restric
   }
 }
 
-// lane = (rg, cg): rows 4 rg .. 4 rg + 3 (rg = lane / 4), columns 8 cg .. 8 cg + 7 (cg = lane % 4) of the 32 x 32 frame
-__global__ void __launch_bounds__(256) moe_moments_tile_kernel(const float* __restrict__ mean, const float* __restrict__ p,
-                                                               const float* __restrict__ base, long long N, int K, int n,
-                                                               float* __restrict__ mu, float* __restrict__ Sigma) {
-  const int lane = threadIdx.x & 31;
-  const long long w0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
+// lane = (rg, cg): rows 4 rg .. 4 rg + 3 (rg = lane / 4), columns 8 cg .. 8 cg + 7 (cg = lane % 4) of the 32 x 32 frame.
+// The means of a sample (K n floats, 8 KB at K = 64, n = 32) are staged through shared memory with cp.async, one chunk of
+// <= MM_KC components ahead per warp: read straight from global memory the same arithmetic ran at 0.9 TB/s (19 ms per 1 Mi
+// samples) — a warp had two 128-byte rows in flight, far too few bytes to cover DRAM latency.
+constexpr int MM_KC = 64;              // components per staged chunk
+constexpr int MM_WARPS = 4;            // warps per CTA (2 x MM_KC x 32 floats = 16 KB of staging per warp)
+
+__device__ __forceinline__ void mm_cp_async16(void* smem, const void* gmem) {
+  unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem));
+}
+__device__ __forceinline__ void mm_cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N_> __device__ __forceinline__ void mm_cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N_)); }
+
+__global__ void __launch_bounds__(MM_WARPS * 32) moe_moments_tile_kernel(const float* __restrict__ mean, const float* __restrict__ p,
+                                                                         const float* __restrict__ base, long long N, int K, int n,
+                                                                         float* __restrict__ mu, float* __restrict__ Sigma) {
+  extern __shared__ __align__(16) float mm_smem[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const long long w0 = (long long)blockIdx.x * MM_WARPS + wib;
+  const long long nw = (long long)gridDim.x * MM_WARPS;
   const int r0 = (lane >> 2) * 4, c0 = (lane & 3) * 8;
   const bool rok = r0 < n, cok0 = c0 < n, cok1 = c0 + 4 < n;         // n % 4 == 0: a float4 is all inside or all outside
-  for (long long s = w0; s < N; s += nw) {
-    const float* ms = mean + (size_t)s * K * n;
-    const float* ps = p + (size_t)s * K;
-    float acc[4][8];
+  float* buf = mm_smem + (size_t)wib * 2 * MM_KC * n;
+  const int nch = (K + MM_KC - 1) / MM_KC;
+  const long long nsamp = w0 < N ? (N - w0 + nw - 1) / nw : 0;       // samples of this warp
+  const long long items = nsamp * nch;
+  auto prefetch = [&](long long t) {
+    const long long s = w0 + (t / nch) * nw;
+    const int kc0 = (int)(t % nch) * MM_KC;
+    const int cnt = min(MM_KC, K - kc0) * n;                         // floats, a multiple of 4
+    const float* src = mean + ((size_t)s * K + kc0) * n;
+    float* dst = buf + (size_t)(t & 1) * MM_KC * n;
+    for (int e = lane * 4; e < cnt; e += 128) mm_cp_async16(dst + e, src + e);
+    mm_cp_async_commit();
+  };
+  float acc[4][8];
+  float4 mur, muc0, muc1;
+  if (items > 0) prefetch(0);
+  for (long long t = 0; t < items; ++t) {
+    const long long s = w0 + (t / nch) * nw;
+    const int ch = (int)(t % nch), kc0 = ch * MM_KC, kn = min(MM_KC, K - kc0);
+    if (t + 1 < items) { prefetch(t + 1); mm_cp_async_wait<1>(); } else { mm_cp_async_wait<0>(); }
+    __syncwarp();
+    if (ch == 0) {
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
+      for (int a = 0; a < 4; ++a)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[a][j] = 0.f;
-    float4 mur = make_float4(0.f, 0.f, 0.f, 0.f), muc0 = mur, muc1 = mur;
-#pragma unroll 2
-    for (int k = 0; k < K; ++k) {
+        for (int j = 0; j < 8; ++j) acc[a][j] = 0.f;
+      mur = make_float4(0.f, 0.f, 0.f, 0.f); muc0 = mur; muc1 = mur;
+    }
+    const float* mb_ = buf + (size_t)(t & 1) * MM_KC * n;
+    const float* ps = p + (size_t)s * K + kc0;
+#pragma unroll 4
+    for (int k = 0; k < kn; ++k) {
       const float pk = __ldg(ps + k);
-      const float* mk = ms + (size_t)k * n;
+      const float* mk = mb_ + (size_t)k * n;
       const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-      const float4 mr = rok ? __ldg(reinterpret_cast<const float4*>(mk + r0)) : z;
-      const float4 ma = cok0 ? __ldg(reinterpret_cast<const float4*>(mk + c0)) : z;
-      const float4 mb = cok1 ? __ldg(reinterpret_cast<const float4*>(mk + c0 + 4)) : z;
+      const float4 mr = rok ? *reinterpret_cast<const float4*>(mk + r0) : z;
+      const float4 ma = cok0 ? *reinterpret_cast<const float4*>(mk + c0) : z;
+      const float4 mb = cok1 ? *reinterpret_cast<const float4*>(mk + c0 + 4) : z;
       const float w[4] = {pk * mr.x, pk * mr.y, pk * mr.z, pk * mr.w};
       const float c[8] = {ma.x, ma.y, ma.z, ma.w, mb.x, mb.y, mb.z, mb.w};
       mur.x += w[0]; mur.y += w[1]; mur.z += w[2]; mur.w += w[3];
@@ -102,6 +137,8 @@ __global__ void __launch_bounds__(256) moe_moments_tile_kernel(const float* __re
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[a][j] = fmaf(w[a], c[j], acc[a][j]);
     }
+    __syncwarp();                                                      // the buffer is refilled two items on
+    if (ch != nch - 1) continue;
     if (rok && (lane & 3) == 0) *reinterpret_cast<float4*>(mu + (size_t)s * n + r0) = mur;
     const float mrow[4] = {mur.x, mur.y, mur.z, mur.w};
     const float mcol[8] = {muc0.x, muc0.y, muc0.z, muc0.w, muc1.x, muc1.y, muc1.z, muc1.w};
@@ -134,7 +171,12 @@ int launch_moe_moments(const float* mean, const float* p, const float* base, lon
   if (blocks > cap) blocks = cap;
   const bool aligned = ((size_t)mean % 16 == 0) && ((size_t)Sigma % 16 == 0) && ((size_t)mu % 16 == 0) && (!base || (size_t)base % 16 == 0);
   if ((n & 3) == 0 && aligned) {
-    moe_moments_tile_kernel<<<(unsigned)blocks, 256, 0, st>>>(mean, p, base, N, K, n, mu, Sigma);
+    const size_t smem = (size_t)MM_WARPS * 2 * MM_KC * n * sizeof(float);       // 64 KB at n = 32: three CTAs per SM
+    long long tb = (N + MM_WARPS - 1) / MM_WARPS;
+    const long long tcap = (long long)num_sms() * 3 * 4;
+    if (tb > tcap) tb = tcap;
+    cudaFuncSetAttribute(moe_moments_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    moe_moments_tile_kernel<<<(unsigned)tb, MM_WARPS * 32, smem, st>>>(mean, p, base, N, K, n, mu, Sigma);
     return check_launch("moe_moments_tile");
   }
   switch (np) {
