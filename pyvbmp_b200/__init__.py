@@ -17,6 +17,7 @@ from .mvn import MultivariateNormal_vector_format, Delta
 from .hmm import HMM, ARHMM, ARHMM_prXY, ARHMM_prXRY
 from .install import install, uninstall, installed_classes
 from . import sharding
+from . import ops          # registers torch.ops.vbmp.*
 from ._lib import VbmpError, LIB_PATH
 
 __all__ = ["Wishart", "NormalInverseWishart", "MatrixNormalWishart", "Gamma", "DiagonalWishart", "NormalGamma",

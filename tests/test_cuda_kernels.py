@@ -375,3 +375,18 @@ def test_moe_moments_kernel(N, K, n, with_base):
         b2 = base.clone()
         mu2, Sig2 = _lib.moe_moments(mean, p, b2, N, K, n, Sigma=b2)
         assert torch.equal(Sig2, Sig) and torch.equal(mu2, mu)
+
+
+def test_torch_custom_ops_match_the_binding():
+    """torch.ops.vbmp.* are the same kernels as the ctypes binding the mirrors call."""
+    import pyvbmp_b200.ops  # noqa: F401
+    N, d0, d1, K = 3001, 32, 32, 64
+    z, z0, z1, W, m, cst, Dp, L = _problem(N, d0, d1, K, seed=21)
+    xg = torch.zeros(1, dtype=torch.int32, device=DEV)
+    lg = torch.ops.vbmp.estep_logits(z0, z1, W, m, cst)
+    assert torch.equal(lg, _lib.estep(z0, z1, N, 1, xg, W, m, cst, 1, K, Dp, 0).view(N, K))
+    p, lzn, NA, lZ = torch.ops.vbmp.estep_assign(z0, z1, W, m, cst)
+    p2, lzn2, NA2, lZ2 = _lib.estep(z0, z1, N, 1, xg, W, m, cst, 1, K, Dp, 1)
+    assert torch.equal(p, p2.view(N, K)) and torch.equal(NA, NA2.view(K)) and torch.equal(lZ, lZ2.view(()))
+    G = torch.ops.vbmp.gram(z0, z1, p, False)
+    assert torch.equal(G, _lib.gram(z0, z1, N, 1, xg, p2.clone(), 1, xg, 1, K, Dp).view(K, d0 + d1 + 1, d0 + d1 + 1))

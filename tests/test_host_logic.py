@@ -107,3 +107,19 @@ def test_install_rebinds_reference_globals():
         sys.path.remove("/root/reference")
     import dists
     assert dists.NormalInverseWishart is not V.NormalInverseWishart
+
+
+def test_torch_custom_ops_are_registered_with_shape_inference():
+    """torch.ops.vbmp.* (pyvbmp_b200/ops.py): registered with the dispatcher, fake-tensor shape functions in place."""
+    import pyvbmp_b200.ops  # noqa: F401
+    from torch._subclasses.fake_tensor import FakeTensorMode
+    for name in ("estep_logits", "estep_assign", "gram", "hmm_forward_backward"):
+        assert hasattr(torch.ops.vbmp, name)
+    with FakeTensorMode():
+        z, W, m, c = torch.empty(100, 8), torch.empty(5, 8, 8), torch.empty(5, 8), torch.empty(5)
+        assert torch.ops.vbmp.estep_logits(z, None, W, m, c).shape == (100, 5)
+        p, lzn, NA, lZ = torch.ops.vbmp.estep_assign(z, torch.empty(100, 4), torch.empty(5, 16, 16), torch.empty(5, 16), c)
+        assert p.shape == (100, 5) and lzn.shape == (100,) and NA.shape == (5,) and lZ.shape == ()
+        assert torch.ops.vbmp.gram(z, torch.empty(100, 3), p, False).shape == (5, 12, 12)
+        out = torch.ops.vbmp.hmm_forward_backward(torch.empty(7, 3, 4), torch.empty(4, 4), torch.empty(4))
+        assert [tuple(t.shape) for t in out] == [(7, 3, 4), (3, 4, 4), (3, 4), (3,)]
