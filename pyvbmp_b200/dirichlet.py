@@ -73,6 +73,14 @@ class Dirichlet():
         ed = self._ed()
         return (X * self.loggeomean()).sum(ed) + (1 + X.sum(ed)).lgamma() - (1 + X).lgamma().sum(ed)
 
+    def KL_lgamma(self, x):
+        """dists/Dirichlet.py:63-66 (infinite entries contribute zero; not in place here)."""
+        return torch.nan_to_num(x.lgamma(), posinf=0.0)
+
+    def KL_digamma(self, x):
+        """dists/Dirichlet.py:68-71."""
+        return torch.nan_to_num(x.digamma(), neginf=0.0)
+
     def KLqprior(self):
         """dists/Dirichlet.py:73-83 (infinite lgamma / digamma entries contribute zero)."""
         ed = self._ed()

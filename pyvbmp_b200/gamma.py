@@ -51,6 +51,10 @@ class Gamma():
         self.alpha = (self.alpha_0 + SElogx) * lr + self.alpha * (1 - lr)
         self.beta = (self.beta_0 + SEx) * lr + self.beta * (1 - lr)
 
+    def update(self, pX, p=None, lr=1.0, beta=None):
+        """dists/Gamma.py:49-62: as raw_update, from a belief's mean."""
+        self.raw_update(pX.mean(), p=p, lr=lr, beta=beta)
+
     def raw_update(self, X, p=None, lr=1.0, beta=None):
         """dists/Gamma.py:64-76 (Poisson observation model)."""
         sample_shape = X.shape[:-self.event_dim - self.batch_dim]

@@ -97,6 +97,18 @@ class HMM():
         p = p / p.sum(-1, keepdim=True)
         return p, SEzz, SEz0, logZ
 
+    def forward_step(self, logits, observation_logits):
+        """models/HMM.py:33-34."""
+        return _lse(logits.unsqueeze(-1) + observation_logits.unsqueeze(-2) + self.transition.loggeomean(), -2)
+
+    def backward_step(self, logits, observation_logits):
+        """models/HMM.py:36-37."""
+        return _lse(logits.unsqueeze(-2) + observation_logits.unsqueeze(-2) + self.transition.loggeomean(), -1)
+
+    def forward_backward_steps(self, X, T):
+        """models/HMM.py:39-71: the same recursion with the observation logits evaluated one time slice at a time."""
+        return self.forward_backward_logits(torch.stack([self.obs_logits(X, t) for t in range(T)], 0))
+
     def assignment_pr(self):
         return self.p
 
@@ -111,9 +123,10 @@ class HMM():
 
     def update_states(self, X, T=None):
         """models/HMM.py:119-132 (T=None path)."""
-        if T is not None:
-            raise NotImplementedError("the step-wise T path calls an undefined helper in the reference (HMM.py:61)")
-        self.p, SEzz, SEz0, logZ = self.forward_backward_logits(self.obs_logits(X))
+        if T is not None:          # models/HMM.py:120-121 (the reference's own version stops at an undefined helper, :61)
+            self.p, SEzz, SEz0, logZ = self.forward_backward_steps(X, T)
+        else:
+            self.p, SEzz, SEz0, logZ = self.forward_backward_logits(self.obs_logits(X))
         NA = self.p.sum(0)
         sample_dims = list(range(NA.ndim - self.batch_dim - self.event_dim))
         NA = NA.sum(sample_dims)

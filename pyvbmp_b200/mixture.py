@@ -279,6 +279,11 @@ class Mixture():
             out = out.sum(-self.dist.event_dim - 1, keepdim)
         return out
 
+    def stable_logsumexp(self, x, dim=None, keepdim=False):
+        """dists/Mixture.py:110-127 (helper kept for callers of the reference's interface)."""
+        dims = (dim,) if isinstance(dim, int) else tuple(dim)
+        return torch.logsumexp(x, dim=dims, keepdim=keepdim)
+
 
 class GaussianMixtureModel(Mixture):
     def __init__(self, nc, dim, isotropic=False):

@@ -216,6 +216,30 @@ class MixtureofLinearTransforms():
     def EXTinvUX(self):
         return self.event_average(self.W.EXTinvUX())
 
+    def EXTAX(self, A):
+        return self.event_average(self.W.EXTAX(A))
+
+    def EXAXT(self, A):
+        return self.event_average(self.W.EXAXT(A))
+
+    def EXinvVXT(self):
+        return self.event_average(self.W.EXinvVXT())
+
+    def EXmMUTinvUXmMU(self):
+        return self.event_average(self.W.EXmMUTinvUXmMU())
+
+    def EXmMUinvVXmMUT(self):
+        return self.event_average(self.W.EXmMUinvVXmMUT())
+
+    def EXTX(self):
+        return self.event_average(self.W.EXTX())
+
+    def EXXT(self):
+        return self.event_average(self.W.EXXT())
+
+    def ElogdetinvU(self):
+        return self.average(self.W.invU.ElogdetinvSigma())
+
     def EinvSigma(self):
         return self.event_average(self.W.EinvSigma())
 
