@@ -189,6 +189,9 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+_ALL_CPUS = set()      # the affinity mask this process started with (restored before the CPU baseline runs)
+
+
 def numa_pin(dev_index):
     """Bind this process to the CPUs next to its GPU BEFORE any pinned host memory is allocated (first touch then places the
     staging buffers on the GPU's NUMA node).  Returns a short description for the JSON line."""
@@ -206,6 +209,7 @@ def numa_pin(dev_index):
             elif part:
                 ids.add(int(part))
         allowed = os.sched_getaffinity(0)
+        _ALL_CPUS.update(allowed)
         ids &= allowed
         if ids and ids != allowed:
             os.sched_setaffinity(0, ids)
@@ -508,6 +512,8 @@ def main():
                 torch.cuda.empty_cache()
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
+            if _ALL_CPUS:
+                os.sched_setaffinity(0, _ALL_CPUS)       # the CPU arm gets every host core, not just the GPU's NUMA node
             threads = os.cpu_count() or 1
             v, s_per, kind = cpu_iteration_rate(args.ref_rows, args.cpu_baseline_iters, 1, threads)
             what = ("the unmodified reference (baseline/_ref: models.GaussianMixtureModel.update, CPU torch)" if kind == "reference"
