@@ -170,6 +170,15 @@ int vbmp_mnw_kl(const float* mu_0, const float* mu, const float* invV_0, const f
 int vbmp_hmm_forward_backward(const float* logits, const float* trans, const float* init, int T, long long S, int G, int K,
                               float ptemp, float* p, float* SEzz, float* SEz0, float* logZ, void* stream);
 
+/* ---- row GEMM with fp32-grade accuracy ----------------------------------------------------------
+ * C[N x M] (+)= A[N x Kd] B[Kd x M] (+ bias[M]), all row-major with leading dimensions lda / ldb / ldc (floats); every
+ * product is the 3-term TF32 split on the warp-level tensor-core path.  For the sample-major products with one small
+ * shared operand: the component means and sum_k p_k ESigma_k of MixtureofLinearTransforms.predict
+ * (transforms/MixtureofLinearTransforms.py:100-103) and the covariance terms of MatrixNormalWishart.Elog_like_given_pX_pY
+ * (transforms/MatrixNormalWishart.py:236-247).  accumulate != 0 adds to C; bias may be NULL.                            */
+int vbmp_rowgemm(const float* A, int lda, const float* B, int ldb, const float* bias, float* C, int ldc,
+                 long long N, int Kd, int M, int accumulate, void* stream);
+
 /* ---- mixture-of-experts predictive moments -------------------------------------------------------
  * The per-sample part of MixtureofLinearTransforms.predict (transforms/MixtureofLinearTransforms.py:100-106):
  *   mu[s] = sum_k p[s,k] mean[s,k,:],   Sigma[s] = base[s] + sum_k p[s,k] mean[s,k,:] mean[s,k,:]^T - mu[s] mu[s]^T

@@ -62,7 +62,7 @@ EXPORTS = (
     "vbmp_mnw_update", "vbmp_wishart_elogdet", "vbmp_wishart_kl", "vbmp_niw_kl", "vbmp_mnw_kl",
     "vbmp_hmm_forward_backward", "vbmp_rpack_bytes", "vbmp_estep_rpack", "vbmp_gram_rpack",
     "vbmp_zpack_bytes", "vbmp_gram_zpack", "vbmp_gram_ex_workspace_bytes", "vbmp_gram_ex",
-    "vbmp_diag_estep_workspace_bytes", "vbmp_diag_estep", "vbmp_diag_estep_rpack", "vbmp_mnw_prep_ex", "vbmp_moe_moments",
+    "vbmp_diag_estep_workspace_bytes", "vbmp_diag_estep", "vbmp_diag_estep_rpack", "vbmp_mnw_prep_ex", "vbmp_moe_moments", "vbmp_rowgemm",
 )
 
 
@@ -458,6 +458,23 @@ def mnw_kl(mu0, mu, invV0, V, ldV, ldV0, invU0, U, nu0, nu, ldU, ldU0, C, n, pp)
     _call("vbmp_mnw_kl", U.device, _ptr(mu0), _ptr(mu), _ptr(invV0), _ptr(V), _ptr(ldV), _ptr(ldV0), _ptr(invU0), _ptr(U),
                              _ptr(nu0), _ptr(nu), _ptr(ldU), _ptr(ldU0), c_int(C), c_int(n), c_int(pp), _ptr(out),
                              _stream(U.device))
+    return out
+
+
+def rowgemm(A, B, bias=None, out=None, accumulate=False):
+    """out (N, M) (+)= A (N, Kd) @ B (Kd, M) (+ bias (M,)) with fp32-grade (3 x TF32) products (vbmp_rowgemm).  A, B, out: fp32,
+    last dimension contiguous."""
+    dev = A.device
+    N, Kd = A.shape
+    M = B.shape[1]
+    assert B.shape[0] == Kd and A.stride(1) == 1 and B.stride(1) == 1
+    if out is None:
+        assert not accumulate
+        out = torch.empty((N, M), dtype=torch.float32, device=dev)
+    assert out.shape == (N, M) and out.stride(1) == 1
+    _call("vbmp_rowgemm", dev, c_void_p(A.data_ptr()), c_int(A.stride(0)), c_void_p(B.data_ptr()), c_int(B.stride(0)), _ptr(bias),
+          c_void_p(out.data_ptr()), c_int(out.stride(0)), c_longlong(N), c_int(Kd), c_int(M), c_int(int(bool(accumulate))),
+          _stream(dev))
     return out
 
 

@@ -64,6 +64,8 @@ int launch_diag_estep(const float* x, int d, long long N, int GX, const int* xg,
                       void* ws, size_t ws_bytes, cudaStream_t st, unsigned char* rpack = nullptr);
 int launch_moe_moments(const float* mean, const float* p, const float* base, long long N, int K, int n, float* mu, float* Sigma,
                        cudaStream_t st);
+int launch_rowgemm(const float* A, int lda, const float* B, int ldb, const float* bias, float* C, int ldc, long long N, int Kd,
+                   int M, int accumulate, cudaStream_t st);
 bool gram_rpack_usable();
 bool estep_umma_can_pack(long long N, int GX, int G, int K, int Dp, int d0, int d1, int mode);
 size_t gram_rpack_bytes(long long N, int K);
@@ -347,6 +349,12 @@ int vbmp_moe_moments(const float* mean, const float* p, const float* base, long 
                      float* mu, float* Sigma, void* stream) {
   if (!mean || !p || !mu || !Sigma) { set_error("moe_moments: NULL argument"); return VBMP_ERR_SHAPE; }
   return launch_moe_moments(mean, p, base, N, K, n, mu, Sigma, (cudaStream_t)stream);
+}
+
+int vbmp_rowgemm(const float* A, int lda, const float* B, int ldb, const float* bias, float* C, int ldc,
+                 long long N, int Kd, int M, int accumulate, void* stream) {
+  if (!A || !B || !C) { set_error("rowgemm: NULL argument"); return VBMP_ERR_SHAPE; }
+  return launch_rowgemm(A, lda, B, ldb, bias, C, ldc, N, Kd, M, accumulate, (cudaStream_t)stream);
 }
 
 int vbmp_hmm_forward_backward(const float* logits, const float* trans, const float* init, int T, long long S, int G, int K,

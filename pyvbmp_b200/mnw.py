@@ -275,12 +275,15 @@ class MatrixNormalWishart():
         if bp is not None and self.event_dim == 2:
             N, sample, mx, my, Sx, Sy = bp
             K = self.batch_shape[0]
-            corr = 0.0
+            # tr(Sigma_y E[invSigma_k]) + tr(Sigma_x E[X^T invU X]_k): two (N x n^2) (n^2 x K) products (vbmp_rowgemm)
+            corr = None
             if Sy is not None:
-                corr = corr + Sy @ self.EinvSigma().expand(K, self.n, self.n).reshape(K, -1).t()
+                Ly = self.EinvSigma().expand(K, self.n, self.n).reshape(K, -1).t().contiguous()
+                corr = _lib.rowgemm(_lib.f32(Sy), _lib.f32(Ly))
             if Sx is not None:
-                corr = corr + Sx @ Exx.expand(K, p_in, p_in).reshape(K, -1).t()
-            if isinstance(corr, float):
+                Lx = Exx.expand(K, p_in, p_in).reshape(K, -1).t().contiguous()
+                corr = _lib.rowgemm(_lib.f32(Sx), _lib.f32(Lx), out=corr, accumulate=corr is not None)
+            if corr is None:
                 return base
             return base - 0.5 * corr.view(sample + (K,))
         corr = 0.0

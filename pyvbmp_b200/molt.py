@@ -148,7 +148,7 @@ class MixtureofLinearTransforms():
         M = W.mu                                                           # (K, n, p'): mean_k(x) = M_k [x;1]
         ES = W.EinvSigma().inverse().expand(K, n, n)                       # = pY.ESigma(): (E invSigma)^-1 = invU / nu (:389)
         Mw = M[..., :p_in].reshape(K * n, p_in).t().contiguous()           # (p, K n)
-        Mb = M[..., -1].reshape(1, K * n) if W.pad_X else None
+        Mb = M[..., -1].reshape(K * n).contiguous() if W.pad_X else None
         ESf = ES.reshape(K, n * n).contiguous()
         mu = torch.empty(N, n, 1, device=dev)
         Sigma = torch.empty(N, n, n, device=dev)
@@ -158,14 +158,14 @@ class MixtureofLinearTransforms():
         # weighted rank-K update is vbmp_moe_moments, which writes mu and Sigma in place (Sigma starts as the base term)
         for a in range(0, N, self.PREDICT_ROWS):
             b = min(N, a + self.PREDICT_ROWS)
-            mean = torch.addmm(Mb, X2[a:b], Mw) if Mb is not None else X2[a:b] @ Mw
             pe = p[a:b]
             S = Sigma[a:b]
-            torch.mm(pe, ESf, out=S.view(b - a, n * n))
+            mean = _lib.rowgemm(X2[a:b], Mw, bias=Mb)                                           # (rows, K n)
+            _lib.rowgemm(pe, ESf, out=S.view(b - a, n * n))                                     # sum_k p_k ESigma_k
             if n <= 32:
                 _lib.moe_moments(mean, pe, S, b - a, K, n, mu=mu[a:b].view(b - a, n), Sigma=S)
                 continue
-            mean = mean.view(b - a, K, n)
+            mean = mean.view(b - a, K, n)                                                       # n > 32: batched torch
             mu_b = torch.bmm(pe.unsqueeze(1), mean).squeeze(1)                                  # (rows, n)
             A = mean * pe.sqrt().unsqueeze(-1)
             S.baddbmm_(A.transpose(1, 2), A)

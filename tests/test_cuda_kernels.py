@@ -390,3 +390,31 @@ def test_torch_custom_ops_match_the_binding():
     assert torch.equal(p, p2.view(N, K)) and torch.equal(NA, NA2.view(K)) and torch.equal(lZ, lZ2.view(()))
     G = torch.ops.vbmp.gram(z0, z1, p, False)
     assert torch.equal(G, _lib.gram(z0, z1, N, 1, xg, p2.clone(), 1, xg, 1, K, Dp).view(K, d0 + d1 + 1, d0 + d1 + 1))
+
+
+@pytest.mark.parametrize("N,Kd,M,bias,acc", [(5000, 32, 2048, True, False), (3001, 64, 1024, False, False),
+                                              (4100, 1024, 64, False, True), (777, 7, 13, True, True), (129, 33, 100, True, False)])
+def test_rowgemm_kernel(N, Kd, M, bias, acc):
+    """vbmp_rowgemm (3 x TF32 products on the warp-level tensor-core path) against an fp64 product: fp32-grade accuracy on
+    aligned and ragged shapes, with bias and with accumulation into the output."""
+    g = torch.Generator(device=DEV).manual_seed(N + Kd + M)
+    A = torch.randn(N, Kd, generator=g, device=DEV) * 1.7 + 0.3
+    B = torch.randn(Kd, M, generator=g, device=DEV)
+    b = torch.randn(M, generator=g, device=DEV) if bias else None
+    C0 = torch.randn(N, M, generator=g, device=DEV) if acc else None
+    ref = A.double() @ B.double()
+    if bias:
+        ref = ref + b.double()
+    if acc:
+        ref = ref + C0.double()
+    out = _lib.rowgemm(A, B, bias=b, out=None if not acc else C0.clone(), accumulate=acc)
+    scale = float((A.abs().double() @ B.abs().double()).max())
+    assert float((out.double() - ref).abs().max()) <= 2e-6 * scale
+    # a strided view as A (rows of a wider matrix) and as the output
+    if Kd >= 8:
+        wide = torch.randn(N, Kd + 12, generator=g, device=DEV)
+        out2 = torch.zeros(N, M + 4, device=DEV)
+        _lib.rowgemm(wide[:, 4:4 + Kd], B, out=out2[:, :M])
+        ref2 = wide[:, 4:4 + Kd].double() @ B.double()
+        assert float((out2[:, :M].double() - ref2).abs().max()) <= 2e-6 * float((wide.abs().double()[:, 4:4 + Kd] @ B.abs().double()).max())
+        assert float(out2[:, M:].abs().max()) == 0.0

@@ -27,7 +27,7 @@ b.record(); b.synchronize()
 t = a.elapsed_time(b) / 3
 ke = sum(x.elapsed_time(y) for x, y in _lib.PROFILE.get("vbmp_estep", [])) / 3
 print(f"MoLT.predict N={N} p={p} n={n} K={K}: {t:.2f} ms per call ({N * K / t / 1e6:.2f}e9 sample*component evaluations/s); "
-      f"gate probabilities (K2 kernel) {ke:.2f} ms, moment sums (torch batched GEMMs, {N * n * n * 4 / 1e9:.2f} GB of covariances out) {t - ke:.2f} ms")
+      f"gate probabilities (K2 kernel) {ke:.2f} ms, moment sums (means + base row GEMMs + moe_moments, {N * n * n * 4 / 1e9:.2f} GB of covariances out) {t - ke:.2f} ms")
 
 # ---- breakdown of one 64 Ki-row block: component means GEMM, base GEMM, per-sample moments kernel
 W = m.W
@@ -47,9 +47,9 @@ ts = {}
 for rep in range(3):
     e = [ev() for _ in range(4)]
     e[0].record()
-    mean = torch.addmm(Mb, X2, Mw)
+    mean = _lib.rowgemm(X2, Mw, bias=Mb.reshape(-1).contiguous())
     e[1].record()
-    torch.mm(pe, ESf, out=S.view(rows, n * n))
+    _lib.rowgemm(pe, ESf, out=S.view(rows, n * n))
     e[2].record()
     _lib.moe_moments(mean, pe, S, rows, K, n, mu=mu, Sigma=S)
     e[3].record()
