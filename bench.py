@@ -224,7 +224,7 @@ def time_steps(fn, steps, warmup, dev, barrier):
     for _ in range(warmup):
         fn()
     barrier()
-    _lib.PROFILE = {}
+    _lib.profile_begin(16 * steps)
     n0 = _lib.lib().vbmp_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
@@ -232,7 +232,7 @@ def time_steps(fn, steps, warmup, dev, barrier):
         fn()
     ev1.record()
     barrier()
-    prof, _lib.PROFILE = _lib.PROFILE, None
+    prof = _lib.profile_end()
     kern = {}
     for name, evs in prof.items():
         tt = sum(a.elapsed_time(b) for a, b in evs)

@@ -24,6 +24,26 @@ _PROFILE_AS = {"vbmp_estep_rpack": "vbmp_estep", "vbmp_diag_estep_rpack": "vbmp_
                "vbmp_gram_zpack": "vbmp_gram"}
 
 
+_EVENT_POOL = []   # timing events made ahead of a profiled region (profile_begin): creating them inside it costs CPU time per call
+
+
+def profile_begin(n_calls=256):
+    """Start collecting (start, end) CUDA events per C-ABI call into PROFILE, with the events of ``n_calls`` calls made up front."""
+    global PROFILE
+    while len(_EVENT_POOL) < 2 * n_calls:
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()                      # forces the lazy cudaEventCreate now
+        _EVENT_POOL.append(ev)
+    torch.cuda.synchronize()
+    PROFILE = {}
+
+
+def profile_end():
+    global PROFILE
+    prof, PROFILE = PROFILE, None
+    return prof or {}
+
+
 class VbmpError(RuntimeError):
     pass
 
@@ -79,7 +99,8 @@ def _call(name, dev, *args):
     fn = getattr(lib(), name)
     with torch.cuda.device(dev):
         if PROFILE is not None:
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a = _EVENT_POOL.pop() if _EVENT_POOL else torch.cuda.Event(enable_timing=True)
+            b = _EVENT_POOL.pop() if _EVENT_POOL else torch.cuda.Event(enable_timing=True)
             a.record()
             rc = fn(*args)
             b.record()

@@ -20,7 +20,7 @@ Sy = (0.01 * torch.eye(n, device=dev)).expand(N, n, n).contiguous()
 pX, pY = V.MultivariateNormal_vector_format(mu=X, Sigma=Sx), V.MultivariateNormal_vector_format(mu=Y, Sigma=Sy)
 for _ in range(2): m.update(pX, pY, iters=1)
 torch.cuda.synchronize()
-_lib.PROFILE = {}
+_lib.profile_begin(512)
 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 a.record()
 R = 3

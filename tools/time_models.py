@@ -14,12 +14,12 @@ def timed(fn, n=3, warm=2):
         fn()
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    _lib.PROFILE = {}
+    _lib.profile_begin(512)
     a.record()
     for _ in range(n):
         fn()
     b.record(); b.synchronize()
-    prof, _lib.PROFILE = _lib.PROFILE, None
+    prof = _lib.profile_end()
     ker = {k: round(sum(x.elapsed_time(y) for x, y in v) / n, 3) for k, v in prof.items()}
     return a.elapsed_time(b) / n, ker
 
