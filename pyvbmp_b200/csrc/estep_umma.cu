@@ -19,10 +19,12 @@
 //     dense work with KSTEP = 16, 56 % with KSTEP = 8).
 //   * 128-column fp32 accumulators in TMEM, rotating over the (group, half) sequence (two with TF32 operands, three
 //     with fp16 ones); the two MMA-issuing warps (one per half) take strict turns, so the epilogue of one half runs
-//     under the MMAs of the other.  Each burst starts with one TF32 MMA of a small shared-memory A block (1, or the
-//     row's scale) against [-m_hi; -m_lo], which initialises the accumulator to -m: the 8 epilogue warps (one thread per
-//     sample row) only read D with tcgen05.ld, square-reduce with packed fp32x2 FFMA2, keep an online logsumexp and write
-//     the logits.
+//     under the MMAs of the other.  The 8 epilogue warps (one thread per sample row) read D with tcgen05.ld, subtract m,
+//     square-reduce with packed fp32x2 FFMA2, keep an online logsumexp and write the logits.  TF32 variant: each burst
+//     starts with one TF32 MMA of a small shared-memory A block of ones against [-m_hi; -m_lo], which initialises the
+//     accumulator to -m.  fp16 variant: that MMA was 1 of the 8.5 full-width MMA slots of a burst and the kernel runs at
+//     the (power-capped) tensor-pipe rate, so -m is instead the addend of the epilogue's rescaling FFMA2, read from the
+//     stage with warp-broadcast 16-byte loads (32 shared-memory wavefronts per warp and burst).
 //   * mode 1: a 12th warp normalises tile t (p = exp(l - logZ_n), in place, L2 hits, coalesced float4, ex2.approx) while
 //     the MMAs of tile t + 1 run, keeps NA of its fixed columns in a fixed order (deterministic) and, on request, also
 //     writes the responsibilities pre-split into the Gram kernel's fp16 operand images (EstepArgs::rpack).
@@ -33,10 +35,9 @@
 //   * FP16: each sample row is scaled by 2^sh_n (row maximum -> [2^10, 2^11)) and each component's W by 2^t_k (same
 //     normalisation), both EXACT; then z' = a + b and W' = A + B with a, b, A, B fp16 (a = rn(z'), b = rn(z' - a): 22
 //     significant bits, product error ~2^-22, so it is at least as accurate as the TF32 split) and the same three terms
-//     run as kind::f16 MMAs with K = 16, which issue at twice the TF32 rate and halve the operand bytes (stage 24.6 KB
-//     instead of 41 KB, A 64 instead of 128 TMEM columns per half).  The -m fold stays a TF32 MMA whose A block holds
-//     2^sh_n per row and whose B block holds -m 2^t_k; the epilogue multiplies by 2^-(sh_n + t_k) (exact) before squaring,
-//     so nothing can overflow that would not overflow in the unscaled form.  Zero rows get sh = 0; sh and t are clamped to
+//     run as kind::f16 MMAs with K = 16, which issue at twice the TF32 rate and halve the operand bytes (stage 21 KB
+//     instead of 41 KB, A 64 instead of 128 TMEM columns per half).  The epilogue computes acc 2^-(sh_n + t_k) - m (the
+//     scaling is exact) before squaring, so nothing can overflow that would not overflow in the unscaled form.  Zero rows get sh = 0; sh and t are clamped to
 //     +-60.  Before that, feature i of z is multiplied by 2^e_i and row i of every W_k by 2^-e_i (e_i = exponent of the
 //     largest |W_k[i][.]| over all components, estep_rowscale_kernel): the product is unchanged, and features measured in
 //     very different units (tests: 10 decades apart) all land inside the fp16 window — W's rows carry 1/sigma_i, so this
@@ -50,6 +51,9 @@
 namespace vbmp {
 using namespace umma;
 
+#ifndef EU_MFOLD
+#define EU_MFOLD 0      // fp16 variant, where -m is folded in: 0 = by a TF32 MMA that initialises the accumulator,
+#endif                  // 1 = in the epilogue (broadcast shared-memory loads), 2 = nowhere (timing experiment only)
 constexpr int EU_THREADS = 384;     // warp 0: bulk-copy producer, warps 1-2: MMA issuers (one per half), warps 3..10: workers,
                                     // warp 11: normaliser (mode 1)
 constexpr int EU_TILE = 256;
@@ -80,7 +84,9 @@ struct EuCfg {
   }
   static constexpr int WB = blk_off(KS);      // bytes of one operand image (hi or lo) of a group
   static constexpr int GB = 2 * WB;           // hi image then lo image
-  static constexpr int MB = EU_N * 32;        // the "-m" operand block: one K-step (k = 0: -m_hi, k = 1: -m_lo, rest 0)
+  // the "-m" block.  TF32: one K-step of a B operand (k = 0: -m_hi, k = 1: -m_lo, rest 0) for the MMA that initialises the
+  // accumulator.  fp16: the plain fp32 values -m[n] in column order, subtracted in the epilogue (see the kernel header).
+  static constexpr int MB = (F16 && EU_MFOLD) ? EU_N * 4 : EU_N * 32;
   static constexpr int REC = GB + MB + 64;    // + cst of the CG components (floats 0..7) and 2^-t_k (floats 8..15)
   static constexpr int STAGE = (REC + 127) / 128 * 128;
   // component / feature of column n
@@ -153,7 +159,15 @@ __global__ void estep_pack_kernel(const float* __restrict__ W, const float* __re
   // per group, as much as the MMA operand fetch, and the shared-memory pipe is what both compete for.
   float* mo = reinterpret_cast<float*>(Wp + (size_t)g * C::REC + C::GB);
   float* co = reinterpret_cast<float*>(Wp + (size_t)g * C::REC + C::GB + C::MB);
-  for (int o = threadIdx.x; o < EU_N * 8; o += blockDim.x) {
+  if (F16 && EU_MFOLD) {
+    // fp16 operands: the epilogue computes (acc 2^-(sh_n + t_k)) - m with one FFMA2 per column pair, so the record holds
+    // the unscaled -m in column order (512 bytes, read with warp-broadcast 16-byte loads)
+    for (int n = threadIdx.x; n < EU_N; n += blockDim.x) {
+      const int c = g * C::CG + C::col_cl(n);
+      mo[n] = c < K ? -m[(size_t)c * DP + C::col_j(n)] : 0.f;
+    }
+  }
+  for (int o = threadIdx.x; o < ((F16 && EU_MFOLD) ? 0 : EU_N * 8); o += blockDim.x) {
     const int ch = o / (EU_N * 4), n = (o % (EU_N * 4)) / 4, e = o % 4;
     float v = 0.f;
     if (ch == 0 && e < 2) {
@@ -305,13 +319,14 @@ estep_umma_kernel(EstepArgs a, const uint8_t* __restrict__ Wp, const float* __re
         mbar_wait(&S->turn[h], h == 0 ? (itp ^ 1) : itp);     // my turn
         tc_fence_after();
         if (elect_one()) {
-          mma_tf32_ss(dcol, ones_desc, C::desc_m() + sb, idesc_tf32(128, EU_N), 0);   // D = -m
+          if (!(F16 && EU_MFOLD)) mma_tf32_ss(dcol, ones_desc, C::desc_m() + sb, idesc_tf32(128, EU_N), 0);   // D = -m
 #pragma unroll
           for (int ks = 0; ks < C::KS; ++ks) {
             const uint64_t b_hi = C::desc0(ks, 0) + sb, b_lo = C::desc0(ks, 1) + sb;
             if (F16) {
               const uint32_t idesc = idesc_f16(128, C::nn(ks));
-              mma_f16_ts(dcol + C::n0(ks), a_lo + ks * 8, b_hi, idesc, 1);       // small terms first
+              // K-step 0 spans all 128 columns: its first MMA overwrites the accumulator
+              mma_f16_ts(dcol + C::n0(ks), a_lo + ks * 8, b_hi, idesc, (EU_MFOLD && ks == 0) ? 0 : 1);       // small terms first
               mma_f16_ts(dcol + C::n0(ks), a_hi + ks * 8, b_lo, idesc, 1);
               mma_f16_ts(dcol + C::n0(ks), a_hi + ks * 8, b_hi, idesc, 1);
             } else {
@@ -404,9 +419,11 @@ estep_umma_kernel(EstepArgs a, const uint8_t* __restrict__ Wp, const float* __re
             tmem_st8(a_hi + c0 / 2, hi);
             tmem_st8(a_lo + c0 / 2, lo);
           }
-          // the row's scale into the A block of the -m MMA (k = 0 meets -m_hi, k = 1 meets -m_lo)
-          *reinterpret_cast<float2*>(ones + h * 1024 + (q * 32 + lane) * 4) = make_float2(sc, sc);
-          fence_proxy_async();
+          if (!EU_MFOLD) {
+            // the row's scale into the A block of the -m MMA (k = 0 meets -m_hi, k = 1 meets -m_lo)
+            *reinterpret_cast<float2*>(ones + h * 1024 + (q * 32 + lane) * 4) = make_float2(sc, sc);
+            fence_proxy_async();
+          }
         } else {
 #pragma unroll
           for (int c0 = 0; c0 < DP; c0 += 16) {
@@ -451,13 +468,32 @@ estep_umma_kernel(EstepArgs a, const uint8_t* __restrict__ Wp, const float* __re
         for (int cl = 0; cl < C::CG; ++cl)
 #pragma unroll
           for (int u = 0; u < NQ; ++u) qa[cl][u] = make_float2(0.f, 0.f);
+        if (F16 && EU_MFOLD) {
+          // y = (W^T z) 2^(sh_n + t_k): one FFMA2 undoes the scaling (exact) and subtracts m, one squares and accumulates
+          const float4* mneg = reinterpret_cast<const float4*>(stages + (size_t)s * C::STAGE + C::GB);
+          float f[C::CG];
 #pragma unroll
-        for (int j = 0; j < EU_N; j += 2) {                   // y already holds W^T z - m
-          const int cl = C::col_cl(j);                        // columns j, j+1 belong to the same component
-          const int u = (j / (8 * C::CG)) % NQ;
-          float2 r = make_float2(y[j], y[j + 1]);
-          if (F16) { const float f = rs * cs[cl]; r = __fmul2_rn(r, make_float2(f, f)); }   // 2^-(sh_n + t_k), exact
-          qa[cl][u] = __ffma2_rn(r, r, qa[cl][u]);
+          for (int cl = 0; cl < C::CG; ++cl) f[cl] = rs * cs[cl];
+#pragma unroll
+          for (int j = 0; j < EU_N; j += 4) {                 // columns j..j+3 belong to the same component
+            const int cl = C::col_cl(j);
+            const int u = (j / (8 * C::CG)) % NQ;
+            const float4 mm = EU_MFOLD == 2 ? make_float4(0.f, 0.f, 0.f, 0.f) : mneg[j >> 2];   // same address in every lane
+            const float2 ff = make_float2(f[cl], f[cl]);
+            const float2 r0 = __ffma2_rn(make_float2(y[j], y[j + 1]), ff, make_float2(mm.x, mm.y));
+            const float2 r1 = __ffma2_rn(make_float2(y[j + 2], y[j + 3]), ff, make_float2(mm.z, mm.w));
+            qa[cl][u] = __ffma2_rn(r0, r0, qa[cl][u]);
+            qa[cl][u] = __ffma2_rn(r1, r1, qa[cl][u]);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < EU_N; j += 2) {                 // y already holds W^T z - m
+            const int cl = C::col_cl(j);                      // columns j, j+1 belong to the same component
+            const int u = (j / (8 * C::CG)) % NQ;
+            float2 r = make_float2(y[j], y[j + 1]);
+            if (F16) { const float f = rs * cs[cl]; r = __fmul2_rn(r, make_float2(f, f)); }   // 2^-(sh_n + t_k), exact
+            qa[cl][u] = __ffma2_rn(r, r, qa[cl][u]);
+          }
         }
 #pragma unroll
         for (int cl = 0; cl < C::CG; ++cl) {

@@ -202,7 +202,7 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant_
     // one arrival per worker warp; in a pair the leader's bfull / dempty collect both CTAs' warps
     for (int s = 0; s < GU_NR; ++s) { mbar_init(&S->rfull[s], 1); mbar_init(&S->rempty[s], 8); }
     for (int s = 0; s < GU_NSTG; ++s) { mbar_init(&S->bfull[s], PAIR ? 16 : 8); mbar_init(&S->bempty[s], 1); }
-    mbar_init(&S->dfull, 1); mbar_init(&S->dempty, PAIR ? 16 : 8);
+    mbar_init(&S->dfull, 1); mbar_init(&S->dempty, PAIR ? 32 : 16);
     S->consts[0] = 1.f; S->consts[1] = 0.f;
     fence_barrier_init();
   }
@@ -329,12 +329,49 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant_
 #pragma unroll
     for (int i = 0; i < GU_NSTG; ++i) bfull_addr[i] = PAIR ? mapa_u32(&S->bfull[i], 0) : smem_u32(&S->bfull[i]);
     const uint32_t dempty_addr = PAIR ? mapa_u32(&S->dempty, 0) : smem_u32(&S->dempty);
+    // ---- fold D1 into D2 (or, for the last block, write D1 + D2 to this split's partial).  BOTH worker sets fold every
+    // block, a quarter of the columns per warp, and each set first generates its next chunk: the fold can only start when
+    // the block's last MMAs have completed, one chunk time after its last operands were published, so that chunk is
+    // free — and when the fold ends the first two chunks of the next block are already waiting for the MMA warp.
+    // (One set folding all columns right behind its last chunk left the tensor pipe idle for the fold plus the
+    // generation of the chunk after it: ~11 % of the kernel.)  Every set observes every phase of dfull in order, and
+    // phase b + 1 cannot complete before all warps arrived on dempty for block b, so the parity wait is unambiguous.
+    const int nblocks = (nchunks + FL - 1) >> fls;
+    auto fold = [&](int b) {
+      mbar_wait(&S->dfull, (uint32_t)b & 1u);
+      tc_fence_after();
+      const bool firstf = (b == 0), last = (b == nblocks - 1);
+      constexpr int QW = (GU_NPMAX / 4 + 15) / 16 * 16;
+      const int cbeg = (2 * sh + set) * QW, cend = min(cbeg + QW, NPB);
+      float* prow = a.part + ((size_t)split * a.Kp + (size_t)cb * GU_CB + comp) * a.PP + (size_t)poff;
+      for (int c0 = cbeg; c0 < cend; c0 += 16) {
+        float v1[16], v2[16];
+        tmem_ld16(tm + lane_base + c0, v1);
+        if (!firstf) tmem_ld16(tm + lane_base + GU_NPMAX + c0, v2);
+        tmem_wait_ld();
+        if (!firstf) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v1[j] += v2[j];
+        }
+        if (last) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4)
+            *reinterpret_cast<float4*>(prow + c0 + j) = make_float4(v1[j], v1[j + 1], v1[j + 2], v1[j + 3]);
+        } else {
+          tmem_st16(tm + lane_base + GU_NPMAX + c0, reinterpret_cast<const uint32_t*>(v1));
+        }
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(dempty_addr);
+    };
+    int nf = 0;                                            // next block this set folds
     int s = set;                                           // raw ring position of chunk c (nr >= 2): slot, lap parity
     uint32_t rph = 0;
     for (int c = set; c < nchunks; c += 2, s += 2) {
       if (s >= nr) { s -= nr; rph ^= 1u; }
       const int st = c % GU_NSTG;
-      const int nflush = c >> fls;
       mbar_wait(&S->rfull[s], rph);
       mbar_wait(&S->bempty[st], ((c / GU_NSTG) & 1) ^ 1);
       tc_fence_after();
@@ -443,39 +480,10 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant_
         mbar_arrive_cluster(ba);
       }
 
-      const bool last = (c == nchunks - 1);
-      if (((c + 1) & (FL - 1)) == 0 || last) {
-        // ---- fold D1 into D2 (or, at the end, write D1 + D2 to this split's partial)
-        // a parity wait is only unambiguous one phase ahead: when the last block is 1-2 chunks long this set may not
-        // have seen the previous block's completion yet (the other set folded it), so observe that phase first
-        if (nflush > 0) mbar_wait(&S->dfull, (nflush - 1) & 1);
-        mbar_wait(&S->dfull, nflush & 1);
-        tc_fence_after();
-        const bool firstf = (nflush == 0);
-        float* prow = a.part + ((size_t)split * a.Kp + (size_t)cb * GU_CB + comp) * a.PP + (size_t)poff;
-        for (int c0 = sh * (GU_NPMAX / 2); c0 < (sh + 1) * (GU_NPMAX / 2) && c0 < NPB; c0 += 16) {
-          float v1[16], v2[16];
-          tmem_ld16(tm + lane_base + c0, v1);
-          if (!firstf) tmem_ld16(tm + lane_base + GU_NPMAX + c0, v2);
-          tmem_wait_ld();
-          if (!firstf) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v1[j] += v2[j];
-          }
-          if (last) {
-#pragma unroll
-            for (int j = 0; j < 16; j += 4)
-              *reinterpret_cast<float4*>(prow + c0 + j) = make_float4(v1[j], v1[j + 1], v1[j + 2], v1[j + 3]);
-          } else {
-            tmem_st16(tm + lane_base + GU_NPMAX + c0, reinterpret_cast<const uint32_t*>(v1));
-          }
-        }
-        tmem_wait_st();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(dempty_addr);
-      }
+      // this set has just generated a chunk of the block after nf: fold nf
+      while (nf < nblocks - 1 && c >= ((nf + 1) << fls)) fold(nf++);
     }
+    while (nf < nblocks) fold(nf++);
     if (nchunks == 0 && set == 0) {      // empty split: contribute zeros
       float* prow = a.part + ((size_t)split * a.Kp + (size_t)cb * GU_CB + comp) * a.PP + (size_t)poff;
       for (int c0 = sh * (GU_NPMAX / 2); c0 < (sh + 1) * (GU_NPMAX / 2) && c0 < NPB; ++c0) prow[c0] = 0.f;
