@@ -22,9 +22,11 @@
 //     under the MMAs of the other.  The 8 epilogue warps (one thread per sample row) read D with tcgen05.ld, subtract m,
 //     square-reduce with packed fp32x2 FFMA2, keep an online logsumexp and write the logits.  TF32 variant: each burst
 //     starts with one TF32 MMA of a small shared-memory A block of ones against [-m_hi; -m_lo], which initialises the
-//     accumulator to -m.  fp16 variant: that MMA was 1 of the 8.5 full-width MMA slots of a burst and the kernel runs at
-//     the (power-capped) tensor-pipe rate, so -m is instead the addend of the epilogue's rescaling FFMA2, read from the
-//     stage with warp-broadcast 16-byte loads (32 shared-memory wavefronts per warp and burst).
+//     accumulator to -m; the fp16 variant does the same with the row's scale in the A block.  That MMA is 1 of the 8.5
+//     full-width MMA slots of a burst and the kernel runs at the (power-capped) tensor-pipe rate, so folding -m into the
+//     epilogue's rescaling FFMA2 instead looked like 12 % — but the values have to come from shared memory, and both
+//     ways of reading them (EU_MFOLD below) load the shared-memory pipe, which the MMAs' operand fetch already keeps
+//     busy, by more than the MMA they save.
 //   * mode 1: a 12th warp normalises tile t (p = exp(l - logZ_n), in place, L2 hits, coalesced float4, ex2.approx) while
 //     the MMAs of tile t + 1 run, keeps NA of its fixed columns in a fixed order (deterministic) and, on request, also
 //     writes the responsibilities pre-split into the Gram kernel's fp16 operand images (EstepArgs::rpack).
@@ -36,8 +38,9 @@
 //     normalisation), both EXACT; then z' = a + b and W' = A + B with a, b, A, B fp16 (a = rn(z'), b = rn(z' - a): 22
 //     significant bits, product error ~2^-22, so it is at least as accurate as the TF32 split) and the same three terms
 //     run as kind::f16 MMAs with K = 16, which issue at twice the TF32 rate and halve the operand bytes (stage 21 KB
-//     instead of 41 KB, A 64 instead of 128 TMEM columns per half).  The epilogue computes acc 2^-(sh_n + t_k) - m (the
-//     scaling is exact) before squaring, so nothing can overflow that would not overflow in the unscaled form.  Zero rows get sh = 0; sh and t are clamped to
+//     instead of 41 KB, A 64 instead of 128 TMEM columns per half).  The -m fold stays a TF32 MMA whose A block holds
+//     2^sh_n per row and whose B block holds -m 2^t_k; the epilogue multiplies by 2^-(sh_n + t_k) (exact) before squaring,
+//     so nothing can overflow that would not overflow in the unscaled form.  Zero rows get sh = 0; sh and t are clamped to
 //     +-60.  Before that, feature i of z is multiplied by 2^e_i and row i of every W_k by 2^-e_i (e_i = exponent of the
 //     largest |W_k[i][.]| over all components, estep_rowscale_kernel): the product is unchanged, and features measured in
 //     very different units (tests: 10 decades apart) all land inside the fp16 window — W's rows carry 1/sigma_i, so this
@@ -52,8 +55,13 @@ namespace vbmp {
 using namespace umma;
 
 #ifndef EU_MFOLD
-#define EU_MFOLD 0      // fp16 variant, where -m is folded in: 0 = by a TF32 MMA that initialises the accumulator,
-#endif                  // 1 = in the epilogue (broadcast shared-memory loads), 2 = nowhere (timing experiment only)
+// fp16 variant, where -m is folded in.  Measured at cfg2, in the EM loop (profiles/r02_summary.md, "E-step: where -m goes"):
+//   0 = by a TF32 MMA that initialises the accumulator                                       13.4 ms   <- built
+//   1 = in the epilogue on m16n8-style fragments (tcgen05.ld.16x256b, quad reduce-scatter)   16.1 ms
+//   (in the epilogue with one row per thread and warp-broadcast loads of all 128 values      15.3 ms)
+//   2 = nowhere (wrong results; the ceiling of any MMA-free fold)                            12.1 ms
+#define EU_MFOLD 0
+#endif
 constexpr int EU_THREADS = 384;     // warp 0: bulk-copy producer, warps 1-2: MMA issuers (one per half), warps 3..10: workers,
                                     // warp 11: normaliser (mode 1)
 constexpr int EU_TILE = 256;
@@ -442,12 +450,88 @@ estep_umma_kernel(EstepArgs a, const uint8_t* __restrict__ Wp, const float* __re
       }
       float mx = -INFINITY, sm = 0.f;
       float l4[4];
+      // the row whose logits this thread finishes, stores and normalises by: its own TMEM lane, or (EU_MFOLD == 1) the row
+      // the quad reduce-scatter leaves it with; rs4 = scales of the four rows it holds fragments of
+      constexpr bool QUAD = F16 && EU_MFOLD == 1;
+      const int rloc_o = QUAD ? h * 128 + q * 32 + 16 * ((lane >> 1) & 1) + 8 * (lane & 1) + (lane >> 2) : rloc;
+      const long long row_o = tile * EU_TILE + rloc_o;
+      const bool valid_o = row_o < a.N;
+      float rs4[4];
+#pragma unroll
+      for (int rho = 0; rho < 4; ++rho)
+        rs4[rho] = QUAD ? __shfl_sync(0xffffffffu, rs, 16 * (rho >> 1) + 8 * (rho & 1) + (lane >> 2)) : rs;
       for (int g = 0; g < ngroups; ++g, rg.next(nstage), br.next()) {
         const int s = rg.s;
         const float* cstage = reinterpret_cast<const float*>(stages + (size_t)s * C::STAGE + C::GB + C::MB);
         mbar_wait(&S->tfull[br.buf], br.ph);      // the MMAs read the stage, so its bulk copy (m, cst too) has landed
         tc_fence_after();
         const uint32_t dcol = tm + lane_base + C::DCOL0 + br.buf * EU_N;
+        // one logit: online logsumexp with one exp per component (ex2.approx: rel. error 2^-22), four logits per store
+        auto emit = [&](int c, float l, bool ok, long long orow) {
+          if (MODE == 1) {
+            const float e = exp2f(-1.44269504f * fabsf(l - mx));
+            sm = (l > mx) ? fmaf(sm, e, 1.f) : sm + e;
+            mx = fmaxf(mx, l);
+          }
+          l4[c & 3] = l;
+          if ((c & 3) == 3 && ok)
+            *reinterpret_cast<float4*>(a.out + (size_t)orow * K + (c - 3)) = make_float4(l4[0], l4[1], l4[2], l4[3]);
+        };
+        float cs[C::CG], cv[C::CG];
+        if constexpr (F16 && EU_MFOLD == 1) {
+          // ---- -m in the epilogue, accumulator read as m16n8-style fragments (tcgen05.ld.16x256b): a thread holds two
+          // columns of every 8-column block for FOUR rows, so it needs only a quarter of the group's m values — 16
+          // 8-byte loads whose four distinct addresses per warp make one shared-memory wavefront each (with one row
+          // per thread every thread needs all 128 values: 4 bytes per wavefront, ~1000 wavefronts per group, more than
+          // the MMAs' own operand fetch — measured 15.3 against 13.4 ms).  The four lanes of a quad then reduce-scatter
+          // their partial sums (3 shuffles per component) and lane t ends up owning row 16 (t/2 % 2) + 8 (t % 2) + t / 4
+          // of the warp's 32.
+          float y[EU_N];
+          tmem_ld_16x256b_x16(dcol, y);
+          tmem_ld_16x256b_x16(dcol + (16u << 16), y + 64);
+#pragma unroll
+          for (int cl = 0; cl < C::CG; ++cl) { cv[cl] = cstage[cl]; cs[cl] = cstage[8 + cl]; }
+          tmem_wait_ld();
+          tc_fence_before();
+          mbar_arrive(&S->tempty[br.buf]);
+          const float2* mneg = reinterpret_cast<const float2*>(stages + (size_t)s * C::STAGE + C::GB) + (lane & 3);
+          float2 qa[4][C::CG];
+          constexpr int NF = C::CG <= 2 ? C::CG : 1;          // scale products kept in registers (few components per group)
+          float f[4][NF];
+#pragma unroll
+          for (int rho = 0; rho < 4; ++rho) {
+#pragma unroll
+            for (int cl = 0; cl < C::CG; ++cl) qa[rho][cl] = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int cl = 0; cl < NF; ++cl) f[rho][cl] = rs4[rho] * cs[cl];
+          }
+#pragma unroll
+          for (int b = 0; b < 16; ++b) {                      // 8-column block b: component b % CG
+            const int cl = b % C::CG;
+            const float2 mm = mneg[4 * b];                    // -m of columns 8 b + 2 (lane % 4) + {0, 1}
+#pragma unroll
+            for (int rho = 0; rho < 4; ++rho) {               // row 16 (rho / 2) + 8 (rho % 2) + lane / 4
+              const int i = 64 * (rho >> 1) + 4 * b + 2 * (rho & 1);
+              // y = (W^T z) 2^(sh_n + t_k): one FFMA2 undoes the scaling (exact) and subtracts m, one squares and accumulates
+              const float ff = C::CG <= 2 ? f[rho][cl % NF] : rs4[rho] * cs[cl];
+              const float2 r = __ffma2_rn(make_float2(y[i], y[i + 1]), make_float2(ff, ff), mm);
+              qa[rho][cl] = __ffma2_rn(r, r, qa[rho][cl]);
+            }
+          }
+          const bool b0 = lane & 1, b1 = lane & 2;
+#pragma unroll
+          for (int cl = 0; cl < C::CG; ++cl) {
+            const int c = g * C::CG + cl;
+            if (c < K) {                                      // warp uniform
+              const float v0 = qa[0][cl].x + qa[0][cl].y, v1 = qa[1][cl].x + qa[1][cl].y;
+              const float v2 = qa[2][cl].x + qa[2][cl].y, v3 = qa[3][cl].x + qa[3][cl].y;
+              float ka = (b0 ? v1 : v0) + __shfl_xor_sync(0xffffffffu, b0 ? v0 : v1, 1);
+              float kb = (b0 ? v3 : v2) + __shfl_xor_sync(0xffffffffu, b0 ? v2 : v3, 1);
+              const float qq = (b1 ? kb : ka) + __shfl_xor_sync(0xffffffffu, b1 ? ka : kb, 2);
+              emit(c, cv[cl] - 0.5f * qq, valid_o, row_o);
+            }
+          }
+        } else {
         // all 128 columns into registers, then hand the accumulator straight back to the MMA warp: the arithmetic
         // below overlaps the next MMAs
         float y[EU_N];
@@ -455,7 +539,6 @@ estep_umma_kernel(EstepArgs a, const uint8_t* __restrict__ Wp, const float* __re
         tmem_ld32(dcol + 32, y + 32);
         tmem_ld32(dcol + 64, y + 64);
         tmem_ld32(dcol + 96, y + 96);
-        float cs[C::CG], cv[C::CG];
 #pragma unroll
         for (int cl = 0; cl < C::CG; ++cl) { cv[cl] = cstage[cl]; cs[cl] = cstage[8 + cl]; }
         tmem_wait_ld();
@@ -468,32 +551,13 @@ estep_umma_kernel(EstepArgs a, const uint8_t* __restrict__ Wp, const float* __re
         for (int cl = 0; cl < C::CG; ++cl)
 #pragma unroll
           for (int u = 0; u < NQ; ++u) qa[cl][u] = make_float2(0.f, 0.f);
-        if (F16 && EU_MFOLD) {
-          // y = (W^T z) 2^(sh_n + t_k): one FFMA2 undoes the scaling (exact) and subtracts m, one squares and accumulates
-          const float4* mneg = reinterpret_cast<const float4*>(stages + (size_t)s * C::STAGE + C::GB);
-          float f[C::CG];
 #pragma unroll
-          for (int cl = 0; cl < C::CG; ++cl) f[cl] = rs * cs[cl];
-#pragma unroll
-          for (int j = 0; j < EU_N; j += 4) {                 // columns j..j+3 belong to the same component
-            const int cl = C::col_cl(j);
-            const int u = (j / (8 * C::CG)) % NQ;
-            const float4 mm = EU_MFOLD == 2 ? make_float4(0.f, 0.f, 0.f, 0.f) : mneg[j >> 2];   // same address in every lane
-            const float2 ff = make_float2(f[cl], f[cl]);
-            const float2 r0 = __ffma2_rn(make_float2(y[j], y[j + 1]), ff, make_float2(mm.x, mm.y));
-            const float2 r1 = __ffma2_rn(make_float2(y[j + 2], y[j + 3]), ff, make_float2(mm.z, mm.w));
-            qa[cl][u] = __ffma2_rn(r0, r0, qa[cl][u]);
-            qa[cl][u] = __ffma2_rn(r1, r1, qa[cl][u]);
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < EU_N; j += 2) {                 // y already holds W^T z - m
-            const int cl = C::col_cl(j);                      // columns j, j+1 belong to the same component
-            const int u = (j / (8 * C::CG)) % NQ;
-            float2 r = make_float2(y[j], y[j + 1]);
-            if (F16) { const float f = rs * cs[cl]; r = __fmul2_rn(r, make_float2(f, f)); }   // 2^-(sh_n + t_k), exact
-            qa[cl][u] = __ffma2_rn(r, r, qa[cl][u]);
-          }
+        for (int j = 0; j < EU_N; j += 2) {                   // y already holds W^T z - m (EU_MFOLD == 2: W^T z)
+          const int cl = C::col_cl(j);                        // columns j, j+1 belong to the same component
+          const int u = (j / (8 * C::CG)) % NQ;
+          float2 r = make_float2(y[j], y[j + 1]);
+          if (F16) { const float f = rs * cs[cl]; r = __fmul2_rn(r, make_float2(f, f)); }   // 2^-(sh_n + t_k), exact
+          qa[cl][u] = __ffma2_rn(r, r, qa[cl][u]);
         }
 #pragma unroll
         for (int cl = 0; cl < C::CG; ++cl) {
@@ -502,24 +566,17 @@ estep_umma_kernel(EstepArgs a, const uint8_t* __restrict__ Wp, const float* __re
             float2 qq = qa[cl][0];
 #pragma unroll
             for (int u = 1; u < NQ; ++u) qq = __fadd2_rn(qq, qa[cl][u]);
-            const float l = cv[cl] - 0.5f * (qq.x + qq.y);
-            if (MODE == 1) {          // online logsumexp with one exp per component (ex2.approx: rel. error 2^-22)
-              const float e = exp2f(-1.44269504f * fabsf(l - mx));
-              sm = (l > mx) ? fmaf(sm, e, 1.f) : sm + e;
-              mx = fmaxf(mx, l);
-            }
-            l4[c & 3] = l;
-            if ((c & 3) == 3 && valid)
-              *reinterpret_cast<float4*>(a.out + (size_t)row * K + (c - 3)) = make_float4(l4[0], l4[1], l4[2], l4[3]);
+            emit(c, cv[cl] - 0.5f * (qq.x + qq.y), valid, row);
           }
+        }
         }
         mbar_arrive(&S->empty[s]);                  // done with the stage's cst (the two MMA commits are the other arrivals)
       }
       if (MODE == 1) {
-        const float v = valid ? mx + logf(sm) : 0.f;
+        const float v = valid_o ? mx + logf(sm) : 0.f;
         if (t >= 2) mbar_wait(&S->nfree[t & 1], ((uint32_t)(t >> 1) & 1) ^ 1);    // tile t-2 has been normalised
-        lz[(t & 1) * EU_TILE + rloc] = v;
-        if (valid) { a.logZn[row] = v; lzsum += (double)v; }
+        lz[(t & 1) * EU_TILE + rloc_o] = v;
+        if (valid_o) { a.logZn[row_o] = v; lzsum += (double)v; }
         mbar_arrive(&S->ndone[t & 1]);              // release: this thread's logits and logZ_n of the tile
       }
     }

@@ -1,8 +1,5 @@
-for v in "" _mf1 _mf2; do
-  echo "== variant '$v'"
-  VBMP_LIB=$PWD/pyvbmp_b200/libvbmp_b200$v.so TK_N=4194304 TK_WHAT=e timeout 300 python tools/time_kernels.py 2>&1 | tail -2
-done
-VBMP_LIB=$PWD/pyvbmp_b200/libvbmp_b200_mf2.so timeout 600 python bench.py --steps 20 --warmup 5 2>/dev/null | python -c "
-import json,sys
-d=json.loads(sys.stdin.read().strip().splitlines()[-1])
-print('mf2 in-step', d['ms_per_step'], json.dumps(d['roofline']['kernels_ms_per_step']), d['clocks'])"
+mkdir -p gpurun_out /tmp/ncu
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"estep_umma_kernel" --launch-skip 2 -c 1 -f -o /tmp/ncu/estep python tools/prof_driver.py cfg2 3 > gpurun_out/ncu_estep.log 2>&1
+ncu -i /tmp/ncu/estep.ncu-rep --page details > gpurun_out/s3_ncu_estep_quad_details.txt 2>&1
+ncu -i /tmp/ncu/estep.ncu-rep --page source --csv > gpurun_out/s3_ncu_estep_quad_source.csv 2>&1
+grep -E "Duration|Issue Slots Busy|Executed Ipc|No Eligible|L1/TEX Hit|Mem Pipes Busy|shared" gpurun_out/s3_ncu_estep_quad_details.txt | head -20
