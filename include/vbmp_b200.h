@@ -179,6 +179,28 @@ int vbmp_hmm_forward_backward(const float* logits, const float* trans, const flo
 int vbmp_rowgemm(const float* A, int lda, const float* B, int ldb, const float* bias, float* C, int ldc,
                  long long N, int Kd, int M, int accumulate, void* stream);
 
+/* ---- per-sample covariance terms --------------------------------------------------------------------
+ * C[n][k] = (accumulate ? C[n][k] : 0) + alpha * sum_f A[n][f] B[f][k]: the trace terms of
+ * MatrixNormalWishart.Elog_like_given_pX_pY (transforms/MatrixNormalWishart.py:236-247), -1/2 tr(Sigma_y,n E[invSigma_k])
+ * and -1/2 tr(Sigma_x,n E[X^T invU X]_k), with A (N, F, row stride lda) the flattened per-sample covariances and B (F, K,
+ * row stride ldb) the flattened K-sized expectations.  tcgen05 kernel: A goes from HBM through registers into tensor
+ * memory (one pass, 3-term TF32 split), B is packed once per call.  Needs N >= 128, F >= 32, F % 4 == 0, lda % 4 == 0,
+ * K <= 256, a 16-byte aligned A; anything else returns VBMP_ERR_UNSUPPORTED (vbmp_rowgemm takes every shape).            */
+size_t vbmp_rowterm_workspace_bytes(int F, int K);
+int vbmp_rowterm(const float* A, int lda, const float* B, int ldb, float* C, int ldc, long long N, int F, int K,
+                 float alpha, int accumulate, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- responsibility-weighted column sums ------------------------------------------------------------
+ * out[K x F] = sum_n p[n][k] S[n][f]: the weighted sums of the flattened input / output covariances in
+ * MatrixNormalWishart.update(pX, pY, p) (transforms/MatrixNormalWishart.py:150-156, SExx = (pX.EXXT() * p).sum(0) etc.; the
+ * mean parts go through vbmp_gram).  p (N, K) and S (N, F, row stride lds floats) row-major fp32; the reduction runs over
+ * the sample axis on the tcgen05 Gram kernel (3-term TF32 split, two-level accumulation, fixed-order fp64 reduce over the
+ * sample splits: bit-reproducible).  Needs N >= 2048, K % 4 == 0, lds % 4 == 0, 16-byte aligned bases; anything else
+ * returns VBMP_ERR_UNSUPPORTED.                                                                                          */
+size_t vbmp_wsum_workspace_bytes(long long N, int K, int F);
+int vbmp_wsum(const float* p, const float* S, int lds, long long N, int K, int F, float* out, void* workspace,
+              size_t workspace_bytes, void* stream);
+
 /* ---- mixture-of-experts predictive moments -------------------------------------------------------
  * The per-sample part of MixtureofLinearTransforms.predict (transforms/MixtureofLinearTransforms.py:100-106):
  *   mu[s] = sum_k p[s,k] mean[s,k,:],   Sigma[s] = base[s] + sum_k p[s,k] mean[s,k,:] mean[s,k,:]^T - mu[s] mu[s]^T

@@ -72,6 +72,10 @@ def lib():
         L.vbmp_diag_estep_workspace_bytes.argtypes = [c_longlong, c_int, c_int, c_int, c_int]
         L.vbmp_zpack_bytes.restype = c_size_t
         L.vbmp_zpack_bytes.argtypes = [c_longlong, c_int, c_int]
+        L.vbmp_rowterm_workspace_bytes.restype = c_size_t
+        L.vbmp_rowterm_workspace_bytes.argtypes = [c_int, c_int]
+        L.vbmp_wsum_workspace_bytes.restype = c_size_t
+        L.vbmp_wsum_workspace_bytes.argtypes = [c_longlong, c_int, c_int]
         _lib = L
     return _lib
 
@@ -83,6 +87,7 @@ EXPORTS = (
     "vbmp_hmm_forward_backward", "vbmp_rpack_bytes", "vbmp_estep_rpack", "vbmp_gram_rpack",
     "vbmp_zpack_bytes", "vbmp_gram_zpack", "vbmp_gram_ex_workspace_bytes", "vbmp_gram_ex",
     "vbmp_diag_estep_workspace_bytes", "vbmp_diag_estep", "vbmp_diag_estep_rpack", "vbmp_mnw_prep_ex", "vbmp_moe_moments", "vbmp_rowgemm",
+    "vbmp_wsum_workspace_bytes", "vbmp_wsum", "vbmp_rowterm_workspace_bytes", "vbmp_rowterm",
 )
 
 
@@ -496,6 +501,48 @@ def rowgemm(A, B, bias=None, out=None, accumulate=False):
     _call("vbmp_rowgemm", dev, c_void_p(A.data_ptr()), c_int(A.stride(0)), c_void_p(B.data_ptr()), c_int(B.stride(0)), _ptr(bias),
           c_void_p(out.data_ptr()), c_int(out.stride(0)), c_longlong(N), c_int(Kd), c_int(M), c_int(int(bool(accumulate))),
           _stream(dev))
+    return out
+
+
+def rowterm_supported(N, F, K, lda):
+    return N >= 128 and F >= 32 and F % 4 == 0 and lda % 4 == 0 and lda >= F and 1 <= K <= 256
+
+
+def rowterm(A, B, C=None, alpha=1.0, accumulate=False):
+    """C (N, K) = (accumulate ? C : 0) + alpha * A (N, F) @ B (F, K) for a long reduction F and few columns K (vbmp_rowterm:
+    tcgen05, A through registers into tensor memory).  A may be row-strided; C is written in place when given."""
+    dev = A.device
+    N, F = A.shape
+    K = B.shape[1]
+    assert B.shape[0] == F and A.stride(1) == 1 and B.stride(1) == 1 and A.dtype == torch.float32 and B.dtype == torch.float32
+    if C is None:
+        assert not accumulate
+        C = torch.empty((N, K), dtype=torch.float32, device=dev)
+    assert C.shape == (N, K) and C.stride(1) == 1 and C.dtype == torch.float32
+    nbytes = lib().vbmp_rowterm_workspace_bytes(c_int(F), c_int(K))
+    ws = _workspace(nbytes, dev)
+    _call("vbmp_rowterm", dev, c_void_p(A.data_ptr()), c_int(A.stride(0)), c_void_p(B.data_ptr()), c_int(B.stride(0)),
+          c_void_p(C.data_ptr()), c_int(C.stride(0)), c_longlong(N), c_int(F), c_int(K), ctypes.c_float(alpha),
+          c_int(int(bool(accumulate))), _ptr(ws), c_size_t(ws.numel()), _stream(dev))
+    return C
+
+
+def wsum_supported(N, K, F, lds):
+    return N >= 2048 and K >= 4 and K % 4 == 0 and F >= 16 and lds % 4 == 0 and lds >= F
+
+
+def wsum(p, S):
+    """out (K, F) = p (N, K)^T @ S (N, F): responsibility-weighted column sums over the sample axis (vbmp_wsum)."""
+    dev = S.device
+    N, K = p.shape
+    F = S.shape[1]
+    assert S.shape[0] == N and p.is_contiguous() and S.stride(1) == 1
+    out = torch.empty((K, F), dtype=torch.float32, device=dev)
+    nbytes = lib().vbmp_wsum_workspace_bytes(c_longlong(N), c_int(K), c_int(F))
+    ws = _workspace(nbytes, dev)
+    assert S.is_cuda and S.dtype == torch.float32 and p.dtype == torch.float32
+    _call("vbmp_wsum", dev, _ptr(p), c_void_p(S.data_ptr()), c_int(S.stride(0)), c_longlong(N), c_int(K), c_int(F), _ptr(out), _ptr(ws),
+          c_size_t(ws.numel()), _stream(dev))
     return out
 
 

@@ -66,6 +66,14 @@ int launch_moe_moments(const float* mean, const float* p, const float* base, lon
                        cudaStream_t st);
 int launch_rowgemm(const float* A, int lda, const float* B, int ldb, const float* bias, float* C, int ldc, long long N, int Kd,
                    int M, int accumulate, cudaStream_t st);
+bool rowterm_umma_supported(long long N, int F, int K, int lda);
+size_t rowterm_umma_workspace_bytes(int F, int K);
+int launch_rowterm_umma(const float* A, int lda, const float* B, int ldb, float* C, int ldc, long long N, int F, int K,
+                        float alpha, int accumulate, void* ws, size_t ws_bytes, cudaStream_t st);
+bool wsum_umma_supported(long long N, int K, int F, int lds);
+size_t wsum_umma_workspace_bytes(long long N, int K, int F);
+int launch_wsum_umma(const float* p, const float* S, int lds, long long N, int K, int F, float* out, void* ws, size_t ws_bytes,
+                     cudaStream_t st);
 bool gram_rpack_usable();
 bool estep_umma_can_pack(long long N, int GX, int G, int K, int Dp, int d0, int d1, int mode);
 size_t gram_rpack_bytes(long long N, int K);
@@ -355,6 +363,22 @@ int vbmp_rowgemm(const float* A, int lda, const float* B, int ldb, const float* 
                  long long N, int Kd, int M, int accumulate, void* stream) {
   if (!A || !B || !C) { set_error("rowgemm: NULL argument"); return VBMP_ERR_SHAPE; }
   return launch_rowgemm(A, lda, B, ldb, bias, C, ldc, N, Kd, M, accumulate, (cudaStream_t)stream);
+}
+
+size_t vbmp_rowterm_workspace_bytes(int F, int K) { return rowterm_umma_workspace_bytes(F, K); }
+
+int vbmp_rowterm(const float* A, int lda, const float* B, int ldb, float* C, int ldc, long long N, int F, int K,
+                 float alpha, int accumulate, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!A || !B || !C) { set_error("rowterm: NULL argument"); return VBMP_ERR_SHAPE; }
+  return launch_rowterm_umma(A, lda, B, ldb, C, ldc, N, F, K, alpha, accumulate, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+size_t vbmp_wsum_workspace_bytes(long long N, int K, int F) { return wsum_umma_workspace_bytes(N, K, F); }
+
+int vbmp_wsum(const float* p, const float* S, int lds, long long N, int K, int F, float* out, void* workspace,
+              size_t workspace_bytes, void* stream) {
+  if (!p || !S || !out) { set_error("wsum: NULL argument"); return VBMP_ERR_SHAPE; }
+  return launch_wsum_umma(p, S, lds, N, K, F, out, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 int vbmp_hmm_forward_backward(const float* logits, const float* trans, const float* init, int T, long long S, int G, int K,

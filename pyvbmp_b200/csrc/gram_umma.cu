@@ -74,6 +74,8 @@ struct GuArgs {
   int npb, NPB, P, ncb, splits;      // pair blocks, pair columns of the widest block, total pairs, component blocks, sample splits
   int nr;                            // raw ring slots in use, 2 <= nr <= GU_NR
   int diag;                          // 1: only the pairs (i, i) and (i, D) — the statistics of the diagonal-precision nodes
+  int lin;                           // 1: "pair" p is column p of z0 itself (phi = z0[n][p]): weighted column sums, see launch_wsum_umma
+  int zw;                            // TF32 variant: floats per row of the z0 box in the raw ring (d0; lin: the widest column block)
   int wbase, wextra;                 // block pb holds 16 (wbase + (pb < wextra)) pair columns starting at 16 (pb wbase + min(pb, wextra))
   long long S_per;                   // samples per split (multiple of GU_SC)
   int Kp, PP;                        // padded partial dims: Kp = ncb*128, PP = P rounded up to 16
@@ -170,7 +172,7 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant_
   const int D = a.d0 + a.d1;
   // carve: raw ring [NR][R 16 x kcb floats | Z0 16 x d0 | Z1 16 x d1], B stages [2][hi NPB*64 B | lo NPB*64 B]
   const int kcb = R128 ? 128 : a.kcb;
-  const int rawR = F16 ? 2 * GU_RREC : SC * kcb * 4, rawZ0 = F16 ? a.zrec : SC * a.d0 * 4, rawZ1 = F16 ? 0 : SC * a.d1 * 4;
+  const int rawR = F16 ? 2 * GU_RREC : SC * kcb * 4, rawZ0 = F16 ? a.zrec : SC * a.zw * 4, rawZ1 = F16 ? 0 : SC * a.d1 * 4;
   const int rawB = (rawR + rawZ0 + rawZ1 + 127) / 128 * 128;
   constexpr int GU_NSTG = gu_nstg(PAIR), GU_NPMAX = gu_npmax(PAIR);
   const int stageB = 2 * (PAIR ? a.NPB / 2 : a.NPB) * 64;    // sized for a full-width pair block
@@ -231,7 +233,7 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant_
           bulk_g2s(dst + rawR, a.zt + (size_t)(r0 >> 5) * a.zrec, (uint32_t)a.zrec, &S->rfull[s]);
         } else {
           tma_load_2d(dst, &tmR, cb * GU_CB, r0, &S->rfull[s]);
-          tma_load_2d(dst + rawR, &tmZ0, 0, r0, &S->rfull[s]);
+          tma_load_2d(dst + rawR, &tmZ0, a.lin ? poff : 0, r0, &S->rfull[s]);    // lin: only this block's columns
           if (a.d1 > 0) tma_load_2d(dst + rawR + rawZ0, &tmZ1, 0, r0, &S->rfull[s]);
         }
       }
@@ -308,7 +310,7 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant_
       const int pg_ = poff + (int)rank * NH + pslot;
       const bool pair_ok = gen && (pg_ < a.P);
       int pi = 0, pj = 0;
-      if (pair_ok) gu_pair_any(pg_, D, a.diag, &pi, &pj);
+      if (pair_ok && !a.lin) gu_pair_any(pg_, D, a.diag, &pi, &pj);
       auto setup = [&](int f, const uint8_t*& b, int& sl, int& stv) {
         if (!pair_ok) { b = reinterpret_cast<const uint8_t*>(&S->consts[1]); sl = 0; stv = 0; }
         else if (f < a.d0) { b = raw + rawR + f * 4; sl = rawB; stv = a.d0 * 4; }
@@ -317,6 +319,10 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant_
       };
       setup(pi, bi, sli, sti);
       setup(pj, bj, slj, stj);
+      if (!F16 && a.lin) {       // weighted column sums: phi = z0[n][column] * 1, the box holds this block's columns only
+        if (pair_ok) { bi = raw + rawR + ((int)rank * NH + pslot) * 4; sli = rawB; sti = a.zw * 4; }
+        bj = reinterpret_cast<const uint8_t*>(&S->consts[pair_ok ? 0 : 1]); slj = 0; stj = 0;
+      }
       plain = SF > 0 && __all_sync(0xffffffffu, pair_ok && pj < D);
       if (F16) {       // transposed, pre-scaled chunk: row f of the record; padding pairs read the zero row D + 1
         bi = raw + rawR + (pair_ok ? pi : D + 1) * (GU_ZS * 4); sli = rawB;
@@ -883,10 +889,11 @@ static bool gu_pair_mode(int K) {
   return pair_ok && (((K + GU_CB - 1) / GU_CB) % 2 == 0);     // CTA pairs share the phi block (cta_group::2)
 }
 
-static void gu_plan(long long N, int K, int D, int sms, GuArgs* g, int diag = 0) {
+static void gu_plan(long long N, int K, int D, int sms, GuArgs* g, int diag = 0, int lin_cols = 0) {
   const int GU_NPMAX = gu_npmax(gu_pair_mode(K));
   g->diag = diag;
-  g->P = gu_npairs(D, diag);
+  g->lin = lin_cols > 0;
+  g->P = lin_cols > 0 ? lin_cols : gu_npairs(D, diag);
   static const int npb_cap = [] { const char* e = getenv("VBMP_GRAM_NPB"); return e ? atoi(e) : 0; }();   // tuning: pair columns per block
   const int npmax = (npb_cap >= 16 && npb_cap <= GU_NPMAX) ? npb_cap / 16 * 16 : GU_NPMAX;
   // 16-column units dealt out evenly: the first wextra blocks are one unit wider than the rest
@@ -1002,19 +1009,21 @@ static int gu_fl() {
   return fl;
 }
 
+// lin_lds > 0 (TF32 variant only): weighted column sums of z0 (N, d0) with row stride lin_lds, see launch_wsum_umma
 template <bool F16>
-static int gu_launch_main(const GramArgs& a, GuArgs g, bool pair, cudaStream_t st) {
+static int gu_launch_main(const GramArgs& a, GuArgs g, bool pair, cudaStream_t st, int lin_lds = 0) {
   constexpr int SC = gu_sc(F16);
   const int D = a.d0 + a.d1;
   (void)D;
+  g.zw = lin_lds > 0 ? g.NPB : a.d0;
   CUtensorMap tmR, tmZ0, tmZ1;
   int e = make_tmap_2d(&tmR, a.p, (uint64_t)a.K, (uint64_t)a.N, (uint64_t)a.K, (uint32_t)g.kcb, SC);
-  if (!e) e = make_tmap_2d(&tmZ0, a.z0, (uint64_t)a.d0, (uint64_t)a.N, (uint64_t)a.d0, (uint32_t)a.d0, SC);
+  if (!e) e = make_tmap_2d(&tmZ0, a.z0, (uint64_t)a.d0, (uint64_t)a.N, (uint64_t)(lin_lds > 0 ? lin_lds : a.d0), (uint32_t)g.zw, SC);
   if (!e && a.d1 > 0) e = make_tmap_2d(&tmZ1, a.z1, (uint64_t)a.d1, (uint64_t)a.N, (uint64_t)a.d1, (uint32_t)a.d1, SC);
   if (a.d1 == 0) tmZ1 = tmZ0;
   if (e) { set_error("gram_umma: cuTensorMapEncodeTiled failed (%d)", e); return VBMP_ERR_CUDA; }
   const int NH = pair ? g.NPB / 2 : g.NPB;
-  const int rawB = (F16 ? 2 * GU_RREC + g.zrec : SC * g.kcb * 4 + SC * a.d0 * 4 + SC * a.d1 * 4) / 128 * 128 + 128;
+  const int rawB = (F16 ? 2 * GU_RREC + g.zrec : SC * g.kcb * 4 + SC * g.zw * 4 + SC * a.d1 * 4) / 128 * 128 + 128;
   const size_t stages = (size_t)gu_nstg(pair) * 2 * NH * 64 + sizeof(GuSmem) + 64;
   int nr = (int)((227 * 1024 - stages) / rawB);
   if (nr > GU_NR) nr = GU_NR;
@@ -1023,7 +1032,7 @@ static int gu_launch_main(const GramArgs& a, GuArgs g, bool pair, cudaStream_t s
   const size_t smem = (size_t)nr * rawB + stages;
   const int grid = g.splits * g.ncb * g.npb;
   const bool same = (a.d1 == 0 || a.d1 == a.d0);
-  const int sf = same && (a.d0 == 64 || a.d0 == 32 || a.d0 == 16) ? a.d0 : 0;
+  const int sf = same && lin_lds == 0 && (a.d0 == 64 || a.d0 == 32 || a.d0 == 16) ? a.d0 : 0;
   const bool r128 = g.kcb == GU_CB;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)grid);
@@ -1171,6 +1180,60 @@ int launch_gram_umma(const GramArgs& a, float* gram, void* ws, size_t ws_bytes, 
   if (rc) return rc;
   gram_pair_reduce_kernel<2><<<rgrid, 256, 0, st>>>(g.part, g.splits, a.K, g.Kp, g.PP, D1, nullptr, flag, gram, g.diag);
   return check_launch("gram_pair_reduce2");
+}
+
+
+// ---- weighted column sums  C[k][f] = sum_n p[n][k] S[n][f]  (K x N)(N x F), reduction over the SAMPLE axis ---------------
+// The responsibility-weighted sums of flattened covariances in MatrixNormalWishart.update(pX, pY, p)
+// (transforms/MatrixNormalWishart.py:150-156: SExx += sum_n p E[xx^T]_n; F = p^2 or n^2 columns, thousands).  This is the
+// Gram contraction with phi_n[f] = S[n][f] instead of a product of two features, so it runs on gram_umma_kernel's TF32
+// variant in "lin" mode: the column blocks take the place of the pair blocks, each CTA's TMA box covers only its block's
+// columns (S is read from HBM once), the weights come through the same box / TMEM path, the two-level accumulation and the
+// fixed-order fp64 reduce over the sample splits are shared.  TF32 operands (3-term split): S has no scale structure to
+// exploit and the call is bound by the bytes of S.
+__global__ void wsum_reduce_kernel(const float* __restrict__ part, int splits, int K, int Kp, int PP, int F, float* __restrict__ out) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (long long)K * F) return;
+  const int k = (int)(e / F), f = (int)(e % F);
+  double acc = 0.0;
+  for (int s = 0; s < splits; ++s) acc += (double)part[((size_t)s * Kp + k) * PP + f];
+  out[e] = (float)acc;
+}
+
+bool wsum_umma_supported(long long N, int K, int F, int lds) {
+  return N >= 2048 && K >= 4 && (K % 4 == 0) && F >= 16 && (lds % 4 == 0) && lds >= F;
+}
+static void wsum_plan(long long N, int K, int F, GuArgs* g) {
+  g->d0 = F; g->d1 = 0; g->N = N; g->K = K;
+  gu_plan(N, K, 0, gu_num_sms(), g, 0, F);
+  g->kcb = K < GU_CB ? K : GU_CB;
+  g->FL = gu_fl();
+  g->flag = nullptr; g->cmax = nullptr;
+}
+size_t wsum_umma_workspace_bytes(long long N, int K, int F) {
+  GuArgs g{};
+  wsum_plan(N, K, F, &g);
+  return 512 + gu_al((size_t)g.splits * g.Kp * g.PP * sizeof(float));
+}
+int launch_wsum_umma(const float* p, const float* S, int lds, long long N, int K, int F, float* out, void* ws, size_t ws_bytes,
+                     cudaStream_t st) {
+  if (!wsum_umma_supported(N, K, F, lds) || ((size_t)S % 16) || ((size_t)p % 16)) {
+    set_error("wsum: unsupported shape N=%lld K=%d F=%d lds=%d (needs N >= 2048, K %% 4 == 0, lds %% 4 == 0, 16-byte aligned bases)",
+              N, K, F, lds);
+    return VBMP_ERR_UNSUPPORTED;
+  }
+  const size_t need = wsum_umma_workspace_bytes(N, K, F);
+  if (ws_bytes < need) { set_error("wsum: workspace too small (%zu < %zu)", ws_bytes, need); return VBMP_ERR_WORKSPACE; }
+  GuArgs g{};
+  wsum_plan(N, K, F, &g);
+  g.part = (float*)gu_al((size_t)ws);
+  GramArgs a{};
+  a.z0 = S; a.z1 = nullptr; a.d0 = F; a.d1 = 0; a.N = N; a.GX = 1; a.p = p; a.GP = 1; a.G = 1; a.K = K; a.Dp = 0;
+  int rc = gu_launch_main<false>(a, g, gu_pair_mode(K), st, lds);
+  if (rc) return rc;
+  const long long tot = (long long)K * F;
+  wsum_reduce_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(g.part, g.splits, K, g.Kp, g.PP, F, out);
+  return check_launch("wsum_reduce");
 }
 
 }  // namespace vbmp

@@ -218,10 +218,16 @@ class MatrixNormalWishart():
         N = 1
         for v in sample:
             N *= v
-        # a point mass (dists/Delta.py: no ESigma) contributes no covariance term
-        Sx = pX.ESigma().expand(sample + (1, p_in, p_in)).reshape(N, p_in * p_in) if hasattr(pX, "ESigma") else None
-        Sy = pY.ESigma().expand(sample + (1, self.n, self.n)).reshape(N, self.n * self.n) if hasattr(pY, "ESigma") else None
-        return N, sample, mx, my, Sx, Sy
+        # a point mass (dists/Delta.py: no ESigma) contributes no covariance term; a covariance shared by all samples
+        # stays one row (its weighted sum is NA_k Sigma, its trace term one K-vector) instead of N copies
+        def flat(b, d):
+            if not hasattr(b, "ESigma"):
+                return None
+            S = b.ESigma()
+            if S.numel() == d * d:
+                return S.reshape(1, d * d)
+            return S.expand(sample + (1, d, d)).reshape(N, d * d)
+        return N, sample, mx, my, flat(pX, p_in), flat(pY, self.n)
 
     def update(self, pX, pY, p=None, lr=1.0, beta=None):
         """transforms/MatrixNormalWishart.py:143-172: M-step from Gaussian beliefs about inputs and outputs.
@@ -238,10 +244,19 @@ class MatrixNormalWishart():
                 D = p_in + n
                 P2 = _lib.f32(p, self.mu.device).reshape(N, K)
                 Gk = G.view(K, D + 1, D + 1)
+                # sum_n p[n,k] Sigma_n: (K x N) (N x p^2) over the sample axis (vbmp_wsum, the Gram kernel's "lin" mode);
+                # shapes outside its window (tiny N, K % 4 != 0) are K-sized-output matmuls on the device
+                def wsum(Sf):
+                    Sf = _lib.f32(Sf)
+                    if Sf.shape[0] == 1 and N > 1:
+                        return P2.sum(0)[:, None] * Sf
+                    if _lib.wsum_supported(N, K, Sf.shape[1], Sf.stride(0)) and Sf.data_ptr() % 16 == 0:
+                        return _lib.wsum(P2, Sf)
+                    return P2.t() @ Sf
                 if Sx is not None:
-                    Gk[:, :p_in, :p_in] += (P2.t() @ Sx).view(K, p_in, p_in)
+                    Gk[:, :p_in, :p_in] += wsum(Sx).view(K, p_in, p_in)
                 if Sy is not None:
-                    Gk[:, p_in:D, p_in:D] += (P2.t() @ Sy).view(K, n, n)
+                    Gk[:, p_in:D, p_in:D] += wsum(Sy).view(K, n, n)
                 self._update_from_gram(G, plan, p is not None, lr, beta)
                 return
         # any other layout: the reference's op order on torch
@@ -275,17 +290,27 @@ class MatrixNormalWishart():
         if bp is not None and self.event_dim == 2:
             N, sample, mx, my, Sx, Sy = bp
             K = self.batch_shape[0]
-            # tr(Sigma_y E[invSigma_k]) + tr(Sigma_x E[X^T invU X]_k): two (N x n^2) (n^2 x K) products (vbmp_rowgemm)
-            corr = None
+            # tr(Sigma_y E[invSigma_k]) + tr(Sigma_x E[X^T invU X]_k): two (N x n^2) (n^2 x K) products (vbmp_rowterm;
+            # vbmp_rowgemm for the shapes outside its window)
+            corr = {}                          # per-sample rows (N, K) and / or one row shared by all samples (1, K)
+            base2d = base.view(N, K) if base.is_contiguous() else None
+            def add(Sf, Lm):
+                nonlocal base2d
+                Sf, Lm = _lib.f32(Sf), _lib.f32(Lm.reshape(K, -1).t().contiguous())
+                key = "shared" if (Sf.shape[0] == 1 and N > 1) else "rows"
+                if key == "rows" and base2d is not None and _lib.rowterm_supported(N, Sf.shape[1], K, Sf.stride(0)):
+                    _lib.rowterm(Sf, Lm, C=base2d, alpha=-0.5, accumulate=True)      # base -= 1/2 Sf Lm, in place (tcgen05)
+                    return
+                corr[key] = _lib.rowgemm(Sf, Lm, out=corr.get(key), accumulate=key in corr)
             if Sy is not None:
-                Ly = self.EinvSigma().expand(K, self.n, self.n).reshape(K, -1).t().contiguous()
-                corr = _lib.rowgemm(_lib.f32(Sy), _lib.f32(Ly))
+                add(Sy, self.EinvSigma().expand(K, self.n, self.n))
             if Sx is not None:
-                Lx = Exx.expand(K, p_in, p_in).reshape(K, -1).t().contiguous()
-                corr = _lib.rowgemm(_lib.f32(Sx), _lib.f32(Lx), out=corr, accumulate=corr is not None)
-            if corr is None:
-                return base
-            return base - 0.5 * corr.view(sample + (K,))
+                add(Sx, Exx.expand(K, p_in, p_in))
+            if "rows" in corr:
+                base = base - 0.5 * corr["rows"].view(sample + (K,))
+            if "shared" in corr:
+                base = base - 0.5 * corr["shared"].view(len(sample) * (1,) + (K,))
+            return base
         corr = 0.0
         if hasattr(pY, "ESigma"):
             corr = corr + (pY.ESigma() * self.EinvSigma()).sum(-1).sum(-1)

@@ -188,3 +188,39 @@ def test_wishart_standalone_update_and_kl():
     assert_close(w2.invU_0, sc ** 2 * torch.eye(d), 1e-7, "invU_0 per-component scale")
     assert_close(w2.logdet_invU_0, (sc ** 2 * torch.eye(d)).logdet(), 1e-5, "logdet_invU_0 per-component scale")
     assert_close(w2.U, (sc ** 2 * torch.eye(d)).inverse(), 1e-6, "U per-component scale")
+
+
+def test_molt_update_given_beliefs_vs_fp64_oracle():
+    """Expectation-input E and M steps at a shape inside the kernels' windows: MoLT n = p = 16, K = 8,
+    N = 8192 with per-sample Gaussian beliefs about inputs and outputs.  Elog_like_given_pX_pY runs K1 + K2 on the means
+    plus vbmp_rowterm on the flattened covariances; update(pX, pY) runs K3 on the means plus vbmp_wsum (the Gram kernel's
+    "lin" mode) on the covariances.  Against the fp64 oracle, two step-wise iterations."""
+    N, n, p, K = 8192, 16, 16, 8
+    X, Y = _cfg3_data(N, n, p, K, seed=21)
+    g = torch.Generator().manual_seed(22)
+    Ax = 0.2 * torch.randn(N, p, p, generator=g)
+    Ay = 0.2 * torch.randn(N, n, n, generator=g)
+    Sx = Ax @ Ax.transpose(-1, -2) + 0.05 * torch.eye(p)
+    Sy = Ay @ Ay.transpose(-1, -2) + 0.05 * torch.eye(n)
+    torch.manual_seed(6)
+    m = V.MixtureofLinearTransforms(n, p, K)
+    ref = O.molt_new(n, p, K)
+    O.load_state(ref, {"W.mu": m.W.mu.clone(), "pi.alpha": m.pi.alpha.clone()})
+    O.to_dtype(ref, torch.float64)
+    m.to(DEV)
+    pX = V.MultivariateNormal_vector_format(mu=X.to(DEV), Sigma=Sx.to(DEV))
+    pY = V.MultivariateNormal_vector_format(mu=Y.to(DEV), Sigma=Sy.to(DEV))
+    from pyvbmp_b200 import _lib
+    for it in range(2):
+        set_state(m, {k: v.float() for k, v in O.flatten_state(ref).items()})
+        _lib.profile_begin(64)
+        m.update(pX, pY, iters=1)
+        prof = _lib.profile_end()
+        assert "vbmp_wsum" in prof and "vbmp_rowterm" in prof, sorted(prof)      # the kernels ran, not the torch branch
+        elbo = O.molt_update_given(ref, X.double(), Sx.double(), Y.double(), Sy.double())
+        assert abs(float(m.ELBO_last) - float(elbo)) <= PARITY * abs(float(elbo)), it
+        assert_maxabs(m.p.cpu().double(), ref["p"], 2e-4 if it == 0 else 2e-5, f"p it{it}")
+        assert_close(m.logZ, ref["logZ"], PARITY, f"logZ_n it{it}")
+        flat = O.flatten_state(ref)
+        for k in MOLT_STATE:
+            assert_close(get(m, k), flat[k], 3e-4 if it == 0 else PARITY, f"{k} it{it}")

@@ -418,3 +418,41 @@ def test_rowgemm_kernel(N, Kd, M, bias, acc):
         ref2 = wide[:, 4:4 + Kd].double() @ B.double()
         assert float((out2[:, :M].double() - ref2).abs().max()) <= 2e-6 * float((wide.abs().double()[:, 4:4 + Kd] @ B.abs().double()).max())
         assert float(out2[:, M:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("N,K,F,lds", [(5000, 64, 1024, 1024), (4100, 256, 100, 128), (2048, 8, 16, 16), (70000, 32, 289, 292),
+                                       (3000, 128, 1089, 1092)])
+def test_wsum_kernel(N, K, F, lds):
+    """vbmp_wsum (weighted column sums over the sample axis on the Gram kernel's "lin" mode, TF32 split) against an fp64
+    product: fp32-grade accuracy per entry, column blocks that do not fill the last TMA box, a row stride wider than F,
+    and bit-reproducibility."""
+    g = torch.Generator(device=DEV).manual_seed(N + K + F)
+    p = torch.softmax(3.0 * torch.randn(N, K, generator=g, device=DEV), dim=-1)
+    wide = torch.randn(N, lds, generator=g, device=DEV) * 1.3 + 0.5
+    S = wide[:, :F]
+    assert _lib.wsum_supported(N, K, F, S.stride(0))
+    out = _lib.wsum(p, S)
+    ref = p.double().t() @ S.double()
+    scale = p.double().t() @ S.abs().double()                  # per entry: what the products could add up to
+    assert float(((out.double() - ref).abs() / scale).max()) <= 4e-6
+    assert torch.equal(out, _lib.wsum(p, S))
+
+
+@pytest.mark.parametrize("N,F,K,lda,acc", [(5000, 1024, 64, 1024, True), (4100, 256, 8, 256, False), (129, 36, 5, 40, True),
+                                           (70000, 1024, 32, 1024, False), (3000, 100, 200, 104, True), (20000, 32, 64, 32, False)])
+def test_rowterm_kernel(N, F, K, lda, acc):
+    """vbmp_rowterm (tcgen05: A from HBM through registers into tensor memory, 3-term TF32 split) against an fp64 product:
+    fp32-grade accuracy, a ragged last row tile, feature counts that do not fill the last chunk, K that is not a multiple of
+    16, a row-strided A, alpha and accumulation."""
+    g = torch.Generator(device=DEV).manual_seed(N + F + K)
+    wide = torch.randn(N, lda, generator=g, device=DEV) * 1.3 + 0.4
+    A = wide[:, :F]
+    B = torch.randn(F, K, generator=g, device=DEV)
+    C0 = torch.randn(N, K, generator=g, device=DEV) if acc else None
+    assert _lib.rowterm_supported(N, F, K, A.stride(0))
+    out = _lib.rowterm(A, B, C=None if not acc else C0.clone(), alpha=-0.5, accumulate=acc)
+    ref = -0.5 * (A.double() @ B.double())
+    if acc:
+        ref = ref + C0.double()
+    scale = 0.5 * (A.abs().double() @ B.abs().double()) + (C0.abs().double() if acc else 0.0)
+    assert float(((out.double() - ref).abs() / scale).max()) <= 2e-6
