@@ -51,6 +51,14 @@ __device__ __forceinline__ void tmem_st_16x256b_x4(uint32_t taddr, const uint32_
       : "memory");
 }
 
+// 16-byte read-only load that the compiler may not sink towards its first use: the loads of chunk gc + 2 must be in flight
+// while chunk gc is processed (asm volatile keeps its order relative to the barrier waits)
+__device__ __forceinline__ float4 rt_ldg16(const float* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+
 // B (F, ldb) row-major -> packed chunks; columns >= K and features >= F are zero
 __global__ void rowterm_pack_kernel(const float* __restrict__ B, int ldb, int F, int K, int Kc, uint8_t* __restrict__ Bp) {
   const int chunk = blockIdx.x;
@@ -162,8 +170,7 @@ __global__ void __launch_bounds__(RT_THREADS) rowterm_umma_kernel(const float* _
 #pragma unroll
           for (int j = 0; j < 2; ++j) {
             const int f = c * RT_FC + 16 * j + 4 * c4;
-            v[hf][j][rw] = (row < N && f < F) ? __ldg(reinterpret_cast<const float4*>(A + (size_t)row * lda + f))
-                                              : make_float4(0.f, 0.f, 0.f, 0.f);
+            v[hf][j][rw] = (row < N && f < F) ? rt_ldg16(A + (size_t)row * lda + f) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
     };

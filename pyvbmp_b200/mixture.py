@@ -133,7 +133,8 @@ class Mixture():
             self.ELBO_last = ELBO
 
     STREAM_ROWS = 1 << 19      # rows per streamed chunk (128 MiB of X at d = 64)
-    STREAM_FIRST = 1 << 15     # rows of the first chunk
+    STREAM_FIRST = 1 << 16     # rows of the first chunk (its copy, 16 MiB at d = 64, is the only exposed one)
+    STREAM_GROWTH = 1.3        # chunk i+1 / chunk i while ramping up
 
     def _rows_fit(self, Xh):
         """Room for a device copy of the rows beside the responsibilities, their operand images and the workspaces?"""
@@ -172,7 +173,7 @@ class Mixture():
         st = getattr(self, "_stream_state", None)
         if st is None or st["key"] != (N, d, K, str(dev)):
             st = {"key": (N, d, K, str(dev)), "copy": torch.cuda.Stream(dev),
-                  "buf": [torch.empty((rows, d), dtype=torch.float32, device=dev) for _ in range(2)],
+                  "buf": None, "stage": None,
                   "free": [torch.cuda.Event() for _ in range(2)],
                   "p": torch.empty((N, K), dtype=torch.float32, device=dev),
                   "lz": torch.empty((N,), dtype=torch.float32, device=dev)}
@@ -180,27 +181,46 @@ class Mixture():
         cur = torch.cuda.current_stream(dev)
         for e in st["free"]:
             e.record(cur)
-        full = torch.empty((N, d), dtype=torch.float32, device=dev) if keep else None
+        # Where the chunks land.  When a device copy of all rows fits, every chunk has its own place: the copies then run
+        # back to back at the link's rate from the first microsecond, independent of the kernels (keep: that tensor is
+        # handed on as the resident rows; otherwise it is a staging area reused by the next call).  Otherwise two staging
+        # buffers alternate and the copy of chunk i+1 has to wait for the kernels of chunk i-1.
+        if keep:
+            full = torch.empty((N, d), dtype=torch.float32, device=dev)
+        elif st["stage"] is not None or self._rows_fit(Xh):
+            if st["stage"] is None:
+                st["stage"] = torch.empty((N, d), dtype=torch.float32, device=dev)
+            full = st["stage"]
+        else:
+            full = None
+            if st["buf"] is None:
+                st["buf"] = [torch.empty((rows, d), dtype=torch.float32, device=dev) for _ in range(2)]
         Gs = NA = logZ = None
-        # chunk sizes ramp up from STREAM_FIRST rows by doubling: only the first, small copy is exposed (the copy of a
-        # full 128 MiB chunk is 2.4 ms at PCIe 5 x16 rates), every later one hides behind the kernels of its predecessor
-        bounds, a, size = [], 0, min(rows, self.STREAM_FIRST)
+        # Chunk sizes grow geometrically from STREAM_FIRST rows: only the first, small copy is exposed.  The growth factor
+        # must stay below (kernel time per row) / (copy time per row) — 6.2 / 4.7 ns at cfg2 over PCIe 5 x16 — or every
+        # chunk of the ramp waits for its rows (doubling cost 1.5 ms per iteration at cfg2).
+        bounds, a, size = [], 0, float(min(rows, self.STREAM_FIRST))
         while a < N:
-            bounds.append((a, min(a + size, N)))
-            a += size
-            size = min(2 * size, rows)
+            step = min(int(size) // 256 * 256 or int(size), rows)
+            bounds.append((a, min(a + step, N)))
+            a += step
+            size = min(size * self.STREAM_GROWTH, float(rows))
         for i, (a, b) in enumerate(bounds):
-            buf = full[a:b] if keep else st["buf"][i & 1][: b - a]
+            buf = full[a:b] if full is not None else st["buf"][i & 1][: b - a]
             ready = torch.cuda.Event()
             with torch.cuda.stream(st["copy"]):
-                st["copy"].wait_event(st["free"][i & 1])          # the kernels of chunk i-2 are done with this buffer
+                if full is None or i == 0:
+                    # staging pair: the kernels of chunk i-2 are done with this buffer; full-size staging: the kernels of
+                    # the previous call are (free[0] was recorded on the compute stream above)
+                    st["copy"].wait_event(st["free"][i & 1])
                 buf.copy_(Xh[a:b], non_blocking=True)
                 ready.record(st["copy"])
             cur.wait_event(ready)
             pc, lzc, NAc, lZc = _lib.estep(buf.view(b - a, 1, d), None, b - a, 1, xg, W, m, cst, 1, K, Dp, 1,
                                            out=st["p"][a:b].view(b - a, 1, K), logZn=st["lz"][a:b].view(b - a, 1))
             Gc = _lib.gram(buf.view(b - a, 1, d), None, b - a, 1, xg, pc, 1, xg, 1, K, Dp)
-            st["free"][i & 1].record(cur)
+            if full is None:
+                st["free"][i & 1].record(cur)
             Gs = Gc if Gs is None else Gs + Gc                   # fixed chunk order: deterministic
             NA = NAc if NA is None else NA + NAc
             logZ = lZc if logZ is None else logZ + lZc

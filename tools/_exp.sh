@@ -1,3 +1,2 @@
-mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -q -x -k "wsum or given or golden or rowterm" > gpurun_out/tests_wsum.log 2>&1; tail -15 gpurun_out/tests_wsum.log
-timeout 300 python tools/time_given.py 2>&1 | tail -3
+timeout 600 python -m pytest tests -m gpu -q -x -k "streamed or full_size" 2>&1 | tail -2
+timeout 600 python tools/time_stream.py 2>&1 | tail -8 | cut -c1-330

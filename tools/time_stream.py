@@ -14,8 +14,9 @@ for a in range(0, N, 1 << 18):
 torch.manual_seed(0)
 m = V.GaussianMixtureModel(K, d).to(dev)
 m.initialize(Xh[:65536].to(dev))
-for rows, first in ((1 << 19, 1 << 15), (1 << 18, 1 << 15), (1 << 17, 1 << 15), (1 << 19, 1 << 19), (1 << 18, 1 << 18)):
-    Mixture.STREAM_ROWS, Mixture.STREAM_FIRST = rows, first
+from pyvbmp_b200 import _lib
+for rows, first, growth in ((1 << 19, 1 << 15, 1.3), (1 << 19, 1 << 15, 1.3), (1 << 19, 1 << 15, 2.0), (1 << 20, 1 << 15, 1.3), (1 << 20, 1 << 16, 1.25), (1 << 19, 1 << 16, 1.3), (1 << 19, 1 << 14, 1.3)):
+    Mixture.STREAM_ROWS, Mixture.STREAM_FIRST, Mixture.STREAM_GROWTH = rows, first, growth
     m._stream_state = None
     for _ in range(2): m.update(Xh, 1)
     torch.cuda.synchronize()
@@ -25,4 +26,10 @@ for rows, first in ((1 << 19, 1 << 15), (1 << 18, 1 << 15), (1 << 17, 1 << 15), 
         m.update(Xh, 1)
         float(m.ELBO_last)
     b.record(); b.synchronize()
-    print(f"STREAM_ROWS={rows} STREAM_FIRST={first}: {a.elapsed_time(b) / 5:.2f} ms per iteration")
+    t = a.elapsed_time(b) / 5
+    _lib.profile_begin(256)
+    m.update(Xh, 1); float(m.ELBO_last)
+    torch.cuda.synchronize()
+    prof = _lib.profile_end()
+    k = {name: (len(ev), round(sum(x.elapsed_time(y) for x, y in ev), 2)) for name, ev in prof.items()}
+    print(f"STREAM_ROWS={rows} STREAM_FIRST={first} GROWTH={growth}: {t:.2f} ms per iteration; per-call events (count, ms): {k}; sum {sum(v[1] for v in k.values()):.2f}")
