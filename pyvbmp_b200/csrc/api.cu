@@ -132,8 +132,9 @@ static int estep_impl(const float* z0, int d0, const float* z1, int d1, long lon
     set_error("estep: bad shape N=%lld GX=%d G=%d K=%d d0=%d d1=%d Dp=%d mode=%d", N, GX, G, K, d0, d1, Dp, mode);
     return VBMP_ERR_SHAPE;
   }
-  if (d1 > 0 && !z1) { set_error("estep: z1 is NULL with d1=%d", d1); return VBMP_ERR_SHAPE; }
-  if (mode == 1 && (!logZn || !NA || !logZ)) { set_error("estep: mode 1 needs logZn, NA, logZ"); return VBMP_ERR_SHAPE; }
+  if (d1 > 0 && !z1 && N > 0) { set_error("estep: z1 is NULL with d1=%d", d1); return VBMP_ERR_SHAPE; }
+  // an empty batch (its buffers may be NULL): NA = 0, logZ = 0, nothing else to write (the reference's sums over no rows)
+  if (mode == 1 && (!NA || !logZ || (N > 0 && !logZn))) { set_error("estep: mode 1 needs logZn, NA, logZ"); return VBMP_ERR_SHAPE; }
   if (N == 0) {
     if (mode == 1) { cudaMemsetAsync(NA, 0, sizeof(float) * G * K, st); cudaMemsetAsync(logZ, 0, sizeof(float) * G, st); }
     return VBMP_OK;
@@ -243,7 +244,7 @@ int vbmp_gram_zpack(const float* z0, int d0, const float* z1, int d1, long long 
                     void* zpack, size_t zpack_bytes, int* packed, void* stream) {
   if (!packed) { set_error("gram_zpack: packed is NULL"); return VBMP_ERR_SHAPE; }
   *packed = 0;
-  if (!valid_dp(Dp) || d0 < 1 || d1 < 0 || d0 + d1 > Dp || N < 0 || K < 1 || (d1 > 0 && !z1)) {
+  if (!valid_dp(Dp) || d0 < 1 || d1 < 0 || d0 + d1 > Dp || N < 0 || K < 1 || (d1 > 0 && !z1 && N > 0)) {
     set_error("gram_zpack: bad shape N=%lld K=%d d0=%d d1=%d Dp=%d", N, K, d0, d1, Dp);
     return VBMP_ERR_SHAPE;
   }
@@ -266,7 +267,7 @@ static int gram_impl(const float* z0, int d0, const float* z1, int d1, long long
     set_error("gram: bad shape N=%lld GX=%d GP=%d G=%d K=%d d0=%d d1=%d Dp=%d", N, GX, GP, G, K, d0, d1, Dp);
     return VBMP_ERR_SHAPE;
   }
-  if (d1 > 0 && !z1) { set_error("gram: z1 is NULL with d1=%d", d1); return VBMP_ERR_SHAPE; }
+  if (d1 > 0 && !z1 && N > 0) { set_error("gram: z1 is NULL with d1=%d", d1); return VBMP_ERR_SHAPE; }
   const size_t D1 = (size_t)d0 + d1 + 1, per = (size_t)G * K * D1 * D1;
   if (N == 0) { cudaMemsetAsync(gram, 0, per * sizeof(float), st); return VBMP_OK; }
   const size_t need = gram_ws_bytes(N, G, K, d0, d1, Dp, rpack != nullptr, zpack != nullptr);

@@ -277,7 +277,7 @@ int launch_diag_estep(const float* x, int d, long long N, int GX, const int* xg,
     set_error("diag_estep: bad shape N=%lld GX=%d G=%d K=%d d=%d mode=%d (d <= %d)", N, GX, G, K, d, mode, VBMP_MAX_D);
     return VBMP_ERR_SHAPE;
   }
-  if (mode == 1 && (!logZn || !NA || !logZ)) { set_error("diag_estep: mode 1 needs logZn, NA, logZ"); return VBMP_ERR_SHAPE; }
+  if (mode == 1 && (!NA || !logZ || (N > 0 && !logZn))) { set_error("diag_estep: mode 1 needs logZn, NA, logZ"); return VBMP_ERR_SHAPE; }
   if (N == 0) {
     if (mode == 1) { cudaMemsetAsync(NA, 0, sizeof(float) * G * K, st); cudaMemsetAsync(logZ, 0, sizeof(float) * G, st); }
     return VBMP_OK;

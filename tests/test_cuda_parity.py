@@ -554,3 +554,48 @@ def test_streamed_host_rows_match_device_rows():
         for k in NIW_STATE:
             assert_close(get(o, k), get(a, k), 2e-5, k)
     assert getattr(b, "_stream_state", {}).get("resident") is None          # the resident copy is dropped after the call
+
+
+@pytest.mark.parametrize("d,K", [(3, 4), (64, 16)])
+@pytest.mark.parametrize("N", [0, 1, 5, 257, 300])
+def test_gmm_empty_and_tiny_inputs(N, d, K):
+    """Edge sizes the reference accepts (an empty batch leaves NA = 0 and moves the posterior to lr-blended priors; one
+    row; a few rows; one row past an E-step tile): two EM iterations against the fp64 oracle run on the same rows."""
+    g = torch.Generator().manual_seed(N + d)
+    X = torch.randn(N, d, generator=g) * 1.5 + 0.25
+    torch.manual_seed(4)
+    m = V.GaussianMixtureModel(K, d)
+    ref = O.gmm_new(K, d)
+    O.load_state(ref, {"dist.mu": m.dist.mu.clone(), "pi.alpha": m.pi.alpha.clone()})
+    O.to_dtype(ref, torch.float64)
+    m.to(DEV)
+    Xd = X.to(DEV)
+    for it in range(2):
+        m.update(Xd, 1)
+        tr = O.mixture_update(ref, X.double(), 1)
+        assert m.p.shape == (N, K)
+        # (after an empty batch the posterior IS the prior: ELBO = -KL = 0 up to the rounding of O(1e2) terms)
+        assert abs(float(m.ELBO_last) - float(tr[0])) <= PARITY * max(abs(float(tr[0])), 1e2), (it, float(m.ELBO_last), float(tr[0]))
+        if N:
+            assert_close(m.NA, ref["NA"], PARITY, "NA")
+        else:
+            assert float(m.NA.abs().max()) == 0.0
+        if N:
+            assert_maxabs(m.p.cpu().double(), ref["p"], 2e-4, "p")
+        flat = O.flatten_state(ref)
+        for k in NIW_STATE:
+            assert_close(get(m, k), flat[k], 3e-4 if it == 0 else PARITY, f"{k} it{it}")
+
+
+def test_other_models_accept_an_empty_batch():
+    """N = 0 through the diagonal-precision, matrix-normal and HMM-free paths: the call succeeds, p has shape (0, K), NA = 0
+    (the reference's sums over no rows), and a following non-empty batch works."""
+    torch.manual_seed(0)
+    m = V.GaussianMixtureModel(8, 16, isotropic=True).to(DEV)
+    for N in (0, 3):
+        m.update(torch.randn(N, 16, device=DEV), 1)
+        assert m.p.shape == (N, 8) and abs(float(m.NA.sum()) - N) < 1e-4 and torch.isfinite(m.ELBO_last)
+    t = V.MixtureofLinearTransforms(4, 3, 8).to(DEV)
+    for N in (0, 3):
+        t.raw_update(torch.randn(N, 3, 1, device=DEV), torch.randn(N, 4, 1, device=DEV), iters=1)
+        assert t.p.shape == (N, 8) and torch.isfinite(t.ELBO_last)
