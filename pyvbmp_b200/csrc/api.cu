@@ -81,6 +81,33 @@ size_t gram_rpack_bytes(long long N, int K);
 static bool valid_dp(int Dp) { return Dp == 8 || Dp == 16 || Dp == 32 || Dp == 64 || Dp == 128; }
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// ---- K that is not a multiple of 4 -----------------------------------------------------------------------------------
+// The tensor-core kernels write responsibilities / read weights in 16-byte pieces of a row, so they need K % 4 == 0.  A call
+// with any other K that is otherwise inside their window runs on them with K padded to Kq = 4 ceil(K / 4) by INERT
+// components (W = 0, m = 0, cst = -1e30: probability exactly 0; weights 0: statistics exactly 0): padded parameters, a
+// padded (N x Kq) responsibility / weight image and padded outputs live in the workspace, and one streaming pass
+// compacts / expands the rows.  Costs ~3 passes over an (N x K) array, against a ~20x slower CUDA-core kernel.
+static int kq_of(int K) { return (K + 3) / 4 * 4; }
+__global__ void padk_cst_kernel(const float* __restrict__ cst, int K, int Kq, float* __restrict__ out) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < Kq) out[k] = k < K ? cst[k] : -1e30f;
+}
+// dst (N x Kd) <- src (N x Ks): the first min(Kd, Ks) columns of every row, zeros beyond
+__global__ void padk_cols_kernel(const float* __restrict__ src, int Ks, float* __restrict__ dst, int Kd, long long N) {
+  const long long tot = N * Kd;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += (long long)gridDim.x * blockDim.x) {
+    const long long n = e / Kd;
+    const int k = (int)(e - n * Kd);
+    dst[e] = k < Ks ? src[n * Ks + k] : 0.f;
+  }
+}
+static int padk_cols(const float* src, int Ks, float* dst, int Kd, long long N, cudaStream_t st) {
+  const long long tot = N * Kd;
+  const unsigned grid = (unsigned)((tot + 255) / 256 < (long long)num_sms() * 16 ? (tot + 255) / 256 : (long long)num_sms() * 16);
+  padk_cols_kernel<<<grid, 256, 0, st>>>(src, Ks, dst, Kd, N);
+  return check_launch("padk_cols");
+}
+
 }  // namespace vbmp
 
 using namespace vbmp;
@@ -111,8 +138,19 @@ int vbmp_mnw_prep_ex(const float* invU, const float* nu, const float* mu, const 
                          tau, elogdet);
 }
 
+// shapes the tcgen05 E-step takes once K is padded (see kq_of)
+static bool estep_padk(long long N, int GX, int G, int K, int Dp, int d0, int d1) {
+  return (K % 4) != 0 && estep_umma_supported(N, GX, G, kq_of(K), Dp, d0, d1);
+}
+static size_t estep_padk_extra(long long N, int K, int Dp) {       // padded W, m, cst, responsibilities, NA
+  const size_t Kq = (size_t)kq_of(K);
+  return align_up(Kq * Dp * Dp * sizeof(float), 256) + align_up(Kq * Dp * sizeof(float), 256) + 2 * align_up(Kq * sizeof(float), 256) +
+         align_up((size_t)N * Kq * sizeof(float), 256);
+}
+
 size_t vbmp_estep_workspace_bytes(long long N, int G, int K, int Dp, int mode) {
   if (!valid_dp(Dp) || N < 0) return 0;
+  if (estep_padk(N, 1, G, K, Dp, 1, 0)) return estep_padk_extra(N, K, Dp) + vbmp_estep_workspace_bytes(N, G, kq_of(K), Dp, mode) + 256;
   size_t simt = 0;
   if (mode == 1) {
     const size_t nb = (size_t)cdiv(N, estep_simt_tile(Dp));
@@ -137,6 +175,39 @@ static int estep_impl(const float* z0, int d0, const float* z1, int d1, long lon
   if (mode == 1 && (!NA || !logZ || (N > 0 && !logZn))) { set_error("estep: mode 1 needs logZn, NA, logZ"); return VBMP_ERR_SHAPE; }
   if (N == 0) {
     if (mode == 1) { cudaMemsetAsync(NA, 0, sizeof(float) * G * K, st); cudaMemsetAsync(logZ, 0, sizeof(float) * G, st); }
+    return VBMP_OK;
+  }
+  if (!(flags & 1) && estep_padk(N, GX, G, K, Dp, d0, d1)) {
+    // K % 4 != 0: run the tensor-core kernel on K padded by inert components, then compact the rows
+    const int Kq = kq_of(K);
+    if (workspace_bytes < vbmp_estep_workspace_bytes(N, G, K, Dp, mode)) {
+      set_error("estep: workspace too small (%zu < %zu)", workspace_bytes, vbmp_estep_workspace_bytes(N, G, K, Dp, mode));
+      return VBMP_ERR_WORKSPACE;
+    }
+    char* q = (char*)align_up((size_t)workspace, 256);
+    float* Wq = (float*)q; q += align_up((size_t)Kq * Dp * Dp * sizeof(float), 256);
+    float* mq = (float*)q; q += align_up((size_t)Kq * Dp * sizeof(float), 256);
+    float* cq = (float*)q; q += align_up((size_t)Kq * sizeof(float), 256);
+    float* NAq = (float*)q; q += align_up((size_t)Kq * sizeof(float), 256);
+    float* outq = (float*)q; q += align_up((size_t)N * Kq * sizeof(float), 256);
+    const size_t nW = (size_t)K * Dp * Dp * sizeof(float), nm = (size_t)K * Dp * sizeof(float);
+    if (cudaMemsetAsync(Wq, 0, (size_t)Kq * Dp * Dp * sizeof(float), st) != cudaSuccess ||
+        cudaMemsetAsync(mq, 0, (size_t)Kq * Dp * sizeof(float), st) != cudaSuccess ||
+        cudaMemcpyAsync(Wq, W, nW, cudaMemcpyDeviceToDevice, st) != cudaSuccess ||
+        cudaMemcpyAsync(mq, m, nm, cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
+      set_error("estep: padding copies failed"); return VBMP_ERR_CUDA;
+    }
+    padk_cst_kernel<<<(Kq + 127) / 128, 128, 0, st>>>(cst, K, Kq, cq);
+    int rc = check_launch("padk_cst");
+    if (rc) return rc;
+    rc = estep_impl(z0, d0, z1, d1, N, GX, xg, Wq, mq, cq, G, Kq, Dp, mode, flags, outq, logZn, NAq, logZ, q,
+                    workspace_bytes - (size_t)(q - (char*)workspace), stream, rpack, rpack_bytes, packed);
+    if (rc) return rc;
+    rc = padk_cols(outq, Kq, out, K, N, st);
+    if (rc) return rc;
+    if (mode == 1 && cudaMemcpyAsync(NA, NAq, (size_t)K * sizeof(float), cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
+      set_error("estep: NA copy failed"); return VBMP_ERR_CUDA;
+    }
     return VBMP_OK;
   }
   if (workspace_bytes < vbmp_estep_workspace_bytes(N, G, K, Dp, mode) && mode == 1) {
@@ -218,8 +289,18 @@ int vbmp_estep_rpack(const float* z0, int d0, const float* z1, int d1, long long
                     workspace_bytes, stream, rpack, rpack_bytes, packed);
 }
 
+static bool gram_padk(long long N, int GX, int GP, int G, int K, int Dp, int d0, int d1, bool has_p) {
+  return (K % 4) != 0 && gram_umma_supported(N, GX, GP, G, kq_of(K), Dp, d0, d1, has_p);
+}
+static size_t gram_padk_extra(long long N, int K, int d0, int d1) {      // padded weights and padded statistics
+  const size_t Kq = (size_t)kq_of(K), D1 = (size_t)d0 + d1 + 1;
+  return align_up((size_t)N * Kq * sizeof(float), 256) + align_up(Kq * D1 * D1 * sizeof(float), 256);
+}
+
 static size_t gram_ws_bytes(long long N, int G, int K, int d0, int d1, int Dp, bool has_rpack, bool has_zpack) {
   if (!valid_dp(Dp) || N < 0) return 0;
+  if (gram_padk(N, 1, 1, G, K, Dp, d0, d1, true))
+    return gram_padk_extra(N, K, d0, d1) + gram_ws_bytes(N, G, kq_of(K), d0, d1, Dp, has_rpack, has_zpack) + 256;
   long long S_per; int splits;
   gram_simt_plan(N > 0 ? N : 1, G, K, Dp, &S_per, &splits);
   const size_t D1 = (size_t)d0 + d1 + 1;
@@ -248,7 +329,7 @@ int vbmp_gram_zpack(const float* z0, int d0, const float* z1, int d1, long long 
     set_error("gram_zpack: bad shape N=%lld K=%d d0=%d d1=%d Dp=%d", N, K, d0, d1, Dp);
     return VBMP_ERR_SHAPE;
   }
-  if (!gram_zpack_usable(N, K, Dp, d0, d1)) return VBMP_OK;       // the kernels that take this shape do not use an image
+  if (!gram_zpack_usable(N, kq_of(K), Dp, d0, d1)) return VBMP_OK;   // the kernels that take this shape do not use an image
   if (zpack_bytes < gram_zpack_bytes(N, d0 + d1)) {
     set_error("gram_zpack: buffer too small (%zu < %zu)", zpack_bytes, gram_zpack_bytes(N, d0 + d1));
     return VBMP_ERR_WORKSPACE;
@@ -274,6 +355,22 @@ static int gram_impl(const float* z0, int d0, const float* z1, int d1, long long
   if (workspace_bytes < need) {
     set_error("gram: workspace too small (%zu < %zu)", workspace_bytes, need);
     return VBMP_ERR_WORKSPACE;
+  }
+  if (!(flags & 1) && gram_padk(N, GX, GP, G, K, Dp, d0, d1, p != nullptr)) {
+    // K % 4 != 0: weights padded with zero columns, statistics of the first K components copied out
+    const int Kq = kq_of(K);
+    char* q = (char*)align_up((size_t)workspace, 256);
+    float* pq = (float*)q; q += align_up((size_t)N * Kq * sizeof(float), 256);
+    float* gq = (float*)q; q += align_up((size_t)Kq * D1 * D1 * sizeof(float), 256);
+    int rc = padk_cols(p, K, pq, Kq, N, st);
+    if (rc) return rc;
+    rc = gram_impl(z0, d0, z1, d1, N, GX, xg, pq, GP, pg, G, Kq, Dp, flags, gq, q,
+                   workspace_bytes - (size_t)(q - (char*)workspace), stream, rpack, zpack);
+    if (rc) return rc;
+    if (cudaMemcpyAsync(gram, gq, (size_t)K * D1 * D1 * sizeof(float), cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
+      set_error("gram: copy of the statistics failed"); return VBMP_ERR_CUDA;
+    }
+    return VBMP_OK;
   }
   GramArgs a{z0, z1, d0, d1, N, GX, xg, p, GP, pg, G, K, Dp, 0, 0, nullptr};
   a.rpack = (const unsigned char*)rpack;

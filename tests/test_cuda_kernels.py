@@ -44,7 +44,9 @@ CASES = [(5000, 64, 0, 256), (66000, 64, 0, 256), (3001, 32, 32, 64), (4099, 16,
          (257, 64, 0, 4), (2048, 8, 8, 4), (2049, 64, 0, 512), (4097, 20, 12, 36), (9000, 64, 0, 132), (2304, 32, 0, 260),
          # 64 < D <= 128 (padded to 128): tcgen05 kernels with fp16 operands — two accumulator buffers in the E-step, 8385
          # pair columns in 44 blocks and a shallower chunk ring in the Gram
-         (3000, 96, 0, 64), (4500, 128, 0, 256), (2500, 64, 64, 64), (2100, 72, 40, 12)]
+         (3000, 96, 0, 64), (4500, 128, 0, 256), (2500, 64, 64, 64), (2100, 72, 40, 12),
+         # K % 4 != 0: the tensor-core kernels run on K padded by inert components (api.cu, kq_of)
+         (5000, 64, 0, 50), (2600, 32, 32, 10), (3000, 128, 0, 30), (4096, 16, 0, 7), (2300, 64, 0, 257)]
 
 
 @pytest.mark.parametrize("N,d0,d1,K", CASES)

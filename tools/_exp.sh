@@ -1,16 +1,17 @@
-timeout 600 python -m pytest tests -m gpu -q -k "empty_and_tiny" 2>&1 | tail -25
+timeout 900 python -m pytest tests/test_cuda_kernels.py -m gpu -q -x -k "estep_kernels or gram_kernels" 2>&1 | tail -6
 python - <<'PY'
-import torch, pyvbmp_b200 as V
+import torch, time, pyvbmp_b200 as V
+from pyvbmp_b200 import _lib
 dev='cuda:0'
-for iso in (False, True):
+for K in (48, 50):
     torch.manual_seed(0)
-    m = V.GaussianMixtureModel(8, 16, isotropic=iso).to(dev)
-    for N in (0, 1, 3):
-        m.update(torch.randn(N, 16, device=dev), 1)
-        print('iso' if iso else 'full', N, float(m.ELBO_last), m.p.shape, float(m.NA.sum()))
-torch.manual_seed(0)
-t = V.MixtureofLinearTransforms(4, 3, 8).to(dev)
-for N in (0, 1, 3):
-    t.raw_update(torch.randn(N, 3, 1, device=dev), torch.randn(N, 4, 1, device=dev), iters=1)
-    print('molt', N, float(t.ELBO_last), t.p.shape)
+    N, d = 1<<20, 64
+    g = torch.Generator(device=dev).manual_seed(1)
+    mu = 3*torch.randn(K, d, generator=g, device=dev)
+    X = mu[torch.randint(K,(N,),generator=g,device=dev)] + torch.randn(N,d,generator=g,device=dev)
+    m = V.GaussianMixtureModel(K, d).to(dev); m.dist.mu = X[:K].clone()
+    for _ in range(3): m.update(X,1)
+    torch.cuda.synchronize(); t0=time.perf_counter()
+    for _ in range(5): m.update(X,1)
+    torch.cuda.synchronize(); print(f"K={K}: {(time.perf_counter()-t0)/5*1e3:.2f} ms per iteration, ELBO {float(m.ELBO_last):.6e}")
 PY
