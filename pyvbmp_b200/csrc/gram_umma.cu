@@ -510,11 +510,40 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant_
 //   * B = the pre-split weight images AS THEY ARE in the raw ring: [hi | lo][8-sample chunk][component][8 fp16] is
 //     the K-major core-matrix layout already (SBO = 128 B between 8-component groups, LBO = Kp x 16 B between the two
 //     8-sample chunks of a K-step); only the first Kp = K rounded up to 16 components of each piece are copied in;
-//   * a CTA owns GS_J = 2 blocks of 128 pairs (D1 and D2 of both: 4 Kp <= 256 columns; A stages: 4 x 2 x 32 = 256), so
+//   * a CTA owns GS_J = 2 blocks of 128 pairs — the first and the second pairs of 128 COUPLES that share a factor, see
+//     gs_couple — (D1 and D2 of both: 4 Kp <= 256 columns; A stages: 4 x 2 x 32 = 256), so
 //     a weight stage is used by 12 MMAs with N = Kp.  MMA time per 32-sample chunk ~ 12 x 0.57 Kp cycles for 256 pairs
 //     against 6 x 0.57 x 224 for 224 pairs: 2.1x less at K = 64, 4.3x at K = 32.
 // Everything else — the sample image, the balanced sample splits, the two-level fp32 accumulation with round-to-nearest
 // folds every GU_FL chunks, the fixed-order fp64 reduce with the resolution check and the TF32 fallback — is shared.
+// Couples.  A worker thread of the swapped-role kernel owns TWO pairs that share their first factor, (i, j1) in the CTA's
+// pair block 0 and (i, j2) in block 1 (same tensor-memory lane, different columns): three factor rows are loaded for two
+// products instead of four — the kernel is paced by exactly those shared-memory loads.  Row i of the upper triangle
+// (j = i .. D, the constant feature last) is cut into couples (i, j), (i, j + 1); an odd row ends in a couple without a
+// second pair.  The partial sums are written at the pairs' canonical indices (gu_pair_any's order), so the reduce kernel
+// does not know about couples.  diag: couple c = ((c, c), (c, D)).
+__host__ __device__ inline int gs_ncouples(int D, int diag) {
+  if (diag) return D + 1;
+  int n = 0;
+  for (int m = 1; m <= D + 1; ++m) n += (m + 1) / 2;
+  return n;
+}
+__host__ __device__ inline int gs_pair_index(int i, int j, int D, int diag) {      // inverse of gu_pair_any
+  if (diag) return (i == j && i < D) ? i : D + i;
+  if (j == D) return D * (D + 1) / 2 + i;
+  return i * D - i * (i - 1) / 2 + (j - i);
+}
+__host__ __device__ inline void gs_couple(int c, int D, int diag, int* i, int* j1, int* j2) {
+  if (diag) { *i = c; *j1 = c < D ? c : D; *j2 = c < D ? D : -1; return; }
+  int r = 0, rem = c;
+  for (;; ++r) {
+    const int nc = (D + 1 - r + 1) / 2;                // couples of row r (D + 1 - r pairs)
+    if (rem < nc) break;
+    rem -= nc;
+  }
+  *i = r; *j1 = r + 2 * rem; *j2 = (*j1 + 1 <= D) ? *j1 + 1 : -1;
+}
+
 constexpr int GS_J = 2;              // pair blocks of 128 per CTA
 constexpr int GS_NSTG = 4;           // A (phi) stages in tensor memory
 constexpr int GS_KMAX = 64;
@@ -526,7 +555,7 @@ struct GsSmem {
   uint32_t tmem_base;
 };
 
-__global__ void __launch_bounds__(GU_THREADS, 1) gram_swap_kernel(GuArgs a, int Kp, int nblk) {
+__global__ void __launch_bounds__(GU_THREADS, 1) gram_swap_kernel(GuArgs a, int Kp, int ncpl) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr int SC = 32;
   const int D = a.d0 + a.d1;
@@ -536,13 +565,13 @@ __global__ void __launch_bounds__(GU_THREADS, 1) gram_swap_kernel(GuArgs a, int 
   uint8_t* raw = smem_raw;
   GsSmem* S = reinterpret_cast<GsSmem*>(raw + (size_t)nr * rawB);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int ntask = (nblk + GS_J - 1) / GS_J;          // pair-block groups
+  const int ntask = (ncpl + 127) / 128;                // 128 couples = two blocks of 128 pairs per CTA
   const int task = (int)blockIdx.x % ntask, split = (int)blockIdx.x / ntask;
   const long long nb = (long long)split * a.S_per;
   long long ne = nb + a.S_per; if (ne > a.N) ne = a.N;
   const int nchunks = ne > nb ? (int)((ne - nb + SC - 1) / SC) : 0;
   const int FL = a.FL;
-  const int jn = min(GS_J, nblk - task * GS_J);        // pair blocks this CTA really has
+  constexpr int jn = GS_J;                             // block 0: the couples' first pairs, block 1: their second pairs
 
   if (tid == 0) {
     for (int s = 0; s < GU_NR; ++s) { mbar_init(&S->rfull[s], 1); mbar_init(&S->rempty[s], 9); }   // 8 worker warps + the MMAs
@@ -618,19 +647,41 @@ __global__ void __launch_bounds__(GU_THREADS, 1) gram_swap_kernel(GuArgs a, int 
       if (flush) { fc = 0; ++nflush; }
     }
   } else {
-    // ================= workers: thread = pair (tensor-memory lane), two sets of 8 warps alternate chunks =================
+    // ================= workers: thread = couple (tensor-memory lane), two sets of 8 warps alternate chunks ================
+    // within a set, warps 0-3 generate K-step 0 of both pair blocks and fold block 0, warps 4-7 K-step 1 and block 1
     const int set = (warp - 2) >> 3, w8 = (warp - 2) & 7;
-    const int j = w8 >> 2, q = warp & 3;                      // pair block, lane quarter (a warp reaches lanes 32 (warp % 4) ..)
+    const int ksel = w8 >> 2, q = warp & 3;                   // K-step / folded block, lane quarter (a warp reaches lanes 32 (warp % 4) ..)
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     const int prow = q * 32 + lane;
-    const int pg_ = (task * GS_J + j) * 128 + prow;           // pair column of the symmetric statistics
-    const bool jok = j < jn;
-    const bool pair_ok = jok && pg_ < a.P;
-    int pi = 0, pj = 0;
-    if (pair_ok) gu_pair_any(pg_, D, a.diag, &pi, &pj);
-    const uint8_t* bi = raw + rawR + (size_t)(pair_ok ? pi : D + 1) * (GU_ZS * 4);      // row D + 1 of the record: zeros
-    const uint8_t* bj = raw + rawR + (size_t)(pair_ok ? pj : D + 1) * (GU_ZS * 4);
+    const int cidx = task * 128 + prow;                       // couple
+    const bool c_ok = cidx < ncpl;
+    int ci = 0, cj1 = 0, cj2 = -1;
+    if (c_ok) gs_couple(cidx, D, a.diag, &ci, &cj1, &cj2);
+    const bool has2 = c_ok && cj2 >= 0;
+    const uint8_t* bi = raw + rawR + (size_t)(c_ok ? ci : D + 1) * (GU_ZS * 4) + ksel * 64;      // row D + 1 of the record: zeros
+    const uint8_t* bj1 = raw + rawR + (size_t)(c_ok ? cj1 : D + 1) * (GU_ZS * 4) + ksel * 64;
+    const uint8_t* bj2 = raw + rawR + (size_t)(has2 ? cj2 : D + 1) * (GU_ZS * 4) + ksel * 64;
+    // the row of the partials this thread writes when it folds block ksel: the canonical index of that pair
+    const int pout = !c_ok ? -1 : (ksel == 0 ? gs_pair_index(ci, cj1, D, a.diag) : (has2 ? gs_pair_index(ci, cj2, D, a.diag) : -1));
     const int fls = __ffs(FL) - 1;
+    // phi of 16 samples (two 16-byte K-chunks of fp16) for one pair: multiply, split, store both images
+    auto gen = [&](const float4 (&av)[4], const float4 (&bv)[4], uint32_t ad) {
+      uint32_t hi[8], lo[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const float4 a4 = av[u >> 1], b4 = bv[u >> 1];
+        // factors carry exact power-of-two scales, so this is the reference's fp32 product times 2^(u_i + u_j)
+        const float2 x = (u & 1) ? __fmul2_rn(make_float2(a4.z, a4.w), make_float2(b4.z, b4.w))
+                                 : __fmul2_rn(make_float2(a4.x, a4.y), make_float2(b4.x, b4.y));
+        const __half2 ah = __floats2half2_rn(x.x, x.y);
+        const float2 af = __half22float2(ah);
+        const __half2 bh2 = __floats2half2_rn(x.x - af.x, x.y - af.y);
+        hi[u] = *reinterpret_cast<const uint32_t*>(&ah);
+        lo[u] = *reinterpret_cast<const uint32_t*>(&bh2);
+      }
+      tmem_st8(ad + ksel * 8, hi);
+      tmem_st8(ad + 16 + ksel * 8, lo);
+    };
     int s = set;
     uint32_t rph = 0;
     for (int c = set; c < nchunks; c += 2, s += 2) {
@@ -640,34 +691,18 @@ __global__ void __launch_bounds__(GU_THREADS, 1) gram_swap_kernel(GuArgs a, int 
       mbar_wait(&S->rfull[s], rph);
       mbar_wait(&S->bempty[st], ((c / GS_NSTG) & 1) ^ 1);
       tc_fence_after();
-      if (jok) {
-        const uint8_t* zi = bi + (size_t)s * rawB;
-        const uint8_t* zj = bj + (size_t)s * rawB;
-        const uint32_t ad = tm + lane_base + ACOL + (st * GS_J + j) * 32;
+      {
+        const size_t so = (size_t)s * rawB;
+        float4 av[4], b1[4], b2[4];
 #pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {
-          float4 av[4], bv[4];
-#pragma unroll
-          for (int v = 0; v < 4; ++v) {
-            av[v] = *reinterpret_cast<const float4*>(zi + ks * 64 + v * 16);
-            bv[v] = *reinterpret_cast<const float4*>(zj + ks * 64 + v * 16);
-          }
-          uint32_t hi[8], lo[8];
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const float4 a4 = av[u >> 1], b4 = bv[u >> 1];
-            // factors carry exact power-of-two scales, so this is the reference's fp32 product times 2^(u_i + u_j)
-            const float2 x = (u & 1) ? __fmul2_rn(make_float2(a4.z, a4.w), make_float2(b4.z, b4.w))
-                                     : __fmul2_rn(make_float2(a4.x, a4.y), make_float2(b4.x, b4.y));
-            const __half2 ah = __floats2half2_rn(x.x, x.y);
-            const float2 af = __half22float2(ah);
-            const __half2 bh2 = __floats2half2_rn(x.x - af.x, x.y - af.y);
-            hi[u] = *reinterpret_cast<const uint32_t*>(&ah);
-            lo[u] = *reinterpret_cast<const uint32_t*>(&bh2);
-          }
-          tmem_st8(ad + ks * 8, hi);
-          tmem_st8(ad + 16 + ks * 8, lo);
+        for (int v = 0; v < 4; ++v) {
+          av[v] = *reinterpret_cast<const float4*>(bi + so + v * 16);
+          b1[v] = *reinterpret_cast<const float4*>(bj1 + so + v * 16);
+          b2[v] = *reinterpret_cast<const float4*>(bj2 + so + v * 16);
         }
+        const uint32_t ad = tm + lane_base + ACOL + (st * GS_J) * 32;
+        gen(av, b1, ad);
+        gen(av, b2, ad + 32);
       }
       tmem_wait_st();
       tc_fence_before();
@@ -676,28 +711,32 @@ __global__ void __launch_bounds__(GU_THREADS, 1) gram_swap_kernel(GuArgs a, int 
 
       const bool last = (c == nchunks - 1);
       if (((c + 1) & (FL - 1)) == 0 || last) {
-        // ---- fold D1 into D2 (or, at the end, write D1 + D2 to this split's partial): thread = pair row, Kp columns
+        // ---- fold D1 into D2 (or, at the end, write D1 + D2 to this split's partial): thread = pair row of block ksel
         if (nflush > 0) mbar_wait(&S->dfull, (nflush - 1) & 1);
         mbar_wait(&S->dfull, nflush & 1);
         tc_fence_after();
         const bool firstf = (nflush == 0);
-        if (jok) {
-          float* prw = a.part + ((size_t)split * a.PP + (size_t)(task * GS_J + j) * 128 + prow) * Kp;
+        {
+          // (the tensor-memory loads / stores are warp-collective: every lane runs them, only the global stores of
+          // lanes without a pair in this block are skipped)
+          float* prw = a.part + ((size_t)split * a.PP + (size_t)(pout >= 0 ? pout : 0)) * Kp;
           for (int c0 = 0; c0 < Kp; c0 += 16) {
             float v1[16], v2[16];
-            tmem_ld16(tm + lane_base + j * 64 + c0, v1);
-            if (!firstf) tmem_ld16(tm + lane_base + D2COL + j * 64 + c0, v2);
+            tmem_ld16(tm + lane_base + ksel * 64 + c0, v1);
+            if (!firstf) tmem_ld16(tm + lane_base + D2COL + ksel * 64 + c0, v2);
             tmem_wait_ld();
             if (!firstf) {
 #pragma unroll
               for (int u = 0; u < 16; ++u) v1[u] += v2[u];
             }
             if (last) {
+              if (pout >= 0) {
 #pragma unroll
-              for (int u = 0; u < 16; u += 4)
-                *reinterpret_cast<float4*>(prw + c0 + u) = make_float4(v1[u], v1[u + 1], v1[u + 2], v1[u + 3]);
+                for (int u = 0; u < 16; u += 4)
+                  *reinterpret_cast<float4*>(prw + c0 + u) = make_float4(v1[u], v1[u + 1], v1[u + 2], v1[u + 3]);
+              }
             } else {
-              tmem_st16(tm + lane_base + D2COL + j * 64 + c0, reinterpret_cast<const uint32_t*>(v1));
+              tmem_st16(tm + lane_base + D2COL + ksel * 64 + c0, reinterpret_cast<const uint32_t*>(v1));
             }
           }
         }
@@ -707,8 +746,8 @@ __global__ void __launch_bounds__(GU_THREADS, 1) gram_swap_kernel(GuArgs a, int 
         if (lane == 0) mbar_arrive(&S->dempty);
       }
     }
-    if (nchunks == 0 && set == 0 && jok) {      // empty split: contribute zeros
-      float* prw = a.part + ((size_t)split * a.PP + (size_t)(task * GS_J + j) * 128 + prow) * Kp;
+    if (nchunks == 0 && set == 0 && pout >= 0) {      // empty split: contribute zeros
+      float* prw = a.part + ((size_t)split * a.PP + (size_t)pout) * Kp;
       for (int c0 = 0; c0 < Kp; ++c0) prw[c0] = 0.f;
     }
   }
@@ -931,7 +970,7 @@ static void gu_plan(long long N, int K, int D, int sms, GuArgs* g, int diag = 0,
 static size_t gu_al(size_t x) { return (x + 255) / 256 * 256; }
 
 // ---- plan of the swapped-role kernel (K <= GS_KMAX): blocks of 128 pairs, GS_J per CTA, same split rule as gu_plan
-struct GsPlan { int Kp, nblk, ntask, splits, PP; long long S_per; };
+struct GsPlan { int Kp, nblk, ncpl, ntask, splits, PP; long long S_per; };
 static bool gs_enabled() {
   static const int on = [] { const char* e = getenv("VBMP_GRAM_SWAP"); return e ? atoi(e) : 1; }();
   return on != 0;
@@ -941,8 +980,9 @@ static GsPlan gs_plan(long long N, int K, int D, int diag, int sms) {
   q.Kp = (K + 15) / 16 * 16;
   const int P = gu_npairs(D, diag);
   q.nblk = (P + 127) / 128;
-  q.ntask = (q.nblk + GS_J - 1) / GS_J;
-  q.PP = q.nblk * 128;
+  q.ncpl = gs_ncouples(D, diag);                     // a CTA takes 128 couples = two blocks of 128 pairs
+  q.ntask = (q.ncpl + 127) / 128;
+  q.PP = q.nblk * 128;                               // rows of the partials: canonical pair index
   const long long cap = 32768;
   long long rounds = ((long long)N * q.ntask + (long long)sms * cap - 1) / ((long long)sms * cap);
   if (rounds < 1) rounds = 1;
@@ -1162,7 +1202,7 @@ int launch_gram_umma(const GramArgs& a, float* gram, void* ws, size_t ws_bytes, 
     gs.nr = nr;
     const size_t smem = (size_t)nr * rawB + sizeof(GsSmem) + 64;
     cudaFuncSetAttribute(gram_swap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    gram_swap_kernel<<<(unsigned)(q.ntask * q.splits), GU_THREADS, smem, st>>>(gs, q.Kp, q.nblk);
+    gram_swap_kernel<<<(unsigned)(q.ntask * q.splits), GU_THREADS, smem, st>>>(gs, q.Kp, q.ncpl);
     rc = check_launch("gram_swap");
     if (rc) return rc;
     gram_pair_reduce_kernel<1><<<rgrid, 256, 0, st>>>(g.part, q.splits, a.K, g.Kp, q.PP, D1, g.cmax, flag, gram, g.diag, q.Kp);

@@ -49,11 +49,21 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug traps (launch failure) instead of hanging the GPU box.
+// Bounded wait: a protocol bug traps (launch failure) instead of hanging the GPU box.  The bound is wall-clock time
+// (%globaltimer, looked at every 4096 failed polls): no legitimate wait in these kernels is longer than milliseconds, and an
+// iteration count alone took a quarter of an hour to run out (a failed try_wait suspends the thread for a while).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  for (uint32_t it = 0; it < (1u << 28); ++it)
+  if (mbar_try_wait(bar, parity)) return;
+  uint64_t t0 = 0;
+  for (uint32_t it = 1;; ++it) {
     if (mbar_try_wait(bar, parity)) return;
-  __trap();
+    if ((it & 4095u) == 0u) {
+      uint64_t t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > 8000000000ull) __trap();       // 8 s
+    }
+  }
 }
 
 // ---- bulk async copy global -> shared (TMA unit, SASS UBLKCP), completes on an mbarrier ------------
