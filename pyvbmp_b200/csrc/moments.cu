@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(MM_WARPS * 32) moe_moments_tile_kernel(const f
     for (int e = lane * 4; e < cnt; e += 128) mm_cp_async16(dst + e, src + e);
     mm_cp_async_commit();
   };
-  float acc[4][8];
+  float2 acc[4][4];                      // 4 rows x 8 columns as packed pairs: one FFMA2 per row and column pair
   float4 mur, muc0, muc1;
   if (items > 0) prefetch(0);
   for (long long t = 0; t < items; ++t) {
@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(MM_WARPS * 32) moe_moments_tile_kernel(const f
 #pragma unroll
       for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[a][j] = 0.f;
+        for (int j = 0; j < 4; ++j) acc[a][j] = make_float2(0.f, 0.f);
       mur = make_float4(0.f, 0.f, 0.f, 0.f); muc0 = mur; muc1 = mur;
     }
     const float* mb_ = buf + (size_t)(t & 1) * MM_KC * n;
@@ -128,14 +128,14 @@ __global__ void __launch_bounds__(MM_WARPS * 32) moe_moments_tile_kernel(const f
       const float4 ma = cok0 ? *reinterpret_cast<const float4*>(mk + c0) : z;
       const float4 mb = cok1 ? *reinterpret_cast<const float4*>(mk + c0 + 4) : z;
       const float w[4] = {pk * mr.x, pk * mr.y, pk * mr.z, pk * mr.w};
-      const float c[8] = {ma.x, ma.y, ma.z, ma.w, mb.x, mb.y, mb.z, mb.w};
+      const float2 c[4] = {make_float2(ma.x, ma.y), make_float2(ma.z, ma.w), make_float2(mb.x, mb.y), make_float2(mb.z, mb.w)};
       mur.x += w[0]; mur.y += w[1]; mur.z += w[2]; mur.w += w[3];
       muc0.x = fmaf(pk, ma.x, muc0.x); muc0.y = fmaf(pk, ma.y, muc0.y); muc0.z = fmaf(pk, ma.z, muc0.z); muc0.w = fmaf(pk, ma.w, muc0.w);
       muc1.x = fmaf(pk, mb.x, muc1.x); muc1.y = fmaf(pk, mb.y, muc1.y); muc1.z = fmaf(pk, mb.z, muc1.z); muc1.w = fmaf(pk, mb.w, muc1.w);
 #pragma unroll
       for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[a][j] = fmaf(w[a], c[j], acc[a][j]);
+        for (int j = 0; j < 4; ++j) acc[a][j] = __ffma2_rn(make_float2(w[a], w[a]), c[j], acc[a][j]);
     }
     __syncwarp();                                                      // the buffer is refilled two items on
     if (ch != nch - 1) continue;
@@ -151,10 +151,10 @@ __global__ void __launch_bounds__(MM_WARPS * 32) moe_moments_tile_kernel(const f
       for (int h = 0; h < 2; ++h) {
         if (!(h ? cok1 : cok0)) continue;
         float4 b4 = Bo ? *reinterpret_cast<const float4*>(Bo + 4 * h) : make_float4(0.f, 0.f, 0.f, 0.f);
-        b4.x += acc[a][4 * h] - mrow[a] * mcol[4 * h];
-        b4.y += acc[a][4 * h + 1] - mrow[a] * mcol[4 * h + 1];
-        b4.z += acc[a][4 * h + 2] - mrow[a] * mcol[4 * h + 2];
-        b4.w += acc[a][4 * h + 3] - mrow[a] * mcol[4 * h + 3];
+        b4.x += acc[a][2 * h].x - mrow[a] * mcol[4 * h];
+        b4.y += acc[a][2 * h].y - mrow[a] * mcol[4 * h + 1];
+        b4.z += acc[a][2 * h + 1].x - mrow[a] * mcol[4 * h + 2];
+        b4.w += acc[a][2 * h + 1].y - mrow[a] * mcol[4 * h + 3];
         *reinterpret_cast<float4*>(So + 4 * h) = b4;
       }
     }
