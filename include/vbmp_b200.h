@@ -178,6 +178,13 @@ int vbmp_hmm_forward_backward(const float* logits, const float* trans, const flo
  * (transforms/MatrixNormalWishart.py:236-247).  accumulate != 0 adds to C; bias may be NULL.                            */
 int vbmp_rowgemm(const float* A, int lda, const float* B, int ldb, const float* bias, float* C, int ldc,
                  long long N, int Kd, int M, int accumulate, void* stream);
+/* The same product given a workspace of vbmp_rowgemm_workspace_bytes(Kd, M, has_bias) bytes: shapes with a short reduction
+ * and a wide output (Kd (+1 with a bias) <= 64 after padding to 8, M >= 64, N >= 128 — the two products of predict) run on a
+ * tcgen05 kernel (A tile in tensor memory, B packed per 128-column chunk, 3-term TF32) that is bound by the bytes of C it
+ * writes; every other shape, or workspace == NULL, takes vbmp_rowgemm's kernel.                                          */
+size_t vbmp_rowgemm_workspace_bytes(int Kd, int M, int has_bias);
+int vbmp_rowgemm_ex(const float* A, int lda, const float* B, int ldb, const float* bias, float* C, int ldc,
+                    long long N, int Kd, int M, int accumulate, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- per-sample covariance terms --------------------------------------------------------------------
  * C[n][k] = (accumulate ? C[n][k] : 0) + alpha * sum_f A[n][f] B[f][k]: the trace terms of

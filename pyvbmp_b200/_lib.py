@@ -72,6 +72,8 @@ def lib():
         L.vbmp_diag_estep_workspace_bytes.argtypes = [c_longlong, c_int, c_int, c_int, c_int]
         L.vbmp_zpack_bytes.restype = c_size_t
         L.vbmp_zpack_bytes.argtypes = [c_longlong, c_int, c_int]
+        L.vbmp_rowgemm_workspace_bytes.restype = c_size_t
+        L.vbmp_rowgemm_workspace_bytes.argtypes = [c_int, c_int, c_int]
         L.vbmp_rowterm_workspace_bytes.restype = c_size_t
         L.vbmp_rowterm_workspace_bytes.argtypes = [c_int, c_int]
         L.vbmp_wsum_workspace_bytes.restype = c_size_t
@@ -88,6 +90,7 @@ EXPORTS = (
     "vbmp_zpack_bytes", "vbmp_gram_zpack", "vbmp_gram_ex_workspace_bytes", "vbmp_gram_ex",
     "vbmp_diag_estep_workspace_bytes", "vbmp_diag_estep", "vbmp_diag_estep_rpack", "vbmp_mnw_prep_ex", "vbmp_moe_moments", "vbmp_rowgemm",
     "vbmp_wsum_workspace_bytes", "vbmp_wsum", "vbmp_rowterm_workspace_bytes", "vbmp_rowterm",
+    "vbmp_rowgemm_workspace_bytes", "vbmp_rowgemm_ex",
 )
 
 
@@ -496,9 +499,11 @@ def rowgemm(A, B, bias=None, out=None, accumulate=False):
         assert not accumulate
         out = torch.empty((N, M), dtype=torch.float32, device=dev)
     assert out.shape == (N, M) and out.stride(1) == 1
-    _call("vbmp_rowgemm", dev, c_void_p(A.data_ptr()), c_int(A.stride(0)), c_void_p(B.data_ptr()), c_int(B.stride(0)), _ptr(bias),
+    nbytes = int(lib().vbmp_rowgemm_workspace_bytes(c_int(Kd), c_int(M), c_int(int(bias is not None)))) if not FORCE_SIMT else 0
+    ws = _workspace(nbytes, dev) if nbytes else None
+    _call("vbmp_rowgemm_ex", dev, c_void_p(A.data_ptr()), c_int(A.stride(0)), c_void_p(B.data_ptr()), c_int(B.stride(0)), _ptr(bias),
           c_void_p(out.data_ptr()), c_int(out.stride(0)), c_longlong(N), c_int(Kd), c_int(M), c_int(int(bool(accumulate))),
-          _stream(dev))
+          _ptr(ws), c_size_t(ws.numel() if ws is not None else 0), _stream(dev))
     return out
 
 

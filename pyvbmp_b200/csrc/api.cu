@@ -66,6 +66,10 @@ int launch_moe_moments(const float* mean, const float* p, const float* base, lon
                        cudaStream_t st);
 int launch_rowgemm(const float* A, int lda, const float* B, int ldb, const float* bias, float* C, int ldc, long long N, int Kd,
                    int M, int accumulate, cudaStream_t st);
+bool rowwide_umma_supported(long long N, int Kd, int M, bool bias);
+size_t rowwide_umma_workspace_bytes(int Kd, int M, bool bias);
+int launch_rowwide_umma(const float* A, int lda, const float* B, int ldb, const float* bias, float* C, int ldc, long long N, int Kd,
+                        int M, int accumulate, void* ws, size_t ws_bytes, cudaStream_t st);
 bool rowterm_umma_supported(long long N, int F, int K, int lda);
 size_t rowterm_umma_workspace_bytes(int F, int K);
 int launch_rowterm_umma(const float* A, int lda, const float* B, int ldb, float* C, int ldc, long long N, int F, int K,
@@ -460,6 +464,20 @@ int vbmp_moe_moments(const float* mean, const float* p, const float* base, long 
 int vbmp_rowgemm(const float* A, int lda, const float* B, int ldb, const float* bias, float* C, int ldc,
                  long long N, int Kd, int M, int accumulate, void* stream) {
   if (!A || !B || !C) { set_error("rowgemm: NULL argument"); return VBMP_ERR_SHAPE; }
+  return launch_rowgemm(A, lda, B, ldb, bias, C, ldc, N, Kd, M, accumulate, (cudaStream_t)stream);
+}
+
+size_t vbmp_rowgemm_workspace_bytes(int Kd, int M, int has_bias) {
+  return (Kd >= 1 && M >= 1 && rowwide_umma_supported(128, Kd, M, has_bias != 0)) ? rowwide_umma_workspace_bytes(Kd, M, has_bias != 0) : 0;
+}
+
+int vbmp_rowgemm_ex(const float* A, int lda, const float* B, int ldb, const float* bias, float* C, int ldc,
+                    long long N, int Kd, int M, int accumulate, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!A || !B || !C) { set_error("rowgemm: NULL argument"); return VBMP_ERR_SHAPE; }
+  // short reduction, wide output: the tcgen05 kernel (needs the workspace for the packed B); anything else: mma.sync kernel
+  if (workspace && N >= 128 && Kd >= 1 && M >= 1 && lda >= Kd && ldb >= M && ldc >= M && rowwide_umma_supported(N, Kd, M, bias != nullptr) &&
+      workspace_bytes >= rowwide_umma_workspace_bytes(Kd, M, bias != nullptr))
+    return launch_rowwide_umma(A, lda, B, ldb, bias, C, ldc, N, Kd, M, accumulate, workspace, workspace_bytes, (cudaStream_t)stream);
   return launch_rowgemm(A, lda, B, ldb, bias, C, ldc, N, Kd, M, accumulate, (cudaStream_t)stream);
 }
 

@@ -116,14 +116,14 @@ class MixtureofLinearTransforms():
                 print('MixLinearTransform: Percent Change in ELBO = ', ((ELBO - self.ELBO_last) / self.ELBO_last.abs()).data * 100)
             self.ELBO_last = ELBO
 
-    PREDICT_ROWS = 1 << 16       # rows per block of the (rows, K, n) temporaries of the moment sums
+    PREDICT_ROWS = 1 << 17       # rows per block of the (rows, K, n) temporaries of the moment sums (1 GiB at K n = 2048)
 
     def predict(self, X):
         """transforms/MixtureofLinearTransforms.py:91-108: mixture-of-experts predictive distribution of Y and the gate
         probabilities for inputs X (..., p, 1).  On the CUDA path the gate probabilities come from the fused E-step kernel
         (K2, softmax epilogue) on the whitened form of the per-component evidence (MatrixNormalWishart._predict_factors);
-        the component means and sum_k p_k ESigma_k are one GEMM each per block of rows (shared operands), the per-sample
-        weighted rank-K update is vbmp_moe_moments (one warp per sample)."""
+        the component means and sum_k p_k ESigma_k are one product each per block of rows (shared operands: vbmp_rowgemm_ex,
+        tcgen05), the per-sample weighted rank-K update is vbmp_moe_moments (one warp per sample)."""
         from .mvn import MultivariateNormal_vector_format
         W = self.W
         if not (isinstance(W, MatrixNormalWishart) and not isinstance(W, MatrixNormalGamma) and self.batch_dim == 0

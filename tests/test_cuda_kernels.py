@@ -458,3 +458,24 @@ def test_rowterm_kernel(N, F, K, lda, acc):
         ref = ref + C0.double()
     scale = 0.5 * (A.abs().double() @ B.abs().double()) + (C0.abs().double() if acc else 0.0)
     assert float(((out.double() - ref).abs() / scale).max()) <= 2e-6
+
+
+@pytest.mark.parametrize("N,Kd,M,bias,acc", [(128, 8, 64, False, False), (40000, 33, 2048, False, True), (20000, 63, 1000, True, False),
+                                              (19000, 17, 204, True, True), (70000, 64, 1024, False, False)])
+def test_rowgemm_short_reduction_wide_output(N, Kd, M, bias, acc):
+    """The tcgen05 kernel behind vbmp_rowgemm_ex (A tile in tensor memory, packed 128-column B chunks, output transposed
+    through shared memory): reduction lengths that need zero padding to 8, a bias row that is the 64th reduction index,
+    a last column chunk that is not full, a ragged last row tile, several tiles per CTA, accumulation."""
+    g = torch.Generator(device=DEV).manual_seed(N + Kd + M)
+    A = torch.randn(N, Kd, generator=g, device=DEV) * 1.7 + 0.3
+    B = torch.randn(Kd, M, generator=g, device=DEV)
+    b = torch.randn(M, generator=g, device=DEV) if bias else None
+    C0 = torch.randn(N, M, generator=g, device=DEV) if acc else None
+    ref = A.double() @ B.double()
+    if bias:
+        ref = ref + b.double()
+    if acc:
+        ref = ref + C0.double()
+    out = _lib.rowgemm(A, B, bias=b, out=None if not acc else C0.clone(), accumulate=acc)
+    scale = float((A.abs().double() @ B.abs().double()).max())
+    assert float((out.double() - ref).abs().max()) <= 2e-6 * scale
