@@ -13,6 +13,7 @@
 // (128 B per cycle per SM), not the flops: the first version kept a full ROW of Sigma_s per lane and therefore every lane
 // read the whole mean vector of every component (132 bytes per lane, 4.2 KB per warp and component — 19.9 ms per 1 Mi
 // samples at n = 32, K = 64, measured).  Other n take that simpler row-per-lane kernel.
+#include <cstdlib>
 #include "common.cuh"
 
 namespace vbmp {
@@ -161,6 +162,135 @@ __global__ void __launch_bounds__(MM_WARPS * 32) moe_moments_tile_kernel(const f
   }
 }
 
+// ---- n = 16 / 32: the per-sample rank-K update as a tensor-core SYRK -------------------------------------------------
+// Sigma_s - base_s + mu_s mu_s^T = M^T diag(p) M with M = the sample's (K x n) means: per warp and sample one
+// (n x K) (K x n) product on mma.sync.m16n8k8 (TF32, 3-term split: fp32-grade).  Both operands are the SAME staged rows
+// of M — the A fragment (scaled by p) and the B fragment of a K-step need exactly the elements M[8 ks + t (+4)][g + 8 c],
+// c = 0 .. n/8 - 1 — so a K-step costs n/4 four-byte shared-memory loads per lane (row stride 40 floats: conflict free)
+// instead of the 3 sixteen-byte loads PER COMPONENT of the register-tiled kernel above, and no FMAs at all; mu comes out
+// of one extra column tile whose B operand is the constant e_0.  What is left is the kernel's traffic (means in, base in,
+// Sigma out).
+constexpr int MQ_KC = 32;              // components per staged chunk
+constexpr int MQ_WARPS = 4;
+constexpr int MQ_RS = 40;              // row stride (floats) of a staged chunk
+
+__device__ __forceinline__ void mq_split(float x, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+  const float r = x - __uint_as_float(hi);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+}
+__device__ __forceinline__ void mq_mma(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <int NN>                      // n = 16 or 32
+__global__ void __launch_bounds__(MQ_WARPS * 32) moe_moments_mma_kernel(const float* __restrict__ mean, const float* __restrict__ p,
+                                                                        const float* __restrict__ base, long long N, int K,
+                                                                        float* __restrict__ mu, float* __restrict__ Sigma) {
+  constexpr int MT = NN / 16, NT = NN / 8, NC = NN / 8;          // row tiles, column tiles, distinct columns per lane
+  extern __shared__ __align__(16) float mq_smem[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const long long w0 = (long long)blockIdx.x * MQ_WARPS + wib;
+  const long long nw = (long long)gridDim.x * MQ_WARPS;
+  float* buf = mq_smem + (size_t)wib * (2 * MQ_KC * MQ_RS + 32);
+  float* mus = buf + 2 * MQ_KC * MQ_RS;                           // the sample's mu, for the final mu mu^T
+  const int nch = (K + MQ_KC - 1) / MQ_KC;
+  const long long nsamp = w0 < N ? (N - w0 + nw - 1) / nw : 0;
+  const long long items = nsamp * nch;
+  auto prefetch = [&](long long it) {
+    const long long s = w0 + (it / nch) * nw;
+    const int kc0 = (int)(it % nch) * MQ_KC;
+    const int rows = min(MQ_KC, K - kc0);
+    const float* src = mean + ((size_t)s * K + kc0) * NN;
+    float* dst = buf + (size_t)(it & 1) * MQ_KC * MQ_RS;
+    for (int e = lane; e < MQ_KC * (NN / 4); e += 32) {             // 16-byte pieces; rows past K are zero filled
+      const int r = e / (NN / 4), c4 = (e % (NN / 4)) * 4;
+      if (r < rows) mm_cp_async16(dst + r * MQ_RS + c4, src + (size_t)r * NN + c4);
+      else *reinterpret_cast<float4*>(dst + r * MQ_RS + c4) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    mm_cp_async_commit();
+  };
+  float acc[MT][NT][4], am[MT][4];
+  const uint32_t one = (g == 0) ? 0x3f800000u : 0u;                // B operand of the mu tile: column 0 = 1
+  if (items > 0) prefetch(0);
+  for (long long it = 0; it < items; ++it) {
+    const long long s = w0 + (it / nch) * nw;
+    const int ch = (int)(it % nch), kc0 = ch * MQ_KC;
+    if (it + 1 < items) { prefetch(it + 1); mm_cp_async_wait<1>(); } else { mm_cp_async_wait<0>(); }
+    __syncwarp();
+    if (ch == 0) {
+#pragma unroll
+      for (int a = 0; a < MT; ++a) {
+#pragma unroll
+        for (int b = 0; b < NT; ++b)
+#pragma unroll
+          for (int v = 0; v < 4; ++v) acc[a][b][v] = 0.f;
+#pragma unroll
+        for (int v = 0; v < 4; ++v) am[a][v] = 0.f;
+      }
+    }
+    const float* mb_ = buf + (size_t)(it & 1) * MQ_KC * MQ_RS;
+    const float pl = (kc0 + lane < K) ? __ldg(p + (size_t)s * K + kc0 + lane) : 0.f;     // lane k holds p of component kc0 + k
+#pragma unroll
+    for (int ks = 0; ks < MQ_KC / 8; ++ks) {
+      const float p0 = __shfl_sync(0xffffffffu, pl, 8 * ks + t), p1 = __shfl_sync(0xffffffffu, pl, 8 * ks + t + 4);
+      // M[8 ks + t][g + 8 c], M[8 ks + t + 4][g + 8 c]: the B fragments as they are, the A fragments scaled by p
+      uint32_t bh[NC][2], bl[NC][2], ah[NC][2], al[NC][2];
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        const float m0 = mb_[(8 * ks + t) * MQ_RS + g + 8 * c], m1 = mb_[(8 * ks + t + 4) * MQ_RS + g + 8 * c];
+        mq_split(m0, bh[c][0], bl[c][0]);
+        mq_split(m1, bh[c][1], bl[c][1]);
+        mq_split(p0 * m0, ah[c][0], al[c][0]);
+        mq_split(p1 * m1, ah[c][1], al[c][1]);
+      }
+#pragma unroll
+      for (int a = 0; a < MT; ++a) {
+        // rows g + 16 a (c = 2a) and g + 8 + 16 a (c = 2a + 1): a0 = (g, t), a1 = (g + 8, t), a2 = (g, t + 4), a3 = (g + 8, t + 4)
+        const uint32_t fh[4] = {ah[2 * a][0], ah[2 * a + 1][0], ah[2 * a][1], ah[2 * a + 1][1]};
+        const uint32_t fl[4] = {al[2 * a][0], al[2 * a + 1][0], al[2 * a][1], al[2 * a + 1][1]};
+#pragma unroll
+        for (int b = 0; b < NT; ++b) {
+          mq_mma(acc[a][b], fl, bh[b][0], bh[b][1]);              // small terms first
+          mq_mma(acc[a][b], fh, bl[b][0], bl[b][1]);
+          mq_mma(acc[a][b], fh, bh[b][0], bh[b][1]);
+        }
+        mq_mma(am[a], fl, one, one);
+        mq_mma(am[a], fh, one, one);
+      }
+    }
+    __syncwarp();                                                  // the buffer is refilled two items on
+    if (ch != nch - 1) continue;
+    // mu[i]: column 0 of the mu tile lives in the lanes with t == 0 (c0: row g, c2: row g + 8)
+    if (t == 0) {
+#pragma unroll
+      for (int a = 0; a < MT; ++a) { mus[16 * a + g] = am[a][0]; mus[16 * a + g + 8] = am[a][2]; }
+    }
+    __syncwarp();
+    if (lane < NN) mu[(size_t)s * NN + lane] = mus[lane];
+#pragma unroll
+    for (int a = 0; a < MT; ++a)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int i = 16 * a + g + 8 * h;
+        const float mi = mus[i];
+#pragma unroll
+        for (int b = 0; b < NT; ++b) {
+          const int j = 8 * b + 2 * t;
+          const size_t o = ((size_t)s * NN + i) * NN + j;
+          float2 r = base ? *reinterpret_cast<const float2*>(base + o) : make_float2(0.f, 0.f);
+          r.x += acc[a][b][2 * h] - mi * mus[j];
+          r.y += acc[a][b][2 * h + 1] - mi * mus[j + 1];
+          *reinterpret_cast<float2*>(Sigma + o) = r;
+        }
+      }
+    __syncwarp();                                                  // mus is rewritten by the next sample
+  }
+}
+
 int launch_moe_moments(const float* mean, const float* p, const float* base, long long N, int K, int n, float* mu, float* Sigma,
                        cudaStream_t st) {
   if (N < 0 || K < 1 || n < 1 || n > 32) { set_error("moe_moments: bad shape N=%lld K=%d n=%d (n <= 32)", N, K, n); return VBMP_ERR_SHAPE; }
@@ -170,6 +300,21 @@ int launch_moe_moments(const float* mean, const float* p, const float* base, lon
   const long long cap = (long long)num_sms() * 16;
   if (blocks > cap) blocks = cap;
   const bool aligned = ((size_t)mean % 16 == 0) && ((size_t)Sigma % 16 == 0) && ((size_t)mu % 16 == 0) && (!base || (size_t)base % 16 == 0);
+  static const int use_mma = [] { const char* e = getenv("VBMP_MOE_MMA"); return e ? atoi(e) : 1; }();
+  if ((n == 32 || n == 16) && aligned && use_mma) {
+    const size_t smem = (size_t)MQ_WARPS * (2 * MQ_KC * MQ_RS + 32) * sizeof(float);    // 41.5 KB: five CTAs per SM
+    long long tb = (N + MQ_WARPS - 1) / MQ_WARPS;
+    const long long tcap = (long long)num_sms() * 5 * 4;
+    if (tb > tcap) tb = tcap;
+    if (n == 32) {
+      cudaFuncSetAttribute(moe_moments_mma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      moe_moments_mma_kernel<32><<<(unsigned)tb, MQ_WARPS * 32, smem, st>>>(mean, p, base, N, K, mu, Sigma);
+    } else {
+      cudaFuncSetAttribute(moe_moments_mma_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      moe_moments_mma_kernel<16><<<(unsigned)tb, MQ_WARPS * 32, smem, st>>>(mean, p, base, N, K, mu, Sigma);
+    }
+    return check_launch("moe_moments_mma");
+  }
   if ((n & 3) == 0 && aligned) {
     const size_t smem = (size_t)MM_WARPS * 2 * MM_KC * n * sizeof(float);       // 64 KB at n = 32: three CTAs per SM
     long long tb = (N + MM_WARPS - 1) / MM_WARPS;

@@ -354,10 +354,11 @@ def test_misaligned_views_are_rebased():
 
 
 @pytest.mark.parametrize("N,K,n,with_base", [(5000, 64, 32, True), (3001, 8, 16, True), (777, 5, 12, False), (1025, 20, 7, True),
-                                              (300, 3, 1, False)])
+                                              (300, 3, 1, False), (4000, 40, 32, False), (2000, 100, 16, True), (3, 33, 32, True)])
 def test_moe_moments_kernel(N, K, n, with_base):
     """vbmp_moe_moments (the per-sample part of MixtureofLinearTransforms.predict, transforms/MixtureofLinearTransforms.py:
-    100-106) against an fp64 evaluation: both the 4 x 8 register-tiled kernel (n % 4 == 0) and the row-per-lane one."""
+    100-106) against an fp64 evaluation: the tensor-core SYRK kernel (n = 16, 32; K that needs zero-filled rows in the last
+    staged chunk), the 4 x 8 register-tiled kernel (other n % 4 == 0) and the row-per-lane one."""
     g = torch.Generator(device=DEV).manual_seed(N + n)
     mean = (torch.randn(N, K, n, generator=g, device=DEV) * 1.3 + 0.4).contiguous()
     p = torch.softmax(1.5 * torch.randn(N, K, generator=g, device=DEV), -1).contiguous()
