@@ -8,7 +8,8 @@ weighted Gram statistics [+ all-reduce] + NIW update) over the rank's rows.  At 
 BASELINE.json configs[1] (N=4 194 304, d=64, K=256, fp32); with N>1 ranks every rank owns the same
 number of rows (weak scaling, sample-sharded, one all-reduce of the statistics per iteration).
 Prints ONE JSON line on rank 0.  Besides the contract's keys the line carries
-  * `secondary` (N=1): BASELINE.json configs[2] (MixtureofLinearTransforms N=8 388 608, n=p=32, K=64) and configs[3]
+  * `secondary` (N=1): the rows next to the hot path, MixtureofLinearTransforms.update(pX, pY) / predict (SURVEY.md 8f,
+    against the HBM peak), and BASELINE.json configs[2] (MixtureofLinearTransforms N=8 388 608, n=p=32, K=64) and configs[3]
     (ARHMM 4096 sequences x T=1024, d=16, K=32), each timed the same way (ms/step, per-kernel ms, roofline fraction);
   * `cfg5` (N=8): BASELINE.json configs[4] at its stated size, 8 388 608 rows per GPU = 67 108 864 rows in total;
   * `e2e_iters20`: one public call update(X_pinned_host, iters=20) — the rows cross the host link once per call;
@@ -290,6 +291,39 @@ def secondary_cfg4(dev, peak, steps=5, warmup=3, S=4096, T=1024, d=16, Kc=32):
             "kernels_ms_per_step": {k: round(v["ms_per_step"], 4) for k, v in kern.items()}, "elbo_last": float(m.ELBO_last)}
 
 
+def secondary_molt_beliefs(dev, peak, steps=3, warmup=2, N=1 << 20, p=32, n=32, Kc=64, hbm=6546.2):
+    """SURVEY.md §8f #2 / #3 (the rows next to the hot path): MixtureofLinearTransforms.update(pX, pY) on Gaussian beliefs with
+    per-sample covariances, and MixtureofLinearTransforms.predict.  Both are bound by bytes (the flattened covariances in,
+    the predictive covariances out): reported against the measured HBM peak."""
+    import pyvbmp_b200 as V
+    g = torch.Generator(device=dev).manual_seed(3)
+    torch.manual_seed(0)
+    m = V.MixtureofLinearTransforms(n, p, Kc).to(dev)
+    X = torch.randn(N, p, 1, generator=g, device=dev)
+    W = torch.randn(Kc, n, p, generator=g, device=dev) / p ** 0.5
+    z = torch.randint(Kc, (N,), generator=g, device=dev)
+    Y = (torch.einsum("nij,nj->ni", W[z], X[..., 0]) + 0.1 * torch.randn(N, n, generator=g, device=dev)).unsqueeze(-1)
+    m.raw_update(X, Y, iters=2)
+    Sx = (0.01 * torch.eye(p, device=dev)).expand(N, p, p).contiguous()
+    Sy = (0.01 * torch.eye(n, device=dev)).expand(N, n, n).contiguous()
+    pX, pY = V.MultivariateNormal_vector_format(mu=X, Sigma=Sx), V.MultivariateNormal_vector_format(mu=Y, Sigma=Sy)
+    sync = lambda: torch.cuda.synchronize(dev)                                  # noqa: E731
+    ms_u, kern_u, l_u = time_steps(lambda: m.update(pX, pY, iters=1), steps, warmup, dev, sync)
+    ms_p, kern_p, l_p = time_steps(lambda: m.predict(X), steps, warmup, dev, sync)
+    # algorithmic bytes: update reads both covariance sets twice (E and M) + means + responsibilities out and in;
+    # predict reads the inputs and writes mu, Sigma and the gate probabilities
+    b_u = N * (2 * 4 * (p * p + n * n) + 2 * 4 * (p + n) + 2 * 4 * Kc)
+    b_p = N * (4 * p + 4 * n * n + 4 * n + 4 * Kc)
+    out = {}
+    for name, ms, kern, ln, by, what in (("molt_update_beliefs", ms_u, kern_u, l_u, b_u, "update(pX, pY)"),
+                                         ("molt_predict", ms_p, kern_p, l_p, b_p, "predict(X)")):
+        out[name] = {"workload": f"MixtureofLinearTransforms.{what}, N={N}, p={p}, n={n}, K={Kc}, per-sample covariances (SURVEY.md 8f)",
+                     "ms_per_step": ms / steps, "value": steps * N * Kc / (ms / 1e3), "unit": UNIT, "steps": steps, "warmup": warmup,
+                     "algorithmic_gb_per_step": by / 1e9, "hbm_frac": by / 1e9 / (ms / steps / 1e3) / hbm, "gpu_launches": ln,
+                     "kernels_ms_per_step": {k: round(v["ms_per_step"], 4) for k, v in kern.items()}}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -510,6 +544,12 @@ def main():
                     secondary[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
                 _lib.release_workspaces()
                 torch.cuda.empty_cache()
+            try:
+                secondary.update(secondary_molt_beliefs(dev, peak, hbm=peaks.get("hbm_gbs", 6546.2)))
+            except Exception as e:
+                secondary["molt_beliefs"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+            _lib.release_workspaces()
+            torch.cuda.empty_cache()
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             if _ALL_CPUS:
