@@ -2,12 +2,16 @@
 
 The mirrors in this package call the ctypes binding (`_lib.py`) directly; these registrations expose the same four hot
 entry points to code that wants dispatcher-visible ops (shape inference under FakeTensor / `torch.compile` graphs around
-the EM loop, profiler names).  CUDA only: there is no CPU kernel to register, a CPU tensor raises from the binding.
+the EM loop, profiler names); the widened rows are registered too.  CUDA only: there is no CPU kernel to register, a CPU tensor raises from the binding.
 
     torch.ops.vbmp.estep_logits(z0, z1, W, m, cst)              -> logits (N, K)
     torch.ops.vbmp.estep_assign(z0, z1, W, m, cst)              -> (p (N, K), logZn (N,), NA (K,), logZ ())
     torch.ops.vbmp.gram(z0, z1, p, diag)                        -> (K, D+1, D+1)
     torch.ops.vbmp.hmm_forward_backward(logits, trans, init)    -> (p (T,S,K), SEzz (S,K,K), SEz0 (S,K), logZ (S,))
+    torch.ops.vbmp.rowgemm(A, B, bias)                          -> A (N, Kd) @ B (Kd, M) (+ bias)          (predict's shared-operand products)
+    torch.ops.vbmp.rowterm(A, B, C, alpha)                      -> C (N, K) + alpha A (N, F) @ B (F, K)    (covariance trace terms)
+    torch.ops.vbmp.wsum(p, S)                                   -> p (N, K)^T @ S (N, F)                   (weighted covariance sums)
+    torch.ops.vbmp.moe_moments(mean, p, base)                   -> (mu (N, n), Sigma (N, n, n))            (mixture-of-experts moments)
 
 z0 (N, d0), z1 (N, d1) or None, W (K, Dp, Dp), m (K, Dp), cst (K,) as produced by vbmp_niw_prep / vbmp_mnw_prep (`_lib.niw_prep`).
 """
@@ -83,3 +87,54 @@ def hmm_forward_backward(logits: torch.Tensor, trans: torch.Tensor, init: torch.
 def _(logits, trans, init, ptemp=1.0):
     T, S, K = logits.shape
     return logits.new_empty((T, S, K)), logits.new_empty((S, K, K)), logits.new_empty((S, K)), logits.new_empty((S,))
+
+
+@torch.library.custom_op("vbmp::rowgemm", mutates_args=())
+def rowgemm(A: torch.Tensor, B: torch.Tensor, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    return _lib.rowgemm(_lib.f32(A), _lib.f32(B), bias=None if bias is None else _lib.f32(bias))
+
+
+@rowgemm.register_fake
+def _(A, B, bias=None):
+    return A.new_empty((A.shape[0], B.shape[1]))
+
+
+@torch.library.custom_op("vbmp::rowterm", mutates_args=())
+def rowterm(A: torch.Tensor, B: torch.Tensor, C: torch.Tensor, alpha: float = 1.0) -> torch.Tensor:
+    A, B = _lib.f32(A), _lib.f32(B)
+    out = _lib.f32(C).clone()
+    N, F = A.shape
+    K = B.shape[1]
+    if _lib.rowterm_supported(N, F, K, A.stride(0)):
+        return _lib.rowterm(A, B, C=out, alpha=alpha, accumulate=True)
+    return out.add_(_lib.rowgemm(A, B), alpha=alpha)
+
+
+@rowterm.register_fake
+def _(A, B, C, alpha=1.0):
+    return C.new_empty(C.shape)
+
+
+@torch.library.custom_op("vbmp::wsum", mutates_args=())
+def wsum(p: torch.Tensor, S: torch.Tensor) -> torch.Tensor:
+    p, S = _lib.f32(p), _lib.f32(S)
+    if _lib.wsum_supported(p.shape[0], p.shape[1], S.shape[1], S.stride(0)):
+        return _lib.wsum(p, S)
+    return _lib.rowgemm(p.t().contiguous(), S)                  # shapes outside the kernel's window
+
+
+@wsum.register_fake
+def _(p, S):
+    return p.new_empty((p.shape[1], S.shape[1]))
+
+
+@torch.library.custom_op("vbmp::moe_moments", mutates_args=())
+def moe_moments(mean: torch.Tensor, p: torch.Tensor, base: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    N, K, n = mean.shape
+    return _lib.moe_moments(_lib.f32(mean), _lib.f32(p), None if base is None else _lib.f32(base), N, K, n)
+
+
+@moe_moments.register_fake
+def _(mean, p, base=None):
+    N, K, n = mean.shape
+    return mean.new_empty((N, n)), mean.new_empty((N, n, n))

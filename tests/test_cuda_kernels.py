@@ -393,6 +393,18 @@ def test_torch_custom_ops_match_the_binding():
     assert torch.equal(p, p2.view(N, K)) and torch.equal(NA, NA2.view(K)) and torch.equal(lZ, lZ2.view(()))
     G = torch.ops.vbmp.gram(z0, z1, p, False)
     assert torch.equal(G, _lib.gram(z0, z1, N, 1, xg, p2.clone(), 1, xg, 1, K, Dp).view(K, d0 + d1 + 1, d0 + d1 + 1))
+    # the widened rows: products with the flattened covariances, mixture-of-experts moments
+    g = torch.Generator(device=DEV).manual_seed(5)
+    S = torch.randn(N, 256, generator=g, device=DEV)
+    L = torch.randn(256, K, generator=g, device=DEV)
+    assert torch.equal(torch.ops.vbmp.wsum(p, S), _lib.wsum(p, S))
+    assert torch.equal(torch.ops.vbmp.rowterm(S, L, lg, -0.5), _lib.rowterm(S, L, C=lg.clone(), alpha=-0.5, accumulate=True))
+    Bm, bias = torch.randn(d0, 512, generator=g, device=DEV), torch.randn(512, generator=g, device=DEV)
+    assert torch.equal(torch.ops.vbmp.rowgemm(z0, Bm, bias), _lib.rowgemm(z0, Bm, bias=bias))
+    mean = torch.randn(N, K, 16, generator=g, device=DEV)
+    mu, Sig = torch.ops.vbmp.moe_moments(mean, p, None)
+    mu2, Sig2 = _lib.moe_moments(mean, p, None, N, K, 16)
+    assert torch.equal(mu, mu2) and torch.equal(Sig, Sig2)
 
 
 @pytest.mark.parametrize("N,Kd,M,bias,acc", [(5000, 32, 2048, True, False), (3001, 64, 1024, False, False),

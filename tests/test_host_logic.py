@@ -113,7 +113,7 @@ def test_torch_custom_ops_are_registered_with_shape_inference():
     """torch.ops.vbmp.* (pyvbmp_b200/ops.py): registered with the dispatcher, fake-tensor shape functions in place."""
     import pyvbmp_b200.ops  # noqa: F401
     from torch._subclasses.fake_tensor import FakeTensorMode
-    for name in ("estep_logits", "estep_assign", "gram", "hmm_forward_backward"):
+    for name in ("estep_logits", "estep_assign", "gram", "hmm_forward_backward", "rowgemm", "rowterm", "wsum", "moe_moments"):
         assert hasattr(torch.ops.vbmp, name)
     with FakeTensorMode():
         z, W, m, c = torch.empty(100, 8), torch.empty(5, 8, 8), torch.empty(5, 8), torch.empty(5)
@@ -123,3 +123,8 @@ def test_torch_custom_ops_are_registered_with_shape_inference():
         assert torch.ops.vbmp.gram(z, torch.empty(100, 3), p, False).shape == (5, 12, 12)
         out = torch.ops.vbmp.hmm_forward_backward(torch.empty(7, 3, 4), torch.empty(4, 4), torch.empty(4))
         assert [tuple(t.shape) for t in out] == [(7, 3, 4), (3, 4, 4), (3, 4), (3,)]
+        assert torch.ops.vbmp.rowgemm(torch.empty(100, 9), torch.empty(9, 40), torch.empty(40)).shape == (100, 40)
+        assert torch.ops.vbmp.rowterm(torch.empty(100, 64), torch.empty(64, 5), torch.empty(100, 5), -0.5).shape == (100, 5)
+        assert torch.ops.vbmp.wsum(torch.empty(100, 8), torch.empty(100, 64)).shape == (8, 64)
+        mu, Sig = torch.ops.vbmp.moe_moments(torch.empty(100, 8, 16), torch.empty(100, 8), None)
+        assert mu.shape == (100, 16) and Sig.shape == (100, 16, 16)
