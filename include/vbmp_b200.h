@@ -186,6 +186,17 @@ size_t vbmp_rowgemm_workspace_bytes(int Kd, int M, int has_bias);
 int vbmp_rowgemm_ex(const float* A, int lda, const float* B, int ldb, const float* bias, float* C, int ldc,
                     long long N, int Kd, int M, int accumulate, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- responsibilities from given logits ---------------------------------------------------------------------------------
+ * p[n][k] = exp(l[n][k] + colbias[k] - logZ_n), logZ_n = logsumexp_k (l[n][k] + colbias[k]), NA[k] = sum_n p[n][k],
+ * logZ = sum_n logZ_n: the responsibility step when the logits do not come out of one vbmp_estep launch —
+ * MixtureofLinearTransforms.update_assignments_given_pX_pY (transforms/MixtureofLinearTransforms.py:62-69: vbmp_estep mode 0 on
+ * the means, vbmp_rowterm for the covariance terms, then this with colbias = Dirichlet.loggeomean()).  logits (N, K, row
+ * stride ldl) and p (N, K, row stride ldp) may be the same buffer; colbias may be NULL.  NA / logZ are reduced in a fixed
+ * order (bit-reproducible).                                                                                             */
+size_t vbmp_softmax_rows_workspace_bytes(long long N, int K);
+int vbmp_softmax_rows(const float* logits, int ldl, const float* colbias, long long N, int K, float* p, int ldp,
+                      float* logZn, float* NA, float* logZ, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- per-sample covariance terms --------------------------------------------------------------------
  * C[n][k] = (accumulate ? C[n][k] : 0) + alpha * sum_f A[n][f] B[f][k]: the trace terms of
  * MatrixNormalWishart.Elog_like_given_pX_pY (transforms/MatrixNormalWishart.py:236-247), -1/2 tr(Sigma_y,n E[invSigma_k])

@@ -72,6 +72,8 @@ def lib():
         L.vbmp_diag_estep_workspace_bytes.argtypes = [c_longlong, c_int, c_int, c_int, c_int]
         L.vbmp_zpack_bytes.restype = c_size_t
         L.vbmp_zpack_bytes.argtypes = [c_longlong, c_int, c_int]
+        L.vbmp_softmax_rows_workspace_bytes.restype = c_size_t
+        L.vbmp_softmax_rows_workspace_bytes.argtypes = [c_longlong, c_int]
         L.vbmp_rowgemm_workspace_bytes.restype = c_size_t
         L.vbmp_rowgemm_workspace_bytes.argtypes = [c_int, c_int, c_int]
         L.vbmp_rowterm_workspace_bytes.restype = c_size_t
@@ -90,7 +92,7 @@ EXPORTS = (
     "vbmp_zpack_bytes", "vbmp_gram_zpack", "vbmp_gram_ex_workspace_bytes", "vbmp_gram_ex",
     "vbmp_diag_estep_workspace_bytes", "vbmp_diag_estep", "vbmp_diag_estep_rpack", "vbmp_mnw_prep_ex", "vbmp_moe_moments", "vbmp_rowgemm",
     "vbmp_wsum_workspace_bytes", "vbmp_wsum", "vbmp_rowterm_workspace_bytes", "vbmp_rowterm",
-    "vbmp_rowgemm_workspace_bytes", "vbmp_rowgemm_ex",
+    "vbmp_rowgemm_workspace_bytes", "vbmp_rowgemm_ex", "vbmp_softmax_rows_workspace_bytes", "vbmp_softmax_rows",
 )
 
 
@@ -505,6 +507,24 @@ def rowgemm(A, B, bias=None, out=None, accumulate=False):
           c_void_p(out.data_ptr()), c_int(out.stride(0)), c_longlong(N), c_int(Kd), c_int(M), c_int(int(bool(accumulate))),
           _ptr(ws), c_size_t(ws.numel() if ws is not None else 0), _stream(dev))
     return out
+
+
+def softmax_rows(logits, colbias=None, out=None):
+    """logits (N, K) (+ colbias (K,)) -> (p (N, K), logZn (N,), NA (K,), logZ ()) (vbmp_softmax_rows); out may be logits itself."""
+    dev = logits.device
+    N, K = logits.shape
+    assert logits.stride(1) == 1 and logits.dtype == torch.float32
+    if out is None:
+        out = torch.empty((N, K), dtype=torch.float32, device=dev)
+    logZn = torch.empty((N,), dtype=torch.float32, device=dev)
+    NA = torch.empty((K,), dtype=torch.float32, device=dev)
+    logZ = torch.empty((), dtype=torch.float32, device=dev)
+    nbytes = lib().vbmp_softmax_rows_workspace_bytes(c_longlong(N), c_int(K))
+    ws = _workspace(nbytes, dev)
+    _call("vbmp_softmax_rows", dev, c_void_p(logits.data_ptr()), c_int(logits.stride(0) if N > 0 else K), _ptr(colbias), c_longlong(N), c_int(K),
+          c_void_p(out.data_ptr()), c_int(out.stride(0) if N > 0 else K), _ptr(logZn), _ptr(NA), _ptr(logZ), _ptr(ws), c_size_t(ws.numel()),
+          _stream(dev))
+    return out, logZn, NA, logZ
 
 
 def rowterm_supported(N, F, K, lda):

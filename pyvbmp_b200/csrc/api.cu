@@ -66,6 +66,9 @@ int launch_moe_moments(const float* mean, const float* p, const float* base, lon
                        cudaStream_t st);
 int launch_rowgemm(const float* A, int lda, const float* B, int ldb, const float* bias, float* C, int ldc, long long N, int Kd,
                    int M, int accumulate, cudaStream_t st);
+size_t softmax_rows_workspace_bytes(long long N, int K);
+int launch_softmax_rows(const float* l, int ldl, const float* bias, long long N, int K, float* p, int ldp, float* logZn,
+                        float* NA, float* logZ, void* ws, size_t ws_bytes, cudaStream_t st);
 bool rowwide_umma_supported(long long N, int Kd, int M, bool bias);
 size_t rowwide_umma_workspace_bytes(int Kd, int M, bool bias);
 int launch_rowwide_umma(const float* A, int lda, const float* B, int ldb, const float* bias, float* C, int ldc, long long N, int Kd,
@@ -465,6 +468,14 @@ int vbmp_rowgemm(const float* A, int lda, const float* B, int ldb, const float* 
                  long long N, int Kd, int M, int accumulate, void* stream) {
   if (!A || !B || !C) { set_error("rowgemm: NULL argument"); return VBMP_ERR_SHAPE; }
   return launch_rowgemm(A, lda, B, ldb, bias, C, ldc, N, Kd, M, accumulate, (cudaStream_t)stream);
+}
+
+size_t vbmp_softmax_rows_workspace_bytes(long long N, int K) { return (N < 0 || K < 1) ? 0 : softmax_rows_workspace_bytes(N, K); }
+
+int vbmp_softmax_rows(const float* logits, int ldl, const float* colbias, long long N, int K, float* p, int ldp,
+                      float* logZn, float* NA, float* logZ, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!NA || !logZ || (N > 0 && (!logits || !p || !logZn))) { set_error("softmax_rows: NULL argument"); return VBMP_ERR_SHAPE; }
+  return launch_softmax_rows(logits, ldl, colbias, N, K, p, ldp, logZn, NA, logZ, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 size_t vbmp_rowgemm_workspace_bytes(int Kd, int M, int has_bias) {

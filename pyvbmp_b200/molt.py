@@ -90,7 +90,12 @@ class MixtureofLinearTransforms():
 
     def update_assignments_given_pX_pY(self, pX, pY):
         """transforms/MixtureofLinearTransforms.py:62-69: max-shifted softmax of the expected log likelihoods."""
-        log_p = self.W.Elog_like_given_pX_pY(pX.unsqueeze(-3), pY.unsqueeze(-3)) + self.pi.loggeomean()
+        ELL = self.W.Elog_like_given_pX_pY(pX.unsqueeze(-3), pY.unsqueeze(-3))
+        if ELL.is_cuda and ELL.ndim == 2 and ELL.is_contiguous() and ELL.dtype == torch.float32 and self.batch_dim == 0:
+            # one pass: + loggeomean, logsumexp, responsibilities (in place over the logits), NA (vbmp_softmax_rows)
+            self.p, self.logZ, self.NA, _ = _lib.softmax_rows(ELL, colbias=_lib.f32(self.pi.loggeomean()), out=ELL)
+            return
+        log_p = ELL + self.pi.loggeomean()
         self.logZ = torch.logsumexp(log_p, -1)
         self.p = (log_p - self.logZ.unsqueeze(-1)).exp()
         self.NA = None
@@ -110,7 +115,7 @@ class MixtureofLinearTransforms():
         for i in range(iters):
             self.update_assignments_given_pX_pY(pX, pY)
             ELBO = self.ELBO()
-            self.pi.ss_update(self.p.sum(0), lr=lr)
+            self.pi.ss_update(self.NA if (self.NA is not None and self.p.ndim == 2) else self.p.sum(0), lr=lr)
             self.W.update(pX.unsqueeze(-3), pY.unsqueeze(-3), p=self.p, lr=lr)
             if verbose:
                 print('MixLinearTransform: Percent Change in ELBO = ', ((ELBO - self.ELBO_last) / self.ELBO_last.abs()).data * 100)

@@ -492,3 +492,25 @@ def test_rowgemm_short_reduction_wide_output(N, Kd, M, bias, acc):
     out = _lib.rowgemm(A, B, bias=b, out=None if not acc else C0.clone(), accumulate=acc)
     scale = float((A.abs().double() @ B.abs().double()).max())
     assert float((out.double() - ref).abs().max()) <= 2e-6 * scale
+
+
+@pytest.mark.parametrize("N,K,bias,inplace", [(5000, 64, True, True), (129, 5, False, False), (3001, 700, True, True),
+                                               (260, 2049, False, True), (70000, 32, True, False)])
+def test_softmax_rows_kernel(N, K, bias, inplace):
+    """vbmp_softmax_rows against an fp64 evaluation: responsibilities, per-row log normaliser, column sums, their
+    bit-reproducibility, in place over the logits and into a separate buffer, a row-strided logits view."""
+    g = torch.Generator(device=DEV).manual_seed(N + K)
+    wide = 6.0 * torch.randn(N, K + 4, generator=g, device=DEV)
+    lg = wide[:, :K]
+    b = torch.randn(K, generator=g, device=DEV) if bias else None
+    L = lg.double() + (b.double() if bias else 0.0)
+    lz = torch.logsumexp(L, -1)
+    P = (L - lz[:, None]).exp()
+    src = lg.clone() if inplace else lg
+    p, lzn, NA, lZ = _lib.softmax_rows(src, colbias=b, out=src if inplace else None)
+    assert float((p.double() - P).abs().max()) <= 2e-6
+    assert float((lzn.double() - lz).abs().max()) <= 2e-6 * float(L.abs().max())
+    assert float(((NA.double() - P.sum(0)).abs() / P.sum(0).clamp_min(1.0)).max()) <= 1e-5
+    assert abs(float(lZ.double() - lz.sum())) <= 1e-6 * abs(float(lz.sum()))
+    p2, lzn2, NA2, lZ2 = _lib.softmax_rows(lg.clone(), colbias=b)
+    assert torch.equal(NA, NA2) and torch.equal(lZ, lZ2) and torch.equal(p, p2)
