@@ -391,8 +391,6 @@ def _note_path(what, N, GX, G, K, Dp, d0, d1, weighted):
         why.append(f"replica / extra-event groups (G={G}, GX={GX})")
     if Dp not in _TC_DP:
         why.append(f"padded feature dimension {Dp}")
-    if what == "estep" and K > 512:
-        why.append(f"K={K} > 512")
     if what == "gram":
         if not weighted:
             why.append("unit or per-group weights")

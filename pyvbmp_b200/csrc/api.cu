@@ -145,9 +145,15 @@ int vbmp_mnw_prep_ex(const float* invU, const float* nu, const float* mu, const 
                          tau, elogdet);
 }
 
+// K > 512 (the tcgen05 E-step holds at most 512 components per launch): blocks of 512 components write their columns of the
+// logits (mode 0, row stride K), then vbmp_softmax_rows turns them into responsibilities (mode 1)
+constexpr int ESTEP_KBLK = 512;
+static bool estep_bigk(long long N, int GX, int G, int K, int Dp, int d0, int d1) {
+  return K > ESTEP_KBLK && (K % 4) == 0 && estep_umma_supported(N, GX, G, ESTEP_KBLK, Dp, d0, d1);
+}
 // shapes the tcgen05 E-step takes once K is padded (see kq_of)
 static bool estep_padk(long long N, int GX, int G, int K, int Dp, int d0, int d1) {
-  return (K % 4) != 0 && estep_umma_supported(N, GX, G, kq_of(K), Dp, d0, d1);
+  return (K % 4) != 0 && (estep_umma_supported(N, GX, G, kq_of(K), Dp, d0, d1) || estep_bigk(N, GX, G, kq_of(K), Dp, d0, d1));
 }
 static size_t estep_padk_extra(long long N, int K, int Dp) {       // padded W, m, cst, responsibilities, NA
   const size_t Kq = (size_t)kq_of(K);
@@ -158,6 +164,10 @@ static size_t estep_padk_extra(long long N, int K, int Dp) {       // padded W, 
 size_t vbmp_estep_workspace_bytes(long long N, int G, int K, int Dp, int mode) {
   if (!valid_dp(Dp) || N < 0) return 0;
   if (estep_padk(N, 1, G, K, Dp, 1, 0)) return estep_padk_extra(N, K, Dp) + vbmp_estep_workspace_bytes(N, G, kq_of(K), Dp, mode) + 256;
+  if (estep_bigk(N, 1, G, K, Dp, 1, 0)) {
+    const size_t u = estep_umma_workspace_bytes(N, G, ESTEP_KBLK, Dp, 0), sm = softmax_rows_workspace_bytes(N, K);
+    return (u > sm ? u : sm) + 512;
+  }
   size_t simt = 0;
   if (mode == 1) {
     const size_t nb = (size_t)cdiv(N, estep_simt_tile(Dp));
@@ -216,6 +226,22 @@ static int estep_impl(const float* z0, int d0, const float* z1, int d1, long lon
       set_error("estep: NA copy failed"); return VBMP_ERR_CUDA;
     }
     return VBMP_OK;
+  }
+  if (!(flags & 1) && estep_bigk(N, GX, G, K, Dp, d0, d1)) {
+    if (workspace_bytes < vbmp_estep_workspace_bytes(N, G, K, Dp, mode)) {
+      set_error("estep: workspace too small (%zu < %zu)", workspace_bytes, vbmp_estep_workspace_bytes(N, G, K, Dp, mode));
+      return VBMP_ERR_WORKSPACE;
+    }
+    for (int k0 = 0; k0 < K; k0 += ESTEP_KBLK) {
+      const int kb = K - k0 < ESTEP_KBLK ? K - k0 : ESTEP_KBLK;
+      EstepArgs b{z0, z1, d0, d1, N, GX, xg, W + (size_t)k0 * Dp * Dp, m + (size_t)k0 * Dp, cst + k0, G, kb, Dp, out + k0, nullptr,
+                  nullptr, nullptr};
+      b.ldo = K;
+      int rc = launch_estep_umma(b, 0, workspace, workspace_bytes, nullptr, nullptr, st);
+      if (rc) return rc;
+    }
+    if (mode == 0) return VBMP_OK;
+    return launch_softmax_rows(out, K, nullptr, N, K, out, K, logZn, NA, logZ, workspace, workspace_bytes, st);
   }
   if (workspace_bytes < vbmp_estep_workspace_bytes(N, G, K, Dp, mode) && mode == 1) {
     set_error("estep: workspace too small (%zu < %zu)", workspace_bytes, vbmp_estep_workspace_bytes(N, G, K, Dp, mode));

@@ -21,6 +21,8 @@ struct EstepArgs {
   int G, K, Dp;
   float* out; float* logZn; float* NA_part; double* logZ_part;
   unsigned char* rpack = nullptr;                    // mode 1, tcgen05 fp16 path: also emit K3's pre-split weight images
+  int ldo = 0;                                       // tcgen05 kernel, mode 0: row stride of `out` in floats (0 = K): a block of
+                                                     // components writes its columns of a wider logits array (K > 512, api.cu)
 };
 struct GramArgs {
   const float* z0; const float* z1; int d0, d1;

@@ -270,6 +270,7 @@ estep_umma_kernel(EstepArgs a, const uint8_t* __restrict__ Wp, const float* __re
   float* lz = reinterpret_cast<float*>(S + 1);                            // [2][256] (tile parity)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int K = a.K;
+  const int ldo = (MODE == 0 && a.ldo > 0) ? a.ldo : K;      // row stride of the logits (mode 0 only)
 
   if (tid == 0) {
     for (int s = 0; s < nstage; ++s) { mbar_init(&S->full[s], 1); mbar_init(&S->empty[s], 2 + 256); }
@@ -475,7 +476,7 @@ estep_umma_kernel(EstepArgs a, const uint8_t* __restrict__ Wp, const float* __re
           }
           l4[c & 3] = l;
           if ((c & 3) == 3 && ok)
-            *reinterpret_cast<float4*>(a.out + (size_t)orow * K + (c - 3)) = make_float4(l4[0], l4[1], l4[2], l4[3]);
+            *reinterpret_cast<float4*>(a.out + (size_t)orow * ldo + (c - 3)) = make_float4(l4[0], l4[1], l4[2], l4[3]);
         };
         float cs[C::CG], cv[C::CG];
         if constexpr (F16 && EU_MFOLD == 1) {
