@@ -44,7 +44,6 @@ namespace vbmp {
 using namespace umma;
 
 constexpr int GU_THREADS = 576;      // warp 0 producer, warp 1 MMA issuer, two sets of 8 worker warps (even / odd chunks)
-constexpr int GU_SC = 16;            // samples per chunk (2 K-steps): TF32; the fp16 variant takes 32
 __host__ __device__ constexpr int gu_sc(bool f16) { return f16 ? 32 : 16; }
 constexpr int GU_RSH = 14;           // fp16 variant: responsibilities are scaled by 2^14
 constexpr float GU_RMAX = 3.99f;     // ... and must stay below 65504 / 2^14
@@ -61,6 +60,9 @@ constexpr int GU_NR = GU_NR_V;       // raw ring depth (the launcher takes fewer
 #define GU_PAIR_NSTG 4
 #define GU_PAIR_NPMAX 192
 #endif
+#ifndef GU_ACP
+#define GU_ACP 1                     // fp16 variant: the weight images go from the raw ring to tensor memory with tcgen05.cp
+#endif                               // (issued by the MMA warp) instead of through the workers' registers
 constexpr int GU_MAXSTG = 6;
 __host__ __device__ constexpr int gu_nstg(bool pair) { return pair ? GU_PAIR_NSTG : 2; }
 __host__ __device__ constexpr int gu_npmax(bool pair) { return pair ? GU_PAIR_NPMAX : 224; }
@@ -202,7 +204,8 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant_
 
   if (tid == 0) {
     // one arrival per worker warp; in a pair the leader's bfull / dempty collect both CTAs' warps
-    for (int s = 0; s < GU_NR; ++s) { mbar_init(&S->rfull[s], 1); mbar_init(&S->rempty[s], 8); }
+    // rempty: the 8 worker warps of the consuming set (+ the commit behind the tcgen05.cp of the weight images)
+    for (int s = 0; s < GU_NR; ++s) { mbar_init(&S->rfull[s], 1); mbar_init(&S->rempty[s], (F16 && GU_ACP) ? 9 : 8); }
     for (int s = 0; s < GU_NSTG; ++s) { mbar_init(&S->bfull[s], PAIR ? 16 : 8); mbar_init(&S->bempty[s], 1); }
     mbar_init(&S->dfull, 1); mbar_init(&S->dempty, PAIR ? 32 : 16);
     S->consts[0] = 1.f; S->consts[1] = 0.f;
@@ -246,7 +249,8 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant_
       const uint64_t dstep = (uint64_t)((2 * NH * 16) >> 4);                 // one K-step = two 16-byte chunks
       const uint64_t d_hi0 = smem_desc(smem_u32(bst), NH * 16, 128), d_lo0 = d_hi0 + (uint64_t)((NH * 64) >> 4);
       int fc = 0, nflush = 0;
-      for (int c = 0; c < nchunks; ++c) {
+      int rs = 0;                                            // raw ring slot of chunk c
+      for (int c = 0; c < nchunks; ++c, rs = (rs + 1 == nr ? 0 : rs + 1)) {
         const int st = c % GU_NSTG;
         mbar_wait(&S->bfull[st], (c / GU_NSTG) & 1);
         const bool first = (fc == 0);
@@ -257,6 +261,20 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant_
         if (elect_one()) {
           const uint64_t sofs = (uint64_t)((st * stageB) >> 4);
           const uint32_t a_hi = tm + ACOL + st * 32, a_lo = a_hi + 16;
+          if (F16 && GU_ACP) {
+            // A operand: the chunk's pre-split weight images are K-major core matrices as they lie in the raw ring
+            // ([hi | lo] x [16-byte K-chunk (2)][component (128)], two 16-sample records): four 128-lane x 8-column copies,
+            // in order ahead of the MMAs that read them (and behind the MMAs that read this stage four chunks ago)
+            const uint32_t rsa = smem_u32(raw + (size_t)rs * rawB);
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+              const uint64_t dh = smem_desc(rsa + ks * GU_RREC, 2048, 128), dl = smem_desc(rsa + ks * GU_RREC + 4096, 2048, 128);
+              if (PAIR) { tmem_cp2_128x256b(a_hi + ks * 8, dh); tmem_cp2_128x256b(a_lo + ks * 8, dl); }
+              else { tmem_cp_128x256b(a_hi + ks * 8, dh); tmem_cp_128x256b(a_lo + ks * 8, dl); }
+            }
+            // the copies have read the raw slot (this arrives with them, one chunk ahead of the chunk's own MMAs)
+            if (PAIR) mma2_commit(&S->rempty[rs], 3); else mma_commit(&S->rempty[rs]);
+          }
 #pragma unroll
           for (int ks = 0; ks < 2; ++ks) {
             const uint64_t b_hi = d_hi0 + sofs + ks * dstep, b_lo = d_lo0 + sofs + ks * dstep;
@@ -280,6 +298,7 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant_
           }
           if (PAIR) { mma2_commit(&S->bempty[st], 3); if (flush) mma2_commit(&S->dfull, 3); }
           else { mma_commit(&S->bempty[st]); if (flush) mma_commit(&S->dfull); }
+
         }
         __syncwarp();
         if (flush) { fc = 0; ++nflush; }
@@ -382,7 +401,9 @@ gram_umma_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant_
       mbar_wait(&S->bempty[st], ((c / GU_NSTG) & 1) ^ 1);
       tc_fence_after();
       // ---- A operand: r[s][comp] for this thread's 8 (fp16: 16) samples, split, into TMEM
-      if (F16) {
+      if (F16 && GU_ACP) {
+        // (copied by the MMA warp, see above)
+      } else if (F16) {
         // pre-split by gram_rsplit_kernel: this thread's 16 samples are two 16-byte chunks of hi and two of lo
         const uint8_t* rr = raw + (size_t)s * rawB + (size_t)sh * GU_RREC + (size_t)comp * 16;
         const uint4 h0 = *reinterpret_cast<const uint4*>(rr), h1 = *reinterpret_cast<const uint4*>(rr + 2048);
