@@ -257,16 +257,27 @@ struct BufRing {
   __device__ __forceinline__ void next() { buf += 2; if (buf >= NBUF) { buf -= NBUF; ph ^= 1u; } }
 };
 
-template <int DP, int MODE, bool F16>
+// AB2: TWO sets of A images in tensor memory.  The workers then build the images of tile t + 1 before the LAST epilogue
+// of tile t instead of behind it, and the MMA warps run on into the next tile while that epilogue is still going: with
+// one set the tensor pipe idles from the last burst of a tile until the next images are stored (~8.7 K cycles per tile:
+// 5 % of the kernel at K = 256, 20 % at K = 64, where a tile is only 64 bursts long).  The second set costs 4 ACOLS
+// columns: nothing up to DP = 32, the third accumulator buffer at DP = 64 — where that loss outweighs the overlap
+// (measured, see eu_launch) —, impossible at DP = 128.
+template <int DP, int MODE, bool F16, bool AB2>
 __global__ void __launch_bounds__(EU_THREADS, 1)
 estep_umma_kernel(EstepArgs a, const uint8_t* __restrict__ Wp, const float* __restrict__ fs, int ntiles, int ngroups,
                   int nstage, long long nsb) {
   using C = EuCfg<DP, F16>;
+  constexpr int ASZ = 4 * C::ACOLS;                                        // columns of one set of A images (both halves)
+  constexpr int DCOL0 = AB2 ? (2 * ASZ > 128 ? 2 * ASZ : 128) : C::DCOL0;
+  constexpr int NBUF = AB2 ? ((512 - DCOL0) / EU_N >= 3 ? 3 : 2) : C::NBUF;
+  static_assert(DCOL0 + NBUF * EU_N <= 512 && NBUF >= 2, "TMEM budget");
+  constexpr int ONES_BYTES = AB2 ? 16384 : 8192;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* stages = smem_raw;                                             // EU_NSTAGE * STAGE
-  float* ones = reinterpret_cast<float*>(stages + nstage * C::STAGE);     // per half: A block [chunk (2)][row (128)][4] with
-                                                                          // 1 (TF32) or 2^sh_row (fp16) at k = 0, 1
-  EuSmem* S = reinterpret_cast<EuSmem*>(stages + nstage * C::STAGE + 8192);
+  float* ones = reinterpret_cast<float*>(stages + nstage * C::STAGE);     // per A set and half: A block [chunk (2)][row (128)][4]
+                                                                          // with 1 (TF32) or 2^sh_row (fp16) at k = 0, 1
+  EuSmem* S = reinterpret_cast<EuSmem*>(stages + nstage * C::STAGE + ONES_BYTES);
   float* lz = reinterpret_cast<float*>(S + 1);                            // [2][256] (tile parity)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int K = a.K;
@@ -280,7 +291,7 @@ estep_umma_kernel(EstepArgs a, const uint8_t* __restrict__ Wp, const float* __re
     for (int b = 0; b < 2; ++b) { mbar_init(&S->ndone[b], 256); mbar_init(&S->nfree[b], 1); }
     fence_barrier_init();
   }
-  for (int o = tid; o < 2048; o += EU_THREADS) ones[o] = ((o & 1023) < 512 && (o & 3) < 2) ? 1.f : 0.f;
+  for (int o = tid; o < ONES_BYTES / 4; o += EU_THREADS) ones[o] = ((o & 1023) < 512 && (o & 3) < 2) ? 1.f : 0.f;
   if (F16 && tid < EU_FS) S->fsc[tid] = tid < DP ? fs[tid] : 1.f;
   fence_proxy_async();
   if (warp == 1) tmem_alloc<512>(&S->tmem_base);
@@ -310,12 +321,13 @@ estep_umma_kernel(EstepArgs a, const uint8_t* __restrict__ Wp, const float* __re
     // take strict turns through a token: if their bursts interleaved in the tensor-pipe FIFO both halves would finish
     // together and both epilogue round trips would be exposed; in turn order half 0's epilogue runs under half 1's MMAs.
     const int h = warp - 1;
-    const uint32_t a_hi = tm + h * 2 * C::ACOLS, a_lo = a_hi + C::ACOLS;
-    const uint64_t ones_desc = smem_desc(smem_u32(ones + h * 1024), 128 * 16, 128);
     Ring rg;
-    BufRing<C::NBUF> br(h);
+    BufRing<NBUF> br(h);
     uint32_t itp = 0;                      // parity of the group counter
     for (int t = 0; t < my_tiles; ++t) {
+      const int ab = AB2 ? (t & 1) : 0;
+      const uint32_t a_hi = tm + ab * ASZ + h * 2 * C::ACOLS, a_lo = a_hi + C::ACOLS;
+      const uint64_t ones_desc = smem_desc(smem_u32(ones + ab * 2048 + h * 1024), 128 * 16, 128);
       mbar_wait(&S->afull, t & 1);
       tc_fence_after();
       for (int g = 0; g < ngroups; ++g, rg.next(nstage), br.next(), itp ^= 1u) {
@@ -323,7 +335,7 @@ estep_umma_kernel(EstepArgs a, const uint8_t* __restrict__ Wp, const float* __re
         mbar_wait(&S->full[s], rg.ph);
         const uint64_t sb = (uint64_t)((smem_u32(stages) + (uint32_t)s * C::STAGE) >> 4);
         const uint32_t buf = br.buf;
-        const uint32_t dcol = tm + C::DCOL0 + buf * EU_N;
+        const uint32_t dcol = tm + DCOL0 + buf * EU_N;
         mbar_wait(&S->tempty[buf], br.ph ^ 1);
         mbar_wait(&S->turn[h], h == 0 ? (itp ^ 1) : itp);     // my turn
         tc_fence_after();
@@ -361,16 +373,16 @@ estep_umma_kernel(EstepArgs a, const uint8_t* __restrict__ Wp, const float* __re
     const int D = a.d0 + a.d1;
     double lzsum = 0.0;
     Ring rg;
-    BufRing<C::NBUF> br(h);
-    for (int t = 0; t < my_tiles; ++t) {
-      const long long tile = (long long)blockIdx.x + (long long)t * gridDim.x;
-      const long long row = tile * EU_TILE + rloc;
+    BufRing<NBUF> br(h);
+    // ---- this thread's sample row of tile tt, split into hi / lo, into the A images of set tt % 2 (AB2) in tensor memory;
+    //      returns 2^-sh of the row (fp16 operands).  The MMAs that last read that set are complete: AB2 — those of tile
+    //      tt - 2 (this thread has seen tfull of every group of tile tt - 1 but the last); otherwise those of tile tt - 1.
+    auto load_A = [&](int tt) -> float {
+      const long long row = ((long long)blockIdx.x + (long long)tt * gridDim.x) * EU_TILE + rloc;
       const bool valid = row < a.N;
-      // ---- this thread's sample row, split into hi / lo, into TMEM (previous tile's MMAs on this half
-      //      are complete: we waited on tfull of its last group)
-      float rs = 1.f;                                            // 2^-sh of this row (fp16 operands)
-      {
-        const uint32_t a_hi = tm + lane_base + h * 2 * C::ACOLS, a_lo = a_hi + C::ACOLS;
+      const int ab = AB2 ? (tt & 1) : 0;
+      float rs = 1.f;
+        const uint32_t a_hi = tm + lane_base + ab * ASZ + h * 2 * C::ACOLS, a_lo = a_hi + C::ACOLS;
         const float* r0 = a.z0 + (size_t)(valid ? row : 0) * a.d0;
         const float* r1 = a.z1 ? a.z1 + (size_t)(valid ? row : 0) * a.d1 : nullptr;
         const bool vec = valid && (a.d0 % 4 == 0) && (a.d1 % 4 == 0);
@@ -430,7 +442,7 @@ estep_umma_kernel(EstepArgs a, const uint8_t* __restrict__ Wp, const float* __re
           }
           if (!EU_MFOLD) {
             // the row's scale into the A block of the -m MMA (k = 0 meets -m_hi, k = 1 meets -m_lo)
-            *reinterpret_cast<float2*>(ones + h * 1024 + (q * 32 + lane) * 4) = make_float2(sc, sc);
+            *reinterpret_cast<float2*>(ones + ab * 2048 + h * 1024 + (q * 32 + lane) * 4) = make_float2(sc, sc);
             fence_proxy_async();
           }
         } else {
@@ -448,7 +460,15 @@ estep_umma_kernel(EstepArgs a, const uint8_t* __restrict__ Wp, const float* __re
         tmem_wait_st();
         tc_fence_before();
         mbar_arrive(&S->afull);
-      }
+      return rs;
+    };
+    float rs_next = 1.f;
+    if (AB2 && my_tiles > 0) rs_next = load_A(0);
+    for (int t = 0; t < my_tiles; ++t) {
+      const long long tile = (long long)blockIdx.x + (long long)t * gridDim.x;
+      const long long row = tile * EU_TILE + rloc;
+      const bool valid = row < a.N;
+      const float rs = AB2 ? rs_next : load_A(t);
       float mx = -INFINITY, sm = 0.f;
       float l4[4];
       // the row whose logits this thread finishes, stores and normalises by: its own TMEM lane, or (EU_MFOLD == 1) the row
@@ -464,9 +484,10 @@ estep_umma_kernel(EstepArgs a, const uint8_t* __restrict__ Wp, const float* __re
       for (int g = 0; g < ngroups; ++g, rg.next(nstage), br.next()) {
         const int s = rg.s;
         const float* cstage = reinterpret_cast<const float*>(stages + (size_t)s * C::STAGE + C::GB + C::MB);
+        if (AB2 && g == ngroups - 1 && t + 1 < my_tiles) rs_next = load_A(t + 1);   // under the tile's last bursts
         mbar_wait(&S->tfull[br.buf], br.ph);      // the MMAs read the stage, so its bulk copy (m, cst too) has landed
         tc_fence_after();
-        const uint32_t dcol = tm + lane_base + C::DCOL0 + br.buf * EU_N;
+        const uint32_t dcol = tm + lane_base + DCOL0 + br.buf * EU_N;
         // one logit: online logsumexp with one exp per component (ex2.approx: rel. error 2^-22), four logits per store
         auto emit = [&](int c, float l, bool ok, long long orow) {
           if (MODE == 1) {
@@ -615,14 +636,20 @@ estep_umma_kernel(EstepArgs a, const uint8_t* __restrict__ Wp, const float* __re
       const bool pack = NUA <= 2 && a.rpack != nullptr;
       const int rows_p = pack ? min(EU_TILE, (rows + 31) & ~31) : rows;      // the images cover whole 32-sample chunks
       const float* lzp = lz + (t & 1) * EU_TILE;
-      float4* base = reinterpret_cast<float4*>(a.out) + (size_t)row0 * K4 + lane;     // 32-bit offsets from here on
+      // K <= 64 (K4 <= 16): a row is at most 16 float4 wide, so the warp splits into 32 / gsz lane groups and group j takes
+      // the rows [r + j RB, r + (j + 1) RB) of every batch — with one group half of the lanes (or more) idled, and at
+      // K = 64 the ONE normaliser warp, not the tensor pipe, set the kernel's pace
+      const int gsz = (NUA == 1 && K4 <= 16) ? (K4 <= 1 ? 1 : K4 <= 2 ? 2 : K4 <= 4 ? 4 : K4 <= 8 ? 8 : 16) : 32;
+      const int ngrp = 32 / gsz, lin = lane % gsz, roff = (lane / gsz) * RB;
+      float4* base = reinterpret_cast<float4*>(a.out) + (size_t)row0 * K4 + lin;      // 32-bit offsets from here on
       bool cok[NUA];
 #pragma unroll
-      for (int u = 0; u < NUA; ++u) cok[u] = lane + 32 * u < K4;
+      for (int u = 0; u < NUA; ++u) cok[u] = lin + 32 * u < K4;
       float4 cs[NUA];
 #pragma unroll
       for (int u = 0; u < NUA; ++u) cs[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int r = 0; r < rows_p; r += RB) {
+      for (int rb = 0; rb < rows_p; rb += RB * ngrp) {
+        const int r = rb + roff;                             // this lane group's rows of the batch
         float4 x[RB][NUA];
 #pragma unroll
         for (int v = 0; v < RB; ++v) {
@@ -650,7 +677,7 @@ estep_umma_kernel(EstepArgs a, const uint8_t* __restrict__ Wp, const float* __re
             x[v][u] = rok ? y : make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
-        if (pack) {
+        if (pack && r < rows_p) {
           constexpr float RS = 16384.f;                                   // GU_RSH = 14
 #pragma unroll
           for (int c = 0; c < RB / 8; ++c) {
@@ -658,7 +685,7 @@ estep_umma_kernel(EstepArgs a, const uint8_t* __restrict__ Wp, const float* __re
 #pragma unroll
             for (int u = 0; u < NUA; ++u) {
               if (cok[u]) {
-                const int comp0 = 4 * (lane + 32 * u);
+                const int comp0 = 4 * (lin + 32 * u);
                 uint8_t* rec = a.rpack + ((size_t)(comp0 >> 7) * nsb + (size_t)(ch >> 1)) * 8192 + (size_t)(ch & 1) * 2048 +
                                (size_t)(comp0 & 127) * 16;
 #pragma unroll
@@ -683,10 +710,18 @@ estep_umma_kernel(EstepArgs a, const uint8_t* __restrict__ Wp, const float* __re
           }
         }
       }
+      // lane groups hold partial column sums of the same columns: add them in a fixed order, group 0 keeps the total
+      for (int o = gsz; o < 32; o <<= 1) {
+#pragma unroll
+        for (int u = 0; u < NUA; ++u) {
+          cs[u].x += __shfl_xor_sync(0xffffffffu, cs[u].x, o); cs[u].y += __shfl_xor_sync(0xffffffffu, cs[u].y, o);
+          cs[u].z += __shfl_xor_sync(0xffffffffu, cs[u].z, o); cs[u].w += __shfl_xor_sync(0xffffffffu, cs[u].w, o);
+        }
+      }
 #pragma unroll
       for (int u = 0; u < NUA; ++u) {
-        const int c4 = lane + 32 * u;
-        if (c4 < K4) {
+        const int c4 = lin + 32 * u;
+        if (c4 < K4 && lane < gsz) {
           na[4 * c4] += (double)cs[u].x; na[4 * c4 + 1] += (double)cs[u].y;
           na[4 * c4 + 2] += (double)cs[u].z; na[4 * c4 + 3] += (double)cs[u].w;
         }
@@ -773,20 +808,33 @@ static int eu_launch(EstepArgs a, int mode, uint8_t* Wp, float* fs, float* NA_pa
   const int grid = ntiles < eu_num_sms() ? ntiles : eu_num_sms();
   const long long nsb = (a.N + 31) / 32 * 2;               // 16-sample blocks per component block of the weight images
   if (!F16) a.rpack = nullptr;
-  const size_t fixed = 8192 + sizeof(EuSmem) + 2 * EU_TILE * sizeof(float) + (mode == 1 ? (size_t)a.K * sizeof(double) : 0) + 64;
+  // two sets of A images (AB2) where tensor memory has room for them beside three accumulators: up to DP = 32 (cfg4's
+  // E-step 0.72 -> 0.70 ms).  At DP = 64 the second set costs the third accumulator buffer, which loses more than the
+  // overlap gains (cfg3, K = 64: 7.05 -> 7.21 ms; cfg2: 13.5 -> 13.8 ms): off unless VBMP_ESTEP_AB2 = 1 (tuning; 0 = never)
+  static const int ab2_env = [] { const char* e = getenv("VBMP_ESTEP_AB2"); return e ? atoi(e) : -1; }();
+  constexpr bool AB2_OK = F16 && DP <= 64;
+  bool ab2 = AB2_OK && ngroups >= 2 && DP <= 32;
+  if (ab2_env == 0) ab2 = false;
+  if (ab2_env == 1) ab2 = AB2_OK && ngroups >= 2;
+  const size_t fixed = (ab2 ? 16384 : 8192) + sizeof(EuSmem) + 2 * EU_TILE * sizeof(float) + (mode == 1 ? (size_t)a.K * sizeof(double) : 0) + 64;
   int nstage = (int)((227 * 1024 - fixed) / C::STAGE);
   if (nstage > EU_MAXSTAGE) nstage = EU_MAXSTAGE;
   if (nstage < 2) { set_error("estep_umma: shared memory too small for K=%d", a.K); return VBMP_ERR_UNSUPPORTED; }
   const size_t smem = (size_t)nstage * C::STAGE + fixed;
   a.NA_part = NA_part;
   a.logZ_part = logZ_part;
-  if (mode == 0) {
-    cudaFuncSetAttribute(estep_umma_kernel<DP, 0, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    estep_umma_kernel<DP, 0, F16><<<grid, EU_THREADS, smem, st>>>(a, Wp, fs, ntiles, ngroups, nstage, nsb);
+#define EU_LAUNCH(MODE_, AB_)                                                                                              \
+  do {                                                                                                                    \
+    cudaFuncSetAttribute(estep_umma_kernel<DP, MODE_, F16, AB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    estep_umma_kernel<DP, MODE_, F16, AB_><<<grid, EU_THREADS, smem, st>>>(a, Wp, fs, ntiles, ngroups, nstage, nsb);      \
+  } while (0)
+  if constexpr (AB2_OK) {
+    if (ab2) { if (mode == 0) EU_LAUNCH(0, true); else EU_LAUNCH(1, true); }
+    else { if (mode == 0) EU_LAUNCH(0, false); else EU_LAUNCH(1, false); }
   } else {
-    cudaFuncSetAttribute(estep_umma_kernel<DP, 1, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    estep_umma_kernel<DP, 1, F16><<<grid, EU_THREADS, smem, st>>>(a, Wp, fs, ntiles, ngroups, nstage, nsb);
+    if (mode == 0) EU_LAUNCH(0, false); else EU_LAUNCH(1, false);
   }
+#undef EU_LAUNCH
   rc = check_launch("estep_umma");
   if (rc) return rc;
   if (mode == 1) rc = launch_estep_reduce(NA_part, logZ_part, grid, 1, a.K, NA, logZ, st);
