@@ -11,6 +11,8 @@ Prints ONE JSON line on rank 0.  Besides the contract's keys the line carries
   * `secondary` (N=1): the rows next to the hot path, MixtureofLinearTransforms.update(pX, pY) / predict (SURVEY.md 8f,
     against the HBM peak), and BASELINE.json configs[2] (MixtureofLinearTransforms N=8 388 608, n=p=32, K=64) and configs[3]
     (ARHMM 4096 sequences x T=1024, d=16, K=32), each timed the same way (ms/step, per-kernel ms, roofline fraction);
+  * `secondary.cfg1` (N=1): BASELINE.json configs[0] (two-moons, N=10 000, d=2, K=20) — the one configuration the reference
+    runs at full size: the same call on the GPU and, like for like, by the unmodified reference on the host cores;
   * `cfg5` (N=8): BASELINE.json configs[4] at its stated size, 8 388 608 rows per GPU = 67 108 864 rows in total;
   * `e2e_iters20`: one public call update(X_pinned_host, iters=20) — the rows cross the host link once per call;
   * `replicas_bitwise_equal` (N>1): the posterior is bit-identical on every rank after the timed steps.
@@ -239,6 +241,65 @@ def time_steps(fn, steps, warmup, dev, barrier):
         tt = sum(a.elapsed_time(b) for a, b in evs)
         kern[name] = {"calls": len(evs), "ms_total": tt, "ms_avg": tt / max(len(evs), 1), "ms_per_step": tt / steps}
     return ev0.elapsed_time(ev1), kern, int(_lib.lib().vbmp_launch_count() - n0)
+
+
+def secondary_cfg1(dev, threads, iters=20, n_per=5000, Kc=20):
+    """BASELINE.json configs[0] — the one configuration the reference runs today at its full size: GaussianMixtureModel on
+    two-moons data (examples/two_moons.py:4-21), N = 10 000, d = 2, K = 20.  Same rows, same initial means, `iters` EM
+    iterations in ONE public call on both sides: this package on the GPU (launch-bound at this size) and, when it is
+    importable, the unmodified reference on the host cores — a like-for-like pair with the ELBO of both beside it."""
+    import math
+    import pyvbmp_b200 as V
+    g = torch.Generator().manual_seed(5)
+    x = torch.linspace(-math.pi / 2, math.pi / 2, n_per)
+    X = torch.cat([torch.stack([torch.sin(x), torch.cos(x) - 0.25], -1),
+                   torch.stack([torch.sin(x) + 1.0, -torch.cos(x) + 0.25], -1)], 0)
+    X = X + 0.05 * torch.randn(X.shape, generator=g)
+    X = X / X.std()
+    N = X.shape[0]
+    idx = torch.randint(N, (Kc,), generator=g)
+    Xd = X.to(dev)
+
+    def ours():
+        torch.manual_seed(0)
+        m = V.GaussianMixtureModel(Kc, 2)
+        m.dist.mu = X[idx].clone()
+        m.to(dev)
+        return m
+    ours().update(Xd, iters)                                  # warm-up call (workspaces, module load)
+    torch.cuda.synchronize(dev)
+    best = None
+    for _ in range(3):
+        m = ours()
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        m.update(Xd, iters)
+        elbo = float(m.ELBO_last)                             # device -> host read of the result closes the call
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    out = {"workload": f"GaussianMixtureModel.update(X, {iters}), two-moons N={N}, d=2, K={Kc} (BASELINE.json configs[0]), "
+                       "one public call, wall clock incl. the final device->host read; launch-bound",
+           "ms_per_iteration": best / iters * 1e3, "value": iters * N * Kc / best, "unit": UNIT, "elbo_last": elbo}
+    ref = _reference_tree()
+    if ref is not None:
+        if ref not in sys.path:
+            sys.path.insert(0, ref)
+        import models as ref_models
+        torch.set_num_threads(threads)
+        rbest = None
+        for _ in range(3):
+            torch.manual_seed(0)
+            r = ref_models.GaussianMixtureModel(Kc, 2)
+            r.dist.mu = X[idx].clone()
+            t0 = time.perf_counter()
+            r.update(X, iters=iters, lr=1.0, verbose=False)
+            dt = time.perf_counter() - t0
+            rbest = dt if rbest is None else min(rbest, dt)
+        relbo = float(r.ELBO_last)
+        out["reference_cpu"] = {"ms_per_iteration": rbest / iters * 1e3, "value": iters * N * Kc / rbest, "cores": threads,
+                                "kind": "reference", "same_config": True, "elbo_last": relbo}
+        out["elbo_rel_diff"] = abs(elbo - relbo) / abs(relbo)
+    return out
 
 
 def secondary_cfg3(dev, peak, steps=5, warmup=3, N=8_388_608, p=32, n=32, Kc=64):
@@ -562,6 +623,11 @@ def main():
                    "sample": f"{args.cpu_baseline_iters} EM iterations on {args.ref_rows} rows of the same workload "
                              f"({s_per:.2f} s/iteration; extrapolates to {s_per * n_rows / args.ref_rows:.0f} s per "
                              f"full-N iteration); {what}: (N,K,d,d) broadcast-multiply-sum"}
+            if secondary is not None:                     # after the affinity reset: the reference half uses every host core
+                try:
+                    secondary["cfg1"] = secondary_cfg1(dev, threads)
+                except Exception as e:
+                    secondary["cfg1"] = {"error": f"{type(e).__name__}: {e}"[:300]}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
