@@ -964,6 +964,27 @@ def arhmm_update(h, X, Y, iters=1, lr=1.0, beta=None, exact=True):
     return trace
 
 
+def hmm_niw_update(h, y, iters=1, lr=1.0, beta=None):
+    """models/HMM.py:113-152 for a NormalInverseWishart emission node (batch_shape = (K,), any event_dim): obs_logits (:113-117),
+    update_states (:119-132), update_markov_parms (:134-136), update_obs_parms (:138-139); ELBO evaluated AFTER the M-step."""
+    trace = []
+    s = h["obs"]
+    for _ in range(iters):
+        Xv = y.unsqueeze(-1 - s["event_dim"])
+        p, SEzz, SEz0, logZ = hmm_forward_backward_logits(h, niw_elog_like_exact(s, Xv))
+        h["p"] = p
+        NA = p.sum(0)
+        sd = list(range(NA.ndim - 1))
+        h["NA"], SEzz, SEz0, h["logZ"] = NA.sum(sd), SEzz.sum(sd), SEz0.sum(sd), logZ.sum(sd)
+        dirichlet_ss_update(h["transition"], SEzz, lr=lr, beta=beta)
+        dirichlet_ss_update(h["initial"], SEz0, lr=lr, beta=beta)
+        niw_raw_update_exact(s, Xv, p, lr=lr, beta=beta)
+        elbo = h["logZ"] - hmm_kl(h, niw_kl(s))
+        h["ELBO_last"] = elbo
+        trace.append(elbo)
+    return trace
+
+
 def arhmm_prxy_update(h, mux, Sx, muy, Sy, iters=1, lr=1.0, beta=None):
     """models/HMM.py:141-152 with models/ARHMM.py:35-46 (ARHMM_prXY): observation logits from Elog_like_given_pX_pY, the
     observation update from update(pX, pY, p).  Beliefs: means (T,S,1,p,1) / (T,S,1,n,1), covariances (T,S,1,p,p) / (T,S,1,n,n)."""

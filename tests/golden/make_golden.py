@@ -356,6 +356,54 @@ def gen_arhmm():
     save("arhmm_k4_n2_p3", **out)
 
 
+def gen_hmm_variants():
+    """models.HMM with NIW emissions in the three layouts of the reference's own script (tests/test_models.py:293-314 plain,
+    :353-356 a batch of HMMs with data y.unsqueeze(-2), :398-409 emissions with event_dim > 1): forward-backward, the Markov
+    statistics and the emission update through HMM.update (models/HMM.py:120-152)."""
+    from models.HMM import HMM
+    g = torch.Generator().manual_seed(71)
+
+    def switching(K, d, Tn, S, noise):
+        A = torch.rand(K, K, generator=g) + 4 * torch.eye(K)
+        A = A / A.sum(-1, keepdim=True)
+        B = 2.0 * torch.randn(K, d, generator=g)
+        z = torch.zeros(Tn, S, dtype=torch.long)
+        z[0] = torch.randint(K, (S,), generator=g)
+        for t in range(1, Tn):
+            z[t] = torch.multinomial(A[z[t - 1]], 1, generator=g).squeeze(-1)
+        return B[z] + noise * torch.randn(Tn, S, d, generator=g)
+
+    cases = (("hmm_niw_k6", dict(K=4, d=2, Tn=30, S=20), (2,), (6,), lambda y: y),
+             ("hmm_batch3_k6", dict(K=4, d=2, Tn=24, S=10), (2,), (3, 6), lambda y: y.unsqueeze(-2)),
+             ("hmm_event32_k5", dict(K=5, d=6, Tn=20, S=15), (3, 2), (5,), lambda y: y.reshape(y.shape[:2] + (3, 2))))
+    for name, gen, ev, bs, shape in cases:
+        y = shape(switching(noise=0.3, **gen))
+        torch.manual_seed(13)
+        obs = dists.NormalInverseWishart(event_shape=ev, batch_shape=bs)
+        m = HMM(obs)
+
+        def st():
+            s = niw_state(m.obs_dist, "obs.")
+            s.update(dir_state(m.transition, "transition."))
+            s.update(dir_state(m.initial, "initial."))
+            return s
+        out = {"y": T(y), "event_shape": np.asarray(ev), "batch_shape": np.asarray(bs)}
+        out.update(tagged(st(), "init"))
+        out["init/obs_logits"] = T(m.obs_logits(y))
+        el = []
+        for i in range(3):
+            m.update(y, iters=1, lr=1.0)
+            el.append(T(m.ELBO_last).astype(np.float64))
+            if i == 0:
+                out.update(tagged(st(), "iter1"))
+                out["iter1/p"], out["iter1/logZ"], out["iter1/NA"] = T(m.p), T(m.logZ), T(m.NA)
+        out.update(tagged(st(), "final"))
+        out["final/p"], out["final/logZ"] = T(m.p), T(m.logZ)
+        out["final/assignment"] = T(m.assignment()).astype(np.int32)
+        out["ELBO"] = np.stack(el)
+        save(name, **out)
+
+
 def gen_arhmm_prxy():
     """models.ARHMM.ARHMM_prXY (models/ARHMM.py:35-46): the ARHMM driven by Gaussian beliefs about regressors and outputs."""
     from dists.MultivariateNormal_vector_format import MultivariateNormal_vector_format as MVN
@@ -571,6 +619,9 @@ if __name__ == "__main__":
         gen_arhmm_prxry()
         gen_diag()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "hmm":       # the HMM layouts added late in round 2
+        gen_hmm_variants()
+        sys.exit(0)
     gen_gmm()
     gen_niw_variants()
     gen_mnw()
@@ -578,6 +629,7 @@ if __name__ == "__main__":
     gen_molt_predict()
     gen_molt_given()
     gen_arhmm()
+    gen_hmm_variants()
     gen_arhmm_prxy()
     gen_diag()
     gen_arhmm_prxry()

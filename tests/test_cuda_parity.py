@@ -323,6 +323,43 @@ def test_arhmm_golden():
     assert np.max(np.abs(np.array(elbo) - fix["ELBO"]) / np.abs(fix["ELBO"])) < PARITY
 
 
+@pytest.mark.parametrize("name", ["hmm_niw_k6", "hmm_batch3_k6", "hmm_event32_k5"])
+def test_hmm_niw_golden(name):
+    """models.HMM with NIW emissions in the reference script's three layouts (tests/test_models.py:293-314 plain, :353-356 a
+    batch of HMMs fed y.unsqueeze(-2), :398-409 emissions with event_dim > 1) against the reference's own outputs: emission
+    logits (K1 + K2), forward-backward (K6, G > 1 for the batch), Markov and emission updates, ELBO trajectory."""
+    fix = load_golden(name)
+    ev, bs = tuple(int(v) for v in fix["event_shape"]), tuple(int(v) for v in fix["batch_shape"])
+    torch.manual_seed(0)
+    h = V.HMM(V.NormalInverseWishart(event_shape=ev, batch_shape=bs)).to(DEV)
+    set_state(h, {k.replace("obs.", "obs_dist."): v for k, v in tag(fix, "init").items()})
+    y = torch.as_tensor(fix["y"]).to(DEV)
+    ol = h.obs_logits(y)
+    assert ol.shape == fix["init/obs_logits"].shape
+    assert_close(ol, fix["init/obs_logits"], PARITY, "obs_logits")
+    h.update(y, iters=1)
+    it1 = tag(fix, "iter1")
+    assert h.p.shape == it1["p"].shape
+    assert_maxabs(h.p.cpu(), it1["p"], 2e-4, "p")
+    assert_close(h.logZ, it1["logZ"], PARITY, "logZ")
+    assert_close(h.NA, it1["NA"], PARITY, "NA")
+    keys = ("obs.mu", "obs.lambda_mu", "obs.invU.invU", "obs.invU.U", "obs.invU.nu", "transition.alpha", "initial.alpha")
+    for k in keys:
+        assert_close(get(h, k.replace("obs.", "obs_dist.")), it1[k], PARITY, k)
+    elbo = [h.ELBO_last.detach().cpu().double().numpy()]
+    for _ in range(2):
+        h.update(y, iters=1)
+        elbo.append(h.ELBO_last.detach().cpu().double().numpy())
+    elbo = np.stack(elbo)
+    assert elbo.shape == fix["ELBO"].shape
+    assert np.max(np.abs(elbo - fix["ELBO"]) / np.abs(fix["ELBO"])) < PARITY
+    fin = tag(fix, "final")
+    for k in keys:
+        assert_close(get(h, k.replace("obs.", "obs_dist.")), fin[k], 3e-4, "final " + k)   # free-running, three iterations
+    agree = float((h.assignment().cpu() == torch.as_tensor(fix["final/assignment"]).long()).float().mean())
+    assert agree > 0.995, agree
+
+
 def test_arhmm_prxy_golden():
     """ARHMM_prXY (models/ARHMM.py:35-46) against the reference's own outputs."""
     fix = load_golden("arhmm_prxy_k4_n2_p3")

@@ -267,3 +267,34 @@ def test_reference_molt_and_arhmm_run_on_the_cuda_path(cuda_default):
                 assert_close(_get(h, k.replace("obs.", "obs_dist.")), it1[k], 1e-4, k)
     assert _lib.LAUNCHES - n0 >= 4 * 5
     assert np.max(np.abs(np.array(elbo) - fix["ELBO"]) / np.abs(fix["ELBO"])) < 1e-4
+
+
+@needs_ref
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["hmm_niw_k6", "hmm_batch3_k6", "hmm_event32_k5"])
+def test_reference_hmm_runs_on_the_cuda_path(cuda_default, name):
+    """The reference's own models.HMM over an installed NormalInverseWishart node — plain, a batch of HMMs
+    (tests/test_models.py:353-356) and emissions with event_dim > 1 (:398-409) — against the unmodified reference's outputs."""
+    dists, transforms, models = cuda_default
+    from pyvbmp_b200 import _lib
+    fix = load_golden(name)
+    ev, bs = tuple(int(v) for v in fix["event_shape"]), tuple(int(v) for v in fix["batch_shape"])
+    torch.manual_seed(0)
+    h = models.HMM(dists.NormalInverseWishart(event_shape=ev, batch_shape=bs))
+    assert type(h).__module__.startswith("models.") and h.obs_dist.mu.is_cuda
+    _set_state(h, {k.replace("obs.", "obs_dist."): v for k, v in tag(fix, "init").items()}, "cuda:0")
+    y = torch.as_tensor(fix["y"]).to("cuda:0")
+    n0 = _lib.LAUNCHES
+    elbo = []
+    for i in range(3):
+        h.update(y, iters=1)
+        elbo.append(h.ELBO_last.detach().cpu().double().numpy())
+        if i == 0:
+            it1 = tag(fix, "iter1")
+            assert float((h.p.cpu() - it1["p"]).abs().max()) < 2e-4
+            for k in ("obs.mu", "obs.lambda_mu", "obs.invU.invU", "obs.invU.nu", "transition.alpha", "initial.alpha"):
+                assert_close(_get(h, k.replace("obs.", "obs_dist.")), it1[k], 1e-4, k)
+            assert_close(h.NA, it1["NA"], 1e-4, "NA")
+    assert _lib.LAUNCHES - n0 >= 4 * 3                        # K1, K2, K6, K3 / K5 every iteration
+    assert np.max(np.abs(np.stack(elbo) - fix["ELBO"]) / np.abs(fix["ELBO"])) < 1e-4
+    assert (h.assignment().cpu().numpy() == fix["final/assignment"]).mean() > 0.995

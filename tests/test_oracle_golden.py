@@ -252,6 +252,29 @@ def test_arhmm_prxry_trajectory():
     assert np.max(np.abs(got - fix["ELBO"]) / np.abs(fix["ELBO"])) < PARITY
 
 
+@pytest.mark.parametrize("name", ["hmm_niw_k6", "hmm_event32_k5"])
+def test_hmm_niw_trajectory(name):
+    """models.HMM with NormalInverseWishart emissions (models/HMM.py:113-152; tests/test_models.py:293-314, :398-409 layouts)."""
+    fix = load_golden(name)
+    ev, bs = tuple(int(v) for v in fix["event_shape"]), tuple(int(v) for v in fix["batch_shape"])
+    torch.manual_seed(0)
+    h = O.hmm_new(O.niw_new(ev, bs), bs[-1])
+    O.load_state(h, tag(fix, "init"))
+    y = torch.as_tensor(fix["y"])
+    ol = O.niw_elog_like_exact(h["obs"], y.unsqueeze(-1 - len(ev)))
+    assert_close(ol, fix["init/obs_logits"], 2e-5, "obs_logits")
+    trace = O.hmm_niw_update(h, y, iters=1)
+    it1 = tag(fix, "iter1")
+    assert float((h["p"] - it1["p"]).abs().max()) < 5e-5
+    assert_close(h["logZ"], it1["logZ"], PARITY, "logZ")
+    assert_close(h["NA"], it1["NA"], PARITY, "NA")
+    for k in ("obs.mu", "obs.lambda_mu", "obs.invU.invU", "obs.invU.nu", "transition.alpha", "initial.alpha"):
+        assert_close(O.flatten_state(h)[k], it1[k], PARITY, k)
+    trace += O.hmm_niw_update(h, y, iters=2)
+    got = np.array([float(e) for e in trace])
+    assert np.max(np.abs(got - fix["ELBO"]) / np.abs(fix["ELBO"])) < PARITY
+
+
 @pytest.mark.parametrize("name", ["molt_given_n3_p4_k5", "molt_given_n8_p16_k6"])
 def test_molt_given_beliefs(name):
     """Expectation-input E and M steps (transforms/MatrixNormalWishart.py:143-172, 234-249;
