@@ -291,7 +291,7 @@ def test_reference_hmm_runs_on_the_cuda_path(cuda_default, name):
         elbo.append(h.ELBO_last.detach().cpu().double().numpy())
         if i == 0:
             it1 = tag(fix, "iter1")
-            assert float((h.p.cpu() - it1["p"]).abs().max()) < 2e-4
+            assert float((h.p.cpu() - it1["p"].cpu()).abs().max()) < 2e-4
             for k in ("obs.mu", "obs.lambda_mu", "obs.invU.invU", "obs.invU.nu", "transition.alpha", "initial.alpha"):
                 assert_close(_get(h, k.replace("obs.", "obs_dist.")), it1[k], 1e-4, k)
             assert_close(h.NA, it1["NA"], 1e-4, "NA")
