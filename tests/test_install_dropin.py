@@ -298,3 +298,161 @@ def test_reference_hmm_runs_on_the_cuda_path(cuda_default, name):
     assert _lib.LAUNCHES - n0 >= 4 * 3                        # K1, K2, K6, K3 / K5 every iteration
     assert np.max(np.abs(np.stack(elbo) - fix["ELBO"]) / np.abs(fix["ELBO"])) < 1e-4
     assert (h.assignment().cpu().numpy() == fix["final/assignment"]).mean() > 0.995
+
+
+# -------------------------------------------------------------------------------------------------------------------
+# GPU: the reference's OTHER models — hierarchical / tensor HMMs, mixtures with replica and extra event dims, LDS,
+# dMixtureofLinearTransforms — drive the installed nodes with layouts the three target models never produce (SURVEY.md
+# Appendix D last row, Appendix E).  Three runs of the same scenario from the same initial state:
+#   (A) the unmodified reference on the CPU                      -> the truth
+#   (B) the unmodified reference on CUDA, nothing installed      -> can the reference itself run this on a GPU at all?
+#   (C) the reference on CUDA with install()                     -> the drop-in
+# If (B) runs, (C) must run and agree with (A); if the reference's own code is not GPU-clean for a scenario, it is skipped.
+# -------------------------------------------------------------------------------------------------------------------
+
+def _walk_tensors(obj, fn, seen=None, depth=0):
+    """Apply fn(owner, key, tensor) to every tensor attribute of a pyVBMP object graph (objects, lists, tuples, dicts)."""
+    seen = set() if seen is None else seen
+    if id(obj) in seen or depth > 8:
+        return
+    seen.add(id(obj))
+    if isinstance(obj, (list, tuple)):
+        items = list(enumerate(obj))
+    elif isinstance(obj, dict):
+        items = list(obj.items())
+    elif hasattr(obj, "__dict__") and type(obj).__module__.split(".")[0] in ("dists", "transforms", "models", "pyvbmp_b200"):
+        items = list(vars(obj).items())
+    else:
+        return
+    for k, v in items:
+        if isinstance(v, torch.Tensor):
+            fn(obj, k, v)
+        else:
+            _walk_tensors(v, fn, seen, depth + 1)
+
+
+def _snapshot(model):
+    out = []
+    _walk_tensors(model, lambda o, k, t: out.append(t.detach().cpu().clone()))
+    return out
+
+
+def _restore(model, snap, device):
+    it = iter(snap)
+
+    def put(o, k, t):
+        v = next(it)
+        assert tuple(v.shape) == tuple(t.shape), (type(o).__name__, k, v.shape, t.shape)
+        if isinstance(o, list):
+            o[k] = v.to(device)
+        elif isinstance(o, dict):
+            o[k] = v.to(device)
+        elif not isinstance(o, tuple):
+            setattr(o, k, v.to(device))
+    _walk_tensors(model, put)
+
+
+def _switching(g, K, d, T, S):
+    A = torch.rand(K, K, generator=g) + 4 * torch.eye(K)
+    A = A / A.sum(-1, keepdim=True)
+    B = 2.0 * torch.randn(K, d, generator=g)
+    z = torch.zeros(T, S, dtype=torch.long)
+    z[0] = torch.randint(K, (S,), generator=g)
+    for t in range(1, T):
+        z[t] = torch.multinomial(A[z[t - 1]], 1, generator=g).squeeze(-1)
+    return B[z] + 0.3 * torch.randn(T, S, d, generator=g)
+
+
+def _scenario(which, mods, data, dev):
+    """Build the model of scenario `which` on the current default device; returns (model, step, outputs)."""
+    dists, transforms, models = mods
+    if which == "hhmm":                      # tests/test_models.py:320-326
+        from models.HHMM import HHMM
+        m = HHMM(dists.NormalInverseWishart(event_shape=(2,), batch_shape=(2, 3, 2)), 3)
+        return m, (lambda: m.update(data["y"].to(dev), iters=1, lr=1)), (lambda: (m.p, m.ELBO_last))
+    if which == "tensor_hmm":                # tests/test_models.py:340-347
+        from models.Tensor_HMM import Tensor_HMM
+        m = Tensor_HMM(dists.NormalInverseWishart(event_shape=(2,), batch_shape=(2, 3, 2)), event_shape=(2, 3, 2))
+        return m, (lambda: m.update(data["y"].to(dev), iters=1, lr=1)), (lambda: (m.p, m.ELBO_last))
+    if which == "mixture_joint":             # tests/test_dists.py:284-288: softmax jointly over (G, K), event_dim > 1 emissions
+        m = dists.Mixture(dists.NormalInverseWishart(event_shape=(3, 2), batch_shape=(2, 4)), event_shape=(2, 4))
+        return m, (lambda: m.update(data["x32"].to(dev), iters=1, lr=1)), (lambda: (m.p, m.ELBO_last, m.NA))
+    if which == "mixture_replicas":          # tests/test_dists.py:261-276: G independent mixtures, each with its own column
+        m = dists.Mixture(dists.NormalInverseWishart(event_shape=(2,), batch_shape=(3, 4)), event_shape=(4,))
+        return m, (lambda: m.update(data["xg"].to(dev), iters=1, lr=1)), (lambda: (m.p, m.ELBO_last, m.NA))
+    if which == "lds":                       # models/LinearDynamicalSystems.py:96,152-153 call MatrixNormalWishart.ss_update
+        m = models.LinearDynamicalSystems((4,), 2, 2, 2, latent_noise='shared')
+        y, u, r = data["ly"].to(dev), data["lu"].to(dev), data["lr"].to(dev)
+        return m, (lambda: m.update(y, u, r, iters=1, lr=1.0, verbose=False)), (lambda: (m.px.mean(), m.logZ))
+    if which == "dmolt":                     # transforms/dMixtureofLinearTransforms.py:42,54
+        m = transforms.dMixtureofLinearTransforms(3, 4, 3, batch_shape=(), pad_X=True)
+        X, Y = data["dx"].to(dev), data["dy"].to(dev)
+        return m, (lambda: m.raw_update(X, Y, iters=1, lr=1.0, verbose=False)), (lambda: (m.predict(X)[1],))
+    raise KeyError(which)
+
+
+def _import_reference(device):
+    V.uninstall()
+    _purge_reference_modules()
+    torch.set_default_device(device)
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    import dists, transforms, models          # noqa: F401,E401
+    return sys.modules["dists"], sys.modules["transforms"], sys.modules["models"]
+
+
+@needs_ref
+@pytest.mark.gpu
+@pytest.mark.parametrize("which", ["hhmm", "tensor_hmm", "mixture_joint", "mixture_replicas", "lds", "dmolt"])
+def test_other_reference_models_on_cuda_match_the_cpu_reference(which):
+    from pyvbmp_b200 import _lib
+    old = torch.empty(0).device
+    g = torch.Generator().manual_seed(91)
+    data = {"y": _switching(g, 5, 2, 16, 6), "x32": torch.randn(300, 3, 2, generator=g) * 1.5,
+            "xg": torch.randn(300, 3, 2, generator=g) * 1.5 + torch.randint(3, (300, 1, 1), generator=g) * 2.0,
+            "ly": torch.randn(12, 5, 4, generator=g), "lu": torch.randn(12, 5, 2, generator=g),
+            "lr": torch.randn(12, 5, 2, generator=g), "dx": torch.randn(200, 4, generator=g),
+            "dy": torch.randn(200, 3, generator=g)}
+    iters = 2
+    try:
+        # (A) the unmodified reference on the CPU
+        mods = _import_reference("cpu")
+        torch.manual_seed(17)
+        m, step, outs = _scenario(which, mods, data, "cpu")
+        snap = _snapshot(m)
+        for _ in range(iters):
+            step()
+        truth = [torch.as_tensor(o).detach().cpu().double().clone() for o in outs()]
+
+        def on_cuda(install):
+            mods = _import_reference("cuda:0")
+            if install:
+                assert V.install(REF) > 0
+            torch.manual_seed(17)
+            m, step, outs = _scenario(which, mods, data, "cuda:0")
+            _restore(m, snap, "cuda:0")
+            for _ in range(iters):
+                step()
+            return [torch.as_tensor(o).detach().cpu().double().clone() for o in outs()]
+        # (B) the unmodified reference on CUDA: is the reference's own code GPU-clean for this scenario?
+        try:
+            plain = on_cuda(False)
+        except Exception as e:                 # noqa: BLE001
+            pytest.skip(f"the unmodified reference does not run this scenario on CUDA itself: {type(e).__name__}: {e}"[:200])
+        # (C) the drop-in
+        n0 = _lib.LAUNCHES
+        ours = on_cuda(True)
+        launched = _lib.LAUNCHES - n0
+    finally:
+        torch.set_default_device(old)
+        V.uninstall()
+        _purge_reference_modules()
+    for a, b, c in zip(truth, plain, ours):
+        assert a.shape == c.shape
+        scale = max(float(a.abs().max()), 1e-30)
+        err_ours, err_plain = float((c - a).abs().max()) / scale, float((b - a).abs().max()) / scale
+        # the drop-in may not be further from the CPU reference than 1e-4 (or than the reference's own CUDA run, if that
+        # is already further: a free-running fp32 trajectory on another device)
+        assert err_ours <= max(2e-4, 3 * err_plain), (which, err_ours, err_plain)
+    if which != "dmolt":
+        assert launched > 0, "install() was active but no kernel of the library ran"
