@@ -224,3 +224,112 @@ def test_molt_update_given_beliefs_vs_fp64_oracle():
         flat = O.flatten_state(ref)
         for k in MOLT_STATE:
             assert_close(get(m, k), flat[k], 3e-4 if it == 0 else PARITY, f"{k} it{it}")
+
+
+def test_cfg3_full_size_properties():
+    """BASELINE.json configs[2] at its full size (MixtureofLinearTransforms, N = 8 388 608, n = p = 32, K = 64): properties that
+    need no oracle, plus an fp64 evaluation of one component's statistics from the kernel's own responsibilities."""
+    import numpy as np
+    N, n, p, K = 8_388_608, 32, 32, 64
+    g = torch.Generator(device=DEV).manual_seed(1)
+    X = torch.randn(N, p, generator=g, device=DEV)
+    W = torch.randn(K, n, p, generator=g, device=DEV) / p ** 0.5
+    b = torch.randn(K, n, generator=g, device=DEV)
+    z = torch.randint(K, (N,), generator=g, device=DEV)
+    Y = torch.empty(N, n, device=DEV)
+    for a in range(0, N, 1 << 20):
+        e = a + (1 << 20)
+        Y[a:e] = torch.einsum("nij,nj->ni", W[z[a:e]], X[a:e]) + b[z[a:e]] + 0.1 * torch.randn(e - a, n, generator=g, device=DEV)
+    del W, b, z
+    torch.manual_seed(0)
+    m = V.MixtureofLinearTransforms(n, p, K, pad_X=True).to(DEV)
+    Xc, Yc = X.unsqueeze(-1), Y.unsqueeze(-1)
+    elbo = []
+    for _ in range(3):
+        m.raw_update(Xc, Yc, iters=1, lr=1)
+        elbo.append(float(m.ELBO_last))
+    assert all(np.isfinite(elbo))
+    assert elbo[1] >= elbo[0] - 1e-6 * abs(elbo[0]) and elbo[2] >= elbo[1] - 1e-6 * abs(elbo[1])     # VB-EM is monotone
+    assert int((m.W.info != 0).sum()) == 0
+    m.update_assignments(Xc, Yc)
+    rs = m.p.sum(-1)
+    assert_maxabs(rs, torch.ones_like(rs), 2e-5, "rows of p sum to 1")
+    assert_close(m.NA, m.p.double().sum(0), 1e-5, "NA vs p.sum")
+    assert abs(float(m.NA.double().sum()) - N) < 1e-6 * N
+    assert torch.isfinite(m.logZ).all() and m.logZ.shape == (N,)
+    # chunk independence of the E-step (bitwise)
+    p_full, lz_full = m.p.clone(), m.logZ.clone()
+    cut = N // 2 + 4321
+    m.update_assignments(Xc[:cut], Yc[:cut])
+    assert torch.equal(m.p, p_full[:cut]) and torch.equal(m.logZ, lz_full[:cut])
+    # M-step: the posterior mean of the busiest component from fp64 sums over the SAME responsibilities
+    # (transforms/MatrixNormalWishart.py:105-108: invV = invV_0 + SExx, mu = (mu_0 invV_0 + SEyx) invV^-1)
+    k0 = int(p_full.sum(0).argmax())
+    w = p_full[:, k0].double()
+    SExx = torch.zeros(p + 1, p + 1, dtype=torch.float64, device=DEV)
+    SEyx = torch.zeros(n, p + 1, dtype=torch.float64, device=DEV)
+    for a in range(0, N, 1 << 19):
+        xa = torch.cat([X[a:a + (1 << 19)], torch.ones(min(1 << 19, N - a), 1, device=DEV)], -1).double()
+        wa = w[a:a + (1 << 19)].unsqueeze(-1)
+        SExx += (xa * wa).t() @ xa
+        SEyx += (Y[a:a + (1 << 19)].double() * wa).t() @ xa
+    W0 = m.W
+    invV0, mu0 = W0.invV_0[k0].double(), W0.mu_0[k0].double()
+    m.p = p_full
+    m.NA = p_full.sum(0)
+    W0.raw_update(X.view(N, 1, p, 1), Y.view(N, 1, n, 1), p=p_full, lr=1.0)
+    invV = invV0 + SExx
+    mu = torch.linalg.solve(invV, (mu0 @ invV0 + SEyx).t()).t()
+    assert_close(W0.invV[k0], invV, 1e-5, "invV of the busiest component vs fp64 sums")
+    assert_close(W0.mu[k0], mu, 1e-4, "mu of the busiest component vs fp64 sums")
+
+
+def test_cfg4_full_size_properties():
+    """BASELINE.json configs[3] at its full size (ARHMM, 4096 sequences x T = 1024, d = 16, K = 32): the forward-backward kernel
+    against the fp64 restatement on a handful of full-length sequences, and reductions that must hold exactly."""
+    import numpy as np
+    S, T, d, K = 4096, 1024, 16, 32
+    g = torch.Generator(device=DEV).manual_seed(2)
+    A = 0.95 * torch.linalg.qr(torch.randn(K, d, d, generator=g, device=DEV))[0]
+    P = 4 * torch.eye(K, device=DEV) + torch.rand(K, K, generator=g, device=DEV)
+    P = P / P.sum(-1, keepdim=True)
+    y = torch.zeros(T + 1, S, d, device=DEV)
+    zt = torch.randint(K, (S,), generator=g, device=DEV)
+    y[0] = torch.randn(S, d, generator=g, device=DEV)
+    for t in range(T):
+        y[t + 1] = torch.einsum("sij,sj->si", A[zt], y[t]) + 0.3 * torch.randn(S, d, generator=g, device=DEV)
+        zt = torch.multinomial(P[zt], 1, generator=g).squeeze(-1)
+    X = y[:-1].reshape(T, S, 1, d, 1).contiguous()
+    Y = y[1:].reshape(T, S, 1, d, 1).contiguous()
+    torch.manual_seed(0)
+    h = V.ARHMM(K, d, d).to(DEV)
+    elbo = []
+    for _ in range(3):
+        h.update((X, Y), iters=1, lr=1)
+        elbo.append(float(h.ELBO_last))
+    assert all(np.isfinite(elbo)) and elbo[2] > elbo[0]
+    # one more E-step by hand: emission logits -> forward-backward
+    ol = h.obs_logits((X, Y))
+    assert ol.shape == (T, S, K)
+    p, SEzz, SEz0, logZ = h.forward_backward_logits(ol.clone())
+    assert p.shape == (T, S, K) and SEzz.shape == (S, K, K) and SEz0.shape == (S, K) and logZ.shape == (S,)
+    rs = p.sum(-1)
+    assert_maxabs(rs, torch.ones_like(rs), 2e-5, "smoothed marginals sum to 1")
+    # every step (T - 1 transitions + the initial one) adds a normalised joint to SEzz; SEz0 is a distribution
+    assert_maxabs(SEzz.double().sum((-1, -2)), torch.full((S,), float(T), dtype=torch.float64), 2e-5 * T, "sum of SEzz per sequence")
+    assert_maxabs(SEz0.sum(-1), torch.ones(S), 2e-5, "SEz0 sums to 1")
+    # the column sums of SEzz are the smoothed marginals summed over time (xi_t marginalised over the previous state)
+    assert_close(SEzz.double().sum(-2), p.double().sum(0), 2e-5, "SEzz column sums vs sum_t p_t")
+    # fp64 restatement of models/HMM.py:72-105 on a few full-length sequences
+    idx = torch.tensor([0, 1, 1777, 4095], device=DEV)
+    ref = O.hmm_new(None, K, dtype=torch.float64)
+    ref["transition"]["alpha"] = h.transition.alpha.detach().cpu().double()
+    ref["transition"]["alpha_0"] = h.transition.alpha_0.detach().cpu().double()
+    ref["initial"]["alpha"] = h.initial.alpha.detach().cpu().double()
+    ref["initial"]["alpha_0"] = h.initial.alpha_0.detach().cpu().double()
+    pr, SEzzr, SEz0r, logZr = O.hmm_forward_backward_logits(ref, ol[:, idx].detach().cpu().double())
+    L = float(ol[:, idx].abs().max())
+    assert_maxabs(p[:, idx].cpu().double(), pr, max(5e-5, 1e-6 * L), f"p vs fp64 forward-backward (|logit| {L:.1e})")
+    assert_close(logZ[idx], logZr, 1e-5, "logZ per sequence")
+    assert_close(SEzz[idx], SEzzr, 1e-4, "SEzz per sequence")
+    assert_maxabs(SEz0[idx].cpu().double(), SEz0r, 5e-5, "SEz0")
