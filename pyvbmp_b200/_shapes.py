@@ -109,5 +109,17 @@ def logits_to_ref(out, plan: Plan):
     return t
 
 
+_IDX_CACHE = {}
+
+
 def idx_tensor(v, device):
-    return torch.tensor(list(v), dtype=torch.int32, device=device)
+    """int32 index vector on `device` (the kernels' xg / pg group maps).  Cached: the same few tuples are asked for by every
+    E-step / Gram call, and building one is a pageable host -> device copy (~15 us of host time each, 2-3 per EM iteration,
+    two per streamed chunk).  The kernels only read them."""
+    key = (tuple(int(i) for i in v), str(device))
+    t = _IDX_CACHE.get(key)
+    if t is None:
+        if len(_IDX_CACHE) > 256:
+            _IDX_CACHE.clear()
+        t = _IDX_CACHE[key] = torch.tensor(list(key[0]), dtype=torch.int32, device=device)
+    return t
