@@ -155,7 +155,10 @@ int gram_simt_plan(long long N, int G, int K, int Dp, long long* S_per, int* spl
   long long want = (148 * 4 + ctas_per_split - 1) / ctas_per_split;      // ~4 waves of CTAs
   const long long min_for_chain = (N + 65535) / 65536;                   // <= 65 536 samples per split
   if (want < min_for_chain) want = min_for_chain;
-  const long long max_useful = (N + 1023) / 1024;                        // >= 1024 samples per split
+  // >= 256 samples per split (one first-level block).  This bound only binds for small N with few components, where the
+  // grid is tiny anyway: at N = 10 000, d = 2, K = 20 the former 1024 gave 10 CTAs (0.30 ms, the longest kernel of an EM
+  // iteration there); the partials stay small (splits x G x K x (D+1)^2 floats) because want is capped at ~4 waves
+  const long long max_useful = (N + 255) / 256;
   if (want > max_useful) want = max_useful;
   if (want < 1) want = 1;
   long long sp = (N + want - 1) / want;
