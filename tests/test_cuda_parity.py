@@ -624,6 +624,43 @@ def test_gmm_empty_and_tiny_inputs(N, d, K):
             assert_close(get(m, k), flat[k], 3e-4 if it == 0 else PARITY, f"{k} it{it}")
 
 
+@pytest.mark.parametrize("N,d,K", [(500, 1, 1), (5000, 1, 3), (700, 2, 1), (4000, 3, 2), (5000, 16, 1), (3000, 64, 2),
+                                   (2600, 64, 1), (3000, 128, 3), (9, 1, 1)])
+def test_gmm_degenerate_shapes(N, d, K):
+    """One feature, one / two / three components (fewer than the 4-component granule of the tensor-core kernels, on both
+    kernel families and at D = 128): a "mixture" of one Gaussian is what a first-time user of the reference fits.  Three
+    STEP-WISE EM iterations against the fp64 oracle: its state is copied in before each step (SURVEY.md Appendix F.3 — run
+    free, an fp32 trajectory at |logit| ~ 1e4 leaves the fp64 one by 1e-3 in p within two iterations, on the CPU just as on
+    the GPU), and responsibilities are gated at the fp32 floor of the logits they come from, max(2e-5, 2e-7 |logit|)."""
+    g = torch.Generator().manual_seed(7 * N + d + K)
+    mu = 2.0 * torch.randn(K, d, generator=g)
+    X = mu[torch.randint(K, (N,), generator=g)] + torch.randn(N, d, generator=g) * 0.8
+    torch.manual_seed(4)
+    m = V.GaussianMixtureModel(K, d)
+    ref = O.gmm_new(K, d)
+    O.load_state(ref, {"dist.mu": m.dist.mu.clone(), "pi.alpha": m.pi.alpha.clone()})
+    O.to_dtype(ref, torch.float64)
+    m.to(DEV)
+    Xd = X.to(DEV)
+    for it in range(3):
+        set_state(m, {k: v.float() for k, v in O.flatten_state(ref).items()})
+        m.update(Xd, 1)
+        tr = O.mixture_update(ref, X.double(), 1, exact=False)
+        assert m.p.shape == (N, K) and m.assignment().shape == (N,)
+        assert abs(float(m.ELBO_last) - float(tr[0])) <= PARITY * abs(float(tr[0])), (it, float(m.ELBO_last), float(tr[0]))
+        assert_close(m.NA, ref["NA"], PARITY, "NA")
+        L = float(ref["log_p"].abs().max())
+        err = float((m.p.cpu().double() - ref["p"]).abs().max())
+        print(f"[p-gate] N={N} d={d} K={K} it{it}: max |dp| = {err:.2e} at |logit| <= {L:.2e}")
+        assert err <= max(2e-5, 2e-7 * L), (it, err, L)
+        nbad, margins = argmax_mismatch_report(m.p, ref["p"], ref["log_p"])
+        assert nbad == 0 or max(margins) < 1e-3 * max(1.0, L / 1e3), (it, nbad, margins)
+        flat = O.flatten_state(ref)
+        for k in NIW_STATE:
+            assert_close(get(m, k), flat[k], 3e-4 if it == 0 else PARITY, f"{k} it{it}")
+    assert int((m.dist.invU.info != 0).sum()) == 0
+
+
 def test_other_models_accept_an_empty_batch():
     """N = 0 through the diagonal-precision, matrix-normal and HMM-free paths: the call succeeds, p has shape (0, K), NA = 0
     (the reference's sums over no rows), and a following non-empty batch works."""
