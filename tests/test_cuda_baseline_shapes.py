@@ -333,3 +333,124 @@ def test_cfg4_full_size_properties():
     assert_close(logZ[idx], logZr, 1e-5, "logZ per sequence")
     assert_close(SEzz[idx], SEzzr, 1e-4, "SEzz per sequence")
     assert_maxabs(SEz0[idx].cpu().double(), SEz0r, 5e-5, "SEz0")
+
+
+# ---- degenerate layouts of the matrix-normal models and the HMM glue (step-wise against the fp64 oracle) -------------------
+
+@pytest.mark.parametrize("N,n,p,K,pad", [(600, 1, 1, 2, True), (3000, 1, 3, 1, True), (2500, 5, 1, 3, False), (4000, 2, 2, 1, False),
+                                         (9, 3, 2, 2, True)])
+def test_molt_degenerate_shapes(N, n, p, K, pad):
+    """MixtureofLinearTransforms with one output, one regressor, one expert, with and without the padded column."""
+    g = torch.Generator().manual_seed(11 * N + n + p + K)
+    X = torch.randn(N, p, 1, generator=g)
+    Wt = torch.randn(K, n, p, generator=g)
+    z = torch.randint(K, (N,), generator=g)
+    Y = (torch.einsum("nij,nj->ni", Wt[z], X[..., 0]) + 0.2 * torch.randn(N, n, generator=g)).unsqueeze(-1)
+    torch.manual_seed(2)
+    m = V.MixtureofLinearTransforms(n, p, K, pad_X=pad)
+    ref = O.molt_new(n, p, K, pad_X=pad)
+    O.load_state(ref, {"W.mu": m.W.mu.clone(), "pi.alpha": m.pi.alpha.clone()})
+    O.to_dtype(ref, torch.float64)
+    m.to(DEV)
+    Xd, Yd = X.to(DEV), Y.to(DEV)
+    for it in range(3):
+        set_state(m, {k: v.float() for k, v in O.flatten_state(ref).items()})
+        m.raw_update(Xd, Yd, iters=1)
+        tr = O.molt_raw_update(ref, X.double(), Y.double(), 1, exact=True)
+        assert m.p.shape == (N, K) and m.logZ.shape == (N,)
+        assert abs(float(m.ELBO_last) - float(tr[0])) <= PARITY * abs(float(tr[0])), (it, float(m.ELBO_last), float(tr[0]))
+        _p_gate(m.p, ref, f"MoLT N={N} n={n} p={p} K={K} pad={pad} it{it}")
+        assert_close(m.logZ, ref["logZ"], PARITY, f"logZ_n it{it}")
+        flat = O.flatten_state(ref)
+        for k in MOLT_STATE:
+            assert_close(get(m, k), flat[k], 3e-4 if it == 0 else PARITY, f"{k} it{it}")
+
+
+@pytest.mark.parametrize("K,n,T,S", [(1, 2, 12, 5), (2, 3, 1, 4), (3, 2, 7, 1), (4, 1, 30, 6)])
+def test_arhmm_degenerate_shapes(K, n, T, S):
+    """ARHMM with one state, one time step, one sequence, one output dimension."""
+    g = torch.Generator().manual_seed(5 * K + n + T + S)
+    X = torch.randn(T, S, 1, n, 1, generator=g)
+    Y = (0.7 * X + 0.3 * torch.randn(T, S, 1, n, 1, generator=g))
+    torch.manual_seed(9)
+    h = V.ARHMM(K, n, n)
+    ref = O.arhmm_new(K, n, n)
+    O.load_state(ref, {"obs.mu": h.obs_dist.mu.clone(), "transition.alpha": h.transition.alpha.clone(),
+                       "initial.alpha": h.initial.alpha.clone()})
+    O.to_dtype(ref, torch.float64)
+    h.to(DEV)
+    Xd, Yd = X.to(DEV), Y.to(DEV)
+    keys = ("obs.mu", "obs.invV", "obs.V", "obs.invU.invU", "obs.invU.U", "obs.invU.nu", "transition.alpha", "initial.alpha")
+    for it in range(3):
+        set_state(h, {k.replace("obs.", "obs_dist."): v.float() for k, v in O.flatten_state(ref).items()})
+        h.update((Xd, Yd), iters=1)
+        tr = O.arhmm_update(ref, X.double(), Y.double(), 1, exact=True)
+        assert h.p.shape == (T, S, K)
+        assert_maxabs(h.p.cpu().double(), ref["p"], 5e-5, f"p it{it}")
+        assert_close(h.logZ, ref["logZ"], PARITY, f"logZ it{it}")
+        assert_close(h.NA, ref["NA"], PARITY, f"NA it{it}")
+        assert abs(float(h.ELBO_last) - float(tr[0])) <= PARITY * abs(float(tr[0])), it
+        flat = O.flatten_state(ref)
+        for k in keys:
+            assert_close(get(h, k.replace("obs.", "obs_dist.")), flat[k], 3e-4 if it == 0 else PARITY, f"{k} it{it}")
+
+
+def test_hmm_more_than_32_states():
+    """K = 40 hidden states: beyond the forward-backward kernel's one-warp-per-sequence layout, so the recursion runs as batched
+    torch ops on the device around the same K1 / K2 / K3 / K5 kernels (hmm.py) — against the fp64 oracle, step-wise."""
+    K, d, T, S = 40, 3, 25, 12
+    g = torch.Generator().manual_seed(77)
+    cent = 3.0 * torch.randn(K, d, generator=g)
+    y = cent[torch.randint(K, (T, S), generator=g)] + 0.4 * torch.randn(T, S, d, generator=g)
+    torch.manual_seed(6)
+    h = V.HMM(V.NormalInverseWishart(event_shape=(d,), batch_shape=(K,)))
+    ref = O.hmm_new(O.niw_new((d,), (K,)), K)
+    O.load_state(ref, {"obs.mu": h.obs_dist.mu.clone(), "transition.alpha": h.transition.alpha.clone(),
+                       "initial.alpha": h.initial.alpha.clone()})
+    O.to_dtype(ref, torch.float64)
+    h.to(DEV)
+    yd = y.to(DEV)
+    keys = ("obs.mu", "obs.lambda_mu", "obs.invU.invU", "obs.invU.U", "obs.invU.nu", "transition.alpha", "initial.alpha")
+    for it in range(3):
+        set_state(h, {k.replace("obs.", "obs_dist."): v.float() for k, v in O.flatten_state(ref).items()})
+        h.update(yd, iters=1)
+        tr = O.hmm_niw_update(ref, y.double(), 1)
+        assert h.p.shape == (T, S, K)
+        assert_maxabs(h.p.cpu().double(), ref["p"], 5e-5, f"p it{it}")
+        assert_close(h.logZ, ref["logZ"], PARITY, f"logZ it{it}")
+        assert abs(float(h.ELBO_last) - float(tr[0])) <= PARITY * abs(float(tr[0])), it
+        flat = O.flatten_state(ref)
+        for k in keys:
+            assert_close(get(h, k.replace("obs.", "obs_dist.")), flat[k], 3e-4 if it == 0 else PARITY, f"{k} it{it}")
+
+
+def test_views_and_offsets_give_the_same_bits():
+    """Rows handed over as a non-contiguous view, as a slice at an odd element offset (not 16-byte aligned) and as fp64 give the
+    results of the contiguous fp32 copy bit for bit (the binding re-bases / converts; the kernels see the same values)."""
+    N, d, K = 3000, 16, 8
+    g = torch.Generator().manual_seed(3)
+    base = torch.randn(N + 1, 2 * d + 1, generator=g).to(DEV)
+    variants = {"contiguous": base[1:, 1:2 * d + 1:2].contiguous(), "strided view": base[1:, 1:2 * d + 1:2],
+                "odd offset": base.reshape(-1)[1:1 + N * d].view(N, d)}
+    variants["fp64"] = variants["contiguous"].double()
+    outs = {}
+    for name, X in variants.items():
+        Xr = variants["contiguous"] if name in ("strided view", "fp64") else X
+        torch.manual_seed(1)
+        m = V.GaussianMixtureModel(K, d)
+        m.dist.mu = variants["contiguous"][:K].clone().cpu() if name != "odd offset" else X[:K].float().clone().cpu()
+        m.to(DEV)
+        m.update(X, 2)
+        outs[name] = (m.p.clone(), m.dist.mu.clone(), m.ELBO_last.clone(), Xr)
+    for name in ("strided view", "fp64"):
+        for a, b in zip(outs[name][:3], outs["contiguous"][:3]):
+            assert torch.equal(a, b), name
+    # the odd-offset slice holds different numbers; it must agree with ITS contiguous clone
+    Xo = variants["odd offset"].clone()
+    torch.manual_seed(1)
+    m = V.GaussianMixtureModel(K, d)
+    m.dist.mu = Xo[:K].clone().cpu()
+    m.to(DEV)
+    m.update(Xo, 2)
+    for a, b in zip(outs["odd offset"][:3], (m.p, m.dist.mu, m.ELBO_last)):
+        assert torch.equal(a, b), "odd offset"
