@@ -454,3 +454,77 @@ def test_views_and_offsets_give_the_same_bits():
     m.update(Xo, 2)
     for a, b in zip(outs["odd offset"][:3], (m.p, m.dist.mu, m.ELBO_last)):
         assert torch.equal(a, b), "odd offset"
+
+
+def test_interleaved_models_and_changing_inputs():
+    """The binding caches three things between calls — the grow-only workspace, the E-step's weight images for the next Gram and
+    the transposed sample image of X — all keyed on tensor identity / version.  Usage patterns that would expose a stale cache:
+    two models updated alternately on the same stream (one of them on a second data set of another size), rows edited in
+    place between iterations, and a model that returns to an earlier, smaller data set.  Every result must equal, bit for bit,
+    the result of the same model run on its own in a fresh state."""
+    from pyvbmp_b200 import _lib
+    d, K = 64, 32
+    g = torch.Generator(device=DEV).manual_seed(12)
+    XA = torch.randn(6000, d, generator=g, device=DEV) * 1.3
+    XB = torch.randn(9001, d, generator=g, device=DEV) * 0.7 + 0.5
+
+    def fresh(seed, X):
+        torch.manual_seed(seed)
+        m = V.GaussianMixtureModel(K, d)
+        m.dist.mu = X[:K].clone().cpu()
+        return m.to(DEV)
+
+    def state(m):
+        return [t.clone() for t in (m.dist.mu, m.dist.invU.invU, m.dist.lambda_mu, m.pi.alpha, m.ELBO_last, m.p)]
+
+    def same(a, b, what):
+        for i, (x, y) in enumerate(zip(a, b)):
+            assert torch.equal(x, y), (what, i)
+
+    # on their own
+    a = fresh(1, XA)
+    for _ in range(3):
+        a.update(XA, 1)
+    alone_a = state(a)
+    b = fresh(2, XB)
+    for _ in range(3):
+        b.update(XB, 1)
+    alone_b = state(b)
+    # alternately (and with the E-step and the M-step of the two models interleaved by hand in the last round)
+    _lib.release_workspaces()
+    a, b = fresh(1, XA), fresh(2, XB)
+    for _ in range(2):
+        a.update(XA, 1)
+        b.update(XB, 1)
+    a.update_assignments(XA)
+    b.update_assignments(XB)                       # B's E-step lands between A's E-step and A's M-step
+    ea = a.ELBO()
+    a.update_parms(XA, 1.0)
+    a.ELBO_last = ea
+    eb = b.ELBO()
+    b.update_parms(XB, 1.0)
+    b.ELBO_last = eb
+    same(state(a), alone_a, "model A interleaved")
+    same(state(b), alone_b, "model B interleaved")
+    # rows edited in place between iterations: the second iteration must see the new rows
+    Xe = XA.clone()
+    c = fresh(3, Xe)
+    c.update(Xe, 1)
+    Xe.mul_(1.5)
+    c.update(Xe, 1)
+    ref = fresh(3, XA)
+    ref.update(XA.clone(), 1)
+    ref.update((XA * 1.5).contiguous(), 1)
+    same(state(c), state(ref), "rows edited in place")
+    # back to an earlier, smaller data set after a larger one
+    e = fresh(4, XA)
+    e.update(XA, 1)
+    e.update(XB, 1)
+    e.update(XA, 1)
+    f = fresh(4, XA)
+    f.update(XA.clone(), 1)
+    _lib.release_workspaces()
+    f.update(XB.clone(), 1)
+    _lib.release_workspaces()
+    f.update(XA.clone(), 1)
+    same(state(e), state(f), "returning to a smaller data set")
