@@ -376,18 +376,30 @@ def gen_hmm_variants():
     cases = (("hmm_niw_k6", dict(K=4, d=2, Tn=30, S=20), (2,), (6,), lambda y: y),
              ("hmm_batch3_k6", dict(K=4, d=2, Tn=24, S=10), (2,), (3, 6), lambda y: y.unsqueeze(-2)),
              ("hmm_event32_k5", dict(K=5, d=6, Tn=20, S=15), (3, 2), (5,), lambda y: y.reshape(y.shape[:2] + (3, 2))))
+    band = torch.tril(torch.ones(6, 6), 1) * torch.triu(torch.ones(6, 6), -1)      # a banded (left-right-ish) transition structure
+    extra = {"hmm_masked_k6": dict(transition_mask=band), "hmm_ptemp2_k6": dict(ptemp=2.0),
+             "hmm_masked_ptemp05_k6": dict(transition_mask=band, ptemp=0.5)}
+    cases = cases + tuple((nm, dict(K=4, d=2, Tn=30, S=20), (2,), (6,), (lambda y: y)) for nm in extra)
+    only = set(sys.argv[2:])
     for name, gen, ev, bs, shape in cases:
+        if only and name not in only:
+            switching(noise=0.3, **gen)          # keep the data generator's stream in step
+            continue
         y = shape(switching(noise=0.3, **gen))
         torch.manual_seed(13)
         obs = dists.NormalInverseWishart(event_shape=ev, batch_shape=bs)
-        m = HMM(obs)
+        kw = extra.get(name, {})
+        m = HMM(obs, **kw)
 
         def st():
             s = niw_state(m.obs_dist, "obs.")
             s.update(dir_state(m.transition, "transition."))
             s.update(dir_state(m.initial, "initial."))
             return s
-        out = {"y": T(y), "event_shape": np.asarray(ev), "batch_shape": np.asarray(bs)}
+        out = {"y": T(y), "event_shape": np.asarray(ev), "batch_shape": np.asarray(bs),
+               "ptemp": np.float64(kw.get("ptemp", 1.0))}
+        if "transition_mask" in kw:
+            out["transition_mask"] = T(kw["transition_mask"])
         out.update(tagged(st(), "init"))
         out["init/obs_logits"] = T(m.obs_logits(y))
         el = []

@@ -323,7 +323,8 @@ def test_arhmm_golden():
     assert np.max(np.abs(np.array(elbo) - fix["ELBO"]) / np.abs(fix["ELBO"])) < PARITY
 
 
-@pytest.mark.parametrize("name", ["hmm_niw_k6", "hmm_batch3_k6", "hmm_event32_k5"])
+@pytest.mark.parametrize("name", ["hmm_niw_k6", "hmm_batch3_k6", "hmm_event32_k5", "hmm_masked_k6", "hmm_ptemp2_k6",
+                                  "hmm_masked_ptemp05_k6"])
 def test_hmm_niw_golden(name):
     """models.HMM with NIW emissions in the reference script's three layouts (tests/test_models.py:293-314 plain, :353-356 a
     batch of HMMs fed y.unsqueeze(-2), :398-409 emissions with event_dim > 1) against the reference's own outputs: emission
@@ -331,7 +332,10 @@ def test_hmm_niw_golden(name):
     fix = load_golden(name)
     ev, bs = tuple(int(v) for v in fix["event_shape"]), tuple(int(v) for v in fix["batch_shape"])
     torch.manual_seed(0)
-    h = V.HMM(V.NormalInverseWishart(event_shape=ev, batch_shape=bs)).to(DEV)
+    kw = {"ptemp": float(fix["ptemp"])}
+    if "transition_mask" in fix:
+        kw["transition_mask"] = torch.as_tensor(fix["transition_mask"])
+    h = V.HMM(V.NormalInverseWishart(event_shape=ev, batch_shape=bs), **kw).to(DEV)
     set_state(h, {k.replace("obs.", "obs_dist."): v for k, v in tag(fix, "init").items()})
     y = torch.as_tensor(fix["y"]).to(DEV)
     ol = h.obs_logits(y)

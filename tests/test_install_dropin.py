@@ -271,7 +271,8 @@ def test_reference_molt_and_arhmm_run_on_the_cuda_path(cuda_default):
 
 @needs_ref
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["hmm_niw_k6", "hmm_batch3_k6", "hmm_event32_k5"])
+@pytest.mark.parametrize("name", ["hmm_niw_k6", "hmm_batch3_k6", "hmm_event32_k5", "hmm_masked_k6", "hmm_ptemp2_k6",
+                                  "hmm_masked_ptemp05_k6"])
 def test_reference_hmm_runs_on_the_cuda_path(cuda_default, name):
     """The reference's own models.HMM over an installed NormalInverseWishart node — plain, a batch of HMMs
     (tests/test_models.py:353-356) and emissions with event_dim > 1 (:398-409) — against the unmodified reference's outputs."""
@@ -280,7 +281,10 @@ def test_reference_hmm_runs_on_the_cuda_path(cuda_default, name):
     fix = load_golden(name)
     ev, bs = tuple(int(v) for v in fix["event_shape"]), tuple(int(v) for v in fix["batch_shape"])
     torch.manual_seed(0)
-    h = models.HMM(dists.NormalInverseWishart(event_shape=ev, batch_shape=bs))
+    kw = {"ptemp": float(fix["ptemp"])}
+    if "transition_mask" in fix:
+        kw["transition_mask"] = torch.as_tensor(fix["transition_mask"]).to("cuda:0")
+    h = models.HMM(dists.NormalInverseWishart(event_shape=ev, batch_shape=bs), **kw)
     assert type(h).__module__.startswith("models.") and h.obs_dist.mu.is_cuda
     _set_state(h, {k.replace("obs.", "obs_dist."): v for k, v in tag(fix, "init").items()}, "cuda:0")
     y = torch.as_tensor(fix["y"]).to("cuda:0")

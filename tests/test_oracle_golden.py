@@ -252,14 +252,15 @@ def test_arhmm_prxry_trajectory():
     assert np.max(np.abs(got - fix["ELBO"]) / np.abs(fix["ELBO"])) < PARITY
 
 
-@pytest.mark.parametrize("name", ["hmm_niw_k6", "hmm_event32_k5"])
+@pytest.mark.parametrize("name", ["hmm_niw_k6", "hmm_event32_k5", "hmm_masked_k6", "hmm_ptemp2_k6", "hmm_masked_ptemp05_k6"])
 def test_hmm_niw_trajectory(name):
     """models.HMM with NormalInverseWishart emissions (models/HMM.py:113-152; tests/test_models.py:293-314, :398-409 layouts)."""
     fix = load_golden(name)
     ev, bs = tuple(int(v) for v in fix["event_shape"]), tuple(int(v) for v in fix["batch_shape"])
     torch.manual_seed(0)
     h = O.hmm_new(O.niw_new(ev, bs), bs[-1])
-    O.load_state(h, tag(fix, "init"))
+    O.load_state(h, tag(fix, "init"))              # a transition mask lives in the state: zeros in transition.alpha_0 / alpha
+    h["ptemp"] = float(fix["ptemp"])
     y = torch.as_tensor(fix["y"])
     ol = O.niw_elog_like_exact(h["obs"], y.unsqueeze(-1 - len(ev)))
     assert_close(ol, fix["init/obs_logits"], 2e-5, "obs_logits")
