@@ -501,10 +501,13 @@ def main():
                "api": "GaussianMixtureModel.update(X_pinned_host, 1): chunked H2D overlapped with E-step + Gram, every step"}
         # ONE call of 20 iterations on host rows (the reference's own usage, dists/Mixture.py:54-62: same X every iteration):
         # the rows cross the host link once, iterations 2..20 run on the resident copy
-        m.update(Xh, 2)                                            # warm-up of this path (resident-copy allocation)
+        # warm-up of this path with THREE iterations: two resident ones, so that both alternating responsibilities buffers exist
+        # (with two iterations the first timed call still had one 4 GiB cudaMalloc to do, tools/time_e2e20.py)
+        m.update(Xh, 3)
         barrier()
-        calls = []
+        calls, allocs = [], []
         for _ in range(2):                                         # two calls, both reported; the figure is the faster one
+            n_alloc = torch.cuda.memory_stats(dev).get("num_device_alloc", 0)
             s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s0.record()
             m.update(Xh, 20)
@@ -513,10 +516,11 @@ def main():
             s1.record()
             barrier()
             calls.append(max_over_ranks(s0.elapsed_time(s1)))
+            allocs.append(int(torch.cuda.memory_stats(dev).get("num_device_alloc", 0) - n_alloc))
         tms = min(calls)
         e2e20 = {"value": 20 * total_rows * K / (tms / 1e3), "unit": UNIT, "iters_per_call": 20,
                  "h2d_bytes_per_call": X.numel() * 4, "d2h_bytes_per_call": res_h.numel() * 4, "ms_per_iteration": tms / 20,
-                 "ms_per_call": [round(c, 2) for c in calls],
+                 "ms_per_call": [round(c, 2) for c in calls], "cuda_mallocs_in_call": allocs,
                  "api": "GaussianMixtureModel.update(X_pinned_host, 20): rows streamed once, then device-resident"}
         del Xh
 
