@@ -826,6 +826,7 @@ def molt_update_given(m, mux, Sx, muy, Sy, lr=1.0):
     Z = pu.sum(-1, True)
     m["p"] = pu / Z
     m["logZ"] = (Z.log() + shift).squeeze(-1)
+    m["log_p"] = log_p
     elbo = molt_elbo(m)
     dirichlet_ss_update(m["pi"], m["p"].sum(0), lr=lr)
     mnw_ss_update(m["W"], *mnw_stats_given(m["W"], mx, Exx, my, Eyy, m["p"]), lr=lr, beta=None)

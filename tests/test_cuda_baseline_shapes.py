@@ -528,3 +528,79 @@ def test_interleaved_models_and_changing_inputs():
     _lib.release_workspaces()
     f.update(XA.clone(), 1)
     same(state(e), state(f), "returning to a smaller data set")
+
+
+@pytest.mark.parametrize("N,n,p,K,pad", [(5000, 32, 32, 64, True), (3000, 16, 8, 10, True), (100, 5, 3, 3, False), (70000, 32, 16, 128, True),
+                                         (2049, 16, 16, 4, False), (4000, 1, 1, 2, True), (6000, 12, 7, 36, True)])
+def test_molt_predict_vs_fp64_oracle(N, n, p, K, pad):
+    """MixtureofLinearTransforms.predict at model level across the windows of its kernels (tcgen05 row GEMM with K <= 64,
+    the warp-level one otherwise; the SYRK moments kernel at n = 16 / 32, the register-tiled and row-per-lane ones otherwise;
+    K % 4 != 0; a few rows): predictive mean, covariance and gate probabilities against the fp64 oracle on a fitted model."""
+    g = torch.Generator().manual_seed(13 * N + n + p + K)
+    X = torch.randn(N, p, 1, generator=g)
+    Wt = torch.randn(K, n, p, generator=g) / p ** 0.5
+    z = torch.randint(K, (N,), generator=g)
+    Y = (torch.einsum("nij,nj->ni", Wt[z], X[..., 0]) + 0.1 * torch.randn(N, n, generator=g)).unsqueeze(-1)
+    torch.manual_seed(8)
+    m = V.MixtureofLinearTransforms(n, p, K, pad_X=pad)
+    ref = O.molt_new(n, p, K, pad_X=pad)
+    O.load_state(ref, {"W.mu": m.W.mu.clone(), "pi.alpha": m.pi.alpha.clone()})
+    O.to_dtype(ref, torch.float64)
+    O.molt_raw_update(ref, X.double(), Y.double(), 3, exact=False, chunk=8192)         # a fitted state, from the oracle
+    m.to(DEV)
+    set_state(m, {k: v.float() for k, v in O.flatten_state(ref).items()})
+    Xq = torch.randn(N, p, 1, generator=g)
+    mu_r, Sig_r, p_r = O.molt_predict(ref, Xq.double())
+    pY, pr = m.predict(Xq.to(DEV))
+    mu, Sig = pY.mean(), pY.ESigma()
+    assert mu.shape == (N, n, 1) and Sig.shape == (N, n, n) and pr.shape == (N, K)
+    assert_maxabs(pr.cpu().double(), p_r, 5e-5, "gate probabilities")
+    assert_close(mu, mu_r, 2e-5, "predictive mean")
+    # covariance entries relative to the largest one of the same sample (mu mu^T is subtracted from a sum of the same size)
+    scale = Sig_r.abs().amax((-1, -2), keepdim=True)
+    err = float(((Sig.cpu().double() - Sig_r).abs() / scale).max())
+    assert err < 5e-5, f"predictive covariance: {err:.2e}"
+    assert torch.equal(Sig, Sig.transpose(-1, -2)) or float((Sig - Sig.transpose(-1, -2)).abs().max()) <= 1e-6 * float(scale.max())
+
+
+@pytest.mark.parametrize("N,n,p,K,shared", [(4096, 32, 32, 64, False), (100, 5, 3, 3, False), (3000, 8, 4, 6, False), (5000, 16, 16, 8, True)])
+def test_molt_update_given_beliefs_windows(N, n, p, K, shared):
+    """update(pX, pY) inside (N >= 2048, K % 4 == 0) and outside the windows of vbmp_rowterm / vbmp_wsum, and with ONE covariance
+    shared by all samples (kept as a single row: its weighted sum is NA_k Sigma).  Two step-wise iterations, fp64 oracle."""
+    X, Y = _cfg3_data(N, n, p, K, seed=31)
+    g = torch.Generator().manual_seed(32)
+    if shared:
+        Ax, Ay = 0.2 * torch.randn(p, p, generator=g), 0.2 * torch.randn(n, n, generator=g)
+        Sx1, Sy1 = Ax @ Ax.t() + 0.05 * torch.eye(p), Ay @ Ay.t() + 0.05 * torch.eye(n)
+        Sx, Sy = Sx1.expand(N, p, p), Sy1.expand(N, n, n)
+        Sx_in, Sy_in = Sx1, Sy1
+    else:
+        Ax, Ay = 0.2 * torch.randn(N, p, p, generator=g), 0.2 * torch.randn(N, n, n, generator=g)
+        Sx = Ax @ Ax.transpose(-1, -2) + 0.05 * torch.eye(p)
+        Sy = Ay @ Ay.transpose(-1, -2) + 0.05 * torch.eye(n)
+        Sx_in, Sy_in = Sx, Sy
+    torch.manual_seed(6)
+    m = V.MixtureofLinearTransforms(n, p, K)
+    ref = O.molt_new(n, p, K)
+    O.load_state(ref, {"W.mu": m.W.mu.clone(), "pi.alpha": m.pi.alpha.clone()})
+    O.to_dtype(ref, torch.float64)
+    m.to(DEV)
+    pX = V.MultivariateNormal_vector_format(mu=X.to(DEV), Sigma=Sx_in.to(DEV))
+    pY = V.MultivariateNormal_vector_format(mu=Y.to(DEV), Sigma=Sy_in.to(DEV))
+    for it in range(2):
+        state_in = {k: v.clone() for k, v in O.flatten_state(ref).items()}
+        set_state(m, {k: v.float() for k, v in state_in.items()})
+        m.update(pX, pY, iters=1)
+        elbo = O.molt_update_given(ref, X.double(), Sx.double(), Y.double(), Sy.double())
+        assert abs(float(m.ELBO_last) - float(elbo)) <= PARITY * abs(float(elbo)), it
+        # the same step in fp32 on the CPU, from the same state: what plain fp32 arithmetic is from fp64 here
+        r32 = O.molt_new(n, p, K)
+        O.load_state(r32, {k: v.float() for k, v in state_in.items()})
+        O.molt_update_given(r32, X, Sx.float(), Y, Sy.float())
+        e32 = float((r32["p"].double() - ref["p"]).abs().max())
+        print(f"[fp32 CPU restatement] it{it}: max |dp| = {e32:.2e}")
+        _p_gate(m.p, ref, f"update(pX, pY) N={N} n={n} p={p} K={K} shared={shared} it{it}")
+        assert_close(m.logZ, ref["logZ"], PARITY, f"logZ_n it{it}")
+        flat = O.flatten_state(ref)
+        for k in MOLT_STATE:
+            assert_close(get(m, k), flat[k], 3e-4 if it == 0 else PARITY, f"{k} it{it}")
