@@ -367,3 +367,35 @@ def test_diag_estep_kernel_general_shapes(N, d, K, G):
 # (No replica-batch Mixture test for NormalGamma: dists/NormalGamma.py:88-94 adds `self.gamma.KLqprior().sum(-1)` — the Gamma
 # KL summed over the LAST BATCH dim as well — to a per-component vector, which broadcasts only for batch_shape = (K,); with
 # batch (G, K) the reference itself raises.  The mirror and the oracle reproduce that expression, quirk included.)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N,d,K", [(500, 1, 1), (4000, 1, 3), (700, 3, 2), (3000, 64, 1), (2600, 64, 3), (3000, 128, 2), (9, 2, 1)])
+def test_isotropic_gmm_degenerate_shapes(N, d, K):
+    """GaussianMixtureModel(isotropic=True) with one feature and with one / two / three components (diagonal E-step, the Gram
+    kernel's diagonal mode at K below its 4-component granule, D = 128): three step-wise iterations against the fp64 oracle."""
+    g = torch.Generator().manual_seed(5 * N + d + K)
+    mu = 2.0 * torch.randn(K, d, generator=g)
+    X = mu[torch.randint(K, (N,), generator=g)] + (0.5 + torch.rand(K, d, generator=g))[torch.randint(K, (N,), generator=g)] * torch.randn(N, d, generator=g)
+    torch.manual_seed(7)
+    m = V.GaussianMixtureModel(K, d, isotropic=True)
+    m.initialize(X)
+    ref = O.gmm_new(K, d, isotropic=True)
+    O.load_state(ref, {"dist.mu": m.dist.mu.clone(), "dist.lambda_mu": m.dist.lambda_mu.clone(),
+                       "dist.gamma.alpha": m.dist.gamma.alpha.clone(), "dist.gamma.beta": m.dist.gamma.beta.clone(),
+                       "pi.alpha": m.pi.alpha.clone()})
+    O.to_dtype(ref, torch.float64)
+    m.to(DEV)
+    Xd, X64 = X.to(DEV), X.double()
+    for it in range(3):
+        _set(m, {k: v.float() for k, v in O.flatten_state(ref).items()})
+        m.update(Xd, 1)
+        tr = O.mixture_update(ref, X64, 1)
+        assert m.p.shape == (N, K)
+        assert abs(float(m.ELBO_last) - float(tr[0])) <= PARITY * abs(float(tr[0])), it
+        L = float(ref["log_p"].abs().max())
+        assert_maxabs(m.p.cpu().double(), ref["p"], max(2e-5, 4e-7 * L), f"p it{it} (|logit| {L:.1e})")
+        assert_close(m.NA, ref["NA"], PARITY, "NA")
+        flat = O.flatten_state(ref)
+        for k in NG_STATE:
+            assert_close(_get(m, k), flat[k], PARITY, f"{k} it{it}")
