@@ -677,3 +677,27 @@ def test_other_models_accept_an_empty_batch():
     for N in (0, 3):
         t.raw_update(torch.randn(N, 3, 1, device=DEV), torch.randn(N, 4, 1, device=DEV), iters=1)
         assert t.p.shape == (N, 8) and torch.isfinite(t.ELBO_last)
+
+
+@pytest.mark.parametrize("N,d,K", [(3000, 64, 16), (500, 3, 4)])
+@pytest.mark.parametrize("bad", [float("nan"), float("inf"), 3e38])
+def test_non_finite_rows_neither_hang_nor_poison_the_context(N, d, K, bad):
+    """A NaN / Inf / overflowing entry in the data: the reference's arithmetic turns the whole posterior into NaN.  Here the
+    call must return (the kernels' barrier waits are bounded, nothing may spin on a NaN), report it — NaN ELBO, the per-component
+    Cholesky status `info` set — and leave the CUDA context usable for the next model."""
+    g = torch.Generator().manual_seed(1)
+    X = torch.randn(N, d, generator=g)
+    X[7, min(3, d - 1)] = bad
+    torch.manual_seed(0)
+    m = V.GaussianMixtureModel(K, d)
+    m.dist.mu = X[100:100 + K].clone()
+    m.to(DEV)
+    m.update(X.to(DEV), 2)
+    torch.cuda.synchronize()
+    assert not bool(torch.isfinite(m.ELBO_last))
+    assert int((m.dist.invU.info != 0).sum()) > 0
+    # the next, clean model runs as if nothing had happened
+    torch.manual_seed(0)
+    c = V.GaussianMixtureModel(4, 3).to(DEV)
+    c.update(torch.randn(300, 3, generator=g).to(DEV), 2)
+    assert bool(torch.isfinite(c.ELBO_last)) and bool(torch.isfinite(c.p).all()) and int((c.dist.invU.info != 0).sum()) == 0
