@@ -597,6 +597,34 @@ def test_streamed_host_rows_match_device_rows():
     assert getattr(b, "_stream_state", {}).get("resident") is None          # the resident copy is dropped after the call
 
 
+@pytest.mark.parametrize("kind", ["pageable", "fp64", "strided", "lr"])
+def test_streamed_host_rows_in_other_forms(kind):
+    """Host rows that are not a pinned, contiguous fp32 tensor — pageable memory, fp64, a strided view — and a learning rate
+    below 1 on the streamed path: same results as the device-resident fp32 copy of the same rows (parameters to 2e-5; the
+    chunked Gram sums in another order)."""
+    N, K, d = 300_000, 32, 16
+    g = torch.Generator().manual_seed(19)
+    base = torch.randn(N, 2 * d, generator=g) * 1.3 + 0.4
+    Xc = base[:, ::2].contiguous()
+    Xh = {"pageable": Xc, "fp64": Xc.double(), "strided": base[:, ::2], "lr": Xc.pin_memory()}[kind]
+    lr = 0.5 if kind == "lr" else 1.0
+    ms = []
+    for X in (Xc.to(DEV), Xh):
+        torch.manual_seed(3)
+        m = V.GaussianMixtureModel(K, d)
+        m.initialize(Xc[:4096])
+        m.to(DEV)
+        m.update(X, 1, lr)
+        m.update(X, 2, lr)
+        ms.append(m)
+    a, o = ms
+    assert abs(float(a.ELBO_last) - float(o.ELBO_last)) <= 2e-6 * abs(float(a.ELBO_last))
+    assert_maxabs(o.p, a.p, 1e-4, "p")
+    assert bool((a.assignment() == o.assignment()).float().mean() > 0.9999)
+    for k in NIW_STATE:
+        assert_close(get(o, k), get(a, k), 2e-5, k)
+
+
 @pytest.mark.parametrize("d,K", [(3, 4), (64, 16)])
 @pytest.mark.parametrize("N", [0, 1, 5, 257, 300])
 def test_gmm_empty_and_tiny_inputs(N, d, K):
