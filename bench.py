@@ -393,7 +393,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rows-per-gpu", type=int, default=ROWS_PER_GPU)
     ap.add_argument("--ref-rows", type=int, default=512)
-    ap.add_argument("--cpu-baseline-iters", type=int, default=10)
+    ap.add_argument("--cpu-baseline-iters", type=int, default=40)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-secondary", action="store_true")
