@@ -63,7 +63,12 @@ class ClockSampler:
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        self.rows, self.proc, self.idx = [], None, gpu_index
+        self.rows, self.proc, self.idx, self.first = [], None, gpu_index, 0
+
+    def mark(self):
+        """The timed region starts here: only samples from now on count (the process is started earlier, during warm-up, because
+        nvidia-smi needs a few hundred ms before its first line)."""
+        self.first = len(self.rows)
 
     def start(self):
         try:
@@ -89,7 +94,10 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        rows, note = self.rows[self.first:], None
+        if not rows and self.rows:               # a timed region shorter than the sampling period
+            rows, note = self.rows[-1:], "no sample inside the timed region; the last one before it"
+        for r in rows:
             try:
                 sm.append(float(r[1])); mx.append(float(r[2]))
                 for nm, v in zip(names, r[5:9]):
@@ -98,8 +106,11 @@ class ClockSampler:
             except Exception:
                 pass
         sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        out = {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+               "reasons": sorted(reasons), "samples": len(sm)}
+        if note:
+            out["note"] = note
+        return out
 
 
 def measure_tf32_peak(device, seconds=1.5):
@@ -453,11 +464,12 @@ def main():
 
     # ---- warm-up, then K timed steps (device-resident inputs) ----------------------------------------
     sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()                          # streaming by the time the timed region begins
     for _ in range(args.warmup):
         m.update(X, 1)
     barrier()
-    if rank == 0:
-        sampler.start()
+    sampler.mark()
     ms, kern, launches = time_steps(lambda: m.update(X, 1), args.steps, 0, dev, barrier)
     clocks = sampler.stop() if rank == 0 else None
     ms = max_over_ranks(ms)
