@@ -128,3 +128,33 @@ def test_torch_custom_ops_are_registered_with_shape_inference():
         assert torch.ops.vbmp.wsum(torch.empty(100, 8), torch.empty(100, 64)).shape == (8, 64)
         mu, Sig = torch.ops.vbmp.moe_moments(torch.empty(100, 8, 16), torch.empty(100, 8), None)
         assert mu.shape == (100, 16) and Sig.shape == (100, 16, 16)
+
+
+def test_bench_clock_sampler_counts_only_the_timed_region():
+    """bench.py starts nvidia-smi during warm-up (it needs a few hundred ms before its first line) and must report only the
+    samples taken after mark(); with none inside a very short region it falls back to the last one before it and says so."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+
+    class FakeProc:
+        def terminate(self): pass
+        def wait(self, timeout=None): pass
+
+    def row(mhz, cap):
+        return ["0", str(mhz), "1965", "900.0", "0x4", "Not Active", "Not Active", "Not Active", "Active" if cap else "Not Active"]
+    s = bench.ClockSampler(0)
+    s.proc = FakeProc()
+    s.rows = [row(1965, False), row(1900, False)]           # warm-up
+    s.mark()
+    s.rows += [row(1500, True), row(1520, True), row(1540, True)]
+    out = s.stop()
+    assert out["samples"] == 3 and out["sm_mhz"] == 1520.0 and out["reasons"] == ["sw_power_cap"] and "note" not in out
+    s = bench.ClockSampler(0)
+    s.proc = FakeProc()
+    s.rows = [row(1965, False), row(1700, True)]
+    s.mark()
+    out = s.stop()
+    assert out["samples"] == 1 and out["sm_mhz"] == 1700.0 and "note" in out
